@@ -1,0 +1,11 @@
+"""gnn_fpga_b200: B200-native implementation of gnn-fpga's SegmentClassifier hot path.
+
+Public surface mirrors the reference modules gnn/model.py, gnn/graph.py:
+    SegmentClassifier, EdgeNetwork, NodeNetwork, MaskedLinear,
+    Graph, SparseGraph, make_sparse_graph, graph_from_sparse, save_graph(s), load_graph(s)
+plus the device batch (DeviceGraphBatch) that replaces the dense incidence tensors.
+"""
+from .graph import (Graph, SparseGraph, make_sparse_graph, graph_from_sparse, save_graph,  # noqa: F401
+                    save_graphs, load_graph, load_graphs, DeviceGraphBatch, pack_sparse_batch_host)
+from .model import MaskedLinear, EdgeNetwork, NodeNetwork, SegmentClassifier  # noqa: F401
+from ._lib import GnnsegError, LIB_PATH  # noqa: F401

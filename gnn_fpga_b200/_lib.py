@@ -1,0 +1,82 @@
+"""ctypes binding of libgnnseg_b200.so (the C ABI in include/gnnseg.h).
+
+There is no CPU fallback: if the shared library is missing, `lib()` raises, and every
+compute entry point of the package goes through `lib()`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgnnseg_b200.so")
+
+OK = 0
+ERRORS = {-1: "EINVAL", -2: "EUNSUPPORTED", -3: "EWORKSPACE", -4: "ECUDA", -5: "ENODEVICE"}
+BAD_VALUE = 1
+BAD_HYPEREDGE = 2
+
+_f32p = C.c_void_p
+_i32p = C.c_void_p
+
+
+class GnnsegParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "w_in", "b_in", "w_e1", "b_e1", "w_e2", "b_e2", "w_n1", "b_n1", "w_n2", "b_n2",
+        "m_e1", "m_e2", "m_n1", "m_n2")]
+
+
+class GnnsegGraph(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("n_slots", C.c_int32)] + [(n, C.c_void_p) for n in (
+        "src", "dst", "in_ptr", "in_eid", "in_nbr", "out_ptr", "out_eid", "out_nbr")]
+
+
+# name -> (restype, argtypes); must list every symbol include/gnnseg.h declares
+SIGNATURES = {
+    "gnnseg_abi_version": (C.c_int, []),
+    "gnnseg_strerror": (C.c_char_p, [C.c_int]),
+    "gnnseg_supported": (C.c_int, [C.c_int, C.c_int]),
+    "gnnseg_device_sm_count": (C.c_int, []),
+    "gnnseg_weights_floats": (C.c_size_t, [C.c_int, C.c_int]),
+    "gnnseg_pack_weights": (C.c_int, [C.POINTER(GnnsegParams), C.c_int, C.c_int, _f32p, C.c_void_p]),
+    "gnnseg_dense_to_edges": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, C.c_void_p]),
+    "gnnseg_csr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "gnnseg_build_csr": (C.c_int, [_i32p, _i32p, C.c_int, C.c_int, _i32p, _i32p, _i32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnnseg_forward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gnnseg_forward": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnnseg_input_step": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_void_p]),
+    "gnnseg_edge_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, _f32p, C.c_void_p]),
+    "gnnseg_node_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_void_p]),
+    "gnnseg_pack_sparse_batch_host": (C.c_int, [
+        C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+}
+
+_lib = None
+
+
+class GnnsegError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library once.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GnnsegError(
+                "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C gnn_fpga_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.gnnseg_abi_version() != 1:
+            raise GnnsegError("ABI version mismatch in %s" % LIB_PATH)
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != OK:
+        msg = lib().gnnseg_strerror(rc).decode()
+        raise GnnsegError("%s failed: %s (%s)" % (what, msg, ERRORS.get(rc, rc)))

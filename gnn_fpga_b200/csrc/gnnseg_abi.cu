@@ -1,0 +1,169 @@
+// extern "C" entry points declared in include/gnnseg.h.  Argument checking happens here, on
+// the host; the kernels live in gnnseg_forward.cu / gnnseg_graph.cu.
+#include "gnnseg_common.cuh"
+
+namespace gnnseg {
+int input_step(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
+int edge_step(const float*, const GnnsegGraph*, const float*, int, float*, cudaStream_t);
+int node_step(const float*, const GnnsegGraph*, const float*, const float*, int, float*, float*, cudaStream_t);
+int pack_weights(const GnnsegParams*, int, int, float*, cudaStream_t);
+int dense_to_edges(const float*, const float*, int, int, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
+size_t csr_workspace_bytes(int, int);
+int build_csr(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+}  // namespace gnnseg
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct FwdWorkspace {
+    float* hx[2];
+    float* p;
+    float* e;
+    size_t bytes;
+};
+
+// HX0 | HX1 | P | e, each 256-byte aligned.
+FwdWorkspace carve(void* ws, int n_nodes, int n_slots, int h) {
+    FwdWorkspace w;
+    const size_t hx_b = align_up((size_t)n_nodes * (h + 4) * 4, 256);
+    const size_t p_b = align_up((size_t)n_nodes * 2 * h * 4, 256);
+    const size_t e_b = align_up((size_t)n_slots * 4, 256);
+    char* base = static_cast<char*>(ws);
+    w.hx[0] = reinterpret_cast<float*>(base);
+    w.hx[1] = reinterpret_cast<float*>(base + hx_b);
+    w.p = reinterpret_cast<float*>(base + 2 * hx_b);
+    w.e = reinterpret_cast<float*>(base + 2 * hx_b + p_b);
+    w.bytes = 2 * hx_b + p_b + e_b;
+    return w;
+}
+
+inline bool graph_ok(const GnnsegGraph* g) {
+    if (!g || g->n_nodes < 0 || g->n_slots < 0) return false;
+    if (g->n_slots > 0 && (!g->src || !g->dst)) return false;
+    return true;
+}
+inline bool csr_ok(const GnnsegGraph* g) {
+    if (!graph_ok(g)) return false;
+    if (!g->in_ptr || !g->out_ptr) return false;
+    if (g->n_slots > 0 && (!g->in_eid || !g->in_nbr || !g->out_eid || !g->out_nbr)) return false;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gnnseg_abi_version(void) { return GNNSEG_ABI_VERSION; }
+
+const char* gnnseg_strerror(int code) {
+    switch (code) {
+        case GNNSEG_OK:           return "ok";
+        case GNNSEG_EINVAL:       return "invalid argument";
+        case GNNSEG_EUNSUPPORTED: return "unsupported (input_dim, hidden_dim): need input_dim in 1..4 and hidden_dim in {4,8,16,32,64}";
+        case GNNSEG_EWORKSPACE:   return "workspace too small";
+        case GNNSEG_ECUDA:        return "CUDA runtime error";
+        case GNNSEG_ENODEVICE:    return "no CUDA device";
+        default:                  return "unknown gnnseg error";
+    }
+}
+
+int gnnseg_supported(int F, int h) {
+    return (F >= 1 && F <= 4 && (h == 4 || h == 8 || h == 16 || h == 32 || h == 64)) ? 1 : 0;
+}
+
+int gnnseg_device_sm_count(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return GNNSEG_ENODEVICE;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return GNNSEG_ECUDA;
+    return n;
+}
+
+size_t gnnseg_weights_floats(int F, int h) {
+    return gnnseg_supported(F, h) ? (size_t)gnnseg::blob_total(h) : 0;
+}
+
+int gnnseg_pack_weights(const GnnsegParams* p, int F, int h, float* blob, void* stream) {
+    if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
+    if (!p || !blob || !p->w_in || !p->b_in || !p->w_e1 || !p->b_e1 || !p->w_e2 || !p->b_e2 ||
+        !p->w_n1 || !p->b_n1 || !p->w_n2 || !p->b_n2)
+        return GNNSEG_EINVAL;
+    return gnnseg::pack_weights(p, F, h, blob, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_dense_to_edges(const float* Ri, const float* Ro, int B, int N, int E, int32_t* src,
+                          int32_t* dst, int32_t* err_flag, void* stream) {
+    if (B < 0 || N < 0 || E < 0 || !err_flag) return GNNSEG_EINVAL;
+    if ((long long)B * N > 0x7fffffffLL || (long long)B * E > 0x7fffffffLL) return GNNSEG_EINVAL;
+    if ((long long)B * E > 0 && (!src || !dst)) return GNNSEG_EINVAL;
+    if ((long long)B * N * E > 0 && (!Ri || !Ro)) return GNNSEG_EINVAL;
+    return gnnseg::dense_to_edges(Ri, Ro, B, N, E, src, dst, err_flag, static_cast<cudaStream_t>(stream));
+}
+
+size_t gnnseg_csr_workspace_bytes(int n_nodes, int n_slots) {
+    if (n_nodes < 0 || n_slots < 0) return 0;
+    return gnnseg::csr_workspace_bytes(n_nodes, n_slots);
+}
+
+int gnnseg_build_csr(const int32_t* key, const int32_t* other, int n_slots, int n_nodes,
+                     int32_t* ptr, int32_t* eid, int32_t* nbr, void* ws, size_t ws_bytes,
+                     void* stream) {
+    if (n_slots < 0 || n_nodes < 0 || !ptr || !ws) return GNNSEG_EINVAL;
+    if (n_slots > 0 && (!key || !other || !eid || !nbr)) return GNNSEG_EINVAL;
+    return gnnseg::build_csr(key, other, n_slots, n_nodes, ptr, eid, nbr, ws, ws_bytes,
+                             static_cast<cudaStream_t>(stream));
+}
+
+size_t gnnseg_forward_workspace_bytes(int n_nodes, int n_slots, int F, int h) {
+    if (!gnnseg_supported(F, h) || n_nodes < 0 || n_slots < 0) return 0;
+    return carve(nullptr, n_nodes, n_slots, h).bytes + 256;
+}
+
+int gnnseg_input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* HX,
+                      float* P, void* stream) {
+    if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || n_nodes < 0 || (n_nodes > 0 && (!X || !HX || !P))) return GNNSEG_EINVAL;
+    return gnnseg::input_step(blob, X, n_nodes, F, h, HX, P, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_edge_step(const float* blob, const GnnsegGraph* g, const float* P, int h, float* e,
+                     void* stream) {
+    if (!gnnseg_supported(1, h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || !graph_ok(g) || (g->n_slots > 0 && !e) || (g->n_nodes > 0 && !P)) return GNNSEG_EINVAL;
+    return gnnseg::edge_step(blob, g, P, h, e, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_node_step(const float* blob, const GnnsegGraph* g, const float* HX_in, const float* e,
+                     int h, float* HX_out, float* P_out, void* stream) {
+    if (!gnnseg_supported(1, h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || !csr_ok(g)) return GNNSEG_EINVAL;
+    if (g->n_nodes > 0 && (!HX_in || !HX_out || !P_out)) return GNNSEG_EINVAL;
+    if (g->n_slots > 0 && !e) return GNNSEG_EINVAL;
+    return gnnseg::node_step(blob, g, HX_in, e, h, HX_out, P_out, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int F, int h,
+                   int n_iters, float* scores, void* ws, size_t ws_bytes, void* stream) {
+    if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || !csr_ok(g) || n_iters < 0 || !ws) return GNNSEG_EINVAL;
+    if (g->n_nodes > 0 && !X) return GNNSEG_EINVAL;
+    if (g->n_slots > 0 && !scores) return GNNSEG_EINVAL;
+    // 256-byte align the caller's pointer ourselves
+    const uintptr_t raw = reinterpret_cast<uintptr_t>(ws);
+    const uintptr_t al = (raw + 255) & ~uintptr_t(255);
+    const FwdWorkspace w = carve(reinterpret_cast<void*>(al), g->n_nodes, g->n_slots, h);
+    if (ws_bytes < w.bytes + (al - raw)) return GNNSEG_EWORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    int rc = gnnseg::input_step(blob, X, g->n_nodes, F, h, w.hx[0], w.p, st);
+    int cur = 0;
+    for (int it = 0; it < n_iters && rc == GNNSEG_OK; ++it) {
+        rc = gnnseg::edge_step(blob, g, w.p, h, w.e, st);
+        if (rc == GNNSEG_OK) rc = gnnseg::node_step(blob, g, w.hx[cur], w.e, h, w.hx[cur ^ 1], w.p, st);
+        cur ^= 1;
+    }
+    if (rc == GNNSEG_OK) rc = gnnseg::edge_step(blob, g, w.p, h, scores, st);
+    return rc;
+}
+
+}  // extern "C"

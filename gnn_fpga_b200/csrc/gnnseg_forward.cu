@@ -1,0 +1,462 @@
+// Forward kernels of the segment classifier for sm_100a: weight packing, input step,
+// edge step, node step.  The math follows gnn/model.py:140-156 of the reference with the
+// dense incidence bmm replaced by int32 gathers and an ordered CSR segment sum:
+//
+//   edge step (gnn/model.py:69-81)   e_j = sigmoid(W2 . tanh(W1 . [HX[src_j]; HX[dst_j]] + b1) + b2)
+//     computed "projection first": W1.[a;b] = W1a.a + W1b.b, and P[n] = [W1a.HX[n]+b1 | W1b.HX[n]]
+//     is produced once per node by the kernel that wrote HX[n]; the edge kernel gathers two
+//     h-wide rows of P with 16-byte loads, adds, tanh, dots with W2, sigmoid.
+//   node step (gnn/model.py:113-125) mi[n] = sum_{dst_j = n} e_j HX[src_j]  (ascending j)
+//                                    mo[n] = sum_{src_j = n} e_j HX[dst_j]  (ascending j)
+//                                    H'[n] = tanh(W4 . tanh(W3 . [mi; mo; HX[n]] + b3) + b4)
+//     one persistent CTA per tile of nodes: sub-warp groups walk the two CSR rows (no
+//     atomics, fixed order), the tile's [mi|mo|self] rows are staged in shared memory, and
+//     the two layers + the next step's projection run as register-tiled fp32 GEMMs against
+//     weights resident in shared memory.  HX' = [H' | X] is written back (the reference's
+//     cat([H, X]), gnn/model.py:146,154) together with P'.
+#include "gnnseg_common.cuh"
+
+namespace gnnseg {
+
+// ------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(GnnsegParams p, int F, int H, float* __restrict__ blob) {
+    const int D = F + H, D4 = H + 4;
+    const int o_bin = 4 * H, o_w1 = o_bin + H, o_b1 = o_w1 + D4 * 2 * H, o_w2 = o_b1 + H,
+              o_b2 = o_w2 + H, o_w3 = o_b2 + 4, o_b3 = o_w3 + 3 * D4 * H, o_w4 = o_b3 + H,
+              o_b4 = o_w4 + H * H, total = o_b4 + H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (i < o_bin) {                       // Win^T [4][H]
+            const int f = i / H, j = i % H;
+            if (f < F) v = p.w_in[j * F + f];
+        } else if (i < o_w1) {
+            v = p.b_in[i - o_bin];
+        } else if (i < o_b1) {                 // W1^T [D4][2H]
+            const int r = i - o_w1, k = r / (2 * H), c = r % (2 * H), part = c / H, j = c % H;
+            if (k < D) {
+                const int idx = j * (2 * D) + part * D + k;
+                v = p.w_e1[idx];
+                if (p.m_e1) v *= p.m_e1[idx];
+            }
+        } else if (i < o_w2) {
+            v = p.b_e1[i - o_b1];
+        } else if (i < o_b2) {
+            const int j = i - o_w2;
+            v = p.w_e2[j];
+            if (p.m_e2) v *= p.m_e2[j];
+        } else if (i < o_w3) {
+            if (i == o_b2) v = p.b_e2[0];
+        } else if (i < o_b3) {                 // W3^T [3*D4][H]
+            const int r = i - o_w3, row = r / H, j = r % H, part = row / D4, k = row % D4;
+            if (k < D) {
+                const int idx = j * (3 * D) + part * D + k;
+                v = p.w_n1[idx];
+                if (p.m_n1) v *= p.m_n1[idx];
+            }
+        } else if (i < o_w4) {
+            v = p.b_n1[i - o_b3];
+        } else if (i < o_b4) {                 // W4^T [H][H]
+            const int r = i - o_w4, k = r / H, j = r % H;
+            const int idx = j * H + k;
+            v = p.w_n2[idx];
+            if (p.m_n2) v *= p.m_n2[idx];
+        } else {
+            v = p.b_n2[i - o_b4];
+        }
+        blob[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// register-tiled shared-memory GEMM:  out[node][o] = sum_k A[node][k] * W[k][o]
+// A: [TN][lda] fp32 in shared memory, W: [K][HOUT] fp32 in shared memory.
+// A thread owns RN nodes (ng, ng+NG, ...) x 4 consecutive outputs.  Lanes run over the
+// output groups first, so W reads are contiguous and the (few) distinct A rows of a warp
+// are consecutive rows, which tile_stride() keeps on distinct banks.
+// ------------------------------------------------------------------------------------
+template <int K, int HOUT, int TN, int NT, int RN, typename Epi>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, const int lda,
+                                          const float* __restrict__ sW, Epi epi) {
+    constexpr int OG = HOUT / 4, NG = TN / RN, TILES = OG * NG;
+    static_assert(K % 4 == 0 && HOUT % 4 == 0 && TN % RN == 0, "tile shape");
+    for (int t = threadIdx.x; t < TILES; t += NT) {
+        const int og = t % OG, ng = t / OG;
+        float acc[RN][4];
+#pragma unroll
+        for (int i = 0; i < RN; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        const float* a0 = sA + ng * lda;
+        const float* w0 = sW + og * 4;
+#pragma unroll 2
+        for (int k = 0; k < K; k += 4) {
+            float4 a[RN];
+#pragma unroll
+            for (int i = 0; i < RN; ++i) a[i] = lds4(a0 + i * NG * lda + k);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 w = lds4(w0 + (k + kk) * HOUT);
+#pragma unroll
+                for (int i = 0; i < RN; ++i) {
+                    const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                    acc[i][0] = fmaf(av, w.x, acc[i][0]);
+                    acc[i][1] = fmaf(av, w.y, acc[i][1]);
+                    acc[i][2] = fmaf(av, w.z, acc[i][2]);
+                    acc[i][3] = fmaf(av, w.w, acc[i][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RN; ++i) epi(ng + i * NG, og * 4, acc[i]);
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void copy_to_smem(float* __restrict__ dst, const float* __restrict__ src, int n_floats) {
+    for (int i = threadIdx.x * 4; i < n_floats; i += NT * 4) st4(dst + i, ldg4(src + i));
+}
+
+// Kernel shape per hidden size.
+template <int H>
+struct NodeCfg {
+    static constexpr int TN  = 64;                 // nodes per tile
+    static constexpr int NT  = 256;                // threads per CTA
+    static constexpr int RN1 = (H >= 64) ? 4 : 2;  // nodes per thread, layers with H outputs
+    static constexpr int RNP = 4;                  // nodes per thread, projection (2H outputs)
+    static constexpr int D4  = H + 4;
+    static constexpr int K1  = 3 * D4;
+    static constexpr int SM  = tile_stride(K1);    // [mi|mo|self] tile stride
+    static constexpr int SH  = tile_stride(H);     // hidden-layer tile stride
+    static constexpr int SD  = tile_stride(D4);    // HX tile stride
+    static constexpr int W_FLOATS = K1 * H + H * H + D4 * 2 * H + 3 * H;
+    static constexpr int SMEM_FLOATS = W_FLOATS + TN * (SM + SH + SD);
+    static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
+};
+
+template <int H>
+struct InputCfg {
+    static constexpr int TN = 64, NT = 256, RNP = 4;
+    static constexpr int D4 = H + 4;
+    static constexpr int SD = tile_stride(D4);
+    static constexpr int SMEM_FLOATS = 4 * H + H + D4 * 2 * H + H + TN * SD + TN * 4;
+    static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
+};
+
+// Write the tile's HX rows and its projection P = [W1a.HX+b1 | W1b.HX] to global memory.
+template <int H, int TN, int NT, int RNP>
+__device__ __forceinline__ void store_hx_and_project(const float* __restrict__ sHX, const int sd,
+                                                     const float* __restrict__ sW1,
+                                                     const float* __restrict__ sB1,
+                                                     const int node0, const int n_nodes,
+                                                     float* __restrict__ HX_out,
+                                                     float* __restrict__ P_out) {
+    constexpr int D4 = H + 4, C4 = D4 / 4;
+    for (int i = threadIdx.x; i < TN * C4; i += NT) {
+        const int ln = i / C4, c = i % C4, n = node0 + ln;
+        if (n < n_nodes) st4(HX_out + (size_t)n * D4 + 4 * c, lds4(sHX + ln * sd + 4 * c));
+    }
+    tile_gemm<D4, 2 * H, TN, NT, RNP>(sHX, sd, sW1, [&](int ln, int o, const float (&acc)[4]) {
+        const int n = node0 + ln;
+        if (n < n_nodes) {
+            float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            if (o < H) {
+                const float4 b = lds4(sB1 + o);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            st4(P_out + (size_t)n * 2 * H + o, v);
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------
+// input step: H0 = tanh(Win.X + bin), HX = [H0 | X], P = projection   (gnn/model.py:144-146)
+// ------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(InputCfg<H>::NT)
+input_kernel(const float* __restrict__ blob, const float* __restrict__ X, const int F,
+             const int n_nodes, const int n_tiles, float* __restrict__ HX_out,
+             float* __restrict__ P_out) {
+    using C = InputCfg<H>;
+    using B = Blob<H>;
+    constexpr int TN = C::TN, NT = C::NT, D4 = C::D4, SD = C::SD;
+    extern __shared__ __align__(16) float smem[];
+    float* sWin = smem;                 // [4][H]
+    float* sBin = sWin + 4 * H;         // [H]
+    float* sW1  = sBin + H;             // [D4][2H]
+    float* sB1  = sW1 + D4 * 2 * H;     // [H]
+    float* sHX  = sB1 + H;              // [TN][SD]
+    float* sX   = sHX + TN * SD;        // [TN][4]
+    copy_to_smem<NT>(sWin, blob + B::WIN, 4 * H + H);
+    copy_to_smem<NT>(sW1, blob + B::W1, D4 * 2 * H + H);
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int node0 = tile * TN;
+        __syncthreads();   // weights visible (first pass) / previous tile's readers done
+        for (int i = threadIdx.x; i < TN * 4; i += NT) {
+            const int ln = i >> 2, f = i & 3, n = node0 + ln;
+            sX[i] = (n < n_nodes && f < F) ? __ldg(X + (size_t)n * F + f) : 0.f;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < TN * (H / 4 + 1); i += NT) {
+            const int ln = i / (H / 4 + 1), c = i % (H / 4 + 1);
+            const float4 x = lds4(sX + ln * 4);
+            float4 v;
+            if (c < H / 4) {
+                v = lds4(sBin + 4 * c);
+                fma4(v, x.x, lds4(sWin + 0 * H + 4 * c));
+                fma4(v, x.y, lds4(sWin + 1 * H + 4 * c));
+                fma4(v, x.z, lds4(sWin + 2 * H + 4 * c));
+                fma4(v, x.w, lds4(sWin + 3 * H + 4 * c));
+                v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
+            } else {
+                v = x;
+            }
+            st4(sHX + ln * SD + 4 * c, v);
+        }
+        __syncthreads();
+        store_hx_and_project<H, TN, NT, C::RNP>(sHX, SD, sW1, sB1, node0, n_nodes, HX_out, P_out);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// edge step
+// ------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(256)
+edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
+            const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+            const int n_slots, float* __restrict__ e_out) {
+    using B = Blob<H>;
+    constexpr int G = H / 4;        // lanes that share one edge (one float4 of P each)
+    constexpr int EPP = 32 / G;     // edges a warp handles per pass
+    const int lane = threadIdx.x & 31;
+    const int c = lane % G, g = lane / G;
+    const float4 w2 = ldg4(blob + B::W2 + 4 * c);
+    const float4 b1 = ldg4(blob + B::B1 + 4 * c);
+    const float b2 = __ldg(blob + B::B2);
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+
+    for (int base = warp * 32; base < n_slots; base += n_warps * 32) {
+        const int j = base + lane;
+        int s = -1, d = -1;
+        if (j < n_slots) { s = __ldg(src + j); d = __ldg(dst + j); }
+        float mine = 0.f;
+#pragma unroll (G > 8 ? 8 : G)
+        for (int p = 0; p < G; ++p) {
+            const int k = p * EPP + g;                       // which of the warp's 32 edges
+            const int ss = __shfl_sync(0xffffffffu, s, k);
+            const int dd = __shfl_sync(0xffffffffu, d, k);
+            float4 a = b1;                                   // absent start: W1a.0 + b1
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);      // absent end:   W1b.0
+            if (ss >= 0) a = ldg4(P + (size_t)ss * (2 * H) + 4 * c);
+            if (dd >= 0) b = ldg4(P + (size_t)dd * (2 * H) + H + 4 * c);
+            float z = w2.x * tanhf(a.x + b.x);
+            z = fmaf(w2.y, tanhf(a.y + b.y), z);
+            z = fmaf(w2.z, tanhf(a.z + b.z), z);
+            z = fmaf(w2.w, tanhf(a.w + b.w), z);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+            const float v = __shfl_sync(0xffffffffu, z, (lane % EPP) * G);
+            if (lane / EPP == p) mine = v;
+        }
+        if (j < n_slots) e_out[j] = 1.f / (1.f + expf(-(mine + b2)));
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// node step
+// ------------------------------------------------------------------------------------
+// One CSR row: acc += e[eid[s]] * HX[nbr[s]] for s ascending.  Lane c of the node's group
+// owns float4 chunk c of the hidden part; lane 0 also owns the X chunk.
+template <int H>
+__device__ __forceinline__ void csr_row_sum(const int32_t* __restrict__ ptr,
+                                            const int32_t* __restrict__ eid,
+                                            const int32_t* __restrict__ nbr,
+                                            const float* __restrict__ e,
+                                            const float* __restrict__ HX, const int n,
+                                            const int c, float4& acc_h, float4& acc_x) {
+    constexpr int D4 = H + 4;
+    const int beg = __ldg(ptr + n), end = __ldg(ptr + n + 1);
+#pragma unroll 4
+    for (int s = beg; s < end; ++s) {
+        const int nb = __ldg(nbr + s);
+        const float w = __ldg(e + __ldg(eid + s));
+        if (nb >= 0) {   // a half edge (absent other end) gathers the zero row
+            const float* row = HX + (size_t)nb * D4;
+            fma4(acc_h, w, ldg4(row + 4 * c));
+            if (c == 0) fma4(acc_x, w, ldg4(row + H));
+        }
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(NodeCfg<H>::NT)
+node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
+            const float* __restrict__ HX_in, const float* __restrict__ e, const int n_tiles,
+            float* __restrict__ HX_out, float* __restrict__ P_out) {
+    using C = NodeCfg<H>;
+    using B = Blob<H>;
+    constexpr int TN = C::TN, NT = C::NT, D4 = C::D4, K1 = C::K1;
+    constexpr int SM = C::SM, SH = C::SH, SD = C::SD;
+    constexpr int G = H / 4;            // lanes per node in the gather phase
+    constexpr int NGRP = NT / G;        // node groups per CTA
+    extern __shared__ __align__(16) float smem[];
+    float* sW3 = smem;                  // [K1][H]
+    float* sB3 = sW3 + K1 * H;          // [H]
+    float* sW4 = sB3 + H;               // [H][H]
+    float* sB4 = sW4 + H * H;           // [H]
+    float* sW1 = sB4 + H;               // [D4][2H]
+    float* sB1 = sW1 + D4 * 2 * H;      // [H]
+    float* sM  = sB1 + H;               // [TN][SM]   [mi | mo | self]
+    float* sH1 = sM + TN * SM;          // [TN][SH]
+    float* sHX = sH1 + TN * SH;         // [TN][SD]
+    copy_to_smem<NT>(sW3, blob + B::W3, K1 * H + H + H * H + H);   // W3,b3,W4,b4 contiguous
+    copy_to_smem<NT>(sW1, blob + B::W1, D4 * 2 * H + H);           // W1,b1 contiguous
+
+    const int grp = threadIdx.x / G, c = threadIdx.x % G;
+    const int n_nodes = g.n_nodes;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int node0 = tile * TN;
+        // ---- gather: [mi | mo | self] rows of the tile -------------------------------
+        for (int ln = grp; ln < TN; ln += NGRP) {
+            const int n = node0 + ln;
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 mi_h = zero, mi_x = zero, mo_h = zero, mo_x = zero, se_h = zero, se_x = zero;
+            if (n < n_nodes) {
+                csr_row_sum<H>(g.in_ptr, g.in_eid, g.in_nbr, e, HX_in, n, c, mi_h, mi_x);
+                csr_row_sum<H>(g.out_ptr, g.out_eid, g.out_nbr, e, HX_in, n, c, mo_h, mo_x);
+                const float* row = HX_in + (size_t)n * D4;
+                se_h = ldg4(row + 4 * c);
+                if (c == 0) se_x = ldg4(row + H);
+            }
+            float* m = sM + ln * SM;
+            st4(m + 4 * c, mi_h);
+            st4(m + D4 + 4 * c, mo_h);
+            st4(m + 2 * D4 + 4 * c, se_h);
+            if (c == 0) {
+                st4(m + H, mi_x);
+                st4(m + D4 + H, mo_x);
+                st4(m + 2 * D4 + H, se_x);
+            }
+        }
+        __syncthreads();
+        // ---- layer 0: h1 = tanh(W3 . [mi; mo; self] + b3) ------------------------------
+        tile_gemm<K1, H, TN, NT, C::RN1>(sM, SM, sW3, [&](int ln, int o, const float (&acc)[4]) {
+            const float4 b = lds4(sB3 + o);
+            st4(sH1 + ln * SH + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
+                                               tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
+        });
+        // the X part of the new HX row is the old one (self block of sM)
+        for (int i = threadIdx.x; i < TN; i += NT) st4(sHX + i * SD + H, lds4(sM + i * SM + 2 * D4 + H));
+        __syncthreads();
+        // ---- layer 2: H' = tanh(W4 . h1 + b4) ------------------------------------------
+        tile_gemm<H, H, TN, NT, C::RN1>(sH1, SH, sW4, [&](int ln, int o, const float (&acc)[4]) {
+            const float4 b = lds4(sB4 + o);
+            st4(sHX + ln * SD + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
+                                               tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
+        });
+        __syncthreads();
+        // ---- write HX' and the projection for the next edge step ------------------------
+        store_hx_and_project<H, TN, NT, C::RNP>(sHX, SD, sW1, sB1, node0, n_nodes, HX_out, P_out);
+        // next tile's gather only writes sM (last read before the layer-0 barrier), its
+        // later phases are fenced by its own barriers.
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------
+static inline int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return n;
+}
+
+template <typename Kern>
+static inline int persistent_grid(Kern kern, int threads, size_t smem, int n_tiles, int* grid) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return GNNSEG_ECUDA;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1)
+        return GNNSEG_ECUDA;
+    const int sms = sm_count();
+    if (sms < 1) return GNNSEG_ENODEVICE;
+    const int cap = sms * occ;
+    *grid = n_tiles < cap ? n_tiles : cap;
+    return GNNSEG_OK;
+}
+
+static inline int check_launch() {
+    return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+}
+
+template <int H>
+static int launch_input(const float* blob, const float* X, int n_nodes, int F, float* HX, float* P,
+                        cudaStream_t st) {
+    using C = InputCfg<H>;
+    if (n_nodes == 0) return GNNSEG_OK;
+    const int n_tiles = (n_nodes + C::TN - 1) / C::TN;
+    int grid = 0;
+    const int rc = persistent_grid(input_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);
+    if (rc) return rc;
+    input_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, HX, P);
+    return check_launch();
+}
+
+template <int H>
+static int launch_edge(const float* blob, const GnnsegGraph* g, const float* P, float* e, cudaStream_t st) {
+    if (g->n_slots == 0) return GNNSEG_OK;
+    const int sms = sm_count();
+    if (sms < 1) return GNNSEG_ENODEVICE;
+    const int warps_needed = (g->n_slots + 31) / 32;
+    int grid = (warps_needed + 7) / 8;
+    const int cap = sms * 8;   // 8 CTAs of 256 threads per SM
+    if (grid > cap) grid = cap;
+    edge_kernel<H><<<grid, 256, 0, st>>>(blob, P, g->src, g->dst, g->n_slots, e);
+    return check_launch();
+}
+
+template <int H>
+static int launch_node(const float* blob, const GnnsegGraph* g, const float* HX_in, const float* e,
+                       float* HX_out, float* P_out, cudaStream_t st) {
+    using C = NodeCfg<H>;
+    if (g->n_nodes == 0) return GNNSEG_OK;
+    const int n_tiles = (g->n_nodes + C::TN - 1) / C::TN;
+    int grid = 0;
+    const int rc = persistent_grid(node_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);
+    if (rc) return rc;
+    node_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, HX_in, e, n_tiles, HX_out, P_out);
+    return check_launch();
+}
+
+#define GNNSEG_DISPATCH_H(h, CALL)                 \
+    switch (h) {                                   \
+        case 4:  { constexpr int HH = 4;  return CALL; } \
+        case 8:  { constexpr int HH = 8;  return CALL; } \
+        case 16: { constexpr int HH = 16; return CALL; } \
+        case 32: { constexpr int HH = 32; return CALL; } \
+        case 64: { constexpr int HH = 64; return CALL; } \
+        default: return GNNSEG_EUNSUPPORTED;       \
+    }
+
+int input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* HX, float* P,
+               cudaStream_t st) {
+    GNNSEG_DISPATCH_H(h, launch_input<HH>(blob, X, n_nodes, F, HX, P, st));
+}
+int edge_step(const float* blob, const GnnsegGraph* g, const float* P, int h, float* e, cudaStream_t st) {
+    GNNSEG_DISPATCH_H(h, launch_edge<HH>(blob, g, P, e, st));
+}
+int node_step(const float* blob, const GnnsegGraph* g, const float* HX_in, const float* e, int h,
+              float* HX_out, float* P_out, cudaStream_t st) {
+    GNNSEG_DISPATCH_H(h, launch_node<HH>(blob, g, HX_in, e, HX_out, P_out, st));
+}
+int pack_weights(const GnnsegParams* p, int F, int h, float* blob, cudaStream_t st) {
+    const int total = blob_total(h);
+    pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(*p, F, h, blob);
+    return check_launch();
+}
+
+}  // namespace gnnseg

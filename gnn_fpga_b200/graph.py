@@ -1,0 +1,245 @@
+"""Graph tuples and the device batch.
+
+Host side: the reference's graph.py surface (gnn/graph.py:18-35,179-194) with the same
+names, field order, dtypes and NPZ keys, so files and tuples are interchangeable.
+
+Device side: `DeviceGraphBatch`, the flattened block-diagonal batch the CUDA path works on
+(include/gnnseg.h, GnnsegGraph).  It is built either from the dense (X, Ri, Ro) tensors the
+reference's batch_generator yields (gnn/trainSegmentClassifier.py:97-111) or straight from a
+list of SparseGraph tuples without ever densifying.
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# gnn/graph.py:18-21
+Graph = namedtuple("Graph", ["X", "Ri", "Ro", "y"])
+SparseGraph = namedtuple("SparseGraph", ["X", "Ri_rows", "Ri_cols", "Ro_rows", "Ro_cols", "y"])
+
+
+def make_sparse_graph(X, Ri, Ro, y):
+    """Dense incidence matrices -> index tuples, in np.nonzero (row-major) order
+    (gnn/graph.py:23-26).  That order is destination-CSR for Ri and source-CSR for Ro."""
+    in_rows, in_cols = np.nonzero(Ri)
+    out_rows, out_cols = np.nonzero(Ro)
+    return SparseGraph(X, in_rows, in_cols, out_rows, out_cols, y)
+
+
+def graph_from_sparse(sparse_graph, dtype=np.uint8):
+    """Index tuples -> dense (N, E) incidence matrices (gnn/graph.py:28-35).  The edge count
+    is len(Ri_rows), as in the reference.  Host-only helper for small graphs: the device path
+    never calls it."""
+    n_nodes = sparse_graph.X.shape[0]
+    n_edges = sparse_graph.Ri_rows.shape[0]
+    dense = [np.zeros((n_nodes, n_edges), dtype=dtype) for _ in range(2)]
+    dense[0][sparse_graph.Ri_rows, sparse_graph.Ri_cols] = 1
+    dense[1][sparse_graph.Ro_rows, sparse_graph.Ro_cols] = 1
+    return Graph(sparse_graph.X, dense[0], dense[1], sparse_graph.y)
+
+
+def save_graph(graph, filename):
+    """NPZ with the six SparseGraph keys.  Like the reference (gnn/graph.py:179-181) this
+    accepts the `(SparseGraph, segments)` pair construct_graph returns; a bare SparseGraph
+    is accepted too."""
+    sg = graph if isinstance(graph, SparseGraph) else graph[0]
+    np.savez(filename, **sg._asdict())
+
+
+def save_graphs(graphs, filenames):
+    for graph, filename in zip(graphs, filenames):
+        save_graph(graph, filename)
+
+
+def load_graph(filename, graph_type=Graph):
+    """gnn/graph.py:188-191."""
+    with np.load(filename) as f:
+        return graph_type(**{k: f[k] for k in f.files})
+
+
+def load_graphs(filenames, graph_type=Graph):
+    return [load_graph(f, graph_type) for f in filenames]
+
+
+# ---------------------------------------------------------------------------------------
+# device batch
+# ---------------------------------------------------------------------------------------
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(0)
+
+
+def _require_cuda(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.GnnsegError("gnn_fpga_b200 computes on CUDA devices only (got %s); there is no CPU path" % device)
+    return device
+
+
+class DeviceGraphBatch:
+    """A batch of B graphs flattened into one block-diagonal graph on the GPU.
+
+    n_nodes nodes in total; edge slot b*e_max + j is column j of event b in the padded
+    (B, e_max) layout of merge_graphs (gnn/trainSegmentClassifier.py:66-95).  Slots that
+    are padding carry src = dst = -1.
+    """
+
+    def __init__(self, X, src, dst, B, e_max, n_nodes_per_event=None):
+        dev = _require_cuda(X.device)
+        assert X.dtype == torch.float32 and X.dim() == 2 and X.is_contiguous()
+        assert src.dtype == torch.int32 and dst.dtype == torch.int32
+        self.device = dev
+        self.X = X
+        self.src, self.dst = src, dst
+        self.B, self.e_max = int(B), int(e_max)
+        self.n_nodes = int(X.shape[0])
+        self.n_slots = int(src.numel())
+        assert self.n_slots == self.B * self.e_max and dst.numel() == self.n_slots
+        self.F = int(X.shape[1])
+        self.n_nodes_per_event = n_nodes_per_event
+        self.n_real_edges = None       # filled lazily (needs a device->host read)
+        self._build_csr()
+        self._ws = {}
+        self._graphs = {}
+        self.scores = torch.empty(self.n_slots, dtype=torch.float32, device=dev)
+
+    # -- construction ------------------------------------------------------------------
+    def _build_csr(self):
+        L = _lib.lib()
+        dev, n, m = self.device, self.n_nodes, self.n_slots
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.in_ptr = torch.empty(n + 1, **i32)
+        self.out_ptr = torch.empty(n + 1, **i32)
+        self.in_eid, self.in_nbr = torch.empty(m, **i32), torch.empty(m, **i32)
+        self.out_eid, self.out_nbr = torch.empty(m, **i32), torch.empty(m, **i32)
+        ws_bytes = L.gnnseg_csr_workspace_bytes(n, m)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            _lib.check(L.gnnseg_build_csr(_ptr(self.dst), _ptr(self.src), m, n, _ptr(self.in_ptr),
+                                          _ptr(self.in_eid), _ptr(self.in_nbr), _ptr(ws), ws_bytes, st),
+                       "gnnseg_build_csr(dst)")
+            _lib.check(L.gnnseg_build_csr(_ptr(self.src), _ptr(self.dst), m, n, _ptr(self.out_ptr),
+                                          _ptr(self.out_eid), _ptr(self.out_nbr), _ptr(ws), ws_bytes, st),
+                       "gnnseg_build_csr(src)")
+        self._csr_ws = ws   # keep alive until the stream has consumed it
+        self.struct = _lib.GnnsegGraph(
+            n, m, self.src.data_ptr(), self.dst.data_ptr(),
+            self.in_ptr.data_ptr(), self.in_eid.data_ptr(), self.in_nbr.data_ptr(),
+            self.out_ptr.data_ptr(), self.out_eid.data_ptr(), self.out_nbr.data_ptr())
+
+    @classmethod
+    def from_dense(cls, X, Ri, Ro, validate=True):
+        """X (B,N,F), Ri/Ro (B,N,E) fp32 CUDA tensors, as the reference's model receives them
+        (gnn/model.py:142).  Raises ValueError for entries other than 0/1 or a column with
+        more than one non-zero (the dense bmm would sum rows there; not a graph)."""
+        dev = _require_cuda(X.device)
+        if Ri.device != X.device or Ro.device != X.device:
+            raise ValueError("X, Ri, Ro must live on the same device")
+        if X.dim() != 3 or Ri.dim() != 3 or Ro.dim() != 3:
+            raise ValueError("expected X (B,N,F), Ri (B,N,E), Ro (B,N,E)")
+        B, N, F = X.shape
+        E = Ri.shape[2]
+        if tuple(Ri.shape) != (B, N, E) or tuple(Ro.shape) != (B, N, E):
+            raise ValueError("Ri %s / Ro %s do not match X %s" % (tuple(Ri.shape), tuple(Ro.shape), tuple(X.shape)))
+        X = X.to(torch.float32).contiguous()
+        Ri = Ri.to(torch.float32).contiguous()
+        Ro = Ro.to(torch.float32).contiguous()
+        L = _lib.lib()
+        src = torch.empty(B * E, dtype=torch.int32, device=dev)
+        dst = torch.empty(B * E, dtype=torch.int32, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.gnnseg_dense_to_edges(_ptr(Ri), _ptr(Ro), B, N, E, _ptr(src), _ptr(dst),
+                                               _ptr(err), _stream_ptr(dev)), "gnnseg_dense_to_edges")
+        if validate:
+            flag = int(err.item())
+            if flag & _lib.BAD_VALUE:
+                raise ValueError("Ri/Ro must contain only 0 and 1")
+            if flag & _lib.BAD_HYPEREDGE:
+                raise ValueError("a column of Ri or Ro has more than one non-zero entry")
+        return cls(X.reshape(B * N, F), src, dst, B, E, n_nodes_per_event=[N] * B)
+
+    @classmethod
+    def from_sparse_graphs(cls, graphs, device="cuda", pinned=None, n_threads=0):
+        """List of host SparseGraph tuples -> device batch, padded exactly as
+        graph_from_sparse + merge_graphs would pad it (e_max = max len(Ri_rows); node rows
+        are NOT padded because padded nodes influence no score)."""
+        dev = _require_cuda(device)
+        host = pack_sparse_batch_host(graphs, pinned=pinned, n_threads=n_threads)
+        X = host["X"].to(dev, non_blocking=True)
+        src = host["src"].to(dev, non_blocking=True)
+        dst = host["dst"].to(dev, non_blocking=True)
+        return cls(X, src, dst, len(graphs), host["e_max"], n_nodes_per_event=host["n_nodes"])
+
+    # -- helpers -------------------------------------------------------------------------
+    def workspace(self, h):
+        L = _lib.lib()
+        if h not in self._ws:
+            nbytes = L.gnnseg_forward_workspace_bytes(self.n_nodes, self.n_slots, self.F, h)
+            if nbytes == 0:
+                _lib.check(-2, "gnnseg_forward_workspace_bytes(F=%d, h=%d)" % (self.F, h))
+            self._ws[h] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws[h]
+
+    def count_real_edges(self):
+        if self.n_real_edges is None:
+            self.n_real_edges = int(((self.src >= 0) & (self.dst >= 0)).sum().item())
+        return self.n_real_edges
+
+    def scores_2d(self):
+        return self.scores.view(self.B, self.e_max)
+
+
+def pack_sparse_batch_host(graphs, pinned=None, n_threads=0):
+    """Run gnnseg_pack_sparse_batch_host over a list of SparseGraph tuples.  Returns pinned
+    host tensors X (n_nodes,F) f32, src/dst (B*e_max) i32.  `pinned` may pass a dict of
+    pre-allocated (larger) pinned buffers to reuse."""
+    L = _lib.lib()
+    B = len(graphs)
+    if B == 0:
+        raise ValueError("empty batch")
+    F = int(graphs[0].X.shape[1])
+    keep = []   # keep converted arrays alive during the call
+
+    def arr(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a
+
+    Xs = [arr(g.X, np.float32) for g in graphs]
+    cols = [[arr(getattr(g, k), np.int64) for g in graphs] for k in ("Ri_rows", "Ri_cols", "Ro_rows", "Ro_cols")]
+    n_nodes = np.array([x.shape[0] for x in Xs], dtype=np.int64)
+    n_in = np.array([a.shape[0] for a in cols[0]], dtype=np.int64)
+    n_out = np.array([a.shape[0] for a in cols[2]], dtype=np.int64)
+    for b, g in enumerate(graphs):
+        if Xs[b].ndim != 2 or Xs[b].shape[1] != F:
+            raise ValueError("graph %d: X must be (N, %d)" % (b, F))
+        if cols[1][b].shape != cols[0][b].shape or cols[3][b].shape != cols[2][b].shape:
+            raise ValueError("graph %d: rows/cols length mismatch" % b)
+    e_max = int(n_in.max())    # graph_from_sparse: n_edges = len(Ri_rows)
+    nt = int(n_nodes.sum())
+    can_pin = torch.cuda.is_available()
+    if pinned is not None:
+        Xo, src, dst = pinned["X"][:nt], pinned["src"][:B * e_max], pinned["dst"][:B * e_max]
+    else:
+        Xo = torch.empty((nt, F), dtype=torch.float32, pin_memory=can_pin)
+        src = torch.empty(B * e_max, dtype=torch.int32, pin_memory=can_pin)
+        dst = torch.empty(B * e_max, dtype=torch.int32, pin_memory=can_pin)
+
+    def pp(arrs):
+        return (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+
+    rc = L.gnnseg_pack_sparse_batch_host(
+        B, F, e_max, pp(Xs), n_nodes.ctypes.data, pp(cols[0]), pp(cols[1]), pp(cols[2]), pp(cols[3]),
+        n_in.ctypes.data, n_out.ctypes.data, Xo.data_ptr(), src.data_ptr(), dst.data_ptr(), n_threads)
+    if rc == -1:
+        raise ValueError("SparseGraph index out of range (row >= n_nodes or col >= max len(Ri_rows))")
+    _lib.check(rc, "gnnseg_pack_sparse_batch_host")
+    return {"X": Xo, "src": src, "dst": dst, "e_max": e_max, "n_nodes": n_nodes.tolist()}

@@ -1,0 +1,217 @@
+"""Drop-in SegmentClassifier whose forward runs on the B200 CUDA path.
+
+Module tree, constructor signature, parameter names/shapes/order and `state_dict` keys are
+those of the reference (gnn/model.py:14-156), so reference checkpoints load and
+`Estimator` (gnn/estimator.py) can drive it unchanged.  What differs is the execution:
+`SegmentClassifier.forward` packs the (masked) weights and calls `gnnseg_forward` through
+the C ABI (include/gnnseg.h); no dense incidence bmm ever runs.
+
+The sub-modules keep their reference attributes (`network[0].weight`, `.mask`,
+`.mask_flag`, `set_mask`, `get_mask`) because estimator.py:54-55 and
+estimator_maskedlinear.py:85-101 reach into them.  Their own `forward` methods are not
+implemented: the fused path never calls them and there is no CPU fallback.
+"""
+import ctypes as C
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .graph import DeviceGraphBatch, SparseGraph, _ptr, _stream_ptr
+
+
+class MaskedLinear(nn.Linear):
+    """nn.Linear with an optional 0/1 weight mask (gnn/model.py:14-33).  As in the
+    reference the mask is a plain attribute: not a buffer, not in state_dict."""
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__(in_features, out_features, bias)
+        self.mask_flag = False
+        self.mask = None
+
+    def set_mask(self, mask):
+        # gnn/model.py:19-22 (and the twin's device handling, model_maskedlinear.py:19-30):
+        # the mask follows the weight's device, the stored weights are zeroed where masked.
+        self.mask = mask.to(self.weight.device) if isinstance(mask, torch.Tensor) else torch.as_tensor(mask, device=self.weight.device)
+        self.weight.data = self.weight.data * self.mask.data
+        self.mask_flag = True
+
+    def get_mask(self):
+        return self.mask
+
+    def effective_mask(self):
+        """Mask tensor on the weight's device (fp32, contiguous) or None."""
+        if not self.mask_flag or self.mask is None:
+            return None
+        m = self.mask.detach()
+        if m.device != self.weight.device or m.dtype != torch.float32 or not m.is_contiguous():
+            m = m.to(device=self.weight.device, dtype=torch.float32).contiguous()
+            self.mask = m
+        return m
+
+    def forward(self, x):
+        raise _lib.GnnsegError("MaskedLinear.forward is not a standalone op here: call SegmentClassifier(...)")
+
+
+def _check_activation(act):
+    if act is not nn.Tanh:
+        raise ValueError("hidden_activation=%r: the CUDA path implements nn.Tanh only "
+                         "(every reference configuration uses Tanh)" % (act,))
+
+
+class EdgeNetwork(nn.Module):
+    """Parameter container matching gnn/model.py:36-55."""
+
+    def __init__(self, input_dim, hidden_dim=8, hidden_activation=nn.Tanh, mask=None):
+        super().__init__()
+        _check_activation(hidden_activation)
+        self.network = nn.Sequential(
+            MaskedLinear(input_dim * 2, hidden_dim), hidden_activation(),
+            MaskedLinear(hidden_dim, 1), nn.Sigmoid())
+        self.mask = mask
+        if mask is not None:
+            self.network[0].set_mask(mask[0])
+            self.network[2].set_mask(mask[1])
+
+    def forward(self, *a, **k):
+        raise _lib.GnnsegError("EdgeNetwork runs fused inside SegmentClassifier.forward (gnnseg_edge_step)")
+
+
+class NodeNetwork(nn.Module):
+    """Parameter container matching gnn/model.py:84-101.  Unlike gnn/model.py:100 (which
+    raises TypeError) `mask=None` is accepted, as in model_maskedlinear.py:110-112."""
+
+    def __init__(self, input_dim, output_dim, hidden_activation=nn.Tanh, mask=None):
+        super().__init__()
+        _check_activation(hidden_activation)
+        self.network = nn.Sequential(
+            MaskedLinear(input_dim * 3, output_dim), hidden_activation(),
+            MaskedLinear(output_dim, output_dim), hidden_activation())
+        self.mask = mask
+        if mask is not None:
+            self.network[0].set_mask(mask[0])
+            self.network[2].set_mask(mask[1])
+
+    def forward(self, *a, **k):
+        raise _lib.GnnsegError("NodeNetwork runs fused inside SegmentClassifier.forward (gnnseg_node_step)")
+
+
+class SegmentClassifier(nn.Module):
+    """gnn/model.py:127-156.  `forward(inputs)` accepts
+
+    * `[X, Ri, Ro]`: dense fp32 CUDA tensors (B,N,F), (B,N,E), (B,N,E) -> (B,E) scores, the
+      reference call;
+    * a `DeviceGraphBatch` -> (B, e_max) scores (replayed from a CUDA graph on repeat calls);
+    * a list of host `SparseGraph` tuples -> (B, e_max) scores, padded as merge_graphs pads.
+    """
+
+    def __init__(self, input_dim=2, hidden_dim=8, n_iters=3, hidden_activation=nn.Tanh,
+                 masks_e=None, masks_n=None):
+        super().__init__()
+        _check_activation(hidden_activation)
+        self.n_iters = n_iters
+        self.input_dim, self.hidden_dim = input_dim, hidden_dim
+        self.input_network = nn.Sequential(nn.Linear(input_dim, hidden_dim), hidden_activation())
+        self.edge_network = EdgeNetwork(input_dim + hidden_dim, hidden_dim, hidden_activation, masks_e)
+        self.node_network = NodeNetwork(input_dim + hidden_dim, hidden_dim, hidden_activation, masks_n)
+        self._blob = None
+        self.use_cuda_graph = True
+        self._warned_grad = False
+
+    # -- weights -------------------------------------------------------------------------
+    def _device(self):
+        return self.input_network[0].weight.device
+
+    def pack_weights(self):
+        """W*mask, transposed and padded into the kernel layout (gnnseg_pack_weights).  Runs
+        every forward, like the reference recomputes weight*mask (gnn/model.py:30)."""
+        L = _lib.lib()
+        dev = self._device()
+        if dev.type != "cuda":
+            raise _lib.GnnsegError("SegmentClassifier parameters are on %s: move the model to a CUDA "
+                                   "device (model.cuda()); there is no CPU path" % dev)
+        F, h = self.input_dim, self.hidden_dim
+        n = L.gnnseg_weights_floats(F, h)
+        if n == 0:
+            _lib.check(-2, "SegmentClassifier(input_dim=%d, hidden_dim=%d)" % (F, h))
+        if self._blob is None or self._blob.device != dev or self._blob.numel() != n:
+            self._blob = torch.empty(n, dtype=torch.float32, device=dev)
+        e0, e2 = self.edge_network.network[0], self.edge_network.network[2]
+        n0, n2 = self.node_network.network[0], self.node_network.network[2]
+        tensors = [self.input_network[0].weight, self.input_network[0].bias,
+                   e0.weight, e0.bias, e2.weight, e2.bias, n0.weight, n0.bias, n2.weight, n2.bias]
+        keep = []
+        ptrs = []
+        for t in tensors:
+            t = t.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(torch.float32).contiguous()
+            keep.append(t)
+            ptrs.append(t.data_ptr())
+        for lin in (e0, e2, n0, n2):
+            m = lin.effective_mask()
+            keep.append(m)
+            ptrs.append(m.data_ptr() if m is not None else None)
+        params = _lib.GnnsegParams(*ptrs)
+        with torch.cuda.device(dev):
+            _lib.check(L.gnnseg_pack_weights(C.byref(params), F, h, _ptr(self._blob), _stream_ptr(dev)),
+                       "gnnseg_pack_weights")
+        return self._blob
+
+    # -- forward -------------------------------------------------------------------------
+    def _run(self, batch):
+        L = _lib.lib()
+        dev = batch.device
+        if batch.F != self.input_dim:
+            raise ValueError("X has %d features, model expects input_dim=%d" % (batch.F, self.input_dim))
+        blob = self.pack_weights()
+        if blob.device != dev:
+            raise ValueError("graph batch on %s but model on %s" % (dev, blob.device))
+        h = self.hidden_dim
+        ws = batch.workspace(h)
+
+        def launch():
+            _lib.check(L.gnnseg_forward(_ptr(blob), C.byref(batch.struct), _ptr(batch.X), batch.F, h,
+                                        self.n_iters, _ptr(batch.scores), _ptr(ws), ws.numel(),
+                                        _stream_ptr(dev)), "gnnseg_forward")
+
+        with torch.cuda.device(dev):
+            if not self.use_cuda_graph:
+                launch()
+                return batch.scores
+            key = (blob.data_ptr(), h, self.n_iters)
+            entry = batch._graphs.get(key)
+            if entry is None:
+                # first call with this batch: plain launches (also warms up the kernels)
+                launch()
+                batch._graphs[key] = "warm"
+            elif entry == "warm":
+                # second call: capture the 2*n_iters+2 launches once, then replay
+                torch.cuda.current_stream(dev).synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    launch()
+                batch._graphs[key] = graph
+                graph.replay()
+            else:
+                entry.replay()
+        return batch.scores
+
+    def forward(self, inputs):
+        if torch.is_grad_enabled() and self.training and not self._warned_grad and \
+                any(p.requires_grad for p in self.parameters()):
+            warnings.warn("gnn_fpga_b200.SegmentClassifier.forward does not record an autograd graph; "
+                          "use gnn_fpga_b200.training for the native training step")
+            self._warned_grad = True
+        if isinstance(inputs, DeviceGraphBatch):
+            return self._run(inputs).view(inputs.B, inputs.e_max)
+        if isinstance(inputs, (list, tuple)) and len(inputs) > 0 and isinstance(inputs[0], SparseGraph):
+            batch = DeviceGraphBatch.from_sparse_graphs(list(inputs), device=self._device())
+            return self._run(batch).view(batch.B, batch.e_max)
+        X, Ri, Ro = inputs
+        if not (isinstance(X, torch.Tensor) and X.is_cuda):
+            raise ValueError("SegmentClassifier expects CUDA tensors [X, Ri, Ro] (got %s); there is no CPU path"
+                             % (X.device if isinstance(X, torch.Tensor) else type(X)))
+        batch = DeviceGraphBatch.from_dense(X, Ri, Ro)
+        return self._run(batch).view(batch.B, batch.e_max)

@@ -1,0 +1,174 @@
+/*
+ * gnnseg.h — C ABI of libgnnseg_b200.so: the B200 (sm_100a) implementation of the
+ * interaction-network segment classifier forward of jmduarte/gnn-fpga.
+ *
+ * The reference has no FFI: its boundary is the Python module API in gnn/model.py and
+ * gnn/graph.py.  Every entry point below names the reference code it replaces
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - Every `stream` argument is a cudaStream_t passed as void*.
+ *   - Pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - The caller owns every buffer, including workspaces.  The library never allocates or
+ *     frees device memory, never synchronises, and keeps no mutable global state, so every
+ *     device entry point can be captured in a CUDA graph.
+ *   - Return value: GNNSEG_OK (0) or a negative GNNSEG_E* code; gnnseg_strerror() names it.
+ *     Data errors that can only be seen on the device (bad incidence matrices) are written
+ *     to a caller-supplied device `err_flag` word (bit set below).
+ *   - All arithmetic is IEEE fp32 (the reference casts everything to float32,
+ *     gnn/trainSegmentClassifier.py:38-44); node/edge indices are int32.
+ *
+ * Graph layout ("flattened batch"): the B graphs of a batch are one block-diagonal graph
+ * with n_nodes nodes.  Edges live in `n_slots` slots; slot j of event b in a padded
+ * (B, E_max) batch is b*E_max + j, so scores come out directly in the reference's (B, E)
+ * layout.  A slot whose start or end is absent (a zero column of Ro or Ri, i.e. the
+ * zero padding of merge_graphs, gnn/trainSegmentClassifier.py:66-95) carries -1.
+ */
+#ifndef GNNSEG_H_
+#define GNNSEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNNSEG_ABI_VERSION 1
+
+/* error codes */
+#define GNNSEG_OK            0
+#define GNNSEG_EINVAL       -1   /* null pointer / negative size / bad argument        */
+#define GNNSEG_EUNSUPPORTED -2   /* (input_dim, hidden_dim) outside the compiled set    */
+#define GNNSEG_EWORKSPACE   -3   /* workspace smaller than gnnseg_*_workspace_bytes()   */
+#define GNNSEG_ECUDA        -4   /* a CUDA runtime call / launch failed                 */
+#define GNNSEG_ENODEVICE    -5   /* no sm_100 device visible                            */
+
+/* bits written to the device err_flag word by gnnseg_dense_to_edges */
+#define GNNSEG_BAD_VALUE      1  /* an incidence entry is neither 0 nor 1                */
+#define GNNSEG_BAD_HYPEREDGE  2  /* a column of Ri (or Ro) has more than one non-zero    */
+
+/*
+ * The ten parameter tensors of SegmentClassifier (gnn/model.py:128-138), row-major as
+ * torch stores them, plus the four optional MaskedLinear masks (gnn/model.py:19-33;
+ * masks_e = [m_e1, m_e2], masks_n = [m_n1, m_n2]).  D = input_dim + hidden_dim.
+ */
+typedef struct GnnsegParams {
+    const float* w_in;  const float* b_in;   /* input_network.0      (h, F)  , (h) */
+    const float* w_e1;  const float* b_e1;   /* edge_network.network.0 (h, 2D), (h) */
+    const float* w_e2;  const float* b_e2;   /* edge_network.network.2 (1, h) , (1) */
+    const float* w_n1;  const float* b_n1;   /* node_network.network.0 (h, 3D), (h) */
+    const float* w_n2;  const float* b_n2;   /* node_network.network.2 (h, h) , (h) */
+    const float* m_e1;  const float* m_e2;   /* nullable: masks, same shapes as w_e1, w_e2 */
+    const float* m_n1;  const float* m_n2;   /* nullable: masks, same shapes as w_n1, w_n2 */
+} GnnsegParams;
+
+/*
+ * Flattened batch graph in both CSR orders.  (in_ptr, in_eid) is exactly what
+ * np.nonzero(Ri) yields in gnn/graph.py:23-26 (rows ascending, columns ascending within a
+ * row): in_ptr = [0] + cumsum(bincount(Ri_rows)), in_eid = Ri_cols.  Same for Ro / out_*.
+ * in_nbr[s] = src[in_eid[s]] and out_nbr[s] = dst[out_eid[s]] are the neighbour ids.
+ */
+typedef struct GnnsegGraph {
+    int32_t        n_nodes;
+    int32_t        n_slots;
+    const int32_t* src;      /* [n_slots] start node (row of Ro holding the 1) or -1 */
+    const int32_t* dst;      /* [n_slots] end node   (row of Ri holding the 1) or -1 */
+    const int32_t* in_ptr;   /* [n_nodes+1] destination-CSR row pointer              */
+    const int32_t* in_eid;   /* [in_ptr[n_nodes]] slot ids, ascending within a row   */
+    const int32_t* in_nbr;   /* [in_ptr[n_nodes]] src[in_eid]                        */
+    const int32_t* out_ptr;  /* [n_nodes+1] source-CSR row pointer                   */
+    const int32_t* out_eid;  /* [out_ptr[n_nodes]]                                   */
+    const int32_t* out_nbr;  /* [out_ptr[n_nodes]] dst[out_eid]                      */
+} GnnsegGraph;
+
+/* ---- library ------------------------------------------------------------------------ */
+
+int         gnnseg_abi_version(void);
+const char* gnnseg_strerror(int code);
+/* 1 if (input_dim F, hidden_dim h) has compiled kernels: F in 1..4, h in {4,8,16,32,64}. */
+int         gnnseg_supported(int F, int h);
+/* number of SMs of the current device (grid sizing), or a negative error. */
+int         gnnseg_device_sm_count(void);
+
+/* ---- weights: replaces MaskedLinear.forward's per-call weight*mask, gnn/model.py:28-33 */
+
+/* floats in the packed (transposed, 16-byte padded, mask-multiplied) weight blob. */
+size_t gnnseg_weights_floats(int F, int h);
+int    gnnseg_pack_weights(const GnnsegParams* params, int F, int h, float* blob,
+                           void* stream);
+
+/* ---- graph: replaces make_sparse_graph / graph_from_sparse, gnn/graph.py:23-35 -------- */
+
+/*
+ * Dense (B,N,E) fp32 incidence matrices, as batch_generator feeds them to the model
+ * (gnn/trainSegmentClassifier.py:104-110), to per-slot endpoints: dst[b*E+e] = b*N+n where
+ * Ri[b,n,e]==1, src likewise from Ro, -1 where the column is all zero.  *err_flag is
+ * OR-ed with GNNSEG_BAD_* bits (caller zeroes it).
+ */
+int gnnseg_dense_to_edges(const float* Ri, const float* Ro, int B, int N, int E,
+                          int32_t* src, int32_t* dst, int32_t* err_flag, void* stream);
+
+/*
+ * Per-slot keys to CSR.  ptr[n_nodes+1], eid/nbr[n_slots] (only the first ptr[n_nodes] are
+ * meaningful).  Slots with key < 0 are left out.  Rows list slot ids in ascending order,
+ * which is np.nonzero's order, so the result is bit-identical to the reference's sparse
+ * tuples.  nbr[s] = other[eid[s]].
+ */
+size_t gnnseg_csr_workspace_bytes(int n_nodes, int n_slots);
+int    gnnseg_build_csr(const int32_t* key, const int32_t* other, int n_slots, int n_nodes,
+                        int32_t* ptr, int32_t* eid, int32_t* nbr,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* ---- forward: replaces SegmentClassifier.forward, gnn/model.py:140-156 ---------------- */
+
+size_t gnnseg_forward_workspace_bytes(int n_nodes, int n_slots, int F, int h);
+/*
+ * X is (n_nodes, F) row-major fp32.  scores[n_slots] receives the final edge_network
+ * output; a -1/-1 slot gets the reference's padding constant sigmoid(W2.tanh(b1)+b2).
+ * Launches 2*n_iters+2 kernels on `stream`, no host synchronisation.
+ */
+int gnnseg_forward(const float* blob, const GnnsegGraph* graph, const float* X,
+                   int F, int h, int n_iters, float* scores,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * The three steps on their own (used by the per-kernel parity tests).  HX is the
+ * (n_nodes, h+4) row layout [hidden(h) | X(F) | 0-pad], P is (n_nodes, 2h):
+ * P[n,0:h] = W1[:, 0:D].HX[n] + b1 and P[n,h:2h] = W1[:, D:2D].HX[n].
+ *   gnnseg_input_step : input_network + cat([H,X])               gnn/model.py:144-146
+ *   gnnseg_edge_step  : EdgeNetwork.forward                       gnn/model.py:69-81
+ *   gnnseg_node_step  : NodeNetwork.forward + cat([H,X])          gnn/model.py:113-125,154
+ */
+int gnnseg_input_step(const float* blob, const float* X, int n_nodes, int F, int h,
+                      float* HX, float* P, void* stream);
+int gnnseg_edge_step(const float* blob, const GnnsegGraph* graph, const float* P, int h,
+                     float* e, void* stream);
+int gnnseg_node_step(const float* blob, const GnnsegGraph* graph, const float* HX_in,
+                     const float* e, int h, float* HX_out, float* P_out, void* stream);
+
+/* ---- host side: replaces graph_from_sparse + merge_graphs + np_to_torch --------------- */
+
+/*
+ * Pack B host SparseGraph tuples (gnn/graph.py:20-21; int64 indices as np.nonzero and
+ * np.load give them) into flattened int32 endpoint arrays and one X array, without
+ * densifying.  Event b owns nodes [node_off[b], node_off[b+1]) and slots
+ * [b*e_max, (b+1)*e_max).  src_host/dst_host are filled with -1 first.  Returns
+ * GNNSEG_EINVAL if an index is out of range.  Pure CPU; n_threads <= 0 picks a default.
+ */
+int gnnseg_pack_sparse_batch_host(int B, int F, int e_max,
+                                  const float* const* X_host, const int64_t* n_nodes_host,
+                                  const int64_t* const* Ri_rows_host,
+                                  const int64_t* const* Ri_cols_host,
+                                  const int64_t* const* Ro_rows_host,
+                                  const int64_t* const* Ro_cols_host,
+                                  const int64_t* n_in_host, const int64_t* n_out_host,
+                                  float* X_out_host, int32_t* src_host, int32_t* dst_host,
+                                  int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNSEG_H_ */

@@ -1,0 +1,73 @@
+"""The oracle against outputs of the reference itself (tests/golden, oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import MODEL_CASES, load_case, rel_err
+from oracle import segclf_oracle as O
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_dense_restatement_matches_reference(name):
+    rec = load_case(name)
+    torch.set_num_threads(1)
+    p = O.apply_masks(rec["params"], rec["masks_e"], rec["masks_n"])
+    out = O.dense_forward(p, torch.from_numpy(rec["X"]), torch.from_numpy(rec["Ri"].astype(np.float32)),
+                          torch.from_numpy(rec["Ro"].astype(np.float32)), rec["n_iters"])
+    assert out.shape == rec["out"].shape
+    # same torch ops in the same order: equal to the last bit in practice; 1e-6 leaves room for
+    # a different BLAS blocking on another host
+    assert rel_err(out.numpy(), rec["out"]) <= 1e-6
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_sparse_restatement_matches_reference(name):
+    rec = load_case(name)
+    p = O.apply_masks(rec["params"], rec["masks_e"], rec["masks_n"])
+    B, N, F = rec["X"].shape
+    src, dst = O.edges_from_dense(rec["Ri"], rec["Ro"])
+    out32 = O.sparse_forward(p, rec["X"].reshape(B * N, F), src, dst, rec["n_iters"], torch.float32)
+    out64 = O.sparse_forward(p, rec["X"].reshape(B * N, F), src, dst, rec["n_iters"], torch.float64)
+    ref = rec["out"].reshape(-1)
+    assert rel_err(out32.numpy(), ref) <= 2e-6
+    assert rel_err(out64.numpy(), ref) <= 2e-6
+
+
+def test_init_params_reproduces_reference_init():
+    """init_params(F, h, seed) draws the same numbers as the reference constructor."""
+    rec = load_case("c1_toy2d_h8_it1")
+    p = O.init_params(rec["F"], rec["h"], rec["seed"])
+    for k in O.PARAM_KEYS:
+        assert torch.equal(p[k], rec["params"][k]), k
+
+
+def test_param_counts_and_keys():
+    z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "structure.npz"))
+    assert tuple(z["keys"]) == O.PARAM_KEYS
+    for key, count in z["counts"]:
+        F, h = map(int, key.split(","))
+        assert sum(v.numel() for v in O.init_params(F, h).values()) == int(count)
+    # 189 / 569 / 6881 / 26049 / 6689
+    assert dict((k, int(v)) for k, v in z["counts"]) == {"3,4": 189, "3,8": 569, "3,32": 6881, "3,64": 26049, "2,32": 6689}
+
+
+def test_integer_oracle_matches_reference_nonzero():
+    z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "graph_roundtrip.npz"))
+    src, dst = O.edges_from_dense(z["Ri"][None], z["Ro"][None])
+    n = z["Ri"].shape[0]
+    ptr, eid = O.csr_from_keys(dst, n)
+    assert np.array_equal(eid, z["Ri_cols"])
+    assert np.array_equal(np.repeat(np.arange(n), np.diff(ptr)), z["Ri_rows"])
+    ptr, eid = O.csr_from_keys(src, n)
+    assert np.array_equal(eid, z["Ro_cols"])
+    assert np.array_equal(np.repeat(np.arange(n), np.diff(ptr)), z["Ro_rows"])
+
+
+def test_padding_constant():
+    """A -1/-1 slot scores sigmoid(W2.tanh(b1)+b2) at every edge step."""
+    rec = load_case("acts_ragged_h32_it4")
+    p = rec["params"]
+    const = torch.sigmoid(p[O.PARAM_KEYS[4]] @ torch.tanh(p[O.PARAM_KEYS[3]]) + p[O.PARAM_KEYS[5]]).item()
+    pad = (rec["Ri"].sum(axis=1) == 0) & (rec["Ro"].sum(axis=1) == 0)
+    assert pad.any()
+    assert np.allclose(rec["out"][pad], const, rtol=1e-6)
