@@ -1,0 +1,57 @@
+"""The C-ABI library loads and exports every symbol include/gnnseg.h declares.  No compute
+calls here (no GPU needed): only the pure-host queries are invoked."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+from gnn_fpga_b200 import _lib
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "gnnseg.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gnnseg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_something():
+    names = declared_functions()
+    assert "gnnseg_forward" in names and "gnnseg_build_csr" in names and len(names) >= 14
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_functions()
+    for n in names:
+        assert hasattr(handle, n), "libgnnseg_b200.so does not export %s" % n
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+
+
+def test_host_only_queries():
+    L = _lib.lib()
+    assert L.gnnseg_abi_version() == 1
+    assert L.gnnseg_strerror(0) == b"ok"
+    assert b"unsupported" in L.gnnseg_strerror(-2)
+    for h in (4, 8, 16, 32, 64):
+        for F in (1, 2, 3, 4):
+            assert L.gnnseg_supported(F, h) == 1
+    for F, h in ((0, 8), (5, 8), (3, 12), (3, 128), (3, 0)):
+        assert L.gnnseg_supported(F, h) == 0
+        assert L.gnnseg_weights_floats(F, h) == 0
+    # blob size: Win^T[4][h] + b_in + W1^T[(h+4)][2h] + b1 + W2 + 4 + W3^T[3(h+4)][h] + b3 + W4^T + b4
+    h = 32
+    assert L.gnnseg_weights_floats(3, h) == 4 * h + h + (h + 4) * 2 * h + h + h + 4 + 3 * (h + 4) * h + h + h * h + h
+    assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 32) >= 4 * (2 * 1000 * 36 + 1000 * 64 + 5000)
+    assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 12) == 0
+    assert L.gnnseg_csr_workspace_bytes(1000, 5000) >= 8 * 1001
+
+
+def test_argument_errors_without_device_work():
+    """Null / unsupported arguments are rejected on the host before any CUDA call."""
+    L = _lib.lib()
+    assert L.gnnseg_pack_weights(None, 3, 32, None, None) == -1
+    assert L.gnnseg_pack_weights(None, 3, 12, None, None) == -2
+    assert L.gnnseg_forward(None, None, None, 3, 12, 1, None, None, 0, None) == -2
+    assert L.gnnseg_forward(None, None, None, 3, 32, 1, None, None, 0, None) == -1
+    assert L.gnnseg_dense_to_edges(None, None, -1, 1, 1, None, None, None, None) == -1
+    assert L.gnnseg_build_csr(None, None, 5, 5, None, None, None, None, 0, None) == -1

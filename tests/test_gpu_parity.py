@@ -1,0 +1,327 @@
+"""Parity of the CUDA path (through the C ABI) with the reference goldens and the oracle.
+
+Tolerances: indices / CSR bit-exact; edge scores <= 1e-5 relative in fp32
+(BASELINE.json north_star).  Everything here needs a GPU.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import MODEL_CASES, load_case, rel_err
+from oracle import segclf_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def make_model(rec, device):
+    from gnn_fpga_b200 import SegmentClassifier
+    m = SegmentClassifier(rec["F"], rec["h"], rec["n_iters"], masks_e=rec["masks_e"], masks_n=rec["masks_n"])
+    m.load_state_dict(rec["params"])
+    return m.to(device).eval()
+
+
+def sparse_graphs_of(rec):
+    """Per-event SparseGraph tuples (np.nonzero of each event's unpadded block)."""
+    from gnn_fpga_b200 import make_sparse_graph
+    out = []
+    for b in range(rec["X"].shape[0]):
+        Ri, Ro = rec["Ri"][b], rec["Ro"][b]
+        n_e = int(max(np.nonzero(Ri.sum(0))[0].max(initial=-1), np.nonzero(Ro.sum(0))[0].max(initial=-1)) + 1)
+        n_n = int(max(np.nonzero(Ri.sum(1))[0].max(initial=-1), np.nonzero(Ro.sum(1))[0].max(initial=-1)) + 1)
+        out.append(make_sparse_graph(rec["X"][b, :n_n], Ri[:n_n, :n_e], Ro[:n_n, :n_e], np.zeros(n_e, np.float32)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_dense_call_matches_reference(name, cuda_device):
+    """model([X, Ri, Ro]) -- the reference call -- against the reference's stored output."""
+    rec = load_case(name)
+    model = make_model(rec, cuda_device)
+    X = torch.from_numpy(rec["X"]).to(cuda_device)
+    Ri = torch.from_numpy(rec["Ri"].astype(np.float32)).to(cuda_device)
+    Ro = torch.from_numpy(rec["Ro"].astype(np.float32)).to(cuda_device)
+    with torch.no_grad():
+        out = model([X, Ri, Ro])
+    assert out.shape == rec["out"].shape and out.dtype == torch.float32
+    assert rel_err(out.cpu().numpy(), rec["out"]) <= TOL
+
+
+@pytest.mark.parametrize("name", ["acts_ragged_h32_it4", "acts_h64_it6", "c1_toy2d_h8_it1", "acts_masked_h8_it4"])
+def test_sparse_batch_call_matches_reference(name, cuda_device):
+    """List of SparseGraph tuples (no densifying) gives the same padded (B, E_max) scores."""
+    rec = load_case(name)
+    if name == "half_edges_h8_it2":
+        pytest.skip("graph_from_sparse cannot express it")
+    model = make_model(rec, cuda_device)
+    graphs = sparse_graphs_of(rec)
+    with torch.no_grad():
+        out = model(graphs)
+    assert tuple(out.shape) == rec["out"].shape
+    assert rel_err(out.cpu().numpy(), rec["out"]) <= TOL
+
+
+def test_masked_twin_bit_equal(cuda_device):
+    """model.py and model_maskedlinear.py agree to the last bit in the reference; so do we."""
+    a, b = load_case("acts_masked_h8_it4"), load_case("acts_masked_h8_it4_twin")
+    outs = []
+    for rec in (a, b):
+        model = make_model(rec, cuda_device)
+        outs.append(model(sparse_graphs_of(rec)).clone())
+    assert torch.equal(outs[0], outs[1])
+    # masks passed explicitly == weights zeroed beforehand and no masks
+    rec = a
+    from gnn_fpga_b200 import SegmentClassifier
+    m2 = SegmentClassifier(rec["F"], rec["h"], rec["n_iters"])
+    m2.load_state_dict(O.apply_masks(rec["params"], rec["masks_e"], rec["masks_n"]))
+    m2 = m2.to(cuda_device).eval()
+    assert torch.equal(m2(sparse_graphs_of(rec)), outs[0])
+
+
+# ---------------------------------------------------------------------------------------
+def test_dense_to_edges_and_csr_bit_exact(cuda_device):
+    from gnn_fpga_b200 import DeviceGraphBatch
+    for name in ("acts_ragged_h32_it4", "half_edges_h8_it2", "c1_toy2d_h8_it1"):
+        rec = load_case(name)
+        B, N, F = rec["X"].shape
+        batch = DeviceGraphBatch.from_dense(torch.from_numpy(rec["X"]).to(cuda_device),
+                                            torch.from_numpy(rec["Ri"].astype(np.float32)).to(cuda_device),
+                                            torch.from_numpy(rec["Ro"].astype(np.float32)).to(cuda_device))
+        src, dst = O.edges_from_dense(rec["Ri"], rec["Ro"])
+        assert np.array_equal(batch.src.cpu().numpy(), src)
+        assert np.array_equal(batch.dst.cpu().numpy(), dst)
+        for key, other, ptr, eid, nbr in ((dst, src, batch.in_ptr, batch.in_eid, batch.in_nbr),
+                                          (src, dst, batch.out_ptr, batch.out_eid, batch.out_nbr)):
+            optr, oeid = O.csr_from_keys(key, B * N)
+            assert np.array_equal(ptr.cpu().numpy(), optr)
+            n_used = int(optr[-1])
+            assert np.array_equal(eid.cpu().numpy()[:n_used], oeid)
+            assert np.array_equal(nbr.cpu().numpy()[:n_used], other[oeid])
+
+
+def test_csr_matches_reference_nonzero_golden(cuda_device):
+    """Device CSR == np.nonzero tuples written by the reference's make_sparse_graph."""
+    import os
+    from conftest import GOLDEN
+    from gnn_fpga_b200 import DeviceGraphBatch
+    z = np.load(os.path.join(GOLDEN, "graph_roundtrip.npz"))
+    batch = DeviceGraphBatch.from_dense(torch.from_numpy(z["X"][None]).to(cuda_device),
+                                        torch.from_numpy(z["Ri"][None].astype(np.float32)).to(cuda_device),
+                                        torch.from_numpy(z["Ro"][None].astype(np.float32)).to(cuda_device))
+    n = z["Ri"].shape[0]
+    in_ptr = batch.in_ptr.cpu().numpy()
+    assert np.array_equal(batch.in_eid.cpu().numpy()[:in_ptr[-1]], z["Ri_cols"])
+    assert np.array_equal(np.repeat(np.arange(n), np.diff(in_ptr)), z["Ri_rows"])
+    out_ptr = batch.out_ptr.cpu().numpy()
+    assert np.array_equal(batch.out_eid.cpu().numpy()[:out_ptr[-1]], z["Ro_cols"])
+    assert np.array_equal(np.repeat(np.arange(n), np.diff(out_ptr)), z["Ro_rows"])
+
+
+def test_csr_large_random_with_hub(cuda_device):
+    """Unsorted endpoints, a degree-5000 hub (heapsort branch), degree-0 nodes, sentinels."""
+    from gnn_fpga_b200 import DeviceGraphBatch
+    rng = np.random.RandomState(0)
+    n, m = 20000, 300000
+    src = rng.randint(0, n, m)
+    dst = rng.randint(0, n, m)
+    dst[rng.choice(m, 5000, replace=False)] = 7
+    src[rng.choice(m, 1000, replace=False)] = -1
+    dst[rng.choice(m, 1000, replace=False)] = -1
+    src[src == 11] = 12                                      # node 11 has no out-edges
+    X = torch.zeros(n, 3, device=cuda_device)
+    batch = DeviceGraphBatch(X, torch.from_numpy(src.astype(np.int32)).to(cuda_device),
+                             torch.from_numpy(dst.astype(np.int32)).to(cuda_device), 1, m)
+    for key, other, ptr, eid, nbr in ((dst, src, batch.in_ptr, batch.in_eid, batch.in_nbr),
+                                      (src, dst, batch.out_ptr, batch.out_eid, batch.out_nbr)):
+        optr, oeid = O.csr_from_keys(key, n)
+        assert np.array_equal(ptr.cpu().numpy(), optr)
+        assert np.array_equal(eid.cpu().numpy()[:optr[-1]], oeid)
+        assert np.array_equal(nbr.cpu().numpy()[:optr[-1]], other[oeid])
+
+
+def test_bad_incidence_raises(cuda_device):
+    from gnn_fpga_b200 import DeviceGraphBatch
+    X = torch.zeros(1, 4, 3, device=cuda_device)
+    Ri = torch.zeros(1, 4, 5, device=cuda_device)
+    Ro = torch.zeros(1, 4, 5, device=cuda_device)
+    Ri[0, 1, 2] = 0.5
+    with pytest.raises(ValueError, match="only 0 and 1"):
+        DeviceGraphBatch.from_dense(X, Ri, Ro)
+    Ri[0, 1, 2] = 1.0
+    Ri[0, 3, 2] = 1.0
+    with pytest.raises(ValueError, match="more than one"):
+        DeviceGraphBatch.from_dense(X, Ri, Ro)
+
+
+# ---------------------------------------------------------------------------------------
+def _steps_setup(rec, device):
+    from gnn_fpga_b200 import DeviceGraphBatch, _lib
+    model = make_model(rec, device)
+    B, N, F = rec["X"].shape
+    batch = DeviceGraphBatch.from_dense(torch.from_numpy(rec["X"]).to(device),
+                                        torch.from_numpy(rec["Ri"].astype(np.float32)).to(device),
+                                        torch.from_numpy(rec["Ro"].astype(np.float32)).to(device))
+    return model, batch, _lib.lib()
+
+
+@pytest.mark.parametrize("name", ["acts_ragged_h32_it4", "acts_h64_it6", "toy2d_h4_it1", "toy2d_h16_it3", "acts_masked_h8_it4"])
+def test_each_kernel_against_oracle(name, cuda_device):
+    """gnnseg_input_step / gnnseg_edge_step / gnnseg_node_step one at a time vs the oracle."""
+    from gnn_fpga_b200.graph import _ptr, _stream_ptr
+    rec = load_case(name)
+    model, batch, L = _steps_setup(rec, cuda_device)
+    p = O.apply_masks(rec["params"], rec["masks_e"], rec["masks_n"])
+    h, F, n = rec["h"], rec["F"], batch.n_nodes
+    blob = model.pack_weights()
+    HX = torch.zeros(n, h + 4, device=cuda_device)
+    HX2 = torch.zeros_like(HX)
+    P = torch.zeros(n, 2 * h, device=cuda_device)
+    e = torch.zeros(batch.n_slots, device=cuda_device)
+    st = _stream_ptr(cuda_device)
+    src = batch.src.cpu().long()
+    dst = batch.dst.cpu().long()
+    Xh = batch.X.cpu()
+
+    assert L.gnnseg_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(HX), _ptr(P), st) == 0
+    H0 = O.sparse_input(p, Xh)                                   # (n, h+F)
+    got = HX.cpu()
+    assert torch.allclose(got[:, :h], H0[:, :h], rtol=1e-5, atol=1e-6)
+    assert torch.equal(got[:, h:h + F], Xh) and torch.all(got[:, h + F:] == 0)
+    W1 = p[O.PARAM_KEYS[2]]
+    D = h + F
+    Ps = H0 @ W1[:, :D].T + p[O.PARAM_KEYS[3]]
+    Pd = H0 @ W1[:, D:].T
+    assert torch.allclose(P.cpu(), torch.cat([Ps, Pd], 1), rtol=1e-5, atol=2e-6)
+
+    assert L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, _ptr(e), st) == 0
+    e_ref = O.sparse_edge(p, H0, src, dst)
+    assert rel_err(e.cpu().numpy(), e_ref.numpy()) <= TOL
+
+    # node step on the oracle's own e, so that only this kernel is under test
+    e_in = e_ref.to(cuda_device).contiguous()
+    assert L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(HX), _ptr(e_in), h, _ptr(HX2), _ptr(P), st) == 0
+    H1 = O.sparse_node(p, H0, e_ref, src, dst)
+    got = HX2.cpu()
+    assert torch.allclose(got[:, :h], H1, rtol=1e-5, atol=2e-6)
+    assert torch.equal(got[:, h:h + F], Xh)
+
+
+def test_deterministic_and_graph_replay(cuda_device):
+    """Same bits run to run, with and without the CUDA graph, and after rebuilding the batch."""
+    from gnn_fpga_b200 import DeviceGraphBatch
+    rec = load_case("acts_ragged_h32_it4")
+    model = make_model(rec, cuda_device)
+    graphs = sparse_graphs_of(rec)
+    batch = DeviceGraphBatch.from_sparse_graphs(graphs, cuda_device)
+    model.use_cuda_graph = False
+    a = model(batch).clone()
+    model.use_cuda_graph = True
+    b = model(batch).clone()      # warm
+    c = model(batch).clone()      # capture + replay
+    d = model(batch).clone()      # replay
+    e = model(DeviceGraphBatch.from_sparse_graphs(graphs, cuda_device)).clone()
+    for t in (b, c, d, e):
+        assert torch.equal(a, t)
+    # replay picks up changed weights (the blob is re-packed in place before each replay)
+    with torch.no_grad():
+        model.edge_network.network[2].bias.add_(0.25)
+    f = model(batch).clone()
+    model.use_cuda_graph = False
+    g = model(batch).clone()
+    assert torch.equal(f, g) and not torch.equal(f, a)
+
+
+def test_events_are_independent(cuda_device):
+    """Scores of an event do not depend on what else is in the batch: batch == one by one
+    (bit-equal), which is also what makes the multi-GPU event sharding exact."""
+    from gnn_fpga_b200 import data, SegmentClassifier
+    torch.manual_seed(0)
+    model = SegmentClassifier(3, 32, 4).to(cuda_device).eval()
+    graphs = [data.acts_like_graph(n, seed=i) for i, n in enumerate((40, 55, 33, 47))]
+    full = model(graphs).clone()
+    for b, g in enumerate(graphs):
+        one = model([g])
+        n_e = g.Ri_rows.shape[0]
+        assert torch.equal(one[0, :n_e], full[b, :n_e])
+
+
+@pytest.mark.parametrize("h,n_iters,n_tracks", [(32, 4, 400), (64, 8, 1000)])
+def test_event_scale_against_sparse_oracle(h, n_iters, n_tracks, cuda_device):
+    """One ACTS-like event (BASELINE configs[1] event size; a 1/10 mu200 event) vs the fp32 and
+    fp64 sparse restatements: <= 1e-5 relative."""
+    from gnn_fpga_b200 import data, SegmentClassifier
+    g = data.acts_like_graph(n_tracks, seed=3)
+    p = O.init_params(3, h, seed=0)
+    model = SegmentClassifier(3, h, n_iters)
+    model.load_state_dict(p)
+    model = model.to(cuda_device).eval()
+    out = model([g])[0].cpu().numpy()
+    X, src, dst, e_max = O.flatten_sparse_batch([g])
+    ref32 = O.sparse_forward(p, X, src, dst, n_iters, torch.float32).numpy()
+    ref64 = O.sparse_forward(p, X, src, dst, n_iters, torch.float64).numpy()
+    assert rel_err(out, ref32) <= TOL
+    assert rel_err(out, ref64) <= TOL
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE configs[1] at full size (64 events, ~1.28M edges): scores in (0,1), padding
+    slots equal the padding constant, and relabelling the nodes of every event (a permutation
+    of node ids, edges kept in place) leaves every score within fp32 reordering noise."""
+    from gnn_fpga_b200 import data, SegmentClassifier, SparseGraph
+    from gnn_fpga_b200.data import sparse_from_edges
+    graphs = data.acts_like_graphs(64, 400, seed=0)
+    torch.manual_seed(0)
+    model = SegmentClassifier(3, 32, 4).to(cuda_device).eval()
+    out = model(graphs).clone()
+    assert torch.all((out > 0) & (out < 1))
+    p = {k: v.cpu() for k, v in model.state_dict().items()}
+    const = torch.sigmoid(p[O.PARAM_KEYS[4]] @ torch.tanh(p[O.PARAM_KEYS[3]]) + p[O.PARAM_KEYS[5]]).item()
+    for b, g in enumerate(graphs):
+        pad = out[b, g.Ri_rows.shape[0]:].cpu().numpy()
+        assert np.all(np.abs(pad - const) <= 1e-6 * const)
+    rng = np.random.RandomState(5)
+    permuted = []
+    for g in graphs[:8]:
+        n = g.X.shape[0]
+        perm = rng.permutation(n)                 # new id of old node i
+        src = np.empty(g.Ro_cols.shape[0], np.int64); src[g.Ro_cols] = g.Ro_rows
+        dst = np.empty(g.Ri_cols.shape[0], np.int64); dst[g.Ri_cols] = g.Ri_rows
+        Xp = np.empty_like(g.X); Xp[perm] = g.X
+        permuted.append(sparse_from_edges(Xp, perm[src], perm[dst], g.y))
+    out_p = model(permuted)
+    for b, g in enumerate(graphs[:8]):
+        n_e = g.Ri_rows.shape[0]
+        assert rel_err(out_p[b, :n_e].cpu().numpy(), out[b, :n_e].cpu().numpy()) <= TOL
+
+
+def test_unsupported_shapes_fail_loudly(cuda_device):
+    from gnn_fpga_b200 import SegmentClassifier, GnnsegError, data
+    model = SegmentClassifier(3, 12, 1).to(cuda_device)
+    with pytest.raises(GnnsegError, match="unsupported"):
+        model(data.toy2d_graphs(1))
+    model = SegmentClassifier(2, 8, 1).to(cuda_device)
+    with pytest.raises(ValueError, match="input_dim"):
+        model(data.toy2d_graphs(1, input_dim=3))
+
+
+def test_empty_and_tiny_inputs(cuda_device):
+    from gnn_fpga_b200 import SegmentClassifier, SparseGraph
+    torch.manual_seed(1)
+    model = SegmentClassifier(3, 8, 2).to(cuda_device).eval()
+    # a graph with nodes but no edges, next to a normal one
+    i64 = np.zeros(0, np.int64)
+    g0 = SparseGraph(np.random.RandomState(0).rand(5, 3).astype(np.float32), i64, i64, i64, i64, np.zeros(0, np.float32))
+    g1 = SparseGraph(np.random.RandomState(1).rand(3, 3).astype(np.float32), np.array([1, 2]), np.array([0, 1]),
+                     np.array([0, 1]), np.array([0, 1]), np.zeros(2, np.float32))
+    out = model([g0, g1])
+    assert tuple(out.shape) == (2, 2)
+    p = {k: v.cpu() for k, v in model.state_dict().items()}
+    X, src, dst, e_max = O.flatten_sparse_batch([g0, g1])
+    ref = O.sparse_forward(p, X, src, dst, 2).numpy().reshape(2, 2)
+    assert rel_err(out.cpu().numpy(), ref) <= TOL
+    # zero edges in the whole batch
+    out = model([g0])
+    assert tuple(out.shape) == (1, 0)
