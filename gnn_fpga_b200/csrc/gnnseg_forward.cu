@@ -9,11 +9,11 @@
 //   node step (gnn/model.py:113-125) mi[n] = sum_{dst_j = n} e_j HX[src_j]  (ascending j)
 //                                    mo[n] = sum_{src_j = n} e_j HX[dst_j]  (ascending j)
 //                                    H'[n] = tanh(W4 . tanh(W3 . [mi; mo; HX[n]] + b3) + b4)
-//     one persistent CTA per tile of nodes: sub-warp groups walk the two CSR rows (no
-//     atomics, fixed order), the tile's [mi|mo|self] rows are staged in shared memory, and
-//     the two layers + the next step's projection run as register-tiled fp32 GEMMs against
-//     weights resident in shared memory.  HX' = [H' | X] is written back (the reference's
-//     cat([H, X]), gnn/model.py:146,154) together with P'.
+//     persistent warp-specialised CTAs: producer warps walk the two CSR rows of a tile of
+//     nodes (no atomics, fixed order) into shared memory while consumer warps run the two
+//     layers + the next step's projection of the previous tile as register-tiled fp32 GEMMs
+//     against weights resident in shared memory.  HX' = [H' | X] is written back (the
+//     reference's cat([H, X]), gnn/model.py:146,154) together with P'.
 #include "gnnseg_common.cuh"
 
 namespace gnnseg {
@@ -72,22 +72,25 @@ __global__ void pack_weights_kernel(GnnsegParams p, int F, int H, float* __restr
 // ------------------------------------------------------------------------------------
 // register-tiled shared-memory GEMM:  out[node][o] = sum_k A[node][k] * W[k][o]
 // A: [TN][lda] fp32 in shared memory, W: [K][HOUT] fp32 in shared memory.
-// A thread owns RN nodes (ng, ng+NG, ...) x 4 consecutive outputs.  Lanes run over the
+// A thread owns RN nodes (ng, ng+NG, ...) x RC consecutive outputs.  Lanes run over the
 // output groups first, so W reads are contiguous and the (few) distinct A rows of a warp
-// are consecutive rows, which tile_stride() keeps on distinct banks.
+// are consecutive rows, which tile_stride() keeps on distinct banks.  NT = threads taking
+// part (they must be threads 0..NT-1 of the CTA).
 // ------------------------------------------------------------------------------------
-template <int K, int HOUT, int TN, int NT, int RN, typename Epi>
+template <int K, int HOUT, int TN, int NT, int RN, int RC, typename Epi>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, const int lda,
                                           const float* __restrict__ sW, Epi epi) {
-    constexpr int OG = HOUT / 4, NG = TN / RN, TILES = OG * NG;
-    static_assert(K % 4 == 0 && HOUT % 4 == 0 && TN % RN == 0, "tile shape");
+    constexpr int OG = HOUT / RC, NG = TN / RN, TILES = OG * NG;
+    static_assert(K % 4 == 0 && RC % 4 == 0 && HOUT % RC == 0 && TN % RN == 0, "tile shape");
     for (int t = threadIdx.x; t < TILES; t += NT) {
         const int og = t % OG, ng = t / OG;
-        float acc[RN][4];
+        float acc[RN][RC];
 #pragma unroll
-        for (int i = 0; i < RN; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        for (int i = 0; i < RN; ++i)
+#pragma unroll
+            for (int c = 0; c < RC; ++c) acc[i][c] = 0.f;
         const float* a0 = sA + ng * lda;
-        const float* w0 = sW + og * 4;
+        const float* w0 = sW + og * RC;
 #pragma unroll 2
         for (int k = 0; k < K; k += 4) {
             float4 a[RN];
@@ -95,19 +98,24 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, const in
             for (int i = 0; i < RN; ++i) a[i] = lds4(a0 + i * NG * lda + k);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                const float4 w = lds4(w0 + (k + kk) * HOUT);
 #pragma unroll
-                for (int i = 0; i < RN; ++i) {
-                    const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
-                    acc[i][0] = fmaf(av, w.x, acc[i][0]);
-                    acc[i][1] = fmaf(av, w.y, acc[i][1]);
-                    acc[i][2] = fmaf(av, w.z, acc[i][2]);
-                    acc[i][3] = fmaf(av, w.w, acc[i][3]);
+                for (int c4 = 0; c4 < RC / 4; ++c4) {
+                    const float4 w = lds4(w0 + (k + kk) * HOUT + 4 * c4);
+#pragma unroll
+                    for (int i = 0; i < RN; ++i) {
+                        const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                        acc[i][4 * c4 + 0] = fmaf(av, w.x, acc[i][4 * c4 + 0]);
+                        acc[i][4 * c4 + 1] = fmaf(av, w.y, acc[i][4 * c4 + 1]);
+                        acc[i][4 * c4 + 2] = fmaf(av, w.z, acc[i][4 * c4 + 2]);
+                        acc[i][4 * c4 + 3] = fmaf(av, w.w, acc[i][4 * c4 + 3]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int i = 0; i < RN; ++i) epi(ng + i * NG, og * 4, acc[i]);
+        for (int i = 0; i < RN; ++i)
+#pragma unroll
+            for (int c4 = 0; c4 < RC / 4; ++c4) epi(ng + i * NG, og * RC + 4 * c4, &acc[i][4 * c4]);
     }
 }
 
@@ -119,23 +127,30 @@ __device__ __forceinline__ void copy_to_smem(float* __restrict__ dst, const floa
 // Kernel shape per hidden size.
 template <int H>
 struct NodeCfg {
-    static constexpr int TN  = 64;                 // nodes per tile
-    static constexpr int NT  = 256;                // threads per CTA
-    static constexpr int RN1 = (H >= 64) ? 4 : 2;  // nodes per thread, layers with H outputs
-    static constexpr int RNP = 4;                  // nodes per thread, projection (2H outputs)
-    static constexpr int D4  = H + 4;
-    static constexpr int K1  = 3 * D4;
-    static constexpr int SM  = tile_stride(K1);    // [mi|mo|self] tile stride
-    static constexpr int SH  = tile_stride(H);     // hidden-layer tile stride
-    static constexpr int SD  = tile_stride(D4);    // HX tile stride
+    static constexpr int TN   = 64;                  // nodes per tile
+    static constexpr int CW   = 8;                   // consumer warps (MLP)
+    static constexpr int PW   = (H >= 64) ? 16 : 8;  // producer warps (CSR gather)
+    static constexpr int CT   = CW * 32;
+    static constexpr int PT   = PW * 32;
+    static constexpr int NT   = CT + PT;             // threads per CTA
+    static constexpr int NBUF = (H >= 64) ? 1 : 2;   // [mi|mo|self] tile buffers
+    static constexpr int MINB = (H >= 64) ? 1 : 2;   // CTAs per SM the register budget allows
+    static constexpr int RN1  = (H >= 64) ? 4 : 2;   // nodes per thread, layers with H outputs
+    static constexpr int RNP  = 4;                   // nodes per thread, projection (2H outputs)
+    static constexpr int RCP  = (H >= 64) ? 8 : 4;   // outputs per thread, projection
+    static constexpr int D4   = H + 4;
+    static constexpr int K1   = 3 * D4;
+    static constexpr int SM   = tile_stride(K1);     // [mi|mo|self] tile stride
+    static constexpr int SH   = tile_stride(H);      // hidden-layer tile stride
+    static constexpr int SD   = tile_stride(D4);     // HX tile stride
     static constexpr int W_FLOATS = K1 * H + H * H + D4 * 2 * H + 3 * H;
-    static constexpr int SMEM_FLOATS = W_FLOATS + TN * (SM + SH + SD);
+    static constexpr int SMEM_FLOATS = W_FLOATS + TN * (NBUF * SM + SH + SD);
     static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
 };
 
 template <int H>
 struct InputCfg {
-    static constexpr int TN = 64, NT = 256, RNP = 4;
+    static constexpr int TN = 64, NT = 256, RNP = 4, RCP = 4;
     static constexpr int D4 = H + 4;
     static constexpr int SD = tile_stride(D4);
     static constexpr int SMEM_FLOATS = 4 * H + H + D4 * 2 * H + H + TN * SD + TN * 4;
@@ -143,7 +158,8 @@ struct InputCfg {
 };
 
 // Write the tile's HX rows and its projection P = [W1a.HX+b1 | W1b.HX] to global memory.
-template <int H, int TN, int NT, int RNP>
+// Runs on threads 0..NT-1.
+template <int H, int TN, int NT, int RNP, int RCP>
 __device__ __forceinline__ void store_hx_and_project(const float* __restrict__ sHX, const int sd,
                                                      const float* __restrict__ sW1,
                                                      const float* __restrict__ sB1,
@@ -155,7 +171,7 @@ __device__ __forceinline__ void store_hx_and_project(const float* __restrict__ s
         const int ln = i / C4, c = i % C4, n = node0 + ln;
         if (n < n_nodes) st4(HX_out + (size_t)n * D4 + 4 * c, lds4(sHX + ln * sd + 4 * c));
     }
-    tile_gemm<D4, 2 * H, TN, NT, RNP>(sHX, sd, sW1, [&](int ln, int o, const float (&acc)[4]) {
+    tile_gemm<D4, 2 * H, TN, NT, RNP, RCP>(sHX, sd, sW1, [&](int ln, int o, const float* acc) {
         const int n = node0 + ln;
         if (n < n_nodes) {
             float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -214,7 +230,7 @@ input_kernel(const float* __restrict__ blob, const float* __restrict__ X, const 
             st4(sHX + ln * SD + 4 * c, v);
         }
         __syncthreads();
-        store_hx_and_project<H, TN, NT, C::RNP>(sHX, SD, sW1, sB1, node0, n_nodes, HX_out, P_out);
+        store_hx_and_project<H, TN, NT, C::RNP, C::RCP>(sHX, SD, sW1, sB1, node0, n_nodes, HX_out, P_out);
     }
 }
 
@@ -265,42 +281,64 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
 }
 
 // ------------------------------------------------------------------------------------
-// node step
+// node step: warp-specialised persistent kernel.
+//   producer warps  walk the two CSR rows of every node of a tile and leave the tile's
+//                   [mi | mo | self] rows in shared memory (latency bound: many loads in flight)
+//   consumer warps  run layer 0, layer 2 and the projection as register-tiled fp32 GEMMs
+//                   out of shared memory (FMA bound) and write HX' and P'
+// The two halves meet through named barriers (full/empty per tile buffer), so the gather of
+// tile t+1 overlaps the MLP of tile t on the same SM.
 // ------------------------------------------------------------------------------------
-// One CSR row: acc += e[eid[s]] * HX[nbr[s]] for s ascending.  Lane c of the node's group
-// owns float4 chunk c of the hidden part; lane 0 also owns the X chunk.
+__device__ __forceinline__ void bar_sync(const int id, const int n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(const int id, const int n) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+// One CSR row, G lanes per node (lane c owns float4 chunk c of the hidden part, lane 0 also the
+// X chunk).  The lanes first fetch up to G (neighbour, weight) pairs of the row in parallel
+// (coalesced index loads, one dependent gather of e), then every pair is broadcast through the
+// group and its feature row is gathered, ascending slot order: acc += e[eid[s]] * HX[nbr[s]].
+// All control flow is warp-uniform (trip counts are maxima over the warp) so the shuffles are
+// legal; absent work is predicated off.
 template <int H>
-__device__ __forceinline__ void csr_row_sum(const int32_t* __restrict__ ptr,
-                                            const int32_t* __restrict__ eid,
+__device__ __forceinline__ void csr_row_sum(const int32_t* __restrict__ eid,
                                             const int32_t* __restrict__ nbr,
                                             const float* __restrict__ e,
-                                            const float* __restrict__ HX, const int n,
-                                            const int c, float4& acc_h, float4& acc_x) {
-    constexpr int D4 = H + 4;
-    const int beg = __ldg(ptr + n), end = __ldg(ptr + n + 1);
+                                            const float* __restrict__ HX, const int beg,
+                                            const int cnt, const int max_cnt, const int c,
+                                            float4& acc_h, float4& acc_x) {
+    constexpr int D4 = H + 4, G = H / 4;
+    for (int base = 0; base < max_cnt; base += G) {
+        const bool ok = base + c < cnt;
+        const int s = beg + base + c;
+        const int nb = ok ? __ldg(nbr + s) : -1;
+        const float w = ok ? __ldg(e + __ldg(eid + s)) : 0.f;
+        const int m = min(G, max_cnt - base);
 #pragma unroll 4
-    for (int s = beg; s < end; ++s) {
-        const int nb = __ldg(nbr + s);
-        const float w = __ldg(e + __ldg(eid + s));
-        if (nb >= 0) {   // a half edge (absent other end) gathers the zero row
-            const float* row = HX + (size_t)nb * D4;
-            fma4(acc_h, w, ldg4(row + 4 * c));
-            if (c == 0) fma4(acc_x, w, ldg4(row + H));
+        for (int j = 0; j < m; ++j) {
+            const int nbj = __shfl_sync(0xffffffffu, nb, j, G);
+            const float wj = __shfl_sync(0xffffffffu, w, j, G);
+            if (nbj >= 0) {   // a half edge (absent other end) gathers the zero row
+                const float* row = HX + (size_t)nbj * D4;
+                fma4(acc_h, wj, ldg4(row + 4 * c));
+                if (c == 0) fma4(acc_x, wj, ldg4(row + H));
+            }
         }
     }
 }
 
 template <int H>
-__global__ void __launch_bounds__(NodeCfg<H>::NT)
+__global__ void __launch_bounds__(NodeCfg<H>::NT, NodeCfg<H>::MINB)
 node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
             const float* __restrict__ HX_in, const float* __restrict__ e, const int n_tiles,
             float* __restrict__ HX_out, float* __restrict__ P_out) {
     using C = NodeCfg<H>;
     using B = Blob<H>;
-    constexpr int TN = C::TN, NT = C::NT, D4 = C::D4, K1 = C::K1;
-    constexpr int SM = C::SM, SH = C::SH, SD = C::SD;
-    constexpr int G = H / 4;            // lanes per node in the gather phase
-    constexpr int NGRP = NT / G;        // node groups per CTA
+    constexpr int TN = C::TN, NT = C::NT, CT = C::CT, PT = C::PT, NBUF = C::NBUF;
+    constexpr int D4 = C::D4, K1 = C::K1, SM = C::SM, SH = C::SH, SD = C::SD;
+    constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_CONS = 1 + 2 * NBUF;
     extern __shared__ __align__(16) float smem[];
     float* sW3 = smem;                  // [K1][H]
     float* sB3 = sW3 + K1 * H;          // [H]
@@ -308,60 +346,86 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
     float* sB4 = sW4 + H * H;           // [H]
     float* sW1 = sB4 + H;               // [D4][2H]
     float* sB1 = sW1 + D4 * 2 * H;      // [H]
-    float* sM  = sB1 + H;               // [TN][SM]   [mi | mo | self]
-    float* sH1 = sM + TN * SM;          // [TN][SH]
+    float* sM  = sB1 + H;               // [NBUF][TN][SM]   [mi | mo | self]
+    float* sH1 = sM + NBUF * TN * SM;   // [TN][SH]
     float* sHX = sH1 + TN * SH;         // [TN][SD]
     copy_to_smem<NT>(sW3, blob + B::W3, K1 * H + H + H * H + H);   // W3,b3,W4,b4 contiguous
     copy_to_smem<NT>(sW1, blob + B::W1, D4 * 2 * H + H);           // W1,b1 contiguous
-
-    const int grp = threadIdx.x / G, c = threadIdx.x % G;
+    __syncthreads();
     const int n_nodes = g.n_nodes;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int node0 = tile * TN;
-        // ---- gather: [mi | mo | self] rows of the tile -------------------------------
-        for (int ln = grp; ln < TN; ln += NGRP) {
-            const int n = node0 + ln;
-            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 mi_h = zero, mi_x = zero, mo_h = zero, mo_x = zero, se_h = zero, se_x = zero;
-            if (n < n_nodes) {
-                csr_row_sum<H>(g.in_ptr, g.in_eid, g.in_nbr, e, HX_in, n, c, mi_h, mi_x);
-                csr_row_sum<H>(g.out_ptr, g.out_eid, g.out_nbr, e, HX_in, n, c, mo_h, mo_x);
-                const float* row = HX_in + (size_t)n * D4;
-                se_h = ldg4(row + 4 * c);
-                if (c == 0) se_x = ldg4(row + H);
+    if (threadIdx.x >= CT) {
+        // ================================ producers ====================================
+        constexpr int G = H / 4;            // lanes per node
+        constexpr int NGRP = PT / G;        // nodes gathered concurrently
+        const int pt = threadIdx.x - CT;
+        const int grp = pt / G, c = pt % G;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it % NBUF;
+            if (it >= NBUF) bar_sync(BAR_EMPTY + buf, NT);     // consumers are done with this buffer
+            float* sMb = sM + buf * TN * SM;
+            const int node0 = tile * TN;
+            if (grp < TN) {                                    // warp-uniform (G divides 32)
+                for (int ln = grp; ln < TN; ln += NGRP) {
+                    const int n = node0 + ln;
+                    const bool live = n < n_nodes;
+                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 mi_h = zero, mi_x = zero, mo_h = zero, mo_x = zero, se_h = zero, se_x = zero;
+                    int ib = 0, ic = 0, ob = 0, oc = 0;
+                    if (live) {
+                        ib = __ldg(g.in_ptr + n);  ic = __ldg(g.in_ptr + n + 1) - ib;
+                        ob = __ldg(g.out_ptr + n); oc = __ldg(g.out_ptr + n + 1) - ob;
+                        const float* row = HX_in + (size_t)n * D4;
+                        se_h = ldg4(row + 4 * c);
+                        if (c == 0) se_x = ldg4(row + H);
+                    }
+                    const int imax = __reduce_max_sync(0xffffffffu, ic);
+                    const int omax = __reduce_max_sync(0xffffffffu, oc);
+                    csr_row_sum<H>(g.in_eid, g.in_nbr, e, HX_in, ib, ic, imax, c, mi_h, mi_x);
+                    csr_row_sum<H>(g.out_eid, g.out_nbr, e, HX_in, ob, oc, omax, c, mo_h, mo_x);
+                    float* m = sMb + ln * SM;
+                    st4(m + 4 * c, mi_h);
+                    st4(m + D4 + 4 * c, mo_h);
+                    st4(m + 2 * D4 + 4 * c, se_h);
+                    if (c == 0) {
+                        st4(m + H, mi_x);
+                        st4(m + D4 + H, mo_x);
+                        st4(m + 2 * D4 + H, se_x);
+                    }
+                }
             }
-            float* m = sM + ln * SM;
-            st4(m + 4 * c, mi_h);
-            st4(m + D4 + 4 * c, mo_h);
-            st4(m + 2 * D4 + 4 * c, se_h);
-            if (c == 0) {
-                st4(m + H, mi_x);
-                st4(m + D4 + H, mo_x);
-                st4(m + 2 * D4 + H, se_x);
-            }
+            bar_arrive(BAR_FULL + buf, NT);
         }
-        __syncthreads();
-        // ---- layer 0: h1 = tanh(W3 . [mi; mo; self] + b3) ------------------------------
-        tile_gemm<K1, H, TN, NT, C::RN1>(sM, SM, sW3, [&](int ln, int o, const float (&acc)[4]) {
-            const float4 b = lds4(sB3 + o);
-            st4(sH1 + ln * SH + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
-                                               tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
-        });
-        // the X part of the new HX row is the old one (self block of sM)
-        for (int i = threadIdx.x; i < TN; i += NT) st4(sHX + i * SD + H, lds4(sM + i * SM + 2 * D4 + H));
-        __syncthreads();
-        // ---- layer 2: H' = tanh(W4 . h1 + b4) ------------------------------------------
-        tile_gemm<H, H, TN, NT, C::RN1>(sH1, SH, sW4, [&](int ln, int o, const float (&acc)[4]) {
-            const float4 b = lds4(sB4 + o);
-            st4(sHX + ln * SD + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
-                                               tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
-        });
-        __syncthreads();
-        // ---- write HX' and the projection for the next edge step ------------------------
-        store_hx_and_project<H, TN, NT, C::RNP>(sHX, SD, sW1, sB1, node0, n_nodes, HX_out, P_out);
-        // next tile's gather only writes sM (last read before the layer-0 barrier), its
-        // later phases are fenced by its own barriers.
+    } else {
+        // ================================ consumers ====================================
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it % NBUF;
+            const int node0 = tile * TN;
+            const float* sMb = sM + buf * TN * SM;
+            bar_sync(BAR_FULL + buf, NT);                      // the tile's rows are in sMb
+            // ---- layer 0: h1 = tanh(W3 . [mi; mo; self] + b3) ---------------------------
+            tile_gemm<K1, H, TN, CT, C::RN1, 4>(sMb, SM, sW3, [&](int ln, int o, const float* acc) {
+                const float4 b = lds4(sB3 + o);
+                st4(sH1 + ln * SH + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
+                                                   tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
+            });
+            // the X part of the new HX row is the old one (self block of the tile)
+            for (int i = threadIdx.x; i < TN; i += CT) st4(sHX + i * SD + H, lds4(sMb + i * SM + 2 * D4 + H));
+            bar_sync(BAR_CONS, CT);
+            if (tile + NBUF * (int)gridDim.x < n_tiles) bar_arrive(BAR_EMPTY + buf, NT);   // release sMb
+            // ---- layer 2: H' = tanh(W4 . h1 + b4) ---------------------------------------
+            tile_gemm<H, H, TN, CT, C::RN1, 4>(sH1, SH, sW4, [&](int ln, int o, const float* acc) {
+                const float4 b = lds4(sB4 + o);
+                st4(sHX + ln * SD + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
+                                                   tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
+            });
+            bar_sync(BAR_CONS, CT);
+            // ---- write HX' and the projection for the next edge step ---------------------
+            store_hx_and_project<H, TN, CT, C::RNP, C::RCP>(sHX, SD, sW1, sB1, node0, n_nodes, HX_out, P_out);
+            bar_sync(BAR_CONS, CT);   // sHX / sH1 are rewritten by the next tile
+        }
     }
 }
 
