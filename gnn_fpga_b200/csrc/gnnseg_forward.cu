@@ -14,6 +14,7 @@
 //     layers + the next step's projection of the previous tile as register-tiled fp32 GEMMs
 //     against weights resident in shared memory.  HX' = [H' | X] is written back (the
 //     reference's cat([H, X]), gnn/model.py:146,154) together with P'.
+#include <cstdlib>
 #include "gnnseg_common.cuh"
 
 namespace gnnseg {
@@ -143,8 +144,10 @@ struct NodeCfg {
     static constexpr int SM   = tile_stride(K1);     // [mi|mo|self] tile stride
     static constexpr int SH   = tile_stride(H);      // hidden-layer tile stride
     static constexpr int SD   = tile_stride(D4);     // HX tile stride
+    static constexpr int CAP  = (H >= 64) ? 1024 : 512;   // staged CSR slots per direction per tile
     static constexpr int W_FLOATS = K1 * H + H * H + D4 * 2 * H + 3 * H;
-    static constexpr int SMEM_FLOATS = W_FLOATS + TN * (NBUF * SM + SH + SD);
+    static constexpr int STAGE_WORDS = 2 * 2 * CAP + 2 * (TN + 4);   // (nbr,w) pairs + row pointers
+    static constexpr int SMEM_FLOATS = W_FLOATS + TN * (NBUF * SM + SH + SD) + STAGE_WORDS;
     static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
 };
 
@@ -296,36 +299,69 @@ __device__ __forceinline__ void bar_arrive(const int id, const int n) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
-// One CSR row, G lanes per node (lane c owns float4 chunk c of the hidden part, lane 0 also the
-// X chunk).  The lanes first fetch up to G (neighbour, weight) pairs of the row in parallel
-// (coalesced index loads, one dependent gather of e), then every pair is broadcast through the
-// group and its feature row is gathered, ascending slot order: acc += e[eid[s]] * HX[nbr[s]].
-// All control flow is warp-uniform (trip counts are maxima over the warp) so the shuffles are
-// legal; absent work is predicated off.
+// One CSR row, G lanes per node: acc += w_s * HX[nbr_s] for the row's slots in ascending
+// order.  Lane c owns float4 chunk c of the hidden part; the X chunk (4 floats) is spread over
+// the lanes as scalars when the group has >= 4 lanes (lane c takes X[c & 3]), else lane 0 takes
+// it as one float4.  STAGED: the (neighbour, weight) pairs of the whole tile were fetched into
+// shared memory beforehand by coalesced loads, so the only global latency left in this loop is
+// the row gather itself.  Slots go in batches of U: all U row loads are issued before the
+// first FMA (no branch in between: an absent neighbour loads row 0 and is dropped by
+// predication), the FMAs then run in ascending slot order.
 template <int H>
-__device__ __forceinline__ void csr_row_sum(const int32_t* __restrict__ eid,
-                                            const int32_t* __restrict__ nbr,
-                                            const float* __restrict__ e,
-                                            const float* __restrict__ HX, const int beg,
-                                            const int cnt, const int max_cnt, const int c,
-                                            float4& acc_h, float4& acc_x) {
-    constexpr int D4 = H + 4, G = H / 4;
-    for (int base = 0; base < max_cnt; base += G) {
-        const bool ok = base + c < cnt;
-        const int s = beg + base + c;
-        const int nb = ok ? __ldg(nbr + s) : -1;
-        const float w = ok ? __ldg(e + __ldg(eid + s)) : 0.f;
-        const int m = min(G, max_cnt - base);
-#pragma unroll 4
-        for (int j = 0; j < m; ++j) {
-            const int nbj = __shfl_sync(0xffffffffu, nb, j, G);
-            const float wj = __shfl_sync(0xffffffffu, w, j, G);
-            if (nbj >= 0) {   // a half edge (absent other end) gathers the zero row
-                const float* row = HX + (size_t)nbj * D4;
-                fma4(acc_h, wj, ldg4(row + 4 * c));
-                if (c == 0) fma4(acc_x, wj, ldg4(row + H));
+struct XAcc {   // per-lane accumulator of the X chunk
+    static constexpr bool SCALAR = (H / 4) >= 4;
+    float4 v;
+};
+
+template <int H, bool STAGED>
+__device__ __forceinline__ void csr_row_sum(const int2* __restrict__ pairs, const int32_t* __restrict__ eid,
+                                            const int32_t* __restrict__ nbr, const float* __restrict__ e,
+                                            const float* __restrict__ HX, const int beg, const int end,
+                                            const int c, float4& acc_h, float4& acc_x) {
+    constexpr bool SCALAR_X = XAcc<H>::SCALAR;
+    constexpr int D4 = H + 4, U = SCALAR_X ? 4 : 2;
+    for (int s0 = beg; s0 < end; s0 += U) {
+        float w[U];
+        bool ok[U];
+        float4 vh[U];
+        float4 vx4[SCALAR_X ? 1 : U];
+        float vx1[SCALAR_X ? U : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int s = min(s0 + u, end - 1);
+            int nb;
+            if (STAGED) {
+                const int2 pr = pairs[s];
+                nb = pr.x;
+                w[u] = __int_as_float(pr.y);
+            } else {
+                nb = __ldg(nbr + s);
+                w[u] = __ldg(e + __ldg(eid + s));
+            }
+            ok[u] = (s0 + u < end) && nb >= 0;   // nb < 0: half edge, gathers the zero row
+            const float* row = HX + (size_t)max(nb, 0) * D4;
+            vh[u] = ldg4(row + 4 * c);
+            if (SCALAR_X) vx1[u] = __ldg(row + H + (c & 3));
+            else if (c == 0) vx4[u] = ldg4(row + H);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ok[u]) {
+                fma4(acc_h, w[u], vh[u]);
+                if (SCALAR_X) acc_x.x = fmaf(w[u], vx1[u], acc_x.x);
+                else if (c == 0) fma4(acc_x, w[u], vx4[u]);
             }
         }
+    }
+}
+
+// Store the X-chunk accumulator of csr_row_sum into a tile row.
+template <int H>
+__device__ __forceinline__ void store_x_acc(float* __restrict__ dst, const int c, const float4& acc_x) {
+    if (XAcc<H>::SCALAR) {
+        if (c < 4) dst[c] = acc_x.x;
+    } else if (c == 0) {
+        st4(dst, acc_x);
     }
 }
 
@@ -333,12 +369,12 @@ template <int H>
 __global__ void __launch_bounds__(NodeCfg<H>::NT, NodeCfg<H>::MINB)
 node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
             const float* __restrict__ HX_in, const float* __restrict__ e, const int n_tiles,
-            float* __restrict__ HX_out, float* __restrict__ P_out) {
+            float* __restrict__ HX_out, float* __restrict__ P_out, const int dbg) {
     using C = NodeCfg<H>;
     using B = Blob<H>;
     constexpr int TN = C::TN, NT = C::NT, CT = C::CT, PT = C::PT, NBUF = C::NBUF;
     constexpr int D4 = C::D4, K1 = C::K1, SM = C::SM, SH = C::SH, SD = C::SD;
-    constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_CONS = 1 + 2 * NBUF;
+    constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_CONS = 1 + 2 * NBUF, BAR_PROD = 2 + 2 * NBUF;
     extern __shared__ __align__(16) float smem[];
     float* sW3 = smem;                  // [K1][H]
     float* sB3 = sW3 + K1 * H;          // [H]
@@ -349,6 +385,8 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
     float* sM  = sB1 + H;               // [NBUF][TN][SM]   [mi | mo | self]
     float* sH1 = sM + NBUF * TN * SM;   // [TN][SH]
     float* sHX = sH1 + TN * SH;         // [TN][SD]
+    int2* sPair = reinterpret_cast<int2*>(sHX + TN * SD);          // [2][CAP] (nbr, w) in / out
+    int*  sPtr  = reinterpret_cast<int*>(sPair + 2 * C::CAP);      // [2][TN+4] row pointers in / out
     copy_to_smem<NT>(sW3, blob + B::W3, K1 * H + H + H * H + H);   // W3,b3,W4,b4 contiguous
     copy_to_smem<NT>(sW1, blob + B::W1, D4 * 2 * H + H);           // W1,b1 contiguous
     __syncthreads();
@@ -358,41 +396,63 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
         // ================================ producers ====================================
         constexpr int G = H / 4;            // lanes per node
         constexpr int NGRP = PT / G;        // nodes gathered concurrently
+        constexpr int CAP = C::CAP;
         const int pt = threadIdx.x - CT;
         const int grp = pt / G, c = pt % G;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int buf = it % NBUF;
+            const int node0 = tile * TN;
+            // ---- stage the tile's CSR slices: row pointers, then (neighbour, weight) pairs ----
+            bar_sync(BAR_PROD, PT);                            // previous tile's readers are done
+            if (pt <= TN) {
+                const int n = min(node0 + pt, n_nodes);
+                sPtr[pt] = __ldg(g.in_ptr + n);
+                sPtr[TN + 4 + pt] = __ldg(g.out_ptr + n);
+            }
+            bar_sync(BAR_PROD, PT);
+            const int ib = sPtr[0], ic = sPtr[TN] - ib;
+            const int ob = sPtr[TN + 4], oc = sPtr[TN + 4 + TN] - ob;
+            const bool staged = ic <= CAP && oc <= CAP;       // CTA-uniform
+            if (staged) {
+                for (int s = pt; s < ic; s += PT)
+                    sPair[s] = make_int2(__ldg(g.in_nbr + ib + s), __float_as_int(__ldg(e + __ldg(g.in_eid + ib + s))));
+                for (int s = pt; s < oc; s += PT)
+                    sPair[CAP + s] = make_int2(__ldg(g.out_nbr + ob + s), __float_as_int(__ldg(e + __ldg(g.out_eid + ob + s))));
+            }
+            bar_sync(BAR_PROD, PT);
             if (it >= NBUF) bar_sync(BAR_EMPTY + buf, NT);     // consumers are done with this buffer
             float* sMb = sM + buf * TN * SM;
-            const int node0 = tile * TN;
-            if (grp < TN) {                                    // warp-uniform (G divides 32)
-                for (int ln = grp; ln < TN; ln += NGRP) {
-                    const int n = node0 + ln;
-                    const bool live = n < n_nodes;
-                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 mi_h = zero, mi_x = zero, mo_h = zero, mo_x = zero, se_h = zero, se_x = zero;
-                    int ib = 0, ic = 0, ob = 0, oc = 0;
+            for (int ln = grp; ln < TN; ln += NGRP) {
+                const int n = node0 + ln;
+                const bool live = n < n_nodes && !(dbg & 1);
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                float* m = sMb + ln * SM;
+                const int i0 = sPtr[ln], i1 = live ? sPtr[ln + 1] : i0;
+                const int o0 = sPtr[TN + 4 + ln], o1 = live ? sPtr[TN + 4 + ln + 1] : o0;
+                {   // mi: sum over in-edges of e * HX[src]
+                    float4 a_h = zero, a_x = zero;
+                    if (staged) csr_row_sum<H, true>(sPair, nullptr, nullptr, nullptr, HX_in, i0 - ib, i1 - ib, c, a_h, a_x);
+                    else        csr_row_sum<H, false>(nullptr, g.in_eid, g.in_nbr, e, HX_in, i0, i1, c, a_h, a_x);
+                    st4(m + 4 * c, a_h);
+                    store_x_acc<H>(m + H, c, a_x);
+                }
+                {   // mo: sum over out-edges of e * HX[dst]
+                    float4 a_h = zero, a_x = zero;
+                    if (staged) csr_row_sum<H, true>(sPair + CAP, nullptr, nullptr, nullptr, HX_in, o0 - ob, o1 - ob, c, a_h, a_x);
+                    else        csr_row_sum<H, false>(nullptr, g.out_eid, g.out_nbr, e, HX_in, o0, o1, c, a_h, a_x);
+                    st4(m + D4 + 4 * c, a_h);
+                    store_x_acc<H>(m + D4 + H, c, a_x);
+                }
+                {   // the node's own row
+                    float4 a_h = zero, a_x = zero;
                     if (live) {
-                        ib = __ldg(g.in_ptr + n);  ic = __ldg(g.in_ptr + n + 1) - ib;
-                        ob = __ldg(g.out_ptr + n); oc = __ldg(g.out_ptr + n + 1) - ob;
                         const float* row = HX_in + (size_t)n * D4;
-                        se_h = ldg4(row + 4 * c);
-                        if (c == 0) se_x = ldg4(row + H);
+                        a_h = ldg4(row + 4 * c);
+                        if (c == 0) a_x = ldg4(row + H);
                     }
-                    const int imax = __reduce_max_sync(0xffffffffu, ic);
-                    const int omax = __reduce_max_sync(0xffffffffu, oc);
-                    csr_row_sum<H>(g.in_eid, g.in_nbr, e, HX_in, ib, ic, imax, c, mi_h, mi_x);
-                    csr_row_sum<H>(g.out_eid, g.out_nbr, e, HX_in, ob, oc, omax, c, mo_h, mo_x);
-                    float* m = sMb + ln * SM;
-                    st4(m + 4 * c, mi_h);
-                    st4(m + D4 + 4 * c, mo_h);
-                    st4(m + 2 * D4 + 4 * c, se_h);
-                    if (c == 0) {
-                        st4(m + H, mi_x);
-                        st4(m + D4 + H, mo_x);
-                        st4(m + 2 * D4 + H, se_x);
-                    }
+                    st4(m + 2 * D4 + 4 * c, a_h);
+                    if (c == 0) st4(m + 2 * D4 + H, a_x);
                 }
             }
             bar_arrive(BAR_FULL + buf, NT);
@@ -405,6 +465,11 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
             const int node0 = tile * TN;
             const float* sMb = sM + buf * TN * SM;
             bar_sync(BAR_FULL + buf, NT);                      // the tile's rows are in sMb
+            if (dbg & 2) {
+                bar_sync(BAR_CONS, CT);
+                if (tile + NBUF * (int)gridDim.x < n_tiles) bar_arrive(BAR_EMPTY + buf, NT);
+                continue;
+            }
             // ---- layer 0: h1 = tanh(W3 . [mi; mo; self] + b3) ---------------------------
             tile_gemm<K1, H, TN, CT, C::RN1, 4>(sMb, SM, sW3, [&](int ln, int o, const float* acc) {
                 const float4 b = lds4(sB3 + o);
@@ -492,7 +557,8 @@ static int launch_node(const float* blob, const GnnsegGraph* g, const float* HX_
     int grid = 0;
     const int rc = persistent_grid(node_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);
     if (rc) return rc;
-    node_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, HX_in, e, n_tiles, HX_out, P_out);
+    const char* dbg_env = getenv("GNNSEG_DBG");
+    node_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, HX_in, e, n_tiles, HX_out, P_out, dbg_env ? atoi(dbg_env) : 0);
     return check_launch();
 }
 
