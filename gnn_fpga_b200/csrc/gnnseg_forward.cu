@@ -125,6 +125,14 @@ __device__ __forceinline__ void copy_to_smem(float* __restrict__ dst, const floa
     for (int i = threadIdx.x * 4; i < n_floats; i += NT * 4) st4(dst + i, ldg4(src + i));
 }
 
+// Smallest stride >= k (floats) whose rows, read 8 bytes per lane by the mma fragments
+// (4 rows x 4 lanes per half warp), fall on disjoint bank groups: stride mod 32 in {8, 24}.
+__host__ __device__ constexpr int mma_stride(int k) {
+    int s = (k + 7) / 8 * 8;
+    while (s % 32 != 8 && s % 32 != 24) s += 8;
+    return s;
+}
+
 // Kernel shape per hidden size.
 template <int H>
 struct NodeCfg {
@@ -134,18 +142,24 @@ struct NodeCfg {
     static constexpr int CT   = CW * 32;
     static constexpr int PT   = PW * 32;
     static constexpr int NT   = CT + PT;             // threads per CTA
-    static constexpr int NBUF = (H >= 64) ? 1 : 2;   // [mi|mo|self] tile buffers
+    static constexpr bool MMA = H >= 32;             // tensor-core (3xTF32) MLP; SIMT below that
+    static constexpr int NBUF = MMA ? 1 : 2;         // [mi|mo|self] tile buffers
     static constexpr int MINB = (H >= 64) ? 1 : 2;   // CTAs per SM the register budget allows
-    static constexpr int RN1  = (H >= 64) ? 4 : 2;   // nodes per thread, layers with H outputs
-    static constexpr int RNP  = 4;                   // nodes per thread, projection (2H outputs)
-    static constexpr int RCP  = (H >= 64) ? 8 : 4;   // outputs per thread, projection
+    static constexpr int RN1  = 2;                   // SIMT path: nodes per thread, H outputs
+    static constexpr int RNP  = 4;                   // SIMT path: nodes per thread, projection
+    static constexpr int RCP  = 4;                   // SIMT path: outputs per thread, projection
     static constexpr int D4   = H + 4;
     static constexpr int K1   = 3 * D4;
-    static constexpr int SM   = tile_stride(K1);     // [mi|mo|self] tile stride
-    static constexpr int SH   = tile_stride(H);      // hidden-layer tile stride
-    static constexpr int SD   = tile_stride(D4);     // HX tile stride
+    static constexpr int K1P  = (K1 + 7) / 8 * 8;    // MMA path: K padded to the k8 step
+    static constexpr int D4P  = (D4 + 7) / 8 * 8;
+    static constexpr int SM   = MMA ? mma_stride(K1P) : tile_stride(K1);   // [mi|mo|self] tile stride
+    static constexpr int SH   = MMA ? mma_stride(H) : tile_stride(H);      // hidden-layer tile stride
+    static constexpr int SD   = MMA ? mma_stride(D4P) : tile_stride(D4);   // HX tile stride
     static constexpr int CAP  = (H >= 64) ? 1024 : 512;   // staged CSR slots per direction per tile
-    static constexpr int W_FLOATS = K1 * H + H * H + D4 * 2 * H + 3 * H;
+    // weights in shared memory: SIMT keeps the blob's [k][out]; MMA wants [out][k] rows with the
+    // same padded strides as the A tiles
+    static constexpr int W_FLOATS = MMA ? (H * SM + H * SH + 2 * H * SD + 3 * H)
+                                        : (K1 * H + H * H + D4 * 2 * H + 3 * H);
     static constexpr int STAGE_WORDS = 2 * 2 * CAP + 2 * (TN + 4);   // (nbr,w) pairs + row pointers
     static constexpr int SMEM_FLOATS = W_FLOATS + TN * (NBUF * SM + SH + SD) + STAGE_WORDS;
     static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
@@ -292,6 +306,93 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
 // The two halves meet through named barriers (full/empty per tile buffer), so the gather of
 // tile t+1 overlaps the MLP of tile t on the same SM.
 // ------------------------------------------------------------------------------------
+// ---- 3xTF32 tensor-core GEMM on fp32 operands held in shared memory --------------------------
+// x = hi + lo with hi = tf32(x), lo = tf32(x - hi); a.b ~= lo_a.hi_b + hi_a.lo_b + hi_a.hi_b with
+// fp32 accumulation, which keeps the result within a few 1e-7 of the fp32 FMA chain (the
+// dropped lo.lo term is 2^-22 relative).  One warp computes MT x NT tiles of 16 nodes x 8 outputs.
+// A: [rows][lda] fp32 (row = node, k contiguous); B: [cols][ldb] fp32 (row = output, k contiguous).
+// Fragment slots: lane (g = lane/4, t = lane%4) supplies logical k = 8q+2t and 8q+2t+1 for the
+// instruction's k-slots t and t+4 of both A and B, so each fragment is one 8-byte load.
+__device__ __forceinline__ uint32_t to_tf32(const float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(const float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+template <int KB, int MT, int NT>
+__device__ __forceinline__ void warp_gemm_3xtf32(const float* __restrict__ sA, const int lda,
+                                                 const float* __restrict__ sB, const int ldb,
+                                                 float (&acc)[MT][NT][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float* pa = sA + g * lda + 2 * t;
+    const float* pb = sB + g * ldb + 2 * t;
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = acc[mi][ni][2] = acc[mi][ni][3] = 0.f;
+#pragma unroll 2
+    for (int q = 0; q < KB; ++q) {
+        uint32_t ahi[MT][4], alo[MT][4], bhi[NT][2], blo[NT][2];
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+            const float2 r0 = lds2(pa + (mi * 16) * lda + 8 * q);       // row g
+            const float2 r1 = lds2(pa + (mi * 16 + 8) * lda + 8 * q);   // row g + 8
+            split_tf32(r0.x, ahi[mi][0], alo[mi][0]);
+            split_tf32(r1.x, ahi[mi][1], alo[mi][1]);
+            split_tf32(r0.y, ahi[mi][2], alo[mi][2]);
+            split_tf32(r1.y, ahi[mi][3], alo[mi][3]);
+        }
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+            const float2 r = lds2(pb + (ni * 8) * ldb + 8 * q);
+            split_tf32(r.x, bhi[ni][0], blo[ni][0]);
+            split_tf32(r.y, bhi[ni][1], blo[ni][1]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) {
+                mma_m16n8k8_tf32(acc[mi][ni], alo[mi], bhi[ni]);
+                mma_m16n8k8_tf32(acc[mi][ni], ahi[mi], blo[ni]);
+                mma_m16n8k8_tf32(acc[mi][ni], ahi[mi], bhi[ni]);
+            }
+    }
+}
+
+// Tile GEMM of the 8 consumer warps: out[TN=64][HOUT] = A[64][8*KB] . B[HOUT][8*KB]^T.  The warps
+// form a WM x WN grid; epi(row, col, v0, v1) receives two adjacent outputs (col, col+1).
+template <int KB, int HOUT, typename Epi>
+__device__ __forceinline__ void tile_gemm_mma(const float* __restrict__ sA, const int lda,
+                                              const float* __restrict__ sB, const int ldb, Epi epi) {
+    constexpr int MTILES = 4, NTILES = HOUT / 8;          // 16-node x 8-output tiles
+    constexpr int WN = NTILES >= 8 ? 4 : 2, WM = 8 / WN;  // warp grid
+    constexpr int MT = MTILES / WM, NT = NTILES / WN;
+    static_assert(MT >= 1 && NT >= 1 && MT * WM == MTILES && NT * WN == NTILES, "warp tiling");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int m0 = (warp / WN) * MT * 16, n0 = (warp % WN) * NT * 8;
+    float acc[MT][NT][4];
+    warp_gemm_3xtf32<KB, MT, NT>(sA + m0 * lda, lda, sB + n0 * ldb, ldb, acc);
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+            const int r = m0 + mi * 16 + g, cidx = n0 + ni * 8 + 2 * t;
+            epi(r, cidx, acc[mi][ni][0], acc[mi][ni][1]);
+            epi(r + 8, cidx, acc[mi][ni][2], acc[mi][ni][3]);
+        }
+}
+
 __device__ __forceinline__ void bar_sync(const int id, const int n) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
@@ -374,21 +475,47 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
     using B = Blob<H>;
     constexpr int TN = C::TN, NT = C::NT, CT = C::CT, PT = C::PT, NBUF = C::NBUF;
     constexpr int D4 = C::D4, K1 = C::K1, SM = C::SM, SH = C::SH, SD = C::SD;
+    constexpr bool MMA = C::MMA;
     constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_CONS = 1 + 2 * NBUF, BAR_PROD = 2 + 2 * NBUF;
     extern __shared__ __align__(16) float smem[];
-    float* sW3 = smem;                  // [K1][H]
-    float* sB3 = sW3 + K1 * H;          // [H]
-    float* sW4 = sB3 + H;               // [H][H]
-    float* sB4 = sW4 + H * H;           // [H]
-    float* sW1 = sB4 + H;               // [D4][2H]
-    float* sB1 = sW1 + D4 * 2 * H;      // [H]
+    // weights: SIMT path [k][out] as in the blob, MMA path [out][k] with padded row strides
+    float* sW3 = smem;                                     // SIMT [K1][H]    | MMA [H][SM]
+    float* sB3 = sW3 + (MMA ? H * SM : K1 * H);            // [H]
+    float* sW4 = sB3 + H;                                  // SIMT [H][H]     | MMA [H][SH]
+    float* sB4 = sW4 + (MMA ? H * SH : H * H);             // [H]
+    float* sW1 = sB4 + H;                                  // SIMT [D4][2H]   | MMA [2H][SD]
+    float* sB1 = sW1 + (MMA ? 2 * H * SD : D4 * 2 * H);    // [H]
     float* sM  = sB1 + H;               // [NBUF][TN][SM]   [mi | mo | self]
     float* sH1 = sM + NBUF * TN * SM;   // [TN][SH]
     float* sHX = sH1 + TN * SH;         // [TN][SD]
     int2* sPair = reinterpret_cast<int2*>(sHX + TN * SD);          // [2][CAP] (nbr, w) in / out
     int*  sPtr  = reinterpret_cast<int*>(sPair + 2 * C::CAP);      // [2][TN+4] row pointers in / out
-    copy_to_smem<NT>(sW3, blob + B::W3, K1 * H + H + H * H + H);   // W3,b3,W4,b4 contiguous
-    copy_to_smem<NT>(sW1, blob + B::W1, D4 * 2 * H + H);           // W1,b1 contiguous
+    if (MMA) {
+        // transpose the blob's [k][out] matrices into [out][k] rows; k beyond the real width is 0
+        for (int i = threadIdx.x; i < H * SM; i += NT) {
+            const int j = i / SM, k = i % SM;
+            sW3[i] = k < K1 ? __ldg(blob + B::W3 + k * H + j) : 0.f;
+        }
+        for (int i = threadIdx.x; i < H * SH; i += NT) {
+            const int j = i / SH, k = i % SH;
+            sW4[i] = k < H ? __ldg(blob + B::W4 + k * H + j) : 0.f;
+        }
+        for (int i = threadIdx.x; i < 2 * H * SD; i += NT) {
+            const int j = i / SD, k = i % SD;
+            sW1[i] = k < D4 ? __ldg(blob + B::W1 + k * 2 * H + j) : 0.f;
+        }
+        for (int i = threadIdx.x; i < H; i += NT) {
+            sB3[i] = __ldg(blob + B::B3 + i);
+            sB4[i] = __ldg(blob + B::B4 + i);
+            sB1[i] = __ldg(blob + B::B1 + i);
+        }
+        // zero the K padding of the A tiles once: nobody writes those columns afterwards
+        for (int i = threadIdx.x; i < NBUF * TN * (SM - K1); i += NT) sM[(i / (SM - K1)) * SM + K1 + i % (SM - K1)] = 0.f;
+        for (int i = threadIdx.x; i < TN * (SD - D4); i += NT) sHX[(i / (SD - D4)) * SD + D4 + i % (SD - D4)] = 0.f;
+    } else {
+        copy_to_smem<NT>(sW3, blob + B::W3, K1 * H + H + H * H + H);   // W3,b3,W4,b4 contiguous
+        copy_to_smem<NT>(sW1, blob + B::W1, D4 * 2 * H + H);           // W1,b1 contiguous
+    }
     __syncthreads();
     const int n_nodes = g.n_nodes;
 
@@ -471,24 +598,53 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
                 continue;
             }
             // ---- layer 0: h1 = tanh(W3 . [mi; mo; self] + b3) ---------------------------
-            tile_gemm<K1, H, TN, CT, C::RN1, 4>(sMb, SM, sW3, [&](int ln, int o, const float* acc) {
-                const float4 b = lds4(sB3 + o);
-                st4(sH1 + ln * SH + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
-                                                   tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
-            });
+            if constexpr (MMA) {
+                tile_gemm_mma<C::K1P / 8, H>(sMb, SM, sW3, SM, [&](int ln, int o, float v0, float v1) {
+                    *reinterpret_cast<float2*>(sH1 + ln * SH + o) =
+                        make_float2(tanhf(v0 + sB3[o]), tanhf(v1 + sB3[o + 1]));
+                });
+            } else {
+                tile_gemm<K1, H, TN, CT, C::RN1, 4>(sMb, SM, sW3, [&](int ln, int o, const float* acc) {
+                    const float4 b = lds4(sB3 + o);
+                    st4(sH1 + ln * SH + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
+                                                       tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
+                });
+            }
             // the X part of the new HX row is the old one (self block of the tile)
             for (int i = threadIdx.x; i < TN; i += CT) st4(sHX + i * SD + H, lds4(sMb + i * SM + 2 * D4 + H));
             bar_sync(BAR_CONS, CT);
             if (tile + NBUF * (int)gridDim.x < n_tiles) bar_arrive(BAR_EMPTY + buf, NT);   // release sMb
             // ---- layer 2: H' = tanh(W4 . h1 + b4) ---------------------------------------
-            tile_gemm<H, H, TN, CT, C::RN1, 4>(sH1, SH, sW4, [&](int ln, int o, const float* acc) {
-                const float4 b = lds4(sB4 + o);
-                st4(sHX + ln * SD + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
-                                                   tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
-            });
+            if constexpr (MMA) {
+                tile_gemm_mma<H / 8, H>(sH1, SH, sW4, SH, [&](int ln, int o, float v0, float v1) {
+                    *reinterpret_cast<float2*>(sHX + ln * SD + o) =
+                        make_float2(tanhf(v0 + sB4[o]), tanhf(v1 + sB4[o + 1]));
+                });
+            } else {
+                tile_gemm<H, H, TN, CT, C::RN1, 4>(sH1, SH, sW4, [&](int ln, int o, const float* acc) {
+                    const float4 b = lds4(sB4 + o);
+                    st4(sHX + ln * SD + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
+                                                       tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
+                });
+            }
             bar_sync(BAR_CONS, CT);
             // ---- write HX' and the projection for the next edge step ---------------------
-            store_hx_and_project<H, TN, CT, C::RNP, C::RCP>(sHX, SD, sW1, sB1, node0, n_nodes, HX_out, P_out);
+            if constexpr (MMA) {
+                constexpr int C4 = D4 / 4;
+                for (int i = threadIdx.x; i < TN * C4; i += CT) {
+                    const int ln = i / C4, c = i % C4, n = node0 + ln;
+                    if (n < n_nodes) st4(HX_out + (size_t)n * D4 + 4 * c, lds4(sHX + ln * SD + 4 * c));
+                }
+                tile_gemm_mma<C::D4P / 8, 2 * H>(sHX, SD, sW1, SD, [&](int ln, int o, float v0, float v1) {
+                    const int n = node0 + ln;
+                    if (n < n_nodes) {
+                        if (o < H) { v0 += sB1[o]; v1 += sB1[o + 1]; }
+                        *reinterpret_cast<float2*>(P_out + (size_t)n * 2 * H + o) = make_float2(v0, v1);
+                    }
+                });
+            } else {
+                store_hx_and_project<H, TN, CT, C::RNP, C::RCP>(sHX, SD, sW1, sB1, node0, n_nodes, HX_out, P_out);
+            }
             bar_sync(BAR_CONS, CT);   // sHX / sH1 are rewritten by the next tile
         }
     }
