@@ -704,11 +704,18 @@ static int launch_edge(const float* blob, const GnnsegGraph* g, const float* P, 
     return check_launch();
 }
 
+int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* HX_in, const float* e,
+                     float* HX_out, float* P_out, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
+
 template <int H>
 static int launch_node(const float* blob, const GnnsegGraph* g, const float* HX_in, const float* e,
                        float* HX_out, float* P_out, cudaStream_t st) {
     using C = NodeCfg<H>;
     if (g->n_nodes == 0) return GNNSEG_OK;
+    if (H == 32) {
+        const char* impl = getenv("GNNSEG_NODE_IMPL");   // "mma": legacy mma.sync path (for A/B runs)
+        if (!impl || impl[0] != 'm') return launch_node_tc32(blob, g, HX_in, e, HX_out, P_out, st);
+    }
     const int n_tiles = (g->n_nodes + C::TN - 1) / C::TN;
     int grid = 0;
     const int rc = persistent_grid(node_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);
