@@ -155,7 +155,7 @@ struct NodeCfg {
     static constexpr int SM   = MMA ? mma_stride(K1P) : tile_stride(K1);   // [mi|mo|self] tile stride
     static constexpr int SH   = MMA ? mma_stride(H) : tile_stride(H);      // hidden-layer tile stride
     static constexpr int SD   = MMA ? mma_stride(D4P) : tile_stride(D4);   // HX tile stride
-    static constexpr int CAP  = (H >= 64) ? 1024 : 512;   // staged CSR slots per direction per tile
+    static constexpr int CAP  = (H >= 64) ? 1536 : 768;   // staged CSR slots per direction per tile
     // weights in shared memory: SIMT keeps the blob's [k][out]; MMA wants [out][k] rows with the
     // same padded strides as the A tiles
     static constexpr int W_FLOATS = MMA ? (H * SM + H * SH + 2 * H * SD + 3 * H)

@@ -11,9 +11,11 @@
 // a.b ~= lo_a.hi_b + hi_a.lo_b + hi_a.hi_b, all three accumulated into the same TMEM tile.
 //
 // Data flow per 128-node tile (one CTA per SM, persistent):
-//   producers (16 warps)  gather -> A1_hi / A1_lo in shared memory, canonical K-major layout
+//   stagers (4 warps)     CSR slices of the tile after next -> (neighbour, weight) pairs in smem
+//   gather  (16 warps)    4 lanes per node: row gather -> A1_hi / A1_lo in shared memory,
+//                         canonical K-major core-matrix layout
 //   thread 0              GEMM1 (SS: A1 from smem, W3 from smem) -> D1 in TMEM, commit -> mbarrier
-//   epilogue (8 warps)    D1 -> regs -> +b3, tanh, split -> A2_hi / A2_lo in TMEM
+//   epilogue (4 warps)    D1 -> regs -> +b3, tanh, split -> A2_hi / A2_lo in TMEM
 //   thread 0              GEMM2 (TS: A2 from TMEM, W4 from smem) -> D2
 //   epilogue              D2 -> +b4, tanh -> HX' to global; split, with X and zero pad -> A3 in TMEM
 //   thread 0              GEMM3 (TS) -> D3
@@ -28,11 +30,16 @@ namespace gnnseg {
 template <int H>
 struct TcCfg {
     static constexpr int TM   = 128;                 // nodes per tile = UMMA M
-    static constexpr int EW   = 8;                   // epilogue warps (warps 0..7)
-    static constexpr int PW   = 16;                  // producer warps
+    static constexpr int EW   = 4;                   // MLP warps (issuer + epilogue): warp w owns TMEM lanes 32w..32w+31
+    static constexpr int SW   = 4;                   // stager warps: CSR slices of the NEXT tile -> shared memory
+    static constexpr int GW   = 16;                  // gather warps: 4 lanes per node, the whole tile at once
     static constexpr int ET   = EW * 32;
-    static constexpr int PT   = PW * 32;
-    static constexpr int NT   = ET + PT;
+    static constexpr int ST   = SW * 32;
+    static constexpr int GT   = GW * 32;
+    static constexpr int NT   = ET + ST + GT;
+    static constexpr int G    = 4;                   // lanes per node in the gather
+    static_assert(GT / G == TM, "one gather group per node of the tile");
+    static_assert(H == 32, "the gather lane map (2 float4 + 1 scalar per lane) is written for H = 32");
     static constexpr int D4   = H + 4;
     static constexpr int K1   = 3 * D4;
     static constexpr int K1P  = (K1 + 7) / 8 * 8;    // K of GEMM1, padded to the tf32 k-step
@@ -47,7 +54,7 @@ struct TcCfg {
     static constexpr int W3_BYTES = (H / 8) * SBO_K1;
     static constexpr int W4_BYTES = (H / 8) * SBO_H;
     static constexpr int W1_BYTES = (2 * H / 8) * SBO_D4;
-    static constexpr int CAP  = 1024;                // staged CSR slots per direction per tile
+    static constexpr int CAP  = 1536;                // staged CSR slots per direction per tile
     // shared memory map (bytes)
     static constexpr int O_A1H = 0;
     static constexpr int O_A1L = O_A1H + A1_BYTES;
@@ -58,9 +65,9 @@ struct TcCfg {
     static constexpr int O_W1H = O_W4L + W4_BYTES;
     static constexpr int O_W1L = O_W1H + W1_BYTES;
     static constexpr int O_BIAS = O_W1L + W1_BYTES;          // b3, b4, b1
-    static constexpr int O_PAIR = O_BIAS + 3 * H * 4;        // [2][CAP] int2
-    static constexpr int O_PTR  = O_PAIR + 2 * CAP * 8;      // [2][TM+4] int
-    static constexpr int O_MBAR = O_PTR + 2 * (TM + 4) * 4;  // mbarrier (8 B) + tmem base (4 B)
+    static constexpr int STAGE_BYTES = 2 * CAP * 8 + 2 * (TM + 4) * 4;   // [2][CAP] int2 + [2][TM+4] int
+    static constexpr int O_STAGE = O_BIAS + 3 * H * 4;       // two staging buffers (double buffered)
+    static constexpr int O_MBAR = O_STAGE + 2 * STAGE_BYTES; // mbarrier (8 B) + tmem base (4 B)
     static constexpr int SMEM_BYTES = O_MBAR + 16;
     // tensor memory columns (fp32 cells, 128 lanes)
     static constexpr int C_D1  = 0;
@@ -178,68 +185,91 @@ __device__ __forceinline__ int canon_off(const int row, const int k, const int s
 }
 
 // One CSR row of the gather (same contract as csr_row_sum in gnnseg_forward.cu, staged form):
-// lane c of the node's 8-lane group owns float4 chunk c of the hidden part and X[c & 3].
+// lane c of the node's 4-lane group owns float4 chunks c and c+4 of the hidden part and X[c].
+// Slots go in batches of U: every row load of the batch is issued before the first FMA (no
+// branch in between: an absent neighbour loads row 0 and is dropped by predication), then the
+// FMAs run in ascending slot order.
 template <int H>
 __device__ __forceinline__ void tc_row_sum(const int2* __restrict__ pairs, const float* __restrict__ HX,
-                                           const int beg, const int end, const int c, float4& acc_h,
-                                           float& acc_x) {
+                                           const int beg, const int end, const int c, float4& acc0,
+                                           float4& acc1, float& acc_x) {
     constexpr int D4 = H + 4, U = 4;
     for (int s0 = beg; s0 < end; s0 += U) {
         float w[U], vx[U];
         bool ok[U];
-        float4 vh[U];
+        float4 v0[U], v1[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int2 pr = pairs[min(s0 + u, end - 1)];
             w[u] = __int_as_float(pr.y);
             ok[u] = (s0 + u < end) && pr.x >= 0;     // pr.x < 0: half edge, gathers the zero row
             const float* row = HX + (size_t)max(pr.x, 0) * D4;
-            vh[u] = ldg4(row + 4 * c);
-            vx[u] = __ldg(row + H + (c & 3));
+            v0[u] = ldg4(row + 4 * c);
+            v1[u] = ldg4(row + 16 + 4 * c);
+            vx[u] = __ldg(row + H + c);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (ok[u]) {
-                fma4(acc_h, w[u], vh[u]);
+                fma4(acc0, w[u], v0[u]);
+                fma4(acc1, w[u], v1[u]);
                 acc_x = fmaf(w[u], vx[u], acc_x);
             }
     }
 }
-// Slow path for a tile whose CSR slice does not fit the staging buffer.
+// Path for a tile whose CSR slice does not fit the staging buffer: same batching, but the
+// (neighbour, weight) pairs come straight from global memory (one more dependent load level).
 template <int H>
 __device__ __forceinline__ void tc_row_sum_direct(const int32_t* __restrict__ eid, const int32_t* __restrict__ nbr,
                                                   const float* __restrict__ e, const float* __restrict__ HX,
-                                                  const int beg, const int end, const int c, float4& acc_h,
-                                                  float& acc_x) {
-    constexpr int D4 = H + 4;
-    for (int s = beg; s < end; ++s) {
-        const int nb = __ldg(nbr + s);
-        const float w = __ldg(e + __ldg(eid + s));
-        if (nb >= 0) {
-            const float* row = HX + (size_t)nb * D4;
-            fma4(acc_h, w, ldg4(row + 4 * c));
-            acc_x = fmaf(w, __ldg(row + H + (c & 3)), acc_x);
+                                                  const int beg, const int end, const int c, float4& acc0,
+                                                  float4& acc1, float& acc_x) {
+    constexpr int D4 = H + 4, U = 4;
+    for (int s0 = beg; s0 < end; s0 += U) {
+        float w[U], vx[U];
+        bool ok[U];
+        float4 v0[U], v1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int s = min(s0 + u, end - 1);
+            const int nb = __ldg(nbr + s);
+            w[u] = __ldg(e + __ldg(eid + s));
+            ok[u] = (s0 + u < end) && nb >= 0;
+            const float* row = HX + (size_t)max(nb, 0) * D4;
+            v0[u] = ldg4(row + 4 * c);
+            v1[u] = ldg4(row + 16 + 4 * c);
+            vx[u] = __ldg(row + H + c);
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (ok[u]) {
+                fma4(acc0, w[u], v0[u]);
+                fma4(acc1, w[u], v1[u]);
+                acc_x = fmaf(w[u], vx[u], acc_x);
+            }
     }
 }
-// split a row chunk and store it into A1_hi / A1_lo (canonical layout), part = 0 mi, 1 mo, 2 self
+// split the lane's share of a row part and store it into A1_hi / A1_lo (canonical layout);
+// part = 0 mi, 1 mo, 2 self
 template <int H>
 __device__ __forceinline__ void tc_store_part(unsigned char* __restrict__ a1h, unsigned char* __restrict__ a1l,
                                               const int sbo, const int ln, const int part, const int c,
-                                              const float4 h, const float x) {
+                                              const float4 h0, const float4 h1, const float x) {
     constexpr int D4 = H + 4;
-    float4 hh, hl;
-    split3(h.x, hh.x, hl.x); split3(h.y, hh.y, hl.y); split3(h.z, hh.z, hl.z); split3(h.w, hh.w, hl.w);
-    const int off = canon_off(ln, part * D4 + 4 * c, sbo);
-    *reinterpret_cast<float4*>(a1h + off) = hh;
-    *reinterpret_cast<float4*>(a1l + off) = hl;
-    if (c < 4) {
-        float xh, xl;
-        split3(x, xh, xl);
-        const int ox = canon_off(ln, part * D4 + H + c, sbo);
-        *reinterpret_cast<float*>(a1h + ox) = xh;
-        *reinterpret_cast<float*>(a1l + ox) = xl;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const float4 h = half ? h1 : h0;
+        float4 hh, hl;
+        split3(h.x, hh.x, hl.x); split3(h.y, hh.y, hl.y); split3(h.z, hh.z, hl.z); split3(h.w, hh.w, hl.w);
+        const int off = canon_off(ln, part * D4 + 16 * half + 4 * c, sbo);
+        *reinterpret_cast<float4*>(a1h + off) = hh;
+        *reinterpret_cast<float4*>(a1l + off) = hl;
     }
+    float xh, xl;
+    split3(x, xh, xl);
+    const int ox = canon_off(ln, part * D4 + H + c, sbo);
+    *reinterpret_cast<float*>(a1h + ox) = xh;
+    *reinterpret_cast<float*>(a1l + ox) = xl;
 }
 
 template <int H>
@@ -249,16 +279,16 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
                float* __restrict__ P_out) {
     using C = TcCfg<H>;
     using B = Blob<H>;
-    constexpr int TM = C::TM, NT = C::NT, ET = C::ET, PT = C::PT, D4 = C::D4, K1 = C::K1;
-    constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_EPI = 3, BAR_PROD = 4;
+    constexpr int TM = C::TM, NT = C::NT, ET = C::ET, ST = C::ST, GT = C::GT, D4 = C::D4, K1 = C::K1;
+    // named barriers: A1 full / empty (gather <-> MLP), MLP-internal, staging full / empty x2
+    // (stager <-> gather), stager-internal
+    constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_EPI = 3, BAR_SFULL = 4, BAR_SEMPTY = 6, BAR_STG = 8;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* a1h = smem + C::O_A1H;
     unsigned char* a1l = smem + C::O_A1L;
     float* sB3 = reinterpret_cast<float*>(smem + C::O_BIAS);
     float* sB4 = sB3 + H;
     float* sB1 = sB4 + H;
-    int2* sPair = reinterpret_cast<int2*>(smem + C::O_PAIR);
-    int* sPtr = reinterpret_cast<int*>(smem + C::O_PTR);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -314,69 +344,84 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (tid >= ET) {
-        // ================================ producers ====================================
-        constexpr int G = H / 4, NGRP = PT / G, CAP = C::CAP;
-        const int pt = tid - ET;
-        const int grp = pt / G, c = pt % G;
+    if (tid >= ET + ST) {
+        // ================================ gather warps ==================================
+        constexpr int CAP = C::CAP;
+        const int gt = tid - ET - ST;
+        const int ln = gt >> 2, c = gt & 3;                   // node of the tile, lane in its group
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int node0 = tile * TM;
-            tc_bar_sync(BAR_PROD, PT);                         // previous tile's staging readers done
-            if (pt <= TM) {
-                const int n = min(node0 + pt, n_nodes);
-                sPtr[pt] = __ldg(g.in_ptr + n);
-                sPtr[TM + 4 + pt] = __ldg(g.out_ptr + n);
+            const int sb = it & 1;
+            const int2* sPair = reinterpret_cast<const int2*>(smem + C::O_STAGE + sb * C::STAGE_BYTES);
+            const int* sPtr = reinterpret_cast<const int*>(smem + C::O_STAGE + sb * C::STAGE_BYTES + 2 * CAP * 8);
+            const int n = tile * TM + ln;
+            const bool live = n < n_nodes;
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+            float sx = 0.f;
+            if (live) {                                        // own row first: needs no staging
+                const float* row = HX_in + (size_t)n * D4;
+                s0 = ldg4(row + 4 * c);
+                s1 = ldg4(row + 16 + 4 * c);
+                sx = __ldg(row + H + c);
             }
-            tc_bar_sync(BAR_PROD, PT);
+            tc_bar_sync(BAR_SFULL + sb, ST + GT);              // this tile's CSR slices are staged
             const int ib = sPtr[0], ic = sPtr[TM] - ib;
             const int ob = sPtr[TM + 4], oc = sPtr[TM + 4 + TM] - ob;
             const bool staged = ic <= CAP && oc <= CAP;       // CTA-uniform
+            const int i0 = sPtr[ln], i1 = live ? sPtr[ln + 1] : i0;
+            const int o0 = sPtr[TM + 4 + ln], o1 = live ? sPtr[TM + 4 + ln + 1] : o0;
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 i_0 = zero, i_1 = zero, o_0 = zero, o_1 = zero;
+            float i_x = 0.f, o_x = 0.f;
             if (staged) {
-                for (int s = pt; s < ic; s += PT)
+                tc_row_sum<H>(sPair, HX_in, i0 - ib, i1 - ib, c, i_0, i_1, i_x);
+                tc_row_sum<H>(sPair + CAP, HX_in, o0 - ob, o1 - ob, c, o_0, o_1, o_x);
+            } else {
+                tc_row_sum_direct<H>(g.in_eid, g.in_nbr, e, HX_in, i0, i1, c, i_0, i_1, i_x);
+                tc_row_sum_direct<H>(g.out_eid, g.out_nbr, e, HX_in, o0, o1, c, o_0, o_1, o_x);
+            }
+            if (tile + 2 * (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_SEMPTY + sb, ST + GT);   // staging buffer free
+            if (it >= 1) tc_bar_sync(BAR_EMPTY, ET + GT);      // GEMM1 of the previous tile has read A1
+            tc_store_part<H>(a1h, a1l, C::SBO_K1, ln, 0, c, i_0, i_1, i_x);
+            tc_store_part<H>(a1h, a1l, C::SBO_K1, ln, 1, c, o_0, o_1, o_x);
+            tc_store_part<H>(a1h, a1l, C::SBO_K1, ln, 2, c, s0, s1, sx);
+            fence_async_smem();                                // generic-proxy writes -> tensor core reads
+            tc_bar_arrive(BAR_FULL, ET + GT);
+        }
+    } else if (tid >= ET) {
+        // ================================ stager warps ==================================
+        // Run ahead of the gather: row pointers, then (neighbour, edge weight) pairs of the tile's
+        // two CSR slices, fetched with coalesced loads into one of two staging buffers.
+        constexpr int CAP = C::CAP;
+        const int stid = tid - ET;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int sb = it & 1;
+            int2* sPair = reinterpret_cast<int2*>(smem + C::O_STAGE + sb * C::STAGE_BYTES);
+            int* sPtr = reinterpret_cast<int*>(smem + C::O_STAGE + sb * C::STAGE_BYTES + 2 * CAP * 8);
+            const int node0 = tile * TM;
+            if (it >= 2) tc_bar_sync(BAR_SEMPTY + sb, ST + GT);   // the gather is done with this buffer
+            for (int i = stid; i <= TM; i += ST) {
+                const int n = min(node0 + i, n_nodes);
+                sPtr[i] = __ldg(g.in_ptr + n);
+                sPtr[TM + 4 + i] = __ldg(g.out_ptr + n);
+            }
+            tc_bar_sync(BAR_STG, ST);
+            const int ib = sPtr[0], ic = sPtr[TM] - ib;
+            const int ob = sPtr[TM + 4], oc = sPtr[TM + 4 + TM] - ob;
+            if (ic <= CAP && oc <= CAP) {
+                for (int s = stid; s < ic; s += ST)
                     sPair[s] = make_int2(__ldg(g.in_nbr + ib + s), __float_as_int(__ldg(e + __ldg(g.in_eid + ib + s))));
-                for (int s = pt; s < oc; s += PT)
+                for (int s = stid; s < oc; s += ST)
                     sPair[CAP + s] = make_int2(__ldg(g.out_nbr + ob + s), __float_as_int(__ldg(e + __ldg(g.out_eid + ob + s))));
             }
-            tc_bar_sync(BAR_PROD, PT);
-            if (it >= 1) tc_bar_sync(BAR_EMPTY, NT);           // GEMM1 of the previous tile has read A1
-            for (int ln = grp; ln < TM; ln += NGRP) {
-                const int n = node0 + ln;
-                const bool live = n < n_nodes;
-                const int i0 = sPtr[ln], i1 = live ? sPtr[ln + 1] : i0;
-                const int o0 = sPtr[TM + 4 + ln], o1 = live ? sPtr[TM + 4 + ln + 1] : o0;
-                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-                {
-                    float4 a_h = zero; float a_x = 0.f;
-                    if (staged) tc_row_sum<H>(sPair, HX_in, i0 - ib, i1 - ib, c, a_h, a_x);
-                    else        tc_row_sum_direct<H>(g.in_eid, g.in_nbr, e, HX_in, i0, i1, c, a_h, a_x);
-                    tc_store_part<H>(a1h, a1l, C::SBO_K1, ln, 0, c, a_h, a_x);
-                }
-                {
-                    float4 a_h = zero; float a_x = 0.f;
-                    if (staged) tc_row_sum<H>(sPair + CAP, HX_in, o0 - ob, o1 - ob, c, a_h, a_x);
-                    else        tc_row_sum_direct<H>(g.out_eid, g.out_nbr, e, HX_in, o0, o1, c, a_h, a_x);
-                    tc_store_part<H>(a1h, a1l, C::SBO_K1, ln, 1, c, a_h, a_x);
-                }
-                {
-                    float4 a_h = zero; float a_x = 0.f;
-                    if (live) {
-                        const float* row = HX_in + (size_t)n * D4;
-                        a_h = ldg4(row + 4 * c);
-                        a_x = __ldg(row + H + (c & 3));
-                    }
-                    tc_store_part<H>(a1h, a1l, C::SBO_K1, ln, 2, c, a_h, a_x);
-                }
-            }
-            fence_async_smem();                                // generic-proxy writes -> tensor core reads
-            tc_bar_arrive(BAR_FULL, NT);
+            tc_bar_arrive(BAR_SFULL + sb, ST + GT);
         }
     } else {
         // ================================ MLP (issuer + epilogue) ======================
         const uint32_t mb = smem_u32(mbar);
-        const int q = warp & 3, half = warp >> 2;             // TMEM lane quarter, column half
-        const int row = q * 32 + lane;                        // node within the tile = TMEM lane
-        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        const int row = warp * 32 + lane;                     // node within the tile = TMEM lane
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
         constexpr uint32_t ID1 = idesc_tf32(TM, H), ID3 = idesc_tf32(TM, 2 * H);
         const uint32_t sa = smem_u32(smem);
         uint32_t phase = 0;
@@ -385,7 +430,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             const int n = node0 + row;
             const bool live = n < n_nodes;
             // ---- GEMM1: D1 = A1 . W3^T  (A and B from shared memory) ----------------------
-            tc_bar_sync(BAR_FULL, NT);
+            tc_bar_sync(BAR_FULL, ET + GT);
             if (tid == 0) {
                 tc_fence_after();
 #pragma unroll 1
@@ -403,18 +448,18 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             }
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
-            if (tile + (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY, NT);   // A1 may be refilled
+            if (tile + (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY, ET + GT);   // A1 may be refilled
             // ---- epilogue 1: h1 = tanh(D1 + b3) -> A2 (hi, lo) in TMEM ---------------------
-            {
-                const int c0 = half * (H / 2);
+#pragma unroll
+            for (int c0 = 0; c0 < H; c0 += 16) {
                 float v[16], hi[16], lo[16];
                 tmem_ld16(lane_base + C::C_D1 + c0, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) split3(tanhf(v[i] + sB3[c0 + i]), hi[i], lo[i]);
                 tmem_st16(lane_base + C::C_A2H + c0, hi);
                 tmem_st16(lane_base + C::C_A2L + c0, lo);
-                tmem_st_wait();
             }
+            tmem_st_wait();
             tc_fence_before();
             tc_bar_sync(BAR_EPI, ET);
             // ---- GEMM2: D2 = A2 . W4^T  (A from tensor memory) ----------------------------
@@ -434,8 +479,8 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
             // ---- epilogue 2: H' = tanh(D2 + b4) -> global HX', and [H'|X|0] -> A3 in TMEM ---
-            {
-                const int c0 = half * (H / 2);
+#pragma unroll
+            for (int c0 = 0; c0 < H; c0 += 16) {
                 float v[16], hi[16], lo[16];
                 tmem_ld16(lane_base + C::C_D2 + c0, v);
 #pragma unroll
@@ -450,22 +495,22 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
                 }
                 tmem_st16(lane_base + C::C_A3H + c0, hi);
                 tmem_st16(lane_base + C::C_A3L + c0, lo);
-                if (half == 0) {                                  // columns H..H+7: X and the zero K padding
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (live) {
-                        x = ldg4(HX_in + (size_t)n * D4 + H);
-                        st4(HX_out + (size_t)n * D4 + H, x);
-                    }
-                    float xh[8], xl[8];
-                    split3(x.x, xh[0], xl[0]); split3(x.y, xh[1], xl[1]);
-                    split3(x.z, xh[2], xl[2]); split3(x.w, xh[3], xl[3]);
-#pragma unroll
-                    for (int i = 4; i < 8; ++i) xh[i] = xl[i] = 0.f;
-                    tmem_st8(lane_base + C::C_A3H + H, xh);
-                    tmem_st8(lane_base + C::C_A3L + H, xl);
-                }
-                tmem_st_wait();
             }
+            {                                                     // columns H..H+7: X and the zero K padding
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) {
+                    x = ldg4(HX_in + (size_t)n * D4 + H);
+                    st4(HX_out + (size_t)n * D4 + H, x);
+                }
+                float xh[8], xl[8];
+                split3(x.x, xh[0], xl[0]); split3(x.y, xh[1], xl[1]);
+                split3(x.z, xh[2], xl[2]); split3(x.w, xh[3], xl[3]);
+#pragma unroll
+                for (int i = 4; i < 8; ++i) xh[i] = xl[i] = 0.f;
+                tmem_st8(lane_base + C::C_A3H + H, xh);
+                tmem_st8(lane_base + C::C_A3L + H, xl);
+            }
+            tmem_st_wait();
             tc_fence_before();
             tc_bar_sync(BAR_EPI, ET);
             // ---- GEMM3: D3 = A3 . W1^T ----------------------------------------------------
@@ -485,21 +530,18 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
             // ---- epilogue 3: P' = D3 (+ b1 on the source half) -> global ---------------------
-            {
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {
-                    const int c0 = half * H + part * 16;          // this warp's 32 columns, 16 at a time
-                    float v[16];
-                    tmem_ld16(lane_base + C::C_D3 + c0, v);
-                    if (c0 < H) {
+            for (int c0 = 0; c0 < 2 * H; c0 += 16) {
+                float v[16];
+                tmem_ld16(lane_base + C::C_D3 + c0, v);
+                if (c0 < H) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += sB1[c0 + i];
-                    }
-                    if (live) {
-                        float* dst = P_out + (size_t)n * 2 * H + c0;
+                    for (int i = 0; i < 16; ++i) v[i] += sB1[c0 + i];
+                }
+                if (live) {
+                    float* dst = P_out + (size_t)n * 2 * H + c0;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-                    }
+                    for (int i = 0; i < 4; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
                 }
             }
             tc_fence_before();
