@@ -285,7 +285,8 @@ def main():
     L = _lib.lib()
     h, F, it = cfg["h"], cfg["F"], cfg["n_iters"]
     blob = model.pack_weights()
-    HX = [torch.empty(batch.n_nodes, h + 4, device=dev) for _ in range(2)]
+    X4 = torch.empty(batch.n_nodes, 4, device=dev)
+    Q = [torch.empty(batch.n_nodes, 3 * h, device=dev) for _ in range(2)]
     P = torch.empty(batch.n_nodes, 2 * h, device=dev)
     e = torch.empty(batch.n_slots, device=dev)
     kt = {"input": [], "edge": [], "node": []}
@@ -302,11 +303,12 @@ def main():
         if rep == 1:
             kt = {"input": [], "edge": [], "node": []}      # drop the warm-up pass
         flush.zero_()
-        timed("input", lambda: L.gnnseg_input_step(_ptr(blob), _ptr(batch.X), batch.n_nodes, F, h, _ptr(HX[0]), _ptr(P), st))
+        timed("input", lambda: L.gnnseg_input_step(_ptr(blob), _ptr(batch.X), batch.n_nodes, F, h, _ptr(X4), _ptr(P), _ptr(Q[0]), st))
         cur = 0
-        for _ in range(it):
+        for i in range(it):
+            qo = _ptr(Q[cur ^ 1]) if i + 1 < it else None
             timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, _ptr(e), st))
-            timed("node", lambda: L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(HX[cur]), _ptr(e), h, _ptr(HX[cur ^ 1]), _ptr(P), st))
+            timed("node", lambda: L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q[cur]), _ptr(e), h, _ptr(P), qo, st))
             cur ^= 1
         timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, _ptr(e), st))
     torch.cuda.synchronize(dev)

@@ -42,9 +42,9 @@ SIGNATURES = {
     "gnnseg_build_csr": (C.c_int, [_i32p, _i32p, C.c_int, C.c_int, _i32p, _i32p, _i32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnnseg_forward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gnnseg_forward": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "gnnseg_input_step": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_void_p]),
+    "gnnseg_input_step": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_void_p]),
     "gnnseg_edge_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, _f32p, C.c_void_p]),
-    "gnnseg_node_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_void_p]),
+    "gnnseg_node_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_void_p]),
     "gnnseg_pack_sparse_batch_host": (C.c_int, [
         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

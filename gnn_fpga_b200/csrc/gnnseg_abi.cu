@@ -3,9 +3,9 @@
 #include "gnnseg_common.cuh"
 
 namespace gnnseg {
-int input_step(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
+int input_step(const float*, const float*, int, int, int, float*, float*, float*, cudaStream_t);
 int edge_step(const float*, const GnnsegGraph*, const float*, int, float*, cudaStream_t);
-int node_step(const float*, const GnnsegGraph*, const float*, const float*, int, float*, float*, cudaStream_t);
+int node_step(const float*, const GnnsegGraph*, const float*, const float*, const float*, int, float*, float*, int, cudaStream_t);
 int pack_weights(const GnnsegParams*, int, int, float*, cudaStream_t);
 int dense_to_edges(const float*, const float*, int, int, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
 size_t csr_workspace_bytes(int, int);
@@ -17,24 +17,27 @@ namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct FwdWorkspace {
-    float* hx[2];
+    float* x4;
     float* p;
+    float* q[2];
     float* e;
     size_t bytes;
 };
 
-// HX0 | HX1 | P | e, each 256-byte aligned.
+// X4 | P | Q0 | Q1 | e, each 256-byte aligned.
 FwdWorkspace carve(void* ws, int n_nodes, int n_slots, int h) {
     FwdWorkspace w;
-    const size_t hx_b = align_up((size_t)n_nodes * (h + 4) * 4, 256);
+    const size_t x_b = align_up((size_t)n_nodes * 4 * 4, 256);
     const size_t p_b = align_up((size_t)n_nodes * 2 * h * 4, 256);
+    const size_t q_b = align_up((size_t)n_nodes * 3 * h * 4, 256);
     const size_t e_b = align_up((size_t)n_slots * 4, 256);
     char* base = static_cast<char*>(ws);
-    w.hx[0] = reinterpret_cast<float*>(base);
-    w.hx[1] = reinterpret_cast<float*>(base + hx_b);
-    w.p = reinterpret_cast<float*>(base + 2 * hx_b);
-    w.e = reinterpret_cast<float*>(base + 2 * hx_b + p_b);
-    w.bytes = 2 * hx_b + p_b + e_b;
+    w.x4 = reinterpret_cast<float*>(base);
+    w.p = reinterpret_cast<float*>(base + x_b);
+    w.q[0] = reinterpret_cast<float*>(base + x_b + p_b);
+    w.q[1] = reinterpret_cast<float*>(base + x_b + p_b + q_b);
+    w.e = reinterpret_cast<float*>(base + x_b + p_b + 2 * q_b);
+    w.bytes = x_b + p_b + 2 * q_b + e_b;
     return w;
 }
 
@@ -119,11 +122,11 @@ size_t gnnseg_forward_workspace_bytes(int n_nodes, int n_slots, int F, int h) {
     return carve(nullptr, n_nodes, n_slots, h).bytes + 256;
 }
 
-int gnnseg_input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* HX,
-                      float* P, void* stream) {
+int gnnseg_input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* X4,
+                      float* P, float* Q, void* stream) {
     if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
-    if (!blob || n_nodes < 0 || (n_nodes > 0 && (!X || !HX || !P))) return GNNSEG_EINVAL;
-    return gnnseg::input_step(blob, X, n_nodes, F, h, HX, P, static_cast<cudaStream_t>(stream));
+    if (!blob || n_nodes < 0 || (n_nodes > 0 && (!X || !X4 || !P || !Q))) return GNNSEG_EINVAL;
+    return gnnseg::input_step(blob, X, n_nodes, F, h, X4, P, Q, static_cast<cudaStream_t>(stream));
 }
 
 int gnnseg_edge_step(const float* blob, const GnnsegGraph* g, const float* P, int h, float* e,
@@ -133,13 +136,14 @@ int gnnseg_edge_step(const float* blob, const GnnsegGraph* g, const float* P, in
     return gnnseg::edge_step(blob, g, P, h, e, static_cast<cudaStream_t>(stream));
 }
 
-int gnnseg_node_step(const float* blob, const GnnsegGraph* g, const float* HX_in, const float* e,
-                     int h, float* HX_out, float* P_out, void* stream) {
+int gnnseg_node_step(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in,
+                     const float* e, int h, float* P_out, float* Q_out, void* stream) {
     if (!gnnseg_supported(1, h)) return GNNSEG_EUNSUPPORTED;
     if (!blob || !csr_ok(g)) return GNNSEG_EINVAL;
-    if (g->n_nodes > 0 && (!HX_in || !HX_out || !P_out)) return GNNSEG_EINVAL;
+    if (g->n_nodes > 0 && (!X4 || !Q_in || !P_out)) return GNNSEG_EINVAL;
     if (g->n_slots > 0 && !e) return GNNSEG_EINVAL;
-    return gnnseg::node_step(blob, g, HX_in, e, h, HX_out, P_out, static_cast<cudaStream_t>(stream));
+    return gnnseg::node_step(blob, g, X4, Q_in, e, h, P_out, Q_out, Q_out != nullptr,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int F, int h,
@@ -155,11 +159,13 @@ int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int 
     if (ws_bytes < w.bytes + (al - raw)) return GNNSEG_EWORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    int rc = gnnseg::input_step(blob, X, g->n_nodes, F, h, w.hx[0], w.p, st);
+    int rc = gnnseg::input_step(blob, X, g->n_nodes, F, h, w.x4, w.p, w.q[0], st);
     int cur = 0;
     for (int it = 0; it < n_iters && rc == GNNSEG_OK; ++it) {
         rc = gnnseg::edge_step(blob, g, w.p, h, w.e, st);
-        if (rc == GNNSEG_OK) rc = gnnseg::node_step(blob, g, w.hx[cur], w.e, h, w.hx[cur ^ 1], w.p, st);
+        // the last node step feeds only the final edge step: its Q' is never read
+        if (rc == GNNSEG_OK)
+            rc = gnnseg::node_step(blob, g, w.x4, w.q[cur], w.e, h, w.p, w.q[cur ^ 1], it + 1 < n_iters, st);
         cur ^= 1;
     }
     if (rc == GNNSEG_OK) rc = gnnseg::edge_step(blob, g, w.p, h, scores, st);

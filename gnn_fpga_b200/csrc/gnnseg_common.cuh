@@ -6,30 +6,38 @@
 
 namespace gnnseg {
 
-// Offsets (in floats) of the packed weight blob.  Everything is stored transposed
-// ([k][out]) so a thread reads 4 consecutive outputs with one 16-byte shared-memory load,
-// and every D-wide input block [hidden | X] is padded to D4 = h+4 columns (zero weights on
-// the padding) so rows of HX are 16-byte aligned.  Column map: SURVEY.md §3.1 /
-// gnn/model.py:73,120,146.
+// Dataflow ("projection first", exact algebra of gnn/model.py:69-81,113-125):
+//   every node carries, besides its features HX[n] = [H[n] | X[n]], five H-wide projections
+//     Ps[n] = W1[:, 0:D].HX[n] + b1      Pd[n] = W1[:, D:2D].HX[n]            (edge step inputs)
+//     Qi[n] = W3[:, 0:D].HX[n]           Qo[n] = W3[:, D:2D].HX[n]
+//     Qs[n] = W3[:, 2D:3D].HX[n] + b3                                          (node step inputs)
+//   edge step:  e_j  = sigmoid(W2 . tanh(Ps[src_j] + Pd[dst_j]) + b2)
+//   node step:  h1[n] = tanh(Qs[n] + sum_{dst_j=n} e_j Qi[src_j] + sum_{src_j=n} e_j Qo[dst_j])
+//               H'[n] = tanh(W4 . h1[n] + b4),  then the five projections of [H'[n] | X[n]].
+//   (W3.[mi; mo; HX] = sum e.(W3a.HX[src]) + sum e.(W3b.HX[dst]) + W3c.HX: the segment sums move
+//   behind the first linear layer, so a gathered row is one aligned H-float line.)
+// State arrays: X4 (n,4) = X zero padded; P (n,2H) = [Ps|Pd]; Q (n,3H) = [Qi|Qo|Qs].
+//
+// Offsets (in floats) of the packed weight blob.  Matrices are stored transposed ([k][out]),
+// and the D-wide input [hidden | X] is padded to D4 = h+4 rows (zero weights on the padding).
+// Column map of the reference weights: SURVEY.md §3.1 / gnn/model.py:73,120,146.
 template <int H>
 struct Blob {
     static constexpr int D4  = H + 4;
     static constexpr int WIN = 0;                    // [4][H]      input_network.0.weight^T
     static constexpr int BIN = WIN + 4 * H;          // [H]
-    static constexpr int W1  = BIN + H;              // [D4][2H]    edge layer 0: [src part | dst part]
-    static constexpr int B1  = W1 + D4 * 2 * H;      // [H]
-    static constexpr int W2  = B1 + H;               // [H]         edge layer 2
+    static constexpr int WP  = BIN + H;              // [D4][5H]    [W1a | W1b | W3a | W3b | W3c]^T
+    static constexpr int BP  = WP + D4 * 5 * H;      // [5H]        [b1 | 0 | 0 | 0 | b3]
+    static constexpr int W2  = BP + 5 * H;           // [H]         edge layer 2
     static constexpr int B2  = W2 + H;               // [4]         b2, 0, 0, 0
-    static constexpr int W3  = B2 + 4;               // [3*D4][H]   node layer 0: [mi | mo | self]
-    static constexpr int B3  = W3 + 3 * D4 * H;      // [H]
-    static constexpr int W4  = B3 + H;               // [H][H]      node layer 2
+    static constexpr int W4  = B2 + 4;               // [H][H]      node layer 2 ^T
     static constexpr int B4  = W4 + H * H;           // [H]
     static constexpr int TOTAL = B4 + H;
 };
 
 __host__ __device__ inline int blob_total(int h) {
     const int d4 = h + 4;
-    return 4 * h + h + d4 * 2 * h + h + h + 4 + 3 * d4 * h + h + h * h + h;
+    return 4 * h + h + d4 * 5 * h + 5 * h + h + 4 + h * h + h;
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) {

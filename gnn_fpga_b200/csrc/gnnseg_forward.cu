@@ -1,19 +1,19 @@
-// Forward kernels of the segment classifier for sm_100a: weight packing, input step,
-// edge step, node step.  The math follows gnn/model.py:140-156 of the reference with the
-// dense incidence bmm replaced by int32 gathers and an ordered CSR segment sum:
+// Forward kernels of the segment classifier for sm_100a: weight packing, input step, edge step,
+// node step (generic path; hidden_dim = 32 runs the tcgen05 kernel in gnnseg_node_tc.cu).
+// The math is gnn/model.py:140-156 of the reference with the dense incidence bmm replaced by int32
+// gathers and an ordered CSR segment sum, in the projection-first form described in
+// gnnseg_common.cuh:
 //
-//   edge step (gnn/model.py:69-81)   e_j = sigmoid(W2 . tanh(W1 . [HX[src_j]; HX[dst_j]] + b1) + b2)
-//     computed "projection first": W1.[a;b] = W1a.a + W1b.b, and P[n] = [W1a.HX[n]+b1 | W1b.HX[n]]
-//     is produced once per node by the kernel that wrote HX[n]; the edge kernel gathers two
-//     h-wide rows of P with 16-byte loads, adds, tanh, dots with W2, sigmoid.
-//   node step (gnn/model.py:113-125) mi[n] = sum_{dst_j = n} e_j HX[src_j]  (ascending j)
-//                                    mo[n] = sum_{src_j = n} e_j HX[dst_j]  (ascending j)
-//                                    H'[n] = tanh(W4 . tanh(W3 . [mi; mo; HX[n]] + b3) + b4)
-//     persistent warp-specialised CTAs: producer warps walk the two CSR rows of a tile of
-//     nodes (no atomics, fixed order) into shared memory while consumer warps run the two
-//     layers + the next step's projection of the previous tile as register-tiled fp32 GEMMs
-//     against weights resident in shared memory.  HX' = [H' | X] is written back (the
-//     reference's cat([H, X]), gnn/model.py:146,154) together with P'.
+//   input step (gnn/model.py:144-146)  H0 = tanh(Win.X + bin); projections of [H0 | X]
+//   edge step  (gnn/model.py:69-81)    e_j = sigmoid(W2 . tanh(Ps[src_j] + Pd[dst_j]) + b2)
+//     two aligned H-float rows gathered with 16-byte loads per lane, tanh, dot, sigmoid.
+//   node step  (gnn/model.py:113-125)  h1 = tanh(Qs[n] + sum_in e Qi[src] + sum_out e Qo[dst])
+//                                      H' = tanh(W4 . h1 + b4); projections of [H' | X]
+//     persistent warp-specialised CTAs: producer warps walk the two CSR rows of every node of a
+//     tile (no atomics, ascending slot order, own term first, then in-edges, then out-edges) and
+//     leave h1 in shared memory; consumer warps run layer 2 and the five projections as
+//     register-tiled GEMMs (SIMT fp32, or 3xTF32 mma.sync for hidden_dim >= 32) against weights
+//     resident in shared memory and write P' and Q'.
 #include <cstdlib>
 #include "gnnseg_common.cuh"
 
@@ -24,40 +24,38 @@ namespace gnnseg {
 // ------------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(GnnsegParams p, int F, int H, float* __restrict__ blob) {
     const int D = F + H, D4 = H + 4;
-    const int o_bin = 4 * H, o_w1 = o_bin + H, o_b1 = o_w1 + D4 * 2 * H, o_w2 = o_b1 + H,
-              o_b2 = o_w2 + H, o_w3 = o_b2 + 4, o_b3 = o_w3 + 3 * D4 * H, o_w4 = o_b3 + H,
-              o_b4 = o_w4 + H * H, total = o_b4 + H;
+    const int o_bin = 4 * H, o_wp = o_bin + H, o_bp = o_wp + D4 * 5 * H, o_w2 = o_bp + 5 * H,
+              o_b2 = o_w2 + H, o_w4 = o_b2 + 4, o_b4 = o_w4 + H * H, total = o_b4 + H;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         float v = 0.f;
         if (i < o_bin) {                       // Win^T [4][H]
             const int f = i / H, j = i % H;
             if (f < F) v = p.w_in[j * F + f];
-        } else if (i < o_w1) {
+        } else if (i < o_wp) {
             v = p.b_in[i - o_bin];
-        } else if (i < o_b1) {                 // W1^T [D4][2H]
-            const int r = i - o_w1, k = r / (2 * H), c = r % (2 * H), part = c / H, j = c % H;
+        } else if (i < o_bp) {                 // WP^T [D4][5H] = [W1a | W1b | W3a | W3b | W3c]
+            const int r = i - o_wp, k = r / (5 * H), c = r % (5 * H), blk = c / H, j = c % H;
             if (k < D) {
-                const int idx = j * (2 * D) + part * D + k;
-                v = p.w_e1[idx];
-                if (p.m_e1) v *= p.m_e1[idx];
+                if (blk < 2) {
+                    const int idx = j * (2 * D) + blk * D + k;
+                    v = p.w_e1[idx];
+                    if (p.m_e1) v *= p.m_e1[idx];
+                } else {
+                    const int idx = j * (3 * D) + (blk - 2) * D + k;
+                    v = p.w_n1[idx];
+                    if (p.m_n1) v *= p.m_n1[idx];
+                }
             }
-        } else if (i < o_w2) {
-            v = p.b_e1[i - o_b1];
+        } else if (i < o_w2) {                 // BP [5H] = [b1 | 0 | 0 | 0 | b3]
+            const int c = i - o_bp;
+            if (c < H) v = p.b_e1[c];
+            else if (c >= 4 * H) v = p.b_n1[c - 4 * H];
         } else if (i < o_b2) {
             const int j = i - o_w2;
             v = p.w_e2[j];
             if (p.m_e2) v *= p.m_e2[j];
-        } else if (i < o_w3) {
-            if (i == o_b2) v = p.b_e2[0];
-        } else if (i < o_b3) {                 // W3^T [3*D4][H]
-            const int r = i - o_w3, row = r / H, j = r % H, part = row / D4, k = row % D4;
-            if (k < D) {
-                const int idx = j * (3 * D) + part * D + k;
-                v = p.w_n1[idx];
-                if (p.m_n1) v *= p.m_n1[idx];
-            }
         } else if (i < o_w4) {
-            v = p.b_n1[i - o_b3];
+            if (i == o_b2) v = p.b_e2[0];
         } else if (i < o_b4) {                 // W4^T [H][H]
             const int r = i - o_w4, k = r / H, j = r % H;
             const int idx = j * H + k;
@@ -133,179 +131,6 @@ __host__ __device__ constexpr int mma_stride(int k) {
     return s;
 }
 
-// Kernel shape per hidden size.
-template <int H>
-struct NodeCfg {
-    static constexpr int TN   = 64;                  // nodes per tile
-    static constexpr int CW   = 8;                   // consumer warps (MLP)
-    static constexpr int PW   = (H >= 64) ? 16 : 8;  // producer warps (CSR gather)
-    static constexpr int CT   = CW * 32;
-    static constexpr int PT   = PW * 32;
-    static constexpr int NT   = CT + PT;             // threads per CTA
-    static constexpr bool MMA = H >= 32;             // tensor-core (3xTF32) MLP; SIMT below that
-    static constexpr int NBUF = MMA ? 1 : 2;         // [mi|mo|self] tile buffers
-    static constexpr int MINB = (H >= 64) ? 1 : 2;   // CTAs per SM the register budget allows
-    static constexpr int RN1  = 2;                   // SIMT path: nodes per thread, H outputs
-    static constexpr int RNP  = 4;                   // SIMT path: nodes per thread, projection
-    static constexpr int RCP  = 4;                   // SIMT path: outputs per thread, projection
-    static constexpr int D4   = H + 4;
-    static constexpr int K1   = 3 * D4;
-    static constexpr int K1P  = (K1 + 7) / 8 * 8;    // MMA path: K padded to the k8 step
-    static constexpr int D4P  = (D4 + 7) / 8 * 8;
-    static constexpr int SM   = MMA ? mma_stride(K1P) : tile_stride(K1);   // [mi|mo|self] tile stride
-    static constexpr int SH   = MMA ? mma_stride(H) : tile_stride(H);      // hidden-layer tile stride
-    static constexpr int SD   = MMA ? mma_stride(D4P) : tile_stride(D4);   // HX tile stride
-    static constexpr int CAP  = (H >= 64) ? 1536 : 768;   // staged CSR slots per direction per tile
-    // weights in shared memory: SIMT keeps the blob's [k][out]; MMA wants [out][k] rows with the
-    // same padded strides as the A tiles
-    static constexpr int W_FLOATS = MMA ? (H * SM + H * SH + 2 * H * SD + 3 * H)
-                                        : (K1 * H + H * H + D4 * 2 * H + 3 * H);
-    static constexpr int STAGE_WORDS = 2 * 2 * CAP + 2 * (TN + 4);   // (nbr,w) pairs + row pointers
-    static constexpr int SMEM_FLOATS = W_FLOATS + TN * (NBUF * SM + SH + SD) + STAGE_WORDS;
-    static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
-};
-
-template <int H>
-struct InputCfg {
-    static constexpr int TN = 64, NT = 256, RNP = 4, RCP = 4;
-    static constexpr int D4 = H + 4;
-    static constexpr int SD = tile_stride(D4);
-    static constexpr int SMEM_FLOATS = 4 * H + H + D4 * 2 * H + H + TN * SD + TN * 4;
-    static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
-};
-
-// Write the tile's HX rows and its projection P = [W1a.HX+b1 | W1b.HX] to global memory.
-// Runs on threads 0..NT-1.
-template <int H, int TN, int NT, int RNP, int RCP>
-__device__ __forceinline__ void store_hx_and_project(const float* __restrict__ sHX, const int sd,
-                                                     const float* __restrict__ sW1,
-                                                     const float* __restrict__ sB1,
-                                                     const int node0, const int n_nodes,
-                                                     float* __restrict__ HX_out,
-                                                     float* __restrict__ P_out) {
-    constexpr int D4 = H + 4, C4 = D4 / 4;
-    for (int i = threadIdx.x; i < TN * C4; i += NT) {
-        const int ln = i / C4, c = i % C4, n = node0 + ln;
-        if (n < n_nodes) st4(HX_out + (size_t)n * D4 + 4 * c, lds4(sHX + ln * sd + 4 * c));
-    }
-    tile_gemm<D4, 2 * H, TN, NT, RNP, RCP>(sHX, sd, sW1, [&](int ln, int o, const float* acc) {
-        const int n = node0 + ln;
-        if (n < n_nodes) {
-            float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            if (o < H) {
-                const float4 b = lds4(sB1 + o);
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-            }
-            st4(P_out + (size_t)n * 2 * H + o, v);
-        }
-    });
-}
-
-// ------------------------------------------------------------------------------------
-// input step: H0 = tanh(Win.X + bin), HX = [H0 | X], P = projection   (gnn/model.py:144-146)
-// ------------------------------------------------------------------------------------
-template <int H>
-__global__ void __launch_bounds__(InputCfg<H>::NT)
-input_kernel(const float* __restrict__ blob, const float* __restrict__ X, const int F,
-             const int n_nodes, const int n_tiles, float* __restrict__ HX_out,
-             float* __restrict__ P_out) {
-    using C = InputCfg<H>;
-    using B = Blob<H>;
-    constexpr int TN = C::TN, NT = C::NT, D4 = C::D4, SD = C::SD;
-    extern __shared__ __align__(16) float smem[];
-    float* sWin = smem;                 // [4][H]
-    float* sBin = sWin + 4 * H;         // [H]
-    float* sW1  = sBin + H;             // [D4][2H]
-    float* sB1  = sW1 + D4 * 2 * H;     // [H]
-    float* sHX  = sB1 + H;              // [TN][SD]
-    float* sX   = sHX + TN * SD;        // [TN][4]
-    copy_to_smem<NT>(sWin, blob + B::WIN, 4 * H + H);
-    copy_to_smem<NT>(sW1, blob + B::W1, D4 * 2 * H + H);
-
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int node0 = tile * TN;
-        __syncthreads();   // weights visible (first pass) / previous tile's readers done
-        for (int i = threadIdx.x; i < TN * 4; i += NT) {
-            const int ln = i >> 2, f = i & 3, n = node0 + ln;
-            sX[i] = (n < n_nodes && f < F) ? __ldg(X + (size_t)n * F + f) : 0.f;
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < TN * (H / 4 + 1); i += NT) {
-            const int ln = i / (H / 4 + 1), c = i % (H / 4 + 1);
-            const float4 x = lds4(sX + ln * 4);
-            float4 v;
-            if (c < H / 4) {
-                v = lds4(sBin + 4 * c);
-                fma4(v, x.x, lds4(sWin + 0 * H + 4 * c));
-                fma4(v, x.y, lds4(sWin + 1 * H + 4 * c));
-                fma4(v, x.z, lds4(sWin + 2 * H + 4 * c));
-                fma4(v, x.w, lds4(sWin + 3 * H + 4 * c));
-                v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
-            } else {
-                v = x;
-            }
-            st4(sHX + ln * SD + 4 * c, v);
-        }
-        __syncthreads();
-        store_hx_and_project<H, TN, NT, C::RNP, C::RCP>(sHX, SD, sW1, sB1, node0, n_nodes, HX_out, P_out);
-    }
-}
-
-// ------------------------------------------------------------------------------------
-// edge step
-// ------------------------------------------------------------------------------------
-template <int H>
-__global__ void __launch_bounds__(256)
-edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
-            const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
-            const int n_slots, float* __restrict__ e_out) {
-    using B = Blob<H>;
-    constexpr int G = H / 4;        // lanes that share one edge (one float4 of P each)
-    constexpr int EPP = 32 / G;     // edges a warp handles per pass
-    const int lane = threadIdx.x & 31;
-    const int c = lane % G, g = lane / G;
-    const float4 w2 = ldg4(blob + B::W2 + 4 * c);
-    const float4 b1 = ldg4(blob + B::B1 + 4 * c);
-    const float b2 = __ldg(blob + B::B2);
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-
-    for (int base = warp * 32; base < n_slots; base += n_warps * 32) {
-        const int j = base + lane;
-        int s = -1, d = -1;
-        if (j < n_slots) { s = __ldg(src + j); d = __ldg(dst + j); }
-        float mine = 0.f;
-#pragma unroll (G > 8 ? 8 : G)
-        for (int p = 0; p < G; ++p) {
-            const int k = p * EPP + g;                       // which of the warp's 32 edges
-            const int ss = __shfl_sync(0xffffffffu, s, k);
-            const int dd = __shfl_sync(0xffffffffu, d, k);
-            float4 a = b1;                                   // absent start: W1a.0 + b1
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);      // absent end:   W1b.0
-            if (ss >= 0) a = ldg4(P + (size_t)ss * (2 * H) + 4 * c);
-            if (dd >= 0) b = ldg4(P + (size_t)dd * (2 * H) + H + 4 * c);
-            float z = w2.x * tanhf(a.x + b.x);
-            z = fmaf(w2.y, tanhf(a.y + b.y), z);
-            z = fmaf(w2.z, tanhf(a.z + b.z), z);
-            z = fmaf(w2.w, tanhf(a.w + b.w), z);
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-            const float v = __shfl_sync(0xffffffffu, z, (lane % EPP) * G);
-            if (lane / EPP == p) mine = v;
-        }
-        if (j < n_slots) e_out[j] = 1.f / (1.f + expf(-(mine + b2)));
-    }
-}
-
-// ------------------------------------------------------------------------------------
-// node step: warp-specialised persistent kernel.
-//   producer warps  walk the two CSR rows of every node of a tile and leave the tile's
-//                   [mi | mo | self] rows in shared memory (latency bound: many loads in flight)
-//   consumer warps  run layer 0, layer 2 and the projection as register-tiled fp32 GEMMs
-//                   out of shared memory (FMA bound) and write HX' and P'
-// The two halves meet through named barriers (full/empty per tile buffer), so the gather of
-// tile t+1 overlaps the MLP of tile t on the same SM.
-// ------------------------------------------------------------------------------------
 // ---- 3xTF32 tensor-core GEMM on fp32 operands held in shared memory --------------------------
 // x = hi + lo with hi = tf32(x), lo = tf32(x - hi); a.b ~= lo_a.hi_b + hi_a.lo_b + hi_a.hi_b with
 // fp32 accumulation, which keeps the result within a few 1e-7 of the fp32 FMA chain (the
@@ -393,6 +218,167 @@ __device__ __forceinline__ void tile_gemm_mma(const float* __restrict__ sA, cons
         }
 }
 
+// Store one float4 of the projection row of node n: columns [0,2H) go to P, [2H,5H) to Q.
+template <int H>
+__device__ __forceinline__ void store_proj4(float* __restrict__ P, float* __restrict__ Q, const int n,
+                                            const int o, const float4 v, const bool write_q) {
+    if (o < 2 * H) st4(P + (size_t)n * 2 * H + o, v);
+    else if (write_q) st4(Q + (size_t)n * 3 * H + (o - 2 * H), v);
+}
+template <int H>
+__device__ __forceinline__ void store_proj2(float* __restrict__ P, float* __restrict__ Q, const int n,
+                                            const int o, const float v0, const float v1, const bool write_q) {
+    if (o < 2 * H) *reinterpret_cast<float2*>(P + (size_t)n * 2 * H + o) = make_float2(v0, v1);
+    else if (write_q) *reinterpret_cast<float2*>(Q + (size_t)n * 3 * H + (o - 2 * H)) = make_float2(v0, v1);
+}
+
+// Kernel shape per hidden size.
+template <int H>
+struct NodeCfg {
+    static constexpr int TN   = 64;                  // nodes per tile
+    static constexpr int CW   = 8;                   // consumer warps (MLP)
+    static constexpr int PW   = (H >= 64) ? 16 : 8;  // producer warps (CSR gather)
+    static constexpr int CT   = CW * 32;
+    static constexpr int PT   = PW * 32;
+    static constexpr int NT   = CT + PT;             // threads per CTA
+    static constexpr bool MMA = H >= 32;             // 3xTF32 mma.sync MLP; SIMT fp32 below that
+    static constexpr int NBUF = 2;                   // h1 tile buffers
+    static constexpr int MINB = (H >= 64) ? 1 : 2;   // CTAs per SM the register budget allows
+    static constexpr int RN   = 2;                   // SIMT path: nodes per thread
+    static constexpr int D4   = H + 4;
+    static constexpr int D4P  = (D4 + 7) / 8 * 8;    // MMA path: K padded to the k8 step
+    static constexpr int SH   = MMA ? mma_stride(H) : tile_stride(H);      // h1 tile stride
+    static constexpr int SD   = MMA ? mma_stride(D4P) : tile_stride(D4);   // [H'|X] tile stride
+    static constexpr int CAP  = (H >= 64) ? 1536 : 768;   // staged CSR slots per direction per tile
+    // weights in shared memory: SIMT keeps the blob's [k][out]; MMA wants [out][k] rows with the
+    // same padded strides as the A tiles
+    static constexpr int W_FLOATS = (MMA ? (H * SH + 5 * H * SD) : (H * H + D4 * 5 * H)) + 6 * H;
+    static constexpr int STAGE_WORDS = 2 * 2 * CAP + 2 * (TN + 4);   // (nbr,w) pairs + row pointers
+    static constexpr int SMEM_FLOATS = W_FLOATS + TN * (NBUF * SH + SD) + STAGE_WORDS;
+    static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
+};
+
+template <int H>
+struct InputCfg {
+    static constexpr int TN = 64, NT = 256, RN = 2;
+    static constexpr int D4 = H + 4;
+    static constexpr int SD = tile_stride(D4);
+    static constexpr int SMEM_FLOATS = 4 * H + H + D4 * 5 * H + 5 * H + TN * SD + TN * 4;
+    static constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
+};
+
+// ------------------------------------------------------------------------------------
+// input step: H0 = tanh(Win.X + bin), then X4, P, Q of [H0 | X]        (gnn/model.py:144-146)
+// ------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(InputCfg<H>::NT)
+input_kernel(const float* __restrict__ blob, const float* __restrict__ X, const int F,
+             const int n_nodes, const int n_tiles, float* __restrict__ X4,
+             float* __restrict__ P_out, float* __restrict__ Q_out) {
+    using C = InputCfg<H>;
+    using B = Blob<H>;
+    constexpr int TN = C::TN, NT = C::NT, D4 = C::D4, SD = C::SD;
+    extern __shared__ __align__(16) float smem[];
+    float* sWin = smem;                 // [4][H]
+    float* sBin = sWin + 4 * H;         // [H]
+    float* sWP  = sBin + H;             // [D4][5H]
+    float* sBP  = sWP + D4 * 5 * H;     // [5H]
+    float* sHX  = sBP + 5 * H;          // [TN][SD]
+    float* sX   = sHX + TN * SD;        // [TN][4]
+    copy_to_smem<NT>(sWin, blob + B::WIN, 4 * H + H);
+    copy_to_smem<NT>(sWP, blob + B::WP, D4 * 5 * H + 5 * H);
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int node0 = tile * TN;
+        __syncthreads();   // weights visible (first pass) / previous tile's readers done
+        for (int i = threadIdx.x; i < TN * 4; i += NT) {
+            const int ln = i >> 2, f = i & 3, n = node0 + ln;
+            sX[i] = (n < n_nodes && f < F) ? __ldg(X + (size_t)n * F + f) : 0.f;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < TN * (H / 4 + 1); i += NT) {
+            const int ln = i / (H / 4 + 1), c = i % (H / 4 + 1);
+            const float4 x = lds4(sX + ln * 4);
+            float4 v;
+            if (c < H / 4) {
+                v = lds4(sBin + 4 * c);
+                fma4(v, x.x, lds4(sWin + 0 * H + 4 * c));
+                fma4(v, x.y, lds4(sWin + 1 * H + 4 * c));
+                fma4(v, x.z, lds4(sWin + 2 * H + 4 * c));
+                fma4(v, x.w, lds4(sWin + 3 * H + 4 * c));
+                v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
+            } else {
+                v = x;
+                if (node0 + ln < n_nodes) st4(X4 + (size_t)(node0 + ln) * 4, x);
+            }
+            st4(sHX + ln * SD + 4 * c, v);
+        }
+        __syncthreads();
+        tile_gemm<D4, 5 * H, TN, NT, C::RN, 4>(sHX, SD, sWP, [&](int ln, int o, const float* acc) {
+            const int n = node0 + ln;
+            if (n < n_nodes) {
+                const float4 b = lds4(sBP + o);
+                store_proj4<H>(P_out, Q_out, n, o, make_float4(acc[0] + b.x, acc[1] + b.y, acc[2] + b.z, acc[3] + b.w), true);
+            }
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// edge step
+// ------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(256)
+edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
+            const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+            const int n_slots, float* __restrict__ e_out) {
+    using B = Blob<H>;
+    constexpr int G = H / 4;        // lanes that share one edge (one float4 of P each)
+    constexpr int EPP = 32 / G;     // edges a warp handles per pass
+    const int lane = threadIdx.x & 31;
+    const int c = lane % G, g = lane / G;
+    const float4 w2 = ldg4(blob + B::W2 + 4 * c);
+    const float4 b1 = ldg4(blob + B::BP + 4 * c);
+    const float b2 = __ldg(blob + B::B2);
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+
+    for (int base = warp * 32; base < n_slots; base += n_warps * 32) {
+        const int j = base + lane;
+        int s = -1, d = -1;
+        if (j < n_slots) { s = __ldg(src + j); d = __ldg(dst + j); }
+        float mine = 0.f;
+#pragma unroll (G > 8 ? 8 : G)
+        for (int p = 0; p < G; ++p) {
+            const int k = p * EPP + g;                       // which of the warp's 32 edges
+            const int ss = __shfl_sync(0xffffffffu, s, k);
+            const int dd = __shfl_sync(0xffffffffu, d, k);
+            float4 a = b1;                                   // absent start: W1a.0 + b1
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);      // absent end:   W1b.0
+            if (ss >= 0) a = ldg4(P + (size_t)ss * (2 * H) + 4 * c);
+            if (dd >= 0) b = ldg4(P + (size_t)dd * (2 * H) + H + 4 * c);
+            float z = w2.x * tanhf(a.x + b.x);
+            z = fmaf(w2.y, tanhf(a.y + b.y), z);
+            z = fmaf(w2.z, tanhf(a.z + b.z), z);
+            z = fmaf(w2.w, tanhf(a.w + b.w), z);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+            const float v = __shfl_sync(0xffffffffu, z, (lane % EPP) * G);
+            if (lane / EPP == p) mine = v;
+        }
+        if (j < n_slots) e_out[j] = 1.f / (1.f + expf(-(mine + b2)));
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// node step (generic path): warp-specialised persistent kernel.
+//   producer warps  stage the tile's CSR slices, gather and sum the aligned Q rows and leave
+//                   h1 = tanh(...) of the tile in shared memory (latency bound: many loads in flight)
+//   consumer warps  run layer 2 and the projections as register-tiled GEMMs out of shared memory
+//                   and write P' and Q'
+// The two halves meet through named barriers (full/empty per tile buffer), so the gather of
+// tile t+1 overlaps the MLP of tile t on the same SM.
+// ------------------------------------------------------------------------------------
 __device__ __forceinline__ void bar_sync(const int id, const int n) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
@@ -400,33 +386,21 @@ __device__ __forceinline__ void bar_arrive(const int id, const int n) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
-// One CSR row, G lanes per node: acc += w_s * HX[nbr_s] for the row's slots in ascending
-// order.  Lane c owns float4 chunk c of the hidden part; the X chunk (4 floats) is spread over
-// the lanes as scalars when the group has >= 4 lanes (lane c takes X[c & 3]), else lane 0 takes
-// it as one float4.  STAGED: the (neighbour, weight) pairs of the whole tile were fetched into
-// shared memory beforehand by coalesced loads, so the only global latency left in this loop is
-// the row gather itself.  Slots go in batches of U: all U row loads are issued before the
-// first FMA (no branch in between: an absent neighbour loads row 0 and is dropped by
-// predication), the FMAs then run in ascending slot order.
-template <int H>
-struct XAcc {   // per-lane accumulator of the X chunk
-    static constexpr bool SCALAR = (H / 4) >= 4;
-    float4 v;
-};
-
-template <int H, bool STAGED>
+// One CSR row, one float4 chunk per lane: acc += w_s * Qrow[nbr_s] for the row's slots in
+// ascending order.  Slots go in batches of U: all U row loads are issued before the first FMA
+// (no branch in between: an absent neighbour loads row 0 and is dropped by predication).
+// STAGED: the (neighbour, weight) pairs of the whole tile were fetched into shared memory
+// beforehand by coalesced loads.
+template <bool STAGED>
 __device__ __forceinline__ void csr_row_sum(const int2* __restrict__ pairs, const int32_t* __restrict__ eid,
                                             const int32_t* __restrict__ nbr, const float* __restrict__ e,
-                                            const float* __restrict__ HX, const int beg, const int end,
-                                            const int c, float4& acc_h, float4& acc_x) {
-    constexpr bool SCALAR_X = XAcc<H>::SCALAR;
-    constexpr int D4 = H + 4, U = SCALAR_X ? 4 : 2;
+                                            const float* __restrict__ Qcol, const int row_floats,
+                                            const int beg, const int end, float4& acc) {
+    constexpr int U = 4;
     for (int s0 = beg; s0 < end; s0 += U) {
         float w[U];
         bool ok[U];
-        float4 vh[U];
-        float4 vx4[SCALAR_X ? 1 : U];
-        float vx1[SCALAR_X ? U : 1];
+        float4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int s = min(s0 + u, end - 1);
@@ -440,82 +414,53 @@ __device__ __forceinline__ void csr_row_sum(const int2* __restrict__ pairs, cons
                 w[u] = __ldg(e + __ldg(eid + s));
             }
             ok[u] = (s0 + u < end) && nb >= 0;   // nb < 0: half edge, gathers the zero row
-            const float* row = HX + (size_t)max(nb, 0) * D4;
-            vh[u] = ldg4(row + 4 * c);
-            if (SCALAR_X) vx1[u] = __ldg(row + H + (c & 3));
-            else if (c == 0) vx4[u] = ldg4(row + H);
+            v[u] = ldg4(Qcol + (size_t)max(nb, 0) * row_floats);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (ok[u]) {
-                fma4(acc_h, w[u], vh[u]);
-                if (SCALAR_X) acc_x.x = fmaf(w[u], vx1[u], acc_x.x);
-                else if (c == 0) fma4(acc_x, w[u], vx4[u]);
-            }
-        }
-    }
-}
-
-// Store the X-chunk accumulator of csr_row_sum into a tile row.
-template <int H>
-__device__ __forceinline__ void store_x_acc(float* __restrict__ dst, const int c, const float4& acc_x) {
-    if (XAcc<H>::SCALAR) {
-        if (c < 4) dst[c] = acc_x.x;
-    } else if (c == 0) {
-        st4(dst, acc_x);
+        for (int u = 0; u < U; ++u)
+            if (ok[u]) fma4(acc, w[u], v[u]);
     }
 }
 
 template <int H>
 __global__ void __launch_bounds__(NodeCfg<H>::NT, NodeCfg<H>::MINB)
-node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
-            const float* __restrict__ HX_in, const float* __restrict__ e, const int n_tiles,
-            float* __restrict__ HX_out, float* __restrict__ P_out, const int dbg) {
+node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __restrict__ X4,
+            const float* __restrict__ Q_in, const float* __restrict__ e, const int n_tiles,
+            float* __restrict__ P_out, float* __restrict__ Q_out, const int write_q) {
     using C = NodeCfg<H>;
     using B = Blob<H>;
     constexpr int TN = C::TN, NT = C::NT, CT = C::CT, PT = C::PT, NBUF = C::NBUF;
-    constexpr int D4 = C::D4, K1 = C::K1, SM = C::SM, SH = C::SH, SD = C::SD;
+    constexpr int D4 = C::D4, SH = C::SH, SD = C::SD;
     constexpr bool MMA = C::MMA;
     constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + NBUF, BAR_CONS = 1 + 2 * NBUF, BAR_PROD = 2 + 2 * NBUF;
     extern __shared__ __align__(16) float smem[];
     // weights: SIMT path [k][out] as in the blob, MMA path [out][k] with padded row strides
-    float* sW3 = smem;                                     // SIMT [K1][H]    | MMA [H][SM]
-    float* sB3 = sW3 + (MMA ? H * SM : K1 * H);            // [H]
-    float* sW4 = sB3 + H;                                  // SIMT [H][H]     | MMA [H][SH]
-    float* sB4 = sW4 + (MMA ? H * SH : H * H);             // [H]
-    float* sW1 = sB4 + H;                                  // SIMT [D4][2H]   | MMA [2H][SD]
-    float* sB1 = sW1 + (MMA ? 2 * H * SD : D4 * 2 * H);    // [H]
-    float* sM  = sB1 + H;               // [NBUF][TN][SM]   [mi | mo | self]
-    float* sH1 = sM + NBUF * TN * SM;   // [TN][SH]
-    float* sHX = sH1 + TN * SH;         // [TN][SD]
+    float* sW4 = smem;                                     // SIMT [H][H]     | MMA [H][SH]
+    float* sWP = sW4 + (MMA ? H * SH : H * H);             // SIMT [D4][5H]   | MMA [5H][SD]
+    float* sBP = sWP + (MMA ? 5 * H * SD : D4 * 5 * H);    // [5H]
+    float* sB4 = sBP + 5 * H;                              // [H]
+    float* sH1 = sB4 + H;               // [NBUF][TN][SH]   h1 tiles
+    float* sHX = sH1 + NBUF * TN * SH;  // [TN][SD]         [H' | X | 0]
     int2* sPair = reinterpret_cast<int2*>(sHX + TN * SD);          // [2][CAP] (nbr, w) in / out
     int*  sPtr  = reinterpret_cast<int*>(sPair + 2 * C::CAP);      // [2][TN+4] row pointers in / out
-    if (MMA) {
+    if constexpr (MMA) {
         // transpose the blob's [k][out] matrices into [out][k] rows; k beyond the real width is 0
-        for (int i = threadIdx.x; i < H * SM; i += NT) {
-            const int j = i / SM, k = i % SM;
-            sW3[i] = k < K1 ? __ldg(blob + B::W3 + k * H + j) : 0.f;
-        }
         for (int i = threadIdx.x; i < H * SH; i += NT) {
             const int j = i / SH, k = i % SH;
             sW4[i] = k < H ? __ldg(blob + B::W4 + k * H + j) : 0.f;
         }
-        for (int i = threadIdx.x; i < 2 * H * SD; i += NT) {
+        for (int i = threadIdx.x; i < 5 * H * SD; i += NT) {
             const int j = i / SD, k = i % SD;
-            sW1[i] = k < D4 ? __ldg(blob + B::W1 + k * 2 * H + j) : 0.f;
+            sWP[i] = k < D4 ? __ldg(blob + B::WP + k * 5 * H + j) : 0.f;
         }
-        for (int i = threadIdx.x; i < H; i += NT) {
-            sB3[i] = __ldg(blob + B::B3 + i);
-            sB4[i] = __ldg(blob + B::B4 + i);
-            sB1[i] = __ldg(blob + B::B1 + i);
-        }
-        // zero the K padding of the A tiles once: nobody writes those columns afterwards
-        for (int i = threadIdx.x; i < NBUF * TN * (SM - K1); i += NT) sM[(i / (SM - K1)) * SM + K1 + i % (SM - K1)] = 0.f;
+        // zero the K padding of the [H'|X] tile once: nobody writes those columns afterwards
         for (int i = threadIdx.x; i < TN * (SD - D4); i += NT) sHX[(i / (SD - D4)) * SD + D4 + i % (SD - D4)] = 0.f;
     } else {
-        copy_to_smem<NT>(sW3, blob + B::W3, K1 * H + H + H * H + H);   // W3,b3,W4,b4 contiguous
-        copy_to_smem<NT>(sW1, blob + B::W1, D4 * 2 * H + H);           // W1,b1 contiguous
+        copy_to_smem<NT>(sW4, blob + B::W4, H * H);
+        copy_to_smem<NT>(sWP, blob + B::WP, D4 * 5 * H);
     }
+    for (int i = threadIdx.x; i < 5 * H; i += NT) sBP[i] = __ldg(blob + B::BP + i);
+    for (int i = threadIdx.x; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
     __syncthreads();
     const int n_nodes = g.n_nodes;
 
@@ -549,38 +494,23 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
             }
             bar_sync(BAR_PROD, PT);
             if (it >= NBUF) bar_sync(BAR_EMPTY + buf, NT);     // consumers are done with this buffer
-            float* sMb = sM + buf * TN * SM;
+            float* sHb = sH1 + buf * TN * SH;
             for (int ln = grp; ln < TN; ln += NGRP) {
                 const int n = node0 + ln;
-                const bool live = n < n_nodes && !(dbg & 1);
-                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-                float* m = sMb + ln * SM;
-                const int i0 = sPtr[ln], i1 = live ? sPtr[ln + 1] : i0;
-                const int o0 = sPtr[TN + 4 + ln], o1 = live ? sPtr[TN + 4 + ln + 1] : o0;
-                {   // mi: sum over in-edges of e * HX[src]
-                    float4 a_h = zero, a_x = zero;
-                    if (staged) csr_row_sum<H, true>(sPair, nullptr, nullptr, nullptr, HX_in, i0 - ib, i1 - ib, c, a_h, a_x);
-                    else        csr_row_sum<H, false>(nullptr, g.in_eid, g.in_nbr, e, HX_in, i0, i1, c, a_h, a_x);
-                    st4(m + 4 * c, a_h);
-                    store_x_acc<H>(m + H, c, a_x);
-                }
-                {   // mo: sum over out-edges of e * HX[dst]
-                    float4 a_h = zero, a_x = zero;
-                    if (staged) csr_row_sum<H, true>(sPair + CAP, nullptr, nullptr, nullptr, HX_in, o0 - ob, o1 - ob, c, a_h, a_x);
-                    else        csr_row_sum<H, false>(nullptr, g.out_eid, g.out_nbr, e, HX_in, o0, o1, c, a_h, a_x);
-                    st4(m + D4 + 4 * c, a_h);
-                    store_x_acc<H>(m + D4 + H, c, a_x);
-                }
-                {   // the node's own row
-                    float4 a_h = zero, a_x = zero;
-                    if (live) {
-                        const float* row = HX_in + (size_t)n * D4;
-                        a_h = ldg4(row + 4 * c);
-                        if (c == 0) a_x = ldg4(row + H);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < n_nodes) {
+                    acc = ldg4(Q_in + (size_t)n * 3 * H + 2 * H + 4 * c);             // Qs[n] (holds b3)
+                    const int i0 = sPtr[ln], i1 = sPtr[ln + 1], o0 = sPtr[TN + 4 + ln], o1 = sPtr[TN + 4 + ln + 1];
+                    if (staged) {
+                        csr_row_sum<true>(sPair, nullptr, nullptr, nullptr, Q_in + 4 * c, 3 * H, i0 - ib, i1 - ib, acc);
+                        csr_row_sum<true>(sPair + CAP, nullptr, nullptr, nullptr, Q_in + H + 4 * c, 3 * H, o0 - ob, o1 - ob, acc);
+                    } else {
+                        csr_row_sum<false>(nullptr, g.in_eid, g.in_nbr, e, Q_in + 4 * c, 3 * H, i0, i1, acc);
+                        csr_row_sum<false>(nullptr, g.out_eid, g.out_nbr, e, Q_in + H + 4 * c, 3 * H, o0, o1, acc);
                     }
-                    st4(m + 2 * D4 + 4 * c, a_h);
-                    if (c == 0) st4(m + 2 * D4 + H, a_x);
+                    acc.x = tanhf(acc.x); acc.y = tanhf(acc.y); acc.z = tanhf(acc.z); acc.w = tanhf(acc.w);
                 }
+                st4(sHb + ln * SH + 4 * c, acc);
             }
             bar_arrive(BAR_FULL + buf, NT);
         }
@@ -590,62 +520,48 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g,
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int buf = it % NBUF;
             const int node0 = tile * TN;
-            const float* sMb = sM + buf * TN * SM;
-            bar_sync(BAR_FULL + buf, NT);                      // the tile's rows are in sMb
-            if (dbg & 2) {
-                bar_sync(BAR_CONS, CT);
-                if (tile + NBUF * (int)gridDim.x < n_tiles) bar_arrive(BAR_EMPTY + buf, NT);
-                continue;
+            const float* sHb = sH1 + buf * TN * SH;
+            // the X part of the [H'|X] rows (independent of the producers)
+            for (int i = threadIdx.x; i < TN; i += CT) {
+                const int n = node0 + i;
+                st4(sHX + i * SD + H, n < n_nodes ? ldg4(X4 + (size_t)n * 4) : make_float4(0.f, 0.f, 0.f, 0.f));
             }
-            // ---- layer 0: h1 = tanh(W3 . [mi; mo; self] + b3) ---------------------------
-            if constexpr (MMA) {
-                tile_gemm_mma<C::K1P / 8, H>(sMb, SM, sW3, SM, [&](int ln, int o, float v0, float v1) {
-                    *reinterpret_cast<float2*>(sH1 + ln * SH + o) =
-                        make_float2(tanhf(v0 + sB3[o]), tanhf(v1 + sB3[o + 1]));
-                });
-            } else {
-                tile_gemm<K1, H, TN, CT, C::RN1, 4>(sMb, SM, sW3, [&](int ln, int o, const float* acc) {
-                    const float4 b = lds4(sB3 + o);
-                    st4(sH1 + ln * SH + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
-                                                       tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
-                });
-            }
-            // the X part of the new HX row is the old one (self block of the tile)
-            for (int i = threadIdx.x; i < TN; i += CT) st4(sHX + i * SD + H, lds4(sMb + i * SM + 2 * D4 + H));
-            bar_sync(BAR_CONS, CT);
-            if (tile + NBUF * (int)gridDim.x < n_tiles) bar_arrive(BAR_EMPTY + buf, NT);   // release sMb
+            bar_sync(BAR_FULL + buf, NT);                      // the tile's h1 rows are in sHb
             // ---- layer 2: H' = tanh(W4 . h1 + b4) ---------------------------------------
             if constexpr (MMA) {
-                tile_gemm_mma<H / 8, H>(sH1, SH, sW4, SH, [&](int ln, int o, float v0, float v1) {
+                tile_gemm_mma<H / 8, H>(sHb, SH, sW4, SH, [&](int ln, int o, float v0, float v1) {
                     *reinterpret_cast<float2*>(sHX + ln * SD + o) =
                         make_float2(tanhf(v0 + sB4[o]), tanhf(v1 + sB4[o + 1]));
                 });
             } else {
-                tile_gemm<H, H, TN, CT, C::RN1, 4>(sH1, SH, sW4, [&](int ln, int o, const float* acc) {
+                tile_gemm<H, H, TN, CT, C::RN, 4>(sHb, SH, sW4, [&](int ln, int o, const float* acc) {
                     const float4 b = lds4(sB4 + o);
                     st4(sHX + ln * SD + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
                                                        tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
                 });
             }
             bar_sync(BAR_CONS, CT);
-            // ---- write HX' and the projection for the next edge step ---------------------
+            if (tile + NBUF * (int)gridDim.x < n_tiles) bar_arrive(BAR_EMPTY + buf, NT);   // release sHb
+            // ---- projections of [H'|X] for the next edge and node steps ---------------------
             if constexpr (MMA) {
-                constexpr int C4 = D4 / 4;
-                for (int i = threadIdx.x; i < TN * C4; i += CT) {
-                    const int ln = i / C4, c = i % C4, n = node0 + ln;
-                    if (n < n_nodes) st4(HX_out + (size_t)n * D4 + 4 * c, lds4(sHX + ln * SD + 4 * c));
+#pragma unroll 1
+                for (int blk = 0; blk < 5; ++blk) {
+                    if (blk >= 2 && !write_q) break;
+                    tile_gemm_mma<C::D4P / 8, H>(sHX, SD, sWP + blk * H * SD, SD, [&](int ln, int o, float v0, float v1) {
+                        const int n = node0 + ln, oc = blk * H + o;
+                        if (n < n_nodes) store_proj2<H>(P_out, Q_out, n, oc, v0 + sBP[oc], v1 + sBP[oc + 1], true);
+                    });
                 }
-                tile_gemm_mma<C::D4P / 8, 2 * H>(sHX, SD, sW1, SD, [&](int ln, int o, float v0, float v1) {
+            } else {
+                tile_gemm<D4, 5 * H, TN, CT, C::RN, 4>(sHX, SD, sWP, [&](int ln, int o, const float* acc) {
                     const int n = node0 + ln;
                     if (n < n_nodes) {
-                        if (o < H) { v0 += sB1[o]; v1 += sB1[o + 1]; }
-                        *reinterpret_cast<float2*>(P_out + (size_t)n * 2 * H + o) = make_float2(v0, v1);
+                        const float4 b = lds4(sBP + o);
+                        store_proj4<H>(P_out, Q_out, n, o, make_float4(acc[0] + b.x, acc[1] + b.y, acc[2] + b.z, acc[3] + b.w), write_q != 0);
                     }
                 });
-            } else {
-                store_hx_and_project<H, TN, CT, C::RNP, C::RCP>(sHX, SD, sW1, sB1, node0, n_nodes, HX_out, P_out);
             }
-            bar_sync(BAR_CONS, CT);   // sHX / sH1 are rewritten by the next tile
+            bar_sync(BAR_CONS, CT);   // sHX is rewritten by the next tile
         }
     }
 }
@@ -679,7 +595,7 @@ static inline int check_launch() {
 }
 
 template <int H>
-static int launch_input(const float* blob, const float* X, int n_nodes, int F, float* HX, float* P,
+static int launch_input(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
                         cudaStream_t st) {
     using C = InputCfg<H>;
     if (n_nodes == 0) return GNNSEG_OK;
@@ -687,7 +603,7 @@ static int launch_input(const float* blob, const float* X, int n_nodes, int F, f
     int grid = 0;
     const int rc = persistent_grid(input_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);
     if (rc) return rc;
-    input_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, HX, P);
+    input_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, P, Q);
     return check_launch();
 }
 
@@ -704,24 +620,23 @@ static int launch_edge(const float* blob, const GnnsegGraph* g, const float* P, 
     return check_launch();
 }
 
-int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* HX_in, const float* e,
-                     float* HX_out, float* P_out, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
+int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e,
+                     float* P_out, float* Q_out, int write_q, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
 
 template <int H>
-static int launch_node(const float* blob, const GnnsegGraph* g, const float* HX_in, const float* e,
-                       float* HX_out, float* P_out, cudaStream_t st) {
+static int launch_node(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e,
+                       float* P_out, float* Q_out, int write_q, cudaStream_t st) {
     using C = NodeCfg<H>;
     if (g->n_nodes == 0) return GNNSEG_OK;
     if (H == 32) {
-        const char* impl = getenv("GNNSEG_NODE_IMPL");   // "mma": legacy mma.sync path (for A/B runs)
-        if (!impl || impl[0] != 'm') return launch_node_tc32(blob, g, HX_in, e, HX_out, P_out, st);
+        const char* impl = getenv("GNNSEG_NODE_IMPL");   // "mma": generic mma.sync path (for A/B runs)
+        if (!impl || impl[0] != 'm') return launch_node_tc32(blob, g, X4, Q_in, e, P_out, Q_out, write_q, st);
     }
     const int n_tiles = (g->n_nodes + C::TN - 1) / C::TN;
     int grid = 0;
     const int rc = persistent_grid(node_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);
     if (rc) return rc;
-    const char* dbg_env = getenv("GNNSEG_DBG");
-    node_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, HX_in, e, n_tiles, HX_out, P_out, dbg_env ? atoi(dbg_env) : 0);
+    node_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e, n_tiles, P_out, Q_out, write_q);
     return check_launch();
 }
 
@@ -735,16 +650,16 @@ static int launch_node(const float* blob, const GnnsegGraph* g, const float* HX_
         default: return GNNSEG_EUNSUPPORTED;       \
     }
 
-int input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* HX, float* P,
+int input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* X4, float* P, float* Q,
                cudaStream_t st) {
-    GNNSEG_DISPATCH_H(h, launch_input<HH>(blob, X, n_nodes, F, HX, P, st));
+    GNNSEG_DISPATCH_H(h, launch_input<HH>(blob, X, n_nodes, F, X4, P, Q, st));
 }
 int edge_step(const float* blob, const GnnsegGraph* g, const float* P, int h, float* e, cudaStream_t st) {
     GNNSEG_DISPATCH_H(h, launch_edge<HH>(blob, g, P, e, st));
 }
-int node_step(const float* blob, const GnnsegGraph* g, const float* HX_in, const float* e, int h,
-              float* HX_out, float* P_out, cudaStream_t st) {
-    GNNSEG_DISPATCH_H(h, launch_node<HH>(blob, g, HX_in, e, HX_out, P_out, st));
+int node_step(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e, int h,
+              float* P_out, float* Q_out, int write_q, cudaStream_t st) {
+    GNNSEG_DISPATCH_H(h, launch_node<HH>(blob, g, X4, Q_in, e, P_out, Q_out, write_q, st));
 }
 int pack_weights(const GnnsegParams* p, int F, int h, float* blob, cudaStream_t st) {
     const int total = blob_total(h);

@@ -1,27 +1,24 @@
 // Node step on the 5th-generation tensor cores (tcgen05 + TMEM) for hidden_dim = 32.
 //
-// Same mathematics as node_kernel in gnnseg_forward.cu (gnn/model.py:113-125,154 of the
-// reference) and the same producer side (staged CSR slices, branch-free batched row gather, no
-// atomics, ascending-slot summation order).  What changes is the MLP: the three per-node GEMMs
-//     h1 = tanh([mi|mo|self] . W3^T + b3)      128 x 112(108) x 32
-//     H' = tanh(h1 . W4^T + b4)                128 x  32      x 32
-//     P' = [H'|X] . W1^T (+ b1)                128 x  40(36)  x 64
+// Same mathematics and dataflow as node_kernel in gnnseg_forward.cu (projection-first form of
+// gnn/model.py:113-125,154, see gnnseg_common.cuh) and the same gather contract (staged CSR
+// slices, branch-free batched row gather, no atomics, own term then in-edges then out-edges in
+// ascending slot order).  What changes is the MLP after the gather: the two per-node GEMMs
+//     H'      = tanh(h1 . W4^T + b4)                        128 x 32 x 32
+//     [P'|Q'] = [H'|X] . [W1a|W1b|W3a|W3b|W3c]^T + bias     128 x 40(36) x 160
 // run as tcgen05.mma kind::tf32 with fp32 accumulators in tensor memory.  fp32 accuracy is kept
 // with the 3xTF32 split: x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and
 // a.b ~= lo_a.hi_b + hi_a.lo_b + hi_a.hi_b, all three accumulated into the same TMEM tile.
 //
 // Data flow per 128-node tile (one CTA per SM, persistent):
 //   stagers (4 warps)     CSR slices of the tile after next -> (neighbour, weight) pairs in smem
-//   gather  (16 warps)    4 lanes per node: row gather -> A1_hi / A1_lo in shared memory,
-//                         canonical K-major core-matrix layout
-//   thread 0              GEMM1 (SS: A1 from smem, W3 from smem) -> D1 in TMEM, commit -> mbarrier
-//   epilogue (4 warps)    D1 -> regs -> +b3, tanh, split -> A2_hi / A2_lo in TMEM
-//   thread 0              GEMM2 (TS: A2 from TMEM, W4 from smem) -> D2
-//   epilogue              D2 -> +b4, tanh -> HX' to global; split, with X and zero pad -> A3 in TMEM
-//   thread 0              GEMM3 (TS) -> D3
-//   epilogue              D3 -> +b1 -> P' to global
-// A1 is released to the producers as soon as GEMM1 has completed, so the gather of tile t+1
-// overlaps everything after GEMM1 of tile t.
+//   gather  (16 warps)    8 lanes per node, one aligned 128-byte Q row per edge and instruction:
+//                         h1 = tanh(Qs + sum e Qi + sum e Qo) -> A_hi / A_lo in shared memory,
+//                         canonical K-major core-matrix layout (double buffered)
+//   thread 0              GEMM2 (SS: A from smem, W4 from smem) -> D2 in TMEM, commit -> mbarrier
+//   epilogue (4 warps)    D2 -> regs -> +b4, tanh, split, X and zero pad appended -> A3 in TMEM
+//   thread 0              GEMM3 (TS: A3 from TMEM, WP from smem) -> D3 (160 columns)
+//   epilogue              D3 -> +bias -> P' and Q' to global
 #include <cstdlib>
 #include "gnnseg_common.cuh"
 
@@ -31,53 +28,45 @@ template <int H>
 struct TcCfg {
     static constexpr int TM   = 128;                 // nodes per tile = UMMA M
     static constexpr int EW   = 4;                   // MLP warps (issuer + epilogue): warp w owns TMEM lanes 32w..32w+31
-    static constexpr int SW   = 4;                   // stager warps: CSR slices of the NEXT tile -> shared memory
-    static constexpr int GW   = 16;                  // gather warps: 4 lanes per node, the whole tile at once
+    static constexpr int SW   = 4;                   // stager warps
+    static constexpr int GW   = 16;                  // gather warps
     static constexpr int ET   = EW * 32;
     static constexpr int ST   = SW * 32;
     static constexpr int GT   = GW * 32;
     static constexpr int NT   = ET + ST + GT;
-    static constexpr int G    = 4;                   // lanes per node in the gather
-    static_assert(GT / G == TM, "one gather group per node of the tile");
-    static_assert(H == 32, "the gather lane map (2 float4 + 1 scalar per lane) is written for H = 32");
+    static constexpr int G    = H / 4;               // lanes per node in the gather: one float4 each
+    static constexpr int NGRP = GT / G;              // nodes gathered concurrently
+    static_assert(TM % NGRP == 0, "whole passes");
     static constexpr int D4   = H + 4;
-    static constexpr int K1   = 3 * D4;
-    static constexpr int K1P  = (K1 + 7) / 8 * 8;    // K of GEMM1, padded to the tf32 k-step
-    static constexpr int D4P  = (D4 + 7) / 8 * 8;    // K of GEMM3
+    static constexpr int D4P  = (D4 + 7) / 8 * 8;    // K of GEMM3, padded to the tf32 k-step
+    static constexpr int NP   = 5 * H;               // projection width
+    static_assert(H % 16 == 0 && NP % 16 == 0 && NP <= 256, "UMMA N constraints at M = 128");
     // canonical K-major, no swizzle: core matrix = 8 rows x 16 bytes, contiguous 128 bytes;
     // LBO = distance between core matrices along K, SBO = distance between 8-row groups
     static constexpr int LBO     = 128;
-    static constexpr int SBO_K1  = (K1P / 4) * LBO;
     static constexpr int SBO_H   = (H / 4) * LBO;
     static constexpr int SBO_D4  = (D4P / 4) * LBO;
-    static constexpr int A1_BYTES = (TM / 8) * SBO_K1;       // one of hi / lo
-    static constexpr int W3_BYTES = (H / 8) * SBO_K1;
+    static constexpr int A_BYTES  = (TM / 8) * SBO_H;        // one of hi / lo, one buffer
     static constexpr int W4_BYTES = (H / 8) * SBO_H;
-    static constexpr int W1_BYTES = (2 * H / 8) * SBO_D4;
+    static constexpr int WP_BYTES = (NP / 8) * SBO_D4;
     static constexpr int CAP  = 1536;                // staged CSR slots per direction per tile
     // shared memory map (bytes)
-    static constexpr int O_A1H = 0;
-    static constexpr int O_A1L = O_A1H + A1_BYTES;
-    static constexpr int O_W3H = O_A1L + A1_BYTES;
-    static constexpr int O_W3L = O_W3H + W3_BYTES;
-    static constexpr int O_W4H = O_W3L + W3_BYTES;
-    static constexpr int O_W4L = O_W4H + W4_BYTES;
-    static constexpr int O_W1H = O_W4L + W4_BYTES;
-    static constexpr int O_W1L = O_W1H + W1_BYTES;
-    static constexpr int O_BIAS = O_W1L + W1_BYTES;          // b3, b4, b1
+    static constexpr int O_A    = 0;                          // [2 buffers][hi, lo]
+    static constexpr int O_W4H  = O_A + 4 * A_BYTES;
+    static constexpr int O_W4L  = O_W4H + W4_BYTES;
+    static constexpr int O_WPH  = O_W4L + W4_BYTES;
+    static constexpr int O_WPL  = O_WPH + WP_BYTES;
+    static constexpr int O_BIAS = O_WPL + WP_BYTES;           // b4 [H], bias of the projections [5H]
     static constexpr int STAGE_BYTES = 2 * CAP * 8 + 2 * (TM + 4) * 4;   // [2][CAP] int2 + [2][TM+4] int
-    static constexpr int O_STAGE = O_BIAS + 3 * H * 4;       // two staging buffers (double buffered)
-    static constexpr int O_MBAR = O_STAGE + 2 * STAGE_BYTES; // mbarrier (8 B) + tmem base (4 B)
+    static constexpr int O_STAGE = O_BIAS + 6 * H * 4;        // two staging buffers
+    static constexpr int O_MBAR = O_STAGE + 2 * STAGE_BYTES;  // mbarrier (8 B) + tmem base (4 B)
     static constexpr int SMEM_BYTES = O_MBAR + 16;
     // tensor memory columns (fp32 cells, 128 lanes)
-    static constexpr int C_D1  = 0;
-    static constexpr int C_A2H = C_D1 + H;
-    static constexpr int C_A2L = C_A2H + H;
-    static constexpr int C_D2  = C_A2L + H;
+    static constexpr int C_D2  = 0;
     static constexpr int C_A3H = C_D2 + H;
     static constexpr int C_A3L = C_A3H + D4P;
     static constexpr int C_D3  = C_A3L + D4P;
-    static constexpr int C_END = C_D3 + 2 * H;
+    static constexpr int C_END = C_D3 + NP;
     static constexpr int TMEM_COLS = C_END <= 32 ? 32 : C_END <= 64 ? 64 : C_END <= 128 ? 128 : C_END <= 256 ? 256 : 512;
     static_assert(C_END <= 512, "tensor memory");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
@@ -184,126 +173,63 @@ __device__ __forceinline__ int canon_off(const int row, const int k, const int s
     return (row >> 3) * sbo + (k >> 2) * 128 + (row & 7) * 16 + (k & 3) * 4;
 }
 
-// One CSR row of the gather (same contract as csr_row_sum in gnnseg_forward.cu, staged form):
-// lane c of the node's 4-lane group owns float4 chunks c and c+4 of the hidden part and X[c].
-// Slots go in batches of U: every row load of the batch is issued before the first FMA (no
-// branch in between: an absent neighbour loads row 0 and is dropped by predication), then the
-// FMAs run in ascending slot order.
-template <int H>
-__device__ __forceinline__ void tc_row_sum(const int2* __restrict__ pairs, const float* __restrict__ HX,
-                                           const int beg, const int end, const int c, float4& acc0,
-                                           float4& acc1, float& acc_x) {
-    constexpr int D4 = H + 4, U = 4;
+// One CSR row of the gather, one float4 chunk of the aligned Q row per lane:
+// acc += w_s * Qcol[nbr_s] for s = beg..end-1 in ascending order.  Slots go in batches of U: all
+// row loads of the batch are issued before the first FMA (no branch in between: an absent slot or
+// neighbour is predicated off).  STAGED: pairs come from shared memory.
+template <bool STAGED>
+__device__ __forceinline__ void tc_row_sum(const int2* __restrict__ pairs, const int32_t* __restrict__ eid,
+                                           const int32_t* __restrict__ nbr, const float* __restrict__ e,
+                                           const float* __restrict__ Qcol, const int row_floats,
+                                           const int beg, const int end, float4& acc) {
+    constexpr int U = 8;
     for (int s0 = beg; s0 < end; s0 += U) {
-        float w[U], vx[U];
+        float w[U];
         bool ok[U];
-        float4 v0[U], v1[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int2 pr = pairs[min(s0 + u, end - 1)];
-            w[u] = __int_as_float(pr.y);
-            ok[u] = (s0 + u < end) && pr.x >= 0;     // pr.x < 0: half edge, gathers the zero row
-            const float* row = HX + (size_t)max(pr.x, 0) * D4;
-            v0[u] = ldg4(row + 4 * c);
-            v1[u] = ldg4(row + 16 + 4 * c);
-            vx[u] = __ldg(row + H + c);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (ok[u]) {
-                fma4(acc0, w[u], v0[u]);
-                fma4(acc1, w[u], v1[u]);
-                acc_x = fmaf(w[u], vx[u], acc_x);
-            }
-    }
-}
-// Path for a tile whose CSR slice does not fit the staging buffer: same batching, but the
-// (neighbour, weight) pairs come straight from global memory (one more dependent load level).
-template <int H>
-__device__ __forceinline__ void tc_row_sum_direct(const int32_t* __restrict__ eid, const int32_t* __restrict__ nbr,
-                                                  const float* __restrict__ e, const float* __restrict__ HX,
-                                                  const int beg, const int end, const int c, float4& acc0,
-                                                  float4& acc1, float& acc_x) {
-    constexpr int D4 = H + 4, U = 4;
-    for (int s0 = beg; s0 < end; s0 += U) {
-        float w[U], vx[U];
-        bool ok[U];
-        float4 v0[U], v1[U];
+        float4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int s = min(s0 + u, end - 1);
-            const int nb = __ldg(nbr + s);
-            w[u] = __ldg(e + __ldg(eid + s));
-            ok[u] = (s0 + u < end) && nb >= 0;
-            const float* row = HX + (size_t)max(nb, 0) * D4;
-            v0[u] = ldg4(row + 4 * c);
-            v1[u] = ldg4(row + 16 + 4 * c);
-            vx[u] = __ldg(row + H + c);
+            int nb;
+            if (STAGED) {
+                const int2 pr = pairs[s];
+                nb = pr.x;
+                w[u] = __int_as_float(pr.y);
+            } else {
+                nb = __ldg(nbr + s);
+                w[u] = __ldg(e + __ldg(eid + s));
+            }
+            ok[u] = (s0 + u < end) && nb >= 0;       // nb < 0: half edge, gathers the zero row
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[u]) v[u] = ldg4(Qcol + (size_t)nb * row_floats);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (ok[u]) {
-                fma4(acc0, w[u], v0[u]);
-                fma4(acc1, w[u], v1[u]);
-                acc_x = fmaf(w[u], vx[u], acc_x);
-            }
+            if (ok[u]) fma4(acc, w[u], v[u]);
     }
-}
-// split the lane's share of a row part and store it into A1_hi / A1_lo (canonical layout);
-// part = 0 mi, 1 mo, 2 self
-template <int H>
-__device__ __forceinline__ void tc_store_part(unsigned char* __restrict__ a1h, unsigned char* __restrict__ a1l,
-                                              const int sbo, const int ln, const int part, const int c,
-                                              const float4 h0, const float4 h1, const float x) {
-    constexpr int D4 = H + 4;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const float4 h = half ? h1 : h0;
-        float4 hh, hl;
-        split3(h.x, hh.x, hl.x); split3(h.y, hh.y, hl.y); split3(h.z, hh.z, hl.z); split3(h.w, hh.w, hl.w);
-        const int off = canon_off(ln, part * D4 + 16 * half + 4 * c, sbo);
-        *reinterpret_cast<float4*>(a1h + off) = hh;
-        *reinterpret_cast<float4*>(a1l + off) = hl;
-    }
-    float xh, xl;
-    split3(x, xh, xl);
-    const int ox = canon_off(ln, part * D4 + H + c, sbo);
-    *reinterpret_cast<float*>(a1h + ox) = xh;
-    *reinterpret_cast<float*>(a1l + ox) = xl;
 }
 
 template <int H>
 __global__ void __launch_bounds__(TcCfg<H>::NT, 1)
-node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float* __restrict__ HX_in,
-               const float* __restrict__ e, const int n_tiles, float* __restrict__ HX_out,
-               float* __restrict__ P_out) {
+node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float* __restrict__ X4,
+               const float* __restrict__ Q_in, const float* __restrict__ e, const int n_tiles,
+               float* __restrict__ P_out, float* __restrict__ Q_out, const int write_q) {
     using C = TcCfg<H>;
     using B = Blob<H>;
-    constexpr int TM = C::TM, NT = C::NT, ET = C::ET, ST = C::ST, GT = C::GT, D4 = C::D4, K1 = C::K1;
-    // named barriers: A1 full / empty (gather <-> MLP), MLP-internal, staging full / empty x2
-    // (stager <-> gather), stager-internal
-    constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_EPI = 3, BAR_SFULL = 4, BAR_SEMPTY = 6, BAR_STG = 8;
+    constexpr int TM = C::TM, NT = C::NT, ET = C::ET, ST = C::ST, GT = C::GT, D4 = C::D4, NP = C::NP;
+    // named barriers: A full / empty per buffer (gather <-> MLP), MLP-internal, staging full /
+    // empty per buffer (stager <-> gather), stager-internal
+    constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_EPI = 5, BAR_SFULL = 6, BAR_SEMPTY = 8, BAR_STG = 10;
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* a1h = smem + C::O_A1H;
-    unsigned char* a1l = smem + C::O_A1L;
-    float* sB3 = reinterpret_cast<float*>(smem + C::O_BIAS);
-    float* sB4 = sB3 + H;
-    float* sB1 = sB4 + H;
+    float* sB4 = reinterpret_cast<float*>(smem + C::O_BIAS);
+    float* sBP = sB4 + H;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_nodes = g.n_nodes;
 
-    // ---- prologue: weights (hi/lo, canonical layout), biases, zero padding, TMEM, mbarrier ----
-    for (int i = tid; i < H * C::K1P; i += NT) {          // W3: [H outputs][K1P]
-        const int j = i / C::K1P, k = i % C::K1P;
-        float hi, lo;
-        split3(k < K1 ? __ldg(blob + B::W3 + k * H + j) : 0.f, hi, lo);
-        const int off = canon_off(j, k, C::SBO_K1);
-        *reinterpret_cast<float*>(smem + C::O_W3H + off) = hi;
-        *reinterpret_cast<float*>(smem + C::O_W3L + off) = lo;
-    }
-    for (int i = tid; i < H * H; i += NT) {               // W4: [H][H]
+    // ---- prologue: weights (hi/lo, canonical layout), biases, TMEM, mbarrier ------------------
+    for (int i = tid; i < H * H; i += NT) {               // W4: [H outputs][H]
         const int j = i / H, k = i % H;
         float hi, lo;
         split3(__ldg(blob + B::W4 + k * H + j), hi, lo);
@@ -311,24 +237,16 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
         *reinterpret_cast<float*>(smem + C::O_W4H + off) = hi;
         *reinterpret_cast<float*>(smem + C::O_W4L + off) = lo;
     }
-    for (int i = tid; i < 2 * H * C::D4P; i += NT) {      // W1: [2H][D4P]
+    for (int i = tid; i < NP * C::D4P; i += NT) {         // WP: [5H outputs][D4P]
         const int j = i / C::D4P, k = i % C::D4P;
         float hi, lo;
-        split3(k < D4 ? __ldg(blob + B::W1 + k * 2 * H + j) : 0.f, hi, lo);
+        split3(k < D4 ? __ldg(blob + B::WP + k * NP + j) : 0.f, hi, lo);
         const int off = canon_off(j, k, C::SBO_D4);
-        *reinterpret_cast<float*>(smem + C::O_W1H + off) = hi;
-        *reinterpret_cast<float*>(smem + C::O_W1L + off) = lo;
+        *reinterpret_cast<float*>(smem + C::O_WPH + off) = hi;
+        *reinterpret_cast<float*>(smem + C::O_WPL + off) = lo;
     }
-    for (int i = tid; i < H; i += NT) {
-        sB3[i] = __ldg(blob + B::B3 + i);
-        sB4[i] = __ldg(blob + B::B4 + i);
-        sB1[i] = __ldg(blob + B::B1 + i);
-    }
-    for (int i = tid; i < TM * (C::K1P - K1); i += NT) {   // K padding of A1 stays zero for ever
-        const int off = canon_off(i / (C::K1P - K1), K1 + i % (C::K1P - K1), C::SBO_K1);
-        *reinterpret_cast<float*>(a1h + off) = 0.f;
-        *reinterpret_cast<float*>(a1l + off) = 0.f;
-    }
+    for (int i = tid; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
+    for (int i = tid; i < NP; i += NT) sBP[i] = __ldg(blob + B::BP + i);
     if (tid == 0) {
         mbar_init(smem_u32(mbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -346,47 +264,47 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
 
     if (tid >= ET + ST) {
         // ================================ gather warps ==================================
-        constexpr int CAP = C::CAP;
+        constexpr int CAP = C::CAP, G = C::G, NGRP = C::NGRP;
         const int gt = tid - ET - ST;
-        const int ln = gt >> 2, c = gt & 3;                   // node of the tile, lane in its group
+        const int grp = gt / G, c = gt % G;                   // node slot of the pass, float4 chunk
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int sb = it & 1;
             const int2* sPair = reinterpret_cast<const int2*>(smem + C::O_STAGE + sb * C::STAGE_BYTES);
             const int* sPtr = reinterpret_cast<const int*>(smem + C::O_STAGE + sb * C::STAGE_BYTES + 2 * CAP * 8);
-            const int n = tile * TM + ln;
-            const bool live = n < n_nodes;
-            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-            float sx = 0.f;
-            if (live) {                                        // own row first: needs no staging
-                const float* row = HX_in + (size_t)n * D4;
-                s0 = ldg4(row + 4 * c);
-                s1 = ldg4(row + 16 + 4 * c);
-                sx = __ldg(row + H + c);
-            }
+            unsigned char* ah = smem + C::O_A + sb * 2 * C::A_BYTES;
+            unsigned char* al = ah + C::A_BYTES;
+            const int node0 = tile * TM;
             tc_bar_sync(BAR_SFULL + sb, ST + GT);              // this tile's CSR slices are staged
+            if (it >= 2) tc_bar_sync(BAR_EMPTY + sb, ET + GT); // GEMM2 of tile it-2 has read this A buffer
             const int ib = sPtr[0], ic = sPtr[TM] - ib;
             const int ob = sPtr[TM + 4], oc = sPtr[TM + 4 + TM] - ob;
             const bool staged = ic <= CAP && oc <= CAP;       // CTA-uniform
-            const int i0 = sPtr[ln], i1 = live ? sPtr[ln + 1] : i0;
-            const int o0 = sPtr[TM + 4 + ln], o1 = live ? sPtr[TM + 4 + ln + 1] : o0;
-            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 i_0 = zero, i_1 = zero, o_0 = zero, o_1 = zero;
-            float i_x = 0.f, o_x = 0.f;
-            if (staged) {
-                tc_row_sum<H>(sPair, HX_in, i0 - ib, i1 - ib, c, i_0, i_1, i_x);
-                tc_row_sum<H>(sPair + CAP, HX_in, o0 - ob, o1 - ob, c, o_0, o_1, o_x);
-            } else {
-                tc_row_sum_direct<H>(g.in_eid, g.in_nbr, e, HX_in, i0, i1, c, i_0, i_1, i_x);
-                tc_row_sum_direct<H>(g.out_eid, g.out_nbr, e, HX_in, o0, o1, c, o_0, o_1, o_x);
+#pragma unroll 1
+            for (int ln = grp; ln < TM; ln += NGRP) {
+                const int n = node0 + ln;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < n_nodes) {
+                    acc = ldg4(Q_in + (size_t)n * 3 * H + 2 * H + 4 * c);            // Qs[n] (holds b3)
+                    const int i0 = sPtr[ln], i1 = sPtr[ln + 1], o0 = sPtr[TM + 4 + ln], o1 = sPtr[TM + 4 + ln + 1];
+                    if (staged) {
+                        tc_row_sum<true>(sPair, nullptr, nullptr, nullptr, Q_in + 4 * c, 3 * H, i0 - ib, i1 - ib, acc);
+                        tc_row_sum<true>(sPair + CAP, nullptr, nullptr, nullptr, Q_in + H + 4 * c, 3 * H, o0 - ob, o1 - ob, acc);
+                    } else {
+                        tc_row_sum<false>(nullptr, g.in_eid, g.in_nbr, e, Q_in + 4 * c, 3 * H, i0, i1, acc);
+                        tc_row_sum<false>(nullptr, g.out_eid, g.out_nbr, e, Q_in + H + 4 * c, 3 * H, o0, o1, acc);
+                    }
+                    acc.x = tanhf(acc.x); acc.y = tanhf(acc.y); acc.z = tanhf(acc.z); acc.w = tanhf(acc.w);
+                }
+                float4 hh, hl;
+                split3(acc.x, hh.x, hl.x); split3(acc.y, hh.y, hl.y); split3(acc.z, hh.z, hl.z); split3(acc.w, hh.w, hl.w);
+                const int off = canon_off(ln, 4 * c, C::SBO_H);
+                *reinterpret_cast<float4*>(ah + off) = hh;
+                *reinterpret_cast<float4*>(al + off) = hl;
             }
             if (tile + 2 * (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_SEMPTY + sb, ST + GT);   // staging buffer free
-            if (it >= 1) tc_bar_sync(BAR_EMPTY, ET + GT);      // GEMM1 of the previous tile has read A1
-            tc_store_part<H>(a1h, a1l, C::SBO_K1, ln, 0, c, i_0, i_1, i_x);
-            tc_store_part<H>(a1h, a1l, C::SBO_K1, ln, 1, c, o_0, o_1, o_x);
-            tc_store_part<H>(a1h, a1l, C::SBO_K1, ln, 2, c, s0, s1, sx);
             fence_async_smem();                                // generic-proxy writes -> tensor core reads
-            tc_bar_arrive(BAR_FULL, ET + GT);
+            tc_bar_arrive(BAR_FULL + sb, ET + GT);
         }
     } else if (tid >= ET) {
         // ================================ stager warps ==================================
@@ -422,86 +340,48 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
         const uint32_t mb = smem_u32(mbar);
         const int row = warp * 32 + lane;                     // node within the tile = TMEM lane
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        constexpr uint32_t ID1 = idesc_tf32(TM, H), ID3 = idesc_tf32(TM, 2 * H);
+        constexpr uint32_t ID2 = idesc_tf32(TM, H), ID3 = idesc_tf32(TM, NP);
         const uint32_t sa = smem_u32(smem);
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int node0 = tile * TM;
-            const int n = node0 + row;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int sb = it & 1;
+            const int n = tile * TM + row;
             const bool live = n < n_nodes;
-            // ---- GEMM1: D1 = A1 . W3^T  (A and B from shared memory) ----------------------
-            tc_bar_sync(BAR_FULL, ET + GT);
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) x = ldg4(X4 + (size_t)n * 4);           // early: independent of the gather
+            // ---- GEMM2: D2 = h1 . W4^T  (A and B from shared memory) ----------------------
+            tc_bar_sync(BAR_FULL + sb, ET + GT);
             if (tid == 0) {
                 tc_fence_after();
-#pragma unroll 1
-                for (int kq = 0; kq < C::K1P / 8; ++kq) {
-                    const uint32_t ko = kq * 2 * C::LBO;      // 8 tf32 = two 16-byte core columns
-                    const uint64_t ah = smem_desc(sa + C::O_A1H + ko, C::LBO, C::SBO_K1);
-                    const uint64_t al = smem_desc(sa + C::O_A1L + ko, C::LBO, C::SBO_K1);
-                    const uint64_t bh = smem_desc(sa + C::O_W3H + ko, C::LBO, C::SBO_K1);
-                    const uint64_t bl = smem_desc(sa + C::O_W3L + ko, C::LBO, C::SBO_K1);
-                    umma_ss(tmem + C::C_D1, al, bh, ID1, kq > 0);
-                    umma_ss(tmem + C::C_D1, ah, bl, ID1, 1);
-                    umma_ss(tmem + C::C_D1, ah, bh, ID1, 1);
-                }
-                umma_commit(mb);
-            }
-            mbar_wait(mb, phase); phase ^= 1;
-            tc_fence_after();
-            if (tile + (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY, ET + GT);   // A1 may be refilled
-            // ---- epilogue 1: h1 = tanh(D1 + b3) -> A2 (hi, lo) in TMEM ---------------------
+                const uint32_t a_hi = sa + C::O_A + sb * 2 * C::A_BYTES, a_lo = a_hi + C::A_BYTES;
 #pragma unroll
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                float v[16], hi[16], lo[16];
-                tmem_ld16(lane_base + C::C_D1 + c0, v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) split3(tanhf(v[i] + sB3[c0 + i]), hi[i], lo[i]);
-                tmem_st16(lane_base + C::C_A2H + c0, hi);
-                tmem_st16(lane_base + C::C_A2L + c0, lo);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            tc_bar_sync(BAR_EPI, ET);
-            // ---- GEMM2: D2 = A2 . W4^T  (A from tensor memory) ----------------------------
-            if (tid == 0) {
-                tc_fence_after();
-#pragma unroll 1
                 for (int kq = 0; kq < H / 8; ++kq) {
-                    const uint32_t ko = kq * 2 * C::LBO;
+                    const uint32_t ko = kq * 2 * C::LBO;      // 8 tf32 = two 16-byte core columns
+                    const uint64_t ah = smem_desc(a_hi + ko, C::LBO, C::SBO_H);
+                    const uint64_t al = smem_desc(a_lo + ko, C::LBO, C::SBO_H);
                     const uint64_t bh = smem_desc(sa + C::O_W4H + ko, C::LBO, C::SBO_H);
                     const uint64_t bl = smem_desc(sa + C::O_W4L + ko, C::LBO, C::SBO_H);
-                    umma_ts(tmem + C::C_D2, tmem + C::C_A2L + 8 * kq, bh, ID1, kq > 0);
-                    umma_ts(tmem + C::C_D2, tmem + C::C_A2H + 8 * kq, bl, ID1, 1);
-                    umma_ts(tmem + C::C_D2, tmem + C::C_A2H + 8 * kq, bh, ID1, 1);
+                    umma_ss(tmem + C::C_D2, al, bh, ID2, kq > 0);
+                    umma_ss(tmem + C::C_D2, ah, bl, ID2, 1);
+                    umma_ss(tmem + C::C_D2, ah, bh, ID2, 1);
                 }
                 umma_commit(mb);
             }
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
-            // ---- epilogue 2: H' = tanh(D2 + b4) -> global HX', and [H'|X|0] -> A3 in TMEM ---
+            if (tile + 2 * (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY + sb, ET + GT);   // A buffer may be refilled
+            // ---- epilogue 2: H' = tanh(D2 + b4); [H'|X|0] -> A3 (hi, lo) in TMEM -------------
 #pragma unroll
             for (int c0 = 0; c0 < H; c0 += 16) {
                 float v[16], hi[16], lo[16];
                 tmem_ld16(lane_base + C::C_D2 + c0, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    v[i] = tanhf(v[i] + sB4[c0 + i]);
-                    split3(v[i], hi[i], lo[i]);
-                }
-                if (live) {
-                    float* dst = HX_out + (size_t)n * D4 + c0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-                }
+                for (int i = 0; i < 16; ++i) split3(tanhf(v[i] + sB4[c0 + i]), hi[i], lo[i]);
                 tmem_st16(lane_base + C::C_A3H + c0, hi);
                 tmem_st16(lane_base + C::C_A3L + c0, lo);
             }
             {                                                     // columns H..H+7: X and the zero K padding
-                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (live) {
-                    x = ldg4(HX_in + (size_t)n * D4 + H);
-                    st4(HX_out + (size_t)n * D4 + H, x);
-                }
                 float xh[8], xl[8];
                 split3(x.x, xh[0], xl[0]); split3(x.y, xh[1], xl[1]);
                 split3(x.z, xh[2], xl[2]); split3(x.w, xh[3], xl[3]);
@@ -513,14 +393,14 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             tmem_st_wait();
             tc_fence_before();
             tc_bar_sync(BAR_EPI, ET);
-            // ---- GEMM3: D3 = A3 . W1^T ----------------------------------------------------
+            // ---- GEMM3: D3 = [H'|X] . WP^T  (A from tensor memory) --------------------------
             if (tid == 0) {
                 tc_fence_after();
-#pragma unroll 1
+#pragma unroll
                 for (int kq = 0; kq < C::D4P / 8; ++kq) {
                     const uint32_t ko = kq * 2 * C::LBO;
-                    const uint64_t bh = smem_desc(sa + C::O_W1H + ko, C::LBO, C::SBO_D4);
-                    const uint64_t bl = smem_desc(sa + C::O_W1L + ko, C::LBO, C::SBO_D4);
+                    const uint64_t bh = smem_desc(sa + C::O_WPH + ko, C::LBO, C::SBO_D4);
+                    const uint64_t bl = smem_desc(sa + C::O_WPL + ko, C::LBO, C::SBO_D4);
                     umma_ts(tmem + C::C_D3, tmem + C::C_A3L + 8 * kq, bh, ID3, kq > 0);
                     umma_ts(tmem + C::C_D3, tmem + C::C_A3H + 8 * kq, bl, ID3, 1);
                     umma_ts(tmem + C::C_D3, tmem + C::C_A3H + 8 * kq, bh, ID3, 1);
@@ -529,19 +409,19 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             }
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
-            // ---- epilogue 3: P' = D3 (+ b1 on the source half) -> global ---------------------
-#pragma unroll
-            for (int c0 = 0; c0 < 2 * H; c0 += 16) {
+            // ---- epilogue 3: [P'|Q'] = D3 + bias -> global ------------------------------------
+            const int c_end = write_q ? NP : 2 * H;
+#pragma unroll 1
+            for (int c0 = 0; c0 < c_end; c0 += 16) {
                 float v[16];
                 tmem_ld16(lane_base + C::C_D3 + c0, v);
-                if (c0 < H) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += sB1[c0 + i];
-                }
                 if (live) {
-                    float* dst = P_out + (size_t)n * 2 * H + c0;
+                    float* dst = c0 < 2 * H ? P_out + (size_t)n * 2 * H + c0 : Q_out + (size_t)n * 3 * H + (c0 - 2 * H);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b = lds4(sBP + c0 + 4 * i);
+                        st4(dst + 4 * i, make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w));
+                    }
                 }
             }
             tc_fence_before();
@@ -557,8 +437,8 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
     }
 }
 
-int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* HX_in, const float* e,
-                     float* HX_out, float* P_out, cudaStream_t st) {
+int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e,
+                     float* P_out, float* Q_out, int write_q, cudaStream_t st) {
     using C = TcCfg<32>;
     if (g->n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (g->n_nodes + C::TM - 1) / C::TM;
@@ -569,7 +449,7 @@ int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* HX_in
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
         return GNNSEG_ENODEVICE;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    node_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, HX_in, e, n_tiles, HX_out, P_out);
+    node_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e, n_tiles, P_out, Q_out, write_q);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 

@@ -135,19 +135,25 @@ int gnnseg_forward(const float* blob, const GnnsegGraph* graph, const float* X,
                    void* ws, size_t ws_bytes, void* stream);
 
 /*
- * The three steps on their own (used by the per-kernel parity tests).  HX is the
- * (n_nodes, h+4) row layout [hidden(h) | X(F) | 0-pad], P is (n_nodes, 2h):
- * P[n,0:h] = W1[:, 0:D].HX[n] + b1 and P[n,h:2h] = W1[:, D:2D].HX[n].
- *   gnnseg_input_step : input_network + cat([H,X])               gnn/model.py:144-146
- *   gnnseg_edge_step  : EdgeNetwork.forward                       gnn/model.py:69-81
- *   gnnseg_node_step  : NodeNetwork.forward + cat([H,X])          gnn/model.py:113-125,154
+ * The three steps on their own (used by the per-kernel parity tests).  State arrays, with
+ * HX[n] = [hidden(h) | X(F)] and D = h + F (the reference's cat([H, X]), gnn/model.py:146,154):
+ *   X4 (n_nodes, 4)   X zero padded to 4 columns
+ *   P  (n_nodes, 2h)  [ W1[:, 0:D].HX + b1 | W1[:, D:2D].HX ]                 edge-step inputs
+ *   Q  (n_nodes, 3h)  [ W3[:, 0:D].HX | W3[:, D:2D].HX | W3[:, 2D:3D].HX + b3 ] node-step inputs
+ * (W1 = edge_network.network.0.weight, W3 = node_network.network.0.weight: the first linear
+ * layer of each network is applied per node before the gather, which is the same algebra.)
+ *   gnnseg_input_step : input_network + cat([H,X]) + projections      gnn/model.py:144-146
+ *   gnnseg_edge_step  : EdgeNetwork.forward                            gnn/model.py:69-81
+ *   gnnseg_node_step  : NodeNetwork.forward + cat([H,X]) + projections gnn/model.py:113-125,154
+ *                       Q_out may be NULL when no further node step follows.
  */
-int gnnseg_input_step(const float* blob, const float* X, int n_nodes, int F, int h,
-                      float* HX, float* P, void* stream);
+int gnnseg_input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* X4,
+                      float* P, float* Q, void* stream);
 int gnnseg_edge_step(const float* blob, const GnnsegGraph* graph, const float* P, int h,
                      float* e, void* stream);
-int gnnseg_node_step(const float* blob, const GnnsegGraph* graph, const float* HX_in,
-                     const float* e, int h, float* HX_out, float* P_out, void* stream);
+int gnnseg_node_step(const float* blob, const GnnsegGraph* graph, const float* X4,
+                     const float* Q_in, const float* e, int h, float* P_out, float* Q_out,
+                     void* stream);
 
 /* ---- host side: replaces graph_from_sparse + merge_graphs + np_to_torch --------------- */
 

@@ -134,6 +134,18 @@ def sparse_forward(p, X, src, dst, n_iters, dtype=torch.float32, return_state=Fa
         return (out, H) if return_state else out
 
 
+def projections(p, HX):
+    """Per-node first-layer projections the CUDA path carries between kernels (same algebra as
+    gnn/model.py:73-81,120-125: W.[a;b;c] = Wa.a + Wb.b + Wc.c).  HX (n, D) = [H | X].
+    Returns P (n, 2h) = [W1a.HX + b1 | W1b.HX] and Q (n, 3h) = [W3a.HX | W3b.HX | W3c.HX + b3]."""
+    D = HX.shape[1]
+    W1, b1 = p[PARAM_KEYS[2]], p[PARAM_KEYS[3]]
+    W3, b3 = p[PARAM_KEYS[6]], p[PARAM_KEYS[7]]
+    P = torch.cat([HX @ W1[:, :D].T + b1, HX @ W1[:, D:].T], dim=1)
+    Q = torch.cat([HX @ W3[:, :D].T, HX @ W3[:, D:2 * D].T, HX @ W3[:, 2 * D:].T + b3], dim=1)
+    return P, Q
+
+
 # ---- integer side --------------------------------------------------------------------------
 def edges_from_dense(Ri, Ro):
     """(B,N,E) 0/1 arrays -> per-slot endpoints src/dst (B*E,), flattened node ids b*N+n,

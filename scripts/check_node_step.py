@@ -1,4 +1,4 @@
-"""Debug helper: run input/edge/node steps on cuda:0 for one golden case and print error stats."""
+"""Debug helper: run input/edge/node steps on cuda:0 for one case and print error stats."""
 import ctypes as C
 import sys
 import numpy as np
@@ -28,29 +28,25 @@ else:
 L = _lib.lib()
 n = batch.n_nodes
 blob = model.pack_weights()
-HX = torch.zeros(n, h + 4, device=dev); HX2 = torch.full((n, h + 4), 7.0, device=dev)
-P = torch.zeros(n, 2 * h, device=dev); P2 = torch.full((n, 2 * h), 7.0, device=dev)
-e = torch.zeros(batch.n_slots, device=dev)
+X4 = torch.zeros(n, 4, device=dev)
+P = torch.zeros(n, 2 * h, device=dev); Q = torch.zeros(n, 3 * h, device=dev)
+P2 = torch.full((n, 2 * h), 7.0, device=dev); Q2 = torch.full((n, 3 * h), 7.0, device=dev)
 st = _stream_ptr(dev)
 src, dst, Xh = batch.src.cpu().long(), batch.dst.cpu().long(), batch.X.cpu()
-assert L.gnnseg_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(HX), _ptr(P), st) == 0
+assert L.gnnseg_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(X4), _ptr(P), _ptr(Q), st) == 0
 H0 = O.sparse_input(p, Xh)
+Pref, Qref = O.projections(p, H0)
+print("input: P err %.3e  Q err %.3e" % ((P.cpu() - Pref).abs().max().item(), (Q.cpu() - Qref).abs().max().item()))
 e_ref = O.sparse_edge(p, H0, src, dst)
-e_in = e_ref.to(dev).contiguous()
-rc = L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(HX), _ptr(e_in), h, _ptr(HX2), _ptr(P2), st)
+e_in = e_ref.to(dev).contiguous(); Q_in = Qref.to(dev).contiguous()
+rc = L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q_in), _ptr(e_in), h, _ptr(P2), _ptr(Q2), st)
 torch.cuda.synchronize()
 print("node_step rc", rc)
-H1 = O.sparse_node(p, H0, e_ref, src, dst)
-got = HX2.cpu()
-dH = (got[:, :h] - H1).abs()
-print("H' max abs err %.3e  (rows with err>1e-4: %d of %d)" % (dH.max().item(), int((dH.max(1).values > 1e-4).sum()), n))
-print("X part equal:", bool(torch.equal(got[:, h:h + F], Xh)), " pad zero:", bool((got[:, h + F:] == 0).all()))
-HXn = torch.cat([H1, Xh], 1)
-W1 = p[O.PARAM_KEYS[2]]; D = h + F
-Pref = torch.cat([HXn @ W1[:, :D].T + p[O.PARAM_KEYS[3]], HXn @ W1[:, D:].T], 1)
-dP = (P2.cpu() - Pref).abs()
-print("P' max abs err %.3e" % dP.max().item())
-if dH.max() > 1e-4:
-    bad = torch.nonzero(dH.max(1).values > 1e-4).flatten()[:10]
-    print("first bad rows", bad.tolist())
-    r = int(bad[0]); print("got", got[r, :8].tolist()); print("ref", H1[r, :8].tolist())
+H1 = torch.cat([O.sparse_node(p, H0, e_ref, src, dst), Xh], 1)
+P1, Q1 = O.projections(p, H1)
+dP = (P2.cpu() - P1).abs(); dQ = (Q2.cpu() - Q1).abs()
+print("node: P' max abs err %.3e (bad rows %d)  Q' max abs err %.3e (bad rows %d) of %d" % (
+    dP.max().item(), int((dP.max(1).values > 1e-4).sum()), dQ.max().item(), int((dQ.max(1).values > 1e-4).sum()), n))
+if dP.max() > 1e-4:
+    bad = torch.nonzero(dP.max(1).values > 1e-4).flatten()[:10]
+    print("first bad rows", bad.tolist()); r = int(bad[0]); print("got", P2[r, :8].tolist()); print("ref", P1[r, :8].tolist())

@@ -38,10 +38,11 @@ def test_host_only_queries():
     for F, h in ((0, 8), (5, 8), (3, 12), (3, 128), (3, 0)):
         assert L.gnnseg_supported(F, h) == 0
         assert L.gnnseg_weights_floats(F, h) == 0
-    # blob size: Win^T[4][h] + b_in + W1^T[(h+4)][2h] + b1 + W2 + 4 + W3^T[3(h+4)][h] + b3 + W4^T + b4
+    # blob size: Win^T[4][h] + b_in + WP^T[(h+4)][5h] + bias[5h] + W2 + 4 + W4^T + b4
     h = 32
-    assert L.gnnseg_weights_floats(3, h) == 4 * h + h + (h + 4) * 2 * h + h + h + 4 + 3 * (h + 4) * h + h + h * h + h
-    assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 32) >= 4 * (2 * 1000 * 36 + 1000 * 64 + 5000)
+    assert L.gnnseg_weights_floats(3, h) == 4 * h + h + (h + 4) * 5 * h + 5 * h + h + 4 + h * h + h
+    # workspace: X4 + P + 2 Q + e
+    assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 32) >= 4 * (1000 * 4 + 1000 * 64 + 2 * 1000 * 96 + 5000)
     assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 12) == 0
     assert L.gnnseg_csr_workspace_bytes(1000, 5000) >= 8 * 1001
 

@@ -169,44 +169,51 @@ def _steps_setup(rec, device):
 
 @pytest.mark.parametrize("name", ["acts_ragged_h32_it4", "acts_h64_it6", "toy2d_h4_it1", "toy2d_h16_it3", "acts_masked_h8_it4"])
 def test_each_kernel_against_oracle(name, cuda_device):
-    """gnnseg_input_step / gnnseg_edge_step / gnnseg_node_step one at a time vs the oracle."""
+    """gnnseg_input_step / gnnseg_edge_step / gnnseg_node_step one at a time vs the oracle.
+    The state between kernels is X4, P = [W1a.HX+b1 | W1b.HX], Q = [W3a.HX | W3b.HX | W3c.HX+b3]
+    (include/gnnseg.h); the oracle computes HX the reference's way and projects it."""
     from gnn_fpga_b200.graph import _ptr, _stream_ptr
     rec = load_case(name)
     model, batch, L = _steps_setup(rec, cuda_device)
     p = O.apply_masks(rec["params"], rec["masks_e"], rec["masks_n"])
     h, F, n = rec["h"], rec["F"], batch.n_nodes
     blob = model.pack_weights()
-    HX = torch.zeros(n, h + 4, device=cuda_device)
-    HX2 = torch.zeros_like(HX)
+    X4 = torch.full((n, 4), 7.0, device=cuda_device)
     P = torch.zeros(n, 2 * h, device=cuda_device)
+    Q = torch.zeros(n, 3 * h, device=cuda_device)
+    P2 = torch.zeros_like(P)
+    Q2 = torch.zeros_like(Q)
     e = torch.zeros(batch.n_slots, device=cuda_device)
     st = _stream_ptr(cuda_device)
     src = batch.src.cpu().long()
     dst = batch.dst.cpu().long()
     Xh = batch.X.cpu()
 
-    assert L.gnnseg_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(HX), _ptr(P), st) == 0
+    assert L.gnnseg_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(X4), _ptr(P), _ptr(Q), st) == 0
     H0 = O.sparse_input(p, Xh)                                   # (n, h+F)
-    got = HX.cpu()
-    assert torch.allclose(got[:, :h], H0[:, :h], rtol=1e-5, atol=1e-6)
-    assert torch.equal(got[:, h:h + F], Xh) and torch.all(got[:, h + F:] == 0)
-    W1 = p[O.PARAM_KEYS[2]]
-    D = h + F
-    Ps = H0 @ W1[:, :D].T + p[O.PARAM_KEYS[3]]
-    Pd = H0 @ W1[:, D:].T
-    assert torch.allclose(P.cpu(), torch.cat([Ps, Pd], 1), rtol=1e-5, atol=2e-6)
+    Pref, Qref = O.projections(p, H0)
+    assert torch.equal(X4.cpu()[:, :F], Xh) and torch.all(X4.cpu()[:, F:] == 0)
+    assert torch.allclose(P.cpu(), Pref, rtol=1e-5, atol=2e-6)
+    assert torch.allclose(Q.cpu(), Qref, rtol=1e-5, atol=2e-6)
 
     assert L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, _ptr(e), st) == 0
     e_ref = O.sparse_edge(p, H0, src, dst)
     assert rel_err(e.cpu().numpy(), e_ref.numpy()) <= TOL
 
-    # node step on the oracle's own e, so that only this kernel is under test
+    # node step on the oracle's own e and Q, so that only this kernel is under test
     e_in = e_ref.to(cuda_device).contiguous()
-    assert L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(HX), _ptr(e_in), h, _ptr(HX2), _ptr(P), st) == 0
-    H1 = O.sparse_node(p, H0, e_ref, src, dst)
-    got = HX2.cpu()
-    assert torch.allclose(got[:, :h], H1, rtol=1e-5, atol=2e-6)
-    assert torch.equal(got[:, h:h + F], Xh)
+    Q_in = Qref.to(cuda_device).contiguous()
+    assert L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q_in), _ptr(e_in), h,
+                              _ptr(P2), _ptr(Q2), st) == 0
+    H1 = torch.cat([O.sparse_node(p, H0, e_ref, src, dst), Xh], dim=1)
+    P1ref, Q1ref = O.projections(p, H1)
+    assert torch.allclose(P2.cpu(), P1ref, rtol=1e-5, atol=3e-6)
+    assert torch.allclose(Q2.cpu(), Q1ref, rtol=1e-5, atol=3e-6)
+    # Q_out = NULL (last iteration): P' identical, nothing else written
+    P3 = torch.zeros_like(P)
+    assert L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q_in), _ptr(e_in), h,
+                              _ptr(P3), None, st) == 0
+    assert torch.equal(P3, P2)
 
 
 def test_deterministic_and_graph_replay(cuda_device):
