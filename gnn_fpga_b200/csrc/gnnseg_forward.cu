@@ -594,11 +594,18 @@ static inline int check_launch() {
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
+int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
+                      cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
+
 template <int H>
 static int launch_input(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
                         cudaStream_t st) {
     using C = InputCfg<H>;
     if (n_nodes == 0) return GNNSEG_OK;
+    if (H == 32) {
+        const char* impl = getenv("GNNSEG_NODE_IMPL");   // "mma": generic path (for A/B runs)
+        if (!impl || impl[0] != 'm') return launch_input_tc32(blob, X, n_nodes, F, X4, P, Q, st);
+    }
     const int n_tiles = (n_nodes + C::TN - 1) / C::TN;
     int grid = 0;
     const int rc = persistent_grid(input_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);

@@ -59,7 +59,10 @@ struct TcCfg {
     static constexpr int O_BIAS = O_WPL + WP_BYTES;           // b4 [H], bias of the projections [5H]
     static constexpr int STAGE_BYTES = 2 * CAP * 8 + 2 * (TM + 4) * 4;   // [2][CAP] int2 + [2][TM+4] int
     static constexpr int O_STAGE = O_BIAS + 6 * H * 4;        // two staging buffers
-    static constexpr int O_MBAR = O_STAGE + 2 * STAGE_BYTES;  // mbarrier (8 B) + tmem base (4 B)
+    static constexpr int OUT_STRIDE = 36;                     // floats per staged output row (32 + pad)
+    static constexpr int OUT_BYTES = 32 * OUT_STRIDE * 4;     // per epilogue warp: 32 rows x 32 columns
+    static constexpr int O_OUT  = O_STAGE + 2 * STAGE_BYTES;  // [EW] output transposition buffers
+    static constexpr int O_MBAR = O_OUT + EW * OUT_BYTES;     // mbarrier (8 B) + tmem base (4 B)
     static constexpr int SMEM_BYTES = O_MBAR + 16;
     // tensor memory columns (fp32 cells, 128 lanes)
     static constexpr int C_D2  = 0;
@@ -206,6 +209,44 @@ __device__ __forceinline__ void tc_row_sum(const int2* __restrict__ pairs, const
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (ok[u]) fma4(acc, w[u], v[u]);
+    }
+}
+
+// Epilogue of the projection GEMM: D3 (this warp's 32 TMEM lanes = 32 consecutive nodes, NP
+// columns) + bias -> P' and Q' in global memory.  Each thread reads its own row from tensor
+// memory; the 32x32 block is turned through a padded shared buffer so that every store
+// instruction writes four full 128-byte lines (a row of P or Q is contiguous in global memory).
+template <int H>
+__device__ __forceinline__ void tc_store_projections(const uint32_t lane_base, const uint32_t col_d3,
+                                                     const float* __restrict__ sBP, float* __restrict__ sOut,
+                                                     const int node_w0, const int n_nodes, const int lane,
+                                                     float* __restrict__ P_out, float* __restrict__ Q_out,
+                                                     const bool write_q) {
+    constexpr int NP = 5 * H, OS = TcCfg<H>::OUT_STRIDE;
+    const int c_end = write_q ? NP : 2 * H;
+#pragma unroll 1
+    for (int c0 = 0; c0 < c_end; c0 += 32) {
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+            float v[16];
+            tmem_ld16(lane_base + col_d3 + c0 + 16 * hb, v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 b = lds4(sBP + c0 + 16 * hb + 4 * i);
+                st4(sOut + lane * OS + 16 * hb + 4 * i,
+                    make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w));
+            }
+        }
+        __syncwarp();
+        const bool to_p = c0 < 2 * H;
+        float* base = to_p ? P_out + (size_t)node_w0 * 2 * H + c0 : Q_out + (size_t)node_w0 * 3 * H + (c0 - 2 * H);
+        const int ld = to_p ? 2 * H : 3 * H;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
+            if (node_w0 + r < n_nodes) st4(base + (size_t)r * ld + c4, lds4(sOut + r * OS + c4));
+        }
+        __syncwarp();
     }
 }
 
@@ -410,20 +451,8 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
             // ---- epilogue 3: [P'|Q'] = D3 + bias -> global ------------------------------------
-            const int c_end = write_q ? NP : 2 * H;
-#pragma unroll 1
-            for (int c0 = 0; c0 < c_end; c0 += 16) {
-                float v[16];
-                tmem_ld16(lane_base + C::C_D3 + c0, v);
-                if (live) {
-                    float* dst = c0 < 2 * H ? P_out + (size_t)n * 2 * H + c0 : Q_out + (size_t)n * 3 * H + (c0 - 2 * H);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 b = lds4(sBP + c0 + 4 * i);
-                        st4(dst + 4 * i, make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w));
-                    }
-                }
-            }
+            tc_store_projections<H>(lane_base, C::C_D3, sBP, reinterpret_cast<float*>(smem + C::O_OUT + warp * C::OUT_BYTES),
+                                    tile * TM + warp * 32, n_nodes, lane, P_out, Q_out, write_q != 0);
             tc_fence_before();
             tc_bar_sync(BAR_EPI, ET);     // TMEM tiles are rewritten by the next tile
         }
@@ -435,6 +464,147 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// input step on the tensor cores: H0 = tanh(Win.X + bin) per thread (K = F <= 4), [H0|X|0] split
+// into tensor memory, one projection GEMM, same epilogue.  (gnn/model.py:144-146)
+// ------------------------------------------------------------------------------------------
+template <int H>
+struct TcInCfg {
+    using N = TcCfg<H>;
+    static constexpr int NT = 128;                          // 4 warps: thread = node = TMEM lane
+    static constexpr int O_WPH  = 0;
+    static constexpr int O_WPL  = O_WPH + N::WP_BYTES;
+    static constexpr int O_BIAS = O_WPL + N::WP_BYTES;      // Win [4][H], bin [H], bias of the projections [5H]
+    static constexpr int O_OUT  = O_BIAS + (4 * H + H + 5 * H) * 4;
+    static constexpr int O_MBAR = O_OUT + 4 * N::OUT_BYTES;
+    static constexpr int SMEM_BYTES = O_MBAR + 16;
+    static constexpr int C_A3H = 0, C_A3L = N::D4P, C_D3 = 2 * N::D4P, C_END = C_D3 + 5 * H;
+    static constexpr int TMEM_COLS = C_END <= 64 ? 64 : C_END <= 128 ? 128 : C_END <= 256 ? 256 : 512;
+};
+
+template <int H>
+__global__ void __launch_bounds__(TcInCfg<H>::NT)
+input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, const int F, const int n_nodes,
+                const int n_tiles, float* __restrict__ X4, float* __restrict__ P_out, float* __restrict__ Q_out) {
+    using C = TcInCfg<H>;
+    using N = TcCfg<H>;
+    using B = Blob<H>;
+    constexpr int NT = C::NT, D4 = N::D4, NP = N::NP, TM = N::TM;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* sWin = reinterpret_cast<float*>(smem + C::O_BIAS);
+    float* sBin = sWin + 4 * H;
+    float* sBP = sBin + H;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < NP * N::D4P; i += NT) {
+        const int j = i / N::D4P, k = i % N::D4P;
+        float hi, lo;
+        split3(k < D4 ? __ldg(blob + B::WP + k * NP + j) : 0.f, hi, lo);
+        const int off = canon_off(j, k, N::SBO_D4);
+        *reinterpret_cast<float*>(smem + C::O_WPH + off) = hi;
+        *reinterpret_cast<float*>(smem + C::O_WPL + off) = lo;
+    }
+    for (int i = tid; i < 5 * H; i += NT) sWin[i] = __ldg(blob + B::WIN + i);      // Win and bin are contiguous
+    for (int i = tid; i < NP; i += NT) sBP[i] = __ldg(blob + B::BP + i);
+    if (tid == 0) {
+        mbar_init(smem_u32(mbar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t mb = smem_u32(mbar);
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    constexpr uint32_t ID3 = idesc_tf32(TM, NP);
+    const uint32_t sa = smem_u32(smem);
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int n = tile * TM + tid;
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        if (n < n_nodes) {
+            for (int f = 0; f < F; ++f) x[f] = __ldg(X + (size_t)n * F + f);
+            st4(X4 + (size_t)n * 4, make_float4(x[0], x[1], x[2], x[3]));
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < H; c0 += 16) {
+            float hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float v = sBin[c0 + i];
+                v = fmaf(x[0], sWin[0 * H + c0 + i], v);
+                v = fmaf(x[1], sWin[1 * H + c0 + i], v);
+                v = fmaf(x[2], sWin[2 * H + c0 + i], v);
+                v = fmaf(x[3], sWin[3 * H + c0 + i], v);
+                split3(tanhf(v), hi[i], lo[i]);
+            }
+            tmem_st16(lane_base + C::C_A3H + c0, hi);
+            tmem_st16(lane_base + C::C_A3L + c0, lo);
+        }
+        {
+            float xh[8], xl[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split3(x[i], xh[i], xl[i]);
+#pragma unroll
+            for (int i = 4; i < 8; ++i) xh[i] = xl[i] = 0.f;
+            tmem_st8(lane_base + C::C_A3H + H, xh);
+            tmem_st8(lane_base + C::C_A3L + H, xl);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int kq = 0; kq < N::D4P / 8; ++kq) {
+                const uint32_t ko = kq * 2 * N::LBO;
+                const uint64_t bh = smem_desc(sa + C::O_WPH + ko, N::LBO, N::SBO_D4);
+                const uint64_t bl = smem_desc(sa + C::O_WPL + ko, N::LBO, N::SBO_D4);
+                umma_ts(tmem + C::C_D3, tmem + C::C_A3L + 8 * kq, bh, ID3, kq > 0);
+                umma_ts(tmem + C::C_D3, tmem + C::C_A3H + 8 * kq, bl, ID3, 1);
+                umma_ts(tmem + C::C_D3, tmem + C::C_A3H + 8 * kq, bh, ID3, 1);
+            }
+            umma_commit(mb);
+        }
+        mbar_wait(mb, phase); phase ^= 1;
+        tc_fence_after();
+        tc_store_projections<H>(lane_base, C::C_D3, sBP, reinterpret_cast<float*>(smem + C::O_OUT + warp * N::OUT_BYTES),
+                                tile * TM + warp * 32, n_nodes, lane, P_out, Q_out, true);
+        tc_fence_before();
+        __syncthreads();       // A3 / D3 are rewritten by the next tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
+                      cudaStream_t st) {
+    using C = TcInCfg<32>;
+    if (n_nodes == 0) return GNNSEG_OK;
+    const int n_tiles = (n_nodes + TcCfg<32>::TM - 1) / TcCfg<32>::TM;
+    if (cudaFuncSetAttribute(input_kernel_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+        return GNNSEG_ECUDA;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+        return GNNSEG_ENODEVICE;
+    const int cap = 2 * sms;     // 256 TMEM columns and ~75 KB of shared memory per CTA: two CTAs per SM
+    const int grid = n_tiles < cap ? n_tiles : cap;
+    input_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, P, Q);
+    return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
 int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e,
