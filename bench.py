@@ -289,6 +289,8 @@ def main():
     Q = [torch.empty(batch.n_nodes, 3 * h, device=dev) for _ in range(2)]
     P = torch.empty(batch.n_nodes, 2 * h, device=dev)
     e = torch.empty(batch.n_slots, device=dev)
+    e_in = torch.empty(batch.n_slots, device=dev)
+    e_out = torch.empty(batch.n_slots, device=dev)
     kt = {"input": [], "edge": [], "node": []}
 
     def timed(name, fn):
@@ -307,10 +309,10 @@ def main():
         cur = 0
         for i in range(it):
             qo = _ptr(Q[cur ^ 1]) if i + 1 < it else None
-            timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, _ptr(e), st))
-            timed("node", lambda: L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q[cur]), _ptr(e), h, _ptr(P), qo, st))
+            timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, None, _ptr(e_in), _ptr(e_out), st))
+            timed("node", lambda: L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q[cur]), _ptr(e_in), _ptr(e_out), h, _ptr(P), qo, st))
             cur ^= 1
-        timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, _ptr(e), st))
+        timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, _ptr(e), None, None, st))
     torch.cuda.synchronize(dev)
     kernel_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in kt.items() if v}
     kernel_share = {k: kernel_ms[k] * {"input": 1, "edge": it + 1, "node": it}[k] for k in kernel_ms}

@@ -26,7 +26,7 @@ class GnnsegParams(C.Structure):
 
 class GnnsegGraph(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_slots", C.c_int32)] + [(n, C.c_void_p) for n in (
-        "src", "dst", "in_ptr", "in_eid", "in_nbr", "out_ptr", "out_eid", "out_nbr")]
+        "src", "dst", "in_ptr", "in_eid", "in_nbr", "out_ptr", "out_eid", "out_nbr", "in_pos", "out_pos")]
 
 
 # name -> (restype, argtypes); must list every symbol include/gnnseg.h declares
@@ -39,12 +39,12 @@ SIGNATURES = {
     "gnnseg_pack_weights": (C.c_int, [C.POINTER(GnnsegParams), C.c_int, C.c_int, _f32p, C.c_void_p]),
     "gnnseg_dense_to_edges": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, C.c_void_p]),
     "gnnseg_csr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
-    "gnnseg_build_csr": (C.c_int, [_i32p, _i32p, C.c_int, C.c_int, _i32p, _i32p, _i32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnnseg_build_csr": (C.c_int, [_i32p, _i32p, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnnseg_forward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gnnseg_forward": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnnseg_input_step": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_void_p]),
-    "gnnseg_edge_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, _f32p, C.c_void_p]),
-    "gnnseg_node_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_void_p]),
+    "gnnseg_edge_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, _f32p, _f32p, _f32p, C.c_void_p]),
+    "gnnseg_node_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, _f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_void_p]),
     "gnnseg_pack_sparse_batch_host": (C.c_int, [
         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

@@ -4,12 +4,12 @@
 
 namespace gnnseg {
 int input_step(const float*, const float*, int, int, int, float*, float*, float*, cudaStream_t);
-int edge_step(const float*, const GnnsegGraph*, const float*, int, float*, cudaStream_t);
-int node_step(const float*, const GnnsegGraph*, const float*, const float*, const float*, int, float*, float*, int, cudaStream_t);
+int edge_step(const float*, const GnnsegGraph*, const float*, int, float*, float*, float*, cudaStream_t);
+int node_step(const float*, const GnnsegGraph*, const float*, const float*, const float*, const float*, int, float*, float*, int, cudaStream_t);
 int pack_weights(const GnnsegParams*, int, int, float*, cudaStream_t);
 int dense_to_edges(const float*, const float*, int, int, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
 size_t csr_workspace_bytes(int, int);
-int build_csr(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+int build_csr(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
 }  // namespace gnnseg
 
 namespace {
@@ -20,11 +20,12 @@ struct FwdWorkspace {
     float* x4;
     float* p;
     float* q[2];
-    float* e;
+    float* e_in;
+    float* e_out;
     size_t bytes;
 };
 
-// X4 | P | Q0 | Q1 | e, each 256-byte aligned.
+// X4 | P | Q0 | Q1 | e_in | e_out, each 256-byte aligned.
 FwdWorkspace carve(void* ws, int n_nodes, int n_slots, int h) {
     FwdWorkspace w;
     const size_t x_b = align_up((size_t)n_nodes * 4 * 4, 256);
@@ -36,8 +37,9 @@ FwdWorkspace carve(void* ws, int n_nodes, int n_slots, int h) {
     w.p = reinterpret_cast<float*>(base + x_b);
     w.q[0] = reinterpret_cast<float*>(base + x_b + p_b);
     w.q[1] = reinterpret_cast<float*>(base + x_b + p_b + q_b);
-    w.e = reinterpret_cast<float*>(base + x_b + p_b + 2 * q_b);
-    w.bytes = x_b + p_b + 2 * q_b + e_b;
+    w.e_in = reinterpret_cast<float*>(base + x_b + p_b + 2 * q_b);
+    w.e_out = reinterpret_cast<float*>(base + x_b + p_b + 2 * q_b + e_b);
+    w.bytes = x_b + p_b + 2 * q_b + 2 * e_b;
     return w;
 }
 
@@ -49,7 +51,7 @@ inline bool graph_ok(const GnnsegGraph* g) {
 inline bool csr_ok(const GnnsegGraph* g) {
     if (!graph_ok(g)) return false;
     if (!g->in_ptr || !g->out_ptr) return false;
-    if (g->n_slots > 0 && (!g->in_eid || !g->in_nbr || !g->out_eid || !g->out_nbr)) return false;
+    if (g->n_slots > 0 && (!g->in_eid || !g->in_nbr || !g->out_eid || !g->out_nbr || !g->in_pos || !g->out_pos)) return false;
     return true;
 }
 
@@ -109,11 +111,11 @@ size_t gnnseg_csr_workspace_bytes(int n_nodes, int n_slots) {
 }
 
 int gnnseg_build_csr(const int32_t* key, const int32_t* other, int n_slots, int n_nodes,
-                     int32_t* ptr, int32_t* eid, int32_t* nbr, void* ws, size_t ws_bytes,
-                     void* stream) {
+                     int32_t* ptr, int32_t* eid, int32_t* nbr, int32_t* pos, void* ws,
+                     size_t ws_bytes, void* stream) {
     if (n_slots < 0 || n_nodes < 0 || !ptr || !ws) return GNNSEG_EINVAL;
     if (n_slots > 0 && (!key || !other || !eid || !nbr)) return GNNSEG_EINVAL;
-    return gnnseg::build_csr(key, other, n_slots, n_nodes, ptr, eid, nbr, ws, ws_bytes,
+    return gnnseg::build_csr(key, other, n_slots, n_nodes, ptr, eid, nbr, pos, ws, ws_bytes,
                              static_cast<cudaStream_t>(stream));
 }
 
@@ -130,19 +132,21 @@ int gnnseg_input_step(const float* blob, const float* X, int n_nodes, int F, int
 }
 
 int gnnseg_edge_step(const float* blob, const GnnsegGraph* g, const float* P, int h, float* e,
-                     void* stream) {
+                     float* e_in, float* e_out, void* stream) {
     if (!gnnseg_supported(1, h)) return GNNSEG_EUNSUPPORTED;
-    if (!blob || !graph_ok(g) || (g->n_slots > 0 && !e) || (g->n_nodes > 0 && !P)) return GNNSEG_EINVAL;
-    return gnnseg::edge_step(blob, g, P, h, e, static_cast<cudaStream_t>(stream));
+    if (!blob || !graph_ok(g) || (g->n_nodes > 0 && !P)) return GNNSEG_EINVAL;
+    if (g->n_slots > 0 && ((e_in && !g->in_pos) || (e_out && !g->out_pos))) return GNNSEG_EINVAL;
+    return gnnseg::edge_step(blob, g, P, h, e, e_in, e_out, static_cast<cudaStream_t>(stream));
 }
 
 int gnnseg_node_step(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in,
-                     const float* e, int h, float* P_out, float* Q_out, void* stream) {
+                     const float* e_in, const float* e_out, int h, float* P_out, float* Q_out,
+                     void* stream) {
     if (!gnnseg_supported(1, h)) return GNNSEG_EUNSUPPORTED;
     if (!blob || !csr_ok(g)) return GNNSEG_EINVAL;
     if (g->n_nodes > 0 && (!X4 || !Q_in || !P_out)) return GNNSEG_EINVAL;
-    if (g->n_slots > 0 && !e) return GNNSEG_EINVAL;
-    return gnnseg::node_step(blob, g, X4, Q_in, e, h, P_out, Q_out, Q_out != nullptr,
+    if (g->n_slots > 0 && (!e_in || !e_out)) return GNNSEG_EINVAL;
+    return gnnseg::node_step(blob, g, X4, Q_in, e_in, e_out, h, P_out, Q_out, Q_out != nullptr,
                              static_cast<cudaStream_t>(stream));
 }
 
@@ -162,13 +166,14 @@ int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int 
     int rc = gnnseg::input_step(blob, X, g->n_nodes, F, h, w.x4, w.p, w.q[0], st);
     int cur = 0;
     for (int it = 0; it < n_iters && rc == GNNSEG_OK; ++it) {
-        rc = gnnseg::edge_step(blob, g, w.p, h, w.e, st);
+        // intermediate scores are only consumed by the node step: CSR order only
+        rc = gnnseg::edge_step(blob, g, w.p, h, nullptr, w.e_in, w.e_out, st);
         // the last node step feeds only the final edge step: its Q' is never read
         if (rc == GNNSEG_OK)
-            rc = gnnseg::node_step(blob, g, w.x4, w.q[cur], w.e, h, w.p, w.q[cur ^ 1], it + 1 < n_iters, st);
+            rc = gnnseg::node_step(blob, g, w.x4, w.q[cur], w.e_in, w.e_out, h, w.p, w.q[cur ^ 1], it + 1 < n_iters, st);
         cur ^= 1;
     }
-    if (rc == GNNSEG_OK) rc = gnnseg::edge_step(blob, g, w.p, h, scores, st);
+    if (rc == GNNSEG_OK) rc = gnnseg::edge_step(blob, g, w.p, h, scores, nullptr, nullptr, st);
     return rc;
 }
 

@@ -49,6 +49,29 @@ __device__ __forceinline__ float4 lds4(const float* p) {
 __device__ __forceinline__ void st4(float* p, float4 v) {
     *reinterpret_cast<float4*>(p) = v;
 }
+// L2 eviction policies: rows that are gathered several times per step (P, Q) are loaded
+// evict_last; arrays that are written once and read by the NEXT kernel are stored evict_first
+// so that they do not push the gathered rows out of the L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg4_hint(const float* p, const uint64_t policy) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void st4_hint(float* p, const float4 v, const uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
     acc.x = fmaf(w, v.x, acc.x);
     acc.y = fmaf(w, v.y, acc.y);

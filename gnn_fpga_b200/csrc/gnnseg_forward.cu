@@ -331,7 +331,9 @@ template <int H>
 __global__ void __launch_bounds__(256)
 edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
             const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
-            const int n_slots, float* __restrict__ e_out) {
+            const int32_t* __restrict__ in_pos, const int32_t* __restrict__ out_pos,
+            const int n_slots, float* __restrict__ e_slot, float* __restrict__ e_in,
+            float* __restrict__ e_out) {
     using B = Blob<H>;
     constexpr int G = H / 4;        // lanes that share one edge (one float4 of P each)
     constexpr int EPP = 32 / G;     // edges a warp handles per pass
@@ -340,6 +342,7 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
     const float4 w2 = ldg4(blob + B::W2 + 4 * c);
     const float4 b1 = ldg4(blob + B::BP + 4 * c);
     const float b2 = __ldg(blob + B::B2);
+    const uint64_t keep = l2_policy_evict_last();   // every P row is gathered ~deg times
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
 
@@ -355,8 +358,8 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
             const int dd = __shfl_sync(0xffffffffu, d, k);
             float4 a = b1;                                   // absent start: W1a.0 + b1
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);      // absent end:   W1b.0
-            if (ss >= 0) a = ldg4(P + (size_t)ss * (2 * H) + 4 * c);
-            if (dd >= 0) b = ldg4(P + (size_t)dd * (2 * H) + H + 4 * c);
+            if (ss >= 0) a = ldg4_hint(P + (size_t)ss * (2 * H) + 4 * c, keep);
+            if (dd >= 0) b = ldg4_hint(P + (size_t)dd * (2 * H) + H + 4 * c, keep);
             float z = w2.x * tanhf(a.x + b.x);
             z = fmaf(w2.y, tanhf(a.y + b.y), z);
             z = fmaf(w2.z, tanhf(a.z + b.z), z);
@@ -366,7 +369,18 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
             const float v = __shfl_sync(0xffffffffu, z, (lane % EPP) * G);
             if (lane / EPP == p) mine = v;
         }
-        if (j < n_slots) e_out[j] = 1.f / (1.f + expf(-(mine + b2)));
+        if (j < n_slots) {
+            const float score = 1.f / (1.f + expf(-(mine + b2)));
+            if (e_slot) e_slot[j] = score;
+            if (e_in) {                       // the node step reads the scores in CSR order
+                const int pi = __ldg(in_pos + j);
+                if (pi >= 0) e_in[pi] = score;
+            }
+            if (e_out) {
+                const int po = __ldg(out_pos + j);
+                if (po >= 0) e_out[po] = score;
+            }
+        }
     }
 }
 
@@ -392,11 +406,11 @@ __device__ __forceinline__ void bar_arrive(const int id, const int n) {
 // STAGED: the (neighbour, weight) pairs of the whole tile were fetched into shared memory
 // beforehand by coalesced loads.
 template <bool STAGED>
-__device__ __forceinline__ void csr_row_sum(const int2* __restrict__ pairs, const int32_t* __restrict__ eid,
-                                            const int32_t* __restrict__ nbr, const float* __restrict__ e,
-                                            const float* __restrict__ Qcol, const int row_floats,
-                                            const int beg, const int end, float4& acc) {
+__device__ __forceinline__ void csr_row_sum(const int2* __restrict__ pairs, const int32_t* __restrict__ nbr,
+                                            const float* __restrict__ ew, const float* __restrict__ Qcol,
+                                            const int row_floats, const int beg, const int end, float4& acc) {
     constexpr int U = 4;
+    const uint64_t keep = l2_policy_evict_last();
     for (int s0 = beg; s0 < end; s0 += U) {
         float w[U];
         bool ok[U];
@@ -411,10 +425,10 @@ __device__ __forceinline__ void csr_row_sum(const int2* __restrict__ pairs, cons
                 w[u] = __int_as_float(pr.y);
             } else {
                 nb = __ldg(nbr + s);
-                w[u] = __ldg(e + __ldg(eid + s));
+                w[u] = __ldg(ew + s);
             }
             ok[u] = (s0 + u < end) && nb >= 0;   // nb < 0: half edge, gathers the zero row
-            v[u] = ldg4(Qcol + (size_t)max(nb, 0) * row_floats);
+            v[u] = ldg4_hint(Qcol + (size_t)max(nb, 0) * row_floats, keep);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -425,7 +439,7 @@ __device__ __forceinline__ void csr_row_sum(const int2* __restrict__ pairs, cons
 template <int H>
 __global__ void __launch_bounds__(NodeCfg<H>::NT, NodeCfg<H>::MINB)
 node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __restrict__ X4,
-            const float* __restrict__ Q_in, const float* __restrict__ e, const int n_tiles,
+            const float* __restrict__ Q_in, const float* __restrict__ e_in, const float* __restrict__ e_out, const int n_tiles,
             float* __restrict__ P_out, float* __restrict__ Q_out, const int write_q) {
     using C = NodeCfg<H>;
     using B = Blob<H>;
@@ -488,9 +502,9 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __
             const bool staged = ic <= CAP && oc <= CAP;       // CTA-uniform
             if (staged) {
                 for (int s = pt; s < ic; s += PT)
-                    sPair[s] = make_int2(__ldg(g.in_nbr + ib + s), __float_as_int(__ldg(e + __ldg(g.in_eid + ib + s))));
+                    sPair[s] = make_int2(__ldg(g.in_nbr + ib + s), __float_as_int(__ldg(e_in + ib + s)));
                 for (int s = pt; s < oc; s += PT)
-                    sPair[CAP + s] = make_int2(__ldg(g.out_nbr + ob + s), __float_as_int(__ldg(e + __ldg(g.out_eid + ob + s))));
+                    sPair[CAP + s] = make_int2(__ldg(g.out_nbr + ob + s), __float_as_int(__ldg(e_out + ob + s)));
             }
             bar_sync(BAR_PROD, PT);
             if (it >= NBUF) bar_sync(BAR_EMPTY + buf, NT);     // consumers are done with this buffer
@@ -502,11 +516,11 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __
                     acc = ldg4(Q_in + (size_t)n * 3 * H + 2 * H + 4 * c);             // Qs[n] (holds b3)
                     const int i0 = sPtr[ln], i1 = sPtr[ln + 1], o0 = sPtr[TN + 4 + ln], o1 = sPtr[TN + 4 + ln + 1];
                     if (staged) {
-                        csr_row_sum<true>(sPair, nullptr, nullptr, nullptr, Q_in + 4 * c, 3 * H, i0 - ib, i1 - ib, acc);
-                        csr_row_sum<true>(sPair + CAP, nullptr, nullptr, nullptr, Q_in + H + 4 * c, 3 * H, o0 - ob, o1 - ob, acc);
+                        csr_row_sum<true>(sPair, nullptr, nullptr, Q_in + 4 * c, 3 * H, i0 - ib, i1 - ib, acc);
+                        csr_row_sum<true>(sPair + CAP, nullptr, nullptr, Q_in + H + 4 * c, 3 * H, o0 - ob, o1 - ob, acc);
                     } else {
-                        csr_row_sum<false>(nullptr, g.in_eid, g.in_nbr, e, Q_in + 4 * c, 3 * H, i0, i1, acc);
-                        csr_row_sum<false>(nullptr, g.out_eid, g.out_nbr, e, Q_in + H + 4 * c, 3 * H, o0, o1, acc);
+                        csr_row_sum<false>(nullptr, g.in_nbr, e_in, Q_in + 4 * c, 3 * H, i0, i1, acc);
+                        csr_row_sum<false>(nullptr, g.out_nbr, e_out, Q_in + H + 4 * c, 3 * H, o0, o1, acc);
                     }
                     acc.x = tanhf(acc.x); acc.y = tanhf(acc.y); acc.z = tanhf(acc.z); acc.w = tanhf(acc.w);
                 }
@@ -615,7 +629,8 @@ static int launch_input(const float* blob, const float* X, int n_nodes, int F, f
 }
 
 template <int H>
-static int launch_edge(const float* blob, const GnnsegGraph* g, const float* P, float* e, cudaStream_t st) {
+static int launch_edge(const float* blob, const GnnsegGraph* g, const float* P, float* e, float* e_in,
+                       float* e_out, cudaStream_t st) {
     if (g->n_slots == 0) return GNNSEG_OK;
     const int sms = sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
@@ -623,27 +638,27 @@ static int launch_edge(const float* blob, const GnnsegGraph* g, const float* P, 
     int grid = (warps_needed + 7) / 8;
     const int cap = sms * 8;   // 8 CTAs of 256 threads per SM
     if (grid > cap) grid = cap;
-    edge_kernel<H><<<grid, 256, 0, st>>>(blob, P, g->src, g->dst, g->n_slots, e);
+    edge_kernel<H><<<grid, 256, 0, st>>>(blob, P, g->src, g->dst, g->in_pos, g->out_pos, g->n_slots, e, e_in, e_out);
     return check_launch();
 }
 
-int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e,
-                     float* P_out, float* Q_out, int write_q, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
+int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e_in,
+                     const float* e_out, float* P_out, float* Q_out, int write_q, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
 
 template <int H>
-static int launch_node(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e,
-                       float* P_out, float* Q_out, int write_q, cudaStream_t st) {
+static int launch_node(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e_in,
+                       const float* e_out, float* P_out, float* Q_out, int write_q, cudaStream_t st) {
     using C = NodeCfg<H>;
     if (g->n_nodes == 0) return GNNSEG_OK;
     if (H == 32) {
         const char* impl = getenv("GNNSEG_NODE_IMPL");   // "mma": generic mma.sync path (for A/B runs)
-        if (!impl || impl[0] != 'm') return launch_node_tc32(blob, g, X4, Q_in, e, P_out, Q_out, write_q, st);
+        if (!impl || impl[0] != 'm') return launch_node_tc32(blob, g, X4, Q_in, e_in, e_out, P_out, Q_out, write_q, st);
     }
     const int n_tiles = (g->n_nodes + C::TN - 1) / C::TN;
     int grid = 0;
     const int rc = persistent_grid(node_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);
     if (rc) return rc;
-    node_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e, n_tiles, P_out, Q_out, write_q);
+    node_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out, Q_out, write_q);
     return check_launch();
 }
 
@@ -661,12 +676,13 @@ int input_step(const float* blob, const float* X, int n_nodes, int F, int h, flo
                cudaStream_t st) {
     GNNSEG_DISPATCH_H(h, launch_input<HH>(blob, X, n_nodes, F, X4, P, Q, st));
 }
-int edge_step(const float* blob, const GnnsegGraph* g, const float* P, int h, float* e, cudaStream_t st) {
-    GNNSEG_DISPATCH_H(h, launch_edge<HH>(blob, g, P, e, st));
+int edge_step(const float* blob, const GnnsegGraph* g, const float* P, int h, float* e, float* e_in, float* e_out,
+              cudaStream_t st) {
+    GNNSEG_DISPATCH_H(h, launch_edge<HH>(blob, g, P, e, e_in, e_out, st));
 }
-int node_step(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e, int h,
-              float* P_out, float* Q_out, int write_q, cudaStream_t st) {
-    GNNSEG_DISPATCH_H(h, launch_node<HH>(blob, g, X4, Q_in, e, P_out, Q_out, write_q, st));
+int node_step(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e_in,
+              const float* e_out, int h, float* P_out, float* Q_out, int write_q, cudaStream_t st) {
+    GNNSEG_DISPATCH_H(h, launch_node<HH>(blob, g, X4, Q_in, e_in, e_out, P_out, Q_out, write_q, st));
 }
 int pack_weights(const GnnsegParams* p, int F, int h, float* blob, cudaStream_t st) {
     const int total = blob_total(h);

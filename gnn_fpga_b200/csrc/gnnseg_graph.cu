@@ -176,10 +176,13 @@ __global__ void csr_sort_rows_kernel(const int32_t* __restrict__ ptr, const int 
 
 __global__ void csr_nbr_kernel(const int32_t* __restrict__ eid, const int32_t* __restrict__ ptr,
                                const int n_nodes, const int32_t* __restrict__ other,
-                               int32_t* __restrict__ nbr) {
+                               int32_t* __restrict__ nbr, int32_t* __restrict__ pos) {
     const int n_used = ptr[n_nodes];
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_used; s += gridDim.x * blockDim.x)
-        nbr[s] = __ldg(other + eid[s]);
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_used; s += gridDim.x * blockDim.x) {
+        const int j = eid[s];
+        nbr[s] = __ldg(other + j);
+        if (pos) pos[j] = s;       // inverse map (pos was filled with -1)
+    }
 }
 
 // ---- launchers -----------------------------------------------------------------------
@@ -210,7 +213,7 @@ size_t csr_workspace_bytes(int n_nodes, int n_slots) {
 }
 
 int build_csr(const int32_t* key, const int32_t* other, int n_slots, int n_nodes, int32_t* ptr,
-              int32_t* eid, int32_t* nbr, void* ws, size_t ws_bytes, cudaStream_t st) {
+              int32_t* eid, int32_t* nbr, int32_t* pos, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (ws_bytes < csr_workspace_bytes(n_nodes, n_slots)) return GNNSEG_EWORKSPACE;
     int32_t* count = static_cast<int32_t*>(ws);
     int32_t* cursor = count + (n_nodes + 1);
@@ -219,6 +222,7 @@ int build_csr(const int32_t* key, const int32_t* other, int n_slots, int n_nodes
     int32_t* grand_total = block_sums + n_blocks + 1;
 
     fill_i32_kernel<<<grid_for(n_nodes + 1, 256, 4096), 256, 0, st>>>(count, 0, (size_t)n_nodes + 1);
+    if (pos && n_slots > 0) fill_i32_kernel<<<grid_for(n_slots, 256, 4096), 256, 0, st>>>(pos, -1, (size_t)n_slots);
     if (n_slots > 0) histogram_kernel<<<grid_for(n_slots, 256, 4096), 256, 0, st>>>(key, n_slots, n_nodes, count);
     if (n_blocks > 0) {
         scan_local_kernel<<<n_blocks, SCAN_THREADS, 0, st>>>(count, n_nodes, ptr, block_sums);
@@ -230,7 +234,7 @@ int build_csr(const int32_t* key, const int32_t* other, int n_slots, int n_nodes
     if (n_slots > 0 && n_nodes > 0) {
         csr_fill_kernel<<<grid_for(n_slots, 256, 4096), 256, 0, st>>>(key, n_slots, n_nodes, cursor, eid);
         csr_sort_rows_kernel<<<grid_for(n_nodes, 128, 8192), 128, 0, st>>>(ptr, n_nodes, eid);
-        csr_nbr_kernel<<<grid_for(n_slots, 256, 4096), 256, 0, st>>>(eid, ptr, n_nodes, other, nbr);
+        csr_nbr_kernel<<<grid_for(n_slots, 256, 4096), 256, 0, st>>>(eid, ptr, n_nodes, other, nbr, pos);
     }
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }

@@ -37,6 +37,7 @@ struct TcCfg {
     static constexpr int G    = H / 4;               // lanes per node in the gather: one float4 each
     static constexpr int NGRP = GT / G;              // nodes gathered concurrently
     static_assert(TM % NGRP == 0, "whole passes");
+    static_assert(ST == TM, "one stager thread per row pointer");
     static constexpr int D4   = H + 4;
     static constexpr int D4P  = (D4 + 7) / 8 * 8;    // K of GEMM3, padded to the tf32 k-step
     static constexpr int NP   = 5 * H;               // projection width
@@ -181,10 +182,10 @@ __device__ __forceinline__ int canon_off(const int row, const int k, const int s
 // row loads of the batch are issued before the first FMA (no branch in between: an absent slot or
 // neighbour is predicated off).  STAGED: pairs come from shared memory.
 template <bool STAGED>
-__device__ __forceinline__ void tc_row_sum(const int2* __restrict__ pairs, const int32_t* __restrict__ eid,
-                                           const int32_t* __restrict__ nbr, const float* __restrict__ e,
-                                           const float* __restrict__ Qcol, const int row_floats,
-                                           const int beg, const int end, float4& acc) {
+__device__ __forceinline__ void tc_row_sum(const int2* __restrict__ pairs, const int32_t* __restrict__ nbr,
+                                           const float* __restrict__ ew, const float* __restrict__ Qcol,
+                                           const int row_floats, const int beg, const int end,
+                                           const uint64_t keep, float4& acc) {
     constexpr int U = 8;
     for (int s0 = beg; s0 < end; s0 += U) {
         float w[U];
@@ -200,11 +201,11 @@ __device__ __forceinline__ void tc_row_sum(const int2* __restrict__ pairs, const
                 w[u] = __int_as_float(pr.y);
             } else {
                 nb = __ldg(nbr + s);
-                w[u] = __ldg(e + __ldg(eid + s));
+                w[u] = __ldg(ew + s);
             }
             ok[u] = (s0 + u < end) && nb >= 0;       // nb < 0: half edge, gathers the zero row
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok[u]) v[u] = ldg4(Qcol + (size_t)nb * row_floats);
+            if (ok[u]) v[u] = ldg4_hint(Qcol + (size_t)nb * row_floats, keep);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -223,6 +224,7 @@ __device__ __forceinline__ void tc_store_projections(const uint32_t lane_base, c
                                                      float* __restrict__ P_out, float* __restrict__ Q_out,
                                                      const bool write_q) {
     constexpr int NP = 5 * H, OS = TcCfg<H>::OUT_STRIDE;
+    const uint64_t stream = l2_policy_evict_first();           // read next by another kernel, not by this one
     const int c_end = write_q ? NP : 2 * H;
 #pragma unroll 1
     for (int c0 = 0; c0 < c_end; c0 += 32) {
@@ -244,7 +246,7 @@ __device__ __forceinline__ void tc_store_projections(const uint32_t lane_base, c
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
-            if (node_w0 + r < n_nodes) st4(base + (size_t)r * ld + c4, lds4(sOut + r * OS + c4));
+            if (node_w0 + r < n_nodes) st4_hint(base + (size_t)r * ld + c4, lds4(sOut + r * OS + c4), stream);
         }
         __syncwarp();
     }
@@ -253,8 +255,9 @@ __device__ __forceinline__ void tc_store_projections(const uint32_t lane_base, c
 template <int H>
 __global__ void __launch_bounds__(TcCfg<H>::NT, 1)
 node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float* __restrict__ X4,
-               const float* __restrict__ Q_in, const float* __restrict__ e, const int n_tiles,
-               float* __restrict__ P_out, float* __restrict__ Q_out, const int write_q) {
+               const float* __restrict__ Q_in, const float* __restrict__ e_in, const float* __restrict__ e_out,
+               const int n_tiles, float* __restrict__ P_out, float* __restrict__ Q_out, const int write_q,
+               const int dbg) {
     using C = TcCfg<H>;
     using B = Blob<H>;
     constexpr int TM = C::TM, NT = C::NT, ET = C::ET, ST = C::ST, GT = C::GT, D4 = C::D4, NP = C::NP;
@@ -308,6 +311,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
         constexpr int CAP = C::CAP, G = C::G, NGRP = C::NGRP;
         const int gt = tid - ET - ST;
         const int grp = gt / G, c = gt % G;                   // node slot of the pass, float4 chunk
+        const uint64_t keep = l2_policy_evict_last();          // gathered rows are re-read ~deg times
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int sb = it & 1;
@@ -325,15 +329,15 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             for (int ln = grp; ln < TM; ln += NGRP) {
                 const int n = node0 + ln;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n < n_nodes) {
+                if (n < n_nodes && !(dbg & 1)) {
                     acc = ldg4(Q_in + (size_t)n * 3 * H + 2 * H + 4 * c);            // Qs[n] (holds b3)
                     const int i0 = sPtr[ln], i1 = sPtr[ln + 1], o0 = sPtr[TM + 4 + ln], o1 = sPtr[TM + 4 + ln + 1];
                     if (staged) {
-                        tc_row_sum<true>(sPair, nullptr, nullptr, nullptr, Q_in + 4 * c, 3 * H, i0 - ib, i1 - ib, acc);
-                        tc_row_sum<true>(sPair + CAP, nullptr, nullptr, nullptr, Q_in + H + 4 * c, 3 * H, o0 - ob, o1 - ob, acc);
+                        tc_row_sum<true>(sPair, nullptr, nullptr, Q_in + 4 * c, 3 * H, i0 - ib, i1 - ib, keep, acc);
+                        tc_row_sum<true>(sPair + CAP, nullptr, nullptr, Q_in + H + 4 * c, 3 * H, o0 - ob, o1 - ob, keep, acc);
                     } else {
-                        tc_row_sum<false>(nullptr, g.in_eid, g.in_nbr, e, Q_in + 4 * c, 3 * H, i0, i1, acc);
-                        tc_row_sum<false>(nullptr, g.out_eid, g.out_nbr, e, Q_in + H + 4 * c, 3 * H, o0, o1, acc);
+                        tc_row_sum<false>(nullptr, g.in_nbr, e_in, Q_in + 4 * c, 3 * H, i0, i1, keep, acc);
+                        tc_row_sum<false>(nullptr, g.out_nbr, e_out, Q_in + H + 4 * c, 3 * H, o0, o1, keep, acc);
                     }
                     acc.x = tanhf(acc.x); acc.y = tanhf(acc.y); acc.z = tanhf(acc.z); acc.w = tanhf(acc.w);
                 }
@@ -350,29 +354,57 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
     } else if (tid >= ET) {
         // ================================ stager warps ==================================
         // Run ahead of the gather: row pointers, then (neighbour, edge weight) pairs of the tile's
-        // two CSR slices, fetched with coalesced loads into one of two staging buffers.
-        constexpr int CAP = C::CAP;
+        // two CSR slices, fetched with coalesced loads into one of two staging buffers.  The row
+        // pointers of the NEXT tile are prefetched into registers while this tile's pairs are in
+        // flight, and the pair loads are issued in batches of UNR per thread before any of them
+        // is stored, so a tile costs about two memory latencies instead of one per slot.
+        constexpr int CAP = C::CAP, UNR = 6;
         const int stid = tid - ET;
         int it = 0;
+        // pointer prefetch registers: entry stid, and entry TM for thread 0
+        int p_in = 0, p_out = 0, p_in_last = 0, p_out_last = 0;
+        auto load_ptrs = [&](const int tile) {
+            const int node0 = tile * TM;
+            const int n = min(node0 + stid, n_nodes);
+            p_in = __ldg(g.in_ptr + n);
+            p_out = __ldg(g.out_ptr + n);
+            if (stid == 0) {
+                const int nl = min(node0 + TM, n_nodes);
+                p_in_last = __ldg(g.in_ptr + nl);
+                p_out_last = __ldg(g.out_ptr + nl);
+            }
+        };
+        if ((int)blockIdx.x < n_tiles) load_ptrs(blockIdx.x);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int sb = it & 1;
             int2* sPair = reinterpret_cast<int2*>(smem + C::O_STAGE + sb * C::STAGE_BYTES);
             int* sPtr = reinterpret_cast<int*>(smem + C::O_STAGE + sb * C::STAGE_BYTES + 2 * CAP * 8);
-            const int node0 = tile * TM;
             if (it >= 2) tc_bar_sync(BAR_SEMPTY + sb, ST + GT);   // the gather is done with this buffer
-            for (int i = stid; i <= TM; i += ST) {
-                const int n = min(node0 + i, n_nodes);
-                sPtr[i] = __ldg(g.in_ptr + n);
-                sPtr[TM + 4 + i] = __ldg(g.out_ptr + n);
-            }
+            sPtr[stid] = p_in;
+            sPtr[TM + 4 + stid] = p_out;
+            if (stid == 0) { sPtr[TM] = p_in_last; sPtr[TM + 4 + TM] = p_out_last; }
             tc_bar_sync(BAR_STG, ST);
             const int ib = sPtr[0], ic = sPtr[TM] - ib;
             const int ob = sPtr[TM + 4], oc = sPtr[TM + 4 + TM] - ob;
+            if (tile + (int)gridDim.x < n_tiles) load_ptrs(tile + gridDim.x);   // in flight during the pair loads
             if (ic <= CAP && oc <= CAP) {
-                for (int s = stid; s < ic; s += ST)
-                    sPair[s] = make_int2(__ldg(g.in_nbr + ib + s), __float_as_int(__ldg(e + __ldg(g.in_eid + ib + s))));
-                for (int s = stid; s < oc; s += ST)
-                    sPair[CAP + s] = make_int2(__ldg(g.out_nbr + ob + s), __float_as_int(__ldg(e + __ldg(g.out_eid + ob + s))));
+#pragma unroll 1
+                for (int base = 0; base < max(ic, oc); base += ST * UNR) {
+                    int nb_i[UNR], nb_o[UNR];
+                    float w_i[UNR], w_o[UNR];
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const int s = base + u * ST + stid;
+                        if (s < ic) { nb_i[u] = __ldg(g.in_nbr + ib + s); w_i[u] = __ldg(e_in + ib + s); }
+                        if (s < oc) { nb_o[u] = __ldg(g.out_nbr + ob + s); w_o[u] = __ldg(e_out + ob + s); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const int s = base + u * ST + stid;
+                        if (s < ic) sPair[s] = make_int2(nb_i[u], __float_as_int(w_i[u]));
+                        if (s < oc) sPair[CAP + s] = make_int2(nb_o[u], __float_as_int(w_o[u]));
+                    }
+                }
             }
             tc_bar_arrive(BAR_SFULL + sb, ST + GT);
         }
@@ -393,6 +425,10 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             if (live) x = ldg4(X4 + (size_t)n * 4);           // early: independent of the gather
             // ---- GEMM2: D2 = h1 . W4^T  (A and B from shared memory) ----------------------
             tc_bar_sync(BAR_FULL + sb, ET + GT);
+            if (dbg & 4) {
+                if (tile + 2 * (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY + sb, ET + GT);
+                continue;
+            }
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t a_hi = sa + C::O_A + sb * 2 * C::A_BYTES, a_lo = a_hi + C::A_BYTES;
@@ -451,6 +487,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
             // ---- epilogue 3: [P'|Q'] = D3 + bias -> global ------------------------------------
+            if (!(dbg & 2))
             tc_store_projections<H>(lane_base, C::C_D3, sBP, reinterpret_cast<float*>(smem + C::O_OUT + warp * C::OUT_BYTES),
                                     tile * TM + warp * 32, n_nodes, lane, P_out, Q_out, write_q != 0);
             tc_fence_before();
@@ -607,8 +644,8 @@ int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, flo
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
-int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e,
-                     float* P_out, float* Q_out, int write_q, cudaStream_t st) {
+int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e_in,
+                     const float* e_out, float* P_out, float* Q_out, int write_q, cudaStream_t st) {
     using C = TcCfg<32>;
     if (g->n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (g->n_nodes + C::TM - 1) / C::TM;
@@ -619,7 +656,8 @@ int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, c
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
         return GNNSEG_ENODEVICE;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    node_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e, n_tiles, P_out, Q_out, write_q);
+    const char* dbg_env = getenv("GNNSEG_DBG");
+    node_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out, Q_out, write_q, dbg_env ? atoi(dbg_env) : 0);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 

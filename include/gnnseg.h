@@ -82,6 +82,8 @@ typedef struct GnnsegGraph {
     const int32_t* out_ptr;  /* [n_nodes+1] source-CSR row pointer                   */
     const int32_t* out_eid;  /* [out_ptr[n_nodes]]                                   */
     const int32_t* out_nbr;  /* [out_ptr[n_nodes]] dst[out_eid]                      */
+    const int32_t* in_pos;   /* [n_slots] position of the slot in in_eid  (in_eid[in_pos[j]] == j), -1 if dst[j] < 0  */
+    const int32_t* out_pos;  /* [n_slots] position of the slot in out_eid, -1 if src[j] < 0 */
 } GnnsegGraph;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -115,11 +117,12 @@ int gnnseg_dense_to_edges(const float* Ri, const float* Ro, int B, int N, int E,
  * Per-slot keys to CSR.  ptr[n_nodes+1], eid/nbr[n_slots] (only the first ptr[n_nodes] are
  * meaningful).  Slots with key < 0 are left out.  Rows list slot ids in ascending order,
  * which is np.nonzero's order, so the result is bit-identical to the reference's sparse
- * tuples.  nbr[s] = other[eid[s]].
+ * tuples.  nbr[s] = other[eid[s]];  pos[n_slots] (nullable) is the inverse map:
+ * pos[eid[s]] = s, -1 for slots that were left out.
  */
 size_t gnnseg_csr_workspace_bytes(int n_nodes, int n_slots);
 int    gnnseg_build_csr(const int32_t* key, const int32_t* other, int n_slots, int n_nodes,
-                        int32_t* ptr, int32_t* eid, int32_t* nbr,
+                        int32_t* ptr, int32_t* eid, int32_t* nbr, int32_t* pos,
                         void* ws, size_t ws_bytes, void* stream);
 
 /* ---- forward: replaces SegmentClassifier.forward, gnn/model.py:140-156 ---------------- */
@@ -144,16 +147,20 @@ int gnnseg_forward(const float* blob, const GnnsegGraph* graph, const float* X,
  * layer of each network is applied per node before the gather, which is the same algebra.)
  *   gnnseg_input_step : input_network + cat([H,X]) + projections      gnn/model.py:144-146
  *   gnnseg_edge_step  : EdgeNetwork.forward                            gnn/model.py:69-81
+ *                       writes the edge scores in slot order to `e` and/or, for the node step,
+ *                       in the two CSR orders to e_in[in_pos[j]] / e_out[out_pos[j]]
+ *                       (each of the three outputs may be NULL)
  *   gnnseg_node_step  : NodeNetwork.forward + cat([H,X]) + projections gnn/model.py:113-125,154
- *                       Q_out may be NULL when no further node step follows.
+ *                       reads the scores in CSR order; Q_out may be NULL when no further node
+ *                       step follows.
  */
 int gnnseg_input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* X4,
                       float* P, float* Q, void* stream);
 int gnnseg_edge_step(const float* blob, const GnnsegGraph* graph, const float* P, int h,
-                     float* e, void* stream);
+                     float* e, float* e_in, float* e_out, void* stream);
 int gnnseg_node_step(const float* blob, const GnnsegGraph* graph, const float* X4,
-                     const float* Q_in, const float* e, int h, float* P_out, float* Q_out,
-                     void* stream);
+                     const float* Q_in, const float* e_in, const float* e_out, int h,
+                     float* P_out, float* Q_out, void* stream);
 
 /* ---- host side: replaces graph_from_sparse + merge_graphs + np_to_torch --------------- */
 

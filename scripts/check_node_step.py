@@ -38,8 +38,10 @@ H0 = O.sparse_input(p, Xh)
 Pref, Qref = O.projections(p, H0)
 print("input: P err %.3e  Q err %.3e" % ((P.cpu() - Pref).abs().max().item(), (Q.cpu() - Qref).abs().max().item()))
 e_ref = O.sparse_edge(p, H0, src, dst)
-e_in = e_ref.to(dev).contiguous(); Q_in = Qref.to(dev).contiguous()
-rc = L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q_in), _ptr(e_in), h, _ptr(P2), _ptr(Q2), st)
+e_dev = e_ref.to(dev); Q_in = Qref.to(dev).contiguous()
+n_in, n_out = int(batch.in_ptr[-1]), int(batch.out_ptr[-1])
+e_in = e_dev[batch.in_eid[:n_in].long()].contiguous(); e_out = e_dev[batch.out_eid[:n_out].long()].contiguous()
+rc = L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q_in), _ptr(e_in), _ptr(e_out), h, _ptr(P2), _ptr(Q2), st)
 torch.cuda.synchronize()
 print("node_step rc", rc)
 H1 = torch.cat([O.sparse_node(p, H0, e_ref, src, dst), Xh], 1)

@@ -42,7 +42,7 @@ def test_host_only_queries():
     h = 32
     assert L.gnnseg_weights_floats(3, h) == 4 * h + h + (h + 4) * 5 * h + 5 * h + h + 4 + h * h + h
     # workspace: X4 + P + 2 Q + e
-    assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 32) >= 4 * (1000 * 4 + 1000 * 64 + 2 * 1000 * 96 + 5000)
+    assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 32) >= 4 * (1000 * 4 + 1000 * 64 + 2 * 1000 * 96 + 2 * 5000)
     assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 12) == 0
     assert L.gnnseg_csr_workspace_bytes(1000, 5000) >= 8 * 1001
 
@@ -55,4 +55,4 @@ def test_argument_errors_without_device_work():
     assert L.gnnseg_forward(None, None, None, 3, 12, 1, None, None, 0, None) == -2
     assert L.gnnseg_forward(None, None, None, 3, 32, 1, None, None, 0, None) == -1
     assert L.gnnseg_dense_to_edges(None, None, -1, 1, 1, None, None, None, None) == -1
-    assert L.gnnseg_build_csr(None, None, 5, 5, None, None, None, None, 0, None) == -1
+    assert L.gnnseg_build_csr(None, None, 5, 5, None, None, None, None, None, 0, None) == -1

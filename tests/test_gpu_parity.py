@@ -100,6 +100,10 @@ def test_dense_to_edges_and_csr_bit_exact(cuda_device):
             n_used = int(optr[-1])
             assert np.array_equal(eid.cpu().numpy()[:n_used], oeid)
             assert np.array_equal(nbr.cpu().numpy()[:n_used], other[oeid])
+        for key, pos, eid in ((dst, batch.in_pos, batch.in_eid), (src, batch.out_pos, batch.out_eid)):
+            pos, eid = pos.cpu().numpy(), eid.cpu().numpy()
+            assert np.array_equal(pos < 0, key < 0)                       # absent endpoint <=> not in the CSR
+            assert np.array_equal(eid[pos[key >= 0]], np.nonzero(key >= 0)[0])   # eid[pos[j]] == j
 
 
 def test_csr_matches_reference_nonzero_golden(cuda_device):
@@ -196,14 +200,22 @@ def test_each_kernel_against_oracle(name, cuda_device):
     assert torch.allclose(P.cpu(), Pref, rtol=1e-5, atol=2e-6)
     assert torch.allclose(Q.cpu(), Qref, rtol=1e-5, atol=2e-6)
 
-    assert L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, _ptr(e), st) == 0
+    e_in = torch.full((batch.n_slots,), -1.0, device=cuda_device)
+    e_out = torch.full((batch.n_slots,), -1.0, device=cuda_device)
+    assert L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, _ptr(e), _ptr(e_in), _ptr(e_out), st) == 0
     e_ref = O.sparse_edge(p, H0, src, dst)
     assert rel_err(e.cpu().numpy(), e_ref.numpy()) <= TOL
+    # the CSR-ordered copies hold exactly the same numbers: e_in[s] == e[in_eid[s]]
+    n_in, n_out = int(batch.in_ptr[-1]), int(batch.out_ptr[-1])
+    assert torch.equal(e_in[:n_in], e[batch.in_eid[:n_in].long()])
+    assert torch.equal(e_out[:n_out], e[batch.out_eid[:n_out].long()])
 
     # node step on the oracle's own e and Q, so that only this kernel is under test
-    e_in = e_ref.to(cuda_device).contiguous()
+    e_dev = e_ref.to(cuda_device)
+    e_in = e_dev[batch.in_eid[:n_in].long()].contiguous()
+    e_out = e_dev[batch.out_eid[:n_out].long()].contiguous()
     Q_in = Qref.to(cuda_device).contiguous()
-    assert L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q_in), _ptr(e_in), h,
+    assert L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q_in), _ptr(e_in), _ptr(e_out), h,
                               _ptr(P2), _ptr(Q2), st) == 0
     H1 = torch.cat([O.sparse_node(p, H0, e_ref, src, dst), Xh], dim=1)
     P1ref, Q1ref = O.projections(p, H1)
@@ -211,7 +223,7 @@ def test_each_kernel_against_oracle(name, cuda_device):
     assert torch.allclose(Q2.cpu(), Q1ref, rtol=1e-5, atol=3e-6)
     # Q_out = NULL (last iteration): P' identical, nothing else written
     P3 = torch.zeros_like(P)
-    assert L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q_in), _ptr(e_in), h,
+    assert L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q_in), _ptr(e_in), _ptr(e_out), h,
                               _ptr(P3), None, st) == 0
     assert torch.equal(P3, P2)
 
