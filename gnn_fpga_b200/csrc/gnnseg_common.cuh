@@ -32,12 +32,20 @@ struct Blob {
     static constexpr int B2  = W2 + H;               // [4]         b2, 0, 0, 0
     static constexpr int W4  = B2 + 4;               // [H][H]      node layer 2 ^T
     static constexpr int B4  = W4 + H * H;           // [H]
-    static constexpr int TOTAL = B4 + H;
+    // operand images for the tcgen05 kernels: W4 and WP as [out][k] matrices, split into tf32
+    // hi / lo parts, in the canonical K-major core-matrix layout (8 rows x 16 bytes per core
+    // matrix, core matrices contiguous along K) so that a CTA copies them to shared memory verbatim
+    static constexpr int D4P = (D4 + 7) / 8 * 8;
+    static constexpr int TC_W4H = B4 + H;            // [H][H]
+    static constexpr int TC_W4L = TC_W4H + H * H;
+    static constexpr int TC_WPH = TC_W4L + H * H;    // [5H][D4P]
+    static constexpr int TC_WPL = TC_WPH + 5 * H * D4P;
+    static constexpr int TOTAL = TC_WPL + 5 * H * D4P;
 };
 
 __host__ __device__ inline int blob_total(int h) {
-    const int d4 = h + 4;
-    return 4 * h + h + d4 * 5 * h + 5 * h + h + 4 + h * h + h;
+    const int d4 = h + 4, d4p = (d4 + 7) / 8 * 8;
+    return 4 * h + h + d4 * 5 * h + 5 * h + h + 4 + h * h + h + 2 * h * h + 2 * 5 * h * d4p;
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) {

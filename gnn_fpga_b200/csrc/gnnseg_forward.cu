@@ -25,7 +25,7 @@ namespace gnnseg {
 __global__ void pack_weights_kernel(GnnsegParams p, int F, int H, float* __restrict__ blob) {
     const int D = F + H, D4 = H + 4;
     const int o_bin = 4 * H, o_wp = o_bin + H, o_bp = o_wp + D4 * 5 * H, o_w2 = o_bp + 5 * H,
-              o_b2 = o_w2 + H, o_w4 = o_b2 + 4, o_b4 = o_w4 + H * H, total = o_b4 + H;
+              o_b2 = o_w2 + H, o_w4 = o_b2 + 4, o_b4 = o_w4 + H * H, total = o_b4 + H;   // fp32 part
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         float v = 0.f;
         if (i < o_bin) {                       // Win^T [4][H]
@@ -65,6 +65,35 @@ __global__ void pack_weights_kernel(GnnsegParams p, int F, int H, float* __restr
             v = p.b_n2[i - o_b4];
         }
         blob[i] = v;
+    }
+}
+
+// tf32 hi / lo operand images of W4 ([H][H]) and WP ([5H][D4P]) in the canonical K-major
+// core-matrix layout, from the fp32 [k][out] matrices written by pack_weights_kernel.
+__global__ void pack_tc_images_kernel(int H, float* __restrict__ blob) {
+    const int D4 = H + 4, D4P = (D4 + 7) / 8 * 8;
+    const int o_wp = 5 * H, o_w4 = o_wp + D4 * 5 * H + 5 * H + H + 4, o_img = o_w4 + H * H + H;
+    const int n_w4 = H * H, n_wp = 5 * H * D4P;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_w4 + n_wp; i += gridDim.x * blockDim.x) {
+        const bool is_w4 = i < n_w4;
+        const int f = is_w4 ? i : i - n_w4;                       // float index inside the image
+        const int K = is_w4 ? H : D4P;                            // padded K of this operand
+        const int sbo = (K / 4) * 128;                            // bytes between 8-row groups
+        const int bytes = f * 4;
+        const int grp = bytes / sbo, rem = bytes % sbo;
+        const int row = grp * 8 + (rem % 128) / 16, k = (rem / 128) * 4 + (rem % 16) / 4;
+        float v;
+        if (is_w4) v = blob[o_w4 + k * H + row];
+        else       v = k < D4 ? blob[o_wp + k * 5 * H + row] : 0.f;
+        uint32_t hi_bits;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi_bits) : "f"(v));
+        const float hi = __uint_as_float(hi_bits);
+        uint32_t lo_bits;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo_bits) : "f"(v - hi));
+        const int o_hi = is_w4 ? o_img : o_img + 2 * n_w4;
+        const int o_lo = is_w4 ? o_img + n_w4 : o_img + 2 * n_w4 + n_wp;
+        blob[o_hi + f] = hi;
+        blob[o_lo + f] = __uint_as_float(lo_bits);
     }
 }
 
@@ -687,6 +716,7 @@ int node_step(const float* blob, const GnnsegGraph* g, const float* X4, const fl
 int pack_weights(const GnnsegParams* p, int F, int h, float* blob, cudaStream_t st) {
     const int total = blob_total(h);
     pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(*p, F, h, blob);
+    pack_tc_images_kernel<<<(total + 255) / 256, 256, 0, st>>>(h, blob);
     return check_launch();
 }
 

@@ -273,22 +273,11 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
     const int n_nodes = g.n_nodes;
 
     // ---- prologue: weights (hi/lo, canonical layout), biases, TMEM, mbarrier ------------------
-    for (int i = tid; i < H * H; i += NT) {               // W4: [H outputs][H]
-        const int j = i / H, k = i % H;
-        float hi, lo;
-        split3(__ldg(blob + B::W4 + k * H + j), hi, lo);
-        const int off = canon_off(j, k, C::SBO_H);
-        *reinterpret_cast<float*>(smem + C::O_W4H + off) = hi;
-        *reinterpret_cast<float*>(smem + C::O_W4L + off) = lo;
-    }
-    for (int i = tid; i < NP * C::D4P; i += NT) {         // WP: [5H outputs][D4P]
-        const int j = i / C::D4P, k = i % C::D4P;
-        float hi, lo;
-        split3(k < D4 ? __ldg(blob + B::WP + k * NP + j) : 0.f, hi, lo);
-        const int off = canon_off(j, k, C::SBO_D4);
-        *reinterpret_cast<float*>(smem + C::O_WPH + off) = hi;
-        *reinterpret_cast<float*>(smem + C::O_WPL + off) = lo;
-    }
+    // the four operand images (W4 hi, W4 lo, WP hi, WP lo) are contiguous in the blob and in smem
+    static_assert(C::O_W4L == C::O_W4H + H * H * 4 && C::O_WPH == C::O_W4L + H * H * 4 &&
+                  C::O_WPL == C::O_WPH + NP * C::D4P * 4, "image order");
+    for (int i = tid * 4; i < 2 * H * H + 2 * NP * C::D4P; i += NT * 4)
+        *reinterpret_cast<float4*>(smem + C::O_W4H + i * 4) = ldg4(blob + B::TC_W4H + i);
     for (int i = tid; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
     for (int i = tid; i < NP; i += NT) sBP[i] = __ldg(blob + B::BP + i);
     if (tid == 0) {
@@ -536,14 +525,8 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < NP * N::D4P; i += NT) {
-        const int j = i / N::D4P, k = i % N::D4P;
-        float hi, lo;
-        split3(k < D4 ? __ldg(blob + B::WP + k * NP + j) : 0.f, hi, lo);
-        const int off = canon_off(j, k, N::SBO_D4);
-        *reinterpret_cast<float*>(smem + C::O_WPH + off) = hi;
-        *reinterpret_cast<float*>(smem + C::O_WPL + off) = lo;
-    }
+    for (int i = tid * 4; i < 2 * NP * N::D4P; i += NT * 4)      // WP hi, WP lo: contiguous images
+        *reinterpret_cast<float4*>(smem + C::O_WPH + i * 4) = ldg4(blob + B::TC_WPH + i);
     for (int i = tid; i < 5 * H; i += NT) sWin[i] = __ldg(blob + B::WIN + i);      // Win and bin are contiguous
     for (int i = tid; i < NP; i += NT) sBP[i] = __ldg(blob + B::BP + i);
     if (tid == 0) {

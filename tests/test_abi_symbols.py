@@ -39,8 +39,10 @@ def test_host_only_queries():
         assert L.gnnseg_supported(F, h) == 0
         assert L.gnnseg_weights_floats(F, h) == 0
     # blob size: Win^T[4][h] + b_in + WP^T[(h+4)][5h] + bias[5h] + W2 + 4 + W4^T + b4
+    #            + tf32 hi/lo operand images of W4 [h][h] and WP [5h][40]
     h = 32
-    assert L.gnnseg_weights_floats(3, h) == 4 * h + h + (h + 4) * 5 * h + 5 * h + h + 4 + h * h + h
+    assert L.gnnseg_weights_floats(3, h) == (4 * h + h + (h + 4) * 5 * h + 5 * h + h + 4 + h * h + h
+                                             + 2 * h * h + 2 * 5 * h * 40)
     # workspace: X4 + P + 2 Q + e
     assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 32) >= 4 * (1000 * 4 + 1000 * 64 + 2 * 1000 * 96 + 2 * 5000)
     assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 12) == 0
