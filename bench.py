@@ -279,7 +279,7 @@ def main():
         clocks = sampler.stop() if sampler else None
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(sum(step_ms))
-    launches_per_step = 1 + 1 + (cfg["n_iters"] + 1) + cfg["n_iters"]   # pack, input, edge x(it+1), node x it
+    launches_per_step = 2 + 1 + (cfg["n_iters"] + 1) + cfg["n_iters"]   # pack x2, input, edge x(it+1), node x it
 
     # ---- per-kernel durations (same process, CUDA events around single launches) ----------
     L = _lib.lib()
@@ -321,30 +321,46 @@ def main():
     e2e = None
     if not args.no_e2e:
         model.use_cuda_graph = False
-        host_out = None
+        host_out = torch.empty((len(graphs), batch.e_max), dtype=torch.float32, pin_memory=True)
         with torch.no_grad():
             for _ in range(3):
-                out = model(graphs)
-                host_out = out.to("cpu", non_blocking=False)
+                host_out.copy_(model(graphs), non_blocking=True)
+                torch.cuda.synchronize(dev)
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
-                out = model(graphs)
-                host_out = out.to("cpu", non_blocking=False)
-            torch.cuda.synchronize(dev)
+                host_out.copy_(model(graphs), non_blocking=True)   # scores land in pinned host memory
+                torch.cuda.synchronize(dev)                        # every step ends with its result on the host
             dt = time.perf_counter() - t0
         model.use_cuda_graph = True
         h2d = batch.X.numel() * 4 + batch.src.numel() * 4 + batch.dst.numel() * 4
         d2h = host_out.numel() * 4
         e2e = {"sec": dt, "h2d": h2d, "d2h": d2h}
 
+    # ---- optional collective: all ranks receive all scores (NCCL all-gather, not in `value`) ------
+    gather_ms = None
+    if world > 1:
+        from gnn_fpga_b200.dist import gather_scores, shard_bounds
+        bounds = shard_bounds(world * n_events, world)
+        local = batch.scores_2d()
+        gather_scores(local, bounds)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            allsc = gather_scores(local, bounds)
+        b.record()
+        torch.cuda.synchronize(dev)
+        gather_ms = a.elapsed_time(b) / 5
+        assert allsc.shape[0] == world * n_events
+
     # ---- reduce over ranks ---------------------------------------------------------------------
-    stats = torch.tensor([total_ms, e2e["sec"] if e2e else 0.0], dtype=torch.float64, device=dev)
+    stats = torch.tensor([total_ms, e2e["sec"] if e2e else 0.0, gather_ms or 0.0], dtype=torch.float64, device=dev)
     counts = torch.tensor([n_real, n_events], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    total_ms, e2e_sec = stats.tolist()
+    total_ms, e2e_sec, gather_ms_max = stats.tolist()
     all_edges, all_events = counts.tolist()
 
     if rank == 0:
@@ -385,6 +401,8 @@ def main():
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "ms_per_step": e2e_sec / args.steps * 1e3,
                            "path": "model(list of host SparseGraph) -> scores.cpu(): C host packing, H2D, device CSR build, forward, D2H"}
+        if world > 1:
+            line["scores_allgather_ms"] = gather_ms_max    # NCCL all-gather of every rank's (B, E_max) scores
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line), flush=True)

@@ -178,6 +178,10 @@ class DeviceGraphBatch:
         X = host["X"].to(dev, non_blocking=True)
         src = host["src"].to(dev, non_blocking=True)
         dst = host["dst"].to(dev, non_blocking=True)
+        if pinned is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            pinned["event"] = ev       # the caller must not refill the buffers before this fires
         return cls(X, src, dst, len(graphs), host["e_max"], n_nodes_per_event=host["n_nodes"])
 
     # -- helpers -------------------------------------------------------------------------

@@ -118,6 +118,7 @@ class SegmentClassifier(nn.Module):
         self._blob = None
         self.use_cuda_graph = True
         self._warned_grad = False
+        self._pinned = None          # reusable pinned staging buffers for host SparseGraph batches
 
     # -- weights -------------------------------------------------------------------------
     def _device(self):
@@ -198,6 +199,25 @@ class SegmentClassifier(nn.Module):
                 entry.replay()
         return batch.scores
 
+    def _pinned_buffers(self, graphs):
+        """Pinned host staging for the packed batch, grown on demand and reused across calls
+        (allocating pinned memory costs more than packing the batch)."""
+        n = sum(int(g.X.shape[0]) for g in graphs)
+        m = len(graphs) * max(int(g.Ri_rows.shape[0]) for g in graphs)
+        F = int(graphs[0].X.shape[1])
+        p = self._pinned
+        if p is None or p["X"].shape[0] < n or p["X"].shape[1] != F or p["src"].numel() < m:
+            cap_n, cap_m = int(n * 1.25) + 1, int(m * 1.25) + 1
+            self._pinned = p = {
+                "X": torch.empty((cap_n, F), dtype=torch.float32, pin_memory=True),
+                "src": torch.empty(cap_m, dtype=torch.int32, pin_memory=True),
+                "dst": torch.empty(cap_m, dtype=torch.int32, pin_memory=True),
+                "event": None,
+            }
+        if p["event"] is not None:
+            p["event"].synchronize()     # the previous batch's H2D copies have left the buffers
+        return p
+
     def forward(self, inputs):
         if torch.is_grad_enabled() and self.training and not self._warned_grad and \
                 any(p.requires_grad for p in self.parameters()):
@@ -207,7 +227,10 @@ class SegmentClassifier(nn.Module):
         if isinstance(inputs, DeviceGraphBatch):
             return self._run(inputs).view(inputs.B, inputs.e_max)
         if isinstance(inputs, (list, tuple)) and len(inputs) > 0 and isinstance(inputs[0], SparseGraph):
-            batch = DeviceGraphBatch.from_sparse_graphs(list(inputs), device=self._device())
+            from .graph import _require_cuda
+            dev = _require_cuda(self._device())        # fails loudly before any host work: no CPU path
+            batch = DeviceGraphBatch.from_sparse_graphs(list(inputs), device=dev,
+                                                        pinned=self._pinned_buffers(inputs))
             return self._run(batch).view(batch.B, batch.e_max)
         X, Ri, Ro = inputs
         if not (isinstance(X, torch.Tensor) and X.is_cuda):

@@ -1,0 +1,78 @@
+"""Event sharding + score gathering on CPU (gloo, world_size 2): the host logic of the
+multi-GPU path.  The per-rank forward is replaced by the CPU oracle here (tests may use it);
+on GPUs the same code runs with the CUDA model and NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gnn_fpga_b200 import data
+from gnn_fpga_b200.dist import shard_bounds, sharded_predict
+from oracle import segclf_oracle as O
+
+
+def test_shard_bounds_cover_and_balance():
+    for n, w in ((64, 8), (10, 4), (3, 8), (0, 2), (7, 1)):
+        b = shard_bounds(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1
+    wts = [100, 1, 1, 1, 100, 1, 1, 100]
+    b = shard_bounds(8, 3, wts)
+    assert b[0][0] == 0 and b[-1][1] == 8 and all(b[i][1] == b[i + 1][0] for i in range(2))
+    loads = [sum(wts[lo:hi]) for lo, hi in b]
+    assert max(loads) <= 1.5 * sum(wts) / 3
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, [1, 2, 3])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _oracle_forward(params, n_iters):
+    def fwd(graphs):
+        X, src, dst, e_max = O.flatten_sparse_batch(graphs)
+        return O.sparse_forward(params, X, src, dst, n_iters).reshape(len(graphs), e_max)
+    return fwd
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    graphs = [data.acts_like_graph(n, seed=i) for i, n in enumerate((12, 20, 9, 15, 11))]
+    params = O.init_params(3, 8, seed=0)
+    scores, bounds = sharded_predict(_oracle_forward(params, 2), graphs)
+    np.save(os.path.join(out_dir, "r%d.npy" % rank), scores.numpy())
+    np.save(os.path.join(out_dir, "b%d.npy" % rank), np.array(bounds))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_predict_equals_single_process(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "r0.npy"), np.load(tmp_path / "r1.npy")
+    assert np.array_equal(r0, r1, equal_nan=True)          # every rank holds all scores
+    graphs = [data.acts_like_graph(n, seed=i) for i, n in enumerate((12, 20, 9, 15, 11))]
+    params = O.init_params(3, 8, seed=0)
+    fwd = _oracle_forward(params, 2)
+    for b, g in enumerate(graphs):
+        n_e = g.Ri_rows.shape[0]
+        one = fwd([g])[0].numpy()
+        # same as the single-event result: an event's scores do not depend on its batch.  (The
+        # torch-CPU oracle's BLAS blocks differently per batch size, hence a 1e-6 tolerance here;
+        # the CUDA kernels are bit-equal, see test_gpu_parity.py::test_events_are_independent.)
+        assert np.allclose(r0[b, :n_e], one[:n_e], rtol=1e-6, atol=0)
+        assert np.all(np.isnan(r0[b, n_e:]) | (r0[b, n_e:] > 0))
+    bounds = np.load(tmp_path / "b0.npy")
+    assert bounds[0][0] == 0 and bounds[-1][1] == len(graphs)
