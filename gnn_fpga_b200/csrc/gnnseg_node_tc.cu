@@ -256,8 +256,7 @@ template <int H>
 __global__ void __launch_bounds__(TcCfg<H>::NT, 1)
 node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float* __restrict__ X4,
                const float* __restrict__ Q_in, const float* __restrict__ e_in, const float* __restrict__ e_out,
-               const int n_tiles, float* __restrict__ P_out, float* __restrict__ Q_out, const int write_q,
-               const int dbg) {
+               const int n_tiles, float* __restrict__ P_out, float* __restrict__ Q_out, const int write_q) {
     using C = TcCfg<H>;
     using B = Blob<H>;
     constexpr int TM = C::TM, NT = C::NT, ET = C::ET, ST = C::ST, GT = C::GT, D4 = C::D4, NP = C::NP;
@@ -318,7 +317,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             for (int ln = grp; ln < TM; ln += NGRP) {
                 const int n = node0 + ln;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n < n_nodes && !(dbg & 1)) {
+                if (n < n_nodes) {
                     acc = ldg4(Q_in + (size_t)n * 3 * H + 2 * H + 4 * c);            // Qs[n] (holds b3)
                     const int i0 = sPtr[ln], i1 = sPtr[ln + 1], o0 = sPtr[TM + 4 + ln], o1 = sPtr[TM + 4 + ln + 1];
                     if (staged) {
@@ -414,10 +413,6 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             if (live) x = ldg4(X4 + (size_t)n * 4);           // early: independent of the gather
             // ---- GEMM2: D2 = h1 . W4^T  (A and B from shared memory) ----------------------
             tc_bar_sync(BAR_FULL + sb, ET + GT);
-            if (dbg & 4) {
-                if (tile + 2 * (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY + sb, ET + GT);
-                continue;
-            }
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t a_hi = sa + C::O_A + sb * 2 * C::A_BYTES, a_lo = a_hi + C::A_BYTES;
@@ -476,7 +471,6 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
             // ---- epilogue 3: [P'|Q'] = D3 + bias -> global ------------------------------------
-            if (!(dbg & 2))
             tc_store_projections<H>(lane_base, C::C_D3, sBP, reinterpret_cast<float*>(smem + C::O_OUT + warp * C::OUT_BYTES),
                                     tile * TM + warp * 32, n_nodes, lane, P_out, Q_out, write_q != 0);
             tc_fence_before();
@@ -639,8 +633,7 @@ int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, c
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
         return GNNSEG_ENODEVICE;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    const char* dbg_env = getenv("GNNSEG_DBG");
-    node_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out, Q_out, write_q, dbg_env ? atoi(dbg_env) : 0);
+    node_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out, Q_out, write_q);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
