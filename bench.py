@@ -374,6 +374,10 @@ def main():
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
         dom = max(kernel_share, key=kernel_share.get)
         dom_bytes = ab[dom]
+        try:     # DRAM bytes per launch of that kernel, from the committed ncu capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[args.workload][dom]
+        except Exception:
+            traffic = None
         achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9
         ms_per_step = total_ms / args.steps
         fwd_gbs = ab["forward"] / (ms_per_step * 1e-3) / 1e9
@@ -388,7 +392,7 @@ def main():
                        "nodes_per_gpu": batch.n_nodes, "edges_per_gpu": n_real, "parallelism": "events sharded, dp%d" % world,
                        "l2": "flushed between timed steps (256 MiB write)", "cuda_graph": True},
             "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": kernel_ms[dom]},
             "roofline_forward": {"achieved": fwd_gbs, "frac": fwd_gbs / peak, "unit": "GB/s",
                                  "algorithmic_bytes": ab["forward"]},
