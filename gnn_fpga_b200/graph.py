@@ -175,6 +175,13 @@ class DeviceGraphBatch:
         are NOT padded because padded nodes influence no score)."""
         dev = _require_cuda(device)
         host = pack_sparse_batch_host(graphs, pinned=pinned, n_threads=n_threads)
+        return cls.from_packed_host(host, dev, pinned=pinned)
+
+    @classmethod
+    def from_packed_host(cls, host, device, pinned=None):
+        """Second half of from_sparse_graphs: H2D of an already packed batch + device CSR build."""
+        dev = _require_cuda(device)
+        graphs = host["n_nodes"]
         X = host["X"].to(dev, non_blocking=True)
         src = host["src"].to(dev, non_blocking=True)
         dst = host["dst"].to(dev, non_blocking=True)

@@ -199,16 +199,16 @@ class SegmentClassifier(nn.Module):
                 entry.replay()
         return batch.scores
 
-    def _pinned_buffers(self, graphs):
-        """Pinned host staging for the packed batch, grown on demand and reused across calls
+    @staticmethod
+    def _grow_pinned(p, graphs):
+        """Pinned host staging for a packed batch, grown on demand and reused across calls
         (allocating pinned memory costs more than packing the batch)."""
         n = sum(int(g.X.shape[0]) for g in graphs)
         m = len(graphs) * max(int(g.Ri_rows.shape[0]) for g in graphs)
         F = int(graphs[0].X.shape[1])
-        p = self._pinned
         if p is None or p["X"].shape[0] < n or p["X"].shape[1] != F or p["src"].numel() < m:
             cap_n, cap_m = int(n * 1.25) + 1, int(m * 1.25) + 1
-            self._pinned = p = {
+            p = {
                 "X": torch.empty((cap_n, F), dtype=torch.float32, pin_memory=True),
                 "src": torch.empty(cap_m, dtype=torch.int32, pin_memory=True),
                 "dst": torch.empty(cap_m, dtype=torch.int32, pin_memory=True),
@@ -217,6 +217,69 @@ class SegmentClassifier(nn.Module):
         if p["event"] is not None:
             p["event"].synchronize()     # the previous batch's H2D copies have left the buffers
         return p
+
+    def _pinned_buffers(self, graphs):
+        self._pinned = self._grow_pinned(self._pinned, graphs)
+        return self._pinned
+
+    def predict_stream(self, batches, depth=2):
+        """Pipelined inference over an iterable of batches (each a list of host SparseGraph
+        tuples): yields, in order, one pinned host tensor (B, E_max) of scores per batch.
+
+        Every batch goes through the same work as `model(graphs).cpu()` -- C host packing into
+        pinned memory, H2D, device CSR build, forward, D2H -- but nothing synchronises in
+        between: a worker thread packs batch i+1 (the C packer releases the GIL) while this
+        thread enqueues batch i and the GPU works on batch i-1.  `depth` batches are in flight;
+        a yielded tensor is reused `depth` batches later."""
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+        from .graph import _require_cuda, pack_sparse_batch_host
+        dev = _require_cuda(self._device())
+        slots = [{"pinned": None, "out": None, "done": None, "view": None} for _ in range(depth + 1)]
+        pending = deque()
+        was_graph, self.use_cuda_graph = self.use_cuda_graph, False    # one-shot batches: plain launches
+
+        def pack(graphs, slot):
+            slot["pinned"] = self._grow_pinned(slot["pinned"], graphs)   # waits for the slot's last H2D
+            return pack_sparse_batch_host(list(graphs), pinned=slot["pinned"])
+
+        pool = ThreadPoolExecutor(max_workers=1)
+        try:
+            with torch.no_grad():
+                it = iter(batches)
+                try:
+                    fut = pool.submit(pack, next(it), slots[0])
+                except StopIteration:
+                    fut = None
+                i = 0
+                while fut is not None:
+                    s = slots[i % (depth + 1)]
+                    host = fut.result()
+                    try:                                           # start packing the next batch right away
+                        fut = pool.submit(pack, next(it), slots[(i + 1) % (depth + 1)])
+                    except StopIteration:
+                        fut = None
+                    if len(pending) == depth:                     # keep `depth` results in flight
+                        old = pending.popleft()
+                        old["done"].synchronize()
+                        yield old["view"]
+                    batch = DeviceGraphBatch.from_packed_host(host, dev, pinned=s["pinned"])
+                    scores = self._run(batch)
+                    if s["out"] is None or s["out"].numel() < scores.numel():
+                        s["out"] = torch.empty(int(scores.numel() * 1.25) + 1, dtype=torch.float32, pin_memory=True)
+                    s["view"] = s["out"][:scores.numel()].view(batch.B, batch.e_max)
+                    s["view"].copy_(scores.view(batch.B, batch.e_max), non_blocking=True)
+                    s["done"] = torch.cuda.Event()
+                    s["done"].record(torch.cuda.current_stream(dev))
+                    pending.append(s)
+                    i += 1
+                while pending:
+                    old = pending.popleft()
+                    old["done"].synchronize()
+                    yield old["view"]
+        finally:
+            pool.shutdown(wait=True)
+            self.use_cuda_graph = was_graph
 
     def forward(self, inputs):
         if torch.is_grad_enabled() and self.training and not self._warned_grad and \

@@ -344,3 +344,18 @@ def test_empty_and_tiny_inputs(cuda_device):
     # zero edges in the whole batch
     out = model([g0])
     assert tuple(out.shape) == (1, 0)
+
+
+def test_predict_stream_matches_blocking_calls(cuda_device):
+    """Pipelined host-to-host inference returns, in order, the same bits as model(graphs)."""
+    from gnn_fpga_b200 import data, SegmentClassifier
+    torch.manual_seed(3)
+    model = SegmentClassifier(3, 32, 2).to(cuda_device).eval()
+    batches = [[data.acts_like_graph(n, seed=10 * b + i) for i, n in enumerate((30 + b, 45, 25 + 2 * b))] for b in range(5)]
+    expect = [model(g).cpu() for g in batches]
+    got = [t.clone() for t in model.predict_stream(batches, depth=2)]
+    assert len(got) == len(expect)
+    for a, b in zip(got, expect):
+        assert a.shape == b.shape and torch.equal(a, b)
+    assert [t.shape for t in model.predict_stream(batches[:1], depth=3)] == [expect[0].shape]
+    assert list(model.predict_stream([])) == []
