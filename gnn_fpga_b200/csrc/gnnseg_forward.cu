@@ -335,7 +335,7 @@ input_kernel(const float* __restrict__ blob, const float* __restrict__ X, const 
                 fma4(v, x.y, lds4(sWin + 1 * H + 4 * c));
                 fma4(v, x.z, lds4(sWin + 2 * H + 4 * c));
                 fma4(v, x.w, lds4(sWin + 3 * H + 4 * c));
-                v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
+                v.x = tanh_fast(v.x); v.y = tanh_fast(v.y); v.z = tanh_fast(v.z); v.w = tanh_fast(v.w);
             } else {
                 v = x;
                 if (node0 + ln < n_nodes) st4(X4 + (size_t)(node0 + ln) * 4, x);
@@ -389,10 +389,10 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);      // absent end:   W1b.0
             if (ss >= 0) a = ldg4_hint(P + (size_t)ss * (2 * H) + 4 * c, keep);
             if (dd >= 0) b = ldg4_hint(P + (size_t)dd * (2 * H) + H + 4 * c, keep);
-            float z = w2.x * tanhf(a.x + b.x);
-            z = fmaf(w2.y, tanhf(a.y + b.y), z);
-            z = fmaf(w2.z, tanhf(a.z + b.z), z);
-            z = fmaf(w2.w, tanhf(a.w + b.w), z);
+            float z = w2.x * tanh_fast(a.x + b.x);
+            z = fmaf(w2.y, tanh_fast(a.y + b.y), z);
+            z = fmaf(w2.z, tanh_fast(a.z + b.z), z);
+            z = fmaf(w2.w, tanh_fast(a.w + b.w), z);
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
             const float v = __shfl_sync(0xffffffffu, z, (lane % EPP) * G);
@@ -551,7 +551,7 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __
                         csr_row_sum<false>(nullptr, g.in_nbr, e_in, Q_in + 4 * c, 3 * H, i0, i1, acc);
                         csr_row_sum<false>(nullptr, g.out_nbr, e_out, Q_in + H + 4 * c, 3 * H, o0, o1, acc);
                     }
-                    acc.x = tanhf(acc.x); acc.y = tanhf(acc.y); acc.z = tanhf(acc.z); acc.w = tanhf(acc.w);
+                    acc.x = tanh_fast(acc.x); acc.y = tanh_fast(acc.y); acc.z = tanh_fast(acc.z); acc.w = tanh_fast(acc.w);
                 }
                 st4(sHb + ln * SH + 4 * c, acc);
             }
@@ -574,13 +574,13 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __
             if constexpr (MMA) {
                 tile_gemm_mma<H / 8, H>(sHb, SH, sW4, SH, [&](int ln, int o, float v0, float v1) {
                     *reinterpret_cast<float2*>(sHX + ln * SD + o) =
-                        make_float2(tanhf(v0 + sB4[o]), tanhf(v1 + sB4[o + 1]));
+                        make_float2(tanh_fast(v0 + sB4[o]), tanh_fast(v1 + sB4[o + 1]));
                 });
             } else {
                 tile_gemm<H, H, TN, CT, C::RN, 4>(sHb, SH, sW4, [&](int ln, int o, const float* acc) {
                     const float4 b = lds4(sB4 + o);
-                    st4(sHX + ln * SD + o, make_float4(tanhf(acc[0] + b.x), tanhf(acc[1] + b.y),
-                                                       tanhf(acc[2] + b.z), tanhf(acc[3] + b.w)));
+                    st4(sHX + ln * SD + o, make_float4(tanh_fast(acc[0] + b.x), tanh_fast(acc[1] + b.y),
+                                                       tanh_fast(acc[2] + b.z), tanh_fast(acc[3] + b.w)));
                 });
             }
             bar_sync(BAR_CONS, CT);

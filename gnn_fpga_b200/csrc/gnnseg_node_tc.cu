@@ -327,7 +327,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
                         tc_row_sum<false>(nullptr, g.in_nbr, e_in, Q_in + 4 * c, 3 * H, i0, i1, keep, acc);
                         tc_row_sum<false>(nullptr, g.out_nbr, e_out, Q_in + H + 4 * c, 3 * H, o0, o1, keep, acc);
                     }
-                    acc.x = tanhf(acc.x); acc.y = tanhf(acc.y); acc.z = tanhf(acc.z); acc.w = tanhf(acc.w);
+                    acc.x = tanh_fast(acc.x); acc.y = tanh_fast(acc.y); acc.z = tanh_fast(acc.z); acc.w = tanh_fast(acc.w);
                 }
                 float4 hh, hl;
                 split3(acc.x, hh.x, hl.x); split3(acc.y, hh.y, hl.y); split3(acc.z, hh.z, hl.z); split3(acc.w, hh.w, hl.w);
@@ -438,7 +438,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
                 float v[16], hi[16], lo[16];
                 tmem_ld16(lane_base + C::C_D2 + c0, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) split3(tanhf(v[i] + sB4[c0 + i]), hi[i], lo[i]);
+                for (int i = 0; i < 16; ++i) split3(tanh_fast(v[i] + sB4[c0 + i]), hi[i], lo[i]);
                 tmem_st16(lane_base + C::C_A3H + c0, hi);
                 tmem_st16(lane_base + C::C_A3L + c0, lo);
             }
@@ -559,7 +559,7 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
                 v = fmaf(x[1], sWin[1 * H + c0 + i], v);
                 v = fmaf(x[2], sWin[2 * H + c0 + i], v);
                 v = fmaf(x[3], sWin[3 * H + c0 + i], v);
-                split3(tanhf(v), hi[i], lo[i]);
+                split3(tanh_fast(v), hi[i], lo[i]);
             }
             tmem_st16(lane_base + C::C_A3H + c0, hi);
             tmem_st16(lane_base + C::C_A3L + c0, lo);

@@ -52,3 +52,10 @@ print("node: P' max abs err %.3e (bad rows %d)  Q' max abs err %.3e (bad rows %d
 if dP.max() > 1e-4:
     bad = torch.nonzero(dP.max(1).values > 1e-4).flatten()[:10]
     print("first bad rows", bad.tolist()); r = int(bad[0]); print("got", P2[r, :8].tolist()); print("ref", P1[r, :8].tolist())
+# end-to-end accuracy of the full forward vs fp32 / fp64 oracles
+if name.startswith("big"):
+    out = model(graphs).cpu().numpy()
+    Xf, s_, d_, _ = O.flatten_sparse_batch(graphs)
+    for dt in (torch.float32, torch.float64):
+        ref = O.sparse_forward(p, Xf, s_, d_, 2, dt).numpy().reshape(out.shape)
+        print("forward rel err vs", dt, float(np.max(np.abs(out - ref) / np.abs(ref))))
