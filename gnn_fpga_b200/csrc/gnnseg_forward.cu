@@ -377,8 +377,13 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
 
     for (int base = warp * 32; base < n_slots; base += n_warps * 32) {
         const int j = base + lane;
-        int s = -1, d = -1;
-        if (j < n_slots) { s = __ldg(src + j); d = __ldg(dst + j); }
+        int s = -1, d = -1, pi = -1, po = -1;
+        if (j < n_slots) {
+            s = __ldg(src + j);
+            d = __ldg(dst + j);
+            if (e_in) pi = __ldg(in_pos + j);      // issued now, needed only after the MLP
+            if (e_out) po = __ldg(out_pos + j);
+        }
         float mine = 0.f;
 #pragma unroll (G > 8 ? 8 : G)
         for (int p = 0; p < G; ++p) {
@@ -401,14 +406,8 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
         if (j < n_slots) {
             const float score = 1.f / (1.f + expf(-(mine + b2)));
             if (e_slot) e_slot[j] = score;
-            if (e_in) {                       // the node step reads the scores in CSR order
-                const int pi = __ldg(in_pos + j);
-                if (pi >= 0) e_in[pi] = score;
-            }
-            if (e_out) {
-                const int po = __ldg(out_pos + j);
-                if (po >= 0) e_out[po] = score;
-            }
+            if (pi >= 0) e_in[pi] = score;       // the node step reads the scores in CSR order
+            if (po >= 0) e_out[po] = score;
         }
     }
 }
