@@ -29,11 +29,14 @@ extern "C" int gnnseg_pack_sparse_batch_host(
     }
     if (node_off[B] > 0x7fffffffLL || (int64_t)B * e_max > 0x7fffffffLL) return GNNSEG_EINVAL;
 
-    std::atomic<int> next(0), bad(0);
-    auto work = [&]() {
-        for (;;) {
-            const int b = next.fetch_add(1);
-            if (b >= B) return;
+    std::atomic<int> bad(0);
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, std::min(B, 64)));
+    // OpenMP keeps its worker team alive between calls (creating 16 std::threads per batch
+    // cost a quarter of the packing time)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+    for (int b = 0; b < B; ++b) {
+        {
             const int64_t nn = n_nodes_host[b], off = node_off[b];
             if (nn > 0) std::memcpy(X_out_host + off * F, X_host[b], sizeof(float) * nn * F);
             int32_t* src = src_host + (int64_t)b * e_max;
@@ -55,15 +58,6 @@ extern "C" int gnnseg_pack_sparse_batch_host(
                 src[c] = (int32_t)(off + r);
             }
         }
-    };
-    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-    nt = std::max(1, std::min(nt, std::min(B, 64)));
-    if (nt == 1) {
-        work();
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nt; ++t) pool.emplace_back(work);
-        for (auto& t : pool) t.join();
     }
     return bad.load() ? GNNSEG_EINVAL : GNNSEG_OK;
 }

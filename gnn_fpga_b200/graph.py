@@ -222,19 +222,20 @@ def pack_sparse_batch_host(graphs, pinned=None, n_threads=0):
     keep = []   # keep converted arrays alive during the call
 
     def arr(a, dt):
-        a = np.ascontiguousarray(a, dtype=dt)
-        keep.append(a)
+        if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
         return a
 
     Xs = [arr(g.X, np.float32) for g in graphs]
-    cols = [[arr(getattr(g, k), np.int64) for g in graphs] for k in ("Ri_rows", "Ri_cols", "Ro_rows", "Ro_cols")]
-    n_nodes = np.array([x.shape[0] for x in Xs], dtype=np.int64)
-    n_in = np.array([a.shape[0] for a in cols[0]], dtype=np.int64)
-    n_out = np.array([a.shape[0] for a in cols[2]], dtype=np.int64)
-    for b, g in enumerate(graphs):
+    cols = [[arr(g[k], np.int64) for g in graphs] for k in (1, 2, 3, 4)]    # Ri_rows, Ri_cols, Ro_rows, Ro_cols
+    n_nodes = np.fromiter((x.shape[0] for x in Xs), dtype=np.int64, count=B)
+    n_in = np.fromiter((a.shape[0] for a in cols[0]), dtype=np.int64, count=B)
+    n_out = np.fromiter((a.shape[0] for a in cols[2]), dtype=np.int64, count=B)
+    for b in range(B):
         if Xs[b].ndim != 2 or Xs[b].shape[1] != F:
             raise ValueError("graph %d: X must be (N, %d)" % (b, F))
-        if cols[1][b].shape != cols[0][b].shape or cols[3][b].shape != cols[2][b].shape:
+        if cols[1][b].shape[0] != n_in[b] or cols[3][b].shape[0] != n_out[b]:
             raise ValueError("graph %d: rows/cols length mismatch" % b)
     e_max = int(n_in.max())    # graph_from_sparse: n_edges = len(Ri_rows)
     nt = int(n_nodes.sum())
@@ -246,12 +247,15 @@ def pack_sparse_batch_host(graphs, pinned=None, n_threads=0):
         src = torch.empty(B * e_max, dtype=torch.int32, pin_memory=can_pin)
         dst = torch.empty(B * e_max, dtype=torch.int32, pin_memory=can_pin)
 
-    def pp(arrs):
-        return (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+    def pp(arrs):     # array of B data pointers (numpy's array interface is much cheaper than .ctypes)
+        t = np.fromiter((a.__array_interface__["data"][0] for a in arrs), dtype=np.uintp, count=B)
+        keep.append(t)
+        return t.__array_interface__["data"][0]
 
     rc = L.gnnseg_pack_sparse_batch_host(
-        B, F, e_max, pp(Xs), n_nodes.ctypes.data, pp(cols[0]), pp(cols[1]), pp(cols[2]), pp(cols[3]),
-        n_in.ctypes.data, n_out.ctypes.data, Xo.data_ptr(), src.data_ptr(), dst.data_ptr(), n_threads)
+        B, F, e_max, pp(Xs), n_nodes.__array_interface__["data"][0], pp(cols[0]), pp(cols[1]), pp(cols[2]), pp(cols[3]),
+        n_in.__array_interface__["data"][0], n_out.__array_interface__["data"][0],
+        Xo.data_ptr(), src.data_ptr(), dst.data_ptr(), n_threads)
     if rc == -1:
         raise ValueError("SparseGraph index out of range (row >= n_nodes or col >= max len(Ri_rows))")
     _lib.check(rc, "gnnseg_pack_sparse_batch_host")

@@ -235,42 +235,71 @@ class SegmentClassifier(nn.Module):
         from concurrent.futures import ThreadPoolExecutor
         from .graph import _require_cuda, pack_sparse_batch_host
         dev = _require_cuda(self._device())
-        slots = [{"pinned": None, "out": None, "done": None, "view": None} for _ in range(depth + 1)]
+        LOOK = 1                                                   # batches being packed ahead (the packer is GIL/DRAM bound: one is enough)
+        n_slots = depth + LOOK
+        slots = [{"pinned": None, "out": None, "done": None, "view": None} for _ in range(n_slots)]
         pending = deque()
         was_graph, self.use_cuda_graph = self.use_cuda_graph, False    # one-shot batches: plain launches
-
         def pack(graphs, slot):
             slot["pinned"] = self._grow_pinned(slot["pinned"], graphs)   # waits for the slot's last H2D
             return pack_sparse_batch_host(list(graphs), pinned=slot["pinned"])
 
-        pool = ThreadPoolExecutor(max_workers=1)
+        pool = ThreadPoolExecutor(max_workers=LOOK)
+        compute = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         try:
             with torch.no_grad():
                 it = iter(batches)
-                try:
-                    fut = pool.submit(pack, next(it), slots[0])
-                except StopIteration:
-                    fut = None
-                i = 0
-                while fut is not None:
-                    s = slots[i % (depth + 1)]
-                    host = fut.result()
-                    try:                                           # start packing the next batch right away
-                        fut = pool.submit(pack, next(it), slots[(i + 1) % (depth + 1)])
+                futs = deque()
+                n_sub = 0
+
+                def submit_next():
+                    nonlocal n_sub
+                    try:
+                        g = next(it)
                     except StopIteration:
-                        fut = None
+                        return
+                    futs.append(pool.submit(pack, g, slots[n_sub % n_slots]))
+                    n_sub += 1
+
+                for _ in range(LOOK):
+                    submit_next()
+                i = 0
+                while futs:
+                    s = slots[i % n_slots]
+                    host = futs.popleft().result()
+                    submit_next()                                 # keep LOOK batches being packed
                     if len(pending) == depth:                     # keep `depth` results in flight
                         old = pending.popleft()
                         old["done"].synchronize()
                         yield old["view"]
-                    batch = DeviceGraphBatch.from_packed_host(host, dev, pinned=s["pinned"])
+                    # H2D on its own stream (copy engine), CSR build + forward on the compute
+                    # stream, D2H on a third stream: the copies of neighbouring batches overlap
+                    # the compute of this one
+                    with torch.cuda.stream(s_in):
+                        X = host["X"].to(dev, non_blocking=True)
+                        src = host["src"].to(dev, non_blocking=True)
+                        dst = host["dst"].to(dev, non_blocking=True)
+                        ev_in = torch.cuda.Event()
+                        ev_in.record(s_in)
+                    s["pinned"]["event"] = ev_in                  # the packer may refill the slot after this
+                    compute.wait_event(ev_in)
+                    for t in (X, src, dst):
+                        t.record_stream(compute)
+                    batch = DeviceGraphBatch(X, src, dst, len(host["n_nodes"]), host["e_max"],
+                                             n_nodes_per_event=host["n_nodes"])
                     scores = self._run(batch)
                     if s["out"] is None or s["out"].numel() < scores.numel():
                         s["out"] = torch.empty(int(scores.numel() * 1.25) + 1, dtype=torch.float32, pin_memory=True)
                     s["view"] = s["out"][:scores.numel()].view(batch.B, batch.e_max)
-                    s["view"].copy_(scores.view(batch.B, batch.e_max), non_blocking=True)
-                    s["done"] = torch.cuda.Event()
-                    s["done"].record(torch.cuda.current_stream(dev))
+                    ev_c = torch.cuda.Event()
+                    ev_c.record(compute)
+                    s_out.wait_event(ev_c)
+                    scores.record_stream(s_out)
+                    with torch.cuda.stream(s_out):
+                        s["view"].copy_(scores.view(batch.B, batch.e_max), non_blocking=True)
+                        s["done"] = torch.cuda.Event()
+                        s["done"].record(s_out)
                     pending.append(s)
                     i += 1
                 while pending:
