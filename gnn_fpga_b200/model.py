@@ -310,12 +310,43 @@ class SegmentClassifier(nn.Module):
             pool.shutdown(wait=True)
             self.use_cuda_graph = was_graph
 
+    def _wants_grad(self):
+        # training mode + autograd on + trainable parameters: what Estimator.fit_gen / training_step
+        # set up (model.train(), gnn/estimator.py:96); eval() or no_grad() always means inference
+        return self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _to_batch(self, inputs):
+        if isinstance(inputs, DeviceGraphBatch):
+            return inputs
+        if isinstance(inputs, (list, tuple)) and len(inputs) > 0 and isinstance(inputs[0], SparseGraph):
+            from .graph import _require_cuda
+            dev = _require_cuda(self._device())
+            return DeviceGraphBatch.from_sparse_graphs(list(inputs), device=dev, pinned=self._pinned_buffers(inputs))
+        X, Ri, Ro = inputs
+        if not (isinstance(X, torch.Tensor) and X.is_cuda):
+            raise ValueError("SegmentClassifier expects CUDA tensors [X, Ri, Ro] (got %s); there is no CPU path"
+                             % (X.device if isinstance(X, torch.Tensor) else type(X)))
+        return DeviceGraphBatch.from_dense(X, Ri, Ro)
+
     def forward(self, inputs):
-        if torch.is_grad_enabled() and self.training and not self._warned_grad and \
-                any(p.requires_grad for p in self.parameters()):
-            warnings.warn("gnn_fpga_b200.SegmentClassifier.forward does not record an autograd graph; "
-                          "use gnn_fpga_b200.training for the native training step")
-            self._warned_grad = True
+        if self._wants_grad():
+            # A forward that must be differentiated (Estimator.training_step, gnn/estimator.py:53):
+            # the sm_100a kernels have no backward yet, so this one call runs the same sparse
+            # formulation with torch ops on the GPU (gnn_fpga_b200/training.py).  Inference
+            # (no_grad, as Estimator.predict does) always takes the CUDA kernels below.
+            if not self._warned_grad:
+                warnings.warn("SegmentClassifier.forward under autograd uses the torch-op sparse path "
+                              "(gnn_fpga_b200.training.autograd_forward); wrap inference in torch.no_grad()")
+                self._warned_grad = True
+            from .training import autograd_forward
+            if self._device().type != "cuda":
+                raise _lib.GnnsegError("SegmentClassifier parameters are on %s: there is no CPU path" % self._device())
+            if _lib.lib().gnnseg_supported(self.input_dim, self.hidden_dim) == 0:   # same shapes as inference
+                _lib.check(-2, "SegmentClassifier(input_dim=%d, hidden_dim=%d)" % (self.input_dim, self.hidden_dim))
+            batch = self._to_batch(inputs)
+            if batch.F != self.input_dim:
+                raise ValueError("X has %d features, model expects input_dim=%d" % (batch.F, self.input_dim))
+            return autograd_forward(self, batch)
         if isinstance(inputs, DeviceGraphBatch):
             return self._run(inputs).view(inputs.B, inputs.e_max)
         if isinstance(inputs, (list, tuple)) and len(inputs) > 0 and isinstance(inputs[0], SparseGraph):

@@ -154,6 +154,38 @@ def main():
                         Ri_rows=sg.Ri_rows, Ri_cols=sg.Ri_cols, Ro_rows=sg.Ro_rows, Ro_cols=sg.Ro_cols)
     print("graph_roundtrip        N=%d E=%d dtype=%s" % (d.Ri.shape[0], d.Ri.shape[1], sg.Ri_rows.dtype))
 
+    # two training steps through the reference's own Estimator.training_step (gnn/estimator.py:49-60):
+    # BCELoss over all padded slots + L1 penalty, Adam
+    import estimator as ref_estimator                                  # noqa: E402  (reference)
+    g_t = [data.acts_like_graph(n, seed=50 + i) for i, n in enumerate((14, 18, 11))]
+    dense = [ref_graph.graph_from_sparse(ref_graph.SparseGraph(*g)) for g in g_t]
+    X, Ri, Ro = merge_graphs(dense)
+    e_max = Ri.shape[2]
+    y = np.zeros((len(g_t), e_max), np.float32)
+    for b, g in enumerate(g_t):
+        y[b, :g.y.shape[0]] = g.y
+    torch.manual_seed(9)
+    net = ref_model.SegmentClassifier(3, 8, 2, masks_e=None, masks_n=ones_masks(3, 8))
+    rec = {"X": X.astype(np.float32), "Ri": Ri.astype(np.uint8), "Ro": Ro.astype(np.uint8), "y": y,
+           "F": 3, "h": 8, "n_iters": 2, "seed": 9, "l1": 1e-4}
+    for k, v in net.state_dict().items():
+        rec["param:" + k] = v.numpy().copy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        est = ref_estimator.Estimator(net, torch.nn.BCELoss(), opt="Adam", l1=1e-4)
+    inputs = [torch.from_numpy(a.astype(np.float32)) for a in (X, Ri, Ro)]
+    net.train()
+    losses = []
+    for step in range(2):
+        losses.append(float(est.training_step(inputs, torch.from_numpy(y)).item()))
+        if step == 0:
+            for k, p_ in net.named_parameters():
+                rec["grad0:" + k] = p_.grad.numpy().copy()
+    for k, v in net.state_dict().items():
+        rec["after:" + k] = v.numpy().copy()
+    rec["losses"] = np.array(losses)
+    np.savez_compressed(os.path.join(OUT, "train_step_h8_it2.npz"), **rec)
+    print("train_step_h8_it2      losses=%s" % losses)
+
     # state_dict key list and parameter counts (SURVEY.md §4 structural pins)
     counts = {}
     for (F, h) in ((3, 4), (3, 8), (3, 32), (3, 64), (2, 32)):

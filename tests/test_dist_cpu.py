@@ -76,3 +76,31 @@ def test_two_rank_sharded_predict_equals_single_process(tmp_path):
         assert np.all(np.isnan(r0[b, n_e:]) | (r0[b, n_e:] > 0))
     bounds = np.load(tmp_path / "b0.npy")
     assert bounds[0][0] == 0 and bounds[-1][1] == len(graphs)
+
+
+def _grad_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gnn_fpga_b200.training import allreduce_gradients
+    torch.manual_seed(0)
+    lin = [torch.nn.Linear(3, 4), torch.nn.Linear(4, 1)]
+    params = [p for l in lin for p in l.parameters()]
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    params[1].grad = None                       # a parameter without gradient is skipped
+    allreduce_gradients(params)
+    np.save(os.path.join(out_dir, "g%d.npy" % rank),
+            np.concatenate([p.grad.reshape(-1).numpy() for p in params if p.grad is not None]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_averages(tmp_path):
+    """allreduce_gradients: one flat all-reduce, mean over ranks, identical on every rank
+    (the NCCL step of the sharded training_step; gloo here)."""
+    mp.spawn(_grad_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    g0, g1 = np.load(tmp_path / "g0.npy"), np.load(tmp_path / "g1.npy")
+    assert np.array_equal(g0, g1)
+    # ranks held (i+1) and 2(i+1): the mean is 1.5 (i+1) for parameter i in {0, 2, 3}
+    expect = np.concatenate([np.full(12, 1.5), np.full(4, 4.5), np.full(1, 6.0)])
+    assert np.allclose(g0, expect)
