@@ -27,7 +27,7 @@ namespace gnnseg {
 template <int H>
 struct TcCfg {
     static constexpr int TM   = 128;                 // nodes per tile = UMMA M
-    static constexpr int EW   = 4;                   // MLP warps (issuer + epilogue): warp w owns TMEM lanes 32w..32w+31
+    static constexpr int EW   = 8;                   // MLP warps (issuer + epilogue): warp w owns TMEM lanes 32(w%4)..+31 and half of the columns
     static constexpr int SW   = 4;                   // stager warps
     static constexpr int GW   = 16;                  // gather warps
     static constexpr int ET   = EW * 32;
@@ -222,12 +222,14 @@ __device__ __forceinline__ void tc_store_projections(const uint32_t lane_base, c
                                                      const float* __restrict__ sBP, float* __restrict__ sOut,
                                                      const int node_w0, const int n_nodes, const int lane,
                                                      float* __restrict__ P_out, float* __restrict__ Q_out,
-                                                     const bool write_q) {
+                                                     const bool write_q, const int chunk0 = 0,
+                                                     const int chunk_step = 1) {
     constexpr int NP = 5 * H, OS = TcCfg<H>::OUT_STRIDE;
     const uint64_t stream = l2_policy_evict_first();           // read next by another kernel, not by this one
     const int c_end = write_q ? NP : 2 * H;
+    // 32-column chunks; two warps that share a TMEM lane quarter take alternate chunks
 #pragma unroll 1
-    for (int c0 = 0; c0 < c_end; c0 += 32) {
+    for (int c0 = 32 * chunk0; c0 < c_end; c0 += 32 * chunk_step) {
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
             float v[16];
@@ -399,8 +401,9 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
     } else {
         // ================================ MLP (issuer + epilogue) ======================
         const uint32_t mb = smem_u32(mbar);
-        const int row = warp * 32 + lane;                     // node within the tile = TMEM lane
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const int q = warp & 3, hf = warp >> 2;               // TMEM lane quarter, which half of the columns
+        const int row = q * 32 + lane;                        // node within the tile = TMEM lane
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         constexpr uint32_t ID2 = idesc_tf32(TM, H), ID3 = idesc_tf32(TM, NP);
         const uint32_t sa = smem_u32(smem);
         uint32_t phase = 0;
@@ -410,7 +413,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             const int n = tile * TM + row;
             const bool live = n < n_nodes;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) x = ldg4(X4 + (size_t)n * 4);           // early: independent of the gather
+            if (live && hf == 0) x = ldg4(X4 + (size_t)n * 4); // early: independent of the gather
             // ---- GEMM2: D2 = h1 . W4^T  (A and B from shared memory) ----------------------
             tc_bar_sync(BAR_FULL + sb, ET + GT);
             if (tid == 0) {
@@ -433,8 +436,8 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             tc_fence_after();
             if (tile + 2 * (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY + sb, ET + GT);   // A buffer may be refilled
             // ---- epilogue 2: H' = tanh(D2 + b4); [H'|X|0] -> A3 (hi, lo) in TMEM -------------
-#pragma unroll
-            for (int c0 = 0; c0 < H; c0 += 16) {
+            {
+                const int c0 = hf * (H / 2);                       // this warp's 16 columns
                 float v[16], hi[16], lo[16];
                 tmem_ld16(lane_base + C::C_D2 + c0, v);
 #pragma unroll
@@ -442,7 +445,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
                 tmem_st16(lane_base + C::C_A3H + c0, hi);
                 tmem_st16(lane_base + C::C_A3L + c0, lo);
             }
-            {                                                     // columns H..H+7: X and the zero K padding
+            if (hf == 0) {                                        // columns H..H+7: X and the zero K padding
                 float xh[8], xl[8];
                 split3(x.x, xh[0], xl[0]); split3(x.y, xh[1], xl[1]);
                 split3(x.z, xh[2], xl[2]); split3(x.w, xh[3], xl[3]);
@@ -472,7 +475,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             tc_fence_after();
             // ---- epilogue 3: [P'|Q'] = D3 + bias -> global ------------------------------------
             tc_store_projections<H>(lane_base, C::C_D3, sBP, reinterpret_cast<float*>(smem + C::O_OUT + warp * C::OUT_BYTES),
-                                    tile * TM + warp * 32, n_nodes, lane, P_out, Q_out, write_q != 0);
+                                    tile * TM + q * 32, n_nodes, lane, P_out, Q_out, write_q != 0, hf, 2);
             tc_fence_before();
             tc_bar_sync(BAR_EPI, ET);     // TMEM tiles are rewritten by the next tile
         }
