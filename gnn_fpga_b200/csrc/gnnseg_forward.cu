@@ -664,7 +664,10 @@ static int launch_edge(const float* blob, const GnnsegGraph* g, const float* P, 
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int warps_needed = (g->n_slots + 31) / 32;
     int grid = (warps_needed + 7) / 8;
-    const int cap = sms * 8;   // 8 CTAs of 256 threads per SM
+    int occ = 0;               // resident CTAs per SM: one full wave, the warps stride over the slots
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, edge_kernel<H>, 256, 0) != cudaSuccess || occ < 1)
+        return GNNSEG_ECUDA;
+    const int cap = sms * occ;
     if (grid > cap) grid = cap;
     edge_kernel<H><<<grid, 256, 0, st>>>(blob, P, g->src, g->dst, g->in_pos, g->out_pos, g->n_slots, e, e_in, e_out);
     return check_launch();
