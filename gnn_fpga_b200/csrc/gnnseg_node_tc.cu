@@ -391,8 +391,15 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
 #pragma unroll
                     for (int u = 0; u < UNR; ++u) {
                         const int s = base + u * ST + stid;
-                        if (s < ic) sPair[s] = make_int2(nb_i[u], __float_as_int(w_i[u]));
-                        if (s < oc) sPair[CAP + s] = make_int2(nb_o[u], __float_as_int(w_o[u]));
+                        if (s < ic) {
+                            sPair[s] = make_int2(nb_i[u], __float_as_int(w_i[u]));
+                            // pull the row the gather will want into the L2 one tile ahead
+                            if (nb_i[u] >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(Q_in + (size_t)nb_i[u] * 3 * H));
+                        }
+                        if (s < oc) {
+                            sPair[CAP + s] = make_int2(nb_o[u], __float_as_int(w_o[u]));
+                            if (nb_o[u] >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(Q_in + (size_t)nb_o[u] * 3 * H + H));
+                        }
                     }
                 }
             }
