@@ -59,16 +59,18 @@ def algorithmic_bytes(Nt, Et, F, h, n_iters):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).
+    Started before the warm-up (nvidia-smi takes a moment to come up); only the samples whose
+    timestamps fall inside [mark_start, mark_end] are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.t0, self.t1 = [], None, None, None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -79,26 +81,40 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        samples = []
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx = float(r[1])
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                samples.append((ts, float(r[1]), float(r[2]), r[4:8]))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+        inside = [x for x in samples if self.t0 is not None and self.t0 - 0.02 <= x[0] <= self.t1 + 0.02]
+        if not inside and samples and self.t0 is not None:      # region shorter than the sampling period
+            mid = 0.5 * (self.t0 + self.t1)
+            inside = [min(samples, key=lambda x: abs(x[0] - mid))]
+        reasons = set()
+        for x in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), x[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median([x[1] for x in inside])) if inside else None,
+                "sm_max_mhz": inside[0][2] if inside else None, "reasons": sorted(reasons), "samples": len(inside)}
 
 
 # -----------------------------------------------------------------------------------------
@@ -219,7 +235,7 @@ def cpu_baseline(workload, budget_s=15.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="acts64", choices=sorted(WORKLOADS))
@@ -264,10 +280,12 @@ def main():
 
     # ---- value: batch resident in HBM ----------------------------------------------------
     with torch.no_grad():
+        sampler = ClockSampler(local_rank) if rank == 0 else None
         for _ in range(args.warmup):
             model(batch)
         barrier()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.mark_start()
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         for i in range(args.steps):
@@ -276,6 +294,8 @@ def main():
             model(batch)
             ends[i].record()
         barrier()
+        if sampler:
+            sampler.mark_end()
         clocks = sampler.stop() if sampler else None
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(sum(step_ms))
@@ -300,7 +320,7 @@ def main():
         kt[name].append((a, b))
 
     st = _stream_ptr(dev)
-    reps = max(3, min(args.steps, 10))
+    reps = max(3, min(args.steps, 20))
     for rep in range(reps + 1):
         if rep == 1:
             kt = {"input": [], "edge": [], "node": []}      # drop the warm-up pass
