@@ -503,12 +503,12 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
 template <int H>
 struct TcInCfg {
     using N = TcCfg<H>;
-    static constexpr int NT = 128;                          // 4 warps: thread = node = TMEM lane
+    static constexpr int NT = 256;                          // 8 warps: two per TMEM lane quarter, each half of the columns
     static constexpr int O_WPH  = 0;
     static constexpr int O_WPL  = O_WPH + N::WP_BYTES;
     static constexpr int O_BIAS = O_WPL + N::WP_BYTES;      // Win [4][H], bin [H], bias of the projections [5H]
     static constexpr int O_OUT  = O_BIAS + (4 * H + H + 5 * H) * 4;
-    static constexpr int O_MBAR = O_OUT + 4 * N::OUT_BYTES;
+    static constexpr int O_MBAR = O_OUT + 8 * N::OUT_BYTES;
     static constexpr int SMEM_BYTES = O_MBAR + 16;
     static constexpr int C_A3H = 0, C_A3L = N::D4P, C_D3 = 2 * N::D4P, C_END = C_D3 + 5 * H;
     static constexpr int TMEM_COLS = C_END <= 64 ? 64 : C_END <= 128 ? 128 : C_END <= 256 ? 256 : 512;
@@ -548,19 +548,20 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t mb = smem_u32(mbar);
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const int q = warp & 3, hf = warp >> 2;                   // TMEM lane quarter, which half of the columns
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     constexpr uint32_t ID3 = idesc_tf32(TM, NP);
     const uint32_t sa = smem_u32(smem);
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int n = tile * TM + tid;
+        const int n = tile * TM + q * 32 + lane;
         float x[4] = {0.f, 0.f, 0.f, 0.f};
         if (n < n_nodes) {
             for (int f = 0; f < F; ++f) x[f] = __ldg(X + (size_t)n * F + f);
-            st4(X4 + (size_t)n * 4, make_float4(x[0], x[1], x[2], x[3]));
+            if (hf == 0) st4(X4 + (size_t)n * 4, make_float4(x[0], x[1], x[2], x[3]));
         }
-#pragma unroll
-        for (int c0 = 0; c0 < H; c0 += 16) {
+        {
+            const int c0 = hf * (H / 2);                           // this warp's 16 hidden columns
             float hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -574,7 +575,7 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
             tmem_st16(lane_base + C::C_A3H + c0, hi);
             tmem_st16(lane_base + C::C_A3L + c0, lo);
         }
-        {
+        if (hf == 0) {
             float xh[8], xl[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split3(x[i], xh[i], xl[i]);
@@ -602,7 +603,7 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
         mbar_wait(mb, phase); phase ^= 1;
         tc_fence_after();
         tc_store_projections<H>(lane_base, C::C_D3, sBP, reinterpret_cast<float*>(smem + C::O_OUT + warp * N::OUT_BYTES),
-                                tile * TM + warp * 32, n_nodes, lane, P_out, Q_out, true);
+                                tile * TM + q * 32, n_nodes, lane, P_out, Q_out, true, hf, 2);
         tc_fence_before();
         __syncthreads();       // A3 / D3 are rewritten by the next tile
     }
@@ -625,7 +626,7 @@ int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, flo
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
         return GNNSEG_ENODEVICE;
-    const int cap = 2 * sms;     // 256 TMEM columns and ~75 KB of shared memory per CTA: two CTAs per SM
+    const int cap = 2 * sms;     // 256 TMEM columns and ~95 KB of shared memory per CTA: two CTAs per SM
     const int grid = n_tiles < cap ? n_tiles : cap;
     input_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, P, Q);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
