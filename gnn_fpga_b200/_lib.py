@@ -40,6 +40,8 @@ SIGNATURES = {
     "gnnseg_dense_to_edges": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, C.c_void_p]),
     "gnnseg_csr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "gnnseg_build_csr": (C.c_int, [_i32p, _i32p, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnnseg_build_graph": (C.c_int, [_i32p, _i32p, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p,
+                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnnseg_forward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gnnseg_forward": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnnseg_input_step": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_void_p]),

@@ -10,6 +10,7 @@ int pack_weights(const GnnsegParams*, int, int, float*, cudaStream_t);
 int dense_to_edges(const float*, const float*, int, int, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
 size_t csr_workspace_bytes(int, int);
 int build_csr(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+int build_graph(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
 }  // namespace gnnseg
 
 namespace {
@@ -117,6 +118,16 @@ int gnnseg_build_csr(const int32_t* key, const int32_t* other, int n_slots, int 
     if (n_slots > 0 && (!key || !other || !eid || !nbr)) return GNNSEG_EINVAL;
     return gnnseg::build_csr(key, other, n_slots, n_nodes, ptr, eid, nbr, pos, ws, ws_bytes,
                              static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_build_graph(const int32_t* src, const int32_t* dst, int n_slots, int n_nodes,
+                       int32_t* in_ptr, int32_t* in_eid, int32_t* in_nbr, int32_t* in_pos,
+                       int32_t* out_ptr, int32_t* out_eid, int32_t* out_nbr, int32_t* out_pos,
+                       void* ws, size_t ws_bytes, void* stream) {
+    if (n_slots < 0 || n_nodes < 0 || !in_ptr || !out_ptr || !ws) return GNNSEG_EINVAL;
+    if (n_slots > 0 && (!src || !dst || !in_eid || !in_nbr || !out_eid || !out_nbr)) return GNNSEG_EINVAL;
+    return gnnseg::build_graph(src, dst, n_slots, n_nodes, in_ptr, in_eid, in_nbr, in_pos, out_ptr, out_eid,
+                               out_nbr, out_pos, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 size_t gnnseg_forward_workspace_bytes(int n_nodes, int n_slots, int F, int h) {

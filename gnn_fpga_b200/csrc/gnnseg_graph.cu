@@ -39,11 +39,35 @@ dense_to_edges_kernel(const float* __restrict__ Ri, const float* __restrict__ Ro
 }
 
 // ---- CSR build -----------------------------------------------------------------------
-__global__ void histogram_kernel(const int32_t* __restrict__ key, const int n_slots,
-                                 const int n_nodes, int32_t* __restrict__ count) {
+// Every kernel handles one or two directions at once (blockIdx.y picks the direction), so that
+// the destination-CSR and the source-CSR of a batch are built by the same eight launches.
+struct CsrDir {
+    const int32_t* key;      // [n_slots] row of each slot (dst for the in-CSR, src for the out-CSR), < 0 = absent
+    const int32_t* other;    // [n_slots] the other endpoint
+    int32_t* ptr;            // [n_nodes+1]
+    int32_t* eid;            // [n_slots]
+    int32_t* nbr;            // [n_slots]
+    int32_t* pos;            // [n_slots] or null
+    int32_t* count;          // workspace [n_nodes+1]
+    int32_t* cursor;         // workspace [n_nodes+1]
+    int32_t* block_sums;     // workspace [n_blocks+1]
+    int32_t* grand_total;    // workspace [1]
+};
+struct CsrPair { CsrDir d[2]; };
+
+__global__ void csr_init_kernel(const CsrPair p, const int n_slots, const int n_nodes) {
+    const CsrDir& d = p.d[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(n_slots, n_nodes + 1); i += gridDim.x * blockDim.x) {
+        if (i <= n_nodes) d.count[i] = 0;
+        if (d.pos && i < n_slots) d.pos[i] = -1;
+    }
+}
+
+__global__ void histogram_kernel(const CsrPair p, const int n_slots, const int n_nodes) {
+    const CsrDir& d = p.d[blockIdx.y];
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_slots; j += gridDim.x * blockDim.x) {
-        const int k = __ldg(key + j);
-        if (k >= 0 && k < n_nodes) atomicAdd(count + k, 1);
+        const int k = __ldg(d.key + j);
+        if (k >= 0 && k < n_nodes) atomicAdd(d.count + k, 1);
     }
 }
 
@@ -80,60 +104,60 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_local_kernel(const int32_t* __restrict__ count, const int n, int32_t* __restrict__ ptr,
-                  int32_t* __restrict__ block_sums) {
+scan_local_kernel(const CsrPair p, const int n) {
+    const CsrDir& d = p.d[blockIdx.y];
     const int base = blockIdx.x * SCAN_ITEMS + threadIdx.x * SCAN_PER_THREAD;
     int v[SCAN_PER_THREAD], sum = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_PER_THREAD; ++i) {
-        v[i] = (base + i < n) ? count[base + i] : 0;
+        v[i] = (base + i < n) ? d.count[base + i] : 0;
         sum += v[i];
     }
     int total;
     int off = block_exclusive_scan(sum, &total);
 #pragma unroll
     for (int i = 0; i < SCAN_PER_THREAD; ++i) {
-        if (base + i < n) ptr[base + i] = off;
+        if (base + i < n) d.ptr[base + i] = off;
         off += v[i];
     }
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+    if (threadIdx.x == 0) d.block_sums[blockIdx.x] = total;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_block_sums_kernel(int32_t* __restrict__ block_sums, const int n_blocks, int32_t* __restrict__ grand_total) {
+scan_block_sums_kernel(const CsrPair p, const int n_blocks) {
+    const CsrDir& d = p.d[blockIdx.y];
     int carry = 0;
     for (int base = 0; base < n_blocks; base += SCAN_THREADS) {
         const int i = base + threadIdx.x;
-        const int v = i < n_blocks ? block_sums[i] : 0;
+        const int v = i < n_blocks ? d.block_sums[i] : 0;
         int total;
         const int ex = block_exclusive_scan(v, &total);
-        if (i < n_blocks) block_sums[i] = carry + ex;
+        if (i < n_blocks) d.block_sums[i] = carry + ex;
         carry += total;
     }
-    if (threadIdx.x == 0) *grand_total = carry;
+    if (threadIdx.x == 0) *d.grand_total = carry;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_add_kernel(int32_t* __restrict__ ptr, const int n, const int32_t* __restrict__ block_sums,
-                const int32_t* __restrict__ grand_total, int32_t* __restrict__ cursor) {
+scan_add_kernel(const CsrPair p, const int n) {
+    const CsrDir& d = p.d[blockIdx.y];
     const int base = blockIdx.x * SCAN_ITEMS + threadIdx.x * SCAN_PER_THREAD;
-    const int off = block_sums[blockIdx.x];
+    const int off = d.block_sums[blockIdx.x];
 #pragma unroll
     for (int i = 0; i < SCAN_PER_THREAD; ++i)
         if (base + i < n) {
-            const int p = ptr[base + i] + off;
-            ptr[base + i] = p;
-            cursor[base + i] = p;
+            const int v = d.ptr[base + i] + off;
+            d.ptr[base + i] = v;
+            d.cursor[base + i] = v;
         }
-    if (blockIdx.x == 0 && threadIdx.x == 0) ptr[n] = *grand_total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.ptr[n] = *d.grand_total;
 }
 
-__global__ void csr_fill_kernel(const int32_t* __restrict__ key, const int n_slots,
-                                const int n_nodes, int32_t* __restrict__ cursor,
-                                int32_t* __restrict__ eid) {
+__global__ void csr_fill_kernel(const CsrPair p, const int n_slots, const int n_nodes) {
+    const CsrDir& d = p.d[blockIdx.y];
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_slots; j += gridDim.x * blockDim.x) {
-        const int k = __ldg(key + j);
-        if (k >= 0 && k < n_nodes) eid[atomicAdd(cursor + k, 1)] = j;
+        const int k = __ldg(d.key + j);
+        if (k >= 0 && k < n_nodes) d.eid[atomicAdd(d.cursor + k, 1)] = j;
     }
 }
 
@@ -152,11 +176,11 @@ __device__ inline void sift_down(int32_t* a, int start, int end) {
     }
 }
 
-__global__ void csr_sort_rows_kernel(const int32_t* __restrict__ ptr, const int n_nodes,
-                                     int32_t* __restrict__ eid) {
+__global__ void csr_sort_rows_kernel(const CsrPair p, const int n_nodes) {
+    const CsrDir& d = p.d[blockIdx.y];
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_nodes; n += gridDim.x * blockDim.x) {
-        const int beg = ptr[n], len = ptr[n + 1] - beg;
-        int32_t* a = eid + beg;
+        const int beg = d.ptr[n], len = d.ptr[n + 1] - beg;
+        int32_t* a = d.eid + beg;
         if (len <= 24) {
             for (int i = 1; i < len; ++i) {
                 const int32_t v = a[i];
@@ -174,14 +198,13 @@ __global__ void csr_sort_rows_kernel(const int32_t* __restrict__ ptr, const int 
     }
 }
 
-__global__ void csr_nbr_kernel(const int32_t* __restrict__ eid, const int32_t* __restrict__ ptr,
-                               const int n_nodes, const int32_t* __restrict__ other,
-                               int32_t* __restrict__ nbr, int32_t* __restrict__ pos) {
-    const int n_used = ptr[n_nodes];
+__global__ void csr_nbr_kernel(const CsrPair p, const int n_nodes) {
+    const CsrDir& d = p.d[blockIdx.y];
+    const int n_used = d.ptr[n_nodes];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_used; s += gridDim.x * blockDim.x) {
-        const int j = eid[s];
-        nbr[s] = __ldg(other + j);
-        if (pos) pos[j] = s;       // inverse map (pos was filled with -1)
+        const int j = d.eid[s];
+        d.nbr[s] = __ldg(d.other + j);
+        if (d.pos) d.pos[j] = s;       // inverse map (pos was filled with -1)
     }
 }
 
@@ -212,31 +235,57 @@ size_t csr_workspace_bytes(int n_nodes, int n_slots) {
     return (2 * ((size_t)n_nodes + 1) + n_blocks + 1 + 4) * sizeof(int32_t);
 }
 
+static void carve_dir(CsrDir& d, void* ws, int n_nodes) {
+    const int n_blocks = (n_nodes + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    d.count = static_cast<int32_t*>(ws);
+    d.cursor = d.count + (n_nodes + 1);
+    d.block_sums = d.cursor + (n_nodes + 1);
+    d.grand_total = d.block_sums + n_blocks + 1;
+}
+
+// n_dirs = 1 or 2 directions in the same launches
+static int build_csr_dirs(const CsrPair& p, int n_dirs, int n_slots, int n_nodes, cudaStream_t st) {
+    const int n_blocks = (n_nodes + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    const dim3 by(1, n_dirs);
+    auto g2 = [&](int gx) { return dim3(gx, n_dirs); };
+    csr_init_kernel<<<g2(grid_for(n_slots > n_nodes + 1 ? n_slots : n_nodes + 1, 256, 2048)), 256, 0, st>>>(p, n_slots, n_nodes);
+    if (n_slots > 0) histogram_kernel<<<g2(grid_for(n_slots, 256, 2048)), 256, 0, st>>>(p, n_slots, n_nodes);
+    if (n_blocks > 0) {
+        scan_local_kernel<<<g2(n_blocks), SCAN_THREADS, 0, st>>>(p, n_nodes);
+        scan_block_sums_kernel<<<by, SCAN_THREADS, 0, st>>>(p, n_blocks);
+        scan_add_kernel<<<g2(n_blocks), SCAN_THREADS, 0, st>>>(p, n_nodes);
+    } else {
+        for (int i = 0; i < n_dirs; ++i) fill_i32_kernel<<<1, 32, 0, st>>>(p.d[i].ptr, 0, 1);
+    }
+    if (n_slots > 0 && n_nodes > 0) {
+        csr_fill_kernel<<<g2(grid_for(n_slots, 256, 2048)), 256, 0, st>>>(p, n_slots, n_nodes);
+        csr_sort_rows_kernel<<<g2(grid_for(n_nodes, 128, 4096)), 128, 0, st>>>(p, n_nodes);
+        csr_nbr_kernel<<<g2(grid_for(n_slots, 256, 2048)), 256, 0, st>>>(p, n_nodes);
+    }
+    return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+}
+
 int build_csr(const int32_t* key, const int32_t* other, int n_slots, int n_nodes, int32_t* ptr,
               int32_t* eid, int32_t* nbr, int32_t* pos, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (ws_bytes < csr_workspace_bytes(n_nodes, n_slots)) return GNNSEG_EWORKSPACE;
-    int32_t* count = static_cast<int32_t*>(ws);
-    int32_t* cursor = count + (n_nodes + 1);
-    int32_t* block_sums = cursor + (n_nodes + 1);
-    const int n_blocks = (n_nodes + SCAN_ITEMS - 1) / SCAN_ITEMS;
-    int32_t* grand_total = block_sums + n_blocks + 1;
+    CsrPair p{};
+    p.d[0] = CsrDir{key, other, ptr, eid, nbr, pos, nullptr, nullptr, nullptr, nullptr};
+    carve_dir(p.d[0], ws, n_nodes);
+    return build_csr_dirs(p, 1, n_slots, n_nodes, st);
+}
 
-    fill_i32_kernel<<<grid_for(n_nodes + 1, 256, 4096), 256, 0, st>>>(count, 0, (size_t)n_nodes + 1);
-    if (pos && n_slots > 0) fill_i32_kernel<<<grid_for(n_slots, 256, 4096), 256, 0, st>>>(pos, -1, (size_t)n_slots);
-    if (n_slots > 0) histogram_kernel<<<grid_for(n_slots, 256, 4096), 256, 0, st>>>(key, n_slots, n_nodes, count);
-    if (n_blocks > 0) {
-        scan_local_kernel<<<n_blocks, SCAN_THREADS, 0, st>>>(count, n_nodes, ptr, block_sums);
-        scan_block_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(block_sums, n_blocks, grand_total);
-        scan_add_kernel<<<n_blocks, SCAN_THREADS, 0, st>>>(ptr, n_nodes, block_sums, grand_total, cursor);
-    } else {
-        fill_i32_kernel<<<1, 32, 0, st>>>(ptr, 0, 1);
-    }
-    if (n_slots > 0 && n_nodes > 0) {
-        csr_fill_kernel<<<grid_for(n_slots, 256, 4096), 256, 0, st>>>(key, n_slots, n_nodes, cursor, eid);
-        csr_sort_rows_kernel<<<grid_for(n_nodes, 128, 8192), 128, 0, st>>>(ptr, n_nodes, eid);
-        csr_nbr_kernel<<<grid_for(n_slots, 256, 4096), 256, 0, st>>>(eid, ptr, n_nodes, other, nbr, pos);
-    }
-    return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+// both CSRs of a graph: destination-CSR (key = dst) into in_*, source-CSR (key = src) into out_*
+int build_graph(const int32_t* src, const int32_t* dst, int n_slots, int n_nodes, int32_t* in_ptr,
+                int32_t* in_eid, int32_t* in_nbr, int32_t* in_pos, int32_t* out_ptr, int32_t* out_eid,
+                int32_t* out_nbr, int32_t* out_pos, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const size_t one = csr_workspace_bytes(n_nodes, n_slots);
+    if (ws_bytes < 2 * one) return GNNSEG_EWORKSPACE;
+    CsrPair p{};
+    p.d[0] = CsrDir{dst, src, in_ptr, in_eid, in_nbr, in_pos, nullptr, nullptr, nullptr, nullptr};
+    p.d[1] = CsrDir{src, dst, out_ptr, out_eid, out_nbr, out_pos, nullptr, nullptr, nullptr, nullptr};
+    carve_dir(p.d[0], ws, n_nodes);
+    carve_dir(p.d[1], static_cast<char*>(ws) + one, n_nodes);
+    return build_csr_dirs(p, 2, n_slots, n_nodes, st);
 }
 
 }  // namespace gnnseg

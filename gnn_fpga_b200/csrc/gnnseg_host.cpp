@@ -30,7 +30,9 @@ extern "C" int gnnseg_pack_sparse_batch_host(
     if (node_off[B] > 0x7fffffffLL || (int64_t)B * e_max > 0x7fffffffLL) return GNNSEG_EINVAL;
 
     std::atomic<int> bad(0);
-    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    // default: all cores but two (the caller's launching thread and the CUDA driver need them;
+    // an oversubscribed team doubles the per-batch time)
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency() - 2;
     nt = std::max(1, std::min(nt, std::min(B, 64)));
     // OpenMP keeps its worker team alive between calls (creating 16 std::threads per batch
     // cost a quarter of the packing time)

@@ -119,16 +119,13 @@ class DeviceGraphBatch:
         self.in_eid, self.in_nbr = torch.empty(m, **i32), torch.empty(m, **i32)
         self.out_eid, self.out_nbr = torch.empty(m, **i32), torch.empty(m, **i32)
         self.in_pos, self.out_pos = torch.empty(m, **i32), torch.empty(m, **i32)
-        ws_bytes = L.gnnseg_csr_workspace_bytes(n, m)
+        ws_bytes = 2 * L.gnnseg_csr_workspace_bytes(n, m)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            st = _stream_ptr(dev)
-            _lib.check(L.gnnseg_build_csr(_ptr(self.dst), _ptr(self.src), m, n, _ptr(self.in_ptr),
-                                          _ptr(self.in_eid), _ptr(self.in_nbr), _ptr(self.in_pos), _ptr(ws), ws_bytes, st),
-                       "gnnseg_build_csr(dst)")
-            _lib.check(L.gnnseg_build_csr(_ptr(self.src), _ptr(self.dst), m, n, _ptr(self.out_ptr),
-                                          _ptr(self.out_eid), _ptr(self.out_nbr), _ptr(self.out_pos), _ptr(ws), ws_bytes, st),
-                       "gnnseg_build_csr(src)")
+            _lib.check(L.gnnseg_build_graph(_ptr(self.src), _ptr(self.dst), m, n,
+                                            _ptr(self.in_ptr), _ptr(self.in_eid), _ptr(self.in_nbr), _ptr(self.in_pos),
+                                            _ptr(self.out_ptr), _ptr(self.out_eid), _ptr(self.out_nbr), _ptr(self.out_pos),
+                                            _ptr(ws), ws_bytes, _stream_ptr(dev)), "gnnseg_build_graph")
         self._csr_ws = ws   # keep alive until the stream has consumed it
         self.struct = _lib.GnnsegGraph(
             n, m, self.src.data_ptr(), self.dst.data_ptr(),

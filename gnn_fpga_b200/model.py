@@ -240,9 +240,14 @@ class SegmentClassifier(nn.Module):
         slots = [{"pinned": None, "out": None, "done": None, "view": None} for _ in range(n_slots)]
         pending = deque()
         was_graph, self.use_cuda_graph = self.use_cuda_graph, False    # one-shot batches: plain launches
+        import os
+        # leave two cores to the launching thread and the driver: an oversubscribed OpenMP team
+        # (its threads spin between batches) makes the per-batch time jump by 2x
+        pack_threads = max(2, (os.cpu_count() or 4) - 2)
+
         def pack(graphs, slot):
             slot["pinned"] = self._grow_pinned(slot["pinned"], graphs)   # waits for the slot's last H2D
-            return pack_sparse_batch_host(list(graphs), pinned=slot["pinned"])
+            return pack_sparse_batch_host(list(graphs), pinned=slot["pinned"], n_threads=pack_threads)
 
         pool = ThreadPoolExecutor(max_workers=LOOK)
         compute = torch.cuda.current_stream(dev)

@@ -125,6 +125,16 @@ int    gnnseg_build_csr(const int32_t* key, const int32_t* other, int n_slots, i
                         int32_t* ptr, int32_t* eid, int32_t* nbr, int32_t* pos,
                         void* ws, size_t ws_bytes, void* stream);
 
+/*
+ * Both CSRs of a batch in one go (the same launches build the destination-CSR, key = dst, and
+ * the source-CSR, key = src).  Workspace: 2 * gnnseg_csr_workspace_bytes(n_nodes, n_slots).
+ * in_pos / out_pos may be NULL.
+ */
+int    gnnseg_build_graph(const int32_t* src, const int32_t* dst, int n_slots, int n_nodes,
+                          int32_t* in_ptr, int32_t* in_eid, int32_t* in_nbr, int32_t* in_pos,
+                          int32_t* out_ptr, int32_t* out_eid, int32_t* out_nbr, int32_t* out_pos,
+                          void* ws, size_t ws_bytes, void* stream);
+
 /* ---- forward: replaces SegmentClassifier.forward, gnn/model.py:140-156 ---------------- */
 
 size_t gnnseg_forward_workspace_bytes(int n_nodes, int n_slots, int F, int h);

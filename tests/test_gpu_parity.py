@@ -397,3 +397,23 @@ def test_training_step_matches_reference_estimator(cuda_device):
     model.train()
     b = model(inputs).detach()
     assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= TOL
+
+
+def test_single_direction_build_csr_entry_point(cuda_device):
+    """gnnseg_build_csr (one key array) gives the same CSR as the paired gnnseg_build_graph."""
+    from gnn_fpga_b200 import _lib, DeviceGraphBatch, data
+    from gnn_fpga_b200.graph import _ptr, _stream_ptr
+    L = _lib.lib()
+    batch = DeviceGraphBatch.from_sparse_graphs([data.acts_like_graph(30, seed=1), data.acts_like_graph(22, seed=2)], cuda_device)
+    n, m = batch.n_nodes, batch.n_slots
+    i32 = dict(dtype=torch.int32, device=cuda_device)
+    ptr, eid, nbr, pos = torch.empty(n + 1, **i32), torch.empty(m, **i32), torch.empty(m, **i32), torch.empty(m, **i32)
+    wsb = L.gnnseg_csr_workspace_bytes(n, m)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=cuda_device)
+    assert L.gnnseg_build_csr(_ptr(batch.dst), _ptr(batch.src), m, n, _ptr(ptr), _ptr(eid), _ptr(nbr), _ptr(pos),
+                              _ptr(ws), wsb, _stream_ptr(cuda_device)) == 0
+    k = int(ptr[-1])
+    assert torch.equal(ptr, batch.in_ptr) and torch.equal(eid[:k], batch.in_eid[:k])
+    assert torch.equal(nbr[:k], batch.in_nbr[:k]) and torch.equal(pos, batch.in_pos)
+    assert L.gnnseg_build_csr(_ptr(batch.dst), _ptr(batch.src), m, n, _ptr(ptr), _ptr(eid), _ptr(nbr), None,
+                              _ptr(ws), wsb // 2, _stream_ptr(cuda_device)) == -3      # workspace too small
