@@ -210,7 +210,12 @@ class DeviceGraphBatch:
 def pack_sparse_batch_host(graphs, pinned=None, n_threads=0):
     """Run gnnseg_pack_sparse_batch_host over a list of SparseGraph tuples.  Returns pinned
     host tensors X (n_nodes,F) f32, src/dst (B*e_max) i32.  `pinned` may pass a dict of
-    pre-allocated (larger) pinned buffers to reuse."""
+    pre-allocated (larger) pinned buffers to reuse.  n_threads <= 0: this process's share of
+    the host cores (cores / LOCAL_WORLD_SIZE) minus two."""
+    if n_threads <= 0:
+        import os
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        n_threads = max(1, (os.cpu_count() or 4) // local_world - 2)
     L = _lib.lib()
     B = len(graphs)
     if B == 0:

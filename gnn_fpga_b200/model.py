@@ -243,7 +243,8 @@ class SegmentClassifier(nn.Module):
         import os
         # leave two cores to the launching thread and the driver: an oversubscribed OpenMP team
         # (its threads spin between batches) makes the per-batch time jump by 2x
-        pack_threads = max(2, (os.cpu_count() or 4) - 2)
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))     # ranks sharing this host (torchrun)
+        pack_threads = max(1, (os.cpu_count() or 4) // local_world - 2)
 
         def pack(graphs, slot):
             slot["pinned"] = self._grow_pinned(slot["pinned"], graphs)   # waits for the slot's last H2D
