@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgnnseg_b200.so")
 
 OK = 0
+ABI_VERSION = 2
 ERRORS = {-1: "EINVAL", -2: "EUNSUPPORTED", -3: "EWORKSPACE", -4: "ECUDA", -5: "ENODEVICE"}
 BAD_VALUE = 1
 BAD_HYPEREDGE = 2
@@ -22,6 +23,11 @@ class GnnsegParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "w_in", "b_in", "w_e1", "b_e1", "w_e2", "b_e2", "w_n1", "b_n1", "w_n2", "b_n2",
         "m_e1", "m_e2", "m_n1", "m_n2")]
+
+
+class GnnsegGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "w_in", "b_in", "w_e1", "b_e1", "w_e2", "b_e2", "w_n1", "b_n1", "w_n2", "b_n2")]
 
 
 class GnnsegGraph(C.Structure):
@@ -47,6 +53,14 @@ SIGNATURES = {
     "gnnseg_input_step": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_void_p]),
     "gnnseg_edge_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, _f32p, _f32p, _f32p, C.c_void_p]),
     "gnnseg_node_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, _f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_void_p]),
+    "gnnseg_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gnnseg_forward_train": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnnseg_backward": (C.c_int, [_f32p, C.POINTER(GnnsegParams), C.POINTER(GnnsegGraph), C.c_int, C.c_int, C.c_int, _f32p,
+                                 C.POINTER(GnnsegGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnnseg_bce_loss": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_void_p, C.c_void_p]),
+    "gnnseg_l1_penalty": (C.c_int, [C.POINTER(GnnsegParams), C.c_int, C.c_int, C.c_float, _f32p, C.POINTER(GnnsegGrads), C.c_void_p]),
+    "gnnseg_adam_step": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_void_p]),
     "gnnseg_pack_sparse_batch_host": (C.c_int, [
         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -72,7 +86,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.gnnseg_abi_version() != 1:
+        if handle.gnnseg_abi_version() != ABI_VERSION:
             raise GnnsegError("ABI version mismatch in %s" % LIB_PATH)
         _lib = handle
     return _lib

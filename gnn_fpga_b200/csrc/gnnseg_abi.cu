@@ -3,14 +3,32 @@
 #include "gnnseg_common.cuh"
 
 namespace gnnseg {
-int input_step(const float*, const float*, int, int, int, float*, float*, float*, cudaStream_t);
+int input_step(const float*, const float*, int, int, int, float*, float*, float*, float*, cudaStream_t);
 int edge_step(const float*, const GnnsegGraph*, const float*, int, float*, float*, float*, cudaStream_t);
-int node_step(const float*, const GnnsegGraph*, const float*, const float*, const float*, const float*, int, float*, float*, int, cudaStream_t);
+int node_step(const float*, const GnnsegGraph*, const float*, const float*, const float*, const float*, int, float*, float*, int, float*, float*, cudaStream_t);
 int pack_weights(const GnnsegParams*, int, int, float*, cudaStream_t);
 int dense_to_edges(const float*, const float*, int, int, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
 size_t csr_workspace_bytes(int, int);
 int build_csr(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
 int build_graph(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+// gnnseg_backward.cu
+struct GradOut {
+    float* w_in; float* b_in; float* w_e1; float* b_e1; float* w_e2; float* b_e2;
+    float* w_n1; float* b_n1; float* w_n2; float* b_n2;
+    const float* m_e1; const float* m_e2; const float* m_n1; const float* m_n2;
+};
+struct TrainState {
+    const float* x4;
+    const float* const* Hs; const float* const* h1s; const float* const* Ps; const float* const* Qs;
+    const float* const* e_in; const float* const* e_out;
+    float* dg; float* dproj; float* ds_in; float* ds_out; float* partE; float* partN;
+};
+size_t edge_part_floats(int h);
+size_t node_part_floats(int h);
+int backward(const float*, const GnnsegGraph*, int, int, int, const float*, const TrainState&, const GradOut&, cudaStream_t);
+int bce_loss(const float*, const float*, const float*, int, float*, float*, float*, cudaStream_t);
+int l1_penalty(const GnnsegParams*, int, int, float, float*, const GnnsegGrads*, cudaStream_t);
+int adam_step(float*, const float*, float*, float*, int, int, float, float, float, float, float, cudaStream_t);
 }  // namespace gnnseg
 
 namespace {
@@ -41,6 +59,50 @@ FwdWorkspace carve(void* ws, int n_nodes, int n_slots, int h) {
     w.e_in = reinterpret_cast<float*>(base + x_b + p_b + 2 * q_b);
     w.e_out = reinterpret_cast<float*>(base + x_b + p_b + 2 * q_b + e_b);
     w.bytes = x_b + p_b + 2 * q_b + 2 * e_b;
+    return w;
+}
+
+constexpr int MAX_ITERS = 64;
+
+// Training workspace: everything the forward leaves behind for the backward pass, then the
+// backward scratch.  X4 | H[0..T] | h1[0..T-1] | P[0..T] | Q[0..max(T,1)-1] | e_in[T] | e_out[T] |
+// dg | dproj | ds_in | ds_out | partE | partN, each 256-byte aligned.
+struct TrainWorkspace {
+    float* x4;
+    float* H[MAX_ITERS + 1];
+    float* h1[MAX_ITERS];
+    float* P[MAX_ITERS + 1];
+    float* Q[MAX_ITERS];
+    float* e_in[MAX_ITERS];
+    float* e_out[MAX_ITERS];
+    float* dg; float* dproj; float* ds_in; float* ds_out; float* partE; float* partN;
+    size_t bytes;
+};
+
+TrainWorkspace carve_train(void* ws, int n_nodes, int n_slots, int h, int T) {
+    TrainWorkspace w;
+    char* base = static_cast<char*>(ws);
+    size_t off = 0;
+    auto take = [&](size_t floats) {
+        float* p = reinterpret_cast<float*>(base + off);
+        off += align_up(floats * 4, 256);
+        return p;
+    };
+    const size_t n = (size_t)n_nodes, m = (size_t)n_slots;
+    w.x4 = take(n * 4);
+    for (int t = 0; t <= T; ++t) w.H[t] = take(n * h);
+    for (int t = 0; t < T; ++t) w.h1[t] = take(n * h);
+    for (int t = 0; t <= T; ++t) w.P[t] = take(n * 2 * h);
+    for (int t = 0; t < (T > 0 ? T : 1); ++t) w.Q[t] = take(n * 3 * h);
+    for (int t = 0; t < T; ++t) w.e_in[t] = take(m);
+    for (int t = 0; t < T; ++t) w.e_out[t] = take(m);
+    w.dg = take(n * h);
+    w.dproj = take(n * 5 * h);
+    w.ds_in = take(m);
+    w.ds_out = take(m);
+    w.partE = take(gnnseg::edge_part_floats(h));
+    w.partN = take(gnnseg::node_part_floats(h));
+    w.bytes = off;
     return w;
 }
 
@@ -139,7 +201,7 @@ int gnnseg_input_step(const float* blob, const float* X, int n_nodes, int F, int
                       float* P, float* Q, void* stream) {
     if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
     if (!blob || n_nodes < 0 || (n_nodes > 0 && (!X || !X4 || !P || !Q))) return GNNSEG_EINVAL;
-    return gnnseg::input_step(blob, X, n_nodes, F, h, X4, P, Q, static_cast<cudaStream_t>(stream));
+    return gnnseg::input_step(blob, X, n_nodes, F, h, X4, P, Q, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int gnnseg_edge_step(const float* blob, const GnnsegGraph* g, const float* P, int h, float* e,
@@ -157,7 +219,7 @@ int gnnseg_node_step(const float* blob, const GnnsegGraph* g, const float* X4, c
     if (!blob || !csr_ok(g)) return GNNSEG_EINVAL;
     if (g->n_nodes > 0 && (!X4 || !Q_in || !P_out)) return GNNSEG_EINVAL;
     if (g->n_slots > 0 && (!e_in || !e_out)) return GNNSEG_EINVAL;
-    return gnnseg::node_step(blob, g, X4, Q_in, e_in, e_out, h, P_out, Q_out, Q_out != nullptr,
+    return gnnseg::node_step(blob, g, X4, Q_in, e_in, e_out, h, P_out, Q_out, Q_out != nullptr, nullptr, nullptr,
                              static_cast<cudaStream_t>(stream));
 }
 
@@ -174,18 +236,93 @@ int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int 
     if (ws_bytes < w.bytes + (al - raw)) return GNNSEG_EWORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    int rc = gnnseg::input_step(blob, X, g->n_nodes, F, h, w.x4, w.p, w.q[0], st);
+    int rc = gnnseg::input_step(blob, X, g->n_nodes, F, h, w.x4, w.p, w.q[0], nullptr, st);
     int cur = 0;
     for (int it = 0; it < n_iters && rc == GNNSEG_OK; ++it) {
         // intermediate scores are only consumed by the node step: CSR order only
         rc = gnnseg::edge_step(blob, g, w.p, h, nullptr, w.e_in, w.e_out, st);
         // the last node step feeds only the final edge step: its Q' is never read
         if (rc == GNNSEG_OK)
-            rc = gnnseg::node_step(blob, g, w.x4, w.q[cur], w.e_in, w.e_out, h, w.p, w.q[cur ^ 1], it + 1 < n_iters, st);
+            rc = gnnseg::node_step(blob, g, w.x4, w.q[cur], w.e_in, w.e_out, h, w.p, w.q[cur ^ 1], it + 1 < n_iters, nullptr, nullptr, st);
         cur ^= 1;
     }
     if (rc == GNNSEG_OK) rc = gnnseg::edge_step(blob, g, w.p, h, scores, nullptr, nullptr, st);
     return rc;
+}
+
+size_t gnnseg_train_workspace_bytes(int n_nodes, int n_slots, int F, int h, int n_iters) {
+    if (!gnnseg_supported(F, h) || n_nodes < 0 || n_slots < 0 || n_iters < 0 || n_iters > MAX_ITERS) return 0;
+    return carve_train(nullptr, n_nodes, n_slots, h, n_iters).bytes + 256;
+}
+
+int gnnseg_forward_train(const float* blob, const GnnsegGraph* g, const float* X, int F, int h, int n_iters,
+                         float* scores, void* ws, size_t ws_bytes, void* stream) {
+    if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || !csr_ok(g) || n_iters < 0 || n_iters > MAX_ITERS || !ws) return GNNSEG_EINVAL;
+    if (g->n_nodes > 0 && !X) return GNNSEG_EINVAL;
+    if (g->n_slots > 0 && !scores) return GNNSEG_EINVAL;
+    const uintptr_t raw = reinterpret_cast<uintptr_t>(ws);
+    const uintptr_t al = (raw + 255) & ~uintptr_t(255);
+    const TrainWorkspace w = carve_train(reinterpret_cast<void*>(al), g->n_nodes, g->n_slots, h, n_iters);
+    if (ws_bytes < w.bytes + (al - raw)) return GNNSEG_EWORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = gnnseg::input_step(blob, X, g->n_nodes, F, h, w.x4, w.P[0], w.Q[0], w.H[0], st);
+    for (int t = 0; t < n_iters && rc == GNNSEG_OK; ++t) {
+        rc = gnnseg::edge_step(blob, g, w.P[t], h, nullptr, w.e_in[t], w.e_out[t], st);
+        const bool more = t + 1 < n_iters;
+        if (rc == GNNSEG_OK)
+            rc = gnnseg::node_step(blob, g, w.x4, w.Q[t], w.e_in[t], w.e_out[t], h, w.P[t + 1],
+                                   more ? w.Q[t + 1] : nullptr, more, w.h1[t], w.H[t + 1], st);
+    }
+    if (rc == GNNSEG_OK) rc = gnnseg::edge_step(blob, g, w.P[n_iters], h, scores, nullptr, nullptr, st);
+    return rc;
+}
+
+int gnnseg_backward(const float* blob, const GnnsegParams* masks, const GnnsegGraph* g, int F, int h, int n_iters,
+                    const float* dscores, const GnnsegGrads* grads, void* ws, size_t ws_bytes, void* stream) {
+    if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || !csr_ok(g) || n_iters < 0 || n_iters > MAX_ITERS || !ws || !grads) return GNNSEG_EINVAL;
+    if (g->n_slots > 0 && !dscores) return GNNSEG_EINVAL;
+    if (!grads->w_in || !grads->b_in || !grads->w_e1 || !grads->b_e1 || !grads->w_e2 || !grads->b_e2 ||
+        !grads->w_n1 || !grads->b_n1 || !grads->w_n2 || !grads->b_n2)
+        return GNNSEG_EINVAL;
+    const uintptr_t raw = reinterpret_cast<uintptr_t>(ws);
+    const uintptr_t al = (raw + 255) & ~uintptr_t(255);
+    const TrainWorkspace w = carve_train(reinterpret_cast<void*>(al), g->n_nodes, g->n_slots, h, n_iters);
+    if (ws_bytes < w.bytes + (al - raw)) return GNNSEG_EWORKSPACE;
+    gnnseg::TrainState s;
+    s.x4 = w.x4;
+    s.Hs = w.H; s.h1s = w.h1; s.Ps = w.P; s.Qs = w.Q; s.e_in = w.e_in; s.e_out = w.e_out;
+    s.dg = w.dg; s.dproj = w.dproj; s.ds_in = w.ds_in; s.ds_out = w.ds_out; s.partE = w.partE; s.partN = w.partN;
+    gnnseg::GradOut go;
+    go.w_in = grads->w_in; go.b_in = grads->b_in; go.w_e1 = grads->w_e1; go.b_e1 = grads->b_e1;
+    go.w_e2 = grads->w_e2; go.b_e2 = grads->b_e2; go.w_n1 = grads->w_n1; go.b_n1 = grads->b_n1;
+    go.w_n2 = grads->w_n2; go.b_n2 = grads->b_n2;
+    go.m_e1 = masks ? masks->m_e1 : nullptr; go.m_e2 = masks ? masks->m_e2 : nullptr;
+    go.m_n1 = masks ? masks->m_n1 : nullptr; go.m_n2 = masks ? masks->m_n2 : nullptr;
+    return gnnseg::backward(blob, g, F, h, n_iters, dscores, s, go, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_bce_loss(const float* scores, const float* targets, const float* weights, int n, float* loss,
+                    float* dscores, void* ws, void* stream) {
+    if (n < 0 || !loss || !ws || (n > 0 && (!scores || !targets))) return GNNSEG_EINVAL;
+    return gnnseg::bce_loss(scores, targets, weights, n, loss, dscores, static_cast<float*>(ws),
+                            static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_l1_penalty(const GnnsegParams* params, int F, int h, float l1, float* loss, const GnnsegGrads* grads,
+                      void* stream) {
+    if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
+    if (!params || !params->w_e1 || !params->w_e2 || !params->w_n1 || !params->w_n2) return GNNSEG_EINVAL;
+    if (grads && (!grads->w_e1 || !grads->w_e2 || !grads->w_n1 || !grads->w_n2)) return GNNSEG_EINVAL;
+    return gnnseg::l1_penalty(params, F, h, l1, loss, grads, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int n, int step,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+    if (n < 0 || step < 1 || (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq))) return GNNSEG_EINVAL;
+    return gnnseg::adam_step(param, grad, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay,
+                             static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

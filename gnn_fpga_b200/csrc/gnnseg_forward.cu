@@ -303,7 +303,7 @@ template <int H>
 __global__ void __launch_bounds__(InputCfg<H>::NT)
 input_kernel(const float* __restrict__ blob, const float* __restrict__ X, const int F,
              const int n_nodes, const int n_tiles, float* __restrict__ X4,
-             float* __restrict__ P_out, float* __restrict__ Q_out) {
+             float* __restrict__ P_out, float* __restrict__ Q_out, float* __restrict__ H_save) {
     using C = InputCfg<H>;
     using B = Blob<H>;
     constexpr int TN = C::TN, NT = C::NT, D4 = C::D4, SD = C::SD;
@@ -336,6 +336,7 @@ input_kernel(const float* __restrict__ blob, const float* __restrict__ X, const 
                 fma4(v, x.z, lds4(sWin + 2 * H + 4 * c));
                 fma4(v, x.w, lds4(sWin + 3 * H + 4 * c));
                 v.x = tanh_fast(v.x); v.y = tanh_fast(v.y); v.z = tanh_fast(v.z); v.w = tanh_fast(v.w);
+                if (H_save && node0 + ln < n_nodes) st4(H_save + (size_t)(node0 + ln) * H + 4 * c, v);   // training: H0
             } else {
                 v = x;
                 if (node0 + ln < n_nodes) st4(X4 + (size_t)(node0 + ln) * 4, x);
@@ -468,7 +469,8 @@ template <int H>
 __global__ void __launch_bounds__(NodeCfg<H>::NT, NodeCfg<H>::MINB)
 node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __restrict__ X4,
             const float* __restrict__ Q_in, const float* __restrict__ e_in, const float* __restrict__ e_out, const int n_tiles,
-            float* __restrict__ P_out, float* __restrict__ Q_out, const int write_q) {
+            float* __restrict__ P_out, float* __restrict__ Q_out, const int write_q,
+            float* __restrict__ h1_save, float* __restrict__ H_save) {
     using C = NodeCfg<H>;
     using B = Blob<H>;
     constexpr int TN = C::TN, NT = C::NT, CT = C::CT, PT = C::PT, NBUF = C::NBUF;
@@ -551,6 +553,7 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __
                         csr_row_sum<false>(nullptr, g.out_nbr, e_out, Q_in + H + 4 * c, 3 * H, o0, o1, acc);
                     }
                     acc.x = tanh_fast(acc.x); acc.y = tanh_fast(acc.y); acc.z = tanh_fast(acc.z); acc.w = tanh_fast(acc.w);
+                    if (h1_save) st4(h1_save + (size_t)n * H + 4 * c, acc);       // training: kept for the backward pass
                 }
                 st4(sHb + ln * SH + 4 * c, acc);
             }
@@ -572,14 +575,17 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __
             // ---- layer 2: H' = tanh(W4 . h1 + b4) ---------------------------------------
             if constexpr (MMA) {
                 tile_gemm_mma<H / 8, H>(sHb, SH, sW4, SH, [&](int ln, int o, float v0, float v1) {
-                    *reinterpret_cast<float2*>(sHX + ln * SD + o) =
-                        make_float2(tanh_fast(v0 + sB4[o]), tanh_fast(v1 + sB4[o + 1]));
+                    const float2 hv = make_float2(tanh_fast(v0 + sB4[o]), tanh_fast(v1 + sB4[o + 1]));
+                    *reinterpret_cast<float2*>(sHX + ln * SD + o) = hv;
+                    if (H_save && node0 + ln < n_nodes) *reinterpret_cast<float2*>(H_save + (size_t)(node0 + ln) * H + o) = hv;
                 });
             } else {
                 tile_gemm<H, H, TN, CT, C::RN, 4>(sHb, SH, sW4, [&](int ln, int o, const float* acc) {
                     const float4 b = lds4(sB4 + o);
-                    st4(sHX + ln * SD + o, make_float4(tanh_fast(acc[0] + b.x), tanh_fast(acc[1] + b.y),
-                                                       tanh_fast(acc[2] + b.z), tanh_fast(acc[3] + b.w)));
+                    const float4 hv = make_float4(tanh_fast(acc[0] + b.x), tanh_fast(acc[1] + b.y),
+                                                  tanh_fast(acc[2] + b.z), tanh_fast(acc[3] + b.w));
+                    st4(sHX + ln * SD + o, hv);
+                    if (H_save && node0 + ln < n_nodes) st4(H_save + (size_t)(node0 + ln) * H + o, hv);
                 });
             }
             bar_sync(BAR_CONS, CT);
@@ -637,22 +643,22 @@ static inline int check_launch() {
 }
 
 int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
-                      cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
+                      float* H_save, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
 
 template <int H>
 static int launch_input(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
-                        cudaStream_t st) {
+                        float* H_save, cudaStream_t st) {
     using C = InputCfg<H>;
     if (n_nodes == 0) return GNNSEG_OK;
     if (H == 32) {
         const char* impl = getenv("GNNSEG_NODE_IMPL");   // "mma": generic path (for A/B runs)
-        if (!impl || impl[0] != 'm') return launch_input_tc32(blob, X, n_nodes, F, X4, P, Q, st);
+        if (!impl || impl[0] != 'm') return launch_input_tc32(blob, X, n_nodes, F, X4, P, Q, H_save, st);
     }
     const int n_tiles = (n_nodes + C::TN - 1) / C::TN;
     int grid = 0;
     const int rc = persistent_grid(input_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);
     if (rc) return rc;
-    input_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, P, Q);
+    input_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, P, Q, H_save);
     return check_launch();
 }
 
@@ -674,22 +680,24 @@ static int launch_edge(const float* blob, const GnnsegGraph* g, const float* P, 
 }
 
 int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e_in,
-                     const float* e_out, float* P_out, float* Q_out, int write_q, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
+                     const float* e_out, float* P_out, float* Q_out, int write_q, float* h1_save, float* H_save,
+                     cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
 
 template <int H>
 static int launch_node(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e_in,
-                       const float* e_out, float* P_out, float* Q_out, int write_q, cudaStream_t st) {
+                       const float* e_out, float* P_out, float* Q_out, int write_q, float* h1_save, float* H_save,
+                       cudaStream_t st) {
     using C = NodeCfg<H>;
     if (g->n_nodes == 0) return GNNSEG_OK;
     if (H == 32) {
         const char* impl = getenv("GNNSEG_NODE_IMPL");   // "mma": generic mma.sync path (for A/B runs)
-        if (!impl || impl[0] != 'm') return launch_node_tc32(blob, g, X4, Q_in, e_in, e_out, P_out, Q_out, write_q, st);
+        if (!impl || impl[0] != 'm') return launch_node_tc32(blob, g, X4, Q_in, e_in, e_out, P_out, Q_out, write_q, h1_save, H_save, st);
     }
     const int n_tiles = (g->n_nodes + C::TN - 1) / C::TN;
     int grid = 0;
     const int rc = persistent_grid(node_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);
     if (rc) return rc;
-    node_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out, Q_out, write_q);
+    node_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out, Q_out, write_q, h1_save, H_save);
     return check_launch();
 }
 
@@ -704,16 +712,17 @@ static int launch_node(const float* blob, const GnnsegGraph* g, const float* X4,
     }
 
 int input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* X4, float* P, float* Q,
-               cudaStream_t st) {
-    GNNSEG_DISPATCH_H(h, launch_input<HH>(blob, X, n_nodes, F, X4, P, Q, st));
+               float* H_save, cudaStream_t st) {
+    GNNSEG_DISPATCH_H(h, launch_input<HH>(blob, X, n_nodes, F, X4, P, Q, H_save, st));
 }
 int edge_step(const float* blob, const GnnsegGraph* g, const float* P, int h, float* e, float* e_in, float* e_out,
               cudaStream_t st) {
     GNNSEG_DISPATCH_H(h, launch_edge<HH>(blob, g, P, e, e_in, e_out, st));
 }
 int node_step(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e_in,
-              const float* e_out, int h, float* P_out, float* Q_out, int write_q, cudaStream_t st) {
-    GNNSEG_DISPATCH_H(h, launch_node<HH>(blob, g, X4, Q_in, e_in, e_out, P_out, Q_out, write_q, st));
+              const float* e_out, int h, float* P_out, float* Q_out, int write_q, float* h1_save, float* H_save,
+              cudaStream_t st) {
+    GNNSEG_DISPATCH_H(h, launch_node<HH>(blob, g, X4, Q_in, e_in, e_out, P_out, Q_out, write_q, h1_save, H_save, st));
 }
 int pack_weights(const GnnsegParams* p, int F, int h, float* blob, cudaStream_t st) {
     const int total = blob_total(h);

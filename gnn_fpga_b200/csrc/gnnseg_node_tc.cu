@@ -258,7 +258,8 @@ template <int H>
 __global__ void __launch_bounds__(TcCfg<H>::NT, 1)
 node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float* __restrict__ X4,
                const float* __restrict__ Q_in, const float* __restrict__ e_in, const float* __restrict__ e_out,
-               const int n_tiles, float* __restrict__ P_out, float* __restrict__ Q_out, const int write_q) {
+               const int n_tiles, float* __restrict__ P_out, float* __restrict__ Q_out, const int write_q,
+               float* __restrict__ h1_save, float* __restrict__ H_save) {
     using C = TcCfg<H>;
     using B = Blob<H>;
     constexpr int TM = C::TM, NT = C::NT, ET = C::ET, ST = C::ST, GT = C::GT, D4 = C::D4, NP = C::NP;
@@ -330,6 +331,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
                         tc_row_sum<false>(nullptr, g.out_nbr, e_out, Q_in + H + 4 * c, 3 * H, o0, o1, keep, acc);
                     }
                     acc.x = tanh_fast(acc.x); acc.y = tanh_fast(acc.y); acc.z = tanh_fast(acc.z); acc.w = tanh_fast(acc.w);
+                    if (h1_save) st4(h1_save + (size_t)n * H + 4 * c, acc);          // training: kept for the backward pass
                 }
                 float4 hh, hl;
                 split3(acc.x, hh.x, hl.x); split3(acc.y, hh.y, hl.y); split3(acc.z, hh.z, hl.z); split3(acc.w, hh.w, hl.w);
@@ -448,7 +450,15 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
                 float v[16], hi[16], lo[16];
                 tmem_ld16(lane_base + C::C_D2 + c0, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) split3(tanh_fast(v[i] + sB4[c0 + i]), hi[i], lo[i]);
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = tanh_fast(v[i] + sB4[c0 + i]);
+                    split3(v[i], hi[i], lo[i]);
+                }
+                if (H_save && live) {                                              // training: H' kept for the backward pass
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        st4(H_save + (size_t)n * H + c0 + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                }
                 tmem_st16(lane_base + C::C_A3H + c0, hi);
                 tmem_st16(lane_base + C::C_A3L + c0, lo);
             }
@@ -517,7 +527,8 @@ struct TcInCfg {
 template <int H>
 __global__ void __launch_bounds__(TcInCfg<H>::NT)
 input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, const int F, const int n_nodes,
-                const int n_tiles, float* __restrict__ X4, float* __restrict__ P_out, float* __restrict__ Q_out) {
+                const int n_tiles, float* __restrict__ X4, float* __restrict__ P_out, float* __restrict__ Q_out,
+                float* __restrict__ H_save) {
     using C = TcInCfg<H>;
     using N = TcCfg<H>;
     using B = Blob<H>;
@@ -562,7 +573,7 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
         }
         {
             const int c0 = hf * (H / 2);                           // this warp's 16 hidden columns
-            float hi[16], lo[16];
+            float hi[16], lo[16], hv[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 float v = sBin[c0 + i];
@@ -570,7 +581,13 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
                 v = fmaf(x[1], sWin[1 * H + c0 + i], v);
                 v = fmaf(x[2], sWin[2 * H + c0 + i], v);
                 v = fmaf(x[3], sWin[3 * H + c0 + i], v);
-                split3(tanh_fast(v), hi[i], lo[i]);
+                hv[i] = tanh_fast(v);
+                split3(hv[i], hi[i], lo[i]);
+            }
+            if (H_save && n < n_nodes) {                                           // training: H0 kept for the backward pass
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    st4(H_save + (size_t)n * H + c0 + 4 * i, make_float4(hv[4 * i], hv[4 * i + 1], hv[4 * i + 2], hv[4 * i + 3]));
             }
             tmem_st16(lane_base + C::C_A3H + c0, hi);
             tmem_st16(lane_base + C::C_A3L + c0, lo);
@@ -616,7 +633,7 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
 }
 
 int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
-                      cudaStream_t st) {
+                      float* H_save, cudaStream_t st) {
     using C = TcInCfg<32>;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + TcCfg<32>::TM - 1) / TcCfg<32>::TM;
@@ -628,12 +645,13 @@ int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, flo
         return GNNSEG_ENODEVICE;
     const int cap = 2 * sms;     // 256 TMEM columns and ~95 KB of shared memory per CTA: two CTAs per SM
     const int grid = n_tiles < cap ? n_tiles : cap;
-    input_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, P, Q);
+    input_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, P, Q, H_save);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
 int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e_in,
-                     const float* e_out, float* P_out, float* Q_out, int write_q, cudaStream_t st) {
+                     const float* e_out, float* P_out, float* Q_out, int write_q, float* h1_save, float* H_save,
+                     cudaStream_t st) {
     using C = TcCfg<32>;
     if (g->n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (g->n_nodes + C::TM - 1) / C::TM;
@@ -644,7 +662,7 @@ int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, c
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
         return GNNSEG_ENODEVICE;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    node_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out, Q_out, write_q);
+    node_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out, Q_out, write_q, h1_save, H_save);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 

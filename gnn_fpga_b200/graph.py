@@ -198,6 +198,17 @@ class DeviceGraphBatch:
             self._ws[h] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return self._ws[h]
 
+    def train_workspace(self, h, n_iters):
+        """Saved activations + backward scratch for gnnseg_forward_train / gnnseg_backward."""
+        L = _lib.lib()
+        key = ("train", h, n_iters)
+        if key not in self._ws:
+            nbytes = L.gnnseg_train_workspace_bytes(self.n_nodes, self.n_slots, self.F, h, n_iters)
+            if nbytes == 0:
+                _lib.check(-2, "gnnseg_train_workspace_bytes(F=%d, h=%d, n_iters=%d)" % (self.F, h, n_iters))
+            self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws[key]
+
     def count_real_edges(self):
         if self.n_real_edges is None:
             self.n_real_edges = int(((self.src >= 0) & (self.dst >= 0)).sum().item())

@@ -12,7 +12,6 @@ estimator_maskedlinear.py:85-101 reach into them.  Their own `forward` methods a
 implemented: the fused path never calls them and there is no CPU fallback.
 """
 import ctypes as C
-import warnings
 
 import torch
 import torch.nn as nn
@@ -117,7 +116,6 @@ class SegmentClassifier(nn.Module):
         self.node_network = NodeNetwork(input_dim + hidden_dim, hidden_dim, hidden_activation, masks_n)
         self._blob = None
         self.use_cuda_graph = True
-        self._warned_grad = False
         self._pinned = None          # reusable pinned staging buffers for host SparseGraph batches
 
     # -- weights -------------------------------------------------------------------------
@@ -337,22 +335,15 @@ class SegmentClassifier(nn.Module):
     def forward(self, inputs):
         if self._wants_grad():
             # A forward that must be differentiated (Estimator.training_step, gnn/estimator.py:53):
-            # the sm_100a kernels have no backward yet, so this one call runs the same sparse
-            # formulation with torch ops on the GPU (gnn_fpga_b200/training.py).  Inference
-            # (no_grad, as Estimator.predict does) always takes the CUDA kernels below.
-            if not self._warned_grad:
-                warnings.warn("SegmentClassifier.forward under autograd uses the torch-op sparse path "
-                              "(gnn_fpga_b200.training.autograd_forward); wrap inference in torch.no_grad()")
-                self._warned_grad = True
-            from .training import autograd_forward
+            # gnnseg_forward_train keeps the activations, the result's grad_fn runs gnnseg_backward
+            # (gnn_fpga_b200/training.py).  Inference (eval() or no_grad, as Estimator.predict
+            # does) takes the lighter path below.
+            from .training import differentiable_forward
             if self._device().type != "cuda":
                 raise _lib.GnnsegError("SegmentClassifier parameters are on %s: there is no CPU path" % self._device())
             if _lib.lib().gnnseg_supported(self.input_dim, self.hidden_dim) == 0:   # same shapes as inference
                 _lib.check(-2, "SegmentClassifier(input_dim=%d, hidden_dim=%d)" % (self.input_dim, self.hidden_dim))
-            batch = self._to_batch(inputs)
-            if batch.F != self.input_dim:
-                raise ValueError("X has %d features, model expects input_dim=%d" % (batch.F, self.input_dim))
-            return autograd_forward(self, batch)
+            return differentiable_forward(self, self._to_batch(inputs))
         if isinstance(inputs, DeviceGraphBatch):
             return self._run(inputs).view(inputs.B, inputs.e_max)
         if isinstance(inputs, (list, tuple)) and len(inputs) > 0 and isinstance(inputs[0], SparseGraph):

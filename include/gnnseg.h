@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GNNSEG_ABI_VERSION 1
+#define GNNSEG_ABI_VERSION 2
 
 /* error codes */
 #define GNNSEG_OK            0
@@ -171,6 +171,59 @@ int gnnseg_edge_step(const float* blob, const GnnsegGraph* graph, const float* P
 int gnnseg_node_step(const float* blob, const GnnsegGraph* graph, const float* X4,
                      const float* Q_in, const float* e_in, const float* e_out, int h,
                      float* P_out, float* Q_out, void* stream);
+
+/* ---- training: replaces loss.backward() / optimizer.step() of Estimator.training_step,
+ *      gnn/estimator.py:49-60 ------------------------------------------------------------- */
+
+/* Gradients of the ten parameter tensors, same shapes and row-major layout as GnnsegParams. */
+typedef struct GnnsegGrads {
+    float* w_in;  float* b_in;
+    float* w_e1;  float* b_e1;
+    float* w_e2;  float* b_e2;
+    float* w_n1;  float* b_n1;
+    float* w_n2;  float* b_n2;
+} GnnsegGrads;
+
+/*
+ * gnnseg_forward_train is gnnseg_forward that keeps, in the caller's workspace, what the backward
+ * pass needs (per iteration: hidden states, first-layer projections, edge scores in both CSR
+ * orders).  n_iters <= 64.  gnnseg_backward must be given the same workspace, untouched, and the
+ * same blob / graph / sizes.  It launches 3*(n_iters+1)+2 kernels on `stream`; the weight
+ * gradients are per-CTA partial sums added in a fixed order (no atomics): bit-identical from run
+ * to run.
+ *   dscores[n_slots] = dL/dscore for every slot of the padded batch, padding slots included (the
+ *                      reference's BCELoss averages over them, gnn/estimator.py:57).
+ *   masks            = nullable; only m_e1, m_e2, m_n1, m_n2 are read: dW = dW_eff * mask
+ *                      (MaskedLinear, gnn/model.py:28-31).
+ *   grads            = written, not accumulated.
+ */
+size_t gnnseg_train_workspace_bytes(int n_nodes, int n_slots, int F, int h, int n_iters);
+int gnnseg_forward_train(const float* blob, const GnnsegGraph* graph, const float* X,
+                         int F, int h, int n_iters, float* scores,
+                         void* ws, size_t ws_bytes, void* stream);
+int gnnseg_backward(const float* blob, const GnnsegParams* masks, const GnnsegGraph* graph,
+                    int F, int h, int n_iters, const float* dscores, const GnnsegGrads* grads,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * nn.BCELoss() as Estimator uses it (mean reduction, log clamped at -100): *loss (device) is
+ * written; dscores (nullable) receives dL/dscore.  weights: nullable per-element weights.
+ * ws: 1024 bytes of device scratch.
+ */
+int gnnseg_bce_loss(const float* scores, const float* targets, const float* weights, int n,
+                    float* loss, float* dscores, void* ws, void* stream);
+/*
+ * The L1 penalty of gnn/estimator.py:54-56: *loss += l1 * sum|W| over w_n1, w_n2, w_e1, w_e2
+ * (raw weights) and, when grads is not NULL, grads->w_* += l1 * sign(W).  loss may be NULL.
+ */
+int gnnseg_l1_penalty(const GnnsegParams* params, int F, int h, float l1, float* loss,
+                      const GnnsegGrads* grads, void* stream);
+/*
+ * torch.optim.Adam step (amsgrad off) on one flat tensor, in place; step counts from 1.
+ */
+int gnnseg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int n,
+                     int step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     void* stream);
 
 /* ---- host side: replaces graph_from_sparse + merge_graphs + np_to_torch --------------- */
 

@@ -134,6 +134,42 @@ def sparse_forward(p, X, src, dst, n_iters, dtype=torch.float32, return_state=Fa
         return (out, H) if return_state else out
 
 
+def sparse_vjp(p, X, src, dst, n_iters, dscores=None, y=None, l1=0.0, masks_e=None, masks_n=None,
+               dtype=torch.float64):
+    """Gradients of the sparse restatement by torch autograd on the CPU (the checker of
+    gnnseg_backward).  Either a cotangent `dscores` (n_slots,) is given, or targets `y`: then the
+    loss is Estimator.training_step's (gnn/estimator.py:53-57): BCELoss mean over ALL slots of the
+    padded batch + l1 * sum|W| over the edge / node network weights.  Masks multiply the weights
+    inside the graph (MaskedLinear, gnn/model.py:28-31), so dW = dW_eff * mask.
+    Returns (scores, loss or None, {key: grad})."""
+    leaf = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in p.items()}
+    q = dict(leaf)
+    if masks_e is not None:
+        q[PARAM_KEYS[2]] = leaf[PARAM_KEYS[2]] * masks_e[0].to(dtype)
+        q[PARAM_KEYS[4]] = leaf[PARAM_KEYS[4]] * masks_e[1].to(dtype)
+    if masks_n is not None:
+        q[PARAM_KEYS[6]] = leaf[PARAM_KEYS[6]] * masks_n[0].to(dtype)
+        q[PARAM_KEYS[8]] = leaf[PARAM_KEYS[8]] * masks_n[1].to(dtype)
+    X = torch.as_tensor(X).to(dtype)
+    src = torch.as_tensor(np.asarray(src)).long()
+    dst = torch.as_tensor(np.asarray(dst)).long()
+    H = sparse_input(q, X)
+    for _ in range(n_iters):
+        e = sparse_edge(q, H, src, dst)
+        H = torch.cat([sparse_node(q, H, e, src, dst), X], dim=-1)
+    out = sparse_edge(q, H, src, dst)
+    loss = None
+    if dscores is not None:
+        out.backward(torch.as_tensor(dscores).to(dtype))
+    else:
+        loss = torch.nn.functional.binary_cross_entropy(out, torch.as_tensor(y).to(dtype).reshape(-1))
+        if l1:
+            loss = loss + l1 * sum(leaf[k].abs().sum() for k in (PARAM_KEYS[6], PARAM_KEYS[8], PARAM_KEYS[2], PARAM_KEYS[4]))
+        loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
+    return out.detach(), (loss.detach() if loss is not None else None), grads
+
+
 def projections(p, HX):
     """Per-node first-layer projections the CUDA path carries between kernels (same algebra as
     gnn/model.py:73-81,120-125: W.[a;b;c] = Wa.a + Wb.b + Wc.c).  HX (n, D) = [H | X].

@@ -362,43 +362,6 @@ def test_predict_stream_matches_blocking_calls(cuda_device):
     assert list(model.predict_stream([])) == []
 
 
-def test_training_step_matches_reference_estimator(cuda_device):
-    """Two optimisation steps, as Estimator.training_step does them (gnn/estimator.py:49-60:
-    BCE over all padded slots + L1 penalty, Adam), against losses / first gradients / final
-    parameters recorded from the reference's own Estimator (tests/golden/train_step_h8_it2.npz).
-    The differentiable forward is the torch-op sparse path on the GPU (training.py)."""
-    import os
-    from conftest import GOLDEN
-    from gnn_fpga_b200 import SegmentClassifier
-    from gnn_fpga_b200.training import training_step
-    z = np.load(os.path.join(GOLDEN, "train_step_h8_it2.npz"))
-    model = SegmentClassifier(int(z["F"]), int(z["h"]), int(z["n_iters"]))
-    model.load_state_dict({k[6:]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith("param:")})
-    model = model.to(cuda_device).train()
-    opt = torch.optim.Adam(model.parameters())
-    inputs = [torch.from_numpy(z[k].astype(np.float32)).to(cuda_device) for k in ("X", "Ri", "Ro")]
-    y = torch.from_numpy(z["y"]).to(cuda_device)
-    losses = []
-    for step in range(2):
-        with pytest.warns(UserWarning) if step == 0 else __import__("contextlib").nullcontext():
-            loss = training_step(model, opt, torch.nn.BCELoss(), inputs, y, l1=float(z["l1"]))
-        losses.append(float(loss.item()))
-        if step == 0:
-            for k, p_ in model.named_parameters():
-                g_ref = z["grad0:" + k]
-                assert np.allclose(p_.grad.cpu().numpy(), g_ref, rtol=2e-4, atol=2e-8), k
-    assert np.allclose(losses, z["losses"], rtol=1e-5)
-    for k, v in model.state_dict().items():
-        assert np.allclose(v.cpu().numpy(), z["after:" + k], rtol=1e-4, atol=1e-6), k
-    # inference after training goes back to the CUDA kernels and agrees with the torch-op path
-    model.eval()
-    with torch.no_grad():
-        a = model(inputs)
-    model.train()
-    b = model(inputs).detach()
-    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= TOL
-
-
 def test_single_direction_build_csr_entry_point(cuda_device):
     """gnnseg_build_csr (one key array) gives the same CSR as the paired gnnseg_build_graph."""
     from gnn_fpga_b200 import _lib, DeviceGraphBatch, data

@@ -71,3 +71,20 @@ def test_padding_constant():
     pad = (rec["Ri"].sum(axis=1) == 0) & (rec["Ro"].sum(axis=1) == 0)
     assert pad.any()
     assert np.allclose(rec["out"][pad], const, rtol=1e-6)
+
+
+def test_gradient_oracle_matches_reference_estimator():
+    """sparse_vjp (autograd over the sparse restatement, the checker of gnnseg_backward) against
+    the loss and first-step gradients recorded from the reference's own Estimator.training_step
+    (tests/golden/train_step_h8_it2.npz, oracle/make_golden.py)."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "train_step_h8_it2.npz"))
+    p = {k[6:]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith("param:")}
+    src, dst = O.edges_from_dense(z["Ri"], z["Ro"])
+    B, N, F = z["X"].shape
+    _, loss, g = O.sparse_vjp(p, z["X"].reshape(B * N, F), src, dst, int(z["n_iters"]), y=z["y"], l1=float(z["l1"]))
+    assert abs(float(loss) - float(z["losses"][0])) <= 1e-6 * abs(float(z["losses"][0]))
+    for k, v in g.items():
+        ref = z["grad0:" + k]
+        assert np.max(np.abs(v.numpy() - ref)) <= 2e-5 * np.max(np.abs(ref)), k
