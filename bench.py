@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--workload", default="acts64", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -369,6 +370,31 @@ def main():
         e2e["sec_pipelined"] = time.perf_counter() - t0
         assert n_out == args.steps and torch.equal(out_host, host_out)
 
+    # ---- training step (BASELINE configs[4]): forward_train + BCE + L1 + backward + all-reduce + Adam ----
+    train = None
+    if not args.no_train:
+        from gnn_fpga_b200.training import NativeTrainer
+        tmodel = SegmentClassifier(cfg["F"], cfg["h"], cfg["n_iters"]).to(dev).train()
+        tmodel.load_state_dict(model.state_dict())
+        y = torch.zeros((n_events, batch.e_max), dtype=torch.float32)
+        for b_, g_ in enumerate(graphs):
+            y[b_, :g_.y.shape[0]] = torch.from_numpy(g_.y)
+        y = y.to(dev)
+        trainer = NativeTrainer(tmodel, l1=1e-4)
+        for _ in range(3):
+            trainer.step(batch, y)
+        barrier()
+        n_tr = max(3, min(args.steps, 20))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_tr):
+            trainer.step(batch, y)
+        b.record()
+        barrier()
+        train = {"ms": a.elapsed_time(b) / n_tr, "loss": float(trainer.loss.item())}
+        del trainer, tmodel
+        batch._ws = {k: v for k, v in batch._ws.items() if not (isinstance(k, tuple) and k[0] == "train")}
+
     # ---- optional collective: all ranks receive all scores (NCCL all-gather, not in `value`) ------
     gather_ms = None
     if world > 1:
@@ -388,12 +414,12 @@ def main():
 
     # ---- reduce over ranks ---------------------------------------------------------------------
     stats = torch.tensor([total_ms, e2e["sec"] if e2e else 0.0, gather_ms or 0.0,
-                          e2e["sec_pipelined"] if e2e else 0.0], dtype=torch.float64, device=dev)
+                          e2e["sec_pipelined"] if e2e else 0.0, train["ms"] if train else 0.0], dtype=torch.float64, device=dev)
     counts = torch.tensor([n_real, n_events], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    total_ms, e2e_sec, gather_ms_max, e2e_pipe_sec = stats.tolist()
+    total_ms, e2e_sec, gather_ms_max, e2e_pipe_sec, train_ms = stats.tolist()
     all_edges, all_events = counts.tolist()
 
     if rank == 0:
@@ -441,6 +467,14 @@ def main():
                                    "H2D, device CSR build, forward, D2H into pinned memory; two batches in flight",
                            "unpipelined": {"value": all_edges * args.steps / e2e_sec, "ms_per_step": e2e_sec / args.steps * 1e3,
                                            "path": "model(graphs) then copy to pinned host memory, synchronised every step"}}
+        if train:
+            n_k = 2 + 2 * it + 2 + 2 + 1 + 3 * (it + 1) + 1 + 1 + 1
+            line["train_step"] = {"ms": train_ms, "edges_per_sec": all_edges / (train_ms * 1e-3),
+                                  "events_per_sec": all_events / (train_ms * 1e-3), "loss": train["loss"],
+                                  "gpu_launches_per_step": n_k,
+                                  "path": "NativeTrainer.step on the resident batch: gnnseg_forward_train, gnnseg_bce_loss, "
+                                          "gnnseg_backward, gnnseg_l1_penalty, %sgnnseg_adam_step; L2 not flushed"
+                                          % ("NCCL all-reduce of the flat gradient, " if world > 1 else "")}
         if world > 1:
             line["scores_allgather_ms"] = gather_ms_max    # NCCL all-gather of every rank's (B, E_max) scores
         if world == 1 and not args.no_cpu_baseline:
