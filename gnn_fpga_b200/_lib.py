@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgnnseg_b200.so")
+# GNNSEG_LIB: another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.path.abspath(os.environ["GNNSEG_LIB"]) if os.environ.get("GNNSEG_LIB") else os.path.join(_HERE, "libgnnseg_b200.so")
 
 OK = 0
 ABI_VERSION = 2

@@ -43,7 +43,7 @@ struct NodePart {
     static constexpr int SIZE = BIN + H;
 };
 constexpr int EDGE_BWD_MAX_BLOCKS = 2048;
-constexpr int DENSE_BWD_MAX_BLOCKS = 160;
+constexpr int DENSE_BWD_MAX_BLOCKS = 320;
 
 size_t edge_part_floats(int h) { return (size_t)EDGE_BWD_MAX_BLOCKS * (2 * h + 4); }
 size_t node_part_floats(int h) {
@@ -203,6 +203,7 @@ template <int H>
 struct DenseCfg {
     static constexpr int TN  = (H >= 64) ? 32 : 64;        // nodes per tile
     static constexpr int NT  = (H >= 64) ? 512 : 256;
+    static constexpr int MINB = (H >= 64) ? 1 : 2;         // CTAs per SM (shared memory: 174 KB at H = 64, <= 99 KB below)
     static constexpr int D4  = H + 4;
     static constexpr int LW  = 5 * H + 4;                  // row strides (floats): +4 keeps 8 consecutive rows on distinct banks
     static constexpr int LH  = H + 4;
@@ -295,7 +296,7 @@ __device__ __forceinline__ void dot_gemm(const float* __restrict__ sA, const int
 // FIRST: H_in is H_0 (input network: dWin, dbin); otherwise H_in = H_t, t > 0, produced by node
 // step t-1 from h1_prev: dW4, db4 and dg_out = dL/dg_{t-1}.
 template <int H, int NB, bool FIRST>
-__global__ void __launch_bounds__(DenseCfg<H>::NT, 1)
+__global__ void __launch_bounds__(DenseCfg<H>::NT, DenseCfg<H>::MINB)
 dense_bwd_kernel(const float* __restrict__ blob, const float* __restrict__ dproj, const float* __restrict__ H_in,
                  const float* __restrict__ X4, const float* __restrict__ h1_prev, const int n_nodes,
                  const int n_tiles, float* __restrict__ dg_out, float* __restrict__ part, const int accumulate) {
@@ -422,9 +423,16 @@ __global__ void finalize_grads_kernel(const float* __restrict__ partE, const int
     const int n_win = H * F, n_e1 = H * 2 * D, n_n1 = H * 3 * D, n_n2 = H * H;
     const int o_bin = n_win, o_e1 = o_bin + H, o_be1 = o_e1 + n_e1, o_e2 = o_be1 + H, o_be2 = o_e2 + H,
               o_n1 = o_be2 + 1, o_bn1 = o_n1 + n_n1, o_n2 = o_bn1 + H, o_bn2 = o_n2 + n_n2, total = o_bn2 + H;
-    auto sumN = [&](const int off) { float s = 0.f; for (int b = 0; b < nN; ++b) s += partN[(size_t)b * NP::SIZE + off]; return s; };
-    auto sumE = [&](const int off) { float s = 0.f; for (int b = 0; b < nE; ++b) s += partE[(size_t)b * EP::SIZE + off]; return s; };
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    // one warp per gradient element: lane l adds CTAs l, l+32, ... in order, then a butterfly
+    const int lane = threadIdx.x & 31;
+    auto wsum = [&](float s) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        return s;
+    };
+    auto sumN = [&](const int off) { float s = 0.f; for (int b = lane; b < nN; b += 32) s += partN[(size_t)b * NP::SIZE + off]; return wsum(s); };
+    auto sumE = [&](const int off) { float s = 0.f; for (int b = lane; b < nE; b += 32) s += partE[(size_t)b * EP::SIZE + off]; return wsum(s); };
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += (gridDim.x * blockDim.x) >> 5) {
         if (i < o_bin) {                                   // input_network.0.weight (h, F)
             const int j = i / F, f = i % F;
             go.w_in[i] = sumN(NP::WIN + f * H + j);
@@ -509,7 +517,7 @@ static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, c
     if (gridG > sms * 16) gridG = sms * 16;
     if (gridG < 1) gridG = 1;
     const int n_tiles = (n + C::TN - 1) / C::TN;
-    int gridD = n_tiles < sms ? n_tiles : sms;
+    int gridD = n_tiles < sms * C::MINB ? n_tiles : sms * C::MINB;
     if (gridD > DENSE_BWD_MAX_BLOCKS) gridD = DENSE_BWD_MAX_BLOCKS;
     if (gridD < 1) gridD = 1;
     auto kF2 = dense_bwd_kernel<H, 2, true>;
@@ -551,7 +559,7 @@ static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, c
         else
             kI5<<<gridD, C::NT, C::SMEM_BYTES, st>>>(blob, s.dproj, s.Hs[t], s.x4, s.h1s[t - 1], n, n_tiles, s.dg, s.partN, 2);
     }
-    finalize_grads_kernel<H><<<32, 256, 0, st>>>(s.partE, gridE, s.partN, n > 0 ? gridD : 0, F, T > 0, go);
+    finalize_grads_kernel<H><<<sms * 4, 256, 0, st>>>(s.partE, gridE, s.partN, n > 0 ? gridD : 0, F, T > 0, go);
     return bwd_check();
 }
 

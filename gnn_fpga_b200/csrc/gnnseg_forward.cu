@@ -357,8 +357,14 @@ input_kernel(const float* __restrict__ blob, const float* __restrict__ X, const 
 // ------------------------------------------------------------------------------------
 // edge step
 // ------------------------------------------------------------------------------------
+// Measured on B200 (scripts/micro/gather_bench.cu): the rate at which an SM gathers random 128-byte
+// rows with LDG.128 grows with the number of resident WARPS, not with the loads a thread keeps in
+// flight (5 TB/s at 16 warps per SM, 9 at 32, 15 at 64, the same for 4, 8 or 16 loads per thread).
+// So the rows of only two slots are in flight per lane group, indices are fetched per pair, and the
+// register budget is set for 48 resident warps (40 registers; 32 registers / 64 warps spills and
+// measured 52 us against 46 us).
 template <int H>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
             const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
             const int32_t* __restrict__ in_pos, const int32_t* __restrict__ out_pos,
@@ -366,49 +372,71 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
             float* __restrict__ e_out) {
     using B = Blob<H>;
     constexpr int G = H / 4;        // lanes that share one edge (one float4 of P each)
-    constexpr int EPP = 32 / G;     // edges a warp handles per pass
+    constexpr int EPP = 32 / G;     // edges a warp handles per iteration; G iterations cover 32 slots
+    constexpr int PAIR = G >= 2 ? 2 : 1;
     const int lane = threadIdx.x & 31;
     const int c = lane % G, g = lane / G;
-    const float4 w2 = ldg4(blob + B::W2 + 4 * c);
-    const float4 b1 = ldg4(blob + B::BP + 4 * c);
-    const float b2 = __ldg(blob + B::B2);
     const uint64_t keep = l2_policy_evict_last();   // every P row is gathered ~deg times
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const float* Pa = P + 4 * c;                    // this lane's chunk of the start-node half
+    const float* Pb = P + H + 4 * c;                // ... and of the end-node half
 
     for (int base = warp * 32; base < n_slots; base += n_warps * 32) {
-        const int j = base + lane;
-        int s = -1, d = -1, pi = -1, po = -1;
-        if (j < n_slots) {
-            s = __ldg(src + j);
-            d = __ldg(dst + j);
-            if (e_in) pi = __ldg(in_pos + j);      // issued now, needed only after the MLP
-            if (e_out) po = __ldg(out_pos + j);
-        }
-        float mine = 0.f;
-#pragma unroll (G > 8 ? 8 : G)
-        for (int p = 0; p < G; ++p) {
-            const int k = p * EPP + g;                       // which of the warp's 32 edges
-            const int ss = __shfl_sync(0xffffffffu, s, k);
-            const int dd = __shfl_sync(0xffffffffu, d, k);
-            float4 a = b1;                                   // absent start: W1a.0 + b1
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);      // absent end:   W1b.0
-            if (ss >= 0) a = ldg4_hint(P + (size_t)ss * (2 * H) + 4 * c, keep);
-            if (dd >= 0) b = ldg4_hint(P + (size_t)dd * (2 * H) + H + 4 * c, keep);
-            float z = w2.x * tanh_fast(a.x + b.x);
-            z = fmaf(w2.y, tanh_fast(a.y + b.y), z);
-            z = fmaf(w2.z, tanh_fast(a.z + b.z), z);
-            z = fmaf(w2.w, tanh_fast(a.w + b.w), z);
+        // iteration p of the group (g, *) works on slot base + p*EPP + g: the G lanes of a group read
+        // the same endpoint words (one broadcast load), no index shuffles
+        float z[G];
 #pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-            const float v = __shfl_sync(0xffffffffu, z, (lane % EPP) * G);
-            if (lane / EPP == p) mine = v;
+        for (int p0 = 0; p0 < G; p0 += PAIR) {
+            int s[PAIR], d[PAIR];
+#pragma unroll
+            for (int q = 0; q < PAIR; ++q) {
+                const int jj = base + (p0 + q) * EPP + g;
+                s[q] = d[q] = -1;
+                if (jj < n_slots) { s[q] = __ldg(src + jj); d[q] = __ldg(dst + jj); }
+            }
+            float4 a[PAIR], b[PAIR];
+#pragma unroll
+            for (int q = 0; q < PAIR; ++q) {
+                // absent start: W1a.0 + b1; absent end: W1b.0.  Branch free: row 0 is loaded and dropped.
+                a[q] = ldg4_hint(Pa + (size_t)max(s[q], 0) * (2 * H), keep);
+                b[q] = ldg4_hint(Pb + (size_t)max(d[q], 0) * (2 * H), keep);
+            }
+            const float4 w2 = ldg4(blob + B::W2 + 4 * c);      // L1-resident: cheaper than four live registers
+#pragma unroll
+            for (int q = 0; q < PAIR; ++q) {
+                if (s[q] < 0) a[q] = ldg4(blob + B::BP + 4 * c);
+                if (d[q] < 0) b[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                float t = w2.x * tanh_fast(a[q].x + b[q].x);
+                t = fmaf(w2.y, tanh_fast(a[q].y + b[q].y), t);
+                t = fmaf(w2.z, tanh_fast(a[q].z + b[q].z), t);
+                z[p0 + q] = fmaf(w2.w, tanh_fast(a[q].w + b[q].w), t);
+            }
         }
+        // transposed butterfly: G partial sums on each of G lanes -> lane c holds the total of
+        // iteration p = c (G - 1 shuffles instead of G log2 G)
+#pragma unroll
+        for (int o = G / 2, cnt = G; o > 0; o >>= 1, cnt >>= 1) {
+            const bool upper = (c & o) != 0;
+#pragma unroll
+            for (int i = 0; i < cnt / 2; ++i) {
+                const float send = upper ? z[i] : z[i + cnt / 2];
+                const float mine = upper ? z[i + cnt / 2] : z[i];
+                z[i] = mine + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+        const int j = base + c * EPP + g;               // the slot whose score this lane now holds
         if (j < n_slots) {
-            const float score = 1.f / (1.f + expf(-(mine + b2)));
+            const float score = 1.f / (1.f + expf(-(z[0] + __ldg(blob + B::B2))));
             if (e_slot) e_slot[j] = score;
-            if (pi >= 0) e_in[pi] = score;       // the node step reads the scores in CSR order
-            if (po >= 0) e_out[po] = score;
+            if (e_in) {                                  // the node step reads the scores in CSR order
+                const int pi = __ldg(in_pos + j);
+                if (pi >= 0) e_in[pi] = score;
+            }
+            if (e_out) {
+                const int po = __ldg(out_pos + j);
+                if (po >= 0) e_out[po] = score;
+            }
         }
     }
 }
