@@ -80,6 +80,31 @@ __device__ __forceinline__ void st4_hint(float* p, const float4 v, const uint64_
     asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
                  ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
 }
+// Programmatic dependent launch: a forward kernel lets its successor start (get resident, run
+// its prologue: weights to shared memory, TMEM allocation) while it is still running; the
+// successor calls pdl_wait() before it touches anything the predecessor writes, which returns when
+// the predecessor grid has completed and its writes are visible.  Every kernel of the forward is
+// a single resident wave, so a waiting successor never keeps a predecessor CTA from being scheduled.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// kernel<<<grid, block, smem, st>>>(args...) with the programmatic-serialisation attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), const int grid, const int block, const size_t smem,
+                              cudaStream_t st, const bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // tanh(x) = sign(x) * (1 - 2 / (exp(2|x|) + 1)) with the hardware ex2 / rcp approximations:
 // 2 MUFU + 5 ALU instructions, branch free (tanhf is ~20 instructions over two divergent paths).
 // Absolute error <= ~2e-7 over the whole range (the result saturates to +-1 for |x| > 44, NaN

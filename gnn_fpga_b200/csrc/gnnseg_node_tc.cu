@@ -24,6 +24,8 @@
 
 namespace gnnseg {
 
+bool use_pdl(int n_slots);   // gnnseg_forward.cu
+
 template <int H>
 struct TcCfg {
     static constexpr int TM   = 128;                 // nodes per tile = UMMA M
@@ -293,9 +295,11 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
     }
     fence_async_smem();            // weights were written through the generic proxy
     tc_fence_before();
+    pdl_launch_dependents();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                    // prologue done; Q_in / e_in / e_out come from the kernels before
 
     if (tid >= ET + ST) {
         // ================================ gather warps ==================================
@@ -555,6 +559,7 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
     }
     fence_async_smem();
     tc_fence_before();
+    pdl_launch_dependents();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
@@ -662,7 +667,9 @@ int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, c
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
         return GNNSEG_ENODEVICE;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    node_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out, Q_out, write_q, h1_save, H_save);
+    if (launch_pdl(node_kernel_tc<32>, grid, C::NT, C::SMEM_BYTES, st, use_pdl(g->n_slots), blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out,
+                   Q_out, write_q, h1_save, H_save) != cudaSuccess)
+        return GNNSEG_ECUDA;
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
