@@ -445,6 +445,57 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
 }
 
 // ------------------------------------------------------------------------------------
+// node step, first half: the ordered CSR sum.  h1[n] = tanh(Qs[n] + sum_in e Qi[src] + sum_out e Qo[dst]),
+// own term first, then in-slots, then out-slots, ascending: one thread per (node, float4 chunk), no
+// atomics.  Written for 64 resident warps per SM: the warp count, not the unrolling, sets the rate at
+// which an SM gathers rows (see edge_kernel).  h1 rows are written with stride ld_out; the tensor-core
+// MLP kernel (node_mlp_kernel_tc) reads them back.
+// ------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(256, 8)
+node_gather_kernel(const GnnsegGraph g, const float* __restrict__ Q_in, const float* __restrict__ e_in,
+                   const float* __restrict__ e_out, float* __restrict__ h1_out, const int ld_out,
+                   float* __restrict__ h1_save) {
+    constexpr int G = H / 4;
+    const uint64_t keep = l2_policy_evict_last();
+    const long long total = (long long)g.n_nodes * G;
+    pdl_launch_dependents();
+    pdl_wait();                                     // Q_in, e_in, e_out come from the kernels before
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(idx / G), c = (int)(idx % G);
+        const int i0 = __ldg(g.in_ptr + n), i1 = __ldg(g.in_ptr + n + 1);
+        const int o0 = __ldg(g.out_ptr + n), o1 = __ldg(g.out_ptr + n + 1);
+        float4 acc = ldg4(Q_in + (size_t)n * 3 * H + 2 * H + 4 * c);             // Qs[n] (holds b3)
+        const float* Qi = Q_in + 4 * c;
+        const float* Qo = Q_in + H + 4 * c;
+#pragma unroll 1
+        for (int s = i0; s < i1; s += 2) {
+            const int nb0 = __ldg(g.in_nbr + s), nb1 = s + 1 < i1 ? __ldg(g.in_nbr + s + 1) : -1;
+            const float w0 = __ldg(e_in + s), w1 = s + 1 < i1 ? __ldg(e_in + s + 1) : 0.f;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (nb0 >= 0) v0 = ldg4_hint(Qi + (size_t)nb0 * 3 * H, keep);
+            if (nb1 >= 0) v1 = ldg4_hint(Qi + (size_t)nb1 * 3 * H, keep);
+            if (nb0 >= 0) fma4(acc, w0, v0);                                  // nb < 0: half edge, the zero row
+            if (nb1 >= 0) fma4(acc, w1, v1);
+        }
+#pragma unroll 1
+        for (int s = o0; s < o1; s += 2) {
+            const int nb0 = __ldg(g.out_nbr + s), nb1 = s + 1 < o1 ? __ldg(g.out_nbr + s + 1) : -1;
+            const float w0 = __ldg(e_out + s), w1 = s + 1 < o1 ? __ldg(e_out + s + 1) : 0.f;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (nb0 >= 0) v0 = ldg4_hint(Qo + (size_t)nb0 * 3 * H, keep);
+            if (nb1 >= 0) v1 = ldg4_hint(Qo + (size_t)nb1 * 3 * H, keep);
+            if (nb0 >= 0) fma4(acc, w0, v0);
+            if (nb1 >= 0) fma4(acc, w1, v1);
+        }
+        acc.x = tanh_fast(acc.x); acc.y = tanh_fast(acc.y); acc.z = tanh_fast(acc.z); acc.w = tanh_fast(acc.w);
+        st4(h1_out + (size_t)n * ld_out + 4 * c, acc);
+        if (h1_save) st4(h1_save + (size_t)n * H + 4 * c, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // node step (generic path): warp-specialised persistent kernel.
 //   producer warps  stage the tile's CSR slices, gather and sum the aligned Q rows and leave
 //                   h1 = tanh(...) of the tile in shared memory (latency bound: many loads in flight)
@@ -724,7 +775,9 @@ static int launch_edge(const float* blob, const GnnsegGraph* g, const float* P, 
 
 int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e_in,
                      const float* e_out, float* P_out, float* Q_out, int write_q, float* h1_save, float* H_save,
-                     cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
+                     cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05, gather fused)
+int launch_node_mlp_tc32(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
+                         float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05, MLP only)
 
 template <int H>
 static int launch_node(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e_in,
@@ -733,8 +786,21 @@ static int launch_node(const float* blob, const GnnsegGraph* g, const float* X4,
     using C = NodeCfg<H>;
     if (g->n_nodes == 0) return GNNSEG_OK;
     if (H == 32) {
-        const char* impl = getenv("GNNSEG_NODE_IMPL");   // "mma": generic mma.sync path (for A/B runs)
-        if (!impl || impl[0] != 'm') return launch_node_tc32(blob, g, X4, Q_in, e_in, e_out, P_out, Q_out, write_q, h1_save, H_save, st);
+        // "mma": generic mma.sync path, "fused": one tcgen05 kernel with the gather inside (for A/B runs);
+        // default: gather kernel at full occupancy + tcgen05 MLP kernel, two CTAs per SM.  The h1 rows
+        // travel through P_out's own rows (row n of P' is written after row n of h1 has been read).
+        const char* impl = getenv("GNNSEG_NODE_IMPL");
+        if (impl && impl[0] == 'f') return launch_node_tc32(blob, g, X4, Q_in, e_in, e_out, P_out, Q_out, write_q, h1_save, H_save, st);
+        if (!impl || impl[0] != 'm') {
+            const int sms = sm_count();
+            if (sms < 1) return GNNSEG_ENODEVICE;
+            long long blocks = ((long long)g->n_nodes * (H / 4) + 255) / 256;
+            if (blocks > sms * 8) blocks = sms * 8;
+            if (launch_pdl(node_gather_kernel<H>, (int)blocks, 256, 0, st, use_pdl(g->n_slots), *g, Q_in, e_in, e_out, P_out, 2 * H,
+                           h1_save) != cudaSuccess)
+                return GNNSEG_ECUDA;
+            return launch_node_mlp_tc32(blob, X4, P_out, 2 * H, g->n_nodes, P_out, Q_out, write_q, H_save, use_pdl(g->n_slots), st);
+        }
     }
     const int n_tiles = (g->n_nodes + C::TN - 1) / C::TN;
     int grid = 0;

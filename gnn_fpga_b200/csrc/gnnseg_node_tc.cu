@@ -511,6 +511,234 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
 }
 
 // ------------------------------------------------------------------------------------------
+// Node step, second half, on the tensor cores: the two per-node GEMMs on rows h1 that
+// node_gather_kernel (gnnseg_forward.cu) left in global memory.  Same GEMMs, same 3xTF32 split and
+// the same epilogues as node_kernel_tc, but no gather inside: the CTA needs 93 KB of shared memory
+// and 256 tensor-memory columns, so TWO CTAs share an SM and the serial chain of one tile
+// (barrier -> GEMM2 -> epilogue -> GEMM3 -> epilogue -> stores, ~9.6 k cycles, mostly latency) overlaps
+// the other CTA's.  The store transposition buffers alias the A tile (free once GEMM2 has read it).
+// ------------------------------------------------------------------------------------------
+template <int H>
+struct TcMlpCfg {
+    using N = TcCfg<H>;
+    static constexpr int TM = N::TM, EW = 8, LW = 4, ET = EW * 32, LT = LW * 32, NT = ET + LT;
+    static constexpr int O_A    = 0;                            // hi, lo (one buffer); reused as [EW] 32x32 swizzled store tiles
+    static constexpr int O_W4H  = O_A + 2 * N::A_BYTES;
+    static constexpr int O_W4L  = O_W4H + N::W4_BYTES;
+    static constexpr int O_WPH  = O_W4L + N::W4_BYTES;
+    static constexpr int O_WPL  = O_WPH + N::WP_BYTES;
+    static constexpr int O_BIAS = O_WPL + N::WP_BYTES;          // b4 [H], bias of the projections [5H]
+    static constexpr int O_MBAR = O_BIAS + 6 * H * 4;
+    static constexpr int SMEM_BYTES = O_MBAR + 16;
+    static_assert(EW * 32 * 32 * 4 <= 2 * N::A_BYTES, "store tiles fit in the A buffer");
+    static constexpr int C_A3H = 0, C_A3L = N::D4P, C_D3 = 2 * N::D4P, C_D2 = C_D3;   // D2 is consumed before GEMM3 writes D3
+    static constexpr int TMEM_COLS = 256;
+    static_assert(C_D3 + N::NP <= TMEM_COLS, "tensor memory");
+    static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
+};
+
+template <int H>
+__global__ void __launch_bounds__(TcMlpCfg<H>::NT, 2)
+node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4, const float* h1,
+                   const int ld_h1, const int n_nodes, const int n_tiles, float* P_out,
+                   float* __restrict__ Q_out, const int write_q, float* __restrict__ H_save) {
+    // h1 may alias P_out (row n of h1 inside row n of P'): no __restrict__, no read-only loads on those two
+    using C = TcMlpCfg<H>;
+    using N = TcCfg<H>;
+    using B = Blob<H>;
+    constexpr int TM = C::TM, NT = C::NT, ET = C::ET, LT = C::LT, NP = N::NP;
+    constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_EPI = 3;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* sB4 = reinterpret_cast<float*>(smem + C::O_BIAS);
+    float* sBP = sB4 + H;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    static_assert(C::O_W4L == C::O_W4H + H * H * 4 && C::O_WPH == C::O_W4L + H * H * 4 &&
+                  C::O_WPL == C::O_WPH + NP * N::D4P * 4, "image order");
+    for (int i = tid * 4; i < 2 * H * H + 2 * NP * N::D4P; i += NT * 4)
+        *reinterpret_cast<float4*>(smem + C::O_W4H + i * 4) = ldg4(blob + B::TC_W4H + i);
+    for (int i = tid; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
+    for (int i = tid; i < NP; i += NT) sBP[i] = __ldg(blob + B::BP + i);
+    if (tid == 0) {
+        mbar_init(smem_u32(mbar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    pdl_launch_dependents();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_wait();                    // h1 comes from the gather kernel before
+
+    if (tid >= ET) {
+        // ================================ loader warps ==================================
+        // h1 rows of the NEXT tile are fetched into registers while the MLP warps work on this one;
+        // after the MLP warps have released the buffer the rows are split into tf32 hi / lo parts and
+        // written as the canonical K-major operand tile.  A quarter warp holds 8 consecutive rows of
+        // ONE float4 chunk, i.e. one contiguous 128-byte row group of the canonical tile: the stores
+        // are bank-conflict free (8 lanes on one row would hit the same banks 8 ways).
+        const int lt = tid - ET, lw = lt >> 5, r7 = lt & 7, cq = (lt >> 3) & 3;
+        float4 v[8];
+        auto fetch = [&](const int tile) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = tile * TM + (lw * 4 + (j >> 1)) * 8 + r7;
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < n_nodes) v[j] = lds4(h1 + (size_t)n * ld_h1 + 4 * (cq + 4 * (j & 1)));     // plain 16-byte load
+            }
+        };
+        if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            if (it >= 1) tc_bar_sync(BAR_EMPTY, ET + LT);       // the previous tile's stores have left the buffer
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 hh, hl;
+                split3(v[j].x, hh.x, hl.x); split3(v[j].y, hh.y, hl.y); split3(v[j].z, hh.z, hl.z); split3(v[j].w, hh.w, hl.w);
+                const int off = canon_off((lw * 4 + (j >> 1)) * 8 + r7, 4 * (cq + 4 * (j & 1)), N::SBO_H);
+                *reinterpret_cast<float4*>(smem + C::O_A + off) = hh;
+                *reinterpret_cast<float4*>(smem + C::O_A + N::A_BYTES + off) = hl;
+            }
+            fence_async_smem();                                // generic-proxy writes -> tensor core reads
+            tc_bar_arrive(BAR_FULL, ET + LT);
+            if (tile + (int)gridDim.x < n_tiles) fetch(tile + gridDim.x);
+        }
+    } else {
+        // ================================ MLP (issuer + epilogue) ======================
+        const uint32_t mb = smem_u32(mbar);
+        const int q = warp & 3, hf = warp >> 2;               // TMEM lane quarter, which half of the columns
+        const int row = q * 32 + lane;                        // node within the tile = TMEM lane
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        constexpr uint32_t ID2 = idesc_tf32(TM, H), ID3 = idesc_tf32(TM, NP);
+        const uint32_t sa = smem_u32(smem);
+        float* sOut = reinterpret_cast<float*>(smem + C::O_A + warp * 4096);   // this warp's 32 x 32 store tile
+        const uint64_t stream = l2_policy_evict_first();       // P', Q' are read next by another kernel
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int n = tile * TM + row;
+            const bool live = n < n_nodes;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && hf == 0) x = ldg4(X4 + (size_t)n * 4);
+            // ---- GEMM2: D2 = h1 . W4^T ----------------------------------------------------
+            tc_bar_sync(BAR_FULL, ET + LT);
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t a_hi = sa + C::O_A, a_lo = a_hi + N::A_BYTES;
+#pragma unroll
+                for (int kq = 0; kq < H / 8; ++kq) {
+                    const uint32_t ko = kq * 2 * N::LBO;
+                    const uint64_t ah = smem_desc(a_hi + ko, N::LBO, N::SBO_H);
+                    const uint64_t al = smem_desc(a_lo + ko, N::LBO, N::SBO_H);
+                    const uint64_t bh = smem_desc(sa + C::O_W4H + ko, N::LBO, N::SBO_H);
+                    const uint64_t bl = smem_desc(sa + C::O_W4L + ko, N::LBO, N::SBO_H);
+                    umma_ss(tmem + C::C_D2, al, bh, ID2, kq > 0);
+                    umma_ss(tmem + C::C_D2, ah, bl, ID2, 1);
+                    umma_ss(tmem + C::C_D2, ah, bh, ID2, 1);
+                }
+                umma_commit(mb);
+            }
+            mbar_wait(mb, phase); phase ^= 1;
+            tc_fence_after();
+            // ---- epilogue 2: H' = tanh(D2 + b4); [H'|X|0] -> A3 (hi, lo) in TMEM -------------
+            {
+                const int c0 = hf * (H / 2);
+                float v[16], hi[16], lo[16];
+                tmem_ld16(lane_base + C::C_D2 + c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = tanh_fast(v[i] + sB4[c0 + i]);
+                    split3(v[i], hi[i], lo[i]);
+                }
+                if (H_save && live) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        st4(H_save + (size_t)n * H + c0 + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                }
+                tmem_st16(lane_base + C::C_A3H + c0, hi);
+                tmem_st16(lane_base + C::C_A3L + c0, lo);
+            }
+            if (hf == 0) {
+                float xh[8], xl[8];
+                split3(x.x, xh[0], xl[0]); split3(x.y, xh[1], xl[1]);
+                split3(x.z, xh[2], xl[2]); split3(x.w, xh[3], xl[3]);
+#pragma unroll
+                for (int i = 4; i < 8; ++i) xh[i] = xl[i] = 0.f;
+                tmem_st8(lane_base + C::C_A3H + H, xh);
+                tmem_st8(lane_base + C::C_A3L + H, xl);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            tc_bar_sync(BAR_EPI, ET);                          // A3 complete, every thread has read its D2 columns
+            // ---- GEMM3: D3 = [H'|X] . WP^T  (A from tensor memory) --------------------------
+            if (tid == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int kq = 0; kq < N::D4P / 8; ++kq) {
+                    const uint32_t ko = kq * 2 * N::LBO;
+                    const uint64_t bh = smem_desc(sa + C::O_WPH + ko, N::LBO, N::SBO_D4);
+                    const uint64_t bl = smem_desc(sa + C::O_WPL + ko, N::LBO, N::SBO_D4);
+                    umma_ts(tmem + C::C_D3, tmem + C::C_A3L + 8 * kq, bh, ID3, kq > 0);
+                    umma_ts(tmem + C::C_D3, tmem + C::C_A3H + 8 * kq, bl, ID3, 1);
+                    umma_ts(tmem + C::C_D3, tmem + C::C_A3H + 8 * kq, bh, ID3, 1);
+                }
+                umma_commit(mb);
+            }
+            mbar_wait(mb, phase); phase ^= 1;
+            tc_fence_after();
+            // ---- epilogue 3: [P'|Q'] = D3 + bias -> global, 32-column chunks through a swizzled
+            //      32 x 32 tile (16-byte chunk j of row r lives at chunk j ^ (r & 7)): conflict free
+            //      both ways, every store instruction writes four full 128-byte lines ------------------
+            {
+                const int c_end = write_q ? NP : 2 * H;
+                const int node_w0 = tile * TM + q * 32;
+#pragma unroll 1
+                for (int c0 = 32 * hf; c0 < c_end; c0 += 64) {
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb) {
+                        float v[16];
+                        tmem_ld16(lane_base + C::C_D3 + c0 + 16 * hb, v);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b = lds4(sBP + c0 + 16 * hb + 4 * i);
+                            st4(sOut + lane * 32 + (((4 * hb + i) ^ (lane & 7)) << 2),
+                                make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w));
+                        }
+                    }
+                    __syncwarp();
+                    const bool to_p = c0 < 2 * H;
+                    float* base = to_p ? P_out + (size_t)node_w0 * 2 * H + c0 : Q_out + (size_t)node_w0 * 3 * H + (c0 - 2 * H);
+                    const int ld = to_p ? 2 * H : 3 * H;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + (lane >> 3), j = lane & 7;
+                        if (node_w0 + r < n_nodes)
+                            st4_hint(base + (size_t)r * ld + 4 * j, lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2)), stream);
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            tc_bar_sync(BAR_EPI, ET);     // TMEM tiles and the store tiles are rewritten by the next tile
+            if (tile + (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY, ET + LT);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // input step on the tensor cores: H0 = tanh(Win.X + bin) per thread (K = F <= 4), [H0|X|0] split
 // into tensor memory, one projection GEMM, same epilogue.  (gnn/model.py:144-146)
 // ------------------------------------------------------------------------------------------
@@ -651,6 +879,24 @@ int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, flo
     const int cap = 2 * sms;     // 256 TMEM columns and ~95 KB of shared memory per CTA: two CTAs per SM
     const int grid = n_tiles < cap ? n_tiles : cap;
     input_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, P, Q, H_save);
+    return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+}
+
+int launch_node_mlp_tc32(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
+                         float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st) {
+    using C = TcMlpCfg<32>;
+    if (n_nodes == 0) return GNNSEG_OK;
+    const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
+    if (cudaFuncSetAttribute(node_mlp_kernel_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+        return GNNSEG_ECUDA;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+        return GNNSEG_ENODEVICE;
+    const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;        // two CTAs per SM
+    if (launch_pdl(node_mlp_kernel_tc<32>, grid, C::NT, C::SMEM_BYTES, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, P_out,
+                   Q_out, write_q, H_save) != cudaSuccess)
+        return GNNSEG_ECUDA;
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
