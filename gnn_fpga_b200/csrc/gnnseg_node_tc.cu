@@ -693,32 +693,53 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
             }
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
-            // ---- epilogue 3: [P'|Q'] = D3 + bias -> global, 32-column chunks through a swizzled
-            //      32 x 32 tile (16-byte chunk j of row r lives at chunk j ^ (r & 7)): conflict free
-            //      both ways, every store instruction writes four full 128-byte lines ------------------
+            // ---- epilogue 3: [P'|Q'] = D3 + bias -> global, through a swizzled 32 x 32 tile per warp
+            //      (16-byte chunk j of row r lives at chunk j ^ (r & 7)): conflict free both ways, every
+            //      store instruction writes full 128-byte lines.  The two warps of a TMEM lane quarter
+            //      share the 5 chunks of 32 columns as 2 + 2 + half of the last one each ----------------
             {
-                const int c_end = write_q ? NP : 2 * H;
                 const int node_w0 = tile * TM + q * 32;
-#pragma unroll 1
-                for (int c0 = 32 * hf; c0 < c_end; c0 += 64) {
+                auto stage16 = [&](const int col, const int jb) {          // 16 columns of D3 -> chunks jb..jb+3 of the tile
+                    float v[16];
+                    tmem_ld16(lane_base + C::C_D3 + col, v);
 #pragma unroll
-                    for (int hb = 0; hb < 2; ++hb) {
-                        float v[16];
-                        tmem_ld16(lane_base + C::C_D3 + c0 + 16 * hb, v);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 b = lds4(sBP + c0 + 16 * hb + 4 * i);
-                            st4(sOut + lane * 32 + (((4 * hb + i) ^ (lane & 7)) << 2),
-                                make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w));
-                        }
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b = lds4(sBP + col + 4 * i);
+                        st4(sOut + lane * 32 + (((jb + i) ^ (lane & 7)) << 2),
+                            make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w));
                     }
+                };
+                auto out_ptr = [&](const int col, int& ld) {               // column `col` of [P'|Q'] for the warp's first node
+                    const bool to_p = col < 2 * H;
+                    ld = to_p ? 2 * H : 3 * H;
+                    return to_p ? P_out + (size_t)node_w0 * 2 * H + col : Q_out + (size_t)node_w0 * 3 * H + (col - 2 * H);
+                };
+                const int n_full = write_q ? 2 : 1;                          // 32-column chunks hf, hf + 2 (P' only: chunk hf)
+#pragma unroll 1
+                for (int t = 0; t < n_full; ++t) {
+                    const int c0 = 32 * (hf + 2 * t);
+                    stage16(c0, 0);
+                    stage16(c0 + 16, 4);
                     __syncwarp();
-                    const bool to_p = c0 < 2 * H;
-                    float* base = to_p ? P_out + (size_t)node_w0 * 2 * H + c0 : Q_out + (size_t)node_w0 * 3 * H + (c0 - 2 * H);
-                    const int ld = to_p ? 2 * H : 3 * H;
+                    int ld;
+                    float* base = out_ptr(c0, ld);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = 4 * i + (lane >> 3), j = lane & 7;
+                        if (node_w0 + r < n_nodes)
+                            st4_hint(base + (size_t)r * ld + 4 * j, lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2)), stream);
+                    }
+                    __syncwarp();
+                }
+                if (write_q) {                                               // last chunk: 16 columns per warp
+                    const int c0 = 128 + 16 * hf;
+                    stage16(c0, 0);
+                    __syncwarp();
+                    int ld;
+                    float* base = out_ptr(c0, ld);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = 8 * i + (lane >> 2), j = lane & 3;
                         if (node_w0 + r < n_nodes)
                             st4_hint(base + (size_t)r * ld + 4 * j, lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2)), stream);
                     }
