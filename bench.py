@@ -55,7 +55,11 @@ def algorithmic_bytes(Nt, Et, F, h, n_iters):
     inp = Nt * 4 * (F + h)
     edge = Nt * 4 * D + Et * 8 + Et * 4
     node = Nt * 4 * D + Et * 4 + 2 * (Et * 8 + Nt * 4) + Nt * 4 * h
-    return dict(input=inp, edge=edge, node=node, forward=inp + n_iters * (edge + node) + edge)
+    # hidden_dim = 32 runs the node step as two kernels: the gather touches what §8(d) lists for the node
+    # step (its output is the h-wide h1 instead of H'), the MLP reads h1 and X and writes the new state.
+    # The forward figure stays §8(d)'s: the h1 round trip is traffic the split adds, not algorithmic bytes.
+    return dict(input=inp, edge=edge, node=node, node_gather=node, node_mlp=Nt * 4 * (h + F) + Nt * 4 * D,
+                forward=inp + n_iters * (edge + node) + edge)
 
 
 class ClockSampler:
@@ -300,7 +304,8 @@ def main():
         clocks = sampler.stop() if sampler else None
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(sum(step_ms))
-    launches_per_step = 2 + 1 + (cfg["n_iters"] + 1) + cfg["n_iters"]   # pack x2, input, edge x(it+1), node x it
+    # pack x2, input, edge x(it+1), node x it (two kernels per node step at hidden_dim = 32)
+    launches_per_step = 2 + 1 + (cfg["n_iters"] + 1) + cfg["n_iters"] * (2 if cfg["h"] == 32 else 1)
 
     # ---- per-kernel durations (same process, CUDA events around single launches) ----------
     L = _lib.lib()
@@ -312,31 +317,37 @@ def main():
     e = torch.empty(batch.n_slots, device=dev)
     e_in = torch.empty(batch.n_slots, device=dev)
     e_out = torch.empty(batch.n_slots, device=dev)
-    kt = {"input": [], "edge": [], "node": []}
+    split = h == 32                      # node step = gather kernel + tensor-core MLP kernel (include/gnnseg.h)
+    h1 = torch.empty(batch.n_nodes, h, device=dev) if split else None
+    kt = {}
 
     def timed(name, fn):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); rc = fn(); b.record()
         assert rc == 0, (name, rc)
-        kt[name].append((a, b))
+        kt.setdefault(name, []).append((a, b))
 
     st = _stream_ptr(dev)
     reps = max(3, min(args.steps, 20))
     for rep in range(reps + 1):
         if rep == 1:
-            kt = {"input": [], "edge": [], "node": []}      # drop the warm-up pass
+            kt.clear()                                      # drop the warm-up pass
         flush.zero_()
         timed("input", lambda: L.gnnseg_input_step(_ptr(blob), _ptr(batch.X), batch.n_nodes, F, h, _ptr(X4), _ptr(P), _ptr(Q[0]), st))
         cur = 0
         for i in range(it):
             qo = _ptr(Q[cur ^ 1]) if i + 1 < it else None
             timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, None, _ptr(e_in), _ptr(e_out), st))
-            timed("node", lambda: L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q[cur]), _ptr(e_in), _ptr(e_out), h, _ptr(P), qo, st))
+            if split:
+                timed("node_gather", lambda: L.gnnseg_node_gather_step(C.byref(batch.struct), _ptr(Q[cur]), _ptr(e_in), _ptr(e_out), h, _ptr(h1), h, st))
+                timed("node_mlp", lambda: L.gnnseg_node_mlp_step(_ptr(blob), _ptr(X4), _ptr(h1), h, batch.n_nodes, h, _ptr(P), qo, st))
+            else:
+                timed("node", lambda: L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q[cur]), _ptr(e_in), _ptr(e_out), h, _ptr(P), qo, st))
             cur ^= 1
         timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, _ptr(e), None, None, st))
     torch.cuda.synchronize(dev)
     kernel_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in kt.items() if v}
-    kernel_share = {k: kernel_ms[k] * {"input": 1, "edge": it + 1, "node": it}[k] for k in kernel_ms}
+    kernel_share = {k: kernel_ms[k] * {"input": 1, "edge": it + 1}.get(k, it) for k in kernel_ms}
 
     # ---- e2e: host SparseGraph tuples -> scores on the host ---------------------------------
     e2e = None
@@ -468,7 +479,7 @@ def main():
                            "unpipelined": {"value": all_edges * args.steps / e2e_sec, "ms_per_step": e2e_sec / args.steps * 1e3,
                                            "path": "model(graphs) then copy to pinned host memory, synchronised every step"}}
         if train:
-            n_k = 2 + 2 * it + 2 + 2 + 1 + 3 * (it + 1) + 1 + 1 + 1
+            n_k = 2 + 1 + (it + 1) + it * (2 if h == 32 else 1) + 2 + 1 + 3 * (it + 1) + 1 + 1 + 1
             line["train_step"] = {"ms": train_ms, "edges_per_sec": all_edges / (train_ms * 1e-3),
                                   "events_per_sec": all_events / (train_ms * 1e-3), "loss": train["loss"],
                                   "gpu_launches_per_step": n_k,

@@ -54,6 +54,8 @@ SIGNATURES = {
     "gnnseg_input_step": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_void_p]),
     "gnnseg_edge_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, _f32p, _f32p, _f32p, C.c_void_p]),
     "gnnseg_node_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, _f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_void_p]),
+    "gnnseg_node_gather_step": (C.c_int, [C.POINTER(GnnsegGraph), _f32p, _f32p, _f32p, C.c_int, _f32p, C.c_int, C.c_void_p]),
+    "gnnseg_node_mlp_step": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_void_p]),
     "gnnseg_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gnnseg_forward_train": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnnseg_backward": (C.c_int, [_f32p, C.POINTER(GnnsegParams), C.POINTER(GnnsegGraph), C.c_int, C.c_int, C.c_int, _f32p,

@@ -7,6 +7,8 @@ int input_step(const float*, const float*, int, int, int, float*, float*, float*
 int edge_step(const float*, const GnnsegGraph*, const float*, int, float*, float*, float*, cudaStream_t);
 int node_step(const float*, const GnnsegGraph*, const float*, const float*, const float*, const float*, int, float*, float*, int, float*, float*, cudaStream_t);
 int pack_weights(const GnnsegParams*, int, int, float*, cudaStream_t);
+int node_gather_step(const GnnsegGraph*, const float*, const float*, const float*, int, float*, int, cudaStream_t);
+int node_mlp_step(const float*, const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 int dense_to_edges(const float*, const float*, int, int, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
 size_t csr_workspace_bytes(int, int);
 int build_csr(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
@@ -221,6 +223,23 @@ int gnnseg_node_step(const float* blob, const GnnsegGraph* g, const float* X4, c
     if (g->n_slots > 0 && (!e_in || !e_out)) return GNNSEG_EINVAL;
     return gnnseg::node_step(blob, g, X4, Q_in, e_in, e_out, h, P_out, Q_out, Q_out != nullptr, nullptr, nullptr,
                              static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_node_gather_step(const GnnsegGraph* g, const float* Q_in, const float* e_in, const float* e_out, int h,
+                            float* h1, int ld_h1, void* stream) {
+    if (!gnnseg_supported(1, h)) return GNNSEG_EUNSUPPORTED;
+    if (!csr_ok(g) || ld_h1 < h || (ld_h1 & 3)) return GNNSEG_EINVAL;
+    if (g->n_nodes > 0 && (!Q_in || !h1)) return GNNSEG_EINVAL;
+    if (g->n_slots > 0 && (!e_in || !e_out)) return GNNSEG_EINVAL;
+    return gnnseg::node_gather_step(g, Q_in, e_in, e_out, h, h1, ld_h1, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_node_mlp_step(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, int h,
+                         float* P_out, float* Q_out, void* stream) {
+    if (!gnnseg_supported(1, h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || n_nodes < 0 || ld_h1 < h || (ld_h1 & 3)) return GNNSEG_EINVAL;
+    if (n_nodes > 0 && (!X4 || !h1 || !P_out)) return GNNSEG_EINVAL;
+    return gnnseg::node_mlp_step(blob, X4, h1, ld_h1, n_nodes, h, P_out, Q_out, static_cast<cudaStream_t>(stream));
 }
 
 int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int F, int h,

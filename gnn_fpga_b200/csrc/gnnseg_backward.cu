@@ -475,12 +475,7 @@ __global__ void finalize_grads_kernel(const float* __restrict__ partE, const int
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static inline int bwd_sm_count() {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    return n;
-}
+static inline int bwd_sm_count() { return cached_sm_count(); }
 static inline int bwd_check() { return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA; }
 
 struct TrainState {          // device arrays saved by the training forward + backward scratch
@@ -524,10 +519,10 @@ static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, c
     auto kI2 = dense_bwd_kernel<H, 2, false>;
     auto kF5 = dense_bwd_kernel<H, 5, true>;
     auto kI5 = dense_bwd_kernel<H, 5, false>;
-    if (cudaFuncSetAttribute(kF2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(kI2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(kF5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(kI5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess)
+    if (!ensure_dynamic_smem<dense_bwd_kernel<H, 2, true>>((int)C::SMEM_BYTES) ||
+        !ensure_dynamic_smem<dense_bwd_kernel<H, 2, false>>((int)C::SMEM_BYTES) ||
+        !ensure_dynamic_smem<dense_bwd_kernel<H, 5, true>>((int)C::SMEM_BYTES) ||
+        !ensure_dynamic_smem<dense_bwd_kernel<H, 5, false>>((int)C::SMEM_BYTES))
         return GNNSEG_ECUDA;
     // the dense kernel's partial holds slots (W4/B4 or WIN/BIN) that some launches never write
     zero_kernel<<<64, 256, 0, st>>>(s.partN, (size_t)gridD * NodePart<H>::SIZE);

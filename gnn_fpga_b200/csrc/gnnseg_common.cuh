@@ -105,6 +105,47 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), const int grid, const in
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// Immutable facts about the device and the kernels, looked up once per device instead of on every
+// launch (the host-side launch path is on the critical path of the pipelined end-to-end call).
+// Idempotent writes of the same values: safe without a lock.
+constexpr int MAX_DEVICES = 64;
+inline int cached_sm_count() {
+    static int cache[MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return -1;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) return -1;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+// opt the kernel in to `bytes` of dynamic shared memory (once per device)
+template <auto Kern>
+inline bool ensure_dynamic_smem(const int bytes) {
+    static bool done[MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return false;
+    if (!done[dev]) {
+        if (cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+        done[dev] = true;
+    }
+    return true;
+}
+// resident CTAs per SM of the kernel at this launch shape (once per device)
+template <auto Kern>
+inline int cached_occupancy(const int threads, const size_t smem) {
+    static int cache[MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return -1;
+    if (cache[dev] == 0) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, Kern, threads, smem) != cudaSuccess || occ < 1) return -1;
+        cache[dev] = occ;
+    }
+    return cache[dev];
+}
+
 // tanh(x) = sign(x) * (1 - 2 / (exp(2|x|) + 1)) with the hardware ex2 / rcp approximations:
 // 2 MUFU + 5 ALU instructions, branch free (tanhf is ~20 instructions over two divergent paths).
 // Absolute error <= ~2e-7 over the whole range (the result saturates to +-1 for |x| > 44, NaN

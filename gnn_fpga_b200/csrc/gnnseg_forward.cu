@@ -701,20 +701,13 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __
 // ------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------
-static inline int sm_count() {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    return n;
-}
+static inline int sm_count() { return cached_sm_count(); }
 
-template <typename Kern>
-static inline int persistent_grid(Kern kern, int threads, size_t smem, int n_tiles, int* grid) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return GNNSEG_ECUDA;
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1)
-        return GNNSEG_ECUDA;
+template <auto Kern>
+static inline int persistent_grid(int threads, size_t smem, int n_tiles, int* grid) {
+    if (!ensure_dynamic_smem<Kern>((int)smem)) return GNNSEG_ECUDA;
+    const int occ = cached_occupancy<Kern>(threads, smem);
+    if (occ < 1) return GNNSEG_ECUDA;
     const int sms = sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int cap = sms * occ;
@@ -748,7 +741,7 @@ static int launch_input(const float* blob, const float* X, int n_nodes, int F, f
     }
     const int n_tiles = (n_nodes + C::TN - 1) / C::TN;
     int grid = 0;
-    const int rc = persistent_grid(input_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);
+    const int rc = persistent_grid<input_kernel<H>>(C::NT, C::SMEM_BYTES, n_tiles, &grid);
     if (rc) return rc;
     input_kernel<H><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, P, Q, H_save);
     return check_launch();
@@ -762,9 +755,8 @@ static int launch_edge(const float* blob, const GnnsegGraph* g, const float* P, 
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int warps_needed = (g->n_slots + 31) / 32;
     int grid = (warps_needed + 7) / 8;
-    int occ = 0;               // resident CTAs per SM: one full wave, the warps stride over the slots
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, edge_kernel<H>, 256, 0) != cudaSuccess || occ < 1)
-        return GNNSEG_ECUDA;
+    const int occ = cached_occupancy<edge_kernel<H>>(256, 0);   // resident CTAs per SM: one full wave, the warps stride over the slots
+    if (occ < 1) return GNNSEG_ECUDA;
     const int cap = sms * occ;
     if (grid > cap) grid = cap;
     if (launch_pdl(edge_kernel<H>, grid, 256, 0, st, use_pdl(g->n_slots), blob, P, g->src, g->dst, g->in_pos, g->out_pos, g->n_slots,
@@ -780,6 +772,20 @@ int launch_node_mlp_tc32(const float* blob, const float* X4, const float* h1, in
                          float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05, MLP only)
 
 template <int H>
+static int launch_gather(const GnnsegGraph* g, const float* Q_in, const float* e_in, const float* e_out, float* h1_out,
+                         int ld_out, float* h1_save, cudaStream_t st) {
+    if (g->n_nodes == 0) return GNNSEG_OK;
+    const int sms = sm_count();
+    if (sms < 1) return GNNSEG_ENODEVICE;
+    long long blocks = ((long long)g->n_nodes * (H / 4) + 255) / 256;
+    if (blocks > sms * 8) blocks = sms * 8;                      // one resident wave of 64 warps per SM
+    if (launch_pdl(node_gather_kernel<H>, (int)blocks, 256, 0, st, use_pdl(g->n_slots), *g, Q_in, e_in, e_out, h1_out, ld_out,
+                   h1_save) != cudaSuccess)
+        return GNNSEG_ECUDA;
+    return check_launch();
+}
+
+template <int H>
 static int launch_node(const float* blob, const GnnsegGraph* g, const float* X4, const float* Q_in, const float* e_in,
                        const float* e_out, float* P_out, float* Q_out, int write_q, float* h1_save, float* H_save,
                        cudaStream_t st) {
@@ -792,19 +798,14 @@ static int launch_node(const float* blob, const GnnsegGraph* g, const float* X4,
         const char* impl = getenv("GNNSEG_NODE_IMPL");
         if (impl && impl[0] == 'f') return launch_node_tc32(blob, g, X4, Q_in, e_in, e_out, P_out, Q_out, write_q, h1_save, H_save, st);
         if (!impl || impl[0] != 'm') {
-            const int sms = sm_count();
-            if (sms < 1) return GNNSEG_ENODEVICE;
-            long long blocks = ((long long)g->n_nodes * (H / 4) + 255) / 256;
-            if (blocks > sms * 8) blocks = sms * 8;
-            if (launch_pdl(node_gather_kernel<H>, (int)blocks, 256, 0, st, use_pdl(g->n_slots), *g, Q_in, e_in, e_out, P_out, 2 * H,
-                           h1_save) != cudaSuccess)
-                return GNNSEG_ECUDA;
+            const int rc = launch_gather<H>(g, Q_in, e_in, e_out, P_out, 2 * H, h1_save, st);
+            if (rc) return rc;
             return launch_node_mlp_tc32(blob, X4, P_out, 2 * H, g->n_nodes, P_out, Q_out, write_q, H_save, use_pdl(g->n_slots), st);
         }
     }
     const int n_tiles = (g->n_nodes + C::TN - 1) / C::TN;
     int grid = 0;
-    const int rc = persistent_grid(node_kernel<H>, C::NT, C::SMEM_BYTES, n_tiles, &grid);
+    const int rc = persistent_grid<node_kernel<H>>(C::NT, C::SMEM_BYTES, n_tiles, &grid);
     if (rc) return rc;
     if (launch_pdl(node_kernel<H>, grid, C::NT, C::SMEM_BYTES, st, use_pdl(g->n_slots), blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out,
                    Q_out, write_q, h1_save, H_save) != cudaSuccess)
@@ -834,6 +835,15 @@ int node_step(const float* blob, const GnnsegGraph* g, const float* X4, const fl
               const float* e_out, int h, float* P_out, float* Q_out, int write_q, float* h1_save, float* H_save,
               cudaStream_t st) {
     GNNSEG_DISPATCH_H(h, launch_node<HH>(blob, g, X4, Q_in, e_in, e_out, P_out, Q_out, write_q, h1_save, H_save, st));
+}
+int node_gather_step(const GnnsegGraph* g, const float* Q_in, const float* e_in, const float* e_out, int h, float* h1_out,
+                     int ld_out, cudaStream_t st) {
+    GNNSEG_DISPATCH_H(h, launch_gather<HH>(g, Q_in, e_in, e_out, h1_out, ld_out, nullptr, st));
+}
+int node_mlp_step(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, int h, float* P_out,
+                  float* Q_out, cudaStream_t st) {
+    if (h != 32) return GNNSEG_EUNSUPPORTED;     // the other widths run the fused generic kernel (gnnseg_node_step)
+    return launch_node_mlp_tc32(blob, X4, h1, ld_h1, n_nodes, P_out, Q_out, Q_out != nullptr, nullptr, false, st);
 }
 int pack_weights(const GnnsegParams* p, int F, int h, float* blob, cudaStream_t st) {
     const int total = blob_total(h);

@@ -891,12 +891,9 @@ int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, flo
     using C = TcInCfg<32>;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + TcCfg<32>::TM - 1) / TcCfg<32>::TM;
-    if (cudaFuncSetAttribute(input_kernel_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
-        return GNNSEG_ECUDA;
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
-        return GNNSEG_ENODEVICE;
+    if (!ensure_dynamic_smem<input_kernel_tc<32>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
+    const int sms = cached_sm_count();
+    if (sms < 1) return GNNSEG_ENODEVICE;
     const int cap = 2 * sms;     // 256 TMEM columns and ~95 KB of shared memory per CTA: two CTAs per SM
     const int grid = n_tiles < cap ? n_tiles : cap;
     input_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, P, Q, H_save);
@@ -908,12 +905,9 @@ int launch_node_mlp_tc32(const float* blob, const float* X4, const float* h1, in
     using C = TcMlpCfg<32>;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
-    if (cudaFuncSetAttribute(node_mlp_kernel_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
-        return GNNSEG_ECUDA;
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
-        return GNNSEG_ENODEVICE;
+    if (!ensure_dynamic_smem<node_mlp_kernel_tc<32>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
+    const int sms = cached_sm_count();
+    if (sms < 1) return GNNSEG_ENODEVICE;
     const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;        // two CTAs per SM
     if (launch_pdl(node_mlp_kernel_tc<32>, grid, C::NT, C::SMEM_BYTES, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, P_out,
                    Q_out, write_q, H_save) != cudaSuccess)
@@ -927,12 +921,9 @@ int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, c
     using C = TcCfg<32>;
     if (g->n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (g->n_nodes + C::TM - 1) / C::TM;
-    if (cudaFuncSetAttribute(node_kernel_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
-        return GNNSEG_ECUDA;
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
-        return GNNSEG_ENODEVICE;
+    if (!ensure_dynamic_smem<node_kernel_tc<32>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
+    const int sms = cached_sm_count();
+    if (sms < 1) return GNNSEG_ENODEVICE;
     const int grid = n_tiles < sms ? n_tiles : sms;
     if (launch_pdl(node_kernel_tc<32>, grid, C::NT, C::SMEM_BYTES, st, use_pdl(g->n_slots), blob, *g, X4, Q_in, e_in, e_out, n_tiles, P_out,
                    Q_out, write_q, h1_save, H_save) != cudaSuccess)

@@ -12,7 +12,8 @@
  *   - Every `stream` argument is a cudaStream_t passed as void*.
  *   - Pointers are DEVICE pointers unless the name ends in `_host`.
  *   - The caller owns every buffer, including workspaces.  The library never allocates or
- *     frees device memory, never synchronises, and keeps no mutable global state, so every
+ *     frees device memory, never synchronises, and keeps no mutable global state (only a per-device
+ *     cache of immutable facts: SM count, kernel occupancy, shared-memory opt-in), so every
  *     device entry point can be captured in a CUDA graph.
  *   - Return value: GNNSEG_OK (0) or a negative GNNSEG_E* code; gnnseg_strerror() names it.
  *     Data errors that can only be seen on the device (bad incidence matrices) are written
@@ -171,6 +172,23 @@ int gnnseg_edge_step(const float* blob, const GnnsegGraph* graph, const float* P
 int gnnseg_node_step(const float* blob, const GnnsegGraph* graph, const float* X4,
                      const float* Q_in, const float* e_in, const float* e_out, int h,
                      float* P_out, float* Q_out, void* stream);
+
+/*
+ * The two halves of gnnseg_node_step on their own.  hidden_dim = 32 runs the node step as these two
+ * kernels (a gather rate on B200 is set by the number of resident warps, which a kernel that also
+ * hosts the tensor-core epilogue warps cannot provide):
+ *   gnnseg_node_gather_step : h1[n] = tanh(Qs[n] + sum_in e Qi[src] + sum_out e Qo[dst])   gnn/model.py:114-122
+ *                             own term, in-slots, out-slots in ascending slot order; no atomics.
+ *                             h1 rows are written with row stride ld_h1 floats (>= h, multiple of 4).
+ *   gnnseg_node_mlp_step    : H' = tanh(W4.h1 + b4), projections of [H' | X] -> P_out, Q_out (nullable)
+ *                             gnn/model.py:122-125,154.  hidden_dim = 32 only (GNNSEG_EUNSUPPORTED
+ *                             otherwise).  h1 may live inside P_out (row n of h1 in the first h floats
+ *                             of row n of P_out, ld_h1 = 2h): a row of P' is written after its h1 was read.
+ */
+int gnnseg_node_gather_step(const GnnsegGraph* graph, const float* Q_in, const float* e_in,
+                            const float* e_out, int h, float* h1, int ld_h1, void* stream);
+int gnnseg_node_mlp_step(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes,
+                         int h, float* P_out, float* Q_out, void* stream);
 
 /* ---- training: replaces loss.backward() / optimizer.step() of Estimator.training_step,
  *      gnn/estimator.py:49-60 ------------------------------------------------------------- */

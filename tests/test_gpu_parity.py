@@ -228,6 +228,83 @@ def test_each_kernel_against_oracle(name, cuda_device):
     assert torch.equal(P3, P2)
 
 
+@pytest.mark.parametrize("name", ["acts_ragged_h32_it4", "acts_h64_it6", "toy2d_h16_it3", "half_edges_h8_it2"])
+def test_node_step_halves_against_oracle(name, cuda_device):
+    """gnnseg_node_gather_step (ordered CSR sum + tanh, every width) and gnnseg_node_mlp_step
+    (tcgen05 layer 2 + projections, hidden_dim = 32) one at a time against the oracle, with h1 in
+    its own buffer and aliased into the rows of P_out the way gnnseg_node_step passes it."""
+    from gnn_fpga_b200.graph import _ptr, _stream_ptr
+    rec = load_case(name)
+    model, batch, L = _steps_setup(rec, cuda_device)
+    p = O.apply_masks(rec["params"], rec["masks_e"], rec["masks_n"])
+    h, F, n = rec["h"], rec["F"], batch.n_nodes
+    blob = model.pack_weights()
+    st = _stream_ptr(cuda_device)
+    src, dst, Xh = batch.src.cpu().long(), batch.dst.cpu().long(), batch.X.cpu()
+    H0 = O.sparse_input(p, Xh)
+    _, Qref = O.projections(p, H0)
+    e_ref = O.sparse_edge(p, H0, src, dst)
+    n_in, n_out = int(batch.in_ptr[-1]), int(batch.out_ptr[-1])
+    e_dev = e_ref.to(cuda_device)
+    e_in = e_dev[batch.in_eid[:n_in].long()].contiguous()
+    e_out = e_dev[batch.out_eid[:n_out].long()].contiguous()
+    Q_in = Qref.to(cuda_device).contiguous()
+    # oracle h1 = tanh(W3.[mi; mo; H] + b3), the first layer of the node network (gnn/model.py:114-122)
+    real_i, real_o = dst >= 0, src >= 0
+    mi = torch.zeros_like(H0).index_add_(0, dst[real_i], (e_ref[:, None] * O._gather(H0, src))[real_i])
+    mo = torch.zeros_like(H0).index_add_(0, src[real_o], (e_ref[:, None] * O._gather(H0, dst))[real_o])
+    h1_ref = torch.tanh(O._lin(torch.cat([mi, mo, H0], dim=1), p, 3))
+    for ld in (h, 2 * h):
+        h1 = torch.full((n, ld), 9.0, device=cuda_device)
+        assert L.gnnseg_node_gather_step(C.byref(batch.struct), _ptr(Q_in), _ptr(e_in), _ptr(e_out), h, _ptr(h1), ld, st) == 0
+        assert torch.allclose(h1.cpu()[:, :h], h1_ref, rtol=1e-5, atol=2e-6)
+        assert torch.all(h1[:, h:] == 9.0)                      # nothing written beyond the h columns
+    assert L.gnnseg_node_gather_step(C.byref(batch.struct), _ptr(Q_in), _ptr(e_in), _ptr(e_out), h, _ptr(h1), h - 1, st) == -1
+    X4 = torch.zeros(n, 4, device=cuda_device)
+    X4[:, :F] = batch.X
+    P2, Q2 = torch.zeros(n, 2 * h, device=cuda_device), torch.zeros(n, 3 * h, device=cuda_device)
+    h1d = h1_ref.to(cuda_device).contiguous()
+    rc = L.gnnseg_node_mlp_step(_ptr(blob), _ptr(X4), _ptr(h1d), h, n, h, _ptr(P2), _ptr(Q2), st)
+    if h != 32:
+        assert rc == -2
+        return
+    assert rc == 0
+    H1 = torch.cat([torch.tanh(O._lin(h1_ref, p, 4)), Xh], dim=1)
+    P1ref, Q1ref = O.projections(p, H1)
+    assert torch.allclose(P2.cpu(), P1ref, rtol=1e-5, atol=3e-6)
+    assert torch.allclose(Q2.cpu(), Q1ref, rtol=1e-5, atol=3e-6)
+    # h1 inside the rows of P_out (stride 2h): same result to the bit
+    P3, Q3 = torch.zeros_like(P2), torch.zeros_like(Q2)
+    P3[:, :h] = h1d
+    assert L.gnnseg_node_mlp_step(_ptr(blob), _ptr(X4), _ptr(P3), 2 * h, n, h, _ptr(P3), _ptr(Q3), st) == 0
+    assert torch.equal(P3, P2) and torch.equal(Q3, Q2)
+
+
+def test_fused_and_split_node_step_agree(cuda_device):
+    """hidden_dim = 32: gnnseg_node_step (gather kernel + tcgen05 MLP kernel) and the two halves
+    called one after the other give the same bits."""
+    from gnn_fpga_b200.graph import _ptr, _stream_ptr
+    rec = load_case("acts_ragged_h32_it4")
+    model, batch, L = _steps_setup(rec, cuda_device)
+    h, F, n = rec["h"], rec["F"], batch.n_nodes
+    blob = model.pack_weights()
+    st = _stream_ptr(cuda_device)
+    g = torch.Generator(cuda_device).manual_seed(1)
+    X4 = torch.zeros(n, 4, device=cuda_device)
+    X4[:, :F] = batch.X
+    Q_in = torch.randn(n, 3 * h, device=cuda_device, generator=g) * 0.3
+    e_in = torch.rand(batch.n_slots, device=cuda_device, generator=g)
+    e_out = torch.rand(batch.n_slots, device=cuda_device, generator=g)
+    Pa, Qa = torch.zeros(n, 2 * h, device=cuda_device), torch.zeros(n, 3 * h, device=cuda_device)
+    assert L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q_in), _ptr(e_in), _ptr(e_out), h,
+                              _ptr(Pa), _ptr(Qa), st) == 0
+    h1 = torch.zeros(n, h, device=cuda_device)
+    Pb, Qb = torch.zeros_like(Pa), torch.zeros_like(Qa)
+    assert L.gnnseg_node_gather_step(C.byref(batch.struct), _ptr(Q_in), _ptr(e_in), _ptr(e_out), h, _ptr(h1), h, st) == 0
+    assert L.gnnseg_node_mlp_step(_ptr(blob), _ptr(X4), _ptr(h1), h, n, h, _ptr(Pb), _ptr(Qb), st) == 0
+    assert torch.equal(Pa, Pb) and torch.equal(Qa, Qb)
+
+
 def test_deterministic_and_graph_replay(cuda_device):
     """Same bits run to run, with and without the CUDA graph, and after rebuilding the batch."""
     from gnn_fpga_b200 import DeviceGraphBatch
