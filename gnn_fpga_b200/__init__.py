@@ -6,6 +6,7 @@ Public surface mirrors the reference modules gnn/model.py, gnn/graph.py:
 plus the device batch (DeviceGraphBatch) that replaces the dense incidence tensors.
 """
 from .graph import (Graph, SparseGraph, make_sparse_graph, graph_from_sparse, save_graph,  # noqa: F401
-                    save_graphs, load_graph, load_graphs, DeviceGraphBatch, pack_sparse_batch_host)
+                    save_graphs, load_graph, load_graphs, load_graphs_mapped, NpzGraphFile, DeviceGraphBatch,
+                    pack_sparse_batch_host, pack_npz_batch_host)
 from .model import MaskedLinear, EdgeNetwork, NodeNetwork, SegmentClassifier  # noqa: F401
 from ._lib import GnnsegError, LIB_PATH  # noqa: F401

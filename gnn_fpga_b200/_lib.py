@@ -12,7 +12,7 @@ LIB_PATH = os.path.abspath(os.environ["GNNSEG_LIB"]) if os.environ.get("GNNSEG_L
 
 OK = 0
 ABI_VERSION = 2
-ERRORS = {-1: "EINVAL", -2: "EUNSUPPORTED", -3: "EWORKSPACE", -4: "ECUDA", -5: "ENODEVICE"}
+ERRORS = {-1: "EINVAL", -2: "EUNSUPPORTED", -3: "EWORKSPACE", -4: "ECUDA", -5: "ENODEVICE", -6: "EIO", -7: "EFORMAT"}
 BAD_VALUE = 1
 BAD_HYPEREDGE = 2
 
@@ -29,6 +29,13 @@ class GnnsegParams(C.Structure):
 class GnnsegGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "w_in", "b_in", "w_e1", "b_e1", "w_e2", "b_e2", "w_n1", "b_n1", "w_n2", "b_n2")]
+
+
+class GnnsegNpzGraph(C.Structure):
+    _fields_ = [("handle", C.c_void_p), ("X", C.c_void_p), ("n_nodes", C.c_int64), ("n_features", C.c_int32),
+                ("Ri_rows", C.c_void_p), ("Ri_cols", C.c_void_p), ("n_in", C.c_int64),
+                ("Ro_rows", C.c_void_p), ("Ro_cols", C.c_void_p), ("n_out", C.c_int64),
+                ("y", C.c_void_p), ("n_y", C.c_int64)]
 
 
 class GnnsegGraph(C.Structure):
@@ -64,6 +71,10 @@ SIGNATURES = {
     "gnnseg_l1_penalty": (C.c_int, [C.POINTER(GnnsegParams), C.c_int, C.c_int, C.c_float, _f32p, C.POINTER(GnnsegGrads), C.c_void_p]),
     "gnnseg_adam_step": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_void_p]),
+    "gnnseg_npz_open_graph_host": (C.c_int, [C.c_char_p, C.POINTER(GnnsegNpzGraph)]),
+    "gnnseg_npz_close_graph_host": (C.c_int, [C.POINTER(GnnsegNpzGraph)]),
+    "gnnseg_npz_open_batch_host": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "gnnseg_npz_close_batch_host": (C.c_int, [C.c_int, C.c_void_p]),
     "gnnseg_pack_sparse_batch_host": (C.c_int, [
         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

@@ -134,6 +134,8 @@ const char* gnnseg_strerror(int code) {
         case GNNSEG_EWORKSPACE:   return "workspace too small";
         case GNNSEG_ECUDA:        return "CUDA runtime error";
         case GNNSEG_ENODEVICE:    return "no CUDA device";
+        case GNNSEG_EIO:          return "file cannot be opened or mapped";
+        case GNNSEG_EFORMAT:      return "not an .npz graph file (np.savez of X, Ri_rows, Ri_cols, Ro_rows, Ro_cols, y)";
         default:                  return "unknown gnnseg error";
     }
 }

@@ -64,6 +64,67 @@ def load_graphs(filenames, graph_type=Graph):
     return [load_graph(f, graph_type) for f in filenames]
 
 
+class _NpzMapping:
+    """Owns one gnnseg_npz_open_graph_host mapping; unmapped when the last array viewing it dies."""
+
+    def __init__(self, filename):
+        import ctypes as C
+        self.g = _lib.GnnsegNpzGraph()
+        rc = _lib.lib().gnnseg_npz_open_graph_host(str(filename).encode(), C.byref(self.g))
+        if rc != 0:
+            self.g = None
+            _lib.check(rc, "gnnseg_npz_open_graph_host(%s)" % filename)
+
+    def __del__(self):
+        try:
+            if self.g is not None:
+                import ctypes as C
+                _lib.lib().gnnseg_npz_close_graph_host(C.byref(self.g))
+                self.g = None
+        except Exception:
+            pass
+
+
+class NpzGraphFile:
+    """One graph file of the reference's on-disk format (gnn/graph.py:179-194), memory mapped by the
+    library (gnnseg_npz_open_graph_host).  `.graph` is a SparseGraph whose arrays are zero-copy,
+    read-only views of the mapping; every array keeps the mapping alive, so the tuple (or any slice of
+    its arrays) may outlive this object.  They go straight into pack_sparse_batch_host /
+    SegmentClassifier(...)."""
+
+    def __init__(self, filename):
+        import ctypes as C
+        m = _NpzMapping(filename)
+        g = m.g
+
+        def view(ptr, ctype, shape):
+            n = int(np.prod(shape))
+            if n == 0 or not ptr:
+                return np.zeros(shape, dtype=np.dtype(ctype))
+            buf = (ctype * n).from_address(ptr)
+            buf._gnnseg_mapping = m                       # the array's base chain holds the mapping
+            a = np.ctypeslib.as_array(buf).reshape(shape)
+            a.flags.writeable = False
+            return a
+
+        self.graph = SparseGraph(
+            view(g.X, C.c_float, (g.n_nodes, g.n_features)),
+            view(g.Ri_rows, C.c_int64, (g.n_in,)), view(g.Ri_cols, C.c_int64, (g.n_in,)),
+            view(g.Ro_rows, C.c_int64, (g.n_out,)), view(g.Ro_cols, C.c_int64, (g.n_out,)),
+            view(g.y, C.c_float, (g.n_y,)))
+
+    def close(self):
+        """Drop this object's views (the file is unmapped once no array refers to it any more)."""
+        self.graph = None
+
+
+def load_graphs_mapped(filenames):
+    """load_graphs(filenames, SparseGraph) (gnn/graph.py:193-194) without np.load: every file is
+    memory mapped and parsed by the library; the result is a list of SparseGraph tuples viewing the
+    mappings (read-only arrays; a mapping lives as long as any array that views it)."""
+    return [NpzGraphFile(f).graph for f in filenames]
+
+
 # ---------------------------------------------------------------------------------------
 # device batch
 # ---------------------------------------------------------------------------------------
@@ -166,6 +227,14 @@ class DeviceGraphBatch:
         return cls(X.reshape(B * N, F), src, dst, B, E, n_nodes_per_event=[N] * B)
 
     @classmethod
+    def from_graph_files(cls, filenames, device="cuda", pinned=None, n_threads=0):
+        """A batch straight from graph files in the reference's NPZ format (gnn/graph.py:179-194):
+        mapped, parsed and packed by the library, then as from_sparse_graphs."""
+        dev = _require_cuda(torch.device(device))
+        host = pack_npz_batch_host(list(filenames), pinned=pinned, n_threads=n_threads)
+        return cls.from_packed_host(host, dev, pinned=pinned)
+
+    @classmethod
     def from_sparse_graphs(cls, graphs, device="cuda", pinned=None, n_threads=0):
         """List of host SparseGraph tuples -> device batch, padded exactly as
         graph_from_sparse + merge_graphs would pad it (e_max = max len(Ri_rows); node rows
@@ -216,6 +285,59 @@ class DeviceGraphBatch:
 
     def scores_2d(self):
         return self.scores.view(self.B, self.e_max)
+
+
+def pack_npz_batch_host(filenames, pinned=None, n_threads=0):
+    """Graph files (the reference's NPZ format) -> packed host batch, without building a Python
+    object per array: the library maps and parses the files (gnnseg_npz_open_batch_host), the packer
+    reads the mappings (gnnseg_pack_sparse_batch_host), the files are unmapped again.  Returns what
+    pack_sparse_batch_host returns."""
+    import ctypes as C
+    if n_threads <= 0:
+        import os
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        n_threads = max(1, (os.cpu_count() or 4) // local_world - 2)
+    L = _lib.lib()
+    B = len(filenames)
+    if B == 0:
+        raise ValueError("empty batch")
+    paths = (C.c_char_p * B)(*[str(f).encode() for f in filenames])
+    gs = (_lib.GnnsegNpzGraph * B)()
+    rc = L.gnnseg_npz_open_batch_host(B, C.addressof(paths), C.addressof(gs), n_threads)
+    _lib.check(rc, "gnnseg_npz_open_batch_host")
+    try:
+        rec = np.frombuffer(gs, dtype=np.dtype([(n, "<u8" if t is C.c_void_p else ("<i8" if t is C.c_int64 else "<i4"))
+                                                for n, t in _lib.GnnsegNpzGraph._fields_], align=True))
+        F = int(rec["n_features"][0])
+        if not np.all(rec["n_features"] == F):
+            raise ValueError("graph files with different numbers of features in one batch")
+        n_nodes = np.ascontiguousarray(rec["n_nodes"])
+        n_in, n_out = np.ascontiguousarray(rec["n_in"]), np.ascontiguousarray(rec["n_out"])
+        e_max, nt = int(n_in.max()), int(n_nodes.sum())
+        can_pin = torch.cuda.is_available()
+        if pinned is not None:
+            # a reusable staging dict (see SegmentClassifier._grow_pinned): grown in place when too small
+            if pinned.get("X") is None or pinned["X"].shape[0] < nt or pinned["X"].shape[1] != F or pinned["src"].numel() < B * e_max:
+                cap_n, cap_m = int(nt * 1.25) + 1, int(B * e_max * 1.25) + 1
+                pinned["X"] = torch.empty((cap_n, F), dtype=torch.float32, pin_memory=can_pin)
+                pinned["src"] = torch.empty(cap_m, dtype=torch.int32, pin_memory=can_pin)
+                pinned["dst"] = torch.empty(cap_m, dtype=torch.int32, pin_memory=can_pin)
+            Xo, src, dst = pinned["X"][:nt], pinned["src"][:B * e_max], pinned["dst"][:B * e_max]
+        else:
+            Xo = torch.empty((nt, F), dtype=torch.float32, pin_memory=can_pin)
+            src = torch.empty(B * e_max, dtype=torch.int32, pin_memory=can_pin)
+            dst = torch.empty(B * e_max, dtype=torch.int32, pin_memory=can_pin)
+        cols = [np.ascontiguousarray(rec[k]) for k in ("X", "Ri_rows", "Ri_cols", "Ro_rows", "Ro_cols")]
+        ptr = lambda a: a.__array_interface__["data"][0]
+        rc = L.gnnseg_pack_sparse_batch_host(B, F, e_max, ptr(cols[0]), ptr(n_nodes), ptr(cols[1]), ptr(cols[2]), ptr(cols[3]),
+                                             ptr(cols[4]), ptr(n_in), ptr(n_out), Xo.data_ptr(), src.data_ptr(), dst.data_ptr(),
+                                             n_threads)
+    finally:
+        L.gnnseg_npz_close_batch_host(B, C.addressof(gs))
+    if rc == -1:
+        raise ValueError("graph file index out of range (row >= n_nodes or col >= max len(Ri_rows))")
+    _lib.check(rc, "gnnseg_pack_sparse_batch_host")
+    return {"X": Xo, "src": src, "dst": dst, "e_max": e_max, "n_nodes": n_nodes.tolist()}
 
 
 def pack_sparse_batch_host(graphs, pinned=None, n_threads=0):

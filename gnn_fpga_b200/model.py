@@ -12,6 +12,7 @@ estimator_maskedlinear.py:85-101 reach into them.  Their own `forward` methods a
 implemented: the fused path never calls them and there is no CPU fallback.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -51,6 +52,11 @@ class MaskedLinear(nn.Linear):
 
     def forward(self, x):
         raise _lib.GnnsegError("MaskedLinear.forward is not a standalone op here: call SegmentClassifier(...)")
+
+
+def _is_file_batch(inputs):
+    """A batch given as graph file names (the reference's NPZ format) instead of tuples."""
+    return isinstance(inputs, (list, tuple)) and len(inputs) > 0 and isinstance(inputs[0], (str, os.PathLike))
 
 
 def _check_activation(act):
@@ -102,7 +108,9 @@ class SegmentClassifier(nn.Module):
     * `[X, Ri, Ro]`: dense fp32 CUDA tensors (B,N,F), (B,N,E), (B,N,E) -> (B,E) scores, the
       reference call;
     * a `DeviceGraphBatch` -> (B, e_max) scores (replayed from a CUDA graph on repeat calls);
-    * a list of host `SparseGraph` tuples -> (B, e_max) scores, padded as merge_graphs pads.
+    * a list of host `SparseGraph` tuples -> (B, e_max) scores, padded as merge_graphs pads;
+    * a list of graph file names (the NPZ format of gnn/graph.py:179-194) -> the same, the files
+      being mapped, parsed and packed by the library (no np.load).
     """
 
     def __init__(self, input_dim=2, hidden_dim=8, n_iters=3, hidden_activation=nn.Tanh,
@@ -231,20 +239,25 @@ class SegmentClassifier(nn.Module):
         a yielded tensor is reused `depth` batches later."""
         from collections import deque
         from concurrent.futures import ThreadPoolExecutor
-        from .graph import _require_cuda, pack_sparse_batch_host
+        from .graph import _require_cuda, pack_npz_batch_host, pack_sparse_batch_host
         dev = _require_cuda(self._device())
         LOOK = 1                                                   # batches being packed ahead (the packer is GIL/DRAM bound: one is enough)
         n_slots = depth + LOOK
         slots = [{"pinned": None, "out": None, "done": None, "view": None} for _ in range(n_slots)]
         pending = deque()
         was_graph, self.use_cuda_graph = self.use_cuda_graph, False    # one-shot batches: plain launches
-        import os
         # leave two cores to the launching thread and the driver: an oversubscribed OpenMP team
         # (its threads spin between batches) makes the per-batch time jump by 2x
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))     # ranks sharing this host (torchrun)
         pack_threads = max(1, (os.cpu_count() or 4) // local_world - 2)
 
         def pack(graphs, slot):
+            if _is_file_batch(graphs):                                   # graph files: mapped, parsed and packed by the library
+                p = slot["pinned"] or {"X": None, "src": None, "dst": None, "event": None}
+                if p["event"] is not None:
+                    p["event"].synchronize()                             # the slot's last H2D has left the buffers
+                slot["pinned"] = p
+                return pack_npz_batch_host([os.fspath(f) for f in graphs], pinned=p, n_threads=pack_threads)
             slot["pinned"] = self._grow_pinned(slot["pinned"], graphs)   # waits for the slot's last H2D
             return pack_sparse_batch_host(list(graphs), pinned=slot["pinned"], n_threads=pack_threads)
 
@@ -322,6 +335,9 @@ class SegmentClassifier(nn.Module):
     def _to_batch(self, inputs):
         if isinstance(inputs, DeviceGraphBatch):
             return inputs
+        if _is_file_batch(inputs):
+            from .graph import _require_cuda
+            return DeviceGraphBatch.from_graph_files(inputs, device=_require_cuda(self._device()))
         if isinstance(inputs, (list, tuple)) and len(inputs) > 0 and isinstance(inputs[0], SparseGraph):
             from .graph import _require_cuda
             dev = _require_cuda(self._device())
@@ -346,6 +362,9 @@ class SegmentClassifier(nn.Module):
             return differentiable_forward(self, self._to_batch(inputs))
         if isinstance(inputs, DeviceGraphBatch):
             return self._run(inputs).view(inputs.B, inputs.e_max)
+        if _is_file_batch(inputs):
+            batch = self._to_batch(inputs)
+            return self._run(batch).view(batch.B, batch.e_max)
         if isinstance(inputs, (list, tuple)) and len(inputs) > 0 and isinstance(inputs[0], SparseGraph):
             from .graph import _require_cuda
             dev = _require_cuda(self._device())        # fails loudly before any host work: no CPU path

@@ -46,6 +46,8 @@ extern "C" {
 #define GNNSEG_EWORKSPACE   -3   /* workspace smaller than gnnseg_*_workspace_bytes()   */
 #define GNNSEG_ECUDA        -4   /* a CUDA runtime call / launch failed                 */
 #define GNNSEG_ENODEVICE    -5   /* no sm_100 device visible                            */
+#define GNNSEG_EIO          -6   /* a file could not be opened / mapped                 */
+#define GNNSEG_EFORMAT      -7   /* not an .npz graph file as save_graph writes them     */
 
 /* bits written to the device err_flag word by gnnseg_dense_to_edges */
 #define GNNSEG_BAD_VALUE      1  /* an incidence entry is neither 0 nor 1                */
@@ -261,6 +263,32 @@ int gnnseg_pack_sparse_batch_host(int B, int F, int e_max,
                                   const int64_t* n_in_host, const int64_t* n_out_host,
                                   float* X_out_host, int32_t* src_host, int32_t* dst_host,
                                   int n_threads);
+
+/* ---- on-disk format: replaces load_graph, gnn/graph.py:188-191 -------------------------- */
+
+/*
+ * One graph file as save_graph writes it (gnn/graph.py:179-181: np.savez of the six SparseGraph
+ * members), memory mapped.  The pointers point into the mapping (or into an aligned copy when a
+ * member is not aligned for its type inside the archive) and stay valid until
+ * gnnseg_npz_close_graph_host; they are what gnnseg_pack_sparse_batch_host takes.  X must be
+ * float32 (N, F), the four index arrays int64 (E,), y float32 (E,) (optional member), little
+ * endian, C order, stored uncompressed: GNNSEG_EUNSUPPORTED for np.savez_compressed files or other
+ * dtypes, GNNSEG_EFORMAT for anything that is not such an archive, GNNSEG_EIO if the file cannot
+ * be mapped.  Pure CPU.
+ */
+typedef struct GnnsegNpzGraph {
+    void*          handle;       /* owned by the library */
+    const float*   X;            int64_t n_nodes;  int32_t n_features;
+    const int64_t* Ri_rows;      const int64_t* Ri_cols;   int64_t n_in;
+    const int64_t* Ro_rows;      const int64_t* Ro_cols;   int64_t n_out;
+    const float*   y;            int64_t n_y;      /* y == NULL, n_y == 0 when the file has no y */
+} GnnsegNpzGraph;
+int gnnseg_npz_open_graph_host(const char* path, GnnsegNpzGraph* graph);
+int gnnseg_npz_close_graph_host(GnnsegNpzGraph* graph);
+/* B files at once, opened by n_threads threads (<= 0: a default); all or nothing: on the first
+ * failure every graph is closed again and that file's error code is returned. */
+int gnnseg_npz_open_batch_host(int B, const char* const* paths, GnnsegNpzGraph* graphs, int n_threads);
+int gnnseg_npz_close_batch_host(int B, GnnsegNpzGraph* graphs);
 
 #ifdef __cplusplus
 }

@@ -439,6 +439,27 @@ def test_predict_stream_matches_blocking_calls(cuda_device):
     assert list(model.predict_stream([])) == []
 
 
+def test_graph_files_match_tuples(cuda_device, tmp_path):
+    """model(list of .npz file names) -- mapped, parsed and packed by the library -- gives the same
+    bits as model(list of SparseGraph loaded with np.load), in the blocking call and in predict_stream."""
+    from gnn_fpga_b200 import SegmentClassifier, SparseGraph, data, load_graphs, save_graphs
+    graphs = [data.acts_like_graph(n, seed=20 + i) for i, n in enumerate((40, 25, 33, 12, 50, 8))]
+    names = [str(tmp_path / ("event%06i.npz" % i)) for i in range(len(graphs))]
+    save_graphs(graphs, names)
+    torch.manual_seed(2)
+    model = SegmentClassifier(3, 32, 3).to(cuda_device).eval()
+    with torch.no_grad():
+        a = model(load_graphs(names, SparseGraph)).clone()
+        b = model(names).clone()
+    assert a.shape == b.shape and torch.equal(a, b)
+    batches = [names[:3], names[3:]]
+    with torch.no_grad():
+        expect = [model(load_graphs(bt, SparseGraph)).cpu() for bt in batches]
+    got = [t.clone() for t in model.predict_stream(batches)]
+    for x, y in zip(got, expect):
+        assert torch.equal(x, y)
+
+
 def test_single_direction_build_csr_entry_point(cuda_device):
     """gnnseg_build_csr (one key array) gives the same CSR as the paired gnnseg_build_graph."""
     from gnn_fpga_b200 import _lib, DeviceGraphBatch, data
