@@ -71,6 +71,12 @@ SIGNATURES = {
     "gnnseg_l1_penalty": (C.c_int, [C.POINTER(GnnsegParams), C.c_int, C.c_int, C.c_float, _f32p, C.POINTER(GnnsegGrads), C.c_void_p]),
     "gnnseg_adam_step": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_void_p]),
+    "gnnseg_segments_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "gnnseg_build_segments": (C.c_int, [_i32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f32p,
+                                       _i32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnnseg_scale_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                       _f32p, C.c_void_p]),
     "gnnseg_npz_open_graph_host": (C.c_int, [C.c_char_p, C.POINTER(GnnsegNpzGraph)]),
     "gnnseg_npz_close_graph_host": (C.c_int, [C.POINTER(GnnsegNpzGraph)]),
     "gnnseg_npz_open_batch_host": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int]),

@@ -28,6 +28,10 @@ struct TrainState {
 size_t edge_part_floats(int h);
 size_t node_part_floats(int h);
 int backward(const float*, const GnnsegGraph*, int, int, int, const float*, const TrainState&, const GradOut&, cudaStream_t);
+size_t segments_workspace_bytes(int, int);
+int build_segments(const int32_t*, const void*, const void*, const void*, int, const int64_t*, int, const int32_t*, int, int,
+                   double, double, double, int, int, int, int32_t*, int32_t*, float*, int32_t*, void*, cudaStream_t);
+int scale_features(const void*, const void*, const void*, int, int, double, double, double, float*, cudaStream_t);
 int bce_loss(const float*, const float*, const float*, int, float*, float*, float*, cudaStream_t);
 int l1_penalty(const GnnsegParams*, int, int, float, float*, const GnnsegGrads*, cudaStream_t);
 int adam_step(float*, const float*, float*, float*, int, int, float, float, float, float, float, cudaStream_t);
@@ -269,6 +273,41 @@ int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int 
     }
     if (rc == GNNSEG_OK) rc = gnnseg::edge_step(blob, g, w.p, h, scores, nullptr, nullptr, st);
     return rc;
+}
+
+size_t gnnseg_segments_workspace_bytes(int n_hits, int n_pairs) {
+    if (n_hits < 0 || n_pairs < 0 || n_pairs > 32 || (long long)n_hits * n_pairs > 0x7ffffff0LL) return 0;
+    return gnnseg::segments_workspace_bytes(n_hits, n_pairs) + 256;
+}
+
+int gnnseg_build_segments(const int32_t* layer, const void* r, const void* phi, const void* z, int dtype_bytes,
+                          const int64_t* particle_id, int n_hits, const int32_t* layer_pairs_host, int n_pairs,
+                          int n_layers, double phi_slope_max, double phi_slope_outer_max, double z0_max,
+                          int outer_from_layer, int node_offset, int capacity, int32_t* src, int32_t* dst, float* y,
+                          int32_t* n_edges, void* ws, size_t ws_bytes, void* stream) {
+    if (dtype_bytes != 4 && dtype_bytes != 8) return GNNSEG_EUNSUPPORTED;
+    if (n_hits < 0 || n_pairs < 0 || n_pairs > 32 || n_layers < 1 || n_layers > 32 || capacity < 0 || !n_edges || !ws)
+        return GNNSEG_EINVAL;
+    if (n_pairs > 0 && !layer_pairs_host) return GNNSEG_EINVAL;
+    if (n_hits > 0 && (!layer || !r || !phi || !z)) return GNNSEG_EINVAL;
+    if (capacity > 0 && (!src || !dst)) return GNNSEG_EINVAL;
+    for (int p = 0; p < 2 * n_pairs; ++p)
+        if (layer_pairs_host[p] < 0 || layer_pairs_host[p] >= n_layers) return GNNSEG_EINVAL;
+    const size_t need = gnnseg_segments_workspace_bytes(n_hits, n_pairs);
+    if (need == 0) return GNNSEG_EINVAL;
+    const uintptr_t raw = reinterpret_cast<uintptr_t>(ws);
+    const uintptr_t al = (raw + 255) & ~uintptr_t(255);
+    if (ws_bytes < need - 256 + (al - raw)) return GNNSEG_EWORKSPACE;
+    return gnnseg::build_segments(layer, r, phi, z, dtype_bytes, particle_id, n_hits, layer_pairs_host, n_pairs, n_layers,
+                                  phi_slope_max, phi_slope_outer_max, z0_max, outer_from_layer, node_offset, capacity,
+                                  src, dst, y, n_edges, reinterpret_cast<void*>(al), static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_scale_features(const void* a, const void* b, const void* c, int dtype_bytes, int n_hits, double scale_a,
+                          double scale_b, double scale_c, float* X, void* stream) {
+    if (dtype_bytes != 4 && dtype_bytes != 8) return GNNSEG_EUNSUPPORTED;
+    if (n_hits < 0 || (n_hits > 0 && (!a || !b || !c || !X))) return GNNSEG_EINVAL;
+    return gnnseg::scale_features(a, b, c, dtype_bytes, n_hits, scale_a, scale_b, scale_c, X, static_cast<cudaStream_t>(stream));
 }
 
 size_t gnnseg_train_workspace_bytes(int n_nodes, int n_slots, int F, int h, int n_iters) {

@@ -264,6 +264,36 @@ int gnnseg_pack_sparse_batch_host(int B, int F, int e_max,
                                   float* X_out_host, int32_t* src_host, int32_t* dst_host,
                                   int n_threads);
 
+/* ---- segment construction: replaces construct_graph / select_segments, gnn/graph.py:44-142 --- */
+
+/*
+ * Edge candidates of one event from its hits, on the device.  Hit columns as the reference's
+ * DataFrame holds them, in row order: layer (int32, 0 <= layer < n_layers <= 32), r, phi, z (all
+ * float32 or all float64: dtype_bytes 4 / 8), particle_id (int64, nullable).  For every layer pair
+ * (layer_pairs_host[2p], [2p+1]; HOST array, n_pairs <= 32), hit i on the first layer and hit j on
+ * the second, in row order:  dphi = phi_j - phi_i wrapped once into [-pi, pi];  phi_slope = dphi / dr;
+ * z0 = z_i - r_i * dz / dr;  kept iff |phi_slope| < (first layer < outer_from_layer ? phi_slope_max
+ * : phi_slope_outer_max) and |z0| < z0_max  (select_segments, gnn/graph.py:58-66; the reference passes
+ * outer_from_layer = 5).  All arithmetic in the columns' dtype, IEEE round-to-nearest, in the reference's
+ * order of evaluation: the selection is bit-identical to pandas / numpy.
+ * Output, in the reference's edge order (layer pair, i, j):  src[k] = node_offset + i (Ro row),
+ * dst[k] = node_offset + j (Ri row), y[k] = (particle_id_i == particle_id_j) (nullable), for
+ * k < capacity;  n_edges[0] = number of kept pairs, n_edges[1] = 1 if that exceeds capacity (device
+ * words).  capacity = 0 with src = dst = NULL only counts.  Two passes, no atomics.
+ */
+size_t gnnseg_segments_workspace_bytes(int n_hits, int n_pairs);
+int gnnseg_build_segments(const int32_t* layer, const void* r, const void* phi, const void* z,
+                          int dtype_bytes, const int64_t* particle_id, int n_hits,
+                          const int32_t* layer_pairs_host, int n_pairs, int n_layers,
+                          double phi_slope_max, double phi_slope_outer_max, double z0_max,
+                          int outer_from_layer, int node_offset, int capacity,
+                          int32_t* src, int32_t* dst, float* y, int32_t* n_edges,
+                          void* ws, size_t ws_bytes, void* stream);
+/* X (n_hits, 3) float32 = (column / scale) computed in float64 then rounded, as
+ * (hits[feature_names].values / feature_scale).astype(np.float32), gnn/graph.py:118. */
+int gnnseg_scale_features(const void* a, const void* b, const void* c, int dtype_bytes, int n_hits,
+                          double scale_a, double scale_b, double scale_c, float* X, void* stream);
+
 /* ---- on-disk format: replaces load_graph, gnn/graph.py:188-191 -------------------------- */
 
 /*

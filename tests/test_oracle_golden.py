@@ -88,3 +88,20 @@ def test_gradient_oracle_matches_reference_estimator():
     for k, v in g.items():
         ref = z["grad0:" + k]
         assert np.max(np.abs(v.numpy() - ref)) <= 2e-5 * np.max(np.abs(ref)), k
+
+
+SEGMENT_CASES = ["segments_f32_small", "segments_f32_event", "segments_f64_small", "segments_f32_wide"]
+
+
+@pytest.mark.parametrize("name", SEGMENT_CASES)
+def test_segment_oracle_matches_reference_construct_graph(name):
+    """oracle/segments_oracle.py (numpy, no pandas) against the edges, labels and features the
+    reference's own construct_graph produced (oracle/make_golden_segments.py): bit-exact."""
+    import os
+    from conftest import GOLDEN
+    from oracle import segments_oracle as S
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    s, e, y = S.build_segments(z["layer"], z["r"], z["phi"], z["z"], z["particle_id"], z["layer_pairs"],
+                               float(z["phi_slope_max"]), float(z["phi_slope_outer_max"]), float(z["z0_max"]))
+    assert np.array_equal(s, z["seg_start"]) and np.array_equal(e, z["seg_end"]) and np.array_equal(y, z["y"])
+    assert np.array_equal(S.features([z["r"], z["phi"], z["z"]], z["feature_scale"]), z["X"])
