@@ -388,6 +388,12 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
     for (int base = warp * 32; base < n_slots; base += n_warps * 32) {
         // iteration p of the group (g, *) works on slot base + p*EPP + g: the G lanes of a group read
         // the same endpoint words (one broadcast load), no index shuffles
+        const int j = base + c * EPP + g;               // the slot whose score this lane will hold
+        int pi = -1, po = -1;                           // its CSR positions: fetched now, needed after the MLP
+        if (j < n_slots) {
+            if (e_in) pi = __ldg(in_pos + j);
+            if (e_out) po = __ldg(out_pos + j);
+        }
         float z[G];
 #pragma unroll
         for (int p0 = 0; p0 < G; p0 += PAIR) {
@@ -428,18 +434,11 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
                 z[i] = mine + __shfl_xor_sync(0xffffffffu, send, o);
             }
         }
-        const int j = base + c * EPP + g;               // the slot whose score this lane now holds
         if (j < n_slots) {
             const float score = 1.f / (1.f + expf(-(z[0] + __ldg(blob + B::B2))));
             if (e_slot) e_slot[j] = score;
-            if (e_in) {                                  // the node step reads the scores in CSR order
-                const int pi = __ldg(in_pos + j);
-                if (pi >= 0) e_in[pi] = score;
-            }
-            if (e_out) {
-                const int po = __ldg(out_pos + j);
-                if (po >= 0) e_out[po] = score;
-            }
+            if (pi >= 0) e_in[pi] = score;              // the node step reads the scores in CSR order
+            if (po >= 0) e_out[po] = score;
         }
     }
 }
