@@ -769,6 +769,8 @@ int launch_node_tc32(const float* blob, const GnnsegGraph* g, const float* X4, c
                      cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05, gather fused)
 int launch_node_mlp_tc32(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
                          float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05, MLP only)
+int launch_node_mlp_tc64(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
+                         float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st);   // hidden_dim = 64, weights streamed
 
 template <int H>
 static int launch_gather(const GnnsegGraph* g, const float* Q_in, const float* e_in, const float* e_out, float* h1_out,
@@ -800,6 +802,15 @@ static int launch_node(const float* blob, const GnnsegGraph* g, const float* X4,
             const int rc = launch_gather<H>(g, Q_in, e_in, e_out, P_out, 2 * H, h1_save, st);
             if (rc) return rc;
             return launch_node_mlp_tc32(blob, X4, P_out, 2 * H, g->n_nodes, P_out, Q_out, write_q, H_save, use_pdl(g->n_slots), st);
+        }
+    }
+    if (H == 64) {
+        // gather kernel + tcgen05 MLP kernel with streamed weight images; "mma": the fused mma.sync kernel (A/B runs)
+        const char* impl = getenv("GNNSEG_NODE_IMPL");
+        if (!impl || impl[0] != 'm') {
+            const int rc = launch_gather<H>(g, Q_in, e_in, e_out, P_out, 2 * H, h1_save, st);
+            if (rc) return rc;
+            return launch_node_mlp_tc64(blob, X4, P_out, 2 * H, g->n_nodes, P_out, Q_out, write_q, H_save, use_pdl(g->n_slots), st);
         }
     }
     const int n_tiles = (g->n_nodes + C::TN - 1) / C::TN;
@@ -841,6 +852,7 @@ int node_gather_step(const GnnsegGraph* g, const float* Q_in, const float* e_in,
 }
 int node_mlp_step(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, int h, float* P_out,
                   float* Q_out, cudaStream_t st) {
+    if (h == 64) return launch_node_mlp_tc64(blob, X4, h1, ld_h1, n_nodes, P_out, Q_out, Q_out != nullptr, nullptr, false, st);
     if (h != 32) return GNNSEG_EUNSUPPORTED;     // the other widths run the fused generic kernel (gnnseg_node_step)
     return launch_node_mlp_tc32(blob, X4, h1, ld_h1, n_nodes, P_out, Q_out, Q_out != nullptr, nullptr, false, st);
 }

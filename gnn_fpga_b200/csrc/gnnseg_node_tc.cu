@@ -772,6 +772,257 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
 }
 
 // ------------------------------------------------------------------------------------------
+// hidden_dim = 64: the same MLP on tcgen05.  What does not fit is the projection weight image: 320
+// outputs x 72 (K padded) x {hi, lo} = 184 KB, and N = 320 exceeds one UMMA (N <= 256).  So GEMM3 runs as
+// two halves of 160 outputs, and the half images (92 KB, hi + lo) are STREAMED through one shared
+// buffer by the loader warps with cp.async: half 1 arrives while the MLP warps store the first 160
+// columns (epilogue 3a), half 0 of the next tile while they store the last 160 (epilogue 3b).  One CTA
+// per SM (190 KB of shared memory, 464 tensor-memory columns), 8 MLP + 8 loader warps.
+// ------------------------------------------------------------------------------------------
+struct Mlp64 {
+    static constexpr int H = 64, TM = 128, D4 = 68, D4P = 72, NP = 320, NH = 160;
+    static constexpr int EW = 8, LW = 8, ET = EW * 32, LT = LW * 32, NT = ET + LT;
+    static constexpr int LBO = 128, SBO_H = (H / 4) * LBO, SBO_D4 = (D4P / 4) * LBO;
+    static constexpr int A_BYTES = (TM / 8) * SBO_H;              // 32 KB, one of hi / lo
+    static constexpr int W4_BYTES = (H / 8) * SBO_H;              // 16 KB
+    static constexpr int WPH_BYTES = (NH / 8) * SBO_D4;           // 45 KB: one half of the outputs, one of hi / lo
+    static constexpr int O_A = 0;                                 // hi, lo; the first 32 KB double as [EW] swizzled 32x32 store tiles
+    static constexpr int O_W4H = O_A + 2 * A_BYTES;
+    static constexpr int O_W4L = O_W4H + W4_BYTES;
+    static constexpr int O_WP = O_W4L + W4_BYTES;                 // [hi half][lo half] of the half in flight
+    static constexpr int O_BIAS = O_WP + 2 * WPH_BYTES;           // b4 [H], bias of the projections [5H]
+    static constexpr int O_MBAR = O_BIAS + 6 * H * 4;
+    static constexpr int SMEM_BYTES = O_MBAR + 16;
+    static constexpr int C_A3H = 0, C_A3L = D4P, C_D3 = 2 * D4P, C_D2 = C_D3, TMEM_COLS = 512;
+    static_assert(C_D3 + NP <= TMEM_COLS && SMEM_BYTES <= 227 * 1024, "resources");
+};
+
+__global__ void __launch_bounds__(Mlp64::NT, 1)
+node_mlp_kernel_tc64(const float* __restrict__ blob, const float* __restrict__ X4, const float* h1, const int ld_h1,
+                     const int n_nodes, const int n_tiles, float* P_out, float* __restrict__ Q_out, const int write_q,
+                     float* __restrict__ H_save) {
+    using C = Mlp64;
+    using B = Blob<64>;
+    constexpr int H = C::H, TM = C::TM, NT = C::NT, ET = C::ET, LT = C::LT;
+    constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_EPI = 3, BAR_WPF_A = 4, BAR_WPF_B = 5, BAR_WPE_A = 6, BAR_WPE_B = 7;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* sB4 = reinterpret_cast<float*>(smem + C::O_BIAS);
+    float* sBP = sB4 + H;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // W4 hi, lo (contiguous in the blob and in smem); the WP halves are streamed by the loader warps
+    for (int i = tid * 4; i < 2 * H * H; i += NT * 4) cp_async16(smem + C::O_W4H + i * 4, blob + B::TC_W4H + i);
+    for (int i = tid; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
+    for (int i = tid; i < C::NP; i += NT) sBP[i] = __ldg(blob + B::BP + i);
+    if (tid == 0) {
+        mbar_init(smem_u32(mbar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    cp_async_wait_all();
+    fence_async_smem();
+    tc_fence_before();
+    pdl_launch_dependents();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_wait();
+
+    if (tid >= ET) {
+        // ================================ loader warps ==================================
+        const int lt = tid - ET, lw = lt >> 5, r7 = lt & 7, cq = (lt >> 3) & 3;
+        // half `hf` of the projection weight images -> the shared buffer (hi then lo), then make it
+        // visible to the tensor core and tell the MLP warps
+        auto load_wp_half = [&](const int hf, const int bar) {
+            constexpr int HALF_FLOATS = C::WPH_BYTES / 4, IMG_FLOATS = C::NP * C::D4P;
+            for (int i = lt * 4; i < HALF_FLOATS; i += LT * 4) {
+                cp_async16(smem + C::O_WP + i * 4, blob + B::TC_WPH + hf * HALF_FLOATS + i);
+                cp_async16(smem + C::O_WP + C::WPH_BYTES + i * 4, blob + B::TC_WPH + IMG_FLOATS + hf * HALF_FLOATS + i);
+            }
+            cp_async_wait_all();
+            fence_async_smem();
+            tc_bar_arrive(bar, ET + LT);
+        };
+        float4 v[8];
+        auto fetch = [&](const int tile) {                  // 8 of the tile's 2048 float4: quarter warp = 8 rows of one chunk
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = tile * TM + (lw * 2 + (j >> 2)) * 8 + r7;
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < n_nodes) v[j] = lds4(h1 + (size_t)n * ld_h1 + 4 * (cq + 4 * (j & 3)));
+            }
+        };
+        if ((int)blockIdx.x < n_tiles) {
+            fetch(blockIdx.x);
+            load_wp_half(0, BAR_WPF_A);
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            if (it >= 1) tc_bar_sync(BAR_EMPTY, ET + LT);       // the previous tile's stores have left the buffer
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 hh, hl;
+                split3(v[j].x, hh.x, hl.x); split3(v[j].y, hh.y, hl.y); split3(v[j].z, hh.z, hl.z); split3(v[j].w, hh.w, hl.w);
+                const int off = canon_off((lw * 2 + (j >> 2)) * 8 + r7, 4 * (cq + 4 * (j & 3)), C::SBO_H);
+                *reinterpret_cast<float4*>(smem + C::O_A + off) = hh;
+                *reinterpret_cast<float4*>(smem + C::O_A + C::A_BYTES + off) = hl;
+            }
+            fence_async_smem();
+            tc_bar_arrive(BAR_FULL, ET + LT);
+            const bool more = tile + (int)gridDim.x < n_tiles;
+            if (more) fetch(tile + gridDim.x);
+            if (write_q) {
+                tc_bar_sync(BAR_WPE_A, ET + LT);                // GEMM3a has read half 0
+                load_wp_half(1, BAR_WPF_B);
+                tc_bar_sync(BAR_WPE_B, ET + LT);                // GEMM3b has read half 1
+                if (more) load_wp_half(0, BAR_WPF_A);
+            }
+        }
+    } else {
+        // ================================ MLP (issuer + epilogue) ======================
+        const uint32_t mb = smem_u32(mbar);
+        const int q = warp & 3, hf = warp >> 2;               // TMEM lane quarter, which of its two warps
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        constexpr uint32_t ID2 = idesc_tf32(TM, H), ID3 = idesc_tf32(TM, C::NH);
+        const uint32_t sa = smem_u32(smem);
+        float* sOut = reinterpret_cast<float*>(smem + C::O_A + warp * 4096);
+        const uint64_t stream = l2_policy_evict_first();
+        uint32_t phase = 0;
+        // 32 columns [c0, c0 + 32) of [P'|Q'] for this warp's 32 nodes: TMEM -> + bias -> swizzled tile -> full lines
+        auto store_chunk = [&](const int c0, const int node_w0) {
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+                float v[16];
+                tmem_ld16(lane_base + C::C_D3 + c0 + 16 * hb, v);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b = lds4(sBP + c0 + 16 * hb + 4 * i);
+                    st4(sOut + lane * 32 + (((4 * hb + i) ^ (lane & 7)) << 2),
+                        make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w));
+                }
+            }
+            __syncwarp();
+            const bool to_p = c0 < 2 * H;
+            float* base = to_p ? P_out + (size_t)node_w0 * 2 * H + c0 : Q_out + (size_t)node_w0 * 3 * H + (c0 - 2 * H);
+            const int ld = to_p ? 2 * H : 3 * H;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + (lane >> 3), j = lane & 7;
+                if (node_w0 + r < n_nodes)
+                    st4_hint(base + (size_t)r * ld + 4 * j, lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2)), stream);
+            }
+            __syncwarp();
+        };
+        auto gemm3_half = [&](const int half) {               // D3[:, 160 half ...] = [H'|X] . WP_half^T
+            tc_fence_after();
+#pragma unroll
+            for (int kq = 0; kq < C::D4P / 8; ++kq) {
+                const uint32_t ko = kq * 2 * C::LBO;
+                const uint64_t bh = smem_desc(sa + C::O_WP + ko, C::LBO, C::SBO_D4);
+                const uint64_t bl = smem_desc(sa + C::O_WP + C::WPH_BYTES + ko, C::LBO, C::SBO_D4);
+                const uint32_t d = tmem + C::C_D3 + half * C::NH;
+                umma_ts(d, tmem + C::C_A3L + 8 * kq, bh, ID3, kq > 0);
+                umma_ts(d, tmem + C::C_A3H + 8 * kq, bl, ID3, 1);
+                umma_ts(d, tmem + C::C_A3H + 8 * kq, bh, ID3, 1);
+            }
+            umma_commit(mb);
+        };
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int n = tile * TM + row;
+            const bool live = n < n_nodes;
+            const int node_w0 = tile * TM + q * 32;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && hf == 0) x = ldg4(X4 + (size_t)n * 4);
+            // ---- GEMM2: D2 = h1 . W4^T ----------------------------------------------------
+            tc_bar_sync(BAR_FULL, ET + LT);
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t a_hi = sa + C::O_A, a_lo = a_hi + C::A_BYTES;
+#pragma unroll
+                for (int kq = 0; kq < H / 8; ++kq) {
+                    const uint32_t ko = kq * 2 * C::LBO;
+                    const uint64_t ah = smem_desc(a_hi + ko, C::LBO, C::SBO_H);
+                    const uint64_t al = smem_desc(a_lo + ko, C::LBO, C::SBO_H);
+                    const uint64_t bh = smem_desc(sa + C::O_W4H + ko, C::LBO, C::SBO_H);
+                    const uint64_t bl = smem_desc(sa + C::O_W4L + ko, C::LBO, C::SBO_H);
+                    umma_ss(tmem + C::C_D2, al, bh, ID2, kq > 0);
+                    umma_ss(tmem + C::C_D2, ah, bl, ID2, 1);
+                    umma_ss(tmem + C::C_D2, ah, bh, ID2, 1);
+                }
+                umma_commit(mb);
+            }
+            mbar_wait(mb, phase); phase ^= 1;
+            tc_fence_after();
+            // ---- epilogue 2: H' = tanh(D2 + b4); [H'|X|0] -> A3 (hi, lo) in TMEM; 32 columns per warp ----
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const int c0 = hf * 32 + part * 16;
+                float v[16], hi[16], lo[16];
+                tmem_ld16(lane_base + C::C_D2 + c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = tanh_fast(v[i] + sB4[c0 + i]);
+                    split3(v[i], hi[i], lo[i]);
+                }
+                if (H_save && live) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        st4(H_save + (size_t)n * H + c0 + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                }
+                // D2 aliases the first columns of D3, A3 does not: safe to write while other lanes still read D2
+                tmem_st16(lane_base + C::C_A3H + c0, hi);
+                tmem_st16(lane_base + C::C_A3L + c0, lo);
+            }
+            if (hf == 0) {
+                float xh[8], xl[8];
+                split3(x.x, xh[0], xl[0]); split3(x.y, xh[1], xl[1]);
+                split3(x.z, xh[2], xl[2]); split3(x.w, xh[3], xl[3]);
+#pragma unroll
+                for (int i = 4; i < 8; ++i) xh[i] = xl[i] = 0.f;
+                tmem_st8(lane_base + C::C_A3H + H, xh);
+                tmem_st8(lane_base + C::C_A3L + H, xl);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            tc_bar_sync(BAR_EPI, ET);
+            // ---- GEMM3a: outputs 0..159 = P' (128) and the first 32 columns of Q' -----------------
+            if (write_q || tile == (int)blockIdx.x)            // half 0 of the weight images is in shared memory
+                tc_bar_sync(BAR_WPF_A, ET + LT);               // (it stays there when no tile needs half 1)
+            if (tid == 0) gemm3_half(0);
+            mbar_wait(mb, phase); phase ^= 1;
+            tc_fence_after();
+            if (write_q) tc_bar_arrive(BAR_WPE_A, ET + LT);    // the loader may stream half 1 in
+            // epilogue 3a (chunks 0..4; the last one is Q' and only needed when Q' is)
+            for (int ch = hf; ch < (write_q ? 5 : 4); ch += 2) store_chunk(32 * ch, node_w0);
+            if (write_q) {
+                // ---- GEMM3b: outputs 160..319 ------------------------------------------------
+                tc_bar_sync(BAR_WPF_B, ET + LT);
+                if (tid == 0) gemm3_half(1);
+                mbar_wait(mb, phase); phase ^= 1;
+                tc_fence_after();
+                tc_bar_arrive(BAR_WPE_B, ET + LT);             // ... and half 0 for the next tile
+                for (int ch = 5 + (hf ^ 1); ch < 10; ch += 2) store_chunk(32 * ch, node_w0);
+            }
+            tc_fence_before();
+            tc_bar_sync(BAR_EPI, ET);
+            if (tile + (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY, ET + LT);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // input step on the tensor cores: H0 = tanh(Win.X + bin) per thread (K = F <= 4), [H0|X|0] split
 // into tensor memory, one projection GEMM, same epilogue.  (gnn/model.py:144-146)
 // ------------------------------------------------------------------------------------------
@@ -923,6 +1174,21 @@ int launch_node_mlp_tc32(const float* blob, const float* X4, const float* h1, in
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;        // two CTAs per SM
     if (launch_pdl(node_mlp_kernel_tc<32>, grid, C::NT, C::SMEM_BYTES, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, P_out,
+                   Q_out, write_q, H_save) != cudaSuccess)
+        return GNNSEG_ECUDA;
+    return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+}
+
+int launch_node_mlp_tc64(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
+                         float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st) {
+    using C = Mlp64;
+    if (n_nodes == 0) return GNNSEG_OK;
+    const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
+    if (!ensure_dynamic_smem<node_mlp_kernel_tc64>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
+    const int sms = cached_sm_count();
+    if (sms < 1) return GNNSEG_ENODEVICE;
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    if (launch_pdl(node_mlp_kernel_tc64, grid, C::NT, C::SMEM_BYTES, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, P_out,
                    Q_out, write_q, H_save) != cudaSuccess)
         return GNNSEG_ECUDA;
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;

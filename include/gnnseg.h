@@ -176,15 +176,15 @@ int gnnseg_node_step(const float* blob, const GnnsegGraph* graph, const float* X
                      float* P_out, float* Q_out, void* stream);
 
 /*
- * The two halves of gnnseg_node_step on their own.  hidden_dim = 32 runs the node step as these two
+ * The two halves of gnnseg_node_step on their own.  hidden_dim = 32 and 64 run the node step as these two
  * kernels (a gather rate on B200 is set by the number of resident warps, which a kernel that also
  * hosts the tensor-core epilogue warps cannot provide):
  *   gnnseg_node_gather_step : h1[n] = tanh(Qs[n] + sum_in e Qi[src] + sum_out e Qo[dst])   gnn/model.py:114-122
  *                             own term, in-slots, out-slots in ascending slot order; no atomics.
  *                             h1 rows are written with row stride ld_h1 floats (>= h, multiple of 4).
  *   gnnseg_node_mlp_step    : H' = tanh(W4.h1 + b4), projections of [H' | X] -> P_out, Q_out (nullable)
- *                             gnn/model.py:122-125,154.  hidden_dim = 32 only (GNNSEG_EUNSUPPORTED
- *                             otherwise).  h1 may live inside P_out (row n of h1 in the first h floats
+ *                             gnn/model.py:122-125,154.  hidden_dim = 32 or 64 (GNNSEG_EUNSUPPORTED
+ *                             otherwise: the narrower widths run gnnseg_node_step's fused kernel).  h1 may live inside P_out (row n of h1 in the first h floats
  *                             of row n of P_out, ld_h1 = 2h): a row of P' is written after its h1 was read.
  */
 int gnnseg_node_gather_step(const GnnsegGraph* graph, const float* Q_in, const float* e_in,
