@@ -55,7 +55,7 @@ def algorithmic_bytes(Nt, Et, F, h, n_iters):
     inp = Nt * 4 * (F + h)
     edge = Nt * 4 * D + Et * 8 + Et * 4
     node = Nt * 4 * D + Et * 4 + 2 * (Et * 8 + Nt * 4) + Nt * 4 * h
-    # hidden_dim = 32 runs the node step as two kernels: the gather touches what §8(d) lists for the node
+    # hidden_dim = 32 and 64 run the node step as two kernels: the gather touches what §8(d) lists for the node
     # step (its output is the h-wide h1 instead of H'), the MLP reads h1 and X and writes the new state.
     # The forward figure stays §8(d)'s: the h1 round trip is traffic the split adds, not algorithmic bytes.
     return dict(input=inp, edge=edge, node=node, node_gather=node, node_mlp=Nt * 4 * (h + F) + Nt * 4 * D,
@@ -304,8 +304,8 @@ def main():
         clocks = sampler.stop() if sampler else None
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(sum(step_ms))
-    # pack x2, input, edge x(it+1), node x it (two kernels per node step at hidden_dim = 32)
-    launches_per_step = 2 + 1 + (cfg["n_iters"] + 1) + cfg["n_iters"] * (2 if cfg["h"] == 32 else 1)
+    # pack x2, input, edge x(it+1), node x it (two kernels per node step at hidden_dim = 32 and 64)
+    launches_per_step = 2 + 1 + (cfg["n_iters"] + 1) + cfg["n_iters"] * (2 if cfg["h"] in (32, 64) else 1)
 
     # ---- per-kernel durations (same process, CUDA events around single launches) ----------
     L = _lib.lib()
@@ -317,7 +317,7 @@ def main():
     e = torch.empty(batch.n_slots, device=dev)
     e_in = torch.empty(batch.n_slots, device=dev)
     e_out = torch.empty(batch.n_slots, device=dev)
-    split = h == 32                      # node step = gather kernel + tensor-core MLP kernel (include/gnnseg.h)
+    split = h in (32, 64)                # node step = gather kernel + tensor-core MLP kernel (include/gnnseg.h)
     h1 = torch.empty(batch.n_nodes, h, device=dev) if split else None
     kt = {}
 
@@ -479,7 +479,7 @@ def main():
                            "unpipelined": {"value": all_edges * args.steps / e2e_sec, "ms_per_step": e2e_sec / args.steps * 1e3,
                                            "path": "model(graphs) then copy to pinned host memory, synchronised every step"}}
         if train:
-            n_k = 2 + 1 + (it + 1) + it * (2 if h == 32 else 1) + 2 + 1 + 3 * (it + 1) + 1 + 1 + 1
+            n_k = 2 + 1 + (it + 1) + it * (2 if h in (32, 64) else 1) + 2 + 1 + 3 * (it + 1) + 1 + 1 + 1
             line["train_step"] = {"ms": train_ms, "edges_per_sec": all_edges / (train_ms * 1e-3),
                                   "events_per_sec": all_events / (train_ms * 1e-3), "loss": train["loss"],
                                   "gpu_launches_per_step": n_k,

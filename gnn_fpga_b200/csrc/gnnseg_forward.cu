@@ -728,15 +728,19 @@ static inline int check_launch() {
 
 int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
                       float* H_save, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05)
+int launch_input_tc64(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
+                      float* H_save, cudaStream_t st);   // gnnseg_node_tc.cu (tcgen05, weights streamed)
 
 template <int H>
 static int launch_input(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
                         float* H_save, cudaStream_t st) {
     using C = InputCfg<H>;
     if (n_nodes == 0) return GNNSEG_OK;
-    if (H == 32) {
+    if (H == 32 || H == 64) {
         const char* impl = getenv("GNNSEG_NODE_IMPL");   // "mma": generic path (for A/B runs)
-        if (!impl || impl[0] != 'm') return launch_input_tc32(blob, X, n_nodes, F, X4, P, Q, H_save, st);
+        if (!impl || impl[0] != 'm')
+            return H == 32 ? launch_input_tc32(blob, X, n_nodes, F, X4, P, Q, H_save, st)
+                           : launch_input_tc64(blob, X, n_nodes, F, X4, P, Q, H_save, st);
     }
     const int n_tiles = (n_nodes + C::TN - 1) / C::TN;
     int grid = 0;

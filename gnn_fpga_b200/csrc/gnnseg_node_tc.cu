@@ -797,10 +797,14 @@ struct Mlp64 {
     static_assert(C_D3 + NP <= TMEM_COLS && SMEM_BYTES <= 227 * 1024, "resources");
 };
 
+// INPUT = true is the input step (gnn/model.py:144-146): there is no GEMM2; the MLP warps compute
+// H0 = tanh(Win.X + bin) (K = F <= 4) straight into the A3 operand in tensor memory, the loader warps
+// only stream the weight halves.  X4 is then an output (X zero padded), Xraw the (n, F) input.
+template <bool INPUT>
 __global__ void __launch_bounds__(Mlp64::NT, 1)
-node_mlp_kernel_tc64(const float* __restrict__ blob, const float* __restrict__ X4, const float* h1, const int ld_h1,
+node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, const float* h1, const int ld_h1,
                      const int n_nodes, const int n_tiles, float* P_out, float* __restrict__ Q_out, const int write_q,
-                     float* __restrict__ H_save) {
+                     float* __restrict__ H_save, const float* __restrict__ Xraw, const int F) {
     using C = Mlp64;
     using B = Blob<64>;
     constexpr int H = C::H, TM = C::TM, NT = C::NT, ET = C::ET, LT = C::LT;
@@ -812,8 +816,13 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, const float* __restrict__ X
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // W4 hi, lo (contiguous in the blob and in smem); the WP halves are streamed by the loader warps
-    for (int i = tid * 4; i < 2 * H * H; i += NT * 4) cp_async16(smem + C::O_W4H + i * 4, blob + B::TC_W4H + i);
-    for (int i = tid; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
+    float* sWin = reinterpret_cast<float*>(smem + C::O_W4H);      // INPUT: Win^T [4][H] and bin [H] live where W4 would
+    if (INPUT) {
+        for (int i = tid; i < 5 * H; i += NT) sWin[i] = __ldg(blob + B::WIN + i);      // Win and bin are contiguous
+    } else {
+        for (int i = tid * 4; i < 2 * H * H; i += NT * 4) cp_async16(smem + C::O_W4H + i * 4, blob + B::TC_W4H + i);
+        for (int i = tid; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
+    }
     for (int i = tid; i < C::NP; i += NT) sBP[i] = __ldg(blob + B::BP + i);
     if (tid == 0) {
         mbar_init(smem_u32(mbar), 1);
@@ -858,24 +867,26 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, const float* __restrict__ X
             }
         };
         if ((int)blockIdx.x < n_tiles) {
-            fetch(blockIdx.x);
+            if (!INPUT) fetch(blockIdx.x);
             load_wp_half(0, BAR_WPF_A);
         }
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            if (it >= 1) tc_bar_sync(BAR_EMPTY, ET + LT);       // the previous tile's stores have left the buffer
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 hh, hl;
-                split3(v[j].x, hh.x, hl.x); split3(v[j].y, hh.y, hl.y); split3(v[j].z, hh.z, hl.z); split3(v[j].w, hh.w, hl.w);
-                const int off = canon_off((lw * 2 + (j >> 2)) * 8 + r7, 4 * (cq + 4 * (j & 3)), C::SBO_H);
-                *reinterpret_cast<float4*>(smem + C::O_A + off) = hh;
-                *reinterpret_cast<float4*>(smem + C::O_A + C::A_BYTES + off) = hl;
-            }
-            fence_async_smem();
-            tc_bar_arrive(BAR_FULL, ET + LT);
             const bool more = tile + (int)gridDim.x < n_tiles;
-            if (more) fetch(tile + gridDim.x);
+            if (!INPUT) {
+                if (it >= 1) tc_bar_sync(BAR_EMPTY, ET + LT);   // the previous tile's stores have left the buffer
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 hh, hl;
+                    split3(v[j].x, hh.x, hl.x); split3(v[j].y, hh.y, hl.y); split3(v[j].z, hh.z, hl.z); split3(v[j].w, hh.w, hl.w);
+                    const int off = canon_off((lw * 2 + (j >> 2)) * 8 + r7, 4 * (cq + 4 * (j & 3)), C::SBO_H);
+                    *reinterpret_cast<float4*>(smem + C::O_A + off) = hh;
+                    *reinterpret_cast<float4*>(smem + C::O_A + C::A_BYTES + off) = hl;
+                }
+                fence_async_smem();
+                tc_bar_arrive(BAR_FULL, ET + LT);
+                if (more) fetch(tile + gridDim.x);
+            }
             if (write_q) {
                 tc_bar_sync(BAR_WPE_A, ET + LT);                // GEMM3a has read half 0
                 load_wp_half(1, BAR_WPF_B);
@@ -938,10 +949,19 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, const float* __restrict__ X
             const bool live = n < n_nodes;
             const int node_w0 = tile * TM + q * 32;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live && hf == 0) x = ldg4(X4 + (size_t)n * 4);
+            if (INPUT) {
+                if (live) {
+                    float xv[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int f = 0; f < F; ++f) xv[f] = __ldg(Xraw + (size_t)n * F + f);
+                    x = make_float4(xv[0], xv[1], xv[2], xv[3]);
+                    if (hf == 0) st4(X4 + (size_t)n * 4, x);
+                }
+            } else if (live && hf == 0) {
+                x = ldg4(X4 + (size_t)n * 4);
+            }
             // ---- GEMM2: D2 = h1 . W4^T ----------------------------------------------------
-            tc_bar_sync(BAR_FULL, ET + LT);
-            if (tid == 0) {
+            if (!INPUT) tc_bar_sync(BAR_FULL, ET + LT);
+            if (!INPUT && tid == 0) {
                 tc_fence_after();
                 const uint32_t a_hi = sa + C::O_A, a_lo = a_hi + C::A_BYTES;
 #pragma unroll
@@ -957,17 +977,26 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, const float* __restrict__ X
                 }
                 umma_commit(mb);
             }
-            mbar_wait(mb, phase); phase ^= 1;
+            if (!INPUT) { mbar_wait(mb, phase); phase ^= 1; }
             tc_fence_after();
-            // ---- epilogue 2: H' = tanh(D2 + b4); [H'|X|0] -> A3 (hi, lo) in TMEM; 32 columns per warp ----
+            // ---- epilogue 2: H' = tanh(D2 + b4) (INPUT: tanh(Win.X + bin)); [H'|X|0] -> A3 (hi, lo) in TMEM ----
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
                 const int c0 = hf * 32 + part * 16;
                 float v[16], hi[16], lo[16];
-                tmem_ld16(lane_base + C::C_D2 + c0, v);
+                if (!INPUT) tmem_ld16(lane_base + C::C_D2 + c0, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    v[i] = tanh_fast(v[i] + sB4[c0 + i]);
+                    if (INPUT) {
+                        float t = sWin[4 * H + c0 + i];
+                        t = fmaf(x.x, sWin[0 * H + c0 + i], t);
+                        t = fmaf(x.y, sWin[1 * H + c0 + i], t);
+                        t = fmaf(x.z, sWin[2 * H + c0 + i], t);
+                        t = fmaf(x.w, sWin[3 * H + c0 + i], t);
+                        v[i] = tanh_fast(t);
+                    } else {
+                        v[i] = tanh_fast(v[i] + sB4[c0 + i]);
+                    }
                     split3(v[i], hi[i], lo[i]);
                 }
                 if (H_save && live) {
@@ -1011,7 +1040,7 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, const float* __restrict__ X
             }
             tc_fence_before();
             tc_bar_sync(BAR_EPI, ET);
-            if (tile + (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY, ET + LT);
+            if (!INPUT && tile + (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY, ET + LT);
         }
     }
     tc_fence_before();
@@ -1184,13 +1213,27 @@ int launch_node_mlp_tc64(const float* blob, const float* X4, const float* h1, in
     using C = Mlp64;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
-    if (!ensure_dynamic_smem<node_mlp_kernel_tc64>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
+    if (!ensure_dynamic_smem<node_mlp_kernel_tc64<false>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
     const int sms = cached_sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    if (launch_pdl(node_mlp_kernel_tc64, grid, C::NT, C::SMEM_BYTES, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, P_out,
-                   Q_out, write_q, H_save) != cudaSuccess)
+    if (launch_pdl(node_mlp_kernel_tc64<false>, grid, C::NT, C::SMEM_BYTES, st, pdl, blob, const_cast<float*>(X4), h1, ld_h1, n_nodes,
+                   n_tiles, P_out, Q_out, write_q, H_save, (const float*)nullptr, 0) != cudaSuccess)
         return GNNSEG_ECUDA;
+    return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+}
+
+int launch_input_tc64(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q, float* H_save,
+                      cudaStream_t st) {
+    using C = Mlp64;
+    if (n_nodes == 0) return GNNSEG_OK;
+    const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
+    if (!ensure_dynamic_smem<node_mlp_kernel_tc64<true>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
+    const int sms = cached_sm_count();
+    if (sms < 1) return GNNSEG_ENODEVICE;
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    // the first kernel of a forward: launched fully serialised (it reads the blob the pack kernels wrote)
+    node_mlp_kernel_tc64<true><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X4, nullptr, 0, n_nodes, n_tiles, P, Q, 1, H_save, X, F);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
