@@ -344,6 +344,28 @@ def test_events_are_independent(cuda_device):
         assert torch.equal(one[0, :n_e], full[b, :n_e])
 
 
+@pytest.mark.parametrize("h,n_iters", [(32, 3), (64, 3), (16, 2)])
+def test_many_tiles_per_cta_events_independent(h, n_iters, cuda_device):
+    """A batch large enough that every persistent CTA walks several 128-node tiles (44 k nodes =
+    344 tiles on 148 SMs: tile-to-tile barriers, operand buffer reuse, weight halves re-streamed at
+    h = 64): every event scores bit-equal to the same event run alone, and one event matches the oracle."""
+    from gnn_fpga_b200 import data, SegmentClassifier
+    graphs = [data.acts_like_graph(400, seed=100 + i) for i in range(11)]
+    p = O.init_params(3, h, seed=4)
+    model = SegmentClassifier(3, h, n_iters)
+    model.load_state_dict(p)
+    model = model.to(cuda_device).eval()
+    with torch.no_grad():
+        full = model(graphs).clone()
+        for b in (0, 5, 10):
+            one = model([graphs[b]])
+            n_e = graphs[b].Ri_rows.shape[0]
+            assert torch.equal(one[0, :n_e], full[b, :n_e])
+    X, src, dst, e_max = O.flatten_sparse_batch([graphs[10]])
+    ref = O.sparse_forward(p, X, src, dst, n_iters).numpy()
+    assert rel_err(full[10, :e_max].cpu().numpy(), ref) <= TOL
+
+
 @pytest.mark.parametrize("h,n_iters,n_tracks", [(32, 4, 400), (64, 8, 1000)])
 def test_event_scale_against_sparse_oracle(h, n_iters, n_tracks, cuda_device):
     """One ACTS-like event (BASELINE configs[1] event size; a 1/10 mu200 event) vs the fp32 and
