@@ -33,31 +33,45 @@ extern "C" int gnnseg_pack_sparse_batch_host(
     // default: all cores but two (the caller's launching thread and the CUDA driver need them;
     // an oversubscribed team doubles the per-batch time)
     int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency() - 2;
-    nt = std::max(1, std::min(nt, std::min(B, 64)));
+    nt = std::max(1, std::min(nt, 64));
+    // Work items are (event, range) chunks, not events, so that one big event (a mu200 event has 1 M
+    // edges) is packed by the whole team too.  Two phases: fill + copy, then scatter (a slot is written
+    // by at most one Ri entry and one Ro entry, so the chunks of the second phase never collide).
+    constexpr int64_t CHUNK = 1 << 15;
+    struct Task { int b; int kind; int64_t beg, end; };
+    std::vector<Task> fill, scatter;
+    for (int b = 0; b < B; ++b) {
+        for (int64_t i = 0; i < n_nodes_host[b]; i += CHUNK) fill.push_back({b, 0, i, std::min(n_nodes_host[b], i + CHUNK)});
+        for (int64_t i = 0; i < e_max; i += 2 * CHUNK) fill.push_back({b, 1, i, std::min((int64_t)e_max, i + 2 * CHUNK)});
+        for (int64_t i = 0; i < n_in_host[b]; i += CHUNK) scatter.push_back({b, 2, i, std::min(n_in_host[b], i + CHUNK)});
+        for (int64_t i = 0; i < n_out_host[b]; i += CHUNK) scatter.push_back({b, 3, i, std::min(n_out_host[b], i + CHUNK)});
+    }
+    nt = std::max(1, std::min<int>(nt, (int)std::max(fill.size(), scatter.size())));
     // OpenMP keeps its worker team alive between calls (creating 16 std::threads per batch
     // cost a quarter of the packing time)
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
-    for (int b = 0; b < B; ++b) {
-        {
-            const int64_t nn = n_nodes_host[b], off = node_off[b];
-            if (nn > 0) std::memcpy(X_out_host + off * F, X_host[b], sizeof(float) * nn * F);
-            int32_t* src = src_host + (int64_t)b * e_max;
-            int32_t* dst = dst_host + (int64_t)b * e_max;
-            std::fill(src, src + e_max, -1);
-            std::fill(dst, dst + e_max, -1);
-            const int64_t* rr = Ri_rows_host[b];
-            const int64_t* rc = Ri_cols_host[b];
-            for (int64_t i = 0; i < n_in_host[b]; ++i) {
-                const int64_t r = rr[i], c = rc[i];
-                if (r < 0 || r >= nn || c < 0 || c >= e_max) { bad.store(1); continue; }
-                dst[c] = (int32_t)(off + r);
+#pragma omp parallel num_threads(nt)
+    {
+#pragma omp for schedule(dynamic, 1)
+        for (int t = 0; t < (int)fill.size(); ++t) {
+            const Task& k = fill[t];
+            if (k.kind == 0) {
+                std::memcpy(X_out_host + (node_off[k.b] + k.beg) * F, X_host[k.b] + k.beg * F, sizeof(float) * (k.end - k.beg) * F);
+            } else {
+                std::fill(src_host + (int64_t)k.b * e_max + k.beg, src_host + (int64_t)k.b * e_max + k.end, -1);
+                std::fill(dst_host + (int64_t)k.b * e_max + k.beg, dst_host + (int64_t)k.b * e_max + k.end, -1);
             }
-            rr = Ro_rows_host[b];
-            rc = Ro_cols_host[b];
-            for (int64_t i = 0; i < n_out_host[b]; ++i) {
+        }   // implicit barrier: every slot holds -1 before the first endpoint is written
+#pragma omp for schedule(dynamic, 1)
+        for (int t = 0; t < (int)scatter.size(); ++t) {
+            const Task& k = scatter[t];
+            const int64_t nn = n_nodes_host[k.b], off = node_off[k.b];
+            const int64_t* rr = k.kind == 2 ? Ri_rows_host[k.b] : Ro_rows_host[k.b];
+            const int64_t* rc = k.kind == 2 ? Ri_cols_host[k.b] : Ro_cols_host[k.b];
+            int32_t* out = (k.kind == 2 ? dst_host : src_host) + (int64_t)k.b * e_max;
+            for (int64_t i = k.beg; i < k.end; ++i) {
                 const int64_t r = rr[i], c = rc[i];
                 if (r < 0 || r >= nn || c < 0 || c >= e_max) { bad.store(1); continue; }
-                src[c] = (int32_t)(off + r);
+                out[c] = (int32_t)(off + r);
             }
         }
     }
