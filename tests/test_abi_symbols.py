@@ -58,3 +58,32 @@ def test_argument_errors_without_device_work():
     assert L.gnnseg_forward(None, None, None, 3, 32, 1, None, None, 0, None) == -1
     assert L.gnnseg_dense_to_edges(None, None, -1, 1, 1, None, None, None, None) == -1
     assert L.gnnseg_build_csr(None, None, 5, 5, None, None, None, None, None, 0, None) == -1
+
+
+def test_training_and_segment_entry_points_check_arguments_on_the_host():
+    """The entry points added for the training step and for segment construction reject bad
+    arguments before any device work; their size queries are pure host functions."""
+    L = _lib.lib()
+    n, m, F, h, T = 1000, 5000, 3, 32, 4
+    need = 4 * (n * 4 + (T + 1) * n * h + T * n * h + (T + 1) * n * 2 * h + T * n * 3 * h + 2 * T * m      # saved by the forward
+                + n * h + n * 5 * h + 2 * m)                                                                # backward scratch
+    assert L.gnnseg_train_workspace_bytes(n, m, F, h, T) >= need
+    assert L.gnnseg_train_workspace_bytes(n, m, F, 12, T) == 0 and L.gnnseg_train_workspace_bytes(n, m, F, h, 65) == 0
+    assert L.gnnseg_forward_train(None, None, None, F, h, T, None, None, 0, None) == -1
+    assert L.gnnseg_forward_train(None, None, None, F, 12, T, None, None, 0, None) == -2
+    assert L.gnnseg_backward(None, None, None, F, h, T, None, None, None, 0, None) == -1
+    assert L.gnnseg_backward(None, None, None, F, 5, T, None, None, None, 0, None) == -2
+    assert L.gnnseg_bce_loss(None, None, None, 10, None, None, None, None) == -1
+    assert L.gnnseg_l1_penalty(None, F, h, 0.1, None, None, None) == -1
+    assert L.gnnseg_adam_step(None, None, None, None, 10, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == -1     # step counts from 1
+    assert L.gnnseg_node_gather_step(None, None, None, None, h, None, h, None) == -1
+    assert L.gnnseg_node_mlp_step(None, None, None, h, 10, h, None, None, None) == -1
+    assert L.gnnseg_node_mlp_step(None, None, None, 12, 10, 12, None, None, None) == -2
+    assert L.gnnseg_segments_workspace_bytes(4000, 9) >= 4 * (4000 + 9 * 4000)
+    assert L.gnnseg_segments_workspace_bytes(4000, 33) == 0
+    assert L.gnnseg_build_segments(None, None, None, None, 2, None, 0, None, 0, 1, 1e-3, 1e-3, 200.0, 5, 0, 0,
+                                   None, None, None, None, None, 0, None) == -2                            # dtype
+    assert L.gnnseg_build_segments(None, None, None, None, 4, None, 0, None, 0, 1, 1e-3, 1e-3, 200.0, 5, 0, 0,
+                                   None, None, None, None, None, 0, None) == -1                            # no n_edges word
+    assert L.gnnseg_scale_features(None, None, None, 4, 10, 1.0, 1.0, 1.0, None, None) == -1
+    assert b"npz" in L.gnnseg_strerror(-7) and b"mapped" in L.gnnseg_strerror(-6)
