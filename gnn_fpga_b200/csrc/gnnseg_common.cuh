@@ -146,18 +146,18 @@ inline int cached_occupancy(const int threads, const size_t smem) {
     return cache[dev];
 }
 
-// tanh(x) = sign(x) * (1 - 2 / (exp(2|x|) + 1)) with the hardware ex2 / rcp approximations:
-// 2 MUFU + 5 ALU instructions, branch free (tanhf is ~20 instructions over two divergent paths).
-// Absolute error <= ~2e-7 over the whole range (the result saturates to +-1 for |x| > 44, NaN
-// propagates); the relative error near 0 is larger than tanhf's, which the MLPs do not see: every
-// use feeds a dot product.  Measured end to end: edge scores still agree with the reference to
-// ~2e-7 relative (gate 1e-5).
+// tanh(x) = 1 - 2 / (exp(2x) + 1) with the hardware ex2 / rcp approximations: 2 MUFU + 3 FMA-pipe
+// instructions, branch free (tanhf is ~20 instructions over two divergent paths).  The formula holds
+// for both signs (x -> -inf: exp -> 0, result -1; x -> +inf: exp -> inf, rcp -> 0, result +1; NaN
+// propagates), so no |x| / copysign is needed.  Absolute error <= ~2e-7 over the whole range; the
+// relative error near 0 is larger than tanhf's, which the MLPs do not see: every use feeds a dot
+// product.  Measured end to end: edge scores agree with the reference to ~3e-7 relative (gate 1e-5).
 __device__ __forceinline__ float tanh_fast(const float x) {
     float e, r;
-    const float a = fabsf(x) * 2.885390081777927f;            // 2|x| log2(e)
+    const float a = x * 2.885390081777927f;                   // 2 x log2(e)
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
-    return copysignf(fmaf(-2.f, r, 1.f), x);
+    return fmaf(-2.f, r, 1.f);
 }
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
     acc.x = fmaf(w, v.x, acc.x);
