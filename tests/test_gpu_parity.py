@@ -305,6 +305,22 @@ def test_fused_and_split_node_step_agree(cuda_device):
     assert torch.equal(Pa, Pb) and torch.equal(Qa, Qb)
 
 
+@pytest.mark.parametrize("name,impl", [("acts_ragged_h32_it4", "fused"), ("acts_ragged_h32_it4", "mma"), ("acts_h64_it6", "mma")])
+def test_alternative_node_step_implementations(name, impl, cuda_device, monkeypatch):
+    """The kernels kept for A/B runs (GNNSEG_NODE_IMPL=fused: one tcgen05 kernel with the gather inside;
+    =mma: the generic fused kernel on mma.sync 3xTF32) still meet the same gate as the default path."""
+    rec = load_case(name)
+    model = make_model(rec, cuda_device)
+    model.use_cuda_graph = False
+    graphs = sparse_graphs_of(rec)
+    with torch.no_grad():
+        ref = model(graphs).clone()
+        monkeypatch.setenv("GNNSEG_NODE_IMPL", impl)
+        alt = model(graphs).clone()
+    assert rel_err(alt.cpu().numpy(), rec["out"]) <= TOL
+    assert rel_err(alt.cpu().numpy(), ref.cpu().numpy()) <= 2e-6
+
+
 def test_deterministic_and_graph_replay(cuda_device):
     """Same bits run to run, with and without the CUDA graph, and after rebuilding the batch."""
     from gnn_fpga_b200 import DeviceGraphBatch
