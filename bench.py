@@ -6,6 +6,7 @@
 
 Workloads (BASELINE.json configs):
     acts64  configs[1]: 64 ACTS-like events (~4k hits, ~20k edges each), hidden_dim=32, n_iters=4
+    acts64_masked  configs[2]: the same with the masked-linear twin (masks folded in by gnnseg_pack_weights)
     mu200   configs[3]: one mu200-like event (~100k hits, ~1M edges), hidden_dim=64, n_iters=8
     toy2d   configs[0]: 32 Toy2D graphs (40 hits, 144 edges), hidden_dim=8, n_iters=1
 
@@ -33,6 +34,9 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "acts64": dict(desc="ACTS-like synthetic events (~4k hits, ~20k edges), hidden_dim=32, n_iters=4, batch 64",
                    F=3, h=32, n_iters=4, batch=64, n_tracks=400, edges_per_hit=5.0),
+    "acts64_masked": dict(desc="ACTS-like synthetic events (~4k hits, ~20k edges), hidden_dim=32, n_iters=4, batch 64, "
+                               "model_maskedlinear twin (Bernoulli(0.5) masks on the edge / node MLP weights)",
+                          F=3, h=32, n_iters=4, batch=64, n_tracks=400, edges_per_hit=5.0, masked=True),
     "mu200": dict(desc="mu200-like synthetic event (~100k hits, ~1M edges), hidden_dim=64, n_iters=8, batch 1",
                   F=3, h=64, n_iters=8, batch=1, n_tracks=10000, edges_per_hit=10.0),
     "toy2d": dict(desc="Toy2D graphs (40 hits, 144 edges), hidden_dim=8, n_iters=1, batch 32",
@@ -137,6 +141,9 @@ def run_reference(args, rank, world):
     torch.set_num_threads(cores)
     graphs = make_graphs(args.workload, 0)
     p = O.init_params(cfg["F"], cfg["h"], seed=0)
+    if cfg.get("masked"):
+        from gnn_fpga_b200 import data as _data
+        p = O.apply_masks(p, *_data.random_masks(cfg["F"], cfg["h"], keep=0.5, seed=1234))
     wl = args.workload
 
     if wl == "mu200":
@@ -149,7 +156,7 @@ def run_reference(args, rank, world):
 
         def forward(inp):
             O.sparse_forward(p, inp[0], inp[1], inp[2], cfg["n_iters"])
-    elif wl == "acts64":
+    elif wl in ("acts64", "acts64_masked"):
         sample = "dense restatement of gnn/model.py (incidence bmm), 1 of %d events per step" % len(graphs)
 
         def prepare(i):
@@ -203,6 +210,9 @@ def cpu_baseline(workload, budget_s=15.0):
     torch.set_num_threads(cores)
     graphs = make_graphs(workload, 0)
     p = O.init_params(cfg["F"], cfg["h"], seed=0)
+    if cfg.get("masked"):
+        from gnn_fpga_b200 import data as _data
+        p = O.apply_masks(p, *_data.random_masks(cfg["F"], cfg["h"], keep=0.5, seed=1234))
     out = {"unit": "edges/s", "cores": cores, "kind": "port"}
     X, src, dst, _ = O.flatten_sparse_batch(graphs)
     n_real = int(((src >= 0) & (dst >= 0)).sum())
@@ -215,7 +225,7 @@ def cpu_baseline(workload, budget_s=15.0):
         out["sample"] = "sparse restatement, whole event once (the dense reference needs 800 GB)"
         return out
     edges, n, t_total = 0, 0, 0.0
-    per_event = workload == "acts64"
+    per_event = workload in ("acts64", "acts64_masked")
     while t_total < budget_s and n < (len(graphs) if per_event else 50):
         if per_event:
             g = graph_from_sparse(graphs[n], dtype=np.float32)
@@ -277,7 +287,11 @@ def main():
     cfg = WORKLOADS[args.workload]
     graphs = make_graphs(args.workload, rank)
     torch.manual_seed(0)
-    model = SegmentClassifier(cfg["F"], cfg["h"], cfg["n_iters"]).to(dev).eval()
+    masks_e = masks_n = None
+    if cfg.get("masked"):
+        from gnn_fpga_b200 import data as _data
+        masks_e, masks_n = _data.random_masks(cfg["F"], cfg["h"], keep=0.5, seed=1234)
+    model = SegmentClassifier(cfg["F"], cfg["h"], cfg["n_iters"], masks_e=masks_e, masks_n=masks_n).to(dev).eval()
     batch = DeviceGraphBatch.from_sparse_graphs(graphs, dev)
     n_real = batch.count_real_edges()
     n_events = len(graphs)
@@ -385,7 +399,7 @@ def main():
     train = None
     if not args.no_train:
         from gnn_fpga_b200.training import NativeTrainer
-        tmodel = SegmentClassifier(cfg["F"], cfg["h"], cfg["n_iters"]).to(dev).train()
+        tmodel = SegmentClassifier(cfg["F"], cfg["h"], cfg["n_iters"], masks_e=masks_e, masks_n=masks_n).to(dev).train()
         tmodel.load_state_dict(model.state_dict())
         y = torch.zeros((n_events, batch.e_max), dtype=torch.float32)
         for b_, g_ in enumerate(graphs):
