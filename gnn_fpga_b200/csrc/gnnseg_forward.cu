@@ -83,8 +83,10 @@ __global__ void pack_tc_images_kernel(int H, float* __restrict__ blob) {
         const int grp = bytes / sbo, rem = bytes % sbo;
         const int row = grp * 8 + (rem % 128) / 16, k = (rem / 128) * 4 + (rem % 16) / 4;
         float v;
+        // WP image, K index D4 (the first padding column): the bias of the projections.  The tensor-core
+        // kernels put a constant 1 in that column of the A operand, so the GEMM adds the bias.
         if (is_w4) v = blob[o_w4 + k * H + row];
-        else       v = k < D4 ? blob[o_wp + k * 5 * H + row] : 0.f;
+        else       v = k < D4 ? blob[o_wp + k * 5 * H + row] : (k == D4 ? blob[o_wp + D4 * 5 * H + row] : 0.f);
         uint32_t hi_bits;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi_bits) : "f"(v));
         const float hi = __uint_as_float(hi_bits);

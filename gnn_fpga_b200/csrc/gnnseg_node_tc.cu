@@ -59,7 +59,7 @@ struct TcCfg {
     static constexpr int O_W4L  = O_W4H + W4_BYTES;
     static constexpr int O_WPH  = O_W4L + W4_BYTES;
     static constexpr int O_WPL  = O_WPH + WP_BYTES;
-    static constexpr int O_BIAS = O_WPL + WP_BYTES;           // b4 [H], bias of the projections [5H]
+    static constexpr int O_BIAS = O_WPL + WP_BYTES;           // b4 [H] (the projection bias travels inside the weight image)
     static constexpr int STAGE_BYTES = 2 * CAP * 8 + 2 * (TM + 4) * 4;   // [2][CAP] int2 + [2][TM+4] int
     static constexpr int O_STAGE = O_BIAS + 6 * H * 4;        // two staging buffers
     static constexpr int OUT_STRIDE = 36;                     // floats per staged output row (32 + pad)
@@ -226,12 +226,12 @@ __device__ __forceinline__ void tc_row_sum(const int2* __restrict__ pairs, const
 }
 
 // Epilogue of the projection GEMM: D3 (this warp's 32 TMEM lanes = 32 consecutive nodes, NP
-// columns) + bias -> P' and Q' in global memory.  Each thread reads its own row from tensor
+// columns; the bias is already in it) -> P' and Q' in global memory.  Each thread reads its own row from tensor
 // memory; the 32x32 block is turned through a padded shared buffer so that every store
 // instruction writes four full 128-byte lines (a row of P or Q is contiguous in global memory).
 template <int H>
 __device__ __forceinline__ void tc_store_projections(const uint32_t lane_base, const uint32_t col_d3,
-                                                     const float* __restrict__ sBP, float* __restrict__ sOut,
+                                                     float* __restrict__ sOut,
                                                      const int node_w0, const int n_nodes, const int lane,
                                                      float* __restrict__ P_out, float* __restrict__ Q_out,
                                                      const bool write_q, const int chunk0 = 0,
@@ -247,11 +247,8 @@ __device__ __forceinline__ void tc_store_projections(const uint32_t lane_base, c
             float v[16];
             tmem_ld16(lane_base + col_d3 + c0 + 16 * hb, v);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 b = lds4(sBP + c0 + 16 * hb + 4 * i);
-                st4(sOut + lane * OS + 16 * hb + 4 * i,
-                    make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w));
-            }
+            for (int i = 0; i < 4; ++i)       // the bias is already in D3 (constant-1 column of A x bias row of WP)
+                st4(sOut + lane * OS + 16 * hb + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
         }
         __syncwarp();
         const bool to_p = c0 < 2 * H;
@@ -280,7 +277,6 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
     constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_EPI = 5, BAR_SFULL = 6, BAR_SEMPTY = 8, BAR_STG = 10;
     extern __shared__ __align__(128) unsigned char smem[];
     float* sB4 = reinterpret_cast<float*>(smem + C::O_BIAS);
-    float* sBP = sB4 + H;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -293,7 +289,6 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
     for (int i = tid * 4; i < 2 * H * H + 2 * NP * C::D4P; i += NT * 4)
         cp_async16(smem + C::O_W4H + i * 4, blob + B::TC_W4H + i);
     for (int i = tid; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
-    for (int i = tid; i < NP; i += NT) sBP[i] = __ldg(blob + B::BP + i);
     if (tid == 0) {
         mbar_init(smem_u32(mbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -483,6 +478,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
                 split3(x.z, xh[2], xl[2]); split3(x.w, xh[3], xl[3]);
 #pragma unroll
                 for (int i = 4; i < 8; ++i) xh[i] = xl[i] = 0.f;
+                xh[4] = 1.f;                                      // times the bias row of the weight image
                 tmem_st8(lane_base + C::C_A3H + H, xh);
                 tmem_st8(lane_base + C::C_A3L + H, xl);
             }
@@ -506,7 +502,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
             // ---- epilogue 3: [P'|Q'] = D3 + bias -> global ------------------------------------
-            tc_store_projections<H>(lane_base, C::C_D3, sBP, reinterpret_cast<float*>(smem + C::O_OUT + warp * C::OUT_BYTES),
+            tc_store_projections<H>(lane_base, C::C_D3, reinterpret_cast<float*>(smem + C::O_OUT + warp * C::OUT_BYTES),
                                     tile * TM + q * 32, n_nodes, lane, P_out, Q_out, write_q != 0, hf, 2);
             tc_fence_before();
             tc_bar_sync(BAR_EPI, ET);     // TMEM tiles are rewritten by the next tile
@@ -538,7 +534,7 @@ struct TcMlpCfg {
     static constexpr int O_W4L  = O_W4H + N::W4_BYTES;
     static constexpr int O_WPH  = O_W4L + N::W4_BYTES;
     static constexpr int O_WPL  = O_WPH + N::WP_BYTES;
-    static constexpr int O_BIAS = O_WPL + N::WP_BYTES;          // b4 [H], bias of the projections [5H]
+    static constexpr int O_BIAS = O_WPL + N::WP_BYTES;          // b4 [H] (the projection bias travels inside the weight image)
     static constexpr int O_MBAR = O_BIAS + 6 * H * 4;
     static constexpr int SMEM_BYTES = O_MBAR + 16;
     static_assert(EW * 32 * 32 * 4 <= 2 * N::A_BYTES, "store tiles fit in the A buffer");
@@ -561,7 +557,6 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
     constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_EPI = 3;
     extern __shared__ __align__(128) unsigned char smem[];
     float* sB4 = reinterpret_cast<float*>(smem + C::O_BIAS);
-    float* sBP = sB4 + H;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -571,7 +566,6 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
     for (int i = tid * 4; i < 2 * H * H + 2 * NP * N::D4P; i += NT * 4)
         cp_async16(smem + C::O_W4H + i * 4, blob + B::TC_W4H + i);
     for (int i = tid; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
-    for (int i = tid; i < NP; i += NT) sBP[i] = __ldg(blob + B::BP + i);
     if (tid == 0) {
         mbar_init(smem_u32(mbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -683,6 +677,7 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
                 split3(x.z, xh[2], xl[2]); split3(x.w, xh[3], xl[3]);
 #pragma unroll
                 for (int i = 4; i < 8; ++i) xh[i] = xl[i] = 0.f;
+                xh[4] = 1.f;                                      // times the bias row of the weight image
                 tmem_st8(lane_base + C::C_A3H + H, xh);
                 tmem_st8(lane_base + C::C_A3L + H, xl);
             }
@@ -715,11 +710,9 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
                     float v[16];
                     tmem_ld16(lane_base + C::C_D3 + col, v);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 b = lds4(sBP + col + 4 * i);
+                    for (int i = 0; i < 4; ++i)       // the bias is already in D3 (constant-1 column of A x bias row of WP)
                         st4(sOut + lane * 32 + (((jb + i) ^ (lane & 7)) << 2),
-                            make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w));
-                    }
+                            make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
                 };
                 auto out_ptr = [&](const int col, int& ld) {               // column `col` of [P'|Q'] for the warp's first node
                     const bool to_p = col < 2 * H;
@@ -790,7 +783,7 @@ struct Mlp64 {
     static constexpr int O_W4H = O_A + 2 * A_BYTES;
     static constexpr int O_W4L = O_W4H + W4_BYTES;
     static constexpr int O_WP = O_W4L + W4_BYTES;                 // [hi half][lo half] of the half in flight
-    static constexpr int O_BIAS = O_WP + 2 * WPH_BYTES;           // b4 [H], bias of the projections [5H]
+    static constexpr int O_BIAS = O_WP + 2 * WPH_BYTES;           // b4 [H] (the projection bias travels inside the weight image)
     static constexpr int O_MBAR = O_BIAS + 6 * H * 4;
     static constexpr int SMEM_BYTES = O_MBAR + 16;
     static constexpr int C_A3H = 0, C_A3L = D4P, C_D3 = 2 * D4P, C_D2 = C_D3, TMEM_COLS = 512;
@@ -811,7 +804,6 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, con
     constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_EPI = 3, BAR_WPF_A = 4, BAR_WPF_B = 5, BAR_WPE_A = 6, BAR_WPE_B = 7;
     extern __shared__ __align__(128) unsigned char smem[];
     float* sB4 = reinterpret_cast<float*>(smem + C::O_BIAS);
-    float* sBP = sB4 + H;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -823,7 +815,6 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, con
         for (int i = tid * 4; i < 2 * H * H; i += NT * 4) cp_async16(smem + C::O_W4H + i * 4, blob + B::TC_W4H + i);
         for (int i = tid; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
     }
-    for (int i = tid; i < C::NP; i += NT) sBP[i] = __ldg(blob + B::BP + i);
     if (tid == 0) {
         mbar_init(smem_u32(mbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -912,11 +903,9 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, con
                 float v[16];
                 tmem_ld16(lane_base + C::C_D3 + c0 + 16 * hb, v);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 b = lds4(sBP + c0 + 16 * hb + 4 * i);
+                for (int i = 0; i < 4; ++i)           // the bias is already in D3
                     st4(sOut + lane * 32 + (((4 * hb + i) ^ (lane & 7)) << 2),
-                        make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w));
-                }
+                        make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
             }
             __syncwarp();
             const bool to_p = c0 < 2 * H;
@@ -1014,6 +1003,7 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, con
                 split3(x.z, xh[2], xl[2]); split3(x.w, xh[3], xl[3]);
 #pragma unroll
                 for (int i = 4; i < 8; ++i) xh[i] = xl[i] = 0.f;
+                xh[4] = 1.f;                                      // times the bias row of the weight image
                 tmem_st8(lane_base + C::C_A3H + H, xh);
                 tmem_st8(lane_base + C::C_A3L + H, xl);
             }
@@ -1061,7 +1051,7 @@ struct TcInCfg {
     static constexpr int NT = 256;                          // 8 warps: two per TMEM lane quarter, each half of the columns
     static constexpr int O_WPH  = 0;
     static constexpr int O_WPL  = O_WPH + N::WP_BYTES;
-    static constexpr int O_BIAS = O_WPL + N::WP_BYTES;      // Win [4][H], bin [H], bias of the projections [5H]
+    static constexpr int O_BIAS = O_WPL + N::WP_BYTES;      // Win [4][H], bin [H]
     static constexpr int O_OUT  = O_BIAS + (4 * H + H + 5 * H) * 4;
     static constexpr int O_MBAR = O_OUT + 8 * N::OUT_BYTES;
     static constexpr int SMEM_BYTES = O_MBAR + 16;
@@ -1081,14 +1071,12 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
     extern __shared__ __align__(128) unsigned char smem[];
     float* sWin = reinterpret_cast<float*>(smem + C::O_BIAS);
     float* sBin = sWin + 4 * H;
-    float* sBP = sBin + H;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid * 4; i < 2 * NP * N::D4P; i += NT * 4)      // WP hi, WP lo: contiguous images
         cp_async16(smem + C::O_WPH + i * 4, blob + B::TC_WPH + i);
     for (int i = tid; i < 5 * H; i += NT) sWin[i] = __ldg(blob + B::WIN + i);      // Win and bin are contiguous
-    for (int i = tid; i < NP; i += NT) sBP[i] = __ldg(blob + B::BP + i);
     if (tid == 0) {
         mbar_init(smem_u32(mbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1145,6 +1133,7 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
             for (int i = 0; i < 4; ++i) split3(x[i], xh[i], xl[i]);
 #pragma unroll
             for (int i = 4; i < 8; ++i) xh[i] = xl[i] = 0.f;
+            xh[4] = 1.f;                                          // times the bias row of the weight image
             tmem_st8(lane_base + C::C_A3H + H, xh);
             tmem_st8(lane_base + C::C_A3L + H, xl);
         }
@@ -1166,7 +1155,7 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
         }
         mbar_wait(mb, phase); phase ^= 1;
         tc_fence_after();
-        tc_store_projections<H>(lane_base, C::C_D3, sBP, reinterpret_cast<float*>(smem + C::O_OUT + warp * N::OUT_BYTES),
+        tc_store_projections<H>(lane_base, C::C_D3, reinterpret_cast<float*>(smem + C::O_OUT + warp * N::OUT_BYTES),
                                 tile * TM + q * 32, n_nodes, lane, P_out, Q_out, true, hf, 2);
         tc_fence_before();
         __syncthreads();       // A3 / D3 are rewritten by the next tile
