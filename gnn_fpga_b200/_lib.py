@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.abspath(os.environ["GNNSEG_LIB"]) if os.environ.get("GNNSEG_LIB") else os.path.join(_HERE, "libgnnseg_b200.so")
 
 OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 ERRORS = {-1: "EINVAL", -2: "EUNSUPPORTED", -3: "EWORKSPACE", -4: "ECUDA", -5: "ENODEVICE", -6: "EIO", -7: "EFORMAT"}
 BAD_VALUE = 1
 BAD_HYPEREDGE = 2
@@ -67,6 +67,13 @@ SIGNATURES = {
     "gnnseg_forward_train": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnnseg_backward": (C.c_int, [_f32p, C.POINTER(GnnsegParams), C.POINTER(GnnsegGraph), C.c_int, C.c_int, C.c_int, _f32p,
                                  C.POINTER(GnnsegGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnnseg_pack_node_head": (C.c_int, [C.POINTER(GnnsegParams), _f32p, _f32p, C.c_int, C.c_int, _f32p, C.c_void_p]),
+    "gnnseg_forward_nodes": (C.c_int, [_f32p, _f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p,
+                                      C.c_size_t, C.c_void_p]),
+    "gnnseg_forward_nodes_train": (C.c_int, [_f32p, _f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p,
+                                            C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnnseg_backward_nodes": (C.c_int, [_f32p, _f32p, C.POINTER(GnnsegParams), C.POINTER(GnnsegGraph), C.c_int, C.c_int, C.c_int,
+                                       _f32p, C.POINTER(GnnsegGrads), _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnnseg_bce_loss": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_void_p, C.c_void_p]),
     "gnnseg_l1_penalty": (C.c_int, [C.POINTER(GnnsegParams), C.c_int, C.c_int, C.c_float, _f32p, C.POINTER(GnnsegGrads), C.c_void_p]),
     "gnnseg_adam_step": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -7,6 +7,8 @@ int input_step(const float*, const float*, int, int, int, float*, float*, float*
 int edge_step(const float*, const GnnsegGraph*, const float*, int, float*, float*, float*, cudaStream_t);
 int node_step(const float*, const GnnsegGraph*, const float*, const float*, const float*, const float*, int, float*, float*, int, float*, float*, cudaStream_t);
 int pack_weights(const GnnsegParams*, int, int, float*, cudaStream_t);
+int pack_head_weights(const GnnsegParams*, const float*, const float*, int, int, float*, cudaStream_t);
+int node_head(const float*, int, int, float*, cudaStream_t);
 int node_gather_step(const GnnsegGraph*, const float*, const float*, const float*, int, float*, int, cudaStream_t);
 int node_mlp_step(const float*, const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 int dense_to_edges(const float*, const float*, int, int, int, int32_t*, int32_t*, int32_t*, cudaStream_t);
@@ -27,7 +29,8 @@ struct TrainState {
 };
 size_t edge_part_floats(int h);
 size_t node_part_floats(int h);
-int backward(const float*, const GnnsegGraph*, int, int, int, const float*, const TrainState&, const GradOut&, cudaStream_t);
+int backward(const float*, const GnnsegGraph*, int, int, int, const float*, const TrainState&, const GradOut&, const float*,
+             float*, float*, cudaStream_t);
 size_t segments_workspace_bytes(int, int);
 int build_segments(const int32_t*, const void*, const void*, const void*, int, const int64_t*, int, const int32_t*, int, int,
                    double, double, double, int, int, int, int32_t*, int32_t*, float*, int32_t*, void*, cudaStream_t);
@@ -167,6 +170,15 @@ int gnnseg_pack_weights(const GnnsegParams* p, int F, int h, float* blob, void* 
     return gnnseg::pack_weights(p, F, h, blob, static_cast<cudaStream_t>(stream));
 }
 
+int gnnseg_pack_node_head(const GnnsegParams* p, const float* w_out, const float* b_out, int F, int h,
+                          float* head_blob, void* stream) {
+    if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
+    if (!p || !head_blob || !w_out || !b_out || !p->w_in || !p->b_in || !p->w_n1 || !p->b_n1 || !p->w_n2 || !p->b_n2 ||
+        !p->w_e2 || !p->b_e2)
+        return GNNSEG_EINVAL;
+    return gnnseg::pack_head_weights(p, w_out, b_out, F, h, head_blob, static_cast<cudaStream_t>(stream));
+}
+
 int gnnseg_dense_to_edges(const float* Ri, const float* Ro, int B, int N, int E, int32_t* src,
                           int32_t* dst, int32_t* err_flag, void* stream) {
     if (B < 0 || N < 0 || E < 0 || !err_flag) return GNNSEG_EINVAL;
@@ -275,6 +287,31 @@ int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int 
     return rc;
 }
 
+int gnnseg_forward_nodes(const float* blob, const float* head_blob, const GnnsegGraph* g, const float* X, int F,
+                         int h, int n_iters, float* node_scores, void* ws, size_t ws_bytes, void* stream) {
+    if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || !head_blob || !csr_ok(g) || n_iters < 0 || !ws) return GNNSEG_EINVAL;
+    if (g->n_nodes > 0 && (!X || !node_scores)) return GNNSEG_EINVAL;
+    const uintptr_t raw = reinterpret_cast<uintptr_t>(ws);
+    const uintptr_t al = (raw + 255) & ~uintptr_t(255);
+    const FwdWorkspace w = carve(reinterpret_cast<void*>(al), g->n_nodes, g->n_slots, h);
+    if (ws_bytes < w.bytes + (al - raw)) return GNNSEG_EWORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the last producing step runs on the head blob: column 0 of its P is the node logit
+    int rc = gnnseg::input_step(n_iters == 0 ? head_blob : blob, X, g->n_nodes, F, h, w.x4, w.p, w.q[0], nullptr, st);
+    int cur = 0;
+    for (int it = 0; it < n_iters && rc == GNNSEG_OK; ++it) {
+        const bool last = it + 1 == n_iters;
+        rc = gnnseg::edge_step(blob, g, w.p, h, nullptr, w.e_in, w.e_out, st);
+        if (rc == GNNSEG_OK)
+            rc = gnnseg::node_step(last ? head_blob : blob, g, w.x4, w.q[cur], w.e_in, w.e_out, h, w.p, w.q[cur ^ 1],
+                                   !last, nullptr, nullptr, st);
+        cur ^= 1;
+    }
+    if (rc == GNNSEG_OK) rc = gnnseg::node_head(w.p, 2 * h, g->n_nodes, node_scores, st);
+    return rc;
+}
+
 size_t gnnseg_segments_workspace_bytes(int n_hits, int n_pairs) {
     if (n_hits < 0 || n_pairs < 0 || n_pairs > 32 || (long long)n_hits * n_pairs > 0x7ffffff0LL) return 0;
     return gnnseg::segments_workspace_bytes(n_hits, n_pairs) + 256;
@@ -360,7 +397,58 @@ int gnnseg_backward(const float* blob, const GnnsegParams* masks, const GnnsegGr
     go.w_n2 = grads->w_n2; go.b_n2 = grads->b_n2;
     go.m_e1 = masks ? masks->m_e1 : nullptr; go.m_e2 = masks ? masks->m_e2 : nullptr;
     go.m_n1 = masks ? masks->m_n1 : nullptr; go.m_n2 = masks ? masks->m_n2 : nullptr;
-    return gnnseg::backward(blob, g, F, h, n_iters, dscores, s, go, static_cast<cudaStream_t>(stream));
+    return gnnseg::backward(blob, g, F, h, n_iters, dscores, s, go, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_forward_nodes_train(const float* blob, const float* head_blob, const GnnsegGraph* g, const float* X,
+                               int F, int h, int n_iters, float* node_scores, void* ws, size_t ws_bytes, void* stream) {
+    if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || !head_blob || !csr_ok(g) || n_iters < 0 || n_iters > MAX_ITERS || !ws) return GNNSEG_EINVAL;
+    if (g->n_nodes > 0 && (!X || !node_scores)) return GNNSEG_EINVAL;
+    const uintptr_t raw = reinterpret_cast<uintptr_t>(ws);
+    const uintptr_t al = (raw + 255) & ~uintptr_t(255);
+    const TrainWorkspace w = carve_train(reinterpret_cast<void*>(al), g->n_nodes, g->n_slots, h, n_iters);
+    if (ws_bytes < w.bytes + (al - raw)) return GNNSEG_EWORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = gnnseg::input_step(n_iters == 0 ? head_blob : blob, X, g->n_nodes, F, h, w.x4, w.P[0], w.Q[0], w.H[0], st);
+    for (int t = 0; t < n_iters && rc == GNNSEG_OK; ++t) {
+        rc = gnnseg::edge_step(blob, g, w.P[t], h, nullptr, w.e_in[t], w.e_out[t], st);
+        const bool more = t + 1 < n_iters;
+        if (rc == GNNSEG_OK)
+            rc = gnnseg::node_step(more ? blob : head_blob, g, w.x4, w.Q[t], w.e_in[t], w.e_out[t], h, w.P[t + 1],
+                                   more ? w.Q[t + 1] : nullptr, more, w.h1[t], w.H[t + 1], st);
+    }
+    if (rc == GNNSEG_OK) rc = gnnseg::node_head(w.P[n_iters], 2 * h, g->n_nodes, node_scores, st);
+    return rc;
+}
+
+int gnnseg_backward_nodes(const float* blob, const float* head_blob, const GnnsegParams* masks, const GnnsegGraph* g,
+                          int F, int h, int n_iters, const float* dnode_scores, const GnnsegGrads* grads,
+                          float* grad_w_out, float* grad_b_out, void* ws, size_t ws_bytes, void* stream) {
+    if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || !head_blob || !csr_ok(g) || n_iters < 0 || n_iters > MAX_ITERS || !ws || !grads || !grad_w_out ||
+        !grad_b_out)
+        return GNNSEG_EINVAL;
+    if (g->n_nodes > 0 && !dnode_scores) return GNNSEG_EINVAL;
+    if (!grads->w_in || !grads->b_in || !grads->w_e1 || !grads->b_e1 || !grads->w_e2 || !grads->b_e2 ||
+        !grads->w_n1 || !grads->b_n1 || !grads->w_n2 || !grads->b_n2)
+        return GNNSEG_EINVAL;
+    const uintptr_t raw = reinterpret_cast<uintptr_t>(ws);
+    const uintptr_t al = (raw + 255) & ~uintptr_t(255);
+    const TrainWorkspace w = carve_train(reinterpret_cast<void*>(al), g->n_nodes, g->n_slots, h, n_iters);
+    if (ws_bytes < w.bytes + (al - raw)) return GNNSEG_EWORKSPACE;
+    gnnseg::TrainState s;
+    s.x4 = w.x4;
+    s.Hs = w.H; s.h1s = w.h1; s.Ps = w.P; s.Qs = w.Q; s.e_in = w.e_in; s.e_out = w.e_out;
+    s.dg = w.dg; s.dproj = w.dproj; s.ds_in = w.ds_in; s.ds_out = w.ds_out; s.partE = w.partE; s.partN = w.partN;
+    gnnseg::GradOut go;
+    go.w_in = grads->w_in; go.b_in = grads->b_in; go.w_e1 = grads->w_e1; go.b_e1 = grads->b_e1;
+    go.w_e2 = grads->w_e2; go.b_e2 = grads->b_e2; go.w_n1 = grads->w_n1; go.b_n1 = grads->b_n1;
+    go.w_n2 = grads->w_n2; go.b_n2 = grads->b_n2;
+    go.m_e1 = masks ? masks->m_e1 : nullptr; go.m_e2 = masks ? masks->m_e2 : nullptr;
+    go.m_n1 = masks ? masks->m_n1 : nullptr; go.m_n2 = masks ? masks->m_n2 : nullptr;
+    return gnnseg::backward(blob, g, F, h, n_iters, dnode_scores, s, go, head_blob, grad_w_out, grad_b_out,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int gnnseg_bce_loss(const float* scores, const float* targets, const float* weights, int n, float* loss,

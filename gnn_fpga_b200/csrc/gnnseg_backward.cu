@@ -473,6 +473,46 @@ __global__ void finalize_grads_kernel(const float* __restrict__ partE, const int
 }
 
 // ------------------------------------------------------------------------------------------
+// NodeClassifier head (gnn/MPNN_HitClassifier.ipynb c21: sigmoid(Wo.[H_T | X] + bo) per node).  The
+// forward leaves the logit in column 0 of P_T (pack_weights_kernel, head blob), so its backward is
+// the dense kernel with NB = 2 on dproj = [dlogit | 0 ...]: dWo lands in column 0 of the WP partial,
+// dbo in BP[0].  head_grad_kernel sums them over the CTAs in a fixed order and clears the slots,
+// which the launches of the iterations below use for the edge network's first layer.
+// ------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ P_T, const float* __restrict__ dnode, const int n_nodes,
+                float* __restrict__ dproj) {
+    constexpr int C2 = 2 * H / 4;
+    const long long total = (long long)n_nodes * C2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / C2), c = (int)(i % C2);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c == 0) {
+            const float sg = 1.f / (1.f + expf(-__ldg(P_T + (size_t)n * 2 * H)));
+            v.x = __ldg(dnode + n) * sg * (1.f - sg);
+        }
+        st4(dproj + (size_t)n * 2 * H + 4 * c, v);
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(128)
+head_grad_kernel(float* __restrict__ partN, const int nN, const int D, float* __restrict__ g_w, float* __restrict__ g_b) {
+    using NP = NodePart<H>;
+    const int k = threadIdx.x;                        // k < D: dWo[k]; k == D: dbo
+    if (k > D) return;
+    const int slot = k < D ? NP::WP + k * 5 * H : NP::BP;
+    float s = 0.f;
+    for (int c = 0; c < nN; ++c) {
+        float* q = partN + (size_t)c * NP::SIZE + slot;
+        s += *q;
+        *q = 0.f;
+    }
+    if (k < D) g_w[k] = s; else g_b[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static inline int bwd_sm_count() { return cached_sm_count(); }
@@ -496,7 +536,8 @@ struct TrainState {          // device arrays saved by the training forward + ba
 
 template <int H>
 static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, const int T, const float* dscores,
-                         const TrainState& s, const GradOut& go, cudaStream_t st) {
+                         const TrainState& s, const GradOut& go, const float* head_blob, float* g_wout, float* g_bout,
+                         cudaStream_t st) {
     using C = DenseCfg<H>;
     const int sms = bwd_sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
@@ -527,25 +568,38 @@ static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, c
     // the dense kernel's partial holds slots (W4/B4 or WIN/BIN) that some launches never write
     zero_kernel<<<64, 256, 0, st>>>(s.partN, (size_t)gridD * NodePart<H>::SIZE);
 
-    // ---- final edge step: scores = edge(P_T) ------------------------------------------------
-    if (m > 0)
-        edge_bwd_kernel<H, true><<<gridE, 256, 0, st>>>(blob, s.Ps[T], nullptr, nullptr, dscores, g->src, g->dst,
-                                                         g->in_pos, g->out_pos, m, s.ds_in, s.ds_out, s.partE, 0);
-    else
-        zero_kernel<<<1, 256, 0, st>>>(s.partE, (size_t)gridE * EdgePart<H>::SIZE);
-    if (n > 0) {
-        gather_bwd_kernel<H, true><<<gridG, 256, 0, st>>>(blob, *g, s.Ps[T], nullptr, nullptr, nullptr, s.ds_in,
-                                                           s.ds_out, s.dproj);
-        if (T == 0)
-            kF2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(blob, s.dproj, s.Hs[0], s.x4, nullptr, n, n_tiles, nullptr, s.partN, 0);
+    const bool nodes = head_blob != nullptr;     // NodeClassifier: dscores is per node, no final edge step
+    if (nodes) {
+        zero_kernel<<<64, 256, 0, st>>>(s.partE, (size_t)gridE * EdgePart<H>::SIZE);
+        if (n > 0) {
+            head_bwd_kernel<H><<<gridG, 256, 0, st>>>(s.Ps[T], dscores, n, s.dproj);
+            if (T == 0)
+                kF2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(head_blob, s.dproj, s.Hs[0], s.x4, nullptr, n, n_tiles, nullptr, s.partN, 0);
+            else
+                kI2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(head_blob, s.dproj, s.Hs[T], s.x4, s.h1s[T - 1], n, n_tiles, s.dg, s.partN, 0);
+        }
+        head_grad_kernel<H><<<1, 128, 0, st>>>(s.partN, n > 0 ? gridD : 0, F + H, g_wout, g_bout);
+    } else {
+        // ---- final edge step: scores = edge(P_T) ------------------------------------------------
+        if (m > 0)
+            edge_bwd_kernel<H, true><<<gridE, 256, 0, st>>>(blob, s.Ps[T], nullptr, nullptr, dscores, g->src, g->dst,
+                                                             g->in_pos, g->out_pos, m, s.ds_in, s.ds_out, s.partE, 0);
         else
-            kI2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(blob, s.dproj, s.Hs[T], s.x4, s.h1s[T - 1], n, n_tiles, s.dg, s.partN, 0);
+            zero_kernel<<<1, 256, 0, st>>>(s.partE, (size_t)gridE * EdgePart<H>::SIZE);
+        if (n > 0) {
+            gather_bwd_kernel<H, true><<<gridG, 256, 0, st>>>(blob, *g, s.Ps[T], nullptr, nullptr, nullptr, s.ds_in,
+                                                               s.ds_out, s.dproj);
+            if (T == 0)
+                kF2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(blob, s.dproj, s.Hs[0], s.x4, nullptr, n, n_tiles, nullptr, s.partN, 0);
+            else
+                kI2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(blob, s.dproj, s.Hs[T], s.x4, s.h1s[T - 1], n, n_tiles, s.dg, s.partN, 0);
+        }
     }
     // ---- iterations T-1 .. 0 ------------------------------------------------------------------
     for (int t = T - 1; t >= 0 && n > 0; --t) {
         if (m > 0)
             edge_bwd_kernel<H, false><<<gridE, 256, 0, st>>>(blob, s.Ps[t], s.Qs[t], s.dg, nullptr, g->src, g->dst,
-                                                              g->in_pos, g->out_pos, m, s.ds_in, s.ds_out, s.partE, 1);
+                                                              g->in_pos, g->out_pos, m, s.ds_in, s.ds_out, s.partE, 1);   // accumulates (final step or the zeroing above came first)
         gather_bwd_kernel<H, false><<<gridG, 256, 0, st>>>(blob, *g, s.Ps[t], s.dg, s.e_in[t], s.e_out[t], s.ds_in,
                                                             s.ds_out, s.dproj);
         // accumulate: 1 = projections only (the W4 slots are first written by launch T-1 ... ), 2 = W4 too
@@ -559,13 +613,14 @@ static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, c
 }
 
 int backward(const float* blob, const GnnsegGraph* g, int F, int h, int T, const float* dscores,
-             const TrainState& s, const GradOut& go, cudaStream_t st) {
+             const TrainState& s, const GradOut& go, const float* head_blob, float* g_wout, float* g_bout,
+             cudaStream_t st) {
     switch (h) {
-        case 4:  return backward_impl<4>(blob, g, F, T, dscores, s, go, st);
-        case 8:  return backward_impl<8>(blob, g, F, T, dscores, s, go, st);
-        case 16: return backward_impl<16>(blob, g, F, T, dscores, s, go, st);
-        case 32: return backward_impl<32>(blob, g, F, T, dscores, s, go, st);
-        case 64: return backward_impl<64>(blob, g, F, T, dscores, s, go, st);
+        case 4:  return backward_impl<4>(blob, g, F, T, dscores, s, go, head_blob, g_wout, g_bout, st);
+        case 8:  return backward_impl<8>(blob, g, F, T, dscores, s, go, head_blob, g_wout, g_bout, st);
+        case 16: return backward_impl<16>(blob, g, F, T, dscores, s, go, head_blob, g_wout, g_bout, st);
+        case 32: return backward_impl<32>(blob, g, F, T, dscores, s, go, head_blob, g_wout, g_bout, st);
+        case 64: return backward_impl<64>(blob, g, F, T, dscores, s, go, head_blob, g_wout, g_bout, st);
         default: return GNNSEG_EUNSUPPORTED;
     }
 }

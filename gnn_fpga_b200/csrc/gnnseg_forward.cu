@@ -22,7 +22,13 @@ namespace gnnseg {
 // ------------------------------------------------------------------------------------
 // weight packing
 // ------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(GnnsegParams p, int F, int H, float* __restrict__ blob) {
+// head_w != nullptr packs the blob of the NodeClassifier's LAST producing step
+// (gnn/MPNN_HitClassifier.ipynb c21: output_network = Linear(D, 1) + Sigmoid on [H | X]): the
+// logit Wo.[H | X] + bo is one more linear map of [H | X], so it takes the place of column 0 of
+// the start-node projection (the final step's edge projections have no reader in that model);
+// the other edge-projection columns are zero.  The node-network part is packed as usual.
+__global__ void pack_weights_kernel(GnnsegParams p, int F, int H, float* __restrict__ blob,
+                                    const float* __restrict__ head_w, const float* __restrict__ head_b) {
     const int D = F + H, D4 = H + 4;
     const int o_bin = 4 * H, o_wp = o_bin + H, o_bp = o_wp + D4 * 5 * H, o_w2 = o_bp + 5 * H,
               o_b2 = o_w2 + H, o_w4 = o_b2 + 4, o_b4 = o_w4 + H * H, total = o_b4 + H;   // fp32 part
@@ -36,7 +42,9 @@ __global__ void pack_weights_kernel(GnnsegParams p, int F, int H, float* __restr
         } else if (i < o_bp) {                 // WP^T [D4][5H] = [W1a | W1b | W3a | W3b | W3c]
             const int r = i - o_wp, k = r / (5 * H), c = r % (5 * H), blk = c / H, j = c % H;
             if (k < D) {
-                if (blk < 2) {
+                if (blk < 2 && head_w) {
+                    v = (blk == 0 && j == 0) ? head_w[k] : 0.f;
+                } else if (blk < 2) {
                     const int idx = j * (2 * D) + blk * D + k;
                     v = p.w_e1[idx];
                     if (p.m_e1) v *= p.m_e1[idx];
@@ -48,7 +56,7 @@ __global__ void pack_weights_kernel(GnnsegParams p, int F, int H, float* __restr
             }
         } else if (i < o_w2) {                 // BP [5H] = [b1 | 0 | 0 | 0 | b3]
             const int c = i - o_bp;
-            if (c < H) v = p.b_e1[c];
+            if (c < H) v = head_w ? (c == 0 ? head_b[0] : 0.f) : p.b_e1[c];
             else if (c >= 4 * H) v = p.b_n1[c - 4 * H];
         } else if (i < o_b2) {
             const int j = i - o_w2;
@@ -864,8 +872,29 @@ int node_mlp_step(const float* blob, const float* X4, const float* h1, int ld_h1
 }
 int pack_weights(const GnnsegParams* p, int F, int h, float* blob, cudaStream_t st) {
     const int total = blob_total(h);
-    pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(*p, F, h, blob);
+    pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(*p, F, h, blob, nullptr, nullptr);
     pack_tc_images_kernel<<<(total + 255) / 256, 256, 0, st>>>(h, blob);
+    return check_launch();
+}
+int pack_head_weights(const GnnsegParams* p, const float* w_out, const float* b_out, int F, int h, float* head_blob,
+                      cudaStream_t st) {
+    const int total = blob_total(h);
+    pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(*p, F, h, head_blob, w_out, b_out);
+    pack_tc_images_kernel<<<(total + 255) / 256, 256, 0, st>>>(h, head_blob);
+    return check_launch();
+}
+
+// NodeClassifier output: score[n] = sigmoid(logit[n]); the head blob left the logit in column 0 of P.
+__global__ void node_head_kernel(const float* __restrict__ P, const int ld, const int n_nodes, float* __restrict__ out) {
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_nodes; n += gridDim.x * blockDim.x)
+        out[n] = 1.f / (1.f + expf(-__ldg(P + (size_t)n * ld)));
+}
+int node_head(const float* P, int ld, int n_nodes, float* out, cudaStream_t st) {
+    if (n_nodes == 0) return GNNSEG_OK;
+    int grid = (n_nodes + 255) / 256;
+    const int cap = cached_sm_count() * 8;
+    if (grid > cap) grid = cap;
+    node_head_kernel<<<grid, 256, 0, st>>>(P, ld, n_nodes, out);
     return check_launch();
 }
 

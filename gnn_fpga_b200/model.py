@@ -130,20 +130,8 @@ class SegmentClassifier(nn.Module):
     def _device(self):
         return self.input_network[0].weight.device
 
-    def pack_weights(self):
-        """W*mask, transposed and padded into the kernel layout (gnnseg_pack_weights).  Runs
-        every forward, like the reference recomputes weight*mask (gnn/model.py:30)."""
-        L = _lib.lib()
-        dev = self._device()
-        if dev.type != "cuda":
-            raise _lib.GnnsegError("SegmentClassifier parameters are on %s: move the model to a CUDA "
-                                   "device (model.cuda()); there is no CPU path" % dev)
-        F, h = self.input_dim, self.hidden_dim
-        n = L.gnnseg_weights_floats(F, h)
-        if n == 0:
-            _lib.check(-2, "SegmentClassifier(input_dim=%d, hidden_dim=%d)" % (F, h))
-        if self._blob is None or self._blob.device != dev or self._blob.numel() != n:
-            self._blob = torch.empty(n, dtype=torch.float32, device=dev)
+    def _params_struct(self):
+        """GnnsegParams over the ten parameter tensors and four masks (+ the tensors to keep alive)."""
         e0, e2 = self.edge_network.network[0], self.edge_network.network[2]
         n0, n2 = self.node_network.network[0], self.node_network.network[2]
         tensors = [self.input_network[0].weight, self.input_network[0].bias,
@@ -160,10 +148,27 @@ class SegmentClassifier(nn.Module):
             m = lin.effective_mask()
             keep.append(m)
             ptrs.append(m.data_ptr() if m is not None else None)
-        params = _lib.GnnsegParams(*ptrs)
+        return _lib.GnnsegParams(*ptrs), keep
+
+    def pack_weights(self):
+        """W*mask, transposed and padded into the kernel layout (gnnseg_pack_weights).  Runs
+        every forward, like the reference recomputes weight*mask (gnn/model.py:30)."""
+        L = _lib.lib()
+        dev = self._device()
+        if dev.type != "cuda":
+            raise _lib.GnnsegError("SegmentClassifier parameters are on %s: move the model to a CUDA "
+                                   "device (model.cuda()); there is no CPU path" % dev)
+        F, h = self.input_dim, self.hidden_dim
+        n = L.gnnseg_weights_floats(F, h)
+        if n == 0:
+            _lib.check(-2, "SegmentClassifier(input_dim=%d, hidden_dim=%d)" % (F, h))
+        if self._blob is None or self._blob.device != dev or self._blob.numel() != n:
+            self._blob = torch.empty(n, dtype=torch.float32, device=dev)
+        params, keep = self._params_struct()
         with torch.cuda.device(dev):
             _lib.check(L.gnnseg_pack_weights(C.byref(params), F, h, _ptr(self._blob), _stream_ptr(dev)),
                        "gnnseg_pack_weights")
+        del keep
         return self._blob
 
     # -- forward -------------------------------------------------------------------------

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNSEG_ABI_VERSION 2
+#define GNNSEG_ABI_VERSION 3
 
 /* error codes */
 #define GNNSEG_OK            0
@@ -244,6 +244,41 @@ int gnnseg_l1_penalty(const GnnsegParams* params, int F, int h, float l1, float*
 int gnnseg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int n,
                      int step, float lr, float beta1, float beta2, float eps, float weight_decay,
                      void* stream);
+
+/* ---- NodeClassifier: the per-hit sibling of the segment classifier,
+ *      gnn/MPNN_HitClassifier.ipynb cell 21 (class NodeClassifier): the same input / edge / node
+ *      steps, n_iters times, then output_network = Linear(F+h, 1) + Sigmoid on [H | X] per node
+ *      and no final edge step ------------------------------------------------------------- */
+
+/*
+ * Packs the blob of the model's LAST producing step.  The head's logit Wo.[H|X] + bo is one more
+ * linear map of [H | X], so it rides in column 0 of that step's start-node projection (which has
+ * no reader in this model); params' w_e1 / b_e1 are not read.  head_blob: gnnseg_weights_floats
+ * floats.  w_out [F+h] = output_network.0.weight (1, F+h), b_out [1] = its bias.
+ */
+int gnnseg_pack_node_head(const GnnsegParams* params, const float* w_out, const float* b_out,
+                          int F, int h, float* head_blob, void* stream);
+/*
+ * node_scores[n_nodes] = NodeClassifier.forward.  blob from gnnseg_pack_weights, head_blob from
+ * gnnseg_pack_node_head; workspace of gnnseg_forward_workspace_bytes.  2*n_iters + 2 launches
+ * (h = 32 / 64: 3*n_iters + 2).
+ */
+int gnnseg_forward_nodes(const float* blob, const float* head_blob, const GnnsegGraph* graph,
+                         const float* X, int F, int h, int n_iters, float* node_scores,
+                         void* ws, size_t ws_bytes, void* stream);
+/*
+ * Training pair, as gnnseg_forward_train / gnnseg_backward (workspace of
+ * gnnseg_train_workspace_bytes, kept untouched in between).  dnode_scores[n_nodes] = dL/dscore
+ * per node; grad_w_out [F+h] and grad_b_out [1] receive the head's gradients, grads the ten
+ * tensors of the body (written, not accumulated; bit-identical from run to run).
+ */
+int gnnseg_forward_nodes_train(const float* blob, const float* head_blob, const GnnsegGraph* graph,
+                               const float* X, int F, int h, int n_iters, float* node_scores,
+                               void* ws, size_t ws_bytes, void* stream);
+int gnnseg_backward_nodes(const float* blob, const float* head_blob, const GnnsegParams* masks,
+                          const GnnsegGraph* graph, int F, int h, int n_iters,
+                          const float* dnode_scores, const GnnsegGrads* grads, float* grad_w_out,
+                          float* grad_b_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- host side: replaces graph_from_sparse + merge_graphs + np_to_torch --------------- */
 

@@ -170,6 +170,64 @@ def sparse_vjp(p, X, src, dst, n_iters, dscores=None, y=None, l1=0.0, masks_e=No
     return out.detach(), (loss.detach() if loss is not None else None), grads
 
 
+# ---- NodeClassifier (gnn/MPNN_HitClassifier.ipynb cell 21) -------------------------------
+# The body is the segment classifier's (cells 20-21 restate gnn/model.py's EdgeNetwork / NodeNetwork
+# without masks); the head is output_network = Linear(D, 1) + Sigmoid on [H | X] per node, and there
+# is no final edge step.  Pinned by tests/golden/nodeclf_*.npz (oracle/make_golden_nodeclf.py
+# executes the notebook's own class definitions).
+HEAD_KEYS = ("output_network.0.weight", "output_network.0.bias")
+
+
+def _head(p, H):
+    return torch.sigmoid(torch.nn.functional.linear(H, p[HEAD_KEYS[0]], p[HEAD_KEYS[1]])).squeeze(-1)
+
+
+def nodeclf_dense_forward(p, X, Ri, Ro, n_iters):
+    with torch.no_grad():
+        H = torch.cat([torch.tanh(_lin(X, p, 0)), X], dim=-1)
+        for _ in range(n_iters):
+            e = dense_edge(p, H, Ri, Ro)
+            H = torch.cat([dense_node(p, H, e, Ri, Ro), X], dim=-1)
+        return _head(p, H)
+
+
+def nodeclf_sparse_forward(p, X, src, dst, n_iters, dtype=torch.float32):
+    """X (n_nodes, F); src/dst (n_slots,) node ids or -1.  Returns (n_nodes,) node scores."""
+    with torch.no_grad():
+        p = {k: v.to(dtype) for k, v in p.items()}
+        X = torch.as_tensor(X).to(dtype)
+        src = torch.as_tensor(np.asarray(src)).long()
+        dst = torch.as_tensor(np.asarray(dst)).long()
+        H = sparse_input(p, X)
+        for _ in range(n_iters):
+            e = sparse_edge(p, H, src, dst)
+            H = torch.cat([sparse_node(p, H, e, src, dst), X], dim=-1)
+        return _head(p, H)
+
+
+def nodeclf_sparse_vjp(p, X, src, dst, n_iters, dnode=None, y=None, dtype=torch.float64):
+    """Gradients of the node classifier's sparse restatement (checker of gnnseg_backward_nodes):
+    cotangent `dnode` (n_nodes,), or targets `y` with nn.BCELoss() (mean over all nodes).
+    Returns (scores, loss or None, {key: grad}); parameters the loss does not reach get zeros."""
+    leaf = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in p.items()}
+    X = torch.as_tensor(X).to(dtype)
+    src = torch.as_tensor(np.asarray(src)).long()
+    dst = torch.as_tensor(np.asarray(dst)).long()
+    H = sparse_input(leaf, X)
+    for _ in range(n_iters):
+        e = sparse_edge(leaf, H, src, dst)
+        H = torch.cat([sparse_node(leaf, H, e, src, dst), X], dim=-1)
+    out = _head(leaf, H)
+    loss = None
+    if dnode is not None:
+        out.backward(torch.as_tensor(dnode).to(dtype))
+    else:
+        loss = torch.nn.functional.binary_cross_entropy(out, torch.as_tensor(y).to(dtype).reshape(-1))
+        loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
+    return out.detach(), (loss.detach() if loss is not None else None), grads
+
+
 def projections(p, HX):
     """Per-node first-layer projections the CUDA path carries between kernels (same algebra as
     gnn/model.py:73-81,120-125: W.[a;b;c] = Wa.a + Wb.b + Wc.c).  HX (n, D) = [H | X].

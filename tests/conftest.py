@@ -16,6 +16,10 @@ MODEL_CASES = [
 ]
 
 
+NODECLF_CASES = ["nodeclf_toy2d_h8_it1", "nodeclf_toy2d_h8_it0", "nodeclf_f4_h16_it2", "nodeclf_acts_h32_it3",
+                 "nodeclf_acts_h64_it2"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
@@ -26,6 +30,7 @@ def load_case(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     rec = {k: z[k] for k in z.files}
     rec["params"] = {k[len("param:"):]: torch.from_numpy(v.copy()) for k, v in rec.items() if k.startswith("param:")}
+    rec["grads"] = {k[len("grad:"):]: v for k, v in rec.items() if k.startswith("grad:")}
     for k in ("F", "h", "n_iters", "seed", "n_params"):
         rec[k] = int(rec[k])
     if "mask_e0" in rec:

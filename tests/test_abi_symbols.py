@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_host_only_queries():
     L = _lib.lib()
-    assert L.gnnseg_abi_version() == _lib.ABI_VERSION == 2
+    assert L.gnnseg_abi_version() == _lib.ABI_VERSION == 3
     assert L.gnnseg_strerror(0) == b"ok"
     assert b"unsupported" in L.gnnseg_strerror(-2)
     for h in (4, 8, 16, 32, 64):
@@ -87,3 +87,15 @@ def test_training_and_segment_entry_points_check_arguments_on_the_host():
                                    None, None, None, None, None, 0, None) == -1                            # no n_edges word
     assert L.gnnseg_scale_features(None, None, None, 4, 10, 1.0, 1.0, 1.0, None, None) == -1
     assert b"npz" in L.gnnseg_strerror(-7) and b"mapped" in L.gnnseg_strerror(-6)
+
+
+def test_node_classifier_entry_points_check_arguments_on_the_host():
+    L = _lib.lib()
+    F, h, T = 4, 32, 2
+    assert L.gnnseg_pack_node_head(None, None, None, F, h, None, None) == -1
+    assert L.gnnseg_pack_node_head(None, None, None, 5, h, None, None) == -2
+    assert L.gnnseg_forward_nodes(None, None, None, None, F, h, T, None, None, 0, None) == -1
+    assert L.gnnseg_forward_nodes(None, None, None, None, F, 12, T, None, None, 0, None) == -2
+    assert L.gnnseg_forward_nodes_train(None, None, None, None, F, h, 65, None, None, 0, None) == -1
+    assert L.gnnseg_backward_nodes(None, None, None, None, F, h, T, None, None, None, None, None, 0, None) == -1
+    assert L.gnnseg_backward_nodes(None, None, None, None, F, 7, T, None, None, None, None, None, 0, None) == -2

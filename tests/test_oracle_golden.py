@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import MODEL_CASES, load_case, rel_err
+from conftest import MODEL_CASES, NODECLF_CASES, load_case, rel_err
 from oracle import segclf_oracle as O
 
 
@@ -105,3 +105,37 @@ def test_segment_oracle_matches_reference_construct_graph(name):
                                float(z["phi_slope_max"]), float(z["phi_slope_outer_max"]), float(z["z0_max"]))
     assert np.array_equal(s, z["seg_start"]) and np.array_equal(e, z["seg_end"]) and np.array_equal(y, z["y"])
     assert np.array_equal(S.features([z["r"], z["phi"], z["z"]], z["feature_scale"]), z["X"])
+
+
+# ---- NodeClassifier (gnn/MPNN_HitClassifier.ipynb c21; goldens from oracle/make_golden_nodeclf.py) ----
+@pytest.mark.parametrize("name", NODECLF_CASES)
+def test_nodeclf_restatements_match_reference(name):
+    rec = load_case(name)
+    torch.set_num_threads(1)
+    p = rec["params"]
+    assert tuple(rec["keys"]) == O.PARAM_KEYS + O.HEAD_KEYS
+    X = torch.from_numpy(rec["X"])
+    out = O.nodeclf_dense_forward(p, X, torch.from_numpy(rec["Ri"].astype(np.float32)),
+                                  torch.from_numpy(rec["Ro"].astype(np.float32)), rec["n_iters"])
+    assert out.shape == rec["out"].shape
+    assert rel_err(out.numpy(), rec["out"]) <= 1e-6
+    B, N, F = rec["X"].shape
+    src, dst = O.edges_from_dense(rec["Ri"], rec["Ro"])
+    out32 = O.nodeclf_sparse_forward(p, rec["X"].reshape(B * N, F), src, dst, rec["n_iters"])
+    assert rel_err(out32.numpy(), rec["out"].reshape(-1)) <= 2e-6
+
+
+@pytest.mark.parametrize("name", NODECLF_CASES)
+def test_nodeclf_gradient_oracle_matches_reference(name):
+    """BCELoss backward through the notebook's own model (recorded) vs autograd over the restatement."""
+    rec = load_case(name)
+    B, N, F = rec["X"].shape
+    src, dst = O.edges_from_dense(rec["Ri"], rec["Ro"])
+    _, loss, grads = O.nodeclf_sparse_vjp(rec["params"], rec["X"].reshape(B * N, F), src, dst, rec["n_iters"], y=rec["y"])
+    assert abs(float(loss) - float(rec["loss"])) <= 1e-6 * abs(float(rec["loss"]))
+    for k, ref in rec["grads"].items():
+        scale = np.max(np.abs(ref))
+        if scale == 0:
+            assert float(grads[k].abs().max()) == 0, k
+        else:
+            assert float(np.max(np.abs(grads[k].numpy() - ref)) / scale) <= 1e-5, k
