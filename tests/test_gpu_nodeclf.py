@@ -117,3 +117,30 @@ def test_backward_is_deterministic(cuda_device):
         runs.append([v.grad.clone() for v in model.parameters()])
     for a, b in zip(*runs):
         assert torch.equal(a, b)
+
+
+def test_events_without_edges(cuda_device):
+    """n_slots = 0 with n_iters > 0: the node steps see no messages, the backward has no edge launches."""
+    from gnn_fpga_b200 import SparseGraph
+    rng = np.random.RandomState(5)
+    e = np.zeros(0, np.int64)
+    graphs = [SparseGraph(rng.uniform(-1, 1, (n, 3)).astype(np.float32), e, e, e, e, np.zeros(0, np.float32)) for n in (37, 37)]
+    torch.manual_seed(3)
+    p = O.init_params(3, 32, seed=8)
+    head = torch.nn.Linear(35, 1)
+    p[O.HEAD_KEYS[0]], p[O.HEAD_KEYS[1]] = head.weight.detach().clone(), head.bias.detach().clone()
+    model = _model(p, 3, 32, 2, cuda_device).train()
+    out = model(graphs)
+    assert out.shape == (2, 37)
+    cot = rng.normal(size=74).astype(np.float32)
+    out.backward(torch.from_numpy(cot).to(cuda_device).view_as(out))
+    X = np.concatenate([g.X for g in graphs])
+    ref_out, _, ref = O.nodeclf_sparse_vjp(p, X, e, e, 2, dnode=cot)
+    assert rel_err(out.detach().cpu().numpy().reshape(-1), ref_out.numpy()) <= 1e-5
+    refn = {k: v.numpy() for k, v in ref.items()}
+    for k, v in model.named_parameters():
+        if np.max(np.abs(refn[k])) == 0:
+            assert float(v.grad.abs().max()) == 0, k
+        else:
+            err = grad_err(v.grad.cpu().numpy(), refn[k], _scale_tensor(refn, k))
+            assert err <= GTOL, (k, err)
