@@ -68,5 +68,58 @@ def main():
         print("segments_%-10s hits=%5d edges=%6d true=%d dtype=%s" % (name, len(hits), n_edges, int(sg.y.sum()), np.dtype(dtype).name))
 
 
+def main_multi():
+    """Several events in one hit table, rows of different events interleaved: the reference's event loop
+    (construct_graphs, gnn/graph.py:152-174: groupby('evtid'), events in order of first appearance)
+    around its construct_graph, with the max_tracks / no_missing_hits pre-selection (gnn/graph.py:106-114).
+    np.random is seeded once before the loop; the drop-in must draw the same samples."""
+    l = np.arange(10)
+    layer_pairs = np.stack([l[:-1], l[1:]], axis=1)
+    feature_names = ["r", "phi", "z"]
+    feature_scale = np.array([1000., np.pi / 8, 1000.])
+    for name, sizes, max_tracks, no_missing, seed in (("multi_plain", (30, 18, 41), None, False, 5),
+                                                     ("multi_tracks", (40, 25, 33), 15, False, 6),
+                                                     ("multi_nomiss", (30, 36), 20, True, 7)):
+        parts = []
+        for e, n in enumerate(sizes):
+            h = synth_hits(n, 100 * seed + e, np.float32, False)
+            h["evtid"] = 7 + 3 * e
+            h["particle_id"] += 100000 * e
+            parts.append(h)
+        hits = pd.concat(parts, ignore_index=True).sample(frac=1.0, random_state=seed)
+        c_in, c_out, z0_max = 0.003, 0.006, 200.0
+        np.random.seed(40 + seed)
+        # Work-around needed to run the reference here: pandas 3 hands out read-only `.values`, and
+        # gnn/graph.py:112 shuffles that array in place (ValueError).  The stand-in re-enables writing on
+        # the very same array and calls numpy's shuffle: same generator, same draws, same in-place result.
+        orig_shuffle = np.random.shuffle
+
+        def writable_shuffle(a):
+            a.flags.writeable = True
+            orig_shuffle(a)
+        np.random.shuffle = writable_shuffle
+        groups = hits.groupby("evtid")
+        rec = {"seed": 40 + seed, "max_tracks": -1 if max_tracks is None else max_tracks, "no_missing_hits": int(no_missing),
+               "layer_pairs": layer_pairs.astype(np.int32), "phi_slope_max": c_in, "phi_slope_outer_max": c_out,
+               "z0_max": z0_max, "feature_scale": feature_scale}
+        for k in ("evtid", "layer", "r", "phi", "z", "particle_id"):
+            rec["hits_" + k] = hits[k].values
+        n_hits, n_edges = [], []
+        for b, evtid in enumerate(hits.evtid.unique()):
+            evt_hits = groups.get_group(evtid)
+            sg, segments = ref_graph.construct_graph(evt_hits, layer_pairs, c_in, c_in, c_out, z0_max, feature_names,
+                                                     feature_scale, max_tracks=max_tracks, no_missing_hits=no_missing)
+            src = sg.Ro_rows[np.argsort(sg.Ro_cols, kind="stable")]
+            dst = sg.Ri_rows[np.argsort(sg.Ri_cols, kind="stable")]
+            rec["src_%d" % b], rec["dst_%d" % b], rec["y_%d" % b], rec["X_%d" % b] = src, dst, sg.y, sg.X
+            n_hits.append(sg.X.shape[0])
+            n_edges.append(sg.y.shape[0])
+        np.random.shuffle = orig_shuffle
+        rec["n_hits"], rec["n_edges"] = np.array(n_hits), np.array(n_edges)
+        np.savez_compressed(os.path.join(OUT, "segments_%s.npz" % name), **rec)
+        print("segments_%-12s events=%d hits=%s edges=%s" % (name, len(n_hits), n_hits, n_edges))
+
+
 if __name__ == "__main__":
     main()
+    main_multi()

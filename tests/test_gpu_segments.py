@@ -94,3 +94,42 @@ def test_count_only_overflow_and_errors(cuda_device):
     assert L.gnnseg_build_segments(*bad) == -1                              # a pair names layer >= n_layers
     bad = list(args(m, src, dst)); bad[21] = 64
     assert L.gnnseg_build_segments(*bad) == -3                              # workspace
+
+
+@pytest.mark.parametrize("name", ["segments_multi_plain", "segments_multi_tracks", "segments_multi_nomiss"])
+def test_event_batches_match_reference_event_loop(name, cuda_device):
+    """construct_graphs_device on a multi-event hit table (rows of the events interleaved) against the
+    reference's event loop around construct_graph: one padded device batch, bit-exact per event."""
+    from gnn_fpga_b200 import SegmentClassifier, SparseGraph
+    from gnn_fpga_b200.segments import construct_graphs_device
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    hits = {k: z["hits_" + k] for k in ("evtid", "layer", "r", "phi", "z", "particle_id")}
+    mt = int(z["max_tracks"])
+    np.random.seed(int(z["seed"]))
+    c = float(z["phi_slope_max"])
+    batch, y, n_edges = construct_graphs_device(hits, z["layer_pairs"], c, c, float(z["phi_slope_outer_max"]), float(z["z0_max"]),
+                                                feature_scale=z["feature_scale"], max_tracks=None if mt < 0 else mt,
+                                                no_missing_hits=bool(int(z["no_missing_hits"])), device=cuda_device)
+    B = len(z["n_hits"])
+    assert batch.B == B and list(batch.n_nodes_per_event) == list(z["n_hits"]) and list(n_edges) == list(z["n_edges"])
+    e_max = int(max(z["n_edges"]))
+    assert batch.e_max == e_max and y.shape == (B, e_max)
+    src, dst = batch.src.cpu().numpy().reshape(B, e_max), batch.dst.cpu().numpy().reshape(B, e_max)
+    off = np.concatenate([[0], np.cumsum(z["n_hits"])])
+    graphs = []
+    for b in range(B):
+        m = int(z["n_edges"][b])
+        assert np.array_equal(src[b, :m], z["src_%d" % b] + off[b]) and np.array_equal(dst[b, :m], z["dst_%d" % b] + off[b])
+        assert np.all(src[b, m:] == -1) and np.all(dst[b, m:] == -1)
+        assert np.array_equal(y[b, :m].cpu().numpy(), z["y_%d" % b]) and float(y[b, m:].abs().sum()) == 0
+        assert np.array_equal(batch.X[off[b]:off[b + 1]].cpu().numpy(), z["X_%d" % b])
+        eid = np.arange(m, dtype=np.int64)
+        oi, oo = np.lexsort((eid, z["dst_%d" % b])), np.lexsort((eid, z["src_%d" % b]))
+        graphs.append(SparseGraph(z["X_%d" % b], z["dst_%d" % b][oi], eid[oi], z["src_%d" % b][oo], eid[oo], z["y_%d" % b]))
+    # the device-built batch scores exactly like the same events packed from host tuples
+    torch.manual_seed(0)
+    model = SegmentClassifier(3, 32, 2).to(cuda_device).eval()
+    with torch.no_grad():
+        a = model(batch).clone()
+        b_ = model(graphs)
+    assert torch.equal(a, b_)

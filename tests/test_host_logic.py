@@ -147,3 +147,29 @@ def test_product_does_not_import_oracle():
     for fn in glob.glob(os.path.join(os.path.dirname(G.__file__), "**", "*"), recursive=True):
         if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
             assert "oracle" not in open(fn).read().replace("# oracle", ""), fn
+
+
+MULTI_CASES = ["segments_multi_plain", "segments_multi_tracks", "segments_multi_nomiss"]
+
+
+@pytest.mark.parametrize("name", MULTI_CASES)
+def test_event_loop_and_track_selection_match_reference(name):
+    """Host side of construct_graphs_device (event grouping in order of first appearance, the
+    no_missing_hits / max_tracks pre-selection drawn from numpy's global generator) against the
+    reference's own event loop around construct_graph (oracle/make_golden_segments.py main_multi);
+    the cuts on the selected rows go through the numpy oracle: edges, labels, features bit-exact."""
+    import os
+    from conftest import GOLDEN
+    from gnn_fpga_b200.segments import event_rows
+    from oracle import segments_oracle as S
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cols = {k: z["hits_" + k] for k in ("evtid", "layer", "r", "phi", "z", "particle_id")}
+    np.random.seed(int(z["seed"]))
+    mt = int(z["max_tracks"])
+    groups = event_rows(cols, None, None if mt < 0 else mt, bool(int(z["no_missing_hits"])))
+    assert [len(g) for g in groups] == list(z["n_hits"])
+    for b, g in enumerate(groups):
+        s, e, y = S.build_segments(cols["layer"][g], cols["r"][g], cols["phi"][g], cols["z"][g], cols["particle_id"][g],
+                                   z["layer_pairs"], float(z["phi_slope_max"]), float(z["phi_slope_outer_max"]), float(z["z0_max"]))
+        assert np.array_equal(s, z["src_%d" % b]) and np.array_equal(e, z["dst_%d" % b]) and np.array_equal(y, z["y_%d" % b])
+        assert np.array_equal(S.features([cols[k][g] for k in ("r", "phi", "z")], z["feature_scale"]), z["X_%d" % b])
