@@ -79,6 +79,10 @@ SIGNATURES = {
     "gnnseg_adam_step": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_void_p]),
     "gnnseg_segments_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "gnnseg_segments_batch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "gnnseg_build_segments_batch": (C.c_int, [_i32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, _i32p, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                             C.c_int, _i32p, _i32p, _f32p, _i32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnnseg_build_segments": (C.c_int, [_i32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                        C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f32p,
                                        _i32p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -32,6 +32,10 @@ size_t node_part_floats(int h);
 int backward(const float*, const GnnsegGraph*, int, int, int, const float*, const TrainState&, const GradOut&, const float*,
              float*, float*, cudaStream_t);
 size_t segments_workspace_bytes(int, int);
+size_t segments_batch_workspace_bytes(int, int, int);
+int build_segments_batch(const int32_t*, const void*, const void*, const void*, int, const int64_t*, int, const int32_t*, int, int,
+                         const int32_t*, int, int, double, double, double, int, int, int32_t*, int32_t*, float*, int32_t*, void*,
+                         cudaStream_t);
 int build_segments(const int32_t*, const void*, const void*, const void*, int, const int64_t*, int, const int32_t*, int, int,
                    double, double, double, int, int, int, int32_t*, int32_t*, float*, int32_t*, void*, cudaStream_t);
 int scale_features(const void*, const void*, const void*, int, int, double, double, double, float*, cudaStream_t);
@@ -338,6 +342,39 @@ int gnnseg_build_segments(const int32_t* layer, const void* r, const void* phi, 
     return gnnseg::build_segments(layer, r, phi, z, dtype_bytes, particle_id, n_hits, layer_pairs_host, n_pairs, n_layers,
                                   phi_slope_max, phi_slope_outer_max, z0_max, outer_from_layer, node_offset, capacity,
                                   src, dst, y, n_edges, reinterpret_cast<void*>(al), static_cast<cudaStream_t>(stream));
+}
+
+size_t gnnseg_segments_batch_workspace_bytes(int n_events, int total_hits, int n_pairs) {
+    if (n_events < 0 || total_hits < 0 || n_pairs < 0 || n_pairs > 32 || (long long)total_hits * n_pairs > 0x7ffffff0LL) return 0;
+    return gnnseg::segments_batch_workspace_bytes(n_events, total_hits, n_pairs) + 256;
+}
+
+int gnnseg_build_segments_batch(const int32_t* layer, const void* r, const void* phi, const void* z, int dtype_bytes,
+                                const int64_t* particle_id, int n_events, const int32_t* hit_off, int total_hits,
+                                int max_hits_per_event, const int32_t* layer_pairs_host, int n_pairs, int n_layers,
+                                double phi_slope_max, double phi_slope_outer_max, double z0_max, int outer_from_layer,
+                                int e_max, int32_t* src, int32_t* dst, float* y, int32_t* n_edges, void* ws, size_t ws_bytes,
+                                void* stream) {
+    if (dtype_bytes != 4 && dtype_bytes != 8) return GNNSEG_EUNSUPPORTED;
+    if (n_events < 0 || total_hits < 0 || max_hits_per_event < 0 || max_hits_per_event > total_hits || n_pairs < 0 ||
+        n_pairs > 32 || n_layers < 1 || n_layers > 32 || e_max < 0 || !ws)
+        return GNNSEG_EINVAL;
+    if (n_events > 0 && (!hit_off || !n_edges)) return GNNSEG_EINVAL;
+    if (n_pairs > 0 && !layer_pairs_host) return GNNSEG_EINVAL;
+    if (total_hits > 0 && (!layer || !r || !phi || !z)) return GNNSEG_EINVAL;
+    if (e_max > 0 && (!src || !dst)) return GNNSEG_EINVAL;
+    if ((long long)n_events * e_max > 0x7fffffffLL || n_events > 65535) return GNNSEG_EINVAL;
+    for (int p = 0; p < 2 * n_pairs; ++p)
+        if (layer_pairs_host[p] < 0 || layer_pairs_host[p] >= n_layers) return GNNSEG_EINVAL;
+    const size_t need = gnnseg_segments_batch_workspace_bytes(n_events, total_hits, n_pairs);
+    if (need == 0) return GNNSEG_EINVAL;
+    const uintptr_t raw = reinterpret_cast<uintptr_t>(ws);
+    const uintptr_t al = (raw + 255) & ~uintptr_t(255);
+    if (ws_bytes < need - 256 + (al - raw)) return GNNSEG_EWORKSPACE;
+    return gnnseg::build_segments_batch(layer, r, phi, z, dtype_bytes, particle_id, n_events, hit_off, total_hits,
+                                        max_hits_per_event, layer_pairs_host, n_pairs, n_layers, phi_slope_max,
+                                        phi_slope_outer_max, z0_max, outer_from_layer, e_max, src, dst, y, n_edges,
+                                        reinterpret_cast<void*>(al), static_cast<cudaStream_t>(stream));
 }
 
 int gnnseg_scale_features(const void* a, const void* b, const void* c, int dtype_bytes, int n_hits, double scale_a,

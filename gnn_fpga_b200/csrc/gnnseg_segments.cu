@@ -32,12 +32,38 @@ struct SegWs {
     int* off;
 };
 
-// One block, one warp per layer: count the layer's hits, scan, then list them in row order
+// Which events a launch covers.  Single event (hit_off == nullptr): the columns hold one event of
+// n_hits rows, node ids start at node_offset, slots at 0.  Batch: event b (blockIdx.y, or blockIdx.x
+// of the one-block kernels) owns rows [hit_off[b], hit_off[b+1]) of the concatenated columns, its
+// node ids are those row numbers, its slots start at b * capacity.  Both carve the same workspace:
+//   [n_events][layer_ptr 33 | row_off 33 | 2] | layer_hits [hits_pad] | off [n_pairs * total_hits + n_events]
+struct SegCtx {
+    const int32_t* hit_off;
+    int n_events, n_hits, node_offset, hits_pad, n_pairs;
+    int* ws;
+};
+constexpr int SEG_FIXED = (SEG_MAX_LAYERS + 1) + (SEG_MAX_PAIRS + 1) + 2;
+
+__device__ __forceinline__ SegWs seg_event(const SegCtx& c, const int b, int& h0, int& n, int& node0) {
+    h0 = c.hit_off ? __ldg(c.hit_off + b) : 0;
+    n = c.hit_off ? __ldg(c.hit_off + b + 1) - h0 : c.n_hits;
+    node0 = c.hit_off ? h0 : c.node_offset;
+    SegWs w;
+    w.layer_ptr = c.ws + b * SEG_FIXED;
+    w.row_off = w.layer_ptr + (SEG_MAX_LAYERS + 1);
+    w.layer_hits = c.ws + c.n_events * SEG_FIXED + h0;
+    w.off = c.ws + c.n_events * SEG_FIXED + c.hits_pad + c.n_pairs * h0 + b;
+    return w;
+}
+
+// One block per event, one warp per layer: count the layer's hits, scan, then list them in row order
 // (groupby('layer').get_group(l) keeps the frame's row order, gnn/graph.py:79-85).
 __global__ void __launch_bounds__(32 * SEG_MAX_LAYERS)
-seg_layer_lists_kernel(const int32_t* __restrict__ layer, const int n_hits, const int n_layers, const SegPairs pairs,
-                       const SegWs ws) {
+seg_layer_lists_kernel(const int32_t* __restrict__ layer_all, const SegCtx ctx, const int n_layers, const SegPairs pairs) {
     __shared__ int s_cnt[SEG_MAX_LAYERS], s_ptr[SEG_MAX_LAYERS + 1];
+    int h0, n_hits, node0;
+    const SegWs ws = seg_event(ctx, blockIdx.x, h0, n_hits, node0);
+    const int32_t* __restrict__ layer = layer_all + h0;
     const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int total = 0;
     if (l < n_layers)
@@ -109,10 +135,20 @@ __device__ __forceinline__ bool seg_keep(const T r1, const T phi1, const T z1, c
 // FILL = true: write the kept pairs at off[row], j ascending.
 template <typename T, bool FILL>
 __global__ void __launch_bounds__(256)
-seg_rows_kernel(const T* __restrict__ r, const T* __restrict__ phi, const T* __restrict__ z,
-                const int64_t* __restrict__ pid, const SegPairs pairs, const SegCuts<T> cuts, const SegWs ws,
-                const int node_offset, const int capacity, int32_t* __restrict__ src, int32_t* __restrict__ dst,
-                float* __restrict__ y) {
+seg_rows_kernel(const T* __restrict__ r_all, const T* __restrict__ phi_all, const T* __restrict__ z_all,
+                const int64_t* __restrict__ pid_all, const SegPairs pairs, const SegCuts<T> cuts, const SegCtx ctx,
+                const int capacity, int32_t* __restrict__ src_all, int32_t* __restrict__ dst_all,
+                float* __restrict__ y_all) {
+    int h0, n_hits, node_offset;
+    const SegWs ws = seg_event(ctx, blockIdx.y, h0, n_hits, node_offset);
+    const T* __restrict__ r = r_all + h0;
+    const T* __restrict__ phi = phi_all + h0;
+    const T* __restrict__ z = z_all + h0;
+    const int64_t* __restrict__ pid = pid_all ? pid_all + h0 : nullptr;
+    const size_t slot0 = ctx.hit_off ? (size_t)blockIdx.y * capacity : 0;
+    int32_t* __restrict__ src = FILL ? src_all + slot0 : nullptr;
+    int32_t* __restrict__ dst = FILL ? dst_all + slot0 : nullptr;
+    float* __restrict__ y = (FILL && y_all) ? y_all + slot0 : nullptr;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const int rows = __ldg(ws.row_off + SEG_MAX_PAIRS);
@@ -152,9 +188,12 @@ seg_rows_kernel(const T* __restrict__ r, const T* __restrict__ phi, const T* __r
 
 // exclusive scan of off[0..rows) in place, off[rows] = total; one block (rows <= n_pairs * n_hits)
 __global__ void __launch_bounds__(1024)
-seg_scan_kernel(const SegWs ws, const int capacity, int32_t* __restrict__ n_edges) {
+seg_scan_kernel(const SegCtx ctx, const int capacity, int32_t* __restrict__ n_edges_all) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
+    int h0, n_hits, node0;
+    const SegWs ws = seg_event(ctx, blockIdx.x, h0, n_hits, node0);
+    int32_t* __restrict__ n_edges = n_edges_all + 2 * blockIdx.x;
     const int rows = ws.row_off[SEG_MAX_PAIRS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_carry = 0;
@@ -205,28 +244,17 @@ __global__ void seg_features_kernel(const T* __restrict__ a, const T* __restrict
     }
 }
 
-static SegWs seg_carve(void* ws, int n_hits) {
-    SegWs w;
-    int* p = static_cast<int*>(ws);
-    w.layer_ptr = p;
-    w.row_off = p + (SEG_MAX_LAYERS + 1);
-    w.layer_hits = w.row_off + (SEG_MAX_PAIRS + 1) + 2;      // keep 16-byte groups
-    w.off = w.layer_hits + ((n_hits + 3) & ~3);
-    return w;
+// ints of workspace for n_events events holding total_hits rows in all (see SegCtx)
+static size_t seg_ws_ints(int n_events, int total_hits, int n_pairs) {
+    return (size_t)n_events * SEG_FIXED + ((size_t)(total_hits + 3) & ~size_t(3)) + (size_t)n_pairs * total_hits + n_events + 4;
 }
-
-size_t segments_workspace_bytes(int n_hits, int n_pairs) {
-    const size_t ints = (SEG_MAX_LAYERS + 1) + (SEG_MAX_PAIRS + 1) + 2 + ((size_t)(n_hits + 3) & ~size_t(3)) +
-                        (size_t)n_pairs * n_hits + 4;
-    return ints * 4;
+size_t segments_workspace_bytes(int n_hits, int n_pairs) { return seg_ws_ints(1, n_hits, n_pairs) * 4; }
+size_t segments_batch_workspace_bytes(int n_events, int total_hits, int n_pairs) {
+    return seg_ws_ints(n_events, total_hits, n_pairs) * 4;
 }
 
 template <typename T>
-static int build_segments_t(const int32_t* layer, const T* r, const T* phi, const T* z, const int64_t* pid, int n_hits,
-                            const SegPairs& pairs, int n_layers, double slope_in, double slope_out, double z0_max,
-                            int outer_from, int node_offset, int capacity, int32_t* src, int32_t* dst, float* y,
-                            int32_t* n_edges, void* ws, cudaStream_t st) {
-    const SegWs w = seg_carve(ws, n_hits);
+static SegCuts<T> seg_cuts(double slope_in, double slope_out, double z0_max, int outer_from) {
     SegCuts<T> cuts;
     cuts.pi = (T)3.141592653589793;            // np.pi, converted to the column dtype as numpy converts a Python float
     cuts.two_pi = (T)6.283185307179586;        // 2 * np.pi
@@ -234,17 +262,39 @@ static int build_segments_t(const int32_t* layer, const T* r, const T* phi, cons
     cuts.slope_out = (T)slope_out;
     cuts.z0_max = (T)z0_max;
     cuts.outer_from = outer_from;
-    seg_layer_lists_kernel<<<1, 32 * SEG_MAX_LAYERS, 0, st>>>(layer, n_hits, n_layers, pairs, w);
+    return cuts;
+}
+
+static SegPairs seg_pairs(const int32_t* layer_pairs_host, int n_pairs) {
+    SegPairs pairs;
+    pairs.n = n_pairs;
+    for (int p = 0; p < SEG_MAX_PAIRS; ++p) {
+        pairs.l1[p] = p < n_pairs ? layer_pairs_host[2 * p] : 0;
+        pairs.l2[p] = p < n_pairs ? layer_pairs_host[2 * p + 1] : 0;
+    }
+    return pairs;
+}
+
+// count = lists + per-row counts + scan (leaves the row offsets in the workspace); fill = the second pass.
+template <typename T>
+static int seg_run(const int32_t* layer, const T* r, const T* phi, const T* z, const int64_t* pid, const SegCtx& ctx,
+                   int max_hits, const SegPairs& pairs, int n_layers, const SegCuts<T>& cuts, bool count, bool fill,
+                   int capacity, int32_t* src, int32_t* dst, float* y, int32_t* n_edges, cudaStream_t st) {
     const int sms = cached_sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
-    long long rows_cap = (long long)pairs.n * n_hits;
-    int grid = (int)((rows_cap * 32 + 255) / 256);
-    if (grid > sms * 8) grid = sms * 8;
-    if (grid < 1) grid = 1;
-    seg_rows_kernel<T, false><<<grid, 256, 0, st>>>(r, phi, z, pid, pairs, cuts, w, node_offset, capacity, nullptr, nullptr, nullptr);
-    seg_scan_kernel<<<1, 1024, 0, st>>>(w, capacity, n_edges);
-    if (src && dst && capacity > 0)
-        seg_rows_kernel<T, true><<<grid, 256, 0, st>>>(r, phi, z, pid, pairs, cuts, w, node_offset, capacity, src, dst, y);
+    const long long rows_cap = (long long)pairs.n * max_hits;
+    long long gx = (rows_cap * 32 + 255) / 256;
+    const long long cap = ctx.n_events > 1 ? (sms * 8 + ctx.n_events - 1) / ctx.n_events + 8 : sms * 8;   // a few waves in all
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    const dim3 grid((unsigned)gx, (unsigned)ctx.n_events);
+    if (count) {
+        seg_layer_lists_kernel<<<ctx.n_events, 32 * SEG_MAX_LAYERS, 0, st>>>(layer, ctx, n_layers, pairs);
+        seg_rows_kernel<T, false><<<grid, 256, 0, st>>>(r, phi, z, pid, pairs, cuts, ctx, capacity, nullptr, nullptr, nullptr);
+        seg_scan_kernel<<<ctx.n_events, 1024, 0, st>>>(ctx, capacity, n_edges);
+    }
+    if (fill)
+        seg_rows_kernel<T, true><<<grid, 256, 0, st>>>(r, phi, z, pid, pairs, cuts, ctx, capacity, src, dst, y);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
@@ -252,19 +302,40 @@ int build_segments(const int32_t* layer, const void* r, const void* phi, const v
                    const int64_t* pid, int n_hits, const int32_t* layer_pairs_host, int n_pairs, int n_layers,
                    double slope_in, double slope_out, double z0_max, int outer_from, int node_offset, int capacity,
                    int32_t* src, int32_t* dst, float* y, int32_t* n_edges, void* ws, cudaStream_t st) {
-    SegPairs pairs;
-    pairs.n = n_pairs;
-    for (int p = 0; p < SEG_MAX_PAIRS; ++p) {
-        pairs.l1[p] = p < n_pairs ? layer_pairs_host[2 * p] : 0;
-        pairs.l2[p] = p < n_pairs ? layer_pairs_host[2 * p + 1] : 0;
-    }
+    const SegPairs pairs = seg_pairs(layer_pairs_host, n_pairs);
+    SegCtx ctx;
+    ctx.hit_off = nullptr; ctx.n_events = 1; ctx.n_hits = n_hits; ctx.node_offset = node_offset;
+    ctx.hits_pad = (n_hits + 3) & ~3; ctx.n_pairs = n_pairs; ctx.ws = static_cast<int*>(ws);
+    const bool fill = src && dst && capacity > 0;
     if (dtype_bytes == 4)
-        return build_segments_t<float>(layer, static_cast<const float*>(r), static_cast<const float*>(phi),
-                                       static_cast<const float*>(z), pid, n_hits, pairs, n_layers, slope_in, slope_out,
-                                       z0_max, outer_from, node_offset, capacity, src, dst, y, n_edges, ws, st);
-    return build_segments_t<double>(layer, static_cast<const double*>(r), static_cast<const double*>(phi),
-                                    static_cast<const double*>(z), pid, n_hits, pairs, n_layers, slope_in, slope_out,
-                                    z0_max, outer_from, node_offset, capacity, src, dst, y, n_edges, ws, st);
+        return seg_run<float>(layer, static_cast<const float*>(r), static_cast<const float*>(phi), static_cast<const float*>(z),
+                              pid, ctx, n_hits, pairs, n_layers, seg_cuts<float>(slope_in, slope_out, z0_max, outer_from),
+                              true, fill, capacity, src, dst, y, n_edges, st);
+    return seg_run<double>(layer, static_cast<const double*>(r), static_cast<const double*>(phi), static_cast<const double*>(z),
+                           pid, ctx, n_hits, pairs, n_layers, seg_cuts<double>(slope_in, slope_out, z0_max, outer_from),
+                           true, fill, capacity, src, dst, y, n_edges, st);
+}
+
+// All events of a batch in one set of launches.  e_max == 0: the counting pass (n_edges[2b] = edges of
+// event b); e_max > 0: the filling pass alone, on the workspace the counting pass left behind.
+int build_segments_batch(const int32_t* layer, const void* r, const void* phi, const void* z, int dtype_bytes,
+                         const int64_t* pid, int n_events, const int32_t* hit_off, int total_hits, int max_hits,
+                         const int32_t* layer_pairs_host, int n_pairs, int n_layers, double slope_in, double slope_out,
+                         double z0_max, int outer_from, int e_max, int32_t* src, int32_t* dst, float* y, int32_t* n_edges,
+                         void* ws, cudaStream_t st) {
+    if (n_events == 0) return GNNSEG_OK;
+    const SegPairs pairs = seg_pairs(layer_pairs_host, n_pairs);
+    SegCtx ctx;
+    ctx.hit_off = hit_off; ctx.n_events = n_events; ctx.n_hits = 0; ctx.node_offset = 0;
+    ctx.hits_pad = (total_hits + 3) & ~3; ctx.n_pairs = n_pairs; ctx.ws = static_cast<int*>(ws);
+    const bool fill = e_max > 0;
+    if (dtype_bytes == 4)
+        return seg_run<float>(layer, static_cast<const float*>(r), static_cast<const float*>(phi), static_cast<const float*>(z),
+                              pid, ctx, max_hits, pairs, n_layers, seg_cuts<float>(slope_in, slope_out, z0_max, outer_from),
+                              !fill, fill, e_max, src, dst, y, n_edges, st);
+    return seg_run<double>(layer, static_cast<const double*>(r), static_cast<const double*>(phi), static_cast<const double*>(z),
+                           pid, ctx, max_hits, pairs, n_layers, seg_cuts<double>(slope_in, slope_out, z0_max, outer_from),
+                           !fill, fill, e_max, src, dst, y, n_edges, st);
 }
 
 int scale_features(const void* a, const void* b, const void* c, int dtype_bytes, int n, double sa, double sb, double sc,

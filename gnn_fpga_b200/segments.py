@@ -153,8 +153,8 @@ def construct_graphs_device(hits, layer_pairs, phi_slope_max, phi_slope_mid_max,
     """The event loop of construct_graphs (gnn/graph.py:145-175: group the hit table by `evtid`, events
     in order of first appearance, construct_graph per event) as ONE padded device batch: the hit
     columns of all selected events go to the device in one copy each, the cuts run per event
-    (gnnseg_build_segments with the event's node offset, writing straight into the event's slot
-    range), one host read (the per-event edge counts) in between.
+    (gnnseg_build_segments_batch: every event in one set of launches, counting pass then filling pass
+    straight into the events' slot ranges), one host read (the per-event edge counts) in between.
     Returns (batch, y, n_edges): a DeviceGraphBatch of B events padded to e_max = max edge count
     exactly as merge_graphs pads (absent slots -1), labels (B, e_max) float32 with zeros in the padding,
     and the edge count of every event."""
@@ -181,34 +181,29 @@ def construct_graphs_device(hits, layer_pairs, phi_slope_max, phi_slope_mid_max,
     if n_layers > 32 or pairs.shape[0] > 32:
         raise ValueError("at most 32 layers and 32 layer pairs")
     nb = 4 if r.dtype == torch.float32 else 8
-    n_big = max(n_per) if B else 0
-    wsb = L.gnnseg_segments_workspace_bytes(n_big, pairs.shape[0])
+    n_big, n_tot = (max(n_per) if B else 0), int(node_off[-1])
+    wsb = L.gnnseg_segments_batch_workspace_bytes(B, n_tot, pairs.shape[0])
     ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
     counts = torch.zeros((max(B, 1), 2), dtype=torch.int32, device=dev)
-    at = lambda t, off, size: C.c_void_p(t.data_ptr() + off * size)
+    hit_off = torch.as_tensor(node_off.astype(np.int32)).to(dev)
 
-    def call(b, cap, src, dst, y, slot0):
-        o, n = int(node_off[b]), n_per[b]
-        _lib.check(L.gnnseg_build_segments(at(layer, o, 4), at(r, o, nb), at(phi, o, nb), at(z, o, nb), nb,
-                                           at(pid, o, 8) if pid is not None else None, n, pairs.ctypes.data, pairs.shape[0],
-                                           n_layers, float(phi_slope_max), float(phi_slope_outer_max), float(z0_max),
-                                           int(outer_from_layer), o, cap,
-                                           at(src, slot0, 4) if src is not None else None,
-                                           at(dst, slot0, 4) if dst is not None else None,
-                                           at(y, slot0, 4) if y is not None else None, at(counts, 2 * b, 4), _ptr(ws), wsb,
-                                           _stream_ptr(dev)), "gnnseg_build_segments")
+    def call(e_max, src, dst, y):
+        opt = lambda t: _ptr(t) if t is not None else None
+        _lib.check(L.gnnseg_build_segments_batch(_ptr(layer), _ptr(r), _ptr(phi), _ptr(z), nb, opt(pid), B, _ptr(hit_off), n_tot,
+                                                 n_big, pairs.ctypes.data, pairs.shape[0], n_layers, float(phi_slope_max),
+                                                 float(phi_slope_outer_max), float(z0_max), int(outer_from_layer), e_max,
+                                                 opt(src), opt(dst), opt(y), _ptr(counts), _ptr(ws), wsb, _stream_ptr(dev)),
+                   "gnnseg_build_segments_batch")
 
     with torch.cuda.device(dev):
-        for b in range(B):
-            call(b, 0, None, None, None, 0)                         # count
+        call(0, None, None, None)                                   # count: every event in one set of launches
         n_edges = counts[:B, 0].cpu().numpy().astype(np.int64)      # the one host read
         e_max = int(n_edges.max()) if B else 0
         src = torch.full((B * e_max,), -1, dtype=torch.int32, device=dev)
         dst = torch.full((B * e_max,), -1, dtype=torch.int32, device=dev)
         y = torch.zeros((B, e_max), dtype=torch.float32, device=dev)
-        for b in range(B):
-            if n_edges[b]:
-                call(b, int(n_edges[b]), src, dst, y if pid is not None else None, b * e_max)   # fill
+        if e_max:
+            call(e_max, src, dst, y if pid is not None else None)   # fill, on the offsets the count left in ws
     X = scale_features_device([take(cols[k]) for k in feature_names], feature_scale, device=dev)
     batch = DeviceGraphBatch(X, src, dst, B, e_max, n_nodes_per_event=n_per)
     return batch, y, n_edges

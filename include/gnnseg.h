@@ -324,6 +324,26 @@ int gnnseg_build_segments(const int32_t* layer, const void* r, const void* phi, 
                           int outer_from_layer, int node_offset, int capacity,
                           int32_t* src, int32_t* dst, float* y, int32_t* n_edges,
                           void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * The same for all events of a batch in one set of launches (the event loop of construct_graphs,
+ * gnn/graph.py:145-175).  The hit columns hold the events back to back; event b owns rows
+ * [hit_off[b], hit_off[b+1]) (hit_off: DEVICE array of n_events + 1 words; total_hits = hit_off[n_events];
+ * max_hits_per_event sizes the grid).  Node ids are row numbers of the concatenated table; event b's
+ * edges go to slots [b*e_max, b*e_max + count_b) of src / dst / y (the caller pre-fills the padding
+ * with -1 / 0).  Two calls:
+ *   e_max == 0  counting pass: n_edges[2b] = number of kept pairs of event b (device words);
+ *   e_max  > 0  filling pass alone; it needs the workspace exactly as the counting pass on the same
+ *               arguments left it.  e_max >= every count.  n_events <= 65535.
+ */
+size_t gnnseg_segments_batch_workspace_bytes(int n_events, int total_hits, int n_pairs);
+int gnnseg_build_segments_batch(const int32_t* layer, const void* r, const void* phi, const void* z,
+                                int dtype_bytes, const int64_t* particle_id, int n_events,
+                                const int32_t* hit_off, int total_hits, int max_hits_per_event,
+                                const int32_t* layer_pairs_host, int n_pairs, int n_layers,
+                                double phi_slope_max, double phi_slope_outer_max, double z0_max,
+                                int outer_from_layer, int e_max, int32_t* src, int32_t* dst, float* y,
+                                int32_t* n_edges, void* ws, size_t ws_bytes, void* stream);
 /* X (n_hits, 3) float32 = (column / scale) computed in float64 then rounded, as
  * (hits[feature_names].values / feature_scale).astype(np.float32), gnn/graph.py:118. */
 int gnnseg_scale_features(const void* a, const void* b, const void* c, int dtype_bytes, int n_hits,

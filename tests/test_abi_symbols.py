@@ -99,3 +99,14 @@ def test_node_classifier_entry_points_check_arguments_on_the_host():
     assert L.gnnseg_forward_nodes_train(None, None, None, None, F, h, 65, None, None, 0, None) == -1
     assert L.gnnseg_backward_nodes(None, None, None, None, F, h, T, None, None, None, None, None, 0, None) == -1
     assert L.gnnseg_backward_nodes(None, None, None, None, F, 7, T, None, None, None, None, None, 0, None) == -2
+
+
+def test_batched_segment_entry_point_checks_arguments_on_the_host():
+    L = _lib.lib()
+    assert L.gnnseg_segments_batch_workspace_bytes(64, 256000, 9) >= 4 * (64 * 68 + 256000 + 9 * 256000 + 64)
+    assert L.gnnseg_segments_batch_workspace_bytes(1, 1000, 33) == 0
+    args = lambda **k: [None, None, None, None, k.get("nb", 4), None, k.get("B", 2), None, 100, 60, None, 0, k.get("nl", 10),
+                        1.0, 1.0, 1.0, 5, 0, None, None, None, None, None, 0, None]
+    assert L.gnnseg_build_segments_batch(*args()) == -1            # no workspace / columns
+    assert L.gnnseg_build_segments_batch(*args(nb=2)) == -2        # dtype
+    assert L.gnnseg_build_segments_batch(*args(nl=40)) == -1
