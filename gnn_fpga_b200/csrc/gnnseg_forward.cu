@@ -371,11 +371,12 @@ input_kernel(const float* __restrict__ blob, const float* __restrict__ X, const 
 // Measured on B200 (scripts/micro/gather_bench.cu): the rate at which an SM gathers random 128-byte
 // rows with LDG.128 grows with the number of resident WARPS, not with the loads a thread keeps in
 // flight (5 TB/s at 16 warps per SM, 9 at 32, 15 at 64, the same for 4, 8 or 16 loads per thread).
-// So the rows of only two slots are in flight per lane group, indices are fetched per pair, and the
-// register budget is set for 48 resident warps (40 registers; 32 registers / 64 warps spills and
-// measured 52 us against 46 us).
-template <int H>
-__global__ void __launch_bounds__(256, 6)
+// In this kernel the product (resident warps x rows in flight per warp) is flat around its optimum:
+// at hidden_dim 32, two slots per lane group at 48 warps (40 registers) 44.5 us, four slots at 32 warps
+// 44.0, four at 40 warps 47.1, one slot at 64 warps (32 registers, nothing spilled) 50.9.  PAIRS slots
+// are in flight per lane group, indices are fetched per group of PAIRS.
+template <int H, int PAIRS = 2, int MINB = 6>
+__global__ void __launch_bounds__(256, MINB)
 edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
             const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
             const int32_t* __restrict__ in_pos, const int32_t* __restrict__ out_pos,
@@ -384,7 +385,7 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
     using B = Blob<H>;
     constexpr int G = H / 4;        // lanes that share one edge (one float4 of P each)
     constexpr int EPP = 32 / G;     // edges a warp handles per iteration; G iterations cover 32 slots
-    constexpr int PAIR = G >= 2 ? 2 : 1;
+    constexpr int PAIR = G >= PAIRS ? PAIRS : (G >= 2 ? 2 : 1);
     const int lane = threadIdx.x & 31;
     const int c = lane % G, g = lane / G;
     const uint64_t keep = l2_policy_evict_last();   // every P row is gathered ~deg times
@@ -418,6 +419,8 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
 #pragma unroll
             for (int q = 0; q < PAIR; ++q) {
                 // absent start: W1a.0 + b1; absent end: W1b.0.  Branch free: row 0 is loaded and dropped.
+                // (Selecting the pointer instead of the values, or a warp-uniform branch around the selects,
+                // costs registers: 72 - 200 bytes of spills at the same launch bounds.)
                 a[q] = ldg4_hint(Pa + (size_t)max(s[q], 0) * (2 * H), keep);
                 b[q] = ldg4_hint(Pb + (size_t)max(d[q], 0) * (2 * H), keep);
             }
@@ -768,12 +771,16 @@ static int launch_edge(const float* blob, const GnnsegGraph* g, const float* P, 
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int warps_needed = (g->n_slots + 31) / 32;
     int grid = (warps_needed + 7) / 8;
-    const int occ = cached_occupancy<edge_kernel<H>>(256, 0);   // resident CTAs per SM: one full wave, the warps stride over the slots
+    // hidden_dim 64: four slots (eight rows) in flight per lane group at 40 resident warps measured 55.6 us
+    // against 59.8 us for the two-slot form at mu200 size; at hidden_dim 32 the two forms are level
+    // (44.0 - 47.1 us against 44.5 us), so the narrower rows keep the two-slot form and 48 warps.
+    constexpr int PAIRS = H >= 64 ? 4 : 2, MINB = H >= 64 ? 5 : 6;
+    const int occ = cached_occupancy<edge_kernel<H, PAIRS, MINB>>(256, 0);   // resident CTAs per SM: one full wave, the warps stride over the slots
     if (occ < 1) return GNNSEG_ECUDA;
     const int cap = sms * occ;
     if (grid > cap) grid = cap;
-    if (launch_pdl(edge_kernel<H>, grid, 256, 0, st, use_pdl(g->n_slots), blob, P, g->src, g->dst, g->in_pos, g->out_pos, g->n_slots,
-                   e, e_in, e_out) != cudaSuccess)
+    if (launch_pdl(edge_kernel<H, PAIRS, MINB>, grid, 256, 0, st, use_pdl(g->n_slots), blob, P, g->src, g->dst, g->in_pos, g->out_pos,
+                   g->n_slots, e, e_in, e_out) != cudaSuccess)
         return GNNSEG_ECUDA;
     return check_launch();
 }
