@@ -20,6 +20,8 @@
 //   thread 0              GEMM3 (TS: A3 from TMEM, WP from smem) -> D3 (160 columns)
 //   epilogue              D3 -> +bias -> P' and Q' to global
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>
 #include "gnnseg_common.cuh"
 
 namespace gnnseg {
@@ -96,6 +98,15 @@ __device__ __forceinline__ void split3(const float x, float& hi, float& lo) {
     lo = __uint_as_float(tf32_rna(x - hi));
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA store of one box (shared -> global) described by a tensor map; bulk async group per issuing thread
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const uint32_t smem_addr, const int x, const int y,
+                                             const uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_addr), "r"(x), "r"(y), "l"(policy) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -544,18 +555,25 @@ struct TcMlpCfg {
     static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 };
 
-template <int H>
+// TMA = true: P', Q' leave through TMA stores (cp.async.bulk.tensor) of the swizzled 32 x 32 tiles: the
+// hardware's 128-byte swizzle is the tile's own (16-byte chunk j of row r at j ^ (r & 7)), rows past
+// n_nodes are clipped by the tensor map, and the MLP warps no longer read the tile back.
+template <int H, bool TMA>
 __global__ void __launch_bounds__(TcMlpCfg<H>::NT, 2)
 node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4, const float* h1,
                    const int ld_h1, const int n_nodes, const int n_tiles, float* P_out,
-                   float* __restrict__ Q_out, const int write_q, float* __restrict__ H_save) {
+                   float* __restrict__ Q_out, const int write_q, float* __restrict__ H_save,
+                   const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
+                   const __grid_constant__ CUtensorMap tmQ16) {
     // h1 may alias P_out (row n of h1 inside row n of P'): no __restrict__, no read-only loads on those two
     using C = TcMlpCfg<H>;
     using N = TcCfg<H>;
     using B = Blob<H>;
     constexpr int TM = C::TM, NT = C::NT, ET = C::ET, LT = C::LT, NP = N::NP;
     constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_EPI = 3;
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // the store tiles (offset 0, 4 KB apart) must sit on 1024-byte boundaries for the 128-byte swizzle
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* sB4 = reinterpret_cast<float*>(smem + C::O_BIAS);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
@@ -720,41 +738,81 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
                     return to_p ? P_out + (size_t)node_w0 * 2 * H + col : Q_out + (size_t)node_w0 * 3 * H + (col - 2 * H);
                 };
                 const int n_full = write_q ? 2 : 1;                          // 32-column chunks hf, hf + 2 (P' only: chunk hf)
+                if constexpr (TMA) {
+                    const uint32_t s_tile = smem_u32(sOut);
 #pragma unroll 1
-                for (int t = 0; t < n_full; ++t) {
-                    const int c0 = 32 * (hf + 2 * t);
-                    stage16(c0, 0);
-                    stage16(c0 + 16, 4);
-                    __syncwarp();
-                    int ld;
-                    float* base = out_ptr(c0, ld);
+                    for (int t = 0; t < n_full; ++t) {
+                        const int c0 = 32 * (hf + 2 * t);
+                        float v0[16], v1[16];
+                        tmem_ld16(lane_base + C::C_D3 + c0, v0);
+                        tmem_ld16(lane_base + C::C_D3 + c0 + 16, v1);
+                        if (lane == 0) tma_store_wait_read();                // the previous box has left the tile
+                        __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 4 * i + (lane >> 3), j = lane & 7;
-                        if (node_w0 + r < n_nodes)
-                            st4_hint(base + (size_t)r * ld + 4 * j, lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2)), stream);
+                        for (int i = 0; i < 4; ++i) {
+                            st4(sOut + lane * 32 + ((i ^ (lane & 7)) << 2), make_float4(v0[4 * i], v0[4 * i + 1], v0[4 * i + 2], v0[4 * i + 3]));
+                            st4(sOut + lane * 32 + (((4 + i) ^ (lane & 7)) << 2), make_float4(v1[4 * i], v1[4 * i + 1], v1[4 * i + 2], v1[4 * i + 3]));
+                        }
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (c0 < 2 * H) tma_store_2d(&tmP, s_tile, c0, node_w0, stream);
+                            else            tma_store_2d(&tmQ, s_tile, c0 - 2 * H, node_w0, stream);
+                        }
                     }
-                    __syncwarp();
-                }
-                if (write_q) {                                               // last chunk: 16 columns per warp
-                    const int c0 = 128 + 16 * hf;
-                    stage16(c0, 0);
-                    __syncwarp();
-                    int ld;
-                    float* base = out_ptr(c0, ld);
+                    if (write_q) {                                           // last chunk: 16 columns per warp, dense [32][16] tile
+                        const int c0 = 128 + 16 * hf;
+                        float v[16];
+                        tmem_ld16(lane_base + C::C_D3 + c0, v);
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = 8 * i + (lane >> 2), j = lane & 3;
-                        if (node_w0 + r < n_nodes)
-                            st4_hint(base + (size_t)r * ld + 4 * j, lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2)), stream);
+                        for (int i = 0; i < 4; ++i)
+                            st4(sOut + lane * 16 + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) tma_store_2d(&tmQ16, s_tile, c0 - 2 * H, node_w0, stream);
                     }
+                    if (lane == 0) tma_store_wait_read();                    // the tiles alias the A buffer of the next tile
                     __syncwarp();
+                } else {
+#pragma unroll 1
+                    for (int t = 0; t < n_full; ++t) {
+                        const int c0 = 32 * (hf + 2 * t);
+                        stage16(c0, 0);
+                        stage16(c0 + 16, 4);
+                        __syncwarp();
+                        int ld;
+                        float* base = out_ptr(c0, ld);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 4 * i + (lane >> 3), j = lane & 7;
+                            if (node_w0 + r < n_nodes)
+                                st4_hint(base + (size_t)r * ld + 4 * j, lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2)), stream);
+                        }
+                        __syncwarp();
+                    }
+                    if (write_q) {                                               // last chunk: 16 columns per warp
+                        const int c0 = 128 + 16 * hf;
+                        stage16(c0, 0);
+                        __syncwarp();
+                        int ld;
+                        float* base = out_ptr(c0, ld);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = 8 * i + (lane >> 2), j = lane & 3;
+                            if (node_w0 + r < n_nodes)
+                                st4_hint(base + (size_t)r * ld + 4 * j, lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2)), stream);
+                        }
+                        __syncwarp();
+                    }
                 }
             }
             tc_fence_before();
             tc_bar_sync(BAR_EPI, ET);     // TMEM tiles and the store tiles are rewritten by the next tile
             if (tile + (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY, ET + LT);
         }
+        if (TMA && lane == 0) tma_store_wait_all();           // the boxes have reached global memory
     }
     tc_fence_before();
     __syncthreads();
@@ -1182,17 +1240,59 @@ int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, flo
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// fp32 matrix [rows][cols] (row major) seen as boxes of box_cols x 32 rows
+static bool make_store_map(CUtensorMap* tm, float* base, int rows, int cols, int box_cols, bool swizzle128) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int launch_node_mlp_tc32(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
                          float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st) {
     using C = TcMlpCfg<32>;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
-    if (!ensure_dynamic_smem<node_mlp_kernel_tc<32>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
+    constexpr int SMEM = C::SMEM_BYTES + 1024;                      // room to align the store tiles to 1024 bytes
     const int sms = cached_sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;        // two CTAs per SM
-    if (launch_pdl(node_mlp_kernel_tc<32>, grid, C::NT, C::SMEM_BYTES, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, P_out,
-                   Q_out, write_q, H_save) != cudaSuccess)
+    static const bool tma = [] { const char* v = std::getenv("GNNSEG_MLP_STORE"); return v && v[0] == 't'; }();
+    CUtensorMap tmP, tmQ, tmQ16;
+    memset(&tmP, 0, sizeof(tmP)); memset(&tmQ, 0, sizeof(tmQ)); memset(&tmQ16, 0, sizeof(tmQ16));
+    if (tma) {
+        if (!make_store_map(&tmP, P_out, n_nodes, 64, 32, true)) return GNNSEG_ECUDA;
+        if (write_q && (!make_store_map(&tmQ, Q_out, n_nodes, 96, 32, true) || !make_store_map(&tmQ16, Q_out, n_nodes, 96, 16, false)))
+            return GNNSEG_ECUDA;
+        if (!ensure_dynamic_smem<node_mlp_kernel_tc<32, true>>(SMEM)) return GNNSEG_ECUDA;
+        if (launch_pdl(node_mlp_kernel_tc<32, true>, grid, C::NT, SMEM, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, P_out,
+                       Q_out, write_q, H_save, tmP, tmQ, tmQ16) != cudaSuccess)
+            return GNNSEG_ECUDA;
+        return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+    }
+    if (!ensure_dynamic_smem<node_mlp_kernel_tc<32, false>>(SMEM)) return GNNSEG_ECUDA;
+    if (launch_pdl(node_mlp_kernel_tc<32, false>, grid, C::NT, SMEM, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, P_out,
+                   Q_out, write_q, H_save, tmP, tmQ, tmQ16) != cudaSuccess)
         return GNNSEG_ECUDA;
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
