@@ -255,6 +255,8 @@ class SegmentClassifier(nn.Module):
         # (its threads spin between batches) makes the per-batch time jump by 2x
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))     # ranks sharing this host (torchrun)
         pack_threads = max(1, (os.cpu_count() or 4) // local_world - 2)
+        if os.environ.get("GNNSEG_PACK_THREADS"):                     # explicit size of the packer's OpenMP team
+            pack_threads = max(1, int(os.environ["GNNSEG_PACK_THREADS"]))
 
         def pack(graphs, slot):
             if _is_file_batch(graphs):                                   # graph files: mapped, parsed and packed by the library
