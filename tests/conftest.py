@@ -24,6 +24,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built library (*.so is git-ignored): build it once (nvcc cross-compiles
+    without a GPU).  Nothing happens when the library is already there."""
+    if not os.path.exists(os.path.join(ROOT, "gnn_fpga_b200", "libgnnseg_b200.so")):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def load_case(name):
     """Golden record written by oracle/make_golden.py (outputs of the reference itself)."""
     import torch
