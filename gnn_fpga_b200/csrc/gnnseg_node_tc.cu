@@ -28,6 +28,26 @@ namespace gnnseg {
 
 bool use_pdl(int n_slots);   // gnnseg_forward.cu
 
+// `make trace` builds ../libgnnseg_trace.so with -DGNNSEG_TRACE: node_mlp_kernel_tc<32> then records
+// clock64 stamps per role of CTA 0 at the phase boundaries of every tile and %globaltimer at entry /
+// exit of every CTA (scripts/mlp_trace.py reads them).  The shipped library has none of this.
+#ifdef GNNSEG_TRACE
+__device__ long long g_trace[2][16][12];
+__device__ unsigned long long g_cta[512][2];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE_MLP(t, k) do { if (blockIdx.x == 0 && tid == 0 && (t) < 16) g_trace[0][(t)][(k)] = clock64(); } while (0)
+#define TRACE_LDR(t, k) do { if (blockIdx.x == 0 && tid == ET && (t) < 16) g_trace[1][(t)][(k)] = clock64(); } while (0)
+#define TRACE_CTA(k) do { if (tid == 0 && blockIdx.x < 512) g_cta[blockIdx.x][(k)] = gtimer(); } while (0)
+#else
+#define TRACE_MLP(t, k) do { } while (0)
+#define TRACE_LDR(t, k) do { } while (0)
+#define TRACE_CTA(k) do { } while (0)
+#endif
+
 template <int H>
 struct TcCfg {
     static constexpr int TM   = 128;                 // nodes per tile = UMMA M
@@ -578,6 +598,8 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    TRACE_MLP(15, 0);                                  // kernel entry
+    TRACE_CTA(0);
 
     static_assert(C::O_W4L == C::O_W4H + H * H * 4 && C::O_WPH == C::O_W4L + H * H * 4 &&
                   C::O_WPL == C::O_WPH + NP * N::D4P * 4, "image order");
@@ -593,7 +615,9 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
                      ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    TRACE_MLP(15, 1);                                  // copies issued, barrier + TMEM set up
     cp_async_wait_all();
+    TRACE_MLP(15, 2);                                  // weight images have arrived
     fence_async_smem();
     tc_fence_before();
     pdl_launch_dependents();
@@ -601,6 +625,7 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     pdl_wait();                    // h1 comes from the gather kernel before
+    TRACE_MLP(15, 3);                                  // prologue done
 
     if (tid >= ET) {
         // ================================ loader warps ==================================
@@ -622,7 +647,9 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
         if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            TRACE_LDR(it, 0);
             if (it >= 1) tc_bar_sync(BAR_EMPTY, ET + LT);       // the previous tile's stores have left the buffer
+            TRACE_LDR(it, 1);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float4 hh, hl;
@@ -633,7 +660,9 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
             }
             fence_async_smem();                                // generic-proxy writes -> tensor core reads
             tc_bar_arrive(BAR_FULL, ET + LT);
+            TRACE_LDR(it, 2);
             if (tile + (int)gridDim.x < n_tiles) fetch(tile + gridDim.x);
+            TRACE_LDR(it, 3);
         }
     } else {
         // ================================ MLP (issuer + epilogue) ======================
@@ -646,13 +675,16 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
         float* sOut = reinterpret_cast<float*>(smem + C::O_A + warp * 4096);   // this warp's 32 x 32 store tile
         const uint64_t stream = l2_policy_evict_first();       // P', Q' are read next by another kernel
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        [[maybe_unused]] int itm = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itm) {
+            TRACE_MLP(itm, 0);
             const int n = tile * TM + row;
             const bool live = n < n_nodes;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live && hf == 0) x = ldg4(X4 + (size_t)n * 4);
             // ---- GEMM2: D2 = h1 . W4^T ----------------------------------------------------
             tc_bar_sync(BAR_FULL, ET + LT);
+            TRACE_MLP(itm, 1);
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t a_hi = sa + C::O_A, a_lo = a_hi + N::A_BYTES;
@@ -671,6 +703,7 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
             }
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
+            TRACE_MLP(itm, 2);
             // ---- epilogue 2: H' = tanh(D2 + b4); [H'|X|0] -> A3 (hi, lo) in TMEM -------------
             {
                 const int c0 = hf * (H / 2);
@@ -701,7 +734,9 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
             }
             tmem_st_wait();
             tc_fence_before();
+            TRACE_MLP(itm, 3);
             tc_bar_sync(BAR_EPI, ET);                          // A3 complete, every thread has read its D2 columns
+            TRACE_MLP(itm, 4);
             // ---- GEMM3: D3 = [H'|X] . WP^T  (A from tensor memory) --------------------------
             if (tid == 0) {
                 tc_fence_after();
@@ -718,6 +753,7 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
             }
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
+            TRACE_MLP(itm, 5);
             // ---- epilogue 3: [P'|Q'] = D3 + bias -> global, through a swizzled 32 x 32 tile per warp
             //      (16-byte chunk j of row r lives at chunk j ^ (r & 7)): conflict free both ways, every
             //      store instruction writes full 128-byte lines.  The two warps of a TMEM lane quarter
@@ -809,13 +845,18 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
                 }
             }
             tc_fence_before();
+            TRACE_MLP(itm, 6);
             tc_bar_sync(BAR_EPI, ET);     // TMEM tiles and the store tiles are rewritten by the next tile
+            TRACE_MLP(itm, 7);
             if (tile + (int)gridDim.x < n_tiles) tc_bar_arrive(BAR_EMPTY, ET + LT);
         }
         if (TMA && lane == 0) tma_store_wait_all();           // the boxes have reached global memory
     }
+    TRACE_MLP(15, 4);                                  // this thread's tiles done
     tc_fence_before();
     __syncthreads();
+    TRACE_MLP(15, 5);                                  // whole CTA done
+    TRACE_CTA(1);
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
@@ -1296,6 +1337,15 @@ int launch_node_mlp_tc32(const float* blob, const float* X4, const float* h1, in
         return GNNSEG_ECUDA;
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
+
+#ifdef GNNSEG_TRACE
+extern "C" int gnnseg_debug_read_trace(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 2 * 16 * 12) == cudaSuccess ? 0 : -4;
+}
+extern "C" int gnnseg_debug_read_cta(unsigned long long* out) {
+    return cudaMemcpyFromSymbol(out, g_cta, sizeof(unsigned long long) * 512 * 2) == cudaSuccess ? 0 : -4;
+}
+#endif
 
 int launch_node_mlp_tc64(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
                          float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st) {

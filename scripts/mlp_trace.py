@@ -1,5 +1,7 @@
-"""clock64 stamps per role of CTA 0 of node_mlp_kernel_tc<32> (needs a library built with -DGNNSEG_TRACE:
-see the comment in gnn_fpga_b200/csrc/gnnseg_node_tc.cu; run with GNNSEG_LIB=gnn_fpga_b200/libgnnseg_trace.so)."""
+"""clock64 stamps per role of CTA 0 of node_mlp_kernel_tc<32> and %globaltimer per CTA.
+    make -C gnn_fpga_b200/csrc trace
+    GNNSEG_LIB=gnn_fpga_b200/libgnnseg_trace.so python scripts/mlp_trace.py
+(the instrumented library is a separate build, see the Makefile; the shipped one carries no stamps)."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
