@@ -11,8 +11,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.abspath(os.environ["GNNSEG_LIB"]) if os.environ.get("GNNSEG_LIB") else os.path.join(_HERE, "libgnnseg_b200.so")
 
 OK = 0
-ABI_VERSION = 3
-ERRORS = {-1: "EINVAL", -2: "EUNSUPPORTED", -3: "EWORKSPACE", -4: "ECUDA", -5: "ENODEVICE", -6: "EIO", -7: "EFORMAT"}
+ABI_VERSION = 4
+ERRORS = {-1: "EINVAL", -2: "EUNSUPPORTED", -3: "EWORKSPACE", -4: "ECUDA", -5: "ENODEVICE", -6: "EIO", -7: "EFORMAT", -8: "EHYPEREDGE"}
+EHYPEREDGE = -8
 BAD_VALUE = 1
 BAD_HYPEREDGE = 2
 
@@ -36,6 +37,12 @@ class GnnsegNpzGraph(C.Structure):
                 ("Ri_rows", C.c_void_p), ("Ri_cols", C.c_void_p), ("n_in", C.c_int64),
                 ("Ro_rows", C.c_void_p), ("Ro_cols", C.c_void_p), ("n_out", C.c_int64),
                 ("y", C.c_void_p), ("n_y", C.c_int64)]
+
+
+class GnnsegStoreLayout(C.Structure):
+    _fields_ = [("n_events", C.c_int64), ("n_features", C.c_int32), ("col_bytes", C.c_int32)] + [(n, C.c_int64) for n in (
+        "total_nodes", "total_in", "total_out", "total_y", "o_node_off", "o_in_off", "o_out_off", "o_y_off",
+        "o_X", "o_in_ptr", "o_out_ptr", "o_in_col", "o_out_col", "o_y", "o_perm", "bytes")]
 
 
 class GnnsegGraph(C.Structure):
@@ -92,6 +99,12 @@ SIGNATURES = {
     "gnnseg_npz_close_graph_host": (C.c_int, [C.POINTER(GnnsegNpzGraph)]),
     "gnnseg_npz_open_batch_host": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "gnnseg_npz_close_batch_host": (C.c_int, [C.c_int, C.c_void_p]),
+    "gnnseg_store_plan_host": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GnnsegStoreLayout)]),
+    "gnnseg_store_fill_host": (C.c_int, [C.POINTER(GnnsegStoreLayout), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p]),
+    "gnnseg_assemble_batch": (C.c_int, [_i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_void_p, C.c_void_p,
+                                       C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, C.c_void_p]),
     "gnnseg_pack_sparse_batch_host": (C.c_int, [
         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

@@ -15,6 +15,8 @@ int dense_to_edges(const float*, const float*, int, int, int, int32_t*, int32_t*
 size_t csr_workspace_bytes(int, int);
 int build_csr(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
 int build_graph(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+int assemble_batch(const int32_t*, int, int, int, int, int, const int32_t*, const int32_t*, const void*, const void*, int,
+                   const GnnsegGraphMut&, cudaStream_t);
 // gnnseg_backward.cu
 struct GradOut {
     float* w_in; float* b_in; float* w_e1; float* b_e1; float* w_e2; float* b_e2;
@@ -147,6 +149,7 @@ const char* gnnseg_strerror(int code) {
         case GNNSEG_ENODEVICE:    return "no CUDA device";
         case GNNSEG_EIO:          return "file cannot be opened or mapped";
         case GNNSEG_EFORMAT:      return "not an .npz graph file (np.savez of X, Ri_rows, Ri_cols, Ro_rows, Ro_cols, y)";
+        case GNNSEG_EHYPEREDGE:   return "a column of Ri or Ro is listed more than once (hyper-edge)";
         default:                  return "unknown gnnseg error";
     }
 }
@@ -214,6 +217,23 @@ int gnnseg_build_graph(const int32_t* src, const int32_t* dst, int n_slots, int 
     if (n_slots > 0 && (!src || !dst || !in_eid || !in_nbr || !out_eid || !out_nbr)) return GNNSEG_EINVAL;
     return gnnseg::build_graph(src, dst, n_slots, n_nodes, in_ptr, in_eid, in_nbr, in_pos, out_ptr, out_eid,
                                out_nbr, out_pos, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_assemble_batch(const int32_t* meta, int B, int n_nodes, int e_max, int n_in, int n_out,
+                          const int32_t* in_ptr_local, const int32_t* out_ptr_local, const void* in_col,
+                          const void* out_col, int col_bytes, int32_t* src, int32_t* dst, int32_t* in_ptr,
+                          int32_t* in_eid, int32_t* in_nbr, int32_t* in_pos, int32_t* out_ptr, int32_t* out_eid,
+                          int32_t* out_nbr, int32_t* out_pos, void* stream) {
+    if (B < 0 || n_nodes < 0 || e_max < 0 || n_in < 0 || n_out < 0 || (col_bytes != 2 && col_bytes != 4)) return GNNSEG_EINVAL;
+    if ((long long)B * e_max > 0x7fffffffLL || (long long)n_nodes + B > 0x7fffffffLL) return GNNSEG_EINVAL;
+    if (!in_ptr || !out_ptr) return GNNSEG_EINVAL;
+    if (n_nodes > 0 && (!meta || !in_ptr_local || !out_ptr_local)) return GNNSEG_EINVAL;
+    if ((long long)B * e_max > 0 && (!src || !dst || !in_pos || !out_pos)) return GNNSEG_EINVAL;
+    if (n_in > 0 && (!in_col || !in_eid || !in_nbr)) return GNNSEG_EINVAL;
+    if (n_out > 0 && (!out_col || !out_eid || !out_nbr)) return GNNSEG_EINVAL;
+    const gnnseg::GnnsegGraphMut g{src, dst, in_ptr, in_eid, in_nbr, in_pos, out_ptr, out_eid, out_nbr, out_pos};
+    return gnnseg::assemble_batch(meta, B, n_nodes, e_max, n_in, n_out, in_ptr_local, out_ptr_local, in_col, out_col,
+                                  col_bytes, g, static_cast<cudaStream_t>(stream));
 }
 
 size_t gnnseg_forward_workspace_bytes(int n_nodes, int n_slots, int F, int h) {

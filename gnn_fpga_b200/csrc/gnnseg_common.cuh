@@ -6,6 +6,13 @@
 
 namespace gnnseg {
 
+// GnnsegGraph with writable members: what the graph-building kernels fill in
+struct GnnsegGraphMut {
+    int32_t* src; int32_t* dst;
+    int32_t* in_ptr; int32_t* in_eid; int32_t* in_nbr; int32_t* in_pos;
+    int32_t* out_ptr; int32_t* out_eid; int32_t* out_nbr; int32_t* out_pos;
+};
+
 // Dataflow ("projection first", exact algebra of gnn/model.py:69-81,113-125):
 //   every node carries, besides its features HX[n] = [H[n] | X[n]], five H-wide projections
 //     Ps[n] = W1[:, 0:D].HX[n] + b1      Pd[n] = W1[:, D:2D].HX[n]            (edge step inputs)
@@ -158,6 +165,31 @@ __device__ __forceinline__ float tanh_fast(const float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
     return fmaf(-2.f, r, 1.f);
+}
+// The same with one Newton step on the reciprocal (+2 FMA): the rcp.approx error (1 ulp of 2/(e+1), up to
+// 2.4e-7 absolute near -1) goes away, what is left is ex2.approx's 2^-22 relative error on e, at most
+// 1.2e-7 absolute on the result.  Used where a tanh feeds the recurrence directly (the node network's
+// two activations, the input network's): n*h evaluations per step, not E*h.
+__device__ __forceinline__ float tanh_node(const float x) {
+#ifdef GNNSEG_NODE_TANH_FAST
+    return tanh_fast(x);
+#else
+    float e, r;
+    const float a = x * 2.885390081777927f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+    const float d = e + 1.f;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    r = fmaf(r, fmaf(-d, r, 1.f), r);
+    return fmaf(-2.f, r, 1.f);
+#endif
+}
+// the edge network's hidden activation (E*h evaluations per step): the 5-instruction form
+__device__ __forceinline__ float tanh_edge(const float x) {
+#ifdef GNNSEG_EDGE_TANH_ACC
+    return tanh_node(x);
+#else
+    return tanh_fast(x);
+#endif
 }
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
     acc.x = fmaf(w, v.x, acc.x);

@@ -346,7 +346,7 @@ input_kernel(const float* __restrict__ blob, const float* __restrict__ X, const 
                 fma4(v, x.y, lds4(sWin + 1 * H + 4 * c));
                 fma4(v, x.z, lds4(sWin + 2 * H + 4 * c));
                 fma4(v, x.w, lds4(sWin + 3 * H + 4 * c));
-                v.x = tanh_fast(v.x); v.y = tanh_fast(v.y); v.z = tanh_fast(v.z); v.w = tanh_fast(v.w);
+                v.x = tanh_node(v.x); v.y = tanh_node(v.y); v.z = tanh_node(v.z); v.w = tanh_node(v.w);
                 if (H_save && node0 + ln < n_nodes) st4(H_save + (size_t)(node0 + ln) * H + 4 * c, v);   // training: H0
             } else {
                 v = x;
@@ -429,10 +429,10 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
             for (int q = 0; q < PAIR; ++q) {
                 if (s[q] < 0) a[q] = ldg4(blob + B::BP + 4 * c);
                 if (d[q] < 0) b[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                float t = w2.x * tanh_fast(a[q].x + b[q].x);
-                t = fmaf(w2.y, tanh_fast(a[q].y + b[q].y), t);
-                t = fmaf(w2.z, tanh_fast(a[q].z + b[q].z), t);
-                z[p0 + q] = fmaf(w2.w, tanh_fast(a[q].w + b[q].w), t);
+                float t = w2.x * tanh_edge(a[q].x + b[q].x);
+                t = fmaf(w2.y, tanh_edge(a[q].y + b[q].y), t);
+                t = fmaf(w2.z, tanh_edge(a[q].z + b[q].z), t);
+                z[p0 + q] = fmaf(w2.w, tanh_edge(a[q].w + b[q].w), t);
             }
         }
         // transposed butterfly: G partial sums on each of G lanes -> lane c holds the total of
@@ -463,8 +463,8 @@ edge_kernel(const float* __restrict__ blob, const float* __restrict__ P,
 // (see edge_kernel for the measured trade).  h1 rows are written with stride ld_out; the tensor-core
 // MLP kernel (node_mlp_kernel_tc) reads them back.
 // ------------------------------------------------------------------------------------
-template <int H, int U = 3, int MINB = 8>
-__global__ void __launch_bounds__(256, MINB)
+template <int H, int U = 3, int MINB = 8, int NTHR = 256, bool RANGES = false>
+__global__ void __launch_bounds__(NTHR, MINB)
 node_gather_kernel(const GnnsegGraph g, const float* __restrict__ Q_in, const float* __restrict__ e_in,
                    const float* __restrict__ e_out, float* __restrict__ h1_out, const int ld_out,
                    float* __restrict__ h1_save) {
@@ -499,15 +499,23 @@ node_gather_kernel(const GnnsegGraph g, const float* __restrict__ Q_in, const fl
                 if (nb[u] >= 0) fma4(acc, w[u], v[u]);                        // nb < 0: half edge, the zero row
         }
     };
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
+    // RANGES: every CTA sweeps one contiguous range of nodes (neighbouring nodes share neighbours when the
+    // batch was renumbered for locality: the rows stay in this SM's L1); otherwise grid-stride
+    long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, idx1 = total, step = (long long)gridDim.x * blockDim.x;
+    if (RANGES) {
+        const long long chunk = ((total + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
+        idx0 = (long long)blockIdx.x * chunk + threadIdx.x;
+        idx1 = min(total, (long long)(blockIdx.x + 1) * chunk);
+        step = blockDim.x;
+    }
+    for (long long idx = idx0; idx < idx1; idx += step) {
         const int n = (int)(idx / G), c = (int)(idx % G);
         const int i0 = __ldg(g.in_ptr + n), i1 = __ldg(g.in_ptr + n + 1);
         const int o0 = __ldg(g.out_ptr + n), o1 = __ldg(g.out_ptr + n + 1);
         float4 acc = ldg4(Q_in + (size_t)n * 3 * H + 2 * H + 4 * c);             // Qs[n] (holds b3)
         row_sum(g.in_nbr, e_in, Q_in + 4 * c, i0, i1, acc);
         row_sum(g.out_nbr, e_out, Q_in + H + 4 * c, o0, o1, acc);
-        acc.x = tanh_fast(acc.x); acc.y = tanh_fast(acc.y); acc.z = tanh_fast(acc.z); acc.w = tanh_fast(acc.w);
+        acc.x = tanh_node(acc.x); acc.y = tanh_node(acc.y); acc.z = tanh_node(acc.z); acc.w = tanh_node(acc.w);
         st4(h1_out + (size_t)n * ld_out + 4 * c, acc);
         if (h1_save) st4(h1_save + (size_t)n * H + 4 * c, acc);
     }
@@ -654,7 +662,7 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __
                         csr_row_sum<false>(nullptr, g.in_nbr, e_in, Q_in + 4 * c, 3 * H, i0, i1, acc);
                         csr_row_sum<false>(nullptr, g.out_nbr, e_out, Q_in + H + 4 * c, 3 * H, o0, o1, acc);
                     }
-                    acc.x = tanh_fast(acc.x); acc.y = tanh_fast(acc.y); acc.z = tanh_fast(acc.z); acc.w = tanh_fast(acc.w);
+                    acc.x = tanh_node(acc.x); acc.y = tanh_node(acc.y); acc.z = tanh_node(acc.z); acc.w = tanh_node(acc.w);
                     if (h1_save) st4(h1_save + (size_t)n * H + 4 * c, acc);       // training: kept for the backward pass
                 }
                 st4(sHb + ln * SH + 4 * c, acc);
@@ -677,15 +685,15 @@ node_kernel(const float* __restrict__ blob, const GnnsegGraph g, const float* __
             // ---- layer 2: H' = tanh(W4 . h1 + b4) ---------------------------------------
             if constexpr (MMA) {
                 tile_gemm_mma<H / 8, H>(sHb, SH, sW4, SH, [&](int ln, int o, float v0, float v1) {
-                    const float2 hv = make_float2(tanh_fast(v0 + sB4[o]), tanh_fast(v1 + sB4[o + 1]));
+                    const float2 hv = make_float2(tanh_node(v0 + sB4[o]), tanh_node(v1 + sB4[o + 1]));
                     *reinterpret_cast<float2*>(sHX + ln * SD + o) = hv;
                     if (H_save && node0 + ln < n_nodes) *reinterpret_cast<float2*>(H_save + (size_t)(node0 + ln) * H + o) = hv;
                 });
             } else {
                 tile_gemm<H, H, TN, CT, C::RN, 4>(sHb, SH, sW4, [&](int ln, int o, const float* acc) {
                     const float4 b = lds4(sB4 + o);
-                    const float4 hv = make_float4(tanh_fast(acc[0] + b.x), tanh_fast(acc[1] + b.y),
-                                                  tanh_fast(acc[2] + b.z), tanh_fast(acc[3] + b.w));
+                    const float4 hv = make_float4(tanh_node(acc[0] + b.x), tanh_node(acc[1] + b.y),
+                                                  tanh_node(acc[2] + b.z), tanh_node(acc[3] + b.w));
                     st4(sHX + ln * SD + o, hv);
                     if (H_save && node0 + ln < n_nodes) st4(H_save + (size_t)(node0 + ln) * H + o, hv);
                 });
@@ -806,6 +814,18 @@ static int launch_gather(const GnnsegGraph* g, const float* Q_in, const float* e
     const int sms = sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
     long long blocks = ((long long)g->n_nodes * (H / 4) + 255) / 256;
+    static const int ranges = [] { const char* v = getenv("GNNSEG_GATHER_RANGES"); return v ? atoi(v) : 0; }();   // experiment switch
+    if (ranges == 1) {            // contiguous ranges, 256-thread CTAs (8 per SM)
+        if (blocks > sms * 8) blocks = sms * 8;
+        node_gather_kernel<H, 3, 8, 256, true><<<(int)blocks, 256, 0, st>>>(*g, Q_in, e_in, e_out, h1_out, ld_out, h1_save);
+        return check_launch();
+    }
+    if (ranges == 2) {            // contiguous ranges, 1024-thread CTAs (2 per SM)
+        blocks = ((long long)g->n_nodes * (H / 4) + 1023) / 1024;
+        if (blocks > sms * 2) blocks = sms * 2;
+        node_gather_kernel<H, 3, 2, 1024, true><<<(int)blocks, 1024, 0, st>>>(*g, Q_in, e_in, e_out, h1_out, ld_out, h1_save);
+        return check_launch();
+    }
     if (blocks > sms * 8) blocks = sms * 8;                      // one resident wave of 64 warps per SM
     if (launch_pdl(node_gather_kernel<H>, (int)blocks, 256, 0, st, use_pdl(g->n_slots), *g, Q_in, e_in, e_out, h1_out, ld_out,
                    h1_save) != cudaSuccess)

@@ -288,4 +288,88 @@ int build_graph(const int32_t* src, const int32_t* dst, int n_slots, int n_nodes
     return build_csr_dirs(p, 2, n_slots, n_nodes, st);
 }
 
+// ---- batch assembly from the host event store (gnnseg_store.cpp) -----------------------------------
+// A batch of B consecutive events arrives as contiguous slices of the store's arrays: per-event local
+// CSR row pointers and the edge columns of the incidence entries in CSR order.  The flattened batch
+// graph (endpoints per slot, both CSRs, inverse maps) follows without sorting and without atomics:
+// the store was validated at load time (no column listed twice), so every slot has one writer.
+// meta = [node_off (B+1) | in_base (B+1) | out_base (B+1)]: first node / first in-entry / first out-entry
+// of every event relative to the batch.
+template <typename ColT>
+__global__ void __launch_bounds__(256)
+assemble_rows_kernel(const int32_t* __restrict__ meta, const int B, const int n_nodes, const int e_max,
+                     const int32_t* __restrict__ in_ptr_l, const int32_t* __restrict__ out_ptr_l,
+                     const ColT* __restrict__ in_col, const ColT* __restrict__ out_col, GnnsegGraphMut g) {
+    const int32_t* node_off = meta;
+    const int32_t* in_base = meta + (B + 1);
+    const int32_t* out_base = meta + 2 * (B + 1);
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_nodes; n += gridDim.x * blockDim.x) {
+        int lo = 0, hi = B;                                  // event of node n: last b with node_off[b] <= n
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(node_off + mid) <= n) lo = mid; else hi = mid;
+        }
+        const int b = lo;
+        const int lp = n + b;                                // an event owns n_b + 1 local pointer entries
+        const int slot0 = b * e_max;
+        {
+            const int beg = in_base[b] + __ldg(in_ptr_l + lp), end = in_base[b] + __ldg(in_ptr_l + lp + 1);
+            g.in_ptr[n] = beg;
+            if (n == n_nodes - 1) g.in_ptr[n_nodes] = end;
+            for (int k = beg; k < end; ++k) {
+                const int slot = slot0 + (int)in_col[k];
+                g.dst[slot] = n;
+                g.in_eid[k] = slot;
+                g.in_pos[slot] = k;
+            }
+        }
+        {
+            const int beg = out_base[b] + __ldg(out_ptr_l + lp), end = out_base[b] + __ldg(out_ptr_l + lp + 1);
+            g.out_ptr[n] = beg;
+            if (n == n_nodes - 1) g.out_ptr[n_nodes] = end;
+            for (int k = beg; k < end; ++k) {
+                const int slot = slot0 + (int)out_col[k];
+                g.src[slot] = n;
+                g.out_eid[k] = slot;
+                g.out_pos[slot] = k;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+assemble_nbr_kernel(const int n_in, const int n_out, GnnsegGraphMut g) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < max(n_in, n_out); k += gridDim.x * blockDim.x) {
+        if (k < n_in) g.in_nbr[k] = g.src[g.in_eid[k]];
+        if (k < n_out) g.out_nbr[k] = g.dst[g.out_eid[k]];
+    }
+}
+
+int assemble_batch(const int32_t* meta, int B, int n_nodes, int e_max, int n_in, int n_out, const int32_t* in_ptr_l,
+                   const int32_t* out_ptr_l, const void* in_col, const void* out_col, int col_bytes,
+                   const GnnsegGraphMut& g, cudaStream_t st) {
+    const size_t n_slots = (size_t)B * e_max;
+    if (n_slots > 0) {
+        // padding slots (and half edges) carry -1
+        if (cudaMemsetAsync(g.src, 0xFF, n_slots * 4, st) != cudaSuccess || cudaMemsetAsync(g.dst, 0xFF, n_slots * 4, st) != cudaSuccess ||
+            cudaMemsetAsync(g.in_pos, 0xFF, n_slots * 4, st) != cudaSuccess || cudaMemsetAsync(g.out_pos, 0xFF, n_slots * 4, st) != cudaSuccess)
+            return GNNSEG_ECUDA;
+    }
+    if (n_nodes == 0) {
+        fill_i32_kernel<<<1, 32, 0, st>>>(g.in_ptr, 0, 1);
+        fill_i32_kernel<<<1, 32, 0, st>>>(g.out_ptr, 0, 1);
+        return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+    }
+    const int grid = grid_for(n_nodes, 256, 148 * 8);
+    if (col_bytes == 2)
+        assemble_rows_kernel<uint16_t><<<grid, 256, 0, st>>>(meta, B, n_nodes, e_max, in_ptr_l, out_ptr_l,
+                                                             static_cast<const uint16_t*>(in_col), static_cast<const uint16_t*>(out_col), g);
+    else
+        assemble_rows_kernel<int32_t><<<grid, 256, 0, st>>>(meta, B, n_nodes, e_max, in_ptr_l, out_ptr_l,
+                                                            static_cast<const int32_t*>(in_col), static_cast<const int32_t*>(out_col), g);
+    if (n_in > 0 || n_out > 0)
+        assemble_nbr_kernel<<<grid_for(n_in > n_out ? n_in : n_out, 256, 148 * 8), 256, 0, st>>>(n_in, n_out, g);
+    return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+}
+
 }  // namespace gnnseg

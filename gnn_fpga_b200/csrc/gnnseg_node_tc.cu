@@ -371,7 +371,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
                         tc_row_sum<false>(nullptr, g.in_nbr, e_in, Q_in + 4 * c, 3 * H, i0, i1, keep, acc);
                         tc_row_sum<false>(nullptr, g.out_nbr, e_out, Q_in + H + 4 * c, 3 * H, o0, o1, keep, acc);
                     }
-                    acc.x = tanh_fast(acc.x); acc.y = tanh_fast(acc.y); acc.z = tanh_fast(acc.z); acc.w = tanh_fast(acc.w);
+                    acc.x = tanh_node(acc.x); acc.y = tanh_node(acc.y); acc.z = tanh_node(acc.z); acc.w = tanh_node(acc.w);
                     if (h1_save) st4(h1_save + (size_t)n * H + 4 * c, acc);          // training: kept for the backward pass
                 }
                 float4 hh, hl;
@@ -492,7 +492,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
                 tmem_ld16(lane_base + C::C_D2 + c0, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    v[i] = tanh_fast(v[i] + sB4[c0 + i]);
+                    v[i] = tanh_node(v[i] + sB4[c0 + i]);
                     split3(v[i], hi[i], lo[i]);
                 }
                 if (H_save && live) {                                              // training: H' kept for the backward pass
@@ -711,7 +711,7 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
                 tmem_ld16(lane_base + C::C_D2 + c0, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    v[i] = tanh_fast(v[i] + sB4[c0 + i]);
+                    v[i] = tanh_node(v[i] + sB4[c0 + i]);
                     split3(v[i], hi[i], lo[i]);
                 }
                 if (H_save && live) {
@@ -1081,9 +1081,9 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, con
                         t = fmaf(x.y, sWin[1 * H + c0 + i], t);
                         t = fmaf(x.z, sWin[2 * H + c0 + i], t);
                         t = fmaf(x.w, sWin[3 * H + c0 + i], t);
-                        v[i] = tanh_fast(t);
+                        v[i] = tanh_node(t);
                     } else {
-                        v[i] = tanh_fast(v[i] + sB4[c0 + i]);
+                        v[i] = tanh_node(v[i] + sB4[c0 + i]);
                     }
                     split3(v[i], hi[i], lo[i]);
                 }
@@ -1215,7 +1215,7 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
                 v = fmaf(x[1], sWin[1 * H + c0 + i], v);
                 v = fmaf(x[2], sWin[2 * H + c0 + i], v);
                 v = fmaf(x[3], sWin[3 * H + c0 + i], v);
-                hv[i] = tanh_fast(v);
+                hv[i] = tanh_node(v);
                 split3(hv[i], hi[i], lo[i]);
             }
             if (H_save && n < n_nodes) {                                           // training: H0 kept for the backward pass

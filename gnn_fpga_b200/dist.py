@@ -35,23 +35,75 @@ def shard_bounds(n_events, world, weights=None):
     return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
 
 
-def gather_scores(local_scores, bounds, group=None):
-    """All-gather per-rank (B_r, E_r) score blocks into one (B, E_max) tensor on every rank,
-    padded with NaN where an event has fewer than E_max slots on its rank.  Blocks are padded
-    to a common shape first so a single fixed-size all_gather does the job."""
-    world = dist.get_world_size(group)
-    dev = local_scores.device
-    shape = torch.tensor([local_scores.shape[0], local_scores.shape[1]], dtype=torch.int64, device=dev)
-    shapes = [torch.zeros_like(shape) for _ in range(world)]
-    dist.all_gather(shapes, shape, group=group)
-    shapes = [tuple(int(v) for v in s.tolist()) for s in shapes]
-    b_max = max(s[0] for s in shapes)
-    e_max = max(s[1] for s in shapes)
-    block = torch.full((b_max, e_max), float("nan"), dtype=local_scores.dtype, device=dev)
-    block[:local_scores.shape[0], :local_scores.shape[1]] = local_scores
-    blocks = [torch.empty_like(block) for _ in range(world)]
-    dist.all_gather(blocks, block, group=group)
-    out = torch.cat([blk[:s[0]] for blk, s in zip(blocks, shapes)], dim=0)
+class ScoreGatherer:
+    """All-gather of the per-rank (B_r, E_r) score blocks into one (sum B_r, E_max) tensor on every rank
+    (NaN where an event has fewer than E_max slots on its rank), the only collective of the inference path.
+
+    One `all_gather_into_tensor` per call into a preallocated buffer, enqueued on the current (compute) stream
+    with no host synchronisation: the block shapes are exchanged ONCE per shape bucket (`shapes` may also be
+    passed in when the caller knows them, e.g. from the event list), not per call.  Ranks must call it in
+    step; a rank whose local shape changes triggers a new exchange on all ranks only if every rank passes
+    through `exchange_shapes` again, so callers with ragged batches pass `shapes` explicitly or call
+    `reset()` on every rank between buckets."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.shapes = None
+        self._block = None
+        self._out = None
+        self._dirty_cols = 0
+
+    def reset(self):
+        self.shapes = None
+
+    def exchange_shapes(self, local_scores):
+        world = dist.get_world_size(self.group)
+        shape = torch.tensor([local_scores.shape[0], local_scores.shape[1]], dtype=torch.int64, device=local_scores.device)
+        allsh = torch.empty(2 * world, dtype=torch.int64, device=local_scores.device)
+        dist.all_gather_into_tensor(allsh, shape, group=self.group)
+        v = allsh.tolist()                                   # the one host synchronisation, once per bucket
+        self.shapes = [(int(v[2 * r]), int(v[2 * r + 1])) for r in range(world)]
+        return self.shapes
+
+    def __call__(self, local_scores, shapes=None):
+        world = dist.get_world_size(self.group)
+        rank = dist.get_rank(self.group)
+        if shapes is not None:
+            self.shapes = [tuple(int(x) for x in sh) for sh in shapes]
+        if self.shapes is None or self.shapes[rank] != tuple(local_scores.shape):
+            self.exchange_shapes(local_scores)
+        b_max = max(sh[0] for sh in self.shapes)
+        e_max = max(sh[1] for sh in self.shapes)
+        dev, dt = local_scores.device, local_scores.dtype
+        if self._out is None or self._out.shape != (world * b_max, e_max) or self._out.device != dev or self._out.dtype != dt:
+            self._out = torch.empty((world * b_max, e_max), dtype=dt, device=dev)
+            self._block = torch.full((b_max, e_max), float("nan"), dtype=dt, device=dev)
+            self._dirty_cols = 0
+        if tuple(local_scores.shape) == (b_max, e_max) and local_scores.is_contiguous():
+            block = local_scores                            # the common case needs no staging copy
+        else:
+            B, E = local_scores.shape
+            if E < self._dirty_cols or B < b_max:
+                self._block.fill_(float("nan"))             # a narrower block than last time: clear the stale part
+            self._block[:B, :E] = local_scores
+            self._dirty_cols = E
+            block = self._block
+        dist.all_gather_into_tensor(self._out, block, group=self.group)
+        if all(sh[0] == b_max for sh in self.shapes):
+            return self._out                                 # (world * B, E_max): rows already in event order
+        return torch.cat([self._out[r * b_max:r * b_max + sh[0]] for r, sh in enumerate(self.shapes)], dim=0)
+
+
+_default_gatherers = {}
+
+
+def gather_scores(local_scores, bounds, group=None, shapes=None):
+    """All-gather per-rank (B_r, E_r) score blocks into one (B, E_max) tensor on every rank, padded with
+    NaN where an event has fewer than E_max slots on its rank (see ScoreGatherer; one gatherer is kept per
+    group, so repeated calls reuse its buffers and exchange shapes only when the local shape changes).
+    The returned tensor is overwritten by the next call."""
+    g = _default_gatherers.setdefault(id(group) if group is not None else None, ScoreGatherer(group))
+    out = g(local_scores, shapes)
     assert out.shape[0] == bounds[-1][1]
     return out
 

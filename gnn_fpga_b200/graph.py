@@ -151,7 +151,7 @@ class DeviceGraphBatch:
     are padding carry src = dst = -1.
     """
 
-    def __init__(self, X, src, dst, B, e_max, n_nodes_per_event=None):
+    def __init__(self, X, src, dst, B, e_max, n_nodes_per_event=None, _prebuilt=None):
         dev = _require_cuda(X.device)
         assert X.dtype == torch.float32 and X.dim() == 2 and X.is_contiguous()
         assert src.dtype == torch.int32 and dst.dtype == torch.int32
@@ -165,10 +165,17 @@ class DeviceGraphBatch:
         self.F = int(X.shape[1])
         self.n_nodes_per_event = n_nodes_per_event
         self.n_real_edges = None       # filled lazily (needs a device->host read)
-        self._build_csr()
+        self.node_perm = None          # set when the nodes were renumbered internally (GraphStore reorder)
         self._ws = {}
         self._graphs = {}
-        self.scores = torch.empty(self.n_slots, dtype=torch.float32, device=dev)
+        if _prebuilt is None:
+            self._build_csr()
+            self.scores = torch.empty(self.n_slots, dtype=torch.float32, device=dev)
+        else:                          # arrays assembled elsewhere (from_store): no CSR build here
+            for k in ("in_ptr", "in_eid", "in_nbr", "in_pos", "out_ptr", "out_eid", "out_nbr", "out_pos", "scores"):
+                setattr(self, k, _prebuilt[k])
+            self._ws = _prebuilt.get("ws", self._ws)
+            self._set_struct()
 
     # -- construction ------------------------------------------------------------------
     def _build_csr(self):
@@ -188,8 +195,11 @@ class DeviceGraphBatch:
                                             _ptr(self.out_ptr), _ptr(self.out_eid), _ptr(self.out_nbr), _ptr(self.out_pos),
                                             _ptr(ws), ws_bytes, _stream_ptr(dev)), "gnnseg_build_graph")
         self._csr_ws = ws   # keep alive until the stream has consumed it
+        self._set_struct()
+
+    def _set_struct(self):
         self.struct = _lib.GnnsegGraph(
-            n, m, self.src.data_ptr(), self.dst.data_ptr(),
+            self.n_nodes, self.n_slots, self.src.data_ptr(), self.dst.data_ptr(),
             self.in_ptr.data_ptr(), self.in_eid.data_ptr(), self.in_nbr.data_ptr(),
             self.out_ptr.data_ptr(), self.out_eid.data_ptr(), self.out_nbr.data_ptr(),
             self.in_pos.data_ptr(), self.out_pos.data_ptr())
@@ -235,13 +245,74 @@ class DeviceGraphBatch:
         return cls.from_packed_host(host, dev, pinned=pinned)
 
     @classmethod
-    def from_sparse_graphs(cls, graphs, device="cuda", pinned=None, n_threads=0):
+    def from_sparse_graphs(cls, graphs, device="cuda", pinned=None, n_threads=0, reorder=False):
         """List of host SparseGraph tuples -> device batch, padded exactly as
         graph_from_sparse + merge_graphs would pad it (e_max = max len(Ri_rows); node rows
-        are NOT padded because padded nodes influence no score)."""
+        are NOT padded because padded nodes influence no score).  reorder = True / "auto": through a
+        GraphStore that renumbers the nodes for locality (gnn_fpga_b200/store.py)."""
         dev = _require_cuda(device)
+        if reorder:
+            from .store import GraphStore
+            store = GraphStore.from_sparse_graphs(graphs, reorder=reorder, n_threads=n_threads)
+            batch = cls.from_store(store, 0, len(store), dev)
+            torch.cuda.current_stream(dev).synchronize()      # the temporary arena goes away with `store`
+            return batch
         host = pack_sparse_batch_host(graphs, pinned=pinned, n_threads=n_threads)
         return cls.from_packed_host(host, dev, pinned=pinned)
+
+    @classmethod
+    def from_store(cls, store, lo=0, hi=None, device="cuda", bufs=None, copy_stream=None):
+        """Events [lo, hi) of a GraphStore (gnn_fpga_b200/store.py): five contiguous asynchronous copies
+        out of the store's pinned arena, then gnnseg_assemble_batch on the device (no sort, no atomics,
+        no host work).  `bufs`: a DeviceBatchBuffers to reuse (pipelines); `copy_stream`: the stream the
+        copies run on (the current stream waits for them before assembling)."""
+        dev = _require_cuda(torch.device(device))
+        hi = len(store) if hi is None else hi
+        B = hi - lo
+        if B <= 0:
+            raise ValueError("empty batch")
+        meta, n, e_max, n_in, n_out = store.batch_meta(lo, hi)
+        if bufs is None:
+            bufs = DeviceBatchBuffers(dev, n, n_in, n_out, B * e_max, B, store.F, store.col_bytes)
+        v = bufs.views(n, n_in, n_out, B * e_max, B)
+        bufs.meta_host[:meta.shape[0]] = torch.from_numpy(meta)
+        compute = torch.cuda.current_stream(dev)
+        cs = copy_stream if copy_stream is not None else compute
+        with torch.cuda.stream(cs):
+            v["meta"].copy_(bufs.meta_host[:meta.shape[0]], non_blocking=True)
+            for dst_t, src_t in zip((v["X"], v["in_ptr_l"], v["out_ptr_l"], v["in_col"], v["out_col"]), store.slices(lo, hi)):
+                if src_t.numel():
+                    dst_t.copy_(src_t, non_blocking=True)
+            if cs is not compute:
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                compute.wait_event(ev)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            _lib.check(L.gnnseg_assemble_batch(_ptr(v["meta"]), B, n, e_max, n_in, n_out, _ptr(v["in_ptr_l"]), _ptr(v["out_ptr_l"]),
+                                               _ptr(v["in_col"]), _ptr(v["out_col"]), store.col_bytes, _ptr(v["src"]), _ptr(v["dst"]),
+                                               _ptr(v["in_ptr"]), _ptr(v["in_eid"]), _ptr(v["in_nbr"]), _ptr(v["in_pos"]),
+                                               _ptr(v["out_ptr"]), _ptr(v["out_eid"]), _ptr(v["out_nbr"]), _ptr(v["out_pos"]),
+                                               _stream_ptr(dev)), "gnnseg_assemble_batch")
+        v["ws"] = bufs.ws
+        batch = cls(v["X"], v["src"], v["dst"], B, e_max, n_nodes_per_event=np.diff(meta[:B + 1]).tolist(), _prebuilt=v)
+        if store.order_column >= 0:
+            batch.node_perm = (store, lo, hi)      # resolved lazily by node_order(): only per-node outputs need it
+        batch._bufs = bufs
+        return batch
+
+    def node_order(self):
+        """None, or an int64 device tensor `orig` with orig[i] = original flattened node id of internal node i
+        (batches from a store that renumbered its nodes; per-edge scores never need it)."""
+        if self.node_perm is None:
+            return None
+        if not isinstance(self.node_perm, torch.Tensor):
+            store, lo, hi = self.node_perm
+            n0, n1 = int(store.node_off[lo]), int(store.node_off[hi])
+            local = store.perm[n0:n1].to(torch.int64)
+            base = torch.from_numpy(np.repeat(store.node_off[lo:hi] - store.node_off[lo], np.diff(store.node_off[lo:hi + 1])))
+            self.node_perm = (local + base).to(self.device)
+        return self.node_perm
 
     @classmethod
     def from_packed_host(cls, host, device, pinned=None):
@@ -260,10 +331,10 @@ class DeviceGraphBatch:
     # -- helpers -------------------------------------------------------------------------
     def workspace(self, h):
         L = _lib.lib()
-        if h not in self._ws:
-            nbytes = L.gnnseg_forward_workspace_bytes(self.n_nodes, self.n_slots, self.F, h)
-            if nbytes == 0:
-                _lib.check(-2, "gnnseg_forward_workspace_bytes(F=%d, h=%d)" % (self.F, h))
+        nbytes = L.gnnseg_forward_workspace_bytes(self.n_nodes, self.n_slots, self.F, h)
+        if nbytes == 0:
+            _lib.check(-2, "gnnseg_forward_workspace_bytes(F=%d, h=%d)" % (self.F, h))
+        if h not in self._ws or self._ws[h].numel() < nbytes:      # (shared pipeline buffers: grown to the largest batch)
             self._ws[h] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return self._ws[h]
 
@@ -271,10 +342,10 @@ class DeviceGraphBatch:
         """Saved activations + backward scratch for gnnseg_forward_train / gnnseg_backward."""
         L = _lib.lib()
         key = ("train", h, n_iters)
-        if key not in self._ws:
-            nbytes = L.gnnseg_train_workspace_bytes(self.n_nodes, self.n_slots, self.F, h, n_iters)
-            if nbytes == 0:
-                _lib.check(-2, "gnnseg_train_workspace_bytes(F=%d, h=%d, n_iters=%d)" % (self.F, h, n_iters))
+        nbytes = L.gnnseg_train_workspace_bytes(self.n_nodes, self.n_slots, self.F, h, n_iters)
+        if nbytes == 0:
+            _lib.check(-2, "gnnseg_train_workspace_bytes(F=%d, h=%d, n_iters=%d)" % (self.F, h, n_iters))
+        if key not in self._ws or self._ws[key].numel() < nbytes:
             self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return self._ws[key]
 
@@ -285,6 +356,47 @@ class DeviceGraphBatch:
 
     def scores_2d(self):
         return self.scores.view(self.B, self.e_max)
+
+
+class DeviceBatchBuffers:
+    """Device buffers for batches up to a given size, reused from batch to batch (one per pipeline slot
+    of predict_stream / batch_generator): input slices of the store, the assembled graph, the scores and
+    the forward workspaces."""
+
+    def __init__(self, device, n_nodes, n_in, n_out, n_slots, B, F, col_bytes):
+        dev = _require_cuda(torch.device(device))
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.cap = (n_nodes, n_in, n_out, n_slots, B)
+        self.F, self.col_bytes = F, col_bytes
+        col_dt = torch.int16 if col_bytes == 2 else torch.int32
+        self.meta_host = torch.empty(3 * (B + 1), dtype=torch.int32, pin_memory=True)
+        self.t = {
+            "meta": torch.empty(3 * (B + 1), **i32),
+            "X": torch.empty((max(n_nodes, 1), F), dtype=torch.float32, device=dev),
+            "in_ptr_l": torch.empty(n_nodes + B, **i32), "out_ptr_l": torch.empty(n_nodes + B, **i32),
+            "in_col": torch.empty(max(n_in, 1), dtype=col_dt, device=dev), "out_col": torch.empty(max(n_out, 1), dtype=col_dt, device=dev),
+            "src": torch.empty(max(n_slots, 1), **i32), "dst": torch.empty(max(n_slots, 1), **i32),
+            "in_pos": torch.empty(max(n_slots, 1), **i32), "out_pos": torch.empty(max(n_slots, 1), **i32),
+            "in_ptr": torch.empty(n_nodes + 1, **i32), "out_ptr": torch.empty(n_nodes + 1, **i32),
+            "in_eid": torch.empty(max(n_in, 1), **i32), "in_nbr": torch.empty(max(n_in, 1), **i32),
+            "out_eid": torch.empty(max(n_out, 1), **i32), "out_nbr": torch.empty(max(n_out, 1), **i32),
+            "scores": torch.empty(max(n_slots, 1), dtype=torch.float32, device=dev),
+        }
+        self.ws = {}            # forward workspaces by hidden_dim, shared by the batches that pass through
+
+    def fits(self, n_nodes, n_in, n_out, n_slots, B):
+        return all(a <= b for a, b in zip((n_nodes, n_in, n_out, n_slots, B), self.cap))
+
+    def views(self, n_nodes, n_in, n_out, n_slots, B):
+        if not self.fits(n_nodes, n_in, n_out, n_slots, B):
+            raise ValueError("batch %r exceeds the buffers %r" % ((n_nodes, n_in, n_out, n_slots, B), self.cap))
+        t = self.t
+        return {"meta": t["meta"][:3 * (B + 1)], "X": t["X"][:n_nodes], "in_ptr_l": t["in_ptr_l"][:n_nodes + B],
+                "out_ptr_l": t["out_ptr_l"][:n_nodes + B], "in_col": t["in_col"][:n_in], "out_col": t["out_col"][:n_out],
+                "src": t["src"][:n_slots], "dst": t["dst"][:n_slots], "in_pos": t["in_pos"][:n_slots], "out_pos": t["out_pos"][:n_slots],
+                "in_ptr": t["in_ptr"][:n_nodes + 1], "out_ptr": t["out_ptr"][:n_nodes + 1], "in_eid": t["in_eid"][:n_in],
+                "in_nbr": t["in_nbr"][:n_in], "out_eid": t["out_eid"][:n_out], "out_nbr": t["out_nbr"][:n_out],
+                "scores": t["scores"][:n_slots]}
 
 
 def pack_npz_batch_host(filenames, pinned=None, n_threads=0):

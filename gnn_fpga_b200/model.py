@@ -124,7 +124,7 @@ class SegmentClassifier(nn.Module):
         self.node_network = NodeNetwork(input_dim + hidden_dim, hidden_dim, hidden_activation, masks_n)
         self._blob = None
         self.use_cuda_graph = True
-        self._pinned = None          # reusable pinned staging buffers for host SparseGraph batches
+        self._arena = None           # reusable pinned arena for batches given as host SparseGraph tuples
 
     # -- weights -------------------------------------------------------------------------
     def _device(self):
@@ -210,67 +210,55 @@ class SegmentClassifier(nn.Module):
                 entry.replay()
         return batch.scores
 
-    @staticmethod
-    def _grow_pinned(p, graphs):
-        """Pinned host staging for a packed batch, grown on demand and reused across calls
-        (allocating pinned memory costs more than packing the batch)."""
-        n = sum(int(g.X.shape[0]) for g in graphs)
-        m = len(graphs) * max(int(g.Ri_rows.shape[0]) for g in graphs)
-        F = int(graphs[0].X.shape[1])
-        if p is None or p["X"].shape[0] < n or p["X"].shape[1] != F or p["src"].numel() < m:
-            cap_n, cap_m = int(n * 1.25) + 1, int(m * 1.25) + 1
-            p = {
-                "X": torch.empty((cap_n, F), dtype=torch.float32, pin_memory=True),
-                "src": torch.empty(cap_m, dtype=torch.int32, pin_memory=True),
-                "dst": torch.empty(cap_m, dtype=torch.int32, pin_memory=True),
-                "event": None,
-            }
-        if p["event"] is not None:
-            p["event"].synchronize()     # the previous batch's H2D copies have left the buffers
-        return p
+    def _tuple_store(self, graphs, arena=None, n_threads=0):
+        """Host SparseGraph tuples -> a one-batch GraphStore (validated: ValueError for out-of-range indices
+        or a column listed twice).  Node order kept: renumbering is load-time work (GraphStore)."""
+        from .store import GraphStore
+        return GraphStore.from_sparse_graphs(graphs, reorder=False, n_threads=n_threads, arena=arena)
 
-    def _pinned_buffers(self, graphs):
-        self._pinned = self._grow_pinned(self._pinned, graphs)
-        return self._pinned
+    def predict_stream(self, batches, depth=3):
+        """Pipelined inference over an iterable of batches: yields, in order, one pinned host tensor
+        (B, E_max) of scores per batch.  A batch is
 
-    def predict_stream(self, batches, depth=2):
-        """Pipelined inference over an iterable of batches (each a list of host SparseGraph
-        tuples): yields, in order, one pinned host tensor (B, E_max) of scores per batch.
+        * a `StoreBatch` (events [lo, hi) of a GraphStore, gnn_fpga_b200/store.py): the fast path.  The
+          host does no per-batch work: five contiguous asynchronous copies out of the store's pinned arena on
+          a copy stream, gnnseg_assemble_batch + the forward on the compute stream, the scores back on a
+          third stream; `depth` batches are in flight, so the copies of neighbouring batches overlap the
+          compute of this one.  Replaces the reference's per-batch graph_from_sparse + merge_graphs + .cuda()
+          (gnn/trainSegmentClassifier.py:97-111) and Estimator.predict's loop (gnn/estimator.py:137-146);
+        * a list of host SparseGraph tuples or of graph file names: packed on a worker thread into a
+          one-batch store first (the per-batch host work the reference does, minus the densifying), then the
+          same device path.
 
-        Every batch goes through the same work as `model(graphs).cpu()` -- C host packing into
-        pinned memory, H2D, device CSR build, forward, D2H -- but nothing synchronises in
-        between: a worker thread packs batch i+1 (the C packer releases the GIL) while this
-        thread enqueues batch i and the GPU works on batch i-1.  `depth` batches are in flight;
-        a yielded tensor is reused `depth` batches later."""
+        A yielded tensor is reused `depth` batches later."""
         from collections import deque
         from concurrent.futures import ThreadPoolExecutor
-        from .graph import _require_cuda, pack_npz_batch_host, pack_sparse_batch_host
+        from .graph import DeviceBatchBuffers, _require_cuda, load_graphs_mapped
+        from .store import StoreBatch
         dev = _require_cuda(self._device())
-        LOOK = 1                                                   # batches being packed ahead (the packer is GIL/DRAM bound: one is enough)
-        n_slots = depth + LOOK
-        slots = [{"pinned": None, "out": None, "done": None, "view": None} for _ in range(n_slots)]
-        pending = deque()
+        depth = max(1, int(depth))
+        slots = [{"bufs": None, "out": None, "done": None, "view": None, "arena": None, "h2d": None} for _ in range(depth + 1)]
         was_graph, self.use_cuda_graph = self.use_cuda_graph, False    # one-shot batches: plain launches
-        # leave two cores to the launching thread and the driver: an oversubscribed OpenMP team
-        # (its threads spin between batches) makes the per-batch time jump by 2x
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))     # ranks sharing this host (torchrun)
-        pack_threads = max(1, (os.cpu_count() or 4) // local_world - 2)
-        if os.environ.get("GNNSEG_PACK_THREADS"):                     # explicit size of the packer's OpenMP team
+        pack_threads = max(1, min(4, (os.cpu_count() or 4) // local_world - 2))
+        if os.environ.get("GNNSEG_PACK_THREADS"):
             pack_threads = max(1, int(os.environ["GNNSEG_PACK_THREADS"]))
 
-        def pack(graphs, slot):
-            if _is_file_batch(graphs):                                   # graph files: mapped, parsed and packed by the library
-                p = slot["pinned"] or {"X": None, "src": None, "dst": None, "event": None}
-                if p["event"] is not None:
-                    p["event"].synchronize()                             # the slot's last H2D has left the buffers
-                slot["pinned"] = p
-                return pack_npz_batch_host([os.fspath(f) for f in graphs], pinned=p, n_threads=pack_threads)
-            slot["pinned"] = self._grow_pinned(slot["pinned"], graphs)   # waits for the slot's last H2D
-            return pack_sparse_batch_host(list(graphs), pinned=slot["pinned"], n_threads=pack_threads)
+        def prepare(item, slot):
+            """Anything that is not a StoreBatch becomes one (worker thread; the C++ fill releases the GIL)."""
+            if isinstance(item, StoreBatch):
+                return item
+            if slot["h2d"] is not None:
+                slot["h2d"].synchronize()                                # the slot's last copies have left its arena
+            graphs = load_graphs_mapped([os.fspath(f) for f in item]) if _is_file_batch(item) else list(item)
+            st = self._tuple_store(graphs, arena=slot["arena"], n_threads=pack_threads)
+            slot["arena"] = st.arena
+            return StoreBatch(st, 0, len(st))
 
-        pool = ThreadPoolExecutor(max_workers=LOOK)
+        pool = ThreadPoolExecutor(max_workers=1)
         compute = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        pending = deque()
         try:
             with torch.no_grad():
                 it = iter(batches)
@@ -280,38 +268,36 @@ class SegmentClassifier(nn.Module):
                 def submit_next():
                     nonlocal n_sub
                     try:
-                        g = next(it)
+                        item = next(it)
                     except StopIteration:
                         return
-                    futs.append(pool.submit(pack, g, slots[n_sub % n_slots]))
+                    slot = slots[n_sub % len(slots)]
+                    futs.append(item if isinstance(item, StoreBatch) else pool.submit(prepare, item, slot))
                     n_sub += 1
 
-                for _ in range(LOOK):
-                    submit_next()
+                submit_next()
                 i = 0
                 while futs:
-                    s = slots[i % n_slots]
-                    host = futs.popleft().result()
-                    submit_next()                                 # keep LOOK batches being packed
+                    s = slots[i % len(slots)]
+                    f = futs.popleft()
+                    sb = f if isinstance(f, StoreBatch) else f.result()
+                    submit_next()                                 # one batch being prepared ahead
                     if len(pending) == depth:                     # keep `depth` results in flight
                         old = pending.popleft()
                         old["done"].synchronize()
                         yield old["view"]
-                    # H2D on its own stream (copy engine), CSR build + forward on the compute
-                    # stream, D2H on a third stream: the copies of neighbouring batches overlap
-                    # the compute of this one
-                    with torch.cuda.stream(s_in):
-                        X = host["X"].to(dev, non_blocking=True)
-                        src = host["src"].to(dev, non_blocking=True)
-                        dst = host["dst"].to(dev, non_blocking=True)
-                        ev_in = torch.cuda.Event()
-                        ev_in.record(s_in)
-                    s["pinned"]["event"] = ev_in                  # the packer may refill the slot after this
-                    compute.wait_event(ev_in)
-                    for t in (X, src, dst):
-                        t.record_stream(compute)
-                    batch = DeviceGraphBatch(X, src, dst, len(host["n_nodes"]), host["e_max"],
-                                             n_nodes_per_event=host["n_nodes"])
+                    if s["done"] is not None:
+                        s["done"].synchronize()                   # the slot's previous batch has left the device buffers
+                    store = sb.store
+                    _, n, e_max, n_in, n_out = store.batch_meta(sb.lo, sb.hi)
+                    B = sb.hi - sb.lo
+                    if s["bufs"] is None or not s["bufs"].fits(n, n_in, n_out, B * e_max, B) or s["bufs"].F != store.F \
+                            or s["bufs"].col_bytes != store.col_bytes:
+                        g = lambda v: int(v * 1.25) + 1
+                        s["bufs"] = DeviceBatchBuffers(dev, g(n), g(n_in), g(n_out), g(B * e_max), B, store.F, store.col_bytes)
+                    batch = DeviceGraphBatch.from_store(store, sb.lo, sb.hi, dev, bufs=s["bufs"], copy_stream=s_in)
+                    s["h2d"] = torch.cuda.Event()
+                    s["h2d"].record(s_in)
                     scores = self._run(batch)
                     if s["out"] is None or s["out"].numel() < scores.numel():
                         s["out"] = torch.empty(int(scores.numel() * 1.25) + 1, dtype=torch.float32, pin_memory=True)
@@ -319,7 +305,6 @@ class SegmentClassifier(nn.Module):
                     ev_c = torch.cuda.Event()
                     ev_c.record(compute)
                     s_out.wait_event(ev_c)
-                    scores.record_stream(s_out)
                     with torch.cuda.stream(s_out):
                         s["view"].copy_(scores.view(batch.B, batch.e_max), non_blocking=True)
                         s["done"] = torch.cuda.Event()
@@ -340,15 +325,24 @@ class SegmentClassifier(nn.Module):
         return self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def _to_batch(self, inputs):
+        """Anything forward accepts -> DeviceGraphBatch."""
+        from .graph import _require_cuda
+        from .store import StoreBatch
         if isinstance(inputs, DeviceGraphBatch):
             return inputs
+        if isinstance(inputs, StoreBatch):
+            return DeviceGraphBatch.from_store(inputs.store, inputs.lo, inputs.hi, _require_cuda(self._device()))
         if _is_file_batch(inputs):
-            from .graph import _require_cuda
             return DeviceGraphBatch.from_graph_files(inputs, device=_require_cuda(self._device()))
         if isinstance(inputs, (list, tuple)) and len(inputs) > 0 and isinstance(inputs[0], SparseGraph):
-            from .graph import _require_cuda
-            dev = _require_cuda(self._device())
-            return DeviceGraphBatch.from_sparse_graphs(list(inputs), device=dev, pinned=self._pinned_buffers(inputs))
+            dev = _require_cuda(self._device())        # fails loudly before any host work: no CPU path
+            st = self._tuple_store(list(inputs), arena=self._arena)
+            self._arena = st.arena
+            batch = DeviceGraphBatch.from_store(st, 0, len(st), dev)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            ev.synchronize()                           # the arena is reused by the next call
+            return batch
         X, Ri, Ro = inputs
         if not (isinstance(X, torch.Tensor) and X.is_cuda):
             raise ValueError("SegmentClassifier expects CUDA tensors [X, Ri, Ro] (got %s); there is no CPU path"
@@ -356,6 +350,9 @@ class SegmentClassifier(nn.Module):
         return DeviceGraphBatch.from_dense(X, Ri, Ro)
 
     def forward(self, inputs):
+        """Returns a fresh (B, E_max) tensor per call, like the reference (gnn/model.py:156).  For a
+        DeviceGraphBatch the result is a copy of the batch-owned `batch.scores` buffer, which the next call on
+        the same batch (or a CUDA-graph replay) overwrites."""
         if self._wants_grad():
             # A forward that must be differentiated (Estimator.training_step, gnn/estimator.py:53):
             # gnnseg_forward_train keeps the activations, the result's grad_fn runs gnnseg_backward
@@ -367,20 +364,7 @@ class SegmentClassifier(nn.Module):
             if _lib.lib().gnnseg_supported(self.input_dim, self.hidden_dim) == 0:   # same shapes as inference
                 _lib.check(-2, "SegmentClassifier(input_dim=%d, hidden_dim=%d)" % (self.input_dim, self.hidden_dim))
             return differentiable_forward(self, self._to_batch(inputs))
-        if isinstance(inputs, DeviceGraphBatch):
-            return self._run(inputs).view(inputs.B, inputs.e_max)
-        if _is_file_batch(inputs):
-            batch = self._to_batch(inputs)
-            return self._run(batch).view(batch.B, batch.e_max)
-        if isinstance(inputs, (list, tuple)) and len(inputs) > 0 and isinstance(inputs[0], SparseGraph):
-            from .graph import _require_cuda
-            dev = _require_cuda(self._device())        # fails loudly before any host work: no CPU path
-            batch = DeviceGraphBatch.from_sparse_graphs(list(inputs), device=dev,
-                                                        pinned=self._pinned_buffers(inputs))
-            return self._run(batch).view(batch.B, batch.e_max)
-        X, Ri, Ro = inputs
-        if not (isinstance(X, torch.Tensor) and X.is_cuda):
-            raise ValueError("SegmentClassifier expects CUDA tensors [X, Ri, Ro] (got %s); there is no CPU path"
-                             % (X.device if isinstance(X, torch.Tensor) else type(X)))
-        batch = DeviceGraphBatch.from_dense(X, Ri, Ro)
-        return self._run(batch).view(batch.B, batch.e_max)
+        resident = isinstance(inputs, DeviceGraphBatch)
+        batch = self._to_batch(inputs)
+        out = self._run(batch).view(batch.B, batch.e_max)
+        return out.clone() if resident else out        # one-shot batches own their buffer: nothing else writes it

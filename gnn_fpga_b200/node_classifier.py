@@ -76,7 +76,7 @@ class NodeClassifier(SegmentClassifier):
             _lib.check(L.gnnseg_forward_nodes(_ptr(blob), _ptr(head), C.byref(batch.struct), _ptr(batch.X), batch.F, h,
                                               self.n_iters, _ptr(out), _ptr(ws), ws.numel(), _stream_ptr(dev)),
                        "gnnseg_forward_nodes")
-        return out
+        return _original_order(batch, out)
 
     def forward(self, inputs):
         if self._device().type != "cuda":
@@ -94,6 +94,17 @@ class NodeClassifier(SegmentClassifier):
 
     def predict_stream(self, batches, depth=2):
         raise NotImplementedError("predict_stream is the segment classifier's pipeline; call the model per batch")
+
+
+def _original_order(batch, per_node):
+    """Per-node values of a batch whose nodes were renumbered internally (GraphStore reorder) -> the
+    order of the caller's X rows."""
+    order = batch.node_order()
+    if order is None:
+        return per_node
+    out = torch.empty_like(per_node)
+    out[order] = per_node
+    return out
 
 
 class NodeClfFunction(torch.autograd.Function):
@@ -115,7 +126,7 @@ class NodeClfFunction(torch.autograd.Function):
                        "gnnseg_forward_nodes_train")
         ctx.model, ctx.batch, ctx.blob, ctx.head, ctx.ws = model, batch, blob, head, ws
         ctx.shapes = [p.shape for p in params]
-        return out
+        return _original_order(batch, out)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -124,6 +135,8 @@ class NodeClfFunction(torch.autograd.Function):
         model, batch = ctx.model, ctx.batch
         dev = batch.device
         dnode = grad_out.to(torch.float32).contiguous().view(-1)
+        if batch.node_order() is not None:
+            dnode = dnode[batch.node_order()].contiguous()
         grads = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
         masks, keep = _mask_struct(model)
         gs = _lib.GnnsegGrads(*[g.data_ptr() for g in grads[:10]])

@@ -115,25 +115,38 @@ def l1_penalty(model):
     return sum(w.abs().sum() for w in ws)
 
 
-def allreduce_gradients(params, group=None):
-    """Average the gradients over the ranks with ONE all-reduce of a flat buffer."""
+def allreduce_gradients(params, group=None, n_local=None):
+    """Average the gradients over the ranks with ONE all-reduce of a flat buffer.
+
+    n_local = None: equal weights (every rank holds the same number of padded slots, the bench's weak
+    scaling).  n_local = this rank's number of padded slots (B_local * E_max_local): the ranks' gradients
+    are weighted n_local / sum(n_local), which is the gradient of the reference's loss -- nn.BCELoss() is a
+    mean over ALL padded slots of the batch (gnn/estimator.py:57) -- over the union of the shards when the
+    shards are uneven (`shard_bounds(weights=...)`).  The weight travels in the same all-reduce."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat /= dist.get_world_size(group)
+    if n_local is None:
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat /= dist.get_world_size(group)
+    else:
+        w = torch.full((1,), float(n_local), dtype=grads[0].dtype, device=grads[0].device)
+        flat = torch.cat([g.reshape(-1) * float(n_local) for g in grads] + [w])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat = flat[:-1] / flat[-1]
     off = 0
     for g in grads:
         g.copy_(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
 
 
-def training_step(model, optimizer, loss_func, inputs, targets, l1=0.0, group=None):
+def training_step(model, optimizer, loss_func, inputs, targets, l1=0.0, group=None, weight_by_slots=False):
     """Estimator.training_step (gnn/estimator.py:49-60) + gradient all-reduce when
-    torch.distributed is initialised (every rank holds its own shard of events)."""
+    torch.distributed is initialised (every rank holds its own shard of events).  weight_by_slots:
+    weight the ranks by their padded slot counts (uneven shards, see allreduce_gradients)."""
     model.zero_grad()
     optimizer.zero_grad()
     outputs = model(inputs)
@@ -141,7 +154,7 @@ def training_step(model, optimizer, loss_func, inputs, targets, l1=0.0, group=No
     if l1:
         loss = loss + l1 * l1_penalty(model)
     loss.backward()
-    allreduce_gradients(list(model.parameters()), group)
+    allreduce_gradients(list(model.parameters()), group, n_local=targets.numel() if weight_by_slots else None)
     optimizer.step()
     return loss
 
@@ -155,11 +168,13 @@ class NativeTrainer:
     Hyper-parameters default to torch.optim.Adam's, which is what Estimator(opt='Adam') builds
     (gnn/estimator.py:35-36)."""
 
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, l1=0.0, group=None):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, l1=0.0, group=None,
+                 weight_by_slots=False):
         dev = model._device()
         if dev.type != "cuda":
             raise _lib.GnnsegError("NativeTrainer needs the model on a CUDA device: there is no CPU path")
         self.model, self.group = model, group
+        self.weight_by_slots = weight_by_slots       # uneven shards: weight the ranks by their padded slot counts
         self.lr, self.betas, self.eps, self.weight_decay, self.l1 = lr, betas, eps, weight_decay, float(l1)
         self.params = _param_list(model)
         n = sum(p.numel() for p in self.params)
@@ -214,8 +229,14 @@ class NativeTrainer:
                                                C.byref(gs), st), "gnnseg_l1_penalty")
                 del keep
             if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-                self.flat_grad /= dist.get_world_size(self.group)
+                if self.weight_by_slots:
+                    buf = torch.cat([self.flat_grad * float(batch.n_slots),
+                                     torch.full((1,), float(batch.n_slots), dtype=torch.float32, device=dev)])
+                    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+                    self.flat_grad.copy_(buf[:-1] / buf[-1])
+                else:
+                    dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+                    self.flat_grad /= dist.get_world_size(self.group)
             self.step_count += 1
             _lib.check(L.gnnseg_adam_step(_ptr(self.flat), _ptr(self.flat_grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
                                           self.flat.numel(), self.step_count, self.lr, self.betas[0], self.betas[1],

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNSEG_ABI_VERSION 3
+#define GNNSEG_ABI_VERSION 4
 
 /* error codes */
 #define GNNSEG_OK            0
@@ -48,6 +48,7 @@ extern "C" {
 #define GNNSEG_ENODEVICE    -5   /* no sm_100 device visible                            */
 #define GNNSEG_EIO          -6   /* a file could not be opened / mapped                 */
 #define GNNSEG_EFORMAT      -7   /* not an .npz graph file as save_graph writes them     */
+#define GNNSEG_EHYPEREDGE   -8   /* a column listed twice in Ri (or Ro) of a host graph  */
 
 /* bits written to the device err_flag word by gnnseg_dense_to_edges */
 #define GNNSEG_BAD_VALUE      1  /* an incidence entry is neither 0 nor 1                */
@@ -144,7 +145,8 @@ size_t gnnseg_forward_workspace_bytes(int n_nodes, int n_slots, int F, int h);
 /*
  * X is (n_nodes, F) row-major fp32.  scores[n_slots] receives the final edge_network
  * output; a -1/-1 slot gets the reference's padding constant sigmoid(W2.tanh(b1)+b2).
- * Launches 2*n_iters+2 kernels on `stream`, no host synchronisation.
+ * Launches 2*n_iters+2 kernels on `stream` (hidden_dim 32 / 64: 3*n_iters+2, the node step being a
+ * gather kernel and a tensor-core MLP kernel), no host synchronisation.
  */
 int gnnseg_forward(const float* blob, const GnnsegGraph* graph, const float* X,
                    int F, int h, int n_iters, float* scores,
@@ -298,6 +300,69 @@ int gnnseg_pack_sparse_batch_host(int B, int F, int e_max,
                                   const int64_t* n_in_host, const int64_t* n_out_host,
                                   float* X_out_host, int32_t* src_host, int32_t* dst_host,
                                   int n_threads);
+
+/*
+ * The event store: the graphs of a data set narrowed, validated and laid out ONCE at load time in one
+ * caller-allocated (pinned) host arena, so that a batch of consecutive events needs no per-batch host
+ * work: five contiguous slices go to the device and gnnseg_assemble_batch builds the batch graph there.
+ * This is the reference's `graphs = load_graphs(filenames, SparseGraph)` list
+ * (gnn/trainSegmentClassifier.py:129) plus what its batch_generator does per batch
+ * (graph_from_sparse + merge_graphs + np_to_torch, gnn/trainSegmentClassifier.py:97-111), split into a
+ * load-time part (here) and a device part (below).
+ *
+ * Arena arrays, events back to back (offsets in GnnsegStoreLayout, all 256-byte aligned):
+ *   node_off, in_off, out_off, y_off   int64 [n_events+1]  first node / Ri entry / Ro entry / label of an event
+ *   X        float32 [total_nodes, F]   features in internal node order
+ *   in_ptr   int32 [total_nodes + n_events]   per event n+1 local row pointers of the destination-CSR;
+ *   out_ptr  int32 [total_nodes + n_events]   event b's block starts at node_off[b] + b
+ *   in_col   uint16|int32 [total_in]   Ri_cols in CSR order (col_bytes = 2 when every event has <= 65536 edges)
+ *   out_col  uint16|int32 [total_out]  Ro_cols in CSR order
+ *   y        float32 [total_y]         labels by edge column
+ *   perm     int32 [total_nodes]       internal position -> node id within the event
+ * Index arrays may come in any order; np.nonzero order (gnn/graph.py:23-26) is the fast case.
+ * reorder: 0 keeps the node order; 1 renumbers the nodes of every event internally along the feature
+ * column in which edges are most local (the forward's gathers then hit in L1; scores, being per edge
+ * column, do not see it; `perm` undoes it for per-node outputs); 2 = 1 for events of >= 1024 nodes.
+ * Errors: GNNSEG_EINVAL for an index out of range (row >= n_nodes, column >= len(Ri_rows)),
+ * GNNSEG_EHYPEREDGE for a column listed twice in Ri or in Ro (the dense reference would sum two rows,
+ * gnn/model.py:71-72).  info_host (nullable, 2 words): [0] = the first offending event or -1,
+ * [1] = the column chosen for the renumbering or -1.  Pure CPU; n_threads <= 0 picks a default.
+ */
+typedef struct GnnsegStoreLayout {
+    int64_t n_events;    int32_t n_features;  int32_t col_bytes;
+    int64_t total_nodes; int64_t total_in;    int64_t total_out;  int64_t total_y;
+    int64_t o_node_off;  int64_t o_in_off;    int64_t o_out_off;  int64_t o_y_off;
+    int64_t o_X;         int64_t o_in_ptr;    int64_t o_out_ptr;
+    int64_t o_in_col;    int64_t o_out_col;   int64_t o_y;        int64_t o_perm;
+    int64_t bytes;       /* size of the arena */
+} GnnsegStoreLayout;
+int gnnseg_store_plan_host(int n_events, int F, const int64_t* n_nodes_host, const int64_t* n_in_host,
+                           const int64_t* n_out_host, const int64_t* n_y_host /* nullable */,
+                           GnnsegStoreLayout* layout);
+int gnnseg_store_fill_host(const GnnsegStoreLayout* layout,
+                           const float* const* X_host, const int64_t* n_nodes_host,
+                           const int64_t* const* Ri_rows_host, const int64_t* const* Ri_cols_host,
+                           const int64_t* const* Ro_rows_host, const int64_t* const* Ro_cols_host,
+                           const int64_t* n_in_host, const int64_t* n_out_host,
+                           const float* const* y_host /* nullable */, const int64_t* n_y_host /* nullable */,
+                           int reorder, int n_threads, void* arena_host, int32_t* info_host);
+/*
+ * Device part: the flattened batch graph of B consecutive events of a store from their slices
+ * (all DEVICE pointers; copied from the arena with one cudaMemcpyAsync each):
+ *   meta      int32 [3*(B+1)]  node_off | in_base | out_base: first node, first Ri entry, first Ro
+ *                              entry of every event RELATIVE to the batch (entry B = the totals)
+ *   in_ptr_local / out_ptr_local  int32 [n_nodes + B]  the store's in_ptr / out_ptr slices
+ *   in_col / out_col              [n_in] / [n_out]     the store's in_col / out_col slices
+ * Writes every array of `graph` (src, dst, both CSRs, in_pos, out_pos; sizes as in GnnsegGraph with
+ * n_slots = B*e_max; padding slots get -1).  No sort, no atomics, 4 memsets + 2 kernels on `stream`.
+ */
+int gnnseg_assemble_batch(const int32_t* meta, int B, int n_nodes, int e_max, int n_in, int n_out,
+                          const int32_t* in_ptr_local, const int32_t* out_ptr_local,
+                          const void* in_col, const void* out_col, int col_bytes,
+                          int32_t* src, int32_t* dst,
+                          int32_t* in_ptr, int32_t* in_eid, int32_t* in_nbr, int32_t* in_pos,
+                          int32_t* out_ptr, int32_t* out_eid, int32_t* out_nbr, int32_t* out_pos,
+                          void* stream);
 
 /* ---- segment construction: replaces construct_graph / select_segments, gnn/graph.py:44-142 --- */
 

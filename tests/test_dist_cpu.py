@@ -95,6 +95,55 @@ def _grad_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _weighted_grad_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gnn_fpga_b200.training import allreduce_gradients
+    p = torch.nn.Parameter(torch.zeros(3))
+    p.grad = torch.full((3,), float(rank + 1))
+    allreduce_gradients([p], n_local=(30 if rank == 0 else 10))       # uneven shards: 30 and 10 padded slots
+    np.save(os.path.join(out_dir, "w%d.npy" % rank), p.grad.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_weights_uneven_shards(tmp_path):
+    """Uneven shards: the ranks' mean-over-local-slots gradients are weighted by their slot counts, which is
+    the gradient of the reference's mean over ALL padded slots (gnn/estimator.py:57) of the union batch."""
+    mp.spawn(_weighted_grad_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    g0, g1 = np.load(tmp_path / "w0.npy"), np.load(tmp_path / "w1.npy")
+    assert np.array_equal(g0, g1) and np.allclose(g0, (30 * 1.0 + 10 * 2.0) / 40)
+
+
+def _gatherer_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gnn_fpga_b200.dist import ScoreGatherer
+    g = ScoreGatherer()
+    outs = []
+    for step, (e0, e1) in enumerate(((5, 7), (5, 7), (4, 6))):                  # same bucket twice, then a narrower one
+        E = e0 if rank == 0 else e1
+        local = torch.full((2, E), float(10 * step + rank))
+        if step == 2:
+            g.reset()
+        outs.append(g(local).clone().numpy())
+    np.save(os.path.join(out_dir, "s%d.npy" % rank), np.stack([np.pad(o, ((0, 0), (0, 7 - o.shape[1])), constant_values=-1) for o in outs]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_score_gatherer_reuses_buffers_and_keeps_padding_nan(tmp_path):
+    """ScoreGatherer: one all_gather_into_tensor per call into a reused buffer; equal B on every rank gives the
+    (world * B, E_max) tensor directly, NaN where a rank's block is narrower, also after the bucket changed."""
+    mp.spawn(_gatherer_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    s0, s1 = np.load(tmp_path / "s0.npy"), np.load(tmp_path / "s1.npy")
+    assert np.array_equal(s0, s1, equal_nan=True)
+    for step, (e0, e1) in enumerate(((5, 7), (5, 7), (4, 6))):
+        o = s0[step][:, :max(e0, e1)]
+        assert np.all(o[:2, :e0] == 10 * step) and np.all(np.isnan(o[:2, e0:]))
+        assert np.all(o[2:, :e1] == 10 * step + 1)
+
+
 def test_two_rank_gradient_allreduce_averages(tmp_path):
     """allreduce_gradients: one flat all-reduce, mean over ranks, identical on every rank
     (the NCCL step of the sharded training_step; gloo here)."""
