@@ -12,10 +12,15 @@ Workloads (BASELINE.json configs):
 
 A step is one forward pass of the whole batch.  `value` is measured with the batch resident
 in HBM (CUDA graph replay, CUDA events per step, L2 flushed between steps).  `e2e` is the
-same metric through the public call `model(list_of_SparseGraph)` starting from HOST numpy
-tuples: host packing, H2D, device CSR build, forward and D2H of the scores are all inside the
-timed region.  Multi-GPU: events shard across ranks (weak scaling, every rank its own 64
-events), no data-path collective; timing is max over ranks.
+same metric through the public call `model.predict_stream(store.batches(B))` starting from the
+HOST event store (gnn_fpga_b200/store.py: the data set narrowed and laid out once at load time,
+as the reference loads its graph list once): H2D of the batch's slices, device batch assembly,
+forward and D2H of the scores are all inside the timed region; `e2e.from_tuples` is the same from
+raw int64 SparseGraph tuples (per-batch host packing inside the timed region too).  The default
+single-GPU run also carries a `mu200` sub-record (BASELINE configs[3], the configuration the HBM
+target is quoted on).  Multi-GPU: events shard across ranks (weak scaling, every rank its own 64
+events), no data-path collective in `value`; `value_with_gather` includes the NCCL all-gather of the
+scores, and every rank checks the rows it received against a local recompute; timing is max over ranks.
 """
 import argparse
 import json
@@ -125,6 +130,32 @@ class ClockSampler:
                 "sm_max_mhz": inside[0][2] if inside else None, "reasons": sorted(reasons), "samples": len(inside)}
 
 
+def reference_dense_forward(p, cfg, masks=None):
+    """(callable(X, Ri, Ro) -> scores, kind): the reference's own SegmentClassifier (gnn/model.py, placed under
+    oracle/_ref/ by oracle/make_ref.py in the build container; kind "reference") when it is there, otherwise the
+    oracle's operation-for-operation restatement of it (kind "port", bit-identical on the goldens)."""
+    from oracle import segclf_oracle as O
+    ref_py = os.path.join(ROOT, "oracle", "_ref", "model.py")
+    if os.path.exists(ref_py):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_model", ref_py)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        F, h = cfg["F"], cfg["h"]
+        D = F + h
+        ones = lambda *shape: torch.ones(*shape)
+        me, mn = masks if masks is not None else ([ones(h, 2 * D), ones(1, h)], [ones(h, 3 * D), ones(h, h)])   # gnn/model.py:100 needs masks
+        m = mod.SegmentClassifier(input_dim=F, hidden_dim=h, n_iters=cfg["n_iters"], masks_e=me, masks_n=mn)
+        m.load_state_dict(p)
+        m.eval()
+
+        def fwd(X, Ri, Ro):
+            with torch.no_grad():
+                return m([X, Ri, Ro])
+        return fwd, "reference"
+    return (lambda X, Ri, Ro: O.dense_forward(p, X, Ri, Ro, cfg["n_iters"])), "port"
+
+
 # -----------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     """The reference's own algorithm (dense incidence bmm, gnn/model.py:140-156) restated in
@@ -141,12 +172,16 @@ def run_reference(args, rank, world):
     torch.set_num_threads(cores)
     graphs = make_graphs(args.workload, 0)
     p = O.init_params(cfg["F"], cfg["h"], seed=0)
+    masks = None
     if cfg.get("masked"):
         from gnn_fpga_b200 import data as _data
-        p = O.apply_masks(p, *_data.random_masks(cfg["F"], cfg["h"], keep=0.5, seed=1234))
+        masks = _data.random_masks(cfg["F"], cfg["h"], keep=0.5, seed=1234)
+        p = O.apply_masks(p, *masks)
     wl = args.workload
+    dense_fwd, kind = reference_dense_forward(p, cfg, masks)
 
     if wl == "mu200":
+        kind = "port"
         X, src, dst, _ = O.flatten_sparse_batch(graphs)
         n_real = int(((src >= 0) & (dst >= 0)).sum())
         sample = "sparse restatement (gather + ordered index_add) of the whole event per step"
@@ -157,7 +192,8 @@ def run_reference(args, rank, world):
         def forward(inp):
             O.sparse_forward(p, inp[0], inp[1], inp[2], cfg["n_iters"])
     elif wl in ("acts64", "acts64_masked"):
-        sample = "dense restatement of gnn/model.py (incidence bmm), 1 of %d events per step" % len(graphs)
+        what = "gnn/model.py SegmentClassifier.forward itself" if kind == "reference" else "dense restatement of gnn/model.py"
+        sample = "%s (incidence bmm), 1 of %d events per step" % (what, len(graphs))
 
         def prepare(i):
             g = graphs[i % len(graphs)]
@@ -165,9 +201,10 @@ def run_reference(args, rank, world):
             return tuple(torch.from_numpy(a[None]) for a in (d.X, d.Ri, d.Ro)), g.Ri_rows.shape[0], 1
 
         def forward(inp):
-            O.dense_forward(p, inp[0], inp[1], inp[2], cfg["n_iters"])
+            dense_fwd(inp[0], inp[1], inp[2])
     else:
-        sample = "dense restatement of gnn/model.py (incidence bmm), the full batch of %d graphs per step" % len(graphs)
+        what = "gnn/model.py SegmentClassifier.forward itself" if kind == "reference" else "dense restatement of gnn/model.py"
+        sample = "%s (incidence bmm), the full batch of %d graphs per step" % (what, len(graphs))
         dense = tuple(torch.from_numpy(a) for a in O.merge_dense([graph_from_sparse(g) for g in graphs]))
         n_real = sum(g.Ri_rows.shape[0] for g in graphs)
 
@@ -175,7 +212,7 @@ def run_reference(args, rank, world):
             return dense, n_real, len(graphs)
 
         def forward(inp):
-            O.dense_forward(p, inp[0], inp[1], inp[2], cfg["n_iters"])
+            dense_fwd(inp[0], inp[1], inp[2])
 
     for i in range(args.warmup):
         forward(prepare(i)[0])
@@ -194,7 +231,7 @@ def run_reference(args, rank, world):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["desc"], "hidden_dim": cfg["h"], "n_iters": cfg["n_iters"], "batch": cfg["batch"]},
-        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -210,10 +247,13 @@ def cpu_baseline(workload, budget_s=15.0):
     torch.set_num_threads(cores)
     graphs = make_graphs(workload, 0)
     p = O.init_params(cfg["F"], cfg["h"], seed=0)
+    masks = None
     if cfg.get("masked"):
         from gnn_fpga_b200 import data as _data
-        p = O.apply_masks(p, *_data.random_masks(cfg["F"], cfg["h"], keep=0.5, seed=1234))
-    out = {"unit": "edges/s", "cores": cores, "kind": "port"}
+        masks = _data.random_masks(cfg["F"], cfg["h"], keep=0.5, seed=1234)
+        p = O.apply_masks(p, *masks)
+    dense_fwd, kind = reference_dense_forward(p, cfg, masks)
+    out = {"unit": "edges/s", "cores": cores, "kind": "port" if workload == "mu200" else kind}
     X, src, dst, _ = O.flatten_sparse_batch(graphs)
     n_real = int(((src >= 0) & (dst >= 0)).sum())
     t0 = time.perf_counter()
@@ -235,17 +275,344 @@ def cpu_baseline(workload, budget_s=15.0):
             Xd, Ri, Ro = (torch.from_numpy(a) for a in O.merge_dense([graph_from_sparse(g) for g in graphs]))
             e = n_real
         t0 = time.perf_counter()
-        O.dense_forward(p, Xd, Ri, Ro, cfg["n_iters"])
+        dense_fwd(Xd, Ri, Ro)
         t_total += time.perf_counter() - t0
         edges += e
         n += 1
     out["value"] = edges / t_total
-    out["sample"] = ("dense restatement of gnn/model.py, %d %s in %.1f s" %
-                     (n, "events one at a time" if per_event else "full batches", t_total))
+    out["sample"] = ("%s, %d %s in %.1f s" % ("gnn/model.py SegmentClassifier.forward itself" if kind == "reference" else
+                                              "dense restatement of gnn/model.py", n,
+                                              "events one at a time" if per_event else "full batches", t_total))
     return out
 
 
 # -----------------------------------------------------------------------------------------
+def measure_workload(workload, args, rank, world, local_rank, dev, dist, sampler=None, light=False):
+    """Everything bench.py reports for one workload on this rank: device-timed forward (`value`), per-kernel
+    times, e2e through predict_stream from a GraphStore (and from raw tuples), the training step.  Returns a
+    dict of per-rank numbers (reduced over ranks by the caller).  light = True: the sub-record of a second
+    workload (no training step, fewer extras)."""
+    from gnn_fpga_b200 import SegmentClassifier, DeviceGraphBatch, GraphStore, _lib
+    from gnn_fpga_b200.graph import _ptr, _stream_ptr
+    import ctypes as C
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    cfg = WORKLOADS[workload]
+    graphs = make_graphs(workload, rank)
+    torch.manual_seed(0)
+    masks_e = masks_n = None
+    if cfg.get("masked"):
+        from gnn_fpga_b200 import data as _data
+        masks_e, masks_n = _data.random_masks(cfg["F"], cfg["h"], keep=0.5, seed=1234)
+    model = SegmentClassifier(cfg["F"], cfg["h"], cfg["n_iters"], masks_e=masks_e, masks_n=masks_n).to(dev).eval()
+    # load time: the data set goes into the pinned event store once (narrowed, validated, laid out)
+    t0 = time.perf_counter()
+    store = GraphStore.from_sparse_graphs(graphs, reorder=os.environ.get("GNNSEG_BENCH_REORDER", "none"))
+    store_build_s = time.perf_counter() - t0
+    n_events = len(graphs)
+    batch = DeviceGraphBatch.from_store(store, 0, n_events, dev)
+    n_real = batch.count_real_edges()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    steps = args.steps
+    h, F, it = cfg["h"], cfg["F"], cfg["n_iters"]
+    fused = h in (32, 64) and not os.environ.get("GNNSEG_EXACT")
+
+    # ---- value: batch resident in HBM ----------------------------------------------------
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            model(batch)
+        barrier()
+        if sampler:
+            sampler.mark_start()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for i in range(steps):
+            flush.zero_()
+            starts[i].record()
+            model._run(batch)                 # the CUDA-graph replay alone (model(batch) adds a clone of the scores)
+            ends[i].record()
+        barrier()
+        if sampler:
+            sampler.mark_end()
+        model.check_range()
+    step_ms = [s_.elapsed_time(e_) for s_, e_ in zip(starts, ends)]
+    res = {"total_ms": float(sum(step_ms)), "n_real": n_real, "n_events": n_events, "n_nodes": batch.n_nodes,
+           "store_build_ms": store_build_s * 1e3, "fused": fused}
+    # pack x2 + status memset, input, then per iteration: fused path 2 kernels; step-by-step path edge + node (2 kernels at h = 32 / 64)
+    if fused:
+        res["launches_per_step"] = 2 + 1 + 2 * it + 1
+    else:
+        res["launches_per_step"] = 2 + 1 + (it + 1) + it * (2 if h in (32, 64) else 1)
+
+    # ---- per-kernel durations (same process, CUDA events around single launches) ----------
+    L = _lib.lib()
+    blob = model.pack_weights()
+    n, m = batch.n_nodes, batch.n_slots
+    X4 = torch.empty(n, 4, device=dev)
+    kt = {}
+
+    def timed(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); rc = fn(); b.record()
+        assert rc == 0, (name, rc)
+        kt.setdefault(name, []).append((a, b))
+
+    st = _stream_ptr(dev)
+    reps = max(3, min(steps, 20))
+    gs = C.byref(batch.struct)
+    if fused:
+        S = [torch.empty(n, 5 * h, device=dev) for _ in range(2)]
+        P = torch.empty(n, 2 * h, device=dev)
+        sc = torch.empty(m, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        for rep in range(reps + 1):
+            if rep == 1:
+                kt.clear()
+            flush.zero_()
+            if it == 0:
+                timed("input", lambda: L.gnnseg_state_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(X4), _ptr(P), 2, _ptr(status), st))
+            else:
+                timed("input", lambda: L.gnnseg_state_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(X4), _ptr(S[0]), 1, _ptr(status), st))
+            cur = 0
+            for i in range(it):
+                last = i + 1 == it
+                rows, ld = (P, 2 * h) if last else (S[cur ^ 1], 5 * h)
+                timed("fused_gather", lambda: L.gnnseg_fused_gather_step(_ptr(blob), gs, _ptr(S[cur]), h, _ptr(rows), ld, st))
+                timed("node_mlp", lambda: L.gnnseg_state_mlp_step(_ptr(blob), _ptr(X4), _ptr(rows), ld, n, h, _ptr(rows), 2 if last else 1, _ptr(status), st))
+                cur ^= 1
+            timed("edge_final", lambda: L.gnnseg_edge_final_step(_ptr(blob), gs, _ptr(P), 2 * h, 0, h, h, _ptr(sc), st))
+        mult = {"input": 1, "edge_final": 1}
+    else:
+        Q = [torch.empty(n, 3 * h, device=dev) for _ in range(2)]
+        P = torch.empty(n, 2 * h, device=dev)
+        e = torch.empty(m, device=dev)
+        e_in = torch.empty(m, device=dev)
+        e_out = torch.empty(m, device=dev)
+        split = h in (32, 64)
+        h1 = torch.empty(n, h, device=dev) if split else None
+        for rep in range(reps + 1):
+            if rep == 1:
+                kt.clear()
+            flush.zero_()
+            timed("input", lambda: L.gnnseg_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(X4), _ptr(P), _ptr(Q[0]), st))
+            cur = 0
+            for i in range(it):
+                qo = _ptr(Q[cur ^ 1]) if i + 1 < it else None
+                timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), gs, _ptr(P), h, None, _ptr(e_in), _ptr(e_out), st))
+                if split:
+                    timed("node_gather", lambda: L.gnnseg_node_gather_step(gs, _ptr(Q[cur]), _ptr(e_in), _ptr(e_out), h, _ptr(h1), h, st))
+                    timed("node_mlp", lambda: L.gnnseg_node_mlp_step(_ptr(blob), _ptr(X4), _ptr(h1), h, n, h, _ptr(P), qo, st))
+                else:
+                    timed("node", lambda: L.gnnseg_node_step(_ptr(blob), gs, _ptr(X4), _ptr(Q[cur]), _ptr(e_in), _ptr(e_out), h, _ptr(P), qo, st))
+                cur ^= 1
+            timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), gs, _ptr(P), h, _ptr(e), None, None, st))
+        mult = {"input": 1, "edge": it + 1}
+    torch.cuda.synchronize(dev)
+    res["kernel_ms"] = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in kt.items() if v}
+    res["kernel_share"] = {k: res["kernel_ms"][k] * mult.get(k, it) for k in res["kernel_ms"]}
+
+    # ---- e2e: host -> scores on the host, through model.predict_stream ----------------------------
+    if not args.no_e2e:
+        sb = store.batch(0, n_events)
+        host_ref = None
+        with torch.no_grad():
+            for out_host in model.predict_stream([sb] * 3):
+                host_ref = out_host.clone()
+            barrier()
+            t0 = time.perf_counter()
+            n_out = 0
+            for out_host in model.predict_stream([sb] * steps):
+                n_out += 1
+            torch.cuda.synchronize(dev)
+            sec_store = time.perf_counter() - t0
+            assert n_out == steps and torch.equal(out_host, host_ref)
+            assert torch.equal(host_ref, batch.scores.view(n_events, batch.e_max).cpu())      # same bits as the resident run
+            # stage breakdown of one batch, serialised (CUDA events between the stages)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            pinned_out = torch.empty((n_events, batch.e_max), dtype=torch.float32, pin_memory=True)
+            stages = np.zeros(4)
+            host_enqueue = 0.0
+            for rep in range(4):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                ev[0].record()
+                meta, nn, e_max, n_in, n_out_ = store.batch_meta(0, n_events)
+                bufs = batch._bufs
+                v = bufs.views(nn, n_in, n_out_, n_events * e_max, n_events)
+                bufs.meta_host[:meta.shape[0]] = torch.from_numpy(meta)
+                v["meta"].copy_(bufs.meta_host[:meta.shape[0]], non_blocking=True)
+                for d_t, s_t in zip((v["X"], v["in_ptr_l"], v["out_ptr_l"], v["in_col"], v["out_col"]), store.slices(0, n_events)):
+                    d_t.copy_(s_t, non_blocking=True)
+                ev[1].record()
+                b2 = DeviceGraphBatch.from_store(store, 0, n_events, dev, bufs=bufs)      # copies again + assembly (copies subtracted below)
+                ev[2].record()
+                sc2 = model._run(b2)
+                ev[3].record()
+                pinned_out.copy_(sc2.view(n_events, batch.e_max), non_blocking=True)
+                ev[4].record()
+                host_enqueue = time.perf_counter() - t0
+                torch.cuda.synchronize(dev)
+                if rep > 0:
+                    t = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+                    stages += np.array([t[0], max(t[1] - t[0], 0.0), t[2], t[3]])
+            stages /= 3
+            res["e2e"] = {"sec": sec_store, "h2d": store.h2d_bytes(0, n_events), "d2h": pinned_out.numel() * 4 + 4,
+                          "stages_ms": {"host_pack": 0.0, "h2d": float(stages[0]), "assemble": float(stages[1]),
+                                        "forward": float(stages[2]), "d2h": float(stages[3]), "host_enqueue": host_enqueue * 1e3}}
+            if not light:
+                # the same from raw int64 SparseGraph tuples: a worker thread narrows / packs every batch first
+                for _ in model.predict_stream([graphs] * 2):
+                    pass
+                barrier()
+                t0 = time.perf_counter()
+                for out_host in model.predict_stream([graphs] * max(3, steps // 4)):
+                    pass
+                torch.cuda.synchronize(dev)
+                res["e2e"]["sec_tuples"] = (time.perf_counter() - t0) / max(3, steps // 4) * steps
+                assert torch.equal(out_host, host_ref)
+                t0 = time.perf_counter()
+                for _ in range(max(3, steps // 4)):
+                    pinned_out.copy_(model(graphs), non_blocking=True)
+                    torch.cuda.synchronize(dev)
+                res["e2e"]["sec_blocking"] = (time.perf_counter() - t0) / max(3, steps // 4) * steps
+
+    # ---- training step (BASELINE configs[4]): forward_train + BCE + L1 + backward + all-reduce + Adam ----
+    if not args.no_train and not light:
+        from gnn_fpga_b200.training import NativeTrainer
+        tmodel = SegmentClassifier(cfg["F"], cfg["h"], cfg["n_iters"], masks_e=masks_e, masks_n=masks_n).to(dev).train()
+        tmodel.load_state_dict(model.state_dict())
+        y = store.targets(0, n_events).to(dev)
+        trainer = NativeTrainer(tmodel, l1=1e-4)
+        for _ in range(3):
+            trainer.step(batch, y)
+        barrier()
+        n_tr = max(3, min(steps, 20))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_tr):
+            trainer.step(batch, y)
+        b.record()
+        barrier()
+        res["train"] = {"ms": a.elapsed_time(b) / n_tr, "loss": float(trainer.loss.item())}
+        del trainer, tmodel
+        batch._ws = {k: v for k, v in batch._ws.items() if not (isinstance(k, tuple) and k[0] == "train")}
+
+    # ---- the collective of the inference path: all ranks receive all scores (NCCL all-gather) --------
+    if world > 1 and not light:
+        from gnn_fpga_b200.dist import ScoreGatherer
+        gat = ScoreGatherer()
+        local = batch.scores_2d()
+        with torch.no_grad():
+            allsc = gat(local)                                  # exchanges the block shapes once
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                allsc = gat(local)
+            b.record()
+            torch.cuda.synchronize(dev)
+            res["gather_ms"] = a.elapsed_time(b) / 10
+            # value_with_gather: forward + all-gather back to back on the compute stream, L2 flushed per step
+            barrier()
+            sg = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+            eg = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+            for i in range(steps):
+                flush.zero_()
+                sg[i].record()
+                model._run(batch)
+                allsc = gat(batch.scores_2d())
+                eg[i].record()
+            barrier()
+            res["total_ms_with_gather"] = float(sum(s_.elapsed_time(e_) for s_, e_ in zip(sg, eg)))
+            # SURVEY 8(e) gate: the rows rank r receives from rank (r + 1) % world are bit-equal to this rank's own
+            # forward of that rank's events (deterministic kernels, independent events)
+            other = (rank + 1) % world
+            ob = DeviceGraphBatch.from_store(GraphStore.from_sparse_graphs(make_graphs(workload, other), reorder=os.environ.get("GNNSEG_BENCH_REORDER", "none")),
+                                             0, n_events, dev)
+            mine = model._run(ob).view(n_events, ob.e_max)
+            got = allsc[other * n_events:(other + 1) * n_events, :ob.e_max]
+            res["gather_bit_equal"] = bool(torch.equal(mine, got))
+            assert res["gather_bit_equal"], "rank %d: gathered scores of rank %d differ from a local recompute" % (rank, other)
+    res["cfg"] = cfg
+    return res
+
+
+def reduce_over_ranks(res, world, dist, dev):
+    """max over ranks of the times, sum over ranks of the counts (in place)."""
+    if world <= 1:
+        res["all_edges"], res["all_events"] = float(res["n_real"]), float(res["n_events"])
+        return res
+    e2e = res.get("e2e", {})
+    times = torch.tensor([res["total_ms"], e2e.get("sec", 0.0), e2e.get("sec_tuples", 0.0), e2e.get("sec_blocking", 0.0),
+                          res.get("gather_ms", 0.0), res.get("total_ms_with_gather", 0.0), res.get("train", {}).get("ms", 0.0)],
+                         dtype=torch.float64, device=dev)
+    counts = torch.tensor([res["n_real"], res["n_events"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    t = times.tolist()
+    res["total_ms"] = t[0]
+    if e2e:
+        e2e["sec"], e2e["sec_tuples"], e2e["sec_blocking"] = t[1], t[2], t[3]
+    if "gather_ms" in res:
+        res["gather_ms"], res["total_ms_with_gather"] = t[4], t[5]
+    if "train" in res:
+        res["train"]["ms"] = t[6]
+    res["all_edges"], res["all_events"] = counts.tolist()
+    return res
+
+
+def record_of(res, args, world, workload, peak, peak_src):
+    """The JSON fields of one workload from its (rank-reduced) measurements."""
+    cfg = res["cfg"]
+    h, F, it = cfg["h"], cfg["F"], cfg["n_iters"]
+    steps = args.steps
+    ab = algorithmic_bytes(res["n_nodes"], res["n_real"], F, h, it)
+    ab["fused_gather"] = ab["edge"] + ab["node"]        # the edge step evaluated inside the node step's CSR walk
+    ab["edge_final"] = ab["edge"]
+    kernel_ms, share = res["kernel_ms"], res["kernel_share"]
+    dom = max(share, key=share.get)
+    try:     # DRAM bytes per launch of that kernel, from the committed ncu capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[workload][dom]
+    except Exception:
+        traffic = None
+    achieved = ab[dom] / (kernel_ms[dom] * 1e-3) / 1e9
+    ms_per_step = res["total_ms"] / steps
+    fwd_gbs = ab["forward"] / (ms_per_step * 1e-3) / 1e9
+    rec = {
+        "value": res["all_edges"] * steps / (res["total_ms"] * 1e-3), "unit": "edges/s",
+        "events_per_sec": res["all_events"] * steps / (res["total_ms"] * 1e-3), "ms_per_step": ms_per_step,
+        "config": {"workload": cfg["desc"], "hidden_dim": h, "n_iters": it, "batch_per_gpu": res["n_events"],
+                   "nodes_per_gpu": res["n_nodes"], "edges_per_gpu": res["n_real"], "parallelism": "events sharded, dp%d" % world,
+                   "l2": "flushed between timed steps (256 MiB write)", "cuda_graph": True,
+                   "path": "fused (edge step inside the node step's CSR walk)" if res["fused"] else "step by step"},
+        "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ab[dom], "kernel_ms": kernel_ms[dom]},
+        "roofline_forward": {"achieved": fwd_gbs, "frac": fwd_gbs / peak, "unit": "GB/s", "algorithmic_bytes": ab["forward"]},
+        "kernel_ms": kernel_ms, "kernel_ms_per_step": share,
+        "gpu_launches": res["launches_per_step"] * steps,
+    }
+    if "e2e" in res:
+        e = res["e2e"]
+        rec["e2e"] = {"value": res["all_edges"] * steps / e["sec"], "unit": "edges/s",
+                      "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"], "ms_per_step": e["sec"] / steps * 1e3,
+                      "path": "model.predict_stream(store.batches(B)): the data set sits in a GraphStore (pinned host arena, built once at "
+                              "load time: %.1f ms for this batch); per batch five contiguous H2D copies, gnnseg_assemble_batch, forward, "
+                              "D2H of the scores into pinned memory; three batches in flight" % res["store_build_ms"],
+                      "stages_ms": e["stages_ms"]}
+        if e.get("sec_tuples"):
+            rec["e2e"]["from_tuples"] = {"value": res["all_edges"] * steps / e["sec_tuples"], "ms_per_step": e["sec_tuples"] / steps * 1e3,
+                                         "path": "model.predict_stream(batches of raw int64 SparseGraph tuples): a worker thread narrows and "
+                                                 "validates every batch into a one-batch store first (<= 4 threads), then the same device path"}
+            rec["e2e"]["blocking"] = {"value": res["all_edges"] * steps / e["sec_blocking"], "ms_per_step": e["sec_blocking"] / steps * 1e3,
+                                      "path": "model(graphs) then copy to pinned host memory, synchronised every step"}
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -256,6 +623,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-mu200", action="store_true", help="skip the mu200 sub-record of the default single-GPU run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -268,9 +636,6 @@ def main():
         return
 
     import torch.distributed as dist
-    from gnn_fpga_b200 import SegmentClassifier, DeviceGraphBatch, _lib
-    from gnn_fpga_b200.graph import _ptr, _stream_ptr
-    import ctypes as C
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
@@ -279,176 +644,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    cfg = WORKLOADS[args.workload]
-    graphs = make_graphs(args.workload, rank)
-    torch.manual_seed(0)
-    masks_e = masks_n = None
-    if cfg.get("masked"):
-        from gnn_fpga_b200 import data as _data
-        masks_e, masks_n = _data.random_masks(cfg["F"], cfg["h"], keep=0.5, seed=1234)
-    model = SegmentClassifier(cfg["F"], cfg["h"], cfg["n_iters"], masks_e=masks_e, masks_n=masks_n).to(dev).eval()
-    batch = DeviceGraphBatch.from_sparse_graphs(graphs, dev)
-    n_real = batch.count_real_edges()
-    n_events = len(graphs)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-
-    # ---- value: batch resident in HBM ----------------------------------------------------
-    with torch.no_grad():
-        sampler = ClockSampler(local_rank) if rank == 0 else None
-        for _ in range(args.warmup):
-            model(batch)
-        barrier()
-        if sampler:
-            sampler.mark_start()
-        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        for i in range(args.steps):
-            flush.zero_()
-            starts[i].record()
-            model(batch)
-            ends[i].record()
-        barrier()
-        if sampler:
-            sampler.mark_end()
-        clocks = sampler.stop() if sampler else None
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = float(sum(step_ms))
-    # pack x2, input, edge x(it+1), node x it (two kernels per node step at hidden_dim = 32 and 64)
-    launches_per_step = 2 + 1 + (cfg["n_iters"] + 1) + cfg["n_iters"] * (2 if cfg["h"] in (32, 64) else 1)
-
-    # ---- per-kernel durations (same process, CUDA events around single launches) ----------
-    L = _lib.lib()
-    h, F, it = cfg["h"], cfg["F"], cfg["n_iters"]
-    blob = model.pack_weights()
-    X4 = torch.empty(batch.n_nodes, 4, device=dev)
-    Q = [torch.empty(batch.n_nodes, 3 * h, device=dev) for _ in range(2)]
-    P = torch.empty(batch.n_nodes, 2 * h, device=dev)
-    e = torch.empty(batch.n_slots, device=dev)
-    e_in = torch.empty(batch.n_slots, device=dev)
-    e_out = torch.empty(batch.n_slots, device=dev)
-    split = h in (32, 64)                # node step = gather kernel + tensor-core MLP kernel (include/gnnseg.h)
-    h1 = torch.empty(batch.n_nodes, h, device=dev) if split else None
-    kt = {}
-
-    def timed(name, fn):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); rc = fn(); b.record()
-        assert rc == 0, (name, rc)
-        kt.setdefault(name, []).append((a, b))
-
-    st = _stream_ptr(dev)
-    reps = max(3, min(args.steps, 20))
-    for rep in range(reps + 1):
-        if rep == 1:
-            kt.clear()                                      # drop the warm-up pass
-        flush.zero_()
-        timed("input", lambda: L.gnnseg_input_step(_ptr(blob), _ptr(batch.X), batch.n_nodes, F, h, _ptr(X4), _ptr(P), _ptr(Q[0]), st))
-        cur = 0
-        for i in range(it):
-            qo = _ptr(Q[cur ^ 1]) if i + 1 < it else None
-            timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, None, _ptr(e_in), _ptr(e_out), st))
-            if split:
-                timed("node_gather", lambda: L.gnnseg_node_gather_step(C.byref(batch.struct), _ptr(Q[cur]), _ptr(e_in), _ptr(e_out), h, _ptr(h1), h, st))
-                timed("node_mlp", lambda: L.gnnseg_node_mlp_step(_ptr(blob), _ptr(X4), _ptr(h1), h, batch.n_nodes, h, _ptr(P), qo, st))
-            else:
-                timed("node", lambda: L.gnnseg_node_step(_ptr(blob), C.byref(batch.struct), _ptr(X4), _ptr(Q[cur]), _ptr(e_in), _ptr(e_out), h, _ptr(P), qo, st))
-            cur ^= 1
-        timed("edge", lambda: L.gnnseg_edge_step(_ptr(blob), C.byref(batch.struct), _ptr(P), h, _ptr(e), None, None, st))
-    torch.cuda.synchronize(dev)
-    kernel_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in kt.items() if v}
-    kernel_share = {k: kernel_ms[k] * {"input": 1, "edge": it + 1}.get(k, it) for k in kernel_ms}
-
-    # ---- e2e: host SparseGraph tuples -> scores on the host ---------------------------------
-    e2e = None
-    if not args.no_e2e:
-        model.use_cuda_graph = False
-        host_out = torch.empty((len(graphs), batch.e_max), dtype=torch.float32, pin_memory=True)
-        with torch.no_grad():
-            for _ in range(3):
-                host_out.copy_(model(graphs), non_blocking=True)
-                torch.cuda.synchronize(dev)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                host_out.copy_(model(graphs), non_blocking=True)   # scores land in pinned host memory
-                torch.cuda.synchronize(dev)                        # every step ends with its result on the host
-            dt = time.perf_counter() - t0
-        model.use_cuda_graph = True
-        h2d = batch.X.numel() * 4 + batch.src.numel() * 4 + batch.dst.numel() * 4
-        d2h = host_out.numel() * 4
-        e2e = {"sec": dt, "h2d": h2d, "d2h": d2h}
-        # the same work, pipelined: predict_stream keeps two batches in flight (host packing of
-        # batch i+1 overlaps the GPU work of batch i); every batch still does its own H2D and D2H
-        for _ in model.predict_stream([graphs] * 3):
-            pass
-        barrier()
-        t0 = time.perf_counter()
-        n_out = 0
-        for out_host in model.predict_stream([graphs] * args.steps):
-            n_out += 1
-        torch.cuda.synchronize(dev)
-        e2e["sec_pipelined"] = time.perf_counter() - t0
-        assert n_out == args.steps and torch.equal(out_host, host_out)
-
-    # ---- training step (BASELINE configs[4]): forward_train + BCE + L1 + backward + all-reduce + Adam ----
-    train = None
-    if not args.no_train:
-        from gnn_fpga_b200.training import NativeTrainer
-        tmodel = SegmentClassifier(cfg["F"], cfg["h"], cfg["n_iters"], masks_e=masks_e, masks_n=masks_n).to(dev).train()
-        tmodel.load_state_dict(model.state_dict())
-        y = torch.zeros((n_events, batch.e_max), dtype=torch.float32)
-        for b_, g_ in enumerate(graphs):
-            y[b_, :g_.y.shape[0]] = torch.from_numpy(g_.y)
-        y = y.to(dev)
-        trainer = NativeTrainer(tmodel, l1=1e-4)
-        for _ in range(3):
-            trainer.step(batch, y)
-        barrier()
-        n_tr = max(3, min(args.steps, 20))
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(n_tr):
-            trainer.step(batch, y)
-        b.record()
-        barrier()
-        train = {"ms": a.elapsed_time(b) / n_tr, "loss": float(trainer.loss.item())}
-        del trainer, tmodel
-        batch._ws = {k: v for k, v in batch._ws.items() if not (isinstance(k, tuple) and k[0] == "train")}
-
-    # ---- optional collective: all ranks receive all scores (NCCL all-gather, not in `value`) ------
-    gather_ms = None
-    if world > 1:
-        from gnn_fpga_b200.dist import gather_scores, shard_bounds
-        bounds = shard_bounds(world * n_events, world)
-        local = batch.scores_2d()
-        gather_scores(local, bounds)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(5):
-            allsc = gather_scores(local, bounds)
-        b.record()
-        torch.cuda.synchronize(dev)
-        gather_ms = a.elapsed_time(b) / 5
-        assert allsc.shape[0] == world * n_events
-
-    # ---- reduce over ranks ---------------------------------------------------------------------
-    stats = torch.tensor([total_ms, e2e["sec"] if e2e else 0.0, gather_ms or 0.0,
-                          e2e["sec_pipelined"] if e2e else 0.0, train["ms"] if train else 0.0], dtype=torch.float64, device=dev)
-    counts = torch.tensor([n_real, n_events], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    total_ms, e2e_sec, gather_ms_max, e2e_pipe_sec, train_ms = stats.tolist()
-    all_edges, all_events = counts.tolist()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    res = measure_workload(args.workload, args, rank, world, local_rank, dev, dist, sampler=sampler)
+    clocks = sampler.stop() if sampler else None
+    reduce_over_ranks(res, world, dist, dev)
+    # the configuration the HBM target is quoted on (BASELINE configs[3]) rides along in the default single-GPU run
+    sub = None
+    if world == 1 and args.workload == "acts64" and not args.no_mu200:
+        sub = reduce_over_ranks(measure_workload("mu200", args, rank, world, local_rank, dev, dist, light=True), world, dist, dev)
 
     if rank == 0:
-        ab = algorithmic_bytes(batch.n_nodes, n_real, F, h, it)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -456,54 +661,35 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-        dom = max(kernel_share, key=kernel_share.get)
-        dom_bytes = ab[dom]
-        try:     # DRAM bytes per launch of that kernel, from the committed ncu capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[args.workload][dom]
-        except Exception:
-            traffic = None
-        achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9
-        ms_per_step = total_ms / args.steps
-        fwd_gbs = ab["forward"] / (ms_per_step * 1e-3) / 1e9
-        line = {
-            "metric": "segment_classifier_forward_edges_per_sec",
-            "value": all_edges * args.steps / (total_ms * 1e-3),
-            "unit": "edges/s",
-            "events_per_sec": all_events * args.steps / (total_ms * 1e-3),
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "hidden_dim": h, "n_iters": it, "batch_per_gpu": n_events,
-                       "nodes_per_gpu": batch.n_nodes, "edges_per_gpu": n_real, "parallelism": "events sharded, dp%d" % world,
-                       "l2": "flushed between timed steps (256 MiB write)", "cuda_graph": True},
-            "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": kernel_ms[dom]},
-            "roofline_forward": {"achieved": fwd_gbs, "frac": fwd_gbs / peak, "unit": "GB/s",
-                                 "algorithmic_bytes": ab["forward"]},
-            "kernel_ms": kernel_ms, "kernel_ms_per_step": kernel_share,
-            "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks,
-        }
-        if e2e:
-            line["e2e"] = {"value": all_edges * args.steps / e2e_pipe_sec, "unit": "edges/s",
-                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "ms_per_step": e2e_pipe_sec / args.steps * 1e3,
-                           "path": "model.predict_stream(batches of host SparseGraph): per batch C host packing into pinned memory, "
-                                   "H2D, device CSR build, forward, D2H into pinned memory; two batches in flight",
-                           "unpipelined": {"value": all_edges * args.steps / e2e_sec, "ms_per_step": e2e_sec / args.steps * 1e3,
-                                           "path": "model(graphs) then copy to pinned host memory, synchronised every step"}}
-        if train:
+        rec = record_of(res, args, world, args.workload, peak, peak_src)
+        cfg = res["cfg"]
+        it, h = cfg["n_iters"], cfg["h"]
+        line = {"metric": "segment_classifier_forward_edges_per_sec", "value": rec.pop("value"), "unit": rec.pop("unit"),
+                "events_per_sec": rec.pop("events_per_sec"), "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": rec.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic"}
+        line.update(rec)
+        line["clocks"] = clocks
+        if "train" in res:
+            tr = res["train"]
             n_k = 2 + 1 + (it + 1) + it * (2 if h in (32, 64) else 1) + 2 + 1 + 3 * (it + 1) + 1 + 1 + 1
-            line["train_step"] = {"ms": train_ms, "edges_per_sec": all_edges / (train_ms * 1e-3),
-                                  "events_per_sec": all_events / (train_ms * 1e-3), "loss": train["loss"],
+            line["train_step"] = {"ms": tr["ms"], "edges_per_sec": res["all_edges"] / (tr["ms"] * 1e-3),
+                                  "events_per_sec": res["all_events"] / (tr["ms"] * 1e-3), "loss": tr["loss"],
                                   "gpu_launches_per_step": n_k,
                                   "path": "NativeTrainer.step on the resident batch: gnnseg_forward_train, gnnseg_bce_loss, "
                                           "gnnseg_backward, gnnseg_l1_penalty, %sgnnseg_adam_step; L2 not flushed"
                                           % ("NCCL all-reduce of the flat gradient, " if world > 1 else "")}
         if world > 1:
-            line["scores_allgather_ms"] = gather_ms_max    # NCCL all-gather of every rank's (B, E_max) scores
+            line["scores_allgather_ms"] = res["gather_ms"]      # one all_gather_into_tensor of every rank's (B, E_max) scores
+            line["value_with_gather"] = res["all_edges"] * args.steps / (res["total_ms_with_gather"] * 1e-3)
+            line["ms_per_step_with_gather"] = res["total_ms_with_gather"] / args.steps
+            line["gathered_scores_bit_equal_to_local_recompute"] = res.get("gather_bit_equal")
+        if sub is not None:
+            line["mu200"] = record_of(sub, args, world, "mu200", peak, peak_src)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
+            if sub is not None:
+                line["mu200"]["cpu_baseline"] = cpu_baseline("mu200")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -16,6 +16,8 @@ ERRORS = {-1: "EINVAL", -2: "EUNSUPPORTED", -3: "EWORKSPACE", -4: "ECUDA", -5: "
 EHYPEREDGE = -8
 BAD_VALUE = 1
 BAD_HYPEREDGE = 2
+FWD_EXACT = 1            # gnnseg_forward_ex flags: force the step-by-step kernels
+RANGE_CLAMPED = 1        # gnnseg_forward_ex status bit: an edge projection left the fused path's range
 
 _f32p = C.c_void_p
 _i32p = C.c_void_p
@@ -47,7 +49,7 @@ class GnnsegStoreLayout(C.Structure):
 
 class GnnsegGraph(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_slots", C.c_int32)] + [(n, C.c_void_p) for n in (
-        "src", "dst", "in_ptr", "in_eid", "in_nbr", "out_ptr", "out_eid", "out_nbr", "in_pos", "out_pos")]
+        "src", "dst", "in_ptr", "in_eid", "in_nbr", "out_ptr", "out_eid", "out_nbr", "in_pos", "out_pos", "adj_ptr", "adj")]
 
 
 # name -> (restype, argtypes); must list every symbol include/gnnseg.h declares
@@ -65,6 +67,13 @@ SIGNATURES = {
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnnseg_forward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gnnseg_forward": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gnnseg_forward_ex": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t,
+                                   C.c_int, _i32p, C.c_void_p]),
+    "gnnseg_build_adjacency": (C.c_int, [C.POINTER(GnnsegGraph), _i32p, _i32p, C.c_void_p]),
+    "gnnseg_state_input_step": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_int, _i32p, C.c_void_p]),
+    "gnnseg_fused_gather_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, _f32p, C.c_int, C.c_void_p]),
+    "gnnseg_state_mlp_step": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, _i32p, C.c_void_p]),
+    "gnnseg_edge_final_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p]),
     "gnnseg_input_step": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_void_p]),
     "gnnseg_edge_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, _f32p, _f32p, _f32p, C.c_void_p]),
     "gnnseg_node_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, _f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, C.c_void_p]),

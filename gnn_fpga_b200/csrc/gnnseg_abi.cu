@@ -1,5 +1,6 @@
 // extern "C" entry points declared in include/gnnseg.h.  Argument checking happens here, on
 // the host; the kernels live in gnnseg_forward.cu / gnnseg_graph.cu.
+#include <cstdlib>
 #include "gnnseg_common.cuh"
 
 namespace gnnseg {
@@ -15,6 +16,14 @@ int dense_to_edges(const float*, const float*, int, int, int, int32_t*, int32_t*
 size_t csr_workspace_bytes(int, int);
 int build_csr(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
 int build_graph(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+int fused_gather_step(const float*, const GnnsegGraph*, const float*, int, float*, int, cudaStream_t);
+int edge_final_step(const float*, const GnnsegGraph*, const float*, int, int, int, int, float*, cudaStream_t);
+int build_adjacency(const GnnsegGraph*, int32_t*, int32_t*, cudaStream_t);
+int launch_input_tc32_ex(const float*, const float*, int, int, float*, const ProjOut&, bool, float*, cudaStream_t);
+int launch_input_tc64_ex(const float*, const float*, int, int, float*, const ProjOut&, bool, float*, cudaStream_t);
+int launch_node_mlp_tc32_ex(const float*, const float*, const float*, int, int, const ProjOut&, bool, float*, bool, cudaStream_t);
+int launch_node_mlp_tc64_ex(const float*, const float*, const float*, int, int, const ProjOut&, bool, float*, bool, cudaStream_t);
+bool use_pdl(int);
 int assemble_batch(const int32_t*, int, int, int, int, int, const int32_t*, const int32_t*, const void*, const void*, int,
                    const GnnsegGraphMut&, cudaStream_t);
 // gnnseg_backward.cu
@@ -56,16 +65,20 @@ struct FwdWorkspace {
     float* q[2];
     float* e_in;
     float* e_out;
+    float* s[2];          // fused path: state rows (alias q / e_in / e_out)
+    int32_t* status;      // fused path: range flag word
     size_t bytes;
 };
 
-// X4 | P | Q0 | Q1 | e_in | e_out, each 256-byte aligned.
+// X4 | P | Q0 | Q1 | e_in | e_out, each 256-byte aligned.  The fused inference path (gnnseg_fused.cu) uses
+// the same block as X4 | P | S0 | S1 | status word, with S = state rows of 5h floats.
 FwdWorkspace carve(void* ws, int n_nodes, int n_slots, int h) {
     FwdWorkspace w;
     const size_t x_b = align_up((size_t)n_nodes * 4 * 4, 256);
     const size_t p_b = align_up((size_t)n_nodes * 2 * h * 4, 256);
     const size_t q_b = align_up((size_t)n_nodes * 3 * h * 4, 256);
     const size_t e_b = align_up((size_t)n_slots * 4, 256);
+    const size_t s_b = align_up((size_t)n_nodes * 5 * h * 4, 256);
     char* base = static_cast<char*>(ws);
     w.x4 = reinterpret_cast<float*>(base);
     w.p = reinterpret_cast<float*>(base + x_b);
@@ -73,8 +86,28 @@ FwdWorkspace carve(void* ws, int n_nodes, int n_slots, int h) {
     w.q[1] = reinterpret_cast<float*>(base + x_b + p_b + q_b);
     w.e_in = reinterpret_cast<float*>(base + x_b + p_b + 2 * q_b);
     w.e_out = reinterpret_cast<float*>(base + x_b + p_b + 2 * q_b + e_b);
-    w.bytes = x_b + p_b + 2 * q_b + 2 * e_b;
+    w.s[0] = reinterpret_cast<float*>(base + x_b + p_b);
+    w.s[1] = reinterpret_cast<float*>(base + x_b + p_b + s_b);
+    w.status = reinterpret_cast<int32_t*>(base + x_b + p_b + 2 * s_b);
+    const size_t steps = 2 * q_b + 2 * e_b, fused = 2 * s_b + 256;
+    w.bytes = x_b + p_b + (steps > fused ? steps : fused);
     return w;
+}
+
+inline bool fused_width(int h) { return h == 32 || h == 64; }
+inline bool exact_env() {
+    static const bool v = [] { const char* e = getenv("GNNSEG_EXACT"); return e && e[0] != '0'; }();
+    return v;
+}
+inline int state_input(const float* blob, const float* X, int n, int F, int h, float* X4, const gnnseg::ProjOut& out, bool state_order,
+                       cudaStream_t st) {
+    return h == 32 ? gnnseg::launch_input_tc32_ex(blob, X, n, F, X4, out, state_order, nullptr, st)
+                   : gnnseg::launch_input_tc64_ex(blob, X, n, F, X4, out, state_order, nullptr, st);
+}
+inline int state_mlp(const float* blob, const float* X4, const float* h1, int ld_h1, int n, int h, const gnnseg::ProjOut& out,
+                     bool state_order, bool pdl, cudaStream_t st) {
+    return h == 32 ? gnnseg::launch_node_mlp_tc32_ex(blob, X4, h1, ld_h1, n, out, state_order, nullptr, pdl, st)
+                   : gnnseg::launch_node_mlp_tc64_ex(blob, X4, h1, ld_h1, n, out, state_order, nullptr, pdl, st);
 }
 
 constexpr int MAX_ITERS = 64;
@@ -284,8 +317,8 @@ int gnnseg_node_mlp_step(const float* blob, const float* X4, const float* h1, in
     return gnnseg::node_mlp_step(blob, X4, h1, ld_h1, n_nodes, h, P_out, Q_out, static_cast<cudaStream_t>(stream));
 }
 
-int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int F, int h,
-                   int n_iters, float* scores, void* ws, size_t ws_bytes, void* stream) {
+int gnnseg_forward_ex(const float* blob, const GnnsegGraph* g, const float* X, int F, int h, int n_iters, float* scores,
+                      void* ws, size_t ws_bytes, int flags, int32_t* status, void* stream) {
     if (!gnnseg_supported(F, h)) return GNNSEG_EUNSUPPORTED;
     if (!blob || !csr_ok(g) || n_iters < 0 || !ws) return GNNSEG_EINVAL;
     if (g->n_nodes > 0 && !X) return GNNSEG_EINVAL;
@@ -296,6 +329,33 @@ int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int 
     const FwdWorkspace w = carve(reinterpret_cast<void*>(al), g->n_nodes, g->n_slots, h);
     if (ws_bytes < w.bytes + (al - raw)) return GNNSEG_EWORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t* flag = status ? status : w.status;
+    if (cudaMemsetAsync(flag, 0, sizeof(int32_t), st) != cudaSuccess) return GNNSEG_ECUDA;
+
+    const bool fused = fused_width(h) && g->adj_ptr && (g->adj || g->n_slots == 0) && !(flags & GNNSEG_FWD_EXACT) && !exact_env();
+    if (fused) {
+        // gnnseg_fused.cu: input -> n_iters x (edge step inside the node step's CSR walk, tensor-core MLP) -> final
+        // edge step over the destination-CSR.  2 * n_iters + 2 launches.  The last producing step writes only the
+        // edge projections, as exponentials, into P = [SPs | SPd].
+        const int n = g->n_nodes;
+        const bool pdl = gnnseg::use_pdl(g->n_slots);
+        const gnnseg::ProjOut last{w.p, nullptr, 2, 2 * h, flag};
+        int rc = n_iters == 0 ? state_input(blob, X, n, F, h, w.x4, last, false, st)
+                              : state_input(blob, X, n, F, h, w.x4, gnnseg::ProjOut{w.s[0], nullptr, 1, 5 * h, flag}, true, st);
+        int cur = 0;
+        for (int it = 0; it < n_iters && rc == GNNSEG_OK; ++it) {
+            const bool is_last = it + 1 == n_iters;
+            float* rows = is_last ? w.p : w.s[cur ^ 1];          // h1 travels in the first h floats of the rows it becomes
+            const int ld = is_last ? 2 * h : 5 * h;
+            rc = gnnseg::fused_gather_step(blob, g, w.s[cur], h, rows, ld, st);
+            if (rc == GNNSEG_OK)
+                rc = is_last ? state_mlp(blob, w.x4, rows, ld, n, h, last, false, pdl, st)
+                             : state_mlp(blob, w.x4, rows, ld, n, h, gnnseg::ProjOut{rows, nullptr, 1, 5 * h, flag}, true, pdl, st);
+            cur ^= 1;
+        }
+        if (rc == GNNSEG_OK) rc = gnnseg::edge_final_step(blob, g, w.p, 2 * h, 0, h, h, scores, st);
+        return rc;
+    }
 
     int rc = gnnseg::input_step(blob, X, g->n_nodes, F, h, w.x4, w.p, w.q[0], nullptr, st);
     int cur = 0;
@@ -309,6 +369,52 @@ int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int 
     }
     if (rc == GNNSEG_OK) rc = gnnseg::edge_step(blob, g, w.p, h, scores, nullptr, nullptr, st);
     return rc;
+}
+
+int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int F, int h,
+                   int n_iters, float* scores, void* ws, size_t ws_bytes, void* stream) {
+    return gnnseg_forward_ex(blob, g, X, F, h, n_iters, scores, ws, ws_bytes, 0, nullptr, stream);
+}
+
+int gnnseg_build_adjacency(const GnnsegGraph* g, int32_t* adj_ptr, int32_t* adj, void* stream) {
+    if (!csr_ok(g) || !adj_ptr) return GNNSEG_EINVAL;
+    if (g->n_slots > 0 && !adj) return GNNSEG_EINVAL;
+    return gnnseg::build_adjacency(g, adj_ptr, adj, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_fused_gather_step(const float* blob, const GnnsegGraph* g, const float* S, int h, float* h1, int ld_h1, void* stream) {
+    if (!fused_width(h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || !graph_ok(g) || !g->adj_ptr || ld_h1 < h || (ld_h1 & 3)) return GNNSEG_EINVAL;
+    if (g->n_nodes > 0 && (!S || !h1)) return GNNSEG_EINVAL;
+    return gnnseg::fused_gather_step(blob, g, S, h, h1, ld_h1, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_edge_final_step(const float* blob, const GnnsegGraph* g, const float* P, int ld, int off_s, int off_d, int h,
+                           float* scores, void* stream) {
+    if (!fused_width(h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || !csr_ok(g) || ld < 2 * h || (ld & 3) || off_s < 0 || off_d < 0 || (off_s & 3) || (off_d & 3) || off_s + h > ld ||
+        off_d + h > ld)
+        return GNNSEG_EINVAL;
+    if (g->n_nodes > 0 && !P) return GNNSEG_EINVAL;
+    if (g->n_slots > 0 && !scores) return GNNSEG_EINVAL;
+    return gnnseg::edge_final_step(blob, g, P, ld, off_s, off_d, h, scores, static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_state_input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* X4, float* out, int mode,
+                            int32_t* status, void* stream) {
+    if (!gnnseg_supported(F, h) || !fused_width(h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || n_nodes < 0 || (mode != 1 && mode != 2) || (n_nodes > 0 && (!X || !X4 || !out))) return GNNSEG_EINVAL;
+    return state_input(blob, X, n_nodes, F, h, X4, gnnseg::ProjOut{out, nullptr, mode, mode == 1 ? 5 * h : 2 * h, status}, mode == 1,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int gnnseg_state_mlp_step(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, int h, float* out,
+                          int mode, int32_t* status, void* stream) {
+    if (!fused_width(h)) return GNNSEG_EUNSUPPORTED;
+    if (!blob || n_nodes < 0 || (mode != 1 && mode != 2) || ld_h1 < h || (ld_h1 & 3)) return GNNSEG_EINVAL;
+    if (n_nodes > 0 && (!X4 || !h1 || !out)) return GNNSEG_EINVAL;
+    return state_mlp(blob, X4, h1, ld_h1, n_nodes, h, gnnseg::ProjOut{out, nullptr, mode, mode == 1 ? 5 * h : 2 * h, status}, mode == 1,
+                     false, static_cast<cudaStream_t>(stream));
 }
 
 int gnnseg_forward_nodes(const float* blob, const float* head_blob, const GnnsegGraph* g, const float* X, int F,

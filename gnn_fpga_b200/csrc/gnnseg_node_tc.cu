@@ -220,6 +220,31 @@ __device__ __forceinline__ int canon_off(const int row, const int k, const int s
     return (row >> 3) * sbo + (k >> 2) * 128 + (row & 7) * 16 + (k & 3) * 4;
 }
 
+// Where the columns of the projection GEMM go (see ProjOut in gnnseg_common.cuh).
+template <int H>
+__device__ __forceinline__ float* proj_ptr(const ProjOut& o, const int node, const int col, int& ld) {
+    if (o.mode == 1) { ld = 5 * H; return o.p + (size_t)node * 5 * H + col; }
+    if (col < 2 * H) { ld = 2 * H; return o.p + (size_t)node * 2 * H + col; }
+    ld = 3 * H;
+    return o.q + (size_t)node * 3 * H + (col - 2 * H);
+}
+template <int H>
+__device__ __forceinline__ bool proj_is_exp(const ProjOut& o, const int col) {
+    return o.mode == 2 || (o.mode == 1 && (col < H || (col >= 2 * H && col < 3 * H)));
+}
+// edge projection -> 2^(log2e v), exponent clamped to [-63, 63] (gnnseg_fused.cu); a clamp raises the flag
+__device__ __forceinline__ void to_exponentials(float (&v)[16], int* __restrict__ flag) {
+    bool clamped = false;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float a = v[i] * 1.4426950408889634f;
+        clamped |= fabsf(a) > 63.f;
+        a = fminf(fmaxf(a, -63.f), 63.f);
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v[i]) : "f"(a));
+    }
+    if (clamped && flag) atomicOr(flag, 1);
+}
+
 // One CSR row of the gather, one float4 chunk of the aligned Q row per lane:
 // acc += w_s * Qcol[nbr_s] for s = beg..end-1 in ascending order.  Slots go in batches of U: all
 // row loads of the batch are issued before the first FMA (no branch in between: an absent slot or
@@ -264,12 +289,11 @@ template <int H>
 __device__ __forceinline__ void tc_store_projections(const uint32_t lane_base, const uint32_t col_d3,
                                                      float* __restrict__ sOut,
                                                      const int node_w0, const int n_nodes, const int lane,
-                                                     float* __restrict__ P_out, float* __restrict__ Q_out,
-                                                     const bool write_q, const int chunk0 = 0,
+                                                     const ProjOut out, const int chunk0 = 0,
                                                      const int chunk_step = 1) {
-    constexpr int NP = 5 * H, OS = TcCfg<H>::OUT_STRIDE;
+    constexpr int OS = TcCfg<H>::OUT_STRIDE;
     const uint64_t stream = l2_policy_evict_first();           // read next by another kernel, not by this one
-    const int c_end = write_q ? NP : 2 * H;
+    const int c_end = out.n_cols;
     // 32-column chunks; two warps that share a TMEM lane quarter take alternate chunks
 #pragma unroll 1
     for (int c0 = 32 * chunk0; c0 < c_end; c0 += 32 * chunk_step) {
@@ -277,14 +301,14 @@ __device__ __forceinline__ void tc_store_projections(const uint32_t lane_base, c
         for (int hb = 0; hb < 2; ++hb) {
             float v[16];
             tmem_ld16(lane_base + col_d3 + c0 + 16 * hb, v);
+            if (proj_is_exp<H>(out, c0)) to_exponentials(v, out.range_flag);
 #pragma unroll
             for (int i = 0; i < 4; ++i)       // the bias is already in D3 (constant-1 column of A x bias row of WP)
                 st4(sOut + lane * OS + 16 * hb + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
         }
         __syncwarp();
-        const bool to_p = c0 < 2 * H;
-        float* base = to_p ? P_out + (size_t)node_w0 * 2 * H + c0 : Q_out + (size_t)node_w0 * 3 * H + (c0 - 2 * H);
-        const int ld = to_p ? 2 * H : 3 * H;
+        int ld;
+        float* base = proj_ptr<H>(out, node_w0, c0, ld);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
@@ -534,7 +558,7 @@ node_kernel_tc(const float* __restrict__ blob, const GnnsegGraph g, const float*
             tc_fence_after();
             // ---- epilogue 3: [P'|Q'] = D3 + bias -> global ------------------------------------
             tc_store_projections<H>(lane_base, C::C_D3, reinterpret_cast<float*>(smem + C::O_OUT + warp * C::OUT_BYTES),
-                                    tile * TM + q * 32, n_nodes, lane, P_out, Q_out, write_q != 0, hf, 2);
+                                    tile * TM + q * 32, n_nodes, lane, ProjOut{P_out, Q_out, 0, write_q ? NP : 2 * H, nullptr}, hf, 2);
             tc_fence_before();
             tc_bar_sync(BAR_EPI, ET);     // TMEM tiles are rewritten by the next tile
         }
@@ -581,11 +605,14 @@ struct TcMlpCfg {
 template <int H, bool TMA>
 __global__ void __launch_bounds__(TcMlpCfg<H>::NT, 2)
 node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4, const float* h1,
-                   const int ld_h1, const int n_nodes, const int n_tiles, float* P_out,
-                   float* __restrict__ Q_out, const int write_q, float* __restrict__ H_save,
+                   const int ld_h1, const int n_nodes, const int n_tiles, const ProjOut out, const int wp_off,
+                   float* __restrict__ H_save,
                    const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
                    const __grid_constant__ CUtensorMap tmQ16) {
-    // h1 may alias P_out (row n of h1 inside row n of P'): no __restrict__, no read-only loads on those two
+    // h1 may alias the output rows (row n of h1 inside row n of P' / the state row): no __restrict__, no read-only loads on those
+    float* const P_out = out.p;
+    float* const Q_out = out.q;
+    const int write_q = out.n_cols > 2 * H;
     using C = TcMlpCfg<H>;
     using N = TcCfg<H>;
     using B = Blob<H>;
@@ -603,8 +630,10 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
 
     static_assert(C::O_W4L == C::O_W4H + H * H * 4 && C::O_WPH == C::O_W4L + H * H * 4 &&
                   C::O_WPL == C::O_WPH + NP * N::D4P * 4, "image order");
-    for (int i = tid * 4; i < 2 * H * H + 2 * NP * N::D4P; i += NT * 4)
+    for (int i = tid * 4; i < 2 * H * H; i += NT * 4)                     // W4 hi, lo
         cp_async16(smem + C::O_W4H + i * 4, blob + B::TC_W4H + i);
+    for (int i = tid * 4; i < 2 * NP * N::D4P; i += NT * 4)               // projection images hi, lo (either row order)
+        cp_async16(smem + C::O_WPH + i * 4, blob + wp_off + i);
     for (int i = tid; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
     if (tid == 0) {
         mbar_init(smem_u32(mbar), 1);
@@ -763,17 +792,18 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
                 auto stage16 = [&](const int col, const int jb) {          // 16 columns of D3 -> chunks jb..jb+3 of the tile
                     float v[16];
                     tmem_ld16(lane_base + C::C_D3 + col, v);
+                    if (proj_is_exp<H>(out, col)) to_exponentials(v, out.range_flag);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)       // the bias is already in D3 (constant-1 column of A x bias row of WP)
                         st4(sOut + lane * 32 + (((jb + i) ^ (lane & 7)) << 2),
                             make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
                 };
-                auto out_ptr = [&](const int col, int& ld) {               // column `col` of [P'|Q'] for the warp's first node
-                    const bool to_p = col < 2 * H;
-                    ld = to_p ? 2 * H : 3 * H;
-                    return to_p ? P_out + (size_t)node_w0 * 2 * H + col : Q_out + (size_t)node_w0 * 3 * H + (col - 2 * H);
+                auto out_ptr = [&](const int col, int& ld) {               // column `col` of the projections for the warp's first node
+                    return proj_ptr<H>(out, node_w0, col, ld);
                 };
                 const int n_full = write_q ? 2 : 1;                          // 32-column chunks hf, hf + 2 (P' only: chunk hf)
+                // state rows [SPs|Qi|SPd|Qo|Qs]: the two chunks of exponentials (0 and 2) go to different warps
+                auto chunk_of = [&](const int t) { return out.mode == 1 ? (t == 0 ? 2 * hf : 3 - 2 * hf) : hf + 2 * t; };
                 if constexpr (TMA) {
                     const uint32_t s_tile = smem_u32(sOut);
 #pragma unroll 1
@@ -814,7 +844,7 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
                 } else {
 #pragma unroll 1
                     for (int t = 0; t < n_full; ++t) {
-                        const int c0 = 32 * (hf + 2 * t);
+                        const int c0 = 32 * chunk_of(t);
                         stage16(c0, 0);
                         stage16(c0 + 16, 4);
                         __syncwarp();
@@ -895,10 +925,13 @@ struct Mlp64 {
 template <bool INPUT>
 __global__ void __launch_bounds__(Mlp64::NT, 1)
 node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, const float* h1, const int ld_h1,
-                     const int n_nodes, const int n_tiles, float* P_out, float* __restrict__ Q_out, const int write_q,
+                     const int n_nodes, const int n_tiles, const ProjOut out, const int wp_off,
                      float* __restrict__ H_save, const float* __restrict__ Xraw, const int F) {
     using C = Mlp64;
     using B = Blob<64>;
+    // with n_cols <= 160 only the first half of the projection image is needed (P' alone, or [SPs|SPd]): it
+    // stays in shared memory for the whole launch
+    const int write_q = out.n_cols > C::NH;
     constexpr int H = C::H, TM = C::TM, NT = C::NT, ET = C::ET, LT = C::LT;
     constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_EPI = 3, BAR_WPF_A = 4, BAR_WPF_B = 5, BAR_WPE_A = 6, BAR_WPE_B = 7;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -940,8 +973,8 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, con
         auto load_wp_half = [&](const int hf, const int bar) {
             constexpr int HALF_FLOATS = C::WPH_BYTES / 4, IMG_FLOATS = C::NP * C::D4P;
             for (int i = lt * 4; i < HALF_FLOATS; i += LT * 4) {
-                cp_async16(smem + C::O_WP + i * 4, blob + B::TC_WPH + hf * HALF_FLOATS + i);
-                cp_async16(smem + C::O_WP + C::WPH_BYTES + i * 4, blob + B::TC_WPH + IMG_FLOATS + hf * HALF_FLOATS + i);
+                cp_async16(smem + C::O_WP + i * 4, blob + wp_off + hf * HALF_FLOATS + i);
+                cp_async16(smem + C::O_WP + C::WPH_BYTES + i * 4, blob + wp_off + IMG_FLOATS + hf * HALF_FLOATS + i);
             }
             cp_async_wait_all();
             fence_async_smem();
@@ -1001,15 +1034,15 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, con
             for (int hb = 0; hb < 2; ++hb) {
                 float v[16];
                 tmem_ld16(lane_base + C::C_D3 + c0 + 16 * hb, v);
+                if (proj_is_exp<H>(out, c0)) to_exponentials(v, out.range_flag);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)           // the bias is already in D3
                     st4(sOut + lane * 32 + (((4 * hb + i) ^ (lane & 7)) << 2),
                         make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
             }
             __syncwarp();
-            const bool to_p = c0 < 2 * H;
-            float* base = to_p ? P_out + (size_t)node_w0 * 2 * H + c0 : Q_out + (size_t)node_w0 * 3 * H + (c0 - 2 * H);
-            const int ld = to_p ? 2 * H : 3 * H;
+            int ld;
+            float* base = proj_ptr<H>(out, node_w0, c0, ld);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = 4 * i + (lane >> 3), j = lane & 7;
@@ -1116,8 +1149,8 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, con
             mbar_wait(mb, phase); phase ^= 1;
             tc_fence_after();
             if (write_q) tc_bar_arrive(BAR_WPE_A, ET + LT);    // the loader may stream half 1 in
-            // epilogue 3a (chunks 0..4; the last one is Q' and only needed when Q' is)
-            for (int ch = hf; ch < (write_q ? 5 : 4); ch += 2) store_chunk(32 * ch, node_w0);
+            // epilogue 3a (chunks 0..4 of 32 columns; as many as the caller wants stored)
+            for (int ch = hf; ch < 5 && 32 * ch < out.n_cols; ch += 2) store_chunk(32 * ch, node_w0);
             if (write_q) {
                 // ---- GEMM3b: outputs 160..319 ------------------------------------------------
                 tc_bar_sync(BAR_WPF_B, ET + LT);
@@ -1161,7 +1194,7 @@ struct TcInCfg {
 template <int H>
 __global__ void __launch_bounds__(TcInCfg<H>::NT)
 input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, const int F, const int n_nodes,
-                const int n_tiles, float* __restrict__ X4, float* __restrict__ P_out, float* __restrict__ Q_out,
+                const int n_tiles, float* __restrict__ X4, const ProjOut out, const int wp_off,
                 float* __restrict__ H_save) {
     using C = TcInCfg<H>;
     using N = TcCfg<H>;
@@ -1173,8 +1206,8 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid * 4; i < 2 * NP * N::D4P; i += NT * 4)      // WP hi, WP lo: contiguous images
-        cp_async16(smem + C::O_WPH + i * 4, blob + B::TC_WPH + i);
+    for (int i = tid * 4; i < 2 * NP * N::D4P; i += NT * 4)      // WP hi, WP lo: contiguous images (either row order)
+        cp_async16(smem + C::O_WPH + i * 4, blob + wp_off + i);
     for (int i = tid; i < 5 * H; i += NT) sWin[i] = __ldg(blob + B::WIN + i);      // Win and bin are contiguous
     if (tid == 0) {
         mbar_init(smem_u32(mbar), 1);
@@ -1255,7 +1288,7 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
         mbar_wait(mb, phase); phase ^= 1;
         tc_fence_after();
         tc_store_projections<H>(lane_base, C::C_D3, reinterpret_cast<float*>(smem + C::O_OUT + warp * N::OUT_BYTES),
-                                tile * TM + q * 32, n_nodes, lane, P_out, Q_out, true, hf, 2);
+                                tile * TM + q * 32, n_nodes, lane, out, hf, 2);
         tc_fence_before();
         __syncthreads();       // A3 / D3 are rewritten by the next tile
     }
@@ -1267,8 +1300,14 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
     }
 }
 
+int launch_input_tc32_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, bool state_order,
+                         float* H_save, cudaStream_t st);
 int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
                       float* H_save, cudaStream_t st) {
+    return launch_input_tc32_ex(blob, X, n_nodes, F, X4, ProjOut{P, Q, 0, 160, nullptr}, false, H_save, st);
+}
+int launch_input_tc32_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, bool state_order,
+                         float* H_save, cudaStream_t st) {
     using C = TcInCfg<32>;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + TcCfg<32>::TM - 1) / TcCfg<32>::TM;
@@ -1277,7 +1316,8 @@ int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, flo
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int cap = 2 * sms;     // 256 TMEM columns and ~95 KB of shared memory per CTA: two CTAs per SM
     const int grid = n_tiles < cap ? n_tiles : cap;
-    input_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, P, Q, H_save);
+    input_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, out,
+                                                            state_order ? Blob<32>::TC_WSH : Blob<32>::TC_WPH, H_save);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
@@ -1309,33 +1349,43 @@ static bool make_store_map(CUtensorMap* tm, float* base, int rows, int cols, int
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int launch_node_mlp_tc32(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
-                         float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st) {
+// `out` says where the projections go; state_order picks the projection image whose rows are in state-row order
+int launch_node_mlp_tc32_ex(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, const ProjOut& out,
+                            bool state_order, float* H_save, bool pdl, cudaStream_t st) {
     using C = TcMlpCfg<32>;
+    using B = Blob<32>;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
     constexpr int SMEM = C::SMEM_BYTES + 1024;                      // room to align the store tiles to 1024 bytes
     const int sms = cached_sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;        // two CTAs per SM
-    static const bool tma = [] { const char* v = std::getenv("GNNSEG_MLP_STORE"); return v && v[0] == 't'; }();
+    const int wp_off = state_order ? B::TC_WSH : B::TC_WPH;
+    static const bool tma_env = [] { const char* v = std::getenv("GNNSEG_MLP_STORE"); return v && v[0] == 't'; }();
+    const bool tma = tma_env && out.mode == 0;
     CUtensorMap tmP, tmQ, tmQ16;
     memset(&tmP, 0, sizeof(tmP)); memset(&tmQ, 0, sizeof(tmQ)); memset(&tmQ16, 0, sizeof(tmQ16));
     if (tma) {
-        if (!make_store_map(&tmP, P_out, n_nodes, 64, 32, true)) return GNNSEG_ECUDA;
-        if (write_q && (!make_store_map(&tmQ, Q_out, n_nodes, 96, 32, true) || !make_store_map(&tmQ16, Q_out, n_nodes, 96, 16, false)))
+        const bool write_q = out.n_cols > 64;
+        if (!make_store_map(&tmP, out.p, n_nodes, 64, 32, true)) return GNNSEG_ECUDA;
+        if (write_q && (!make_store_map(&tmQ, out.q, n_nodes, 96, 32, true) || !make_store_map(&tmQ16, out.q, n_nodes, 96, 16, false)))
             return GNNSEG_ECUDA;
         if (!ensure_dynamic_smem<node_mlp_kernel_tc<32, true>>(SMEM)) return GNNSEG_ECUDA;
-        if (launch_pdl(node_mlp_kernel_tc<32, true>, grid, C::NT, SMEM, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, P_out,
-                       Q_out, write_q, H_save, tmP, tmQ, tmQ16) != cudaSuccess)
+        if (launch_pdl(node_mlp_kernel_tc<32, true>, grid, C::NT, SMEM, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, out, wp_off,
+                       H_save, tmP, tmQ, tmQ16) != cudaSuccess)
             return GNNSEG_ECUDA;
         return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
     }
     if (!ensure_dynamic_smem<node_mlp_kernel_tc<32, false>>(SMEM)) return GNNSEG_ECUDA;
-    if (launch_pdl(node_mlp_kernel_tc<32, false>, grid, C::NT, SMEM, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, P_out,
-                   Q_out, write_q, H_save, tmP, tmQ, tmQ16) != cudaSuccess)
+    if (launch_pdl(node_mlp_kernel_tc<32, false>, grid, C::NT, SMEM, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, out, wp_off,
+                   H_save, tmP, tmQ, tmQ16) != cudaSuccess)
         return GNNSEG_ECUDA;
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+}
+int launch_node_mlp_tc32(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
+                         float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st) {
+    return launch_node_mlp_tc32_ex(blob, X4, h1, ld_h1, n_nodes, ProjOut{P_out, Q_out, 0, write_q ? 160 : 64, nullptr}, false, H_save,
+                                   pdl, st);
 }
 
 #ifdef GNNSEG_TRACE
@@ -1347,8 +1397,8 @@ extern "C" int gnnseg_debug_read_cta(unsigned long long* out) {
 }
 #endif
 
-int launch_node_mlp_tc64(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
-                         float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st) {
+int launch_node_mlp_tc64_ex(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, const ProjOut& out,
+                            bool state_order, float* H_save, bool pdl, cudaStream_t st) {
     using C = Mlp64;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
@@ -1356,14 +1406,26 @@ int launch_node_mlp_tc64(const float* blob, const float* X4, const float* h1, in
     const int sms = cached_sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int grid = n_tiles < sms ? n_tiles : sms;
+    const int wp_off = state_order ? Blob<64>::TC_WSH : Blob<64>::TC_WPH;
     if (launch_pdl(node_mlp_kernel_tc64<false>, grid, C::NT, C::SMEM_BYTES, st, pdl, blob, const_cast<float*>(X4), h1, ld_h1, n_nodes,
-                   n_tiles, P_out, Q_out, write_q, H_save, (const float*)nullptr, 0) != cudaSuccess)
+                   n_tiles, out, wp_off, H_save, (const float*)nullptr, 0) != cudaSuccess)
         return GNNSEG_ECUDA;
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
+int launch_node_mlp_tc64(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
+                         float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st) {
+    return launch_node_mlp_tc64_ex(blob, X4, h1, ld_h1, n_nodes, ProjOut{P_out, Q_out, 0, write_q ? 320 : 128, nullptr}, false, H_save,
+                                   pdl, st);
+}
 
+int launch_input_tc64_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, bool state_order,
+                         float* H_save, cudaStream_t st);
 int launch_input_tc64(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q, float* H_save,
                       cudaStream_t st) {
+    return launch_input_tc64_ex(blob, X, n_nodes, F, X4, ProjOut{P, Q, 0, 320, nullptr}, false, H_save, st);
+}
+int launch_input_tc64_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, bool state_order,
+                         float* H_save, cudaStream_t st) {
     using C = Mlp64;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
@@ -1372,7 +1434,8 @@ int launch_input_tc64(const float* blob, const float* X, int n_nodes, int F, flo
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int grid = n_tiles < sms ? n_tiles : sms;
     // the first kernel of a forward: launched fully serialised (it reads the blob the pack kernels wrote)
-    node_mlp_kernel_tc64<true><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X4, nullptr, 0, n_nodes, n_tiles, P, Q, 1, H_save, X, F);
+    node_mlp_kernel_tc64<true><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X4, nullptr, 0, n_nodes, n_tiles, out,
+                                                                   state_order ? Blob<64>::TC_WSH : Blob<64>::TC_WPH, H_save, X, F);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 

@@ -172,7 +172,8 @@ class DeviceGraphBatch:
             self._build_csr()
             self.scores = torch.empty(self.n_slots, dtype=torch.float32, device=dev)
         else:                          # arrays assembled elsewhere (from_store): no CSR build here
-            for k in ("in_ptr", "in_eid", "in_nbr", "in_pos", "out_ptr", "out_eid", "out_nbr", "out_pos", "scores"):
+            for k in ("in_ptr", "in_eid", "in_nbr", "in_pos", "out_ptr", "out_eid", "out_nbr", "out_pos", "scores", "adj_ptr", "adj",
+                      "status"):
                 setattr(self, k, _prebuilt[k])
             self._ws = _prebuilt.get("ws", self._ws)
             self._set_struct()
@@ -198,11 +199,22 @@ class DeviceGraphBatch:
         self._set_struct()
 
     def _set_struct(self):
+        """GnnsegGraph over the arrays; builds the combined adjacency list of the fused inference path
+        (gnnseg_build_adjacency: one launch on the current stream) if the arrays for it are there."""
+        dev = self.device
+        if getattr(self, "adj_ptr", None) is None:
+            self.adj_ptr = torch.empty(self.n_nodes + 1, dtype=torch.int32, device=dev)
+            self.adj = torch.empty(max(2 * self.n_slots, 1), dtype=torch.int32, device=dev)
+        if getattr(self, "status", None) is None:
+            self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         self.struct = _lib.GnnsegGraph(
             self.n_nodes, self.n_slots, self.src.data_ptr(), self.dst.data_ptr(),
             self.in_ptr.data_ptr(), self.in_eid.data_ptr(), self.in_nbr.data_ptr(),
             self.out_ptr.data_ptr(), self.out_eid.data_ptr(), self.out_nbr.data_ptr(),
-            self.in_pos.data_ptr(), self.out_pos.data_ptr())
+            self.in_pos.data_ptr(), self.out_pos.data_ptr(), self.adj_ptr.data_ptr(), self.adj.data_ptr())
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().gnnseg_build_adjacency(C.byref(self.struct), _ptr(self.adj_ptr), _ptr(self.adj), _stream_ptr(dev)),
+                       "gnnseg_build_adjacency")
 
     @classmethod
     def from_dense(cls, X, Ri, Ro, validate=True):
@@ -381,6 +393,8 @@ class DeviceBatchBuffers:
             "in_eid": torch.empty(max(n_in, 1), **i32), "in_nbr": torch.empty(max(n_in, 1), **i32),
             "out_eid": torch.empty(max(n_out, 1), **i32), "out_nbr": torch.empty(max(n_out, 1), **i32),
             "scores": torch.empty(max(n_slots, 1), dtype=torch.float32, device=dev),
+            "adj_ptr": torch.empty(n_nodes + 1, **i32), "adj": torch.empty(max(n_in + n_out, 1), **i32),
+            "status": torch.zeros(1, **i32),
         }
         self.ws = {}            # forward workspaces by hidden_dim, shared by the batches that pass through
 
@@ -396,7 +410,7 @@ class DeviceBatchBuffers:
                 "src": t["src"][:n_slots], "dst": t["dst"][:n_slots], "in_pos": t["in_pos"][:n_slots], "out_pos": t["out_pos"][:n_slots],
                 "in_ptr": t["in_ptr"][:n_nodes + 1], "out_ptr": t["out_ptr"][:n_nodes + 1], "in_eid": t["in_eid"][:n_in],
                 "in_nbr": t["in_nbr"][:n_in], "out_eid": t["out_eid"][:n_out], "out_nbr": t["out_nbr"][:n_out],
-                "scores": t["scores"][:n_slots]}
+                "scores": t["scores"][:n_slots], "adj_ptr": t["adj_ptr"][:n_nodes + 1], "adj": t["adj"], "status": t["status"]}
 
 
 def pack_npz_batch_host(filenames, pinned=None, n_threads=0):

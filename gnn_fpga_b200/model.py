@@ -123,6 +123,8 @@ class SegmentClassifier(nn.Module):
         self.edge_network = EdgeNetwork(input_dim + hidden_dim, hidden_dim, hidden_activation, masks_e)
         self.node_network = NodeNetwork(input_dim + hidden_dim, hidden_dim, hidden_activation, masks_n)
         self._blob = None
+        self.exact = False           # True: always the step-by-step kernels (GNNSEG_FWD_EXACT), see check_range
+        self._range_checks = []      # (event, pinned status word) of forwards whose range flag has not been looked at
         self.use_cuda_graph = True
         self._arena = None           # reusable pinned arena for batches given as host SparseGraph tuples
 
@@ -183,10 +185,12 @@ class SegmentClassifier(nn.Module):
         h = self.hidden_dim
         ws = batch.workspace(h)
 
+        flags = _lib.FWD_EXACT if self.exact else 0
+
         def launch():
-            _lib.check(L.gnnseg_forward(_ptr(blob), C.byref(batch.struct), _ptr(batch.X), batch.F, h,
-                                        self.n_iters, _ptr(batch.scores), _ptr(ws), ws.numel(),
-                                        _stream_ptr(dev)), "gnnseg_forward")
+            _lib.check(L.gnnseg_forward_ex(_ptr(blob), C.byref(batch.struct), _ptr(batch.X), batch.F, h,
+                                           self.n_iters, _ptr(batch.scores), _ptr(ws), ws.numel(), flags,
+                                           _ptr(batch.status), _stream_ptr(dev)), "gnnseg_forward_ex")
 
         with torch.cuda.device(dev):
             if not self.use_cuda_graph:
@@ -255,6 +259,11 @@ class SegmentClassifier(nn.Module):
             slot["arena"] = st.arena
             return StoreBatch(st, 0, len(st))
 
+        def range_ok(slot):
+            if int(slot["flag"][0]) & _lib.RANGE_CLAMPED:
+                raise _lib.GnnsegError("an edge-network projection exceeded the fused path's range (|W1.[H|X] + b1| > 43.6); "
+                                       "set model.exact = True and rerun")
+
         pool = ThreadPoolExecutor(max_workers=1)
         compute = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -285,6 +294,7 @@ class SegmentClassifier(nn.Module):
                     if len(pending) == depth:                     # keep `depth` results in flight
                         old = pending.popleft()
                         old["done"].synchronize()
+                        range_ok(old)
                         yield old["view"]
                     if s["done"] is not None:
                         s["done"].synchronize()                   # the slot's previous batch has left the device buffers
@@ -305,8 +315,11 @@ class SegmentClassifier(nn.Module):
                     ev_c = torch.cuda.Event()
                     ev_c.record(compute)
                     s_out.wait_event(ev_c)
+                    if s.get("flag") is None:
+                        s["flag"] = torch.zeros(1, dtype=torch.int32, pin_memory=True)
                     with torch.cuda.stream(s_out):
                         s["view"].copy_(scores.view(batch.B, batch.e_max), non_blocking=True)
+                        s["flag"].copy_(batch.status, non_blocking=True)
                         s["done"] = torch.cuda.Event()
                         s["done"].record(s_out)
                     pending.append(s)
@@ -314,10 +327,39 @@ class SegmentClassifier(nn.Module):
                 while pending:
                     old = pending.popleft()
                     old["done"].synchronize()
+                    range_ok(old)
                     yield old["view"]
         finally:
             pool.shutdown(wait=True)
             self.use_cuda_graph = was_graph
+
+    def _watch_range(self, batch):
+        """Queue an asynchronous read of the batch's range flag (gnnseg_forward_ex's status word)."""
+        host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        host.copy_(batch.status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(batch.device))
+        self._range_checks.append((ev, host))
+
+    def check_range(self, wait=True):
+        """The fused inference path (hidden_dim 32 / 64) keeps the edge network's first-layer projections as
+        exponentials and represents |projection| <= 43.6; a forward that had to clamp one raises its flag.
+        Raises GnnsegError if a finished forward (wait=True: any forward issued so far) was flagged; the
+        cure is `model.exact = True` (the step-by-step kernels).  predict_stream checks every batch it
+        yields; `model(inputs)` checks the calls before it."""
+        left = []
+        bad = False
+        for ev, host in self._range_checks:
+            if wait:
+                ev.synchronize()
+            if ev.query():
+                bad |= bool(int(host[0]) & _lib.RANGE_CLAMPED)
+            else:
+                left.append((ev, host))
+        self._range_checks = left
+        if bad:
+            raise _lib.GnnsegError("an edge-network projection exceeded the fused path's range (|W1.[H|X] + b1| > 43.6): "
+                                   "the scores of that forward may be off; set model.exact = True and rerun")
 
     def _wants_grad(self):
         # training mode + autograd on + trainable parameters: what Estimator.fit_gen / training_step
@@ -365,6 +407,9 @@ class SegmentClassifier(nn.Module):
                 _lib.check(-2, "SegmentClassifier(input_dim=%d, hidden_dim=%d)" % (self.input_dim, self.hidden_dim))
             return differentiable_forward(self, self._to_batch(inputs))
         resident = isinstance(inputs, DeviceGraphBatch)
+        self.check_range(wait=False)
         batch = self._to_batch(inputs)
         out = self._run(batch).view(batch.B, batch.e_max)
+        if not self.exact and self.hidden_dim in (32, 64):
+            self._watch_range(batch)
         return out.clone() if resident else out        # one-shot batches own their buffer: nothing else writes it

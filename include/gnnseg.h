@@ -88,6 +88,11 @@ typedef struct GnnsegGraph {
     const int32_t* out_nbr;  /* [out_ptr[n_nodes]] dst[out_eid]                      */
     const int32_t* in_pos;   /* [n_slots] position of the slot in in_eid  (in_eid[in_pos[j]] == j), -1 if dst[j] < 0  */
     const int32_t* out_pos;  /* [n_slots] position of the slot in out_eid, -1 if src[j] < 0 */
+    /* combined adjacency of the fused inference path (gnnseg_build_adjacency); both NULL: the forward runs
+     * the edge step and the node step as separate kernels */
+    const int32_t* adj_ptr;  /* [n_nodes+1] = in_ptr + out_ptr                                               */
+    const int32_t* adj;      /* [adj_ptr[n_nodes]] per node: in-edges (start node id), then out-edges (end
+                                node id | 0x80000000), ascending slot order; 0x7fffffff = absent neighbour  */
 } GnnsegGraph;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -139,6 +144,13 @@ int    gnnseg_build_graph(const int32_t* src, const int32_t* dst, int n_slots, i
                           int32_t* out_ptr, int32_t* out_eid, int32_t* out_nbr, int32_t* out_pos,
                           void* ws, size_t ws_bytes, void* stream);
 
+/*
+ * The combined adjacency list the fused inference path walks: per node its in-edges then its out-edges
+ * (see GnnsegGraph.adj).  adj_ptr[n_nodes+1], adj[in_ptr[n_nodes] + out_ptr[n_nodes]] (<= 2 * n_slots).
+ * One launch, reads the two CSRs of `graph` (its adj_ptr / adj members are ignored).
+ */
+int    gnnseg_build_adjacency(const GnnsegGraph* graph, int32_t* adj_ptr, int32_t* adj, void* stream);
+
 /* ---- forward: replaces SegmentClassifier.forward, gnn/model.py:140-156 ---------------- */
 
 size_t gnnseg_forward_workspace_bytes(int n_nodes, int n_slots, int F, int h);
@@ -151,6 +163,20 @@ size_t gnnseg_forward_workspace_bytes(int n_nodes, int n_slots, int F, int h);
 int gnnseg_forward(const float* blob, const GnnsegGraph* graph, const float* X,
                    int F, int h, int n_iters, float* scores,
                    void* ws, size_t ws_bytes, void* stream);
+/*
+ * The same with two more arguments.  hidden_dim 32 / 64 and a graph with an adjacency list run the FUSED
+ * inference path (2*n_iters+2 launches: the edge step is evaluated inside the node step's CSR walk, once from
+ * each end of an edge, on exponentials 2^(log2e P) of the edge projections that the producing kernel takes
+ * once per node; nothing is written per edge between the iterations).  That path represents |P| <= 43.6;
+ * beyond, the exponent is clamped and *status (device word, nullable) gets GNNSEG_RANGE_CLAMPED: the scores
+ * of that call may then be off and the caller reruns with GNNSEG_FWD_EXACT, which forces the step-by-step
+ * kernels (as does the environment variable GNNSEG_EXACT=1).  *status is zeroed at the start of the call.
+ */
+#define GNNSEG_FWD_EXACT      1
+#define GNNSEG_RANGE_CLAMPED  1
+int gnnseg_forward_ex(const float* blob, const GnnsegGraph* graph, const float* X,
+                      int F, int h, int n_iters, float* scores,
+                      void* ws, size_t ws_bytes, int flags, int32_t* status, void* stream);
 
 /*
  * The three steps on their own (used by the per-kernel parity tests).  State arrays, with
@@ -193,6 +219,27 @@ int gnnseg_node_gather_step(const GnnsegGraph* graph, const float* Q_in, const f
                             const float* e_out, int h, float* h1, int ld_h1, void* stream);
 int gnnseg_node_mlp_step(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes,
                          int h, float* P_out, float* Q_out, void* stream);
+
+/*
+ * The steps of the fused inference path on their own (per-kernel parity tests, per-kernel timing).
+ * State rows S (n_nodes, 5h) = [SPs | Qi | SPd | Qo | Qs] with SPs = 2^(log2e Ps), SPd = 2^(log2e Pd);
+ * "last" rows P (n_nodes, 2h) = [SPs | SPd] (what the final edge step reads).  hidden_dim 32 or 64.
+ *   gnnseg_state_input_step : gnnseg_input_step writing state rows (mode 1) or last rows (mode 2)
+ *   gnnseg_fused_gather_step: h1[n] = tanh(Qs[n] + sum_in e Qi[src] + sum_out e Qo[dst]) with the edge scores e
+ *                             computed on the fly from SPs / SPd (gnn/model.py:69-81 inside :113-122)
+ *   gnnseg_state_mlp_step   : gnnseg_node_mlp_step writing state rows (mode 1) or last rows (mode 2); h1 may
+ *                             live in the first h floats of the rows it becomes (ld_h1 = 5h or 2h)
+ *   gnnseg_edge_final_step  : scores per slot from rows of `ld` floats holding SPs at column off_s and SPd at
+ *                             column off_d (walks the destination-CSR, then the slots without an end node)
+ */
+int gnnseg_state_input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* X4,
+                            float* out, int mode, int32_t* status, void* stream);
+int gnnseg_fused_gather_step(const float* blob, const GnnsegGraph* graph, const float* S, int h,
+                             float* h1, int ld_h1, void* stream);
+int gnnseg_state_mlp_step(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes,
+                          int h, float* out, int mode, int32_t* status, void* stream);
+int gnnseg_edge_final_step(const float* blob, const GnnsegGraph* graph, const float* P, int ld,
+                           int off_s, int off_d, int h, float* scores, void* stream);
 
 /* ---- training: replaces loss.backward() / optimizer.step() of Estimator.training_step,
  *      gnn/estimator.py:49-60 ------------------------------------------------------------- */

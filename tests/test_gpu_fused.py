@@ -1,0 +1,179 @@
+"""The fused inference path (gnnseg_fused.cu, hidden_dim 32 / 64), one kernel at a time against the oracle,
+then the whole forward against the step-by-step kernels and the reference goldens.
+
+State rows S (n, 5h) = [SPs | Qi | SPd | Qo | Qs], SPs = exp(Ps) (= 2^(log2e Ps)), SPd = exp(Pd); last rows
+P (n, 2h) = [SPs | SPd] (include/gnnseg.h).  Reference: gnn/model.py:69-81 (edge), :113-125 (node), :140-156.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_case, rel_err
+from oracle import segclf_oracle as O
+from test_gpu_parity import _steps_setup, make_model, sparse_graphs_of
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+CASES = ["acts_ragged_h32_it4", "acts_h64_it6", "acts_masked_h32_it4"]
+
+
+def state_rows(P, Q, h):
+    """Oracle projections -> state rows, exponentials taken in fp64."""
+    sp = torch.exp(P.double()).float()
+    return torch.cat([sp[:, :h], Q[:, :h], sp[:, h:], Q[:, h:2 * h], Q[:, 2 * h:]], dim=1).contiguous()
+
+
+def h1_oracle(p, H0, e, src, dst):
+    """tanh(W3.[mi; mo; H] + b3): the first layer of the node network (gnn/model.py:114-122)."""
+    real_i, real_o = dst >= 0, src >= 0
+    mi = torch.zeros_like(H0).index_add_(0, dst[real_i], (e[:, None] * O._gather(H0, src))[real_i])
+    mo = torch.zeros_like(H0).index_add_(0, src[real_o], (e[:, None] * O._gather(H0, dst))[real_o])
+    return torch.tanh(O._lin(torch.cat([mi, mo, H0], dim=1), p, 3))
+
+
+@pytest.mark.parametrize("name", CASES + ["half_edges_h8_it2"])
+def test_fused_steps_against_oracle(name, cuda_device):
+    from gnn_fpga_b200.graph import _ptr, _stream_ptr
+    rec = load_case(name)
+    model, batch, L = _steps_setup(rec, cuda_device)
+    p = O.apply_masks(rec["params"], rec["masks_e"], rec["masks_n"])
+    h, F, n = rec["h"], rec["F"], batch.n_nodes
+    blob = model.pack_weights()
+    st = _stream_ptr(cuda_device)
+    src, dst, Xh = batch.src.cpu().long(), batch.dst.cpu().long(), batch.X.cpu()
+    status = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    X4 = torch.full((n, 4), 7.0, device=cuda_device)
+    S = torch.zeros(n, 5 * h, device=cuda_device)
+    rc = L.gnnseg_state_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(X4), _ptr(S), 1, _ptr(status), st)
+    if h not in (32, 64):
+        assert rc == -2 and L.gnnseg_fused_gather_step(_ptr(blob), C.byref(batch.struct), _ptr(S), h, _ptr(S), 5 * h, st) == -2
+        return
+    assert rc == 0
+    # ---- input step: state rows of [H0 | X]
+    H0 = O.sparse_input(p, Xh)
+    Pref, Qref = O.projections(p, H0)
+    Sref = state_rows(Pref, Qref, h)
+    assert torch.equal(X4.cpu()[:, :F], Xh) and torch.all(X4.cpu()[:, F:] == 0)
+    assert torch.allclose(S.cpu(), Sref, rtol=1e-5, atol=3e-6)
+    P2 = torch.zeros(n, 2 * h, device=cuda_device)
+    assert L.gnnseg_state_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(X4), _ptr(P2), 2, _ptr(status), st) == 0
+    assert torch.allclose(P2.cpu(), torch.exp(Pref.double()).float(), rtol=1e-5, atol=3e-6)
+    # ---- fused edge + gather on the oracle's state rows: h1, in its own buffer and inside wider rows
+    e_ref = O.sparse_edge(p, H0, src, dst)
+    h1_ref = h1_oracle(p, H0, e_ref, src, dst)
+    Sd = Sref.to(cuda_device)
+    for ld in (h, 5 * h):
+        h1 = torch.full((n, ld), 9.0, device=cuda_device)
+        assert L.gnnseg_fused_gather_step(_ptr(blob), C.byref(batch.struct), _ptr(Sd), h, _ptr(h1), ld, st) == 0
+        assert torch.allclose(h1.cpu()[:, :h], h1_ref, rtol=1e-5, atol=3e-6)
+        assert torch.all(h1[:, h:] == 9.0)
+    # ---- tensor-core MLP writing state rows (mode 1) and last rows (mode 2); h1 inside the rows it becomes
+    H1 = torch.cat([torch.tanh(O._lin(h1_ref, p, 4)), Xh], dim=1)
+    P1ref, Q1ref = O.projections(p, H1)
+    S1ref = state_rows(P1ref, Q1ref, h)
+    h1d = h1_ref.to(cuda_device).contiguous()
+    S1 = torch.zeros(n, 5 * h, device=cuda_device)
+    assert L.gnnseg_state_mlp_step(_ptr(blob), _ptr(X4), _ptr(h1d), h, n, h, _ptr(S1), 1, _ptr(status), st) == 0
+    assert torch.allclose(S1.cpu(), S1ref, rtol=1e-5, atol=4e-6)
+    S1b = torch.zeros(n, 5 * h, device=cuda_device)
+    S1b[:, :h] = h1d
+    assert L.gnnseg_state_mlp_step(_ptr(blob), _ptr(X4), _ptr(S1b), 5 * h, n, h, _ptr(S1b), 1, _ptr(status), st) == 0
+    assert torch.equal(S1b, S1)
+    Pl = torch.zeros(n, 2 * h, device=cuda_device)
+    Pl[:, :h] = h1d
+    assert L.gnnseg_state_mlp_step(_ptr(blob), _ptr(X4), _ptr(Pl), 2 * h, n, h, _ptr(Pl), 2, _ptr(status), st) == 0
+    assert torch.allclose(Pl.cpu(), torch.exp(P1ref.double()).float(), rtol=1e-5, atol=4e-6)
+    # ---- final edge step from last rows and from state rows (same numbers, other strides)
+    e1_ref = O.sparse_edge(p, H1, src, dst)
+    Pd = torch.exp(P1ref.double()).float().to(cuda_device).contiguous()
+    sc = torch.full((batch.n_slots,), -1.0, device=cuda_device)
+    assert L.gnnseg_edge_final_step(_ptr(blob), C.byref(batch.struct), _ptr(Pd), 2 * h, 0, h, h, _ptr(sc), st) == 0
+    assert rel_err(sc.cpu().numpy(), e1_ref.numpy()) <= TOL
+    sc2 = torch.full((batch.n_slots,), -1.0, device=cuda_device)
+    S1d = S1ref.to(cuda_device)
+    assert L.gnnseg_edge_final_step(_ptr(blob), C.byref(batch.struct), _ptr(S1d), 5 * h, 0, 2 * h, h, _ptr(sc2), st) == 0
+    assert torch.equal(sc2, sc)
+    assert int(status.item()) == 0
+
+
+def test_adjacency_is_in_edges_then_out_edges(cuda_device):
+    """gnnseg_build_adjacency: adj_ptr = in_ptr + out_ptr; per node the start nodes of its in-edges, then the end
+    nodes of its out-edges with bit 31 set, in ascending slot order; absent neighbours are 0x7fffffff."""
+    rec = load_case("half_edges_h8_it2")
+    _, batch, _ = _steps_setup(rec, cuda_device)
+    n = batch.n_nodes
+    ip, op = batch.in_ptr.cpu().numpy().astype(np.int64), batch.out_ptr.cpu().numpy().astype(np.int64)
+    inb, onb = batch.in_nbr.cpu().numpy().astype(np.int64), batch.out_nbr.cpu().numpy().astype(np.int64)
+    ap, adj = batch.adj_ptr.cpu().numpy().astype(np.int64), batch.adj.cpu().numpy().view(np.uint32).astype(np.int64)
+    assert np.array_equal(ap, ip + op)
+    saw_absent = False
+    for v in range(n):
+        want = [x if x >= 0 else 0x7fffffff for x in inb[ip[v]:ip[v + 1]]] + \
+               [(x | 0x80000000) if x >= 0 else 0x7fffffff for x in onb[op[v]:op[v + 1]]]
+        assert list(adj[ap[v]:ap[v + 1]]) == want
+        saw_absent |= 0x7fffffff in want
+    assert saw_absent
+
+
+@pytest.mark.parametrize("name", CASES + ["toy2d_f2_h32_it10"])
+def test_fused_forward_matches_reference_and_exact_kernels(name, cuda_device):
+    """The whole forward: fused path (default) vs the reference's stored output and vs the step-by-step
+    kernels (model.exact = True); reproducible to the bit; nothing clamped at these weights."""
+    rec = load_case(name)
+    model = make_model(rec, cuda_device)
+    graphs = sparse_graphs_of(rec)
+    with torch.no_grad():
+        a = model(graphs).clone()
+        b = model(graphs).clone()
+        model.exact = True
+        c = model(graphs).clone()
+        model.exact = False
+    model.check_range()
+    assert torch.equal(a, b)
+    assert rel_err(a.cpu().numpy(), rec["out"]) <= TOL
+    assert rel_err(a.cpu().numpy(), c.cpu().numpy()) <= TOL
+    assert not torch.equal(a, c)                                  # they are different kernels
+
+
+def test_zero_iterations_and_empty_batches(cuda_device):
+    from gnn_fpga_b200 import SegmentClassifier, SparseGraph, data
+    g = data.acts_like_graph(30, seed=0)
+    p = O.init_params(3, 32, seed=2)
+    model = SegmentClassifier(3, 32, 0)
+    model.load_state_dict(p)
+    model = model.to(cuda_device).eval()
+    X, src, dst, e_max = O.flatten_sparse_batch([g])
+    with torch.no_grad():
+        out = model([g])[0].cpu().numpy()
+    assert rel_err(out, O.sparse_forward(p, X, src, dst, 0).numpy()) <= TOL
+    empty = SparseGraph(np.zeros((5, 3), np.float32), *(np.zeros(0, np.int64),) * 4, np.zeros(0, np.float32))
+    model2 = SegmentClassifier(3, 32, 2).to(cuda_device).eval()
+    with torch.no_grad():
+        assert tuple(model2([empty]).shape) == (1, 0)
+        both = model2([g, empty])
+        assert tuple(both.shape) == (2, e_max)
+
+
+def test_range_flag_raises_and_exact_path_is_the_cure(cuda_device):
+    """Projections beyond the fused path's range (|W1.[H|X] + b1| > 43.6) raise the flag: predict_stream refuses
+    the batch, model.check_range() reports it, model.exact = True computes it with the step-by-step kernels."""
+    from gnn_fpga_b200 import GnnsegError, SegmentClassifier, data
+    g = data.acts_like_graph(40, seed=3)
+    p = {k: (v * 60.0 if k.startswith("edge_network.network.0") else v) for k, v in O.init_params(3, 32, seed=0).items()}
+    model = SegmentClassifier(3, 32, 2)
+    model.load_state_dict(p)
+    model = model.to(cuda_device).eval()
+    with torch.no_grad():
+        model([g])
+        with pytest.raises(GnnsegError, match="range"):
+            model.check_range()
+        with pytest.raises(GnnsegError, match="range"):
+            list(model.predict_stream([[g]]))
+        model.exact = True
+        out = model([g])[0].cpu().numpy()
+        model.check_range()
+    X, src, dst, e_max = O.flatten_sparse_batch([g])
+    ref = O.sparse_forward(p, X, src, dst, 2, torch.float64).numpy()
+    assert np.max(np.abs(out - ref)) <= 1e-4
