@@ -108,10 +108,11 @@ SIGNATURES = {
     "gnnseg_npz_close_graph_host": (C.c_int, [C.POINTER(GnnsegNpzGraph)]),
     "gnnseg_npz_open_batch_host": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "gnnseg_npz_close_batch_host": (C.c_int, [C.c_int, C.c_void_p]),
-    "gnnseg_store_plan_host": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GnnsegStoreLayout)]),
+    "gnnseg_store_plan_host": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(GnnsegStoreLayout)]),
     "gnnseg_store_fill_host": (C.c_int, [C.POINTER(GnnsegStoreLayout), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                        C.c_void_p]),
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p]),
     "gnnseg_assemble_batch": (C.c_int, [_i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_void_p, C.c_void_p,
                                        C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, C.c_void_p]),
     "gnnseg_pack_sparse_batch_host": (C.c_int, [

@@ -1,6 +1,7 @@
 // Shared definitions for the gnnseg kernels (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include "gnnseg.h"
 
@@ -139,40 +140,43 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), const int grid, const in
 // Idempotent writes of the same values: safe without a lock.
 constexpr int MAX_DEVICES = 64;
 inline int cached_sm_count() {
-    static int cache[MAX_DEVICES];
+    static std::atomic<int> cache[MAX_DEVICES];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return -1;
-    if (cache[dev] == 0) {
-        int n = 0;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) return -1;
-        cache[dev] = n;
+        cache[dev].store(n, std::memory_order_relaxed);
     }
-    return cache[dev];
+    return n;
 }
 // opt the kernel in to `bytes` of dynamic shared memory (once per device)
 template <auto Kern>
 inline bool ensure_dynamic_smem(const int bytes) {
-    static bool done[MAX_DEVICES];
+    static std::atomic<int> done[MAX_DEVICES];                        // largest size opted in so far
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return false;
-    if (!done[dev]) {
+    if (done[dev].load(std::memory_order_acquire) < bytes) {
         if (cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
-        done[dev] = true;
+        done[dev].store(bytes, std::memory_order_release);
     }
     return true;
 }
-// resident CTAs per SM of the kernel at this launch shape (once per device)
+// resident CTAs per SM of the kernel at this launch shape.  One cached value per (kernel, device), tagged with
+// the launch shape it was computed for: another shape recomputes instead of reusing it.  The slot is one atomic
+// 64-bit word (shape tag | occupancy), so concurrent host threads read either nothing or a complete entry.
 template <auto Kern>
 inline int cached_occupancy(const int threads, const size_t smem) {
-    static int cache[MAX_DEVICES];
+    static std::atomic<unsigned long long> cache[MAX_DEVICES];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return -1;
-    if (cache[dev] == 0) {
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, Kern, threads, smem) != cudaSuccess || occ < 1) return -1;
-        cache[dev] = occ;
-    }
-    return cache[dev];
+    const unsigned long long tag = ((unsigned long long)(threads & 0xFFFF) << 48) | ((unsigned long long)(smem & 0xFFFFFFFFull) << 16);
+    const unsigned long long v = cache[dev].load(std::memory_order_acquire);
+    if ((v & ~0xFFFFull) == tag && (v & 0xFFFF) != 0) return (int)(v & 0xFFFF);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, Kern, threads, smem) != cudaSuccess || occ < 1) return -1;
+    cache[dev].store(tag | (unsigned long long)(occ & 0xFFFF), std::memory_order_release);
+    return occ;
 }
 
 // tanh(x) = 1 - 2 / (exp(2x) + 1) with the hardware ex2 / rcp approximations: 2 MUFU + 3 FMA-pipe
@@ -197,12 +201,13 @@ __device__ __forceinline__ float tanh_node(const float x) {
     return tanh_fast(x);
 #else
     float e, r;
-    const float a = x * 2.885390081777927f;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+    const float a = fminf(x * 2.885390081777927f, 126.f);      // e stays finite: the Newton step would turn inf * 0 into NaN
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));       // (fminf keeps a NaN a NaN only by accident: see below)
     const float d = e + 1.f;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
     r = fmaf(r, fmaf(-d, r, 1.f), r);
-    return fmaf(-2.f, r, 1.f);
+    const float t = fmaf(-2.f, r, 1.f);
+    return x != x ? x : t;                                      // fminf(NaN, 126) = 126: put the NaN back
 #endif
 }
 // the edge network's hidden activation (E*h evaluations per step): the 5-instruction form

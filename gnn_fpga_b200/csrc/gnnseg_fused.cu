@@ -43,10 +43,10 @@ __device__ __forceinline__ float ex2_approx(const float x) {
 }
 // sigmoid(z) = 1 / (1 + 2^(-z log2e)), Newton-refined reciprocal (one evaluation per edge, not per hidden unit)
 __device__ __forceinline__ float sigmoid_fast(const float z) {
-    const float d = 1.f + ex2_approx(-LOG2E * z);
+    const float d = 1.f + ex2_approx(fminf(-LOG2E * z, 126.f));   // d stays finite: the Newton step would turn inf * 0 into NaN
     float r = rcp_approx(d);
     r = fmaf(r, fmaf(-d, r, 1.f), r);
-    return r;
+    return z != z ? z : r;                                        // fminf drops a NaN: put it back
 }
 
 // partial sum over this lane's four hidden units of  -2 w2_k / ((a_k * own_k)^2 + 1)

@@ -29,7 +29,7 @@ extern "C" int gnnseg_pack_sparse_batch_host(
     }
     if (node_off[B] > 0x7fffffffLL || (int64_t)B * e_max > 0x7fffffffLL) return GNNSEG_EINVAL;
 
-    std::atomic<int> bad(0);
+    std::atomic<int> bad(0), dup(0);
     // default: all cores but two (the caller's launching thread and the CUDA driver need them;
     // an oversubscribed team doubles the per-batch time)
     int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency() - 2;
@@ -71,9 +71,12 @@ extern "C" int gnnseg_pack_sparse_batch_host(
             for (int64_t i = k.beg; i < k.end; ++i) {
                 const int64_t r = rr[i], c = rc[i];
                 if (r < 0 || r >= nn || c < 0 || c >= e_max) { bad.store(1); continue; }
-                out[c] = (int32_t)(off + r);
+                // a column listed twice (hyper-edge: the dense reference would sum two rows, gnn/model.py:71-72) is an
+                // error, not last-writer-wins; the exchange also makes the two writers' race well defined
+                if (__atomic_exchange_n(&out[c], (int32_t)(off + r), __ATOMIC_RELAXED) != -1) dup.store(1);
             }
         }
     }
-    return bad.load() ? GNNSEG_EINVAL : GNNSEG_OK;
+    if (bad.load()) return GNNSEG_EINVAL;
+    return dup.load() ? GNNSEG_EHYPEREDGE : GNNSEG_OK;
 }

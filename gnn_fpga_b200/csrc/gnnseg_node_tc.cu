@@ -238,9 +238,11 @@ __device__ __forceinline__ void to_exponentials(float (&v)[16], int* __restrict_
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         float a = v[i] * 1.4426950408889634f;
-        clamped |= fabsf(a) > 63.f;
-        a = fminf(fmaxf(a, -63.f), 63.f);
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v[i]) : "f"(a));
+        clamped |= !(fabsf(a) <= 63.f);                         // also a NaN
+        const float c = fminf(fmaxf(a, -63.f), 63.f);
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(c));
+        v[i] = a != a ? a : e;                                  // fminf / fmaxf drop a NaN: keep it visible
     }
     if (clamped && flag) atomicOr(flag, 1);
 }

@@ -58,7 +58,9 @@ bool parse_npy(const unsigned char* p, uint64_t size, Member* m) {
     // 'descr': '<f4'
     size_t k = h.find("'descr'");
     if (k == std::string::npos) return false;
-    k = h.find('\'', h.find(':', k));
+    const size_t dcolon = h.find(':', k);
+    if (dcolon == std::string::npos) return false;
+    k = h.find('\'', dcolon);
     if (k == std::string::npos || k + 4 > h.size()) return false;
     const char order = h[k + 1];
     if (order != '<' && order != '|' && order != '=') return false;       // little endian only
@@ -69,7 +71,9 @@ bool parse_npy(const unsigned char* p, uint64_t size, Member* m) {
     k = h.find("'fortran_order'");
     if (k == std::string::npos) return false;
     const size_t colon = h.find(':', k);
-    if (colon == std::string::npos || h.compare(h.find_first_not_of(' ', colon + 1), 5, "False") != 0) return false;
+    if (colon == std::string::npos) return false;
+    const size_t val = h.find_first_not_of(' ', colon + 1);
+    if (val == std::string::npos || val + 5 > h.size() || h.compare(val, 5, "False") != 0) return false;
     // 'shape': (N,) | (N, F) | ()
     k = h.find("'shape'");
     if (k == std::string::npos) return false;
@@ -88,8 +92,10 @@ bool parse_npy(const unsigned char* p, uint64_t size, Member* m) {
     uint64_t count = 1;
     for (int i = 0; i < m->ndim; ++i) {
         if (m->shape[i] < 0) return false;
+        if (m->shape[i] != 0 && count > size / (uint64_t)m->shape[i]) return false;     // more elements than the member has bytes
         count *= (uint64_t)m->shape[i];
     }
+    if (count > size / (uint64_t)m->item) return false;
     m->data = p + hoff + hlen;
     m->bytes = count * (uint64_t)m->item;
     return hoff + hlen + m->bytes <= size;
@@ -167,6 +173,7 @@ extern "C" int gnnseg_npz_open_graph_host(const char* path, GnnsegNpzGraph* g) {
     int rc = GNNSEG_OK;
     if (!read_directory(b, map->size, &dir)) rc = GNNSEG_EFORMAT;
     bool seen[6] = {false, false, false, false, false, false};
+    int64_t len[4] = {0, 0, 0, 0};                                       // Ri_rows, Ri_cols, Ro_rows, Ro_cols, whatever their order in the archive
     static const char* names[6] = {"X.npy", "Ri_rows.npy", "Ri_cols.npy", "Ro_rows.npy", "Ro_cols.npy", "y.npy"};
     for (size_t i = 0; i < dir.size() && rc == GNNSEG_OK; ++i) {
         int which = -1;
@@ -198,16 +205,19 @@ extern "C" int gnnseg_npz_open_graph_host(const char* path, GnnsegNpzGraph* g) {
         seen[which] = true;
         switch (which) {
             case 0: g->X = static_cast<const float*>(ptr); g->n_nodes = m.shape[0]; g->n_features = (int32_t)m.shape[1]; break;
-            case 1: g->Ri_rows = static_cast<const int64_t*>(ptr); g->n_in = m.shape[0]; break;
-            case 2: g->Ri_cols = static_cast<const int64_t*>(ptr); if (seen[1] && m.shape[0] != g->n_in) rc = GNNSEG_EFORMAT; g->n_in = m.shape[0]; break;
-            case 3: g->Ro_rows = static_cast<const int64_t*>(ptr); g->n_out = m.shape[0]; break;
-            case 4: g->Ro_cols = static_cast<const int64_t*>(ptr); if (seen[3] && m.shape[0] != g->n_out) rc = GNNSEG_EFORMAT; g->n_out = m.shape[0]; break;
+            case 1: g->Ri_rows = static_cast<const int64_t*>(ptr); len[0] = m.shape[0]; break;
+            case 2: g->Ri_cols = static_cast<const int64_t*>(ptr); len[1] = m.shape[0]; break;
+            case 3: g->Ro_rows = static_cast<const int64_t*>(ptr); len[2] = m.shape[0]; break;
+            case 4: g->Ro_cols = static_cast<const int64_t*>(ptr); len[3] = m.shape[0]; break;
             case 5: g->y = static_cast<const float*>(ptr); g->n_y = m.shape[0]; break;
         }
     }
     if (rc == GNNSEG_OK)
         for (int k = 0; k < 5; ++k)                                      // y may be absent; the five others may not
             if (!seen[k]) rc = GNNSEG_EFORMAT;
+    if (rc == GNNSEG_OK && (len[0] != len[1] || len[2] != len[3])) rc = GNNSEG_EFORMAT;   // rows / cols of one matrix differ in length
+    g->n_in = len[0];
+    g->n_out = len[2];
     if (rc != GNNSEG_OK) {
         gnnseg_npz_close_graph_host(g);
         return rc;

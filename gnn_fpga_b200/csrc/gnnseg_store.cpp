@@ -83,7 +83,7 @@ int pick_order_column(int B, int F, const float* const* X, const int64_t* n_node
 template <typename ColT>
 int fill_event(const GnnsegStoreLayout& L, int b, int F, const float* X, int64_t n, const int64_t* rows_in,
                const int64_t* cols_in, int64_t n_in, const int64_t* rows_out, const int64_t* cols_out, int64_t n_out,
-               const float* y, int64_t n_y, int order_col, char* arena) {
+               const float* y, int64_t n_y, int64_t n_edges, int order_col, char* arena) {
     const int64_t* node_off = reinterpret_cast<const int64_t*>(arena + L.o_node_off);
     const int64_t* in_off = reinterpret_cast<const int64_t*>(arena + L.o_in_off);
     const int64_t* out_off = reinterpret_cast<const int64_t*>(arena + L.o_out_off);
@@ -96,7 +96,7 @@ int fill_event(const GnnsegStoreLayout& L, int b, int F, const float* X, int64_t
     const int64_t* rows[2] = {rows_in, rows_out};
     const int64_t* cols[2] = {cols_in, cols_out};
     const int64_t cnt[2] = {n_in, n_out};
-    const int64_t e = n_in;                                    // graph_from_sparse: n_edges = len(Ri_rows)
+    const int64_t e = n_edges;                                 // columns of the event (graph_from_sparse: len(Ri_rows))
 
     // internal order
     std::vector<int32_t> rank((size_t)n);
@@ -139,7 +139,8 @@ int fill_event(const GnnsegStoreLayout& L, int b, int F, const float* X, int64_t
 }  // namespace
 
 extern "C" int gnnseg_store_plan_host(int n_events, int F, const int64_t* n_nodes_host, const int64_t* n_in_host,
-                                      const int64_t* n_out_host, const int64_t* n_y_host, GnnsegStoreLayout* L) {
+                                      const int64_t* n_out_host, const int64_t* n_y_host, const int64_t* n_edges_host,
+                                      GnnsegStoreLayout* L) {
     if (n_events < 0 || F < 1 || !L || (n_events > 0 && (!n_nodes_host || !n_in_host || !n_out_host))) return GNNSEG_EINVAL;
     int64_t tn = 0, ti = 0, to = 0, ty = 0, emax = 0;
     for (int b = 0; b < n_events; ++b) {
@@ -147,7 +148,9 @@ extern "C" int gnnseg_store_plan_host(int n_events, int F, const int64_t* n_node
         if (n_nodes_host[b] < 0 || n_in_host[b] < 0 || n_out_host[b] < 0 || ny < 0) return GNNSEG_EINVAL;
         if (n_nodes_host[b] > 0x7ffffff0LL || n_in_host[b] > 0x7ffffff0LL || n_out_host[b] > 0x7ffffff0LL) return GNNSEG_EINVAL;
         tn += n_nodes_host[b]; ti += n_in_host[b]; to += n_out_host[b]; ty += ny;
-        emax = std::max(emax, n_in_host[b]);
+        const int64_t ne = n_edges_host ? n_edges_host[b] : n_in_host[b];
+        if (ne < n_in_host[b] || ne > 0x7ffffff0LL) return GNNSEG_EINVAL;
+        emax = std::max(emax, ne);
     }
     std::memset(L, 0, sizeof(*L));
     L->n_events = n_events; L->n_features = F;
@@ -174,8 +177,8 @@ extern "C" int gnnseg_store_fill_host(const GnnsegStoreLayout* L, const float* c
                                       const int64_t* const* Ri_rows_host, const int64_t* const* Ri_cols_host,
                                       const int64_t* const* Ro_rows_host, const int64_t* const* Ro_cols_host,
                                       const int64_t* n_in_host, const int64_t* n_out_host, const float* const* y_host,
-                                      const int64_t* n_y_host, int reorder, int n_threads, void* arena_host,
-                                      int32_t* info_host) {
+                                      const int64_t* n_y_host, const int64_t* n_edges_host, int reorder, int n_threads,
+                                      void* arena_host, int32_t* info_host) {
     if (!L || !arena_host) return GNNSEG_EINVAL;
     const int B = (int)L->n_events, F = L->n_features;
     if (info_host) { info_host[0] = -1; info_host[1] = -1; }
@@ -210,11 +213,13 @@ extern "C" int gnnseg_store_fill_host(const GnnsegStoreLayout* L, const float* c
         for (int b = next.fetch_add(1); b < B; b = next.fetch_add(1)) {
             const float* y = (y_host && n_y_host && n_y_host[b] > 0) ? y_host[b] : nullptr;
             const int64_t ny = y ? n_y_host[b] : 0;
-            const int r = L->col_bytes == 2
+            const int64_t ne = n_edges_host ? n_edges_host[b] : n_in_host[b];
+            const bool fits = L->col_bytes == 4 || ne <= 65536;             // the layout was planned for these edge counts
+            const int r = !fits ? GNNSEG_EINVAL : L->col_bytes == 2
                 ? fill_event<uint16_t>(*L, b, F, X_host[b], n_nodes_host[b], Ri_rows_host[b], Ri_cols_host[b], n_in_host[b],
-                                       Ro_rows_host[b], Ro_cols_host[b], n_out_host[b], y, ny, order_col, arena)
+                                       Ro_rows_host[b], Ro_cols_host[b], n_out_host[b], y, ny, ne, order_col, arena)
                 : fill_event<int32_t>(*L, b, F, X_host[b], n_nodes_host[b], Ri_rows_host[b], Ri_cols_host[b], n_in_host[b],
-                                      Ro_rows_host[b], Ro_cols_host[b], n_out_host[b], y, ny, order_col, arena);
+                                      Ro_rows_host[b], Ro_cols_host[b], n_out_host[b], y, ny, ne, order_col, arena);
             if (r != GNNSEG_OK) {
                 int expect = GNNSEG_OK;
                 if (rc.compare_exchange_strong(expect, r)) bad_event.store(b);

@@ -462,6 +462,8 @@ def pack_npz_batch_host(filenames, pinned=None, n_threads=0):
         L.gnnseg_npz_close_batch_host(B, C.addressof(gs))
     if rc == -1:
         raise ValueError("graph file index out of range (row >= n_nodes or col >= max len(Ri_rows))")
+    if rc == _lib.EHYPEREDGE:
+        raise ValueError("a column of Ri or Ro has more than one non-zero entry")
     _lib.check(rc, "gnnseg_pack_sparse_batch_host")
     return {"X": Xo, "src": src, "dst": dst, "e_max": e_max, "n_nodes": n_nodes.tolist()}
 
@@ -519,5 +521,7 @@ def pack_sparse_batch_host(graphs, pinned=None, n_threads=0):
         Xo.data_ptr(), src.data_ptr(), dst.data_ptr(), n_threads)
     if rc == -1:
         raise ValueError("SparseGraph index out of range (row >= n_nodes or col >= max len(Ri_rows))")
+    if rc == _lib.EHYPEREDGE:
+        raise ValueError("a column of Ri or Ro has more than one non-zero entry")
     _lib.check(rc, "gnnseg_pack_sparse_batch_host")
     return {"X": Xo, "src": src, "dst": dst, "e_max": e_max, "n_nodes": n_nodes.tolist()}

@@ -44,7 +44,7 @@ class StoreBatch:
 class GraphStore:
     """Pinned host arena of a list of graphs (include/gnnseg.h, GnnsegStoreLayout)."""
 
-    def __init__(self, graphs, arena, layout, order_column):
+    def __init__(self, graphs, arena, layout, order_column, n_edges=None):
         self.graphs = graphs                      # the original SparseGraph tuples (numpy views), as load_graphs gives them
         self.arena = arena                        # uint8 tensor, pinned when CUDA is available
         self.layout = layout
@@ -67,7 +67,9 @@ class GraphStore:
         self.out_col = arena[L.o_out_col:L.o_out_col + self.col_bytes * to].view(col_dt)
         self.y = arena[L.o_y:L.o_y + 4 * ty].view(torch.float32)
         self.perm = arena[L.o_perm:L.o_perm + 4 * tn].view(torch.int32)
-        self.n_in = np.diff(self.in_off)          # edges per event: len(Ri_rows), as graph_from_sparse counts them
+        # edge columns per event: len(Ri_rows), as graph_from_sparse counts them (gnn/graph.py:30), or more when
+        # the tuple has columns without an end node
+        self.n_in = np.diff(self.in_off) if n_edges is None else np.asarray(n_edges, dtype=np.int64)
 
     def __len__(self):
         return int(self.layout.n_events)
@@ -103,9 +105,16 @@ class GraphStore:
         n_in = np.fromiter((a.shape[0] for a in cols[0]), dtype=np.int64, count=B)
         n_out = np.fromiter((a.shape[0] for a in cols[2]), dtype=np.int64, count=B)
         n_y = np.fromiter((a.shape[0] for a in ys), dtype=np.int64, count=B)
+        # edge columns of an event: len(Ri_rows) as graph_from_sparse has it; a tuple that lists a column only in
+        # Ro (an edge without an end node, which only a dense graph can express in the reference) keeps that column
+        # (every column is listed in Ri or in Ro, so there are at most len(Ri_rows) + len(Ro_rows) of them: a larger
+        # column id is an error, reported by the fill as out of range)
+        n_edges = np.fromiter((max(int(n_in[b]), min(max(int(cols[1][b].max(initial=-1)), int(cols[3][b].max(initial=-1))) + 1,
+                                                     int(n_in[b] + n_out[b])))
+                               for b in range(B)), dtype=np.int64, count=B)
         ptr = lambda a: a.__array_interface__["data"][0]
         layout = _lib.GnnsegStoreLayout()
-        _lib.check(L.gnnseg_store_plan_host(B, F, ptr(n_nodes), ptr(n_in), ptr(n_out), ptr(n_y), C.byref(layout)),
+        _lib.check(L.gnnseg_store_plan_host(B, F, ptr(n_nodes), ptr(n_in), ptr(n_out), ptr(n_y), ptr(n_edges), C.byref(layout)),
                    "gnnseg_store_plan_host")
         if pin is None:
             pin = torch.cuda.is_available()
@@ -119,14 +128,14 @@ class GraphStore:
 
         info = np.full(2, -1, dtype=np.int32)
         rc = L.gnnseg_store_fill_host(C.byref(layout), pp(Xs), ptr(n_nodes), pp(cols[0]), pp(cols[1]), pp(cols[2]), pp(cols[3]),
-                                      ptr(n_in), ptr(n_out), pp(ys), ptr(n_y), REORDER[reorder], n_threads,
+                                      ptr(n_in), ptr(n_out), pp(ys), ptr(n_y), ptr(n_edges), REORDER[reorder], n_threads,
                                       arena.data_ptr(), ptr(info))
         if rc == _lib.EHYPEREDGE:
             raise ValueError("graph %d: a column of Ri or Ro has more than one non-zero entry" % int(info[0]))
         if rc == -1:
             raise ValueError("graph %d: SparseGraph index out of range (row >= n_nodes or col >= len(Ri_rows))" % int(info[0]))
         _lib.check(rc, "gnnseg_store_fill_host")
-        return cls(graphs, arena, layout, int(info[1]))
+        return cls(graphs, arena, layout, int(info[1]), n_edges)
 
     @classmethod
     def from_files(cls, filenames, reorder="auto", n_threads=0):

@@ -370,7 +370,10 @@ int gnnseg_pack_sparse_batch_host(int B, int F, int e_max,
  * reorder: 0 keeps the node order; 1 renumbers the nodes of every event internally along the feature
  * column in which edges are most local (the forward's gathers then hit in L1; scores, being per edge
  * column, do not see it; `perm` undoes it for per-node outputs); 2 = 1 for events of >= 1024 nodes.
- * Errors: GNNSEG_EINVAL for an index out of range (row >= n_nodes, column >= len(Ri_rows)),
+ * n_edges_host: the number of edge columns of every event; NULL = len(Ri_rows), which is what
+ * graph_from_sparse takes (gnn/graph.py:30).  A caller whose tuples have zero columns in Ri (an edge
+ * without an end node: a dense graph can hold one, the reference's sparse form cannot) passes the true count.
+ * Errors: GNNSEG_EINVAL for an index out of range (row >= n_nodes, column >= n_edges),
  * GNNSEG_EHYPEREDGE for a column listed twice in Ri or in Ro (the dense reference would sum two rows,
  * gnn/model.py:71-72).  info_host (nullable, 2 words): [0] = the first offending event or -1,
  * [1] = the column chosen for the renumbering or -1.  Pure CPU; n_threads <= 0 picks a default.
@@ -385,13 +388,14 @@ typedef struct GnnsegStoreLayout {
 } GnnsegStoreLayout;
 int gnnseg_store_plan_host(int n_events, int F, const int64_t* n_nodes_host, const int64_t* n_in_host,
                            const int64_t* n_out_host, const int64_t* n_y_host /* nullable */,
-                           GnnsegStoreLayout* layout);
+                           const int64_t* n_edges_host /* nullable */, GnnsegStoreLayout* layout);
 int gnnseg_store_fill_host(const GnnsegStoreLayout* layout,
                            const float* const* X_host, const int64_t* n_nodes_host,
                            const int64_t* const* Ri_rows_host, const int64_t* const* Ri_cols_host,
                            const int64_t* const* Ro_rows_host, const int64_t* const* Ro_cols_host,
                            const int64_t* n_in_host, const int64_t* n_out_host,
                            const float* const* y_host /* nullable */, const int64_t* n_y_host /* nullable */,
+                           const int64_t* n_edges_host /* nullable */,
                            int reorder, int n_threads, void* arena_host, int32_t* info_host);
 /*
  * Device part: the flattened batch graph of B consecutive events of a store from their slices

@@ -70,7 +70,7 @@ def test_argument_errors_without_device_work():
     assert L.gnnseg_state_mlp_step(None, None, None, 32, 10, 8, None, 1, None, None) == -2
     assert L.gnnseg_assemble_batch(None, 2, 10, 5, 3, 3, None, None, None, None, 3, None, None, None, None, None, None,
                                    None, None, None, None, None) == -1                             # col_bytes 2 or 4
-    assert L.gnnseg_store_plan_host(1, 0, None, None, None, None, None) == -1
+    assert L.gnnseg_store_plan_host(1, 0, None, None, None, None, None, None) == -1
     assert b"hyper-edge" in L.gnnseg_strerror(-8)
 
 

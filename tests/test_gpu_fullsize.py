@@ -91,6 +91,7 @@ def test_large_weights_error_report(h, n_iters, scale, cuda_device):
         ref64 = O.sparse_forward(p, X, src, dst, n_iters, torch.float64).numpy()
         d = graph_from_sparse(g, dtype=np.float32)
         dense32 = O.dense_forward(p, *(torch.from_numpy(a[None]) for a in (d.X, d.Ri, d.Ro)), n_iters)[0].numpy()
+        assert np.all(np.isfinite(out))
         worst_cuda = max(worst_cuda, rel_err(out, ref64))
         worst_ref = max(worst_ref, rel_err(dense32, ref64))
         worst_abs = max(worst_abs, float(np.max(np.abs(out.astype(np.float64) - ref64))))

@@ -161,7 +161,7 @@ def test_range_flag_raises_and_exact_path_is_the_cure(cuda_device):
     the batch, model.check_range() reports it, model.exact = True computes it with the step-by-step kernels."""
     from gnn_fpga_b200 import GnnsegError, SegmentClassifier, data
     g = data.acts_like_graph(40, seed=3)
-    p = {k: (v * 60.0 if k.startswith("edge_network.network.0") else v) for k, v in O.init_params(3, 32, seed=0).items()}
+    p = {k: (v * 300.0 if k.startswith("edge_network.network.0") else v) for k, v in O.init_params(3, 32, seed=0).items()}
     model = SegmentClassifier(3, 32, 2)
     model.load_state_dict(p)
     model = model.to(cuda_device).eval()

@@ -120,9 +120,13 @@ def test_store_rejects_bad_graphs():
     cols = good.Ro_cols.copy(); cols[5] = cols[4]
     with pytest.raises(ValueError, match="graph 0.*more than one"):
         GraphStore.from_sparse_graphs([good._replace(Ro_cols=cols), good], pin=False)
-    cols = good.Ri_cols.copy(); cols[0] = good.Ri_rows.shape[0]
+    cols = good.Ri_cols.copy(); cols[0] = good.Ri_rows.shape[0] + good.Ro_rows.shape[0]
     with pytest.raises(ValueError, match="out of range"):
         GraphStore.from_sparse_graphs([good._replace(Ri_cols=cols)], pin=False)
+    # a column listed only in Ro (an edge without an end node) is a legal graph: it keeps its column
+    half = good._replace(Ri_rows=good.Ri_rows[good.Ri_cols != good.Ri_cols.max()], Ri_cols=good.Ri_cols[good.Ri_cols != good.Ri_cols.max()])
+    st = GraphStore.from_sparse_graphs([half], reorder=False, pin=False)
+    assert int(st.n_in[0]) == good.Ri_rows.shape[0] and st.batch_meta(0, 1)[2] == good.Ri_rows.shape[0]
 
 
 def test_batches_follow_the_reference_generator():
