@@ -44,13 +44,24 @@ class GnnsegNpzGraph(C.Structure):
 class GnnsegStoreLayout(C.Structure):
     _fields_ = [("n_events", C.c_int64), ("n_features", C.c_int32), ("col_bytes", C.c_int32)] + [(n, C.c_int64) for n in (
         "total_nodes", "total_in", "total_out", "total_y", "o_node_off", "o_in_off", "o_out_off", "o_y_off",
-        "o_X", "o_in_ptr", "o_out_ptr", "o_in_col", "o_out_col", "o_y", "o_perm", "bytes")]
+        "o_X", "o_in_ptr", "o_out_ptr", "o_in_col", "o_out_col", "o_y", "o_perm", "o_n_edges", "bytes")]
+
+
+class GnnsegBatchBuffers(C.Structure):
+    """One pipeline slot of gnnseg_store_forward_batch (include/gnnseg.h)."""
+    _fields_ = ([(n, C.c_int32) for n in ("cap_nodes", "cap_in", "cap_out", "cap_slots", "cap_events", "reserved_")] +
+                [(n, C.c_void_p) for n in ("meta", "X", "in_ptr_local", "out_ptr_local", "in_col", "out_col", "src", "dst", "in_pos",
+                                           "out_pos", "in_ptr", "out_ptr", "adj_ptr", "in_eid", "in_nbr", "out_eid", "out_nbr", "adj",
+                                           "node_order", "scores", "status", "ws")] +
+                [("ws_bytes", C.c_size_t)] + [(n, C.c_void_p) for n in ("meta_host", "scores_host", "status_host")])
 
 
 class GnnsegGraph(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_slots", C.c_int32)] + [(n, C.c_void_p) for n in (
-        "src", "dst", "in_ptr", "in_eid", "in_nbr", "out_ptr", "out_eid", "out_nbr", "in_pos", "out_pos", "adj_ptr", "adj")]
+        "src", "dst", "in_ptr", "in_eid", "in_nbr", "out_ptr", "out_eid", "out_nbr", "in_pos", "out_pos", "adj_ptr", "adj", "node_order")]
 
+
+EWORKSPACE = -3
 
 # name -> (restype, argtypes); must list every symbol include/gnnseg.h declares
 SIGNATURES = {
@@ -69,7 +80,13 @@ SIGNATURES = {
     "gnnseg_forward": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "gnnseg_forward_ex": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t,
                                    C.c_int, _i32p, C.c_void_p]),
-    "gnnseg_build_adjacency": (C.c_int, [C.POINTER(GnnsegGraph), _i32p, _i32p, C.c_void_p]),
+    "gnnseg_adjacency_entries": (C.c_size_t, [C.c_int, C.c_int]),
+    "gnnseg_build_adjacency": (C.c_int, [C.POINTER(GnnsegGraph), _i32p, _i32p, _i32p, C.c_void_p]),
+    "gnnseg_store_batch_shape_host": (C.c_int, [C.POINTER(GnnsegStoreLayout), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "gnnseg_store_load_batch": (C.c_int, [C.POINTER(GnnsegStoreLayout), C.c_void_p, C.c_int, C.c_int, C.POINTER(GnnsegBatchBuffers),
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gnnseg_store_forward_batch": (C.c_int, [C.POINTER(GnnsegStoreLayout), C.c_void_p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(GnnsegBatchBuffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnnseg_state_input_step": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_int, _i32p, C.c_void_p]),
     "gnnseg_fused_gather_step": (C.c_int, [_f32p, C.POINTER(GnnsegGraph), _f32p, C.c_int, _f32p, C.c_int, C.c_void_p]),
     "gnnseg_state_mlp_step": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, _i32p, C.c_void_p]),

@@ -18,11 +18,12 @@ int build_csr(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int3
 int build_graph(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
 int fused_gather_step(const float*, const GnnsegGraph*, const float*, int, float*, int, cudaStream_t);
 int edge_final_step(const float*, const GnnsegGraph*, const float*, int, int, int, int, float*, cudaStream_t);
-int build_adjacency(const GnnsegGraph*, int32_t*, int32_t*, cudaStream_t);
-int launch_input_tc32_ex(const float*, const float*, int, int, float*, const ProjOut&, bool, float*, cudaStream_t);
-int launch_input_tc64_ex(const float*, const float*, int, int, float*, const ProjOut&, bool, float*, cudaStream_t);
-int launch_node_mlp_tc32_ex(const float*, const float*, const float*, int, int, const ProjOut&, bool, float*, bool, cudaStream_t);
-int launch_node_mlp_tc64_ex(const float*, const float*, const float*, int, int, const ProjOut&, bool, float*, bool, cudaStream_t);
+int build_adjacency(const GnnsegGraph*, int32_t*, int32_t*, int32_t*, cudaStream_t);
+size_t adjacency_entries(int, int);
+int launch_input_tc32_ex(const float*, const float*, int, int, float*, const ProjOut&, float*, cudaStream_t);
+int launch_input_tc64_ex(const float*, const float*, int, int, float*, const ProjOut&, float*, cudaStream_t);
+int launch_node_mlp_tc32_ex(const float*, const float*, const float*, int, int, const ProjOut&, float*, bool, cudaStream_t);
+int launch_node_mlp_tc64_ex(const float*, const float*, const float*, int, int, const ProjOut&, float*, bool, cudaStream_t);
 bool use_pdl(int);
 int assemble_batch(const int32_t*, int, int, int, int, int, const int32_t*, const int32_t*, const void*, const void*, int,
                    const GnnsegGraphMut&, cudaStream_t);
@@ -71,14 +72,14 @@ struct FwdWorkspace {
 };
 
 // X4 | P | Q0 | Q1 | e_in | e_out, each 256-byte aligned.  The fused inference path (gnnseg_fused.cu) uses
-// the same block as X4 | P | S0 | S1 | status word, with S = state rows of 5h floats.
+// the same block as X4 | (P unused) | S0 | S1 | status word, with S = n_nodes + 1 state rows of 5h floats.
 FwdWorkspace carve(void* ws, int n_nodes, int n_slots, int h) {
     FwdWorkspace w;
     const size_t x_b = align_up((size_t)n_nodes * 4 * 4, 256);
     const size_t p_b = align_up((size_t)n_nodes * 2 * h * 4, 256);
     const size_t q_b = align_up((size_t)n_nodes * 3 * h * 4, 256);
     const size_t e_b = align_up((size_t)n_slots * 4, 256);
-    const size_t s_b = align_up((size_t)n_nodes * 5 * h * 4, 256);
+    const size_t s_b = align_up(((size_t)n_nodes + 1) * 5 * h * 4, 256);      // + the extra row absent neighbours point at
     char* base = static_cast<char*>(ws);
     w.x4 = reinterpret_cast<float*>(base);
     w.p = reinterpret_cast<float*>(base + x_b);
@@ -99,15 +100,14 @@ inline bool exact_env() {
     static const bool v = [] { const char* e = getenv("GNNSEG_EXACT"); return e && e[0] != '0'; }();
     return v;
 }
-inline int state_input(const float* blob, const float* X, int n, int F, int h, float* X4, const gnnseg::ProjOut& out, bool state_order,
-                       cudaStream_t st) {
-    return h == 32 ? gnnseg::launch_input_tc32_ex(blob, X, n, F, X4, out, state_order, nullptr, st)
-                   : gnnseg::launch_input_tc64_ex(blob, X, n, F, X4, out, state_order, nullptr, st);
+inline int state_input(const float* blob, const float* X, int n, int F, int h, float* X4, const gnnseg::ProjOut& out, cudaStream_t st) {
+    return h == 32 ? gnnseg::launch_input_tc32_ex(blob, X, n, F, X4, out, nullptr, st)
+                   : gnnseg::launch_input_tc64_ex(blob, X, n, F, X4, out, nullptr, st);
 }
 inline int state_mlp(const float* blob, const float* X4, const float* h1, int ld_h1, int n, int h, const gnnseg::ProjOut& out,
-                     bool state_order, bool pdl, cudaStream_t st) {
-    return h == 32 ? gnnseg::launch_node_mlp_tc32_ex(blob, X4, h1, ld_h1, n, out, state_order, nullptr, pdl, st)
-                   : gnnseg::launch_node_mlp_tc64_ex(blob, X4, h1, ld_h1, n, out, state_order, nullptr, pdl, st);
+                     bool pdl, cudaStream_t st) {
+    return h == 32 ? gnnseg::launch_node_mlp_tc32_ex(blob, X4, h1, ld_h1, n, out, nullptr, pdl, st)
+                   : gnnseg::launch_node_mlp_tc64_ex(blob, X4, h1, ld_h1, n, out, nullptr, pdl, st);
 }
 
 constexpr int MAX_ITERS = 64;
@@ -332,28 +332,33 @@ int gnnseg_forward_ex(const float* blob, const GnnsegGraph* g, const float* X, i
     int32_t* flag = status ? status : w.status;
     if (cudaMemsetAsync(flag, 0, sizeof(int32_t), st) != cudaSuccess) return GNNSEG_ECUDA;
 
-    const bool fused = fused_width(h) && g->adj_ptr && (g->adj || g->n_slots == 0) && !(flags & GNNSEG_FWD_EXACT) && !exact_env();
+    const bool fused = fused_width(h) && g->adj_ptr && g->adj && !(flags & GNNSEG_FWD_EXACT) && !exact_env();
     if (fused) {
         // gnnseg_fused.cu: input -> n_iters x (edge step inside the node step's CSR walk, tensor-core MLP) -> final
-        // edge step over the destination-CSR.  2 * n_iters + 2 launches.  The last producing step writes only the
-        // edge projections, as exponentials, into P = [SPs | SPd].
+        // edge step over the in-edges of every node.  2 * n_iters + 2 launches.
         const int n = g->n_nodes;
         const bool pdl = gnnseg::use_pdl(g->n_slots);
-        const gnnseg::ProjOut last{w.p, nullptr, 2, 2 * h, flag};
-        int rc = n_iters == 0 ? state_input(blob, X, n, F, h, w.x4, last, false, st)
-                              : state_input(blob, X, n, F, h, w.x4, gnnseg::ProjOut{w.s[0], nullptr, 1, 5 * h, flag}, true, st);
+        // row n of a state buffer is what an absent neighbour reads: zeros while the buffer feeds a node step
+        if (cudaMemsetAsync(w.s[0] + (size_t)n * 5 * h, 0, sizeof(float) * 5 * h, st) != cudaSuccess ||
+            cudaMemsetAsync(w.s[1] + (size_t)n * 5 * h, 0, sizeof(float) * 5 * h, st) != cudaSuccess)
+            return GNNSEG_ECUDA;
+        // the last producing step writes only the edge projections [SPs | SPd] of its rows (n_cols = 2h)
+        int rc = state_input(blob, X, n, F, h, w.x4, gnnseg::ProjOut{w.s[0], nullptr, 1, n_iters == 0 ? 2 * h : 5 * h, flag}, st);
         int cur = 0;
         for (int it = 0; it < n_iters && rc == GNNSEG_OK; ++it) {
             const bool is_last = it + 1 == n_iters;
-            float* rows = is_last ? w.p : w.s[cur ^ 1];          // h1 travels in the first h floats of the rows it becomes
-            const int ld = is_last ? 2 * h : 5 * h;
-            rc = gnnseg::fused_gather_step(blob, g, w.s[cur], h, rows, ld, st);
+            float* rows = w.s[cur ^ 1];                          // h1 travels in the first h floats of the rows it becomes
+            rc = gnnseg::fused_gather_step(blob, g, w.s[cur], h, rows, 5 * h, st);
             if (rc == GNNSEG_OK)
-                rc = is_last ? state_mlp(blob, w.x4, rows, ld, n, h, last, false, pdl, st)
-                             : state_mlp(blob, w.x4, rows, ld, n, h, gnnseg::ProjOut{rows, nullptr, 1, 5 * h, flag}, true, pdl, st);
+                rc = state_mlp(blob, w.x4, rows, 5 * h, n, h, gnnseg::ProjOut{rows, nullptr, 1, is_last ? 2 * h : 5 * h, flag}, pdl, st);
             cur ^= 1;
         }
-        if (rc == GNNSEG_OK) rc = gnnseg::edge_final_step(blob, g, w.p, 2 * h, 0, h, h, scores, st);
+        // ... and for the final edge step an absent start node reads 2^(log2e b1) there (Ps = b1, gnn/model.py:71-73)
+        const int sb1 = gnnseg::blob_total(h) - h;
+        if (rc == GNNSEG_OK &&
+            cudaMemcpyAsync(w.s[cur] + (size_t)n * 5 * h, blob + sb1, sizeof(float) * h, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            return GNNSEG_ECUDA;
+        if (rc == GNNSEG_OK) rc = gnnseg::edge_final_step(blob, g, w.s[cur], 5 * h, 0, h, h, scores, st);
         return rc;
     }
 
@@ -376,15 +381,19 @@ int gnnseg_forward(const float* blob, const GnnsegGraph* g, const float* X, int 
     return gnnseg_forward_ex(blob, g, X, F, h, n_iters, scores, ws, ws_bytes, 0, nullptr, stream);
 }
 
-int gnnseg_build_adjacency(const GnnsegGraph* g, int32_t* adj_ptr, int32_t* adj, void* stream) {
-    if (!csr_ok(g) || !adj_ptr) return GNNSEG_EINVAL;
-    if (g->n_slots > 0 && !adj) return GNNSEG_EINVAL;
-    return gnnseg::build_adjacency(g, adj_ptr, adj, static_cast<cudaStream_t>(stream));
+size_t gnnseg_adjacency_entries(int n_nodes, int n_slots) {
+    if (n_nodes < 0 || n_slots < 0) return 0;
+    return gnnseg::adjacency_entries(n_nodes, n_slots);
+}
+
+int gnnseg_build_adjacency(const GnnsegGraph* g, int32_t* adj_ptr, int32_t* adj, int32_t* node_order, void* stream) {
+    if (!csr_ok(g) || !adj_ptr || !adj) return GNNSEG_EINVAL;
+    return gnnseg::build_adjacency(g, adj_ptr, adj, node_order, static_cast<cudaStream_t>(stream));
 }
 
 int gnnseg_fused_gather_step(const float* blob, const GnnsegGraph* g, const float* S, int h, float* h1, int ld_h1, void* stream) {
     if (!fused_width(h)) return GNNSEG_EUNSUPPORTED;
-    if (!blob || !graph_ok(g) || !g->adj_ptr || ld_h1 < h || (ld_h1 & 3)) return GNNSEG_EINVAL;
+    if (!blob || !graph_ok(g) || !g->adj_ptr || !g->adj || ld_h1 < h || (ld_h1 & 3)) return GNNSEG_EINVAL;
     if (g->n_nodes > 0 && (!S || !h1)) return GNNSEG_EINVAL;
     return gnnseg::fused_gather_step(blob, g, S, h, h1, ld_h1, static_cast<cudaStream_t>(stream));
 }
@@ -392,29 +401,28 @@ int gnnseg_fused_gather_step(const float* blob, const GnnsegGraph* g, const floa
 int gnnseg_edge_final_step(const float* blob, const GnnsegGraph* g, const float* P, int ld, int off_s, int off_d, int h,
                            float* scores, void* stream) {
     if (!fused_width(h)) return GNNSEG_EUNSUPPORTED;
-    if (!blob || !csr_ok(g) || ld < 2 * h || (ld & 3) || off_s < 0 || off_d < 0 || (off_s & 3) || (off_d & 3) || off_s + h > ld ||
-        off_d + h > ld)
+    if (!blob || !csr_ok(g) || !g->adj_ptr || !g->adj || ld < 2 * h || (ld & 3) || off_s < 0 || off_d < 0 || (off_s & 3) ||
+        (off_d & 3) || off_s + h > ld || off_d + h > ld)
         return GNNSEG_EINVAL;
     if (g->n_nodes > 0 && !P) return GNNSEG_EINVAL;
     if (g->n_slots > 0 && !scores) return GNNSEG_EINVAL;
     return gnnseg::edge_final_step(blob, g, P, ld, off_s, off_d, h, scores, static_cast<cudaStream_t>(stream));
 }
 
-int gnnseg_state_input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* X4, float* out, int mode,
+int gnnseg_state_input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* X4, float* S, int n_cols,
                             int32_t* status, void* stream) {
     if (!gnnseg_supported(F, h) || !fused_width(h)) return GNNSEG_EUNSUPPORTED;
-    if (!blob || n_nodes < 0 || (mode != 1 && mode != 2) || (n_nodes > 0 && (!X || !X4 || !out))) return GNNSEG_EINVAL;
-    return state_input(blob, X, n_nodes, F, h, X4, gnnseg::ProjOut{out, nullptr, mode, mode == 1 ? 5 * h : 2 * h, status}, mode == 1,
-                       static_cast<cudaStream_t>(stream));
+    if (!blob || n_nodes < 0 || (n_cols != 5 * h && n_cols != 2 * h) || (n_nodes > 0 && (!X || !X4 || !S))) return GNNSEG_EINVAL;
+    return state_input(blob, X, n_nodes, F, h, X4, gnnseg::ProjOut{S, nullptr, 1, n_cols, status}, static_cast<cudaStream_t>(stream));
 }
 
-int gnnseg_state_mlp_step(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, int h, float* out,
-                          int mode, int32_t* status, void* stream) {
+int gnnseg_state_mlp_step(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, int h, float* S,
+                          int n_cols, int32_t* status, void* stream) {
     if (!fused_width(h)) return GNNSEG_EUNSUPPORTED;
-    if (!blob || n_nodes < 0 || (mode != 1 && mode != 2) || ld_h1 < h || (ld_h1 & 3)) return GNNSEG_EINVAL;
-    if (n_nodes > 0 && (!X4 || !h1 || !out)) return GNNSEG_EINVAL;
-    return state_mlp(blob, X4, h1, ld_h1, n_nodes, h, gnnseg::ProjOut{out, nullptr, mode, mode == 1 ? 5 * h : 2 * h, status}, mode == 1,
-                     false, static_cast<cudaStream_t>(stream));
+    if (!blob || n_nodes < 0 || (n_cols != 5 * h && n_cols != 2 * h) || ld_h1 < h || (ld_h1 & 3)) return GNNSEG_EINVAL;
+    if (n_nodes > 0 && (!X4 || !h1 || !S)) return GNNSEG_EINVAL;
+    return state_mlp(blob, X4, h1, ld_h1, n_nodes, h, gnnseg::ProjOut{S, nullptr, 1, n_cols, status}, false,
+                     static_cast<cudaStream_t>(stream));
 }
 
 int gnnseg_forward_nodes(const float* blob, const float* head_blob, const GnnsegGraph* g, const float* X, int F,

@@ -14,11 +14,10 @@ struct GnnsegGraphMut {
     int32_t* out_ptr; int32_t* out_eid; int32_t* out_nbr; int32_t* out_pos;
 };
 
-// Where the columns of a projection GEMM go (tcgen05 kernels, gnnseg_node_tc.cu):
+// Where the columns [Ps|Pd|Qi|Qo|Qs] of a projection GEMM go (tcgen05 kernels, gnnseg_node_tc.cu):
 //   mode 0  [Ps|Pd] -> rows of p (2H floats), [Qi|Qo|Qs] -> rows of q (3H floats)        the step-by-step path
-//   mode 1  state rows of p (5H floats, [SPs|Qi|SPd|Qo|Qs]): the weight image is in state-row order and the
-//           edge projections are stored as exponentials 2^(log2e v)                       gnnseg_fused.cu
-//   mode 2  [SPs|SPd] -> rows of p (2H floats), both as exponentials                      last node step
+//   mode 1  state rows of p (5H floats): [SPs|SPd|Qi|Qo|Qs], the edge projections stored as exponentials
+//           2^(log2e v)                                                                   gnnseg_fused.cu
 // n_cols: how many of the 5H columns are stored (2H when only the edge projections have a reader).
 struct ProjOut {
     float* p;
@@ -62,12 +61,9 @@ struct Blob {
     static constexpr int TC_W4L = TC_W4H + H * H;
     static constexpr int TC_WPH = TC_W4L + H * H;    // [5H][D4P]
     static constexpr int TC_WPL = TC_WPH + 5 * H * D4P;
-    // the fused inference path (gnnseg_fused.cu): the projection images with their output rows in
-    // state-row order [Ps | Qi | Pd | Qo | Qs], and the edge network's second layer in the form the
+    // the fused inference path (gnnseg_fused.cu): the edge network's second layer in the form the
     // reciprocal formulation wants
-    static constexpr int TC_WSH = TC_WPL + 5 * H * D4P;   // [5H][D4P] hi, state-row order
-    static constexpr int TC_WSL = TC_WSH + 5 * H * D4P;   // lo
-    static constexpr int W2N = TC_WSL + 5 * H * D4P;      // [H]  -2 w2
+    static constexpr int W2N = TC_WPL + 5 * H * D4P;      // [H]  -2 w2
     static constexpr int Z0  = W2N + H;                   // [4]  b2 + sum(w2), 0, 0, 0
     static constexpr int SB1 = Z0 + 4;                    // [H]  2^(log2e b1): SPs of an absent start node
     static constexpr int TOTAL = SB1 + H;
@@ -75,7 +71,7 @@ struct Blob {
 
 __host__ __device__ inline int blob_total(int h) {
     const int d4 = h + 4, d4p = (d4 + 7) / 8 * 8;
-    return 4 * h + h + d4 * 5 * h + 5 * h + h + 4 + h * h + h + 2 * h * h + 4 * 5 * h * d4p + 2 * h + 4;
+    return 4 * h + h + d4 * 5 * h + 5 * h + h + 4 + h * h + h + 2 * h * h + 2 * 5 * h * d4p + 2 * h + 4;
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) {

@@ -82,11 +82,11 @@ __global__ void pack_tc_images_kernel(int H, float* __restrict__ blob) {
     const int D4 = H + 4, D4P = (D4 + 7) / 8 * 8;
     const int o_wp = 5 * H, o_bp = o_wp + D4 * 5 * H, o_w2 = o_bp + 5 * H, o_w4 = o_w2 + H + 4, o_img = o_w4 + H * H + H;
     const int n_w4 = H * H, n_wp = 5 * H * D4P;
-    const int o_ws = o_img + 2 * n_w4 + 2 * n_wp, o_w2n = o_ws + 2 * n_wp, o_z0 = o_w2n + H, o_sb1 = o_z0 + 4;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_w4 + 2 * n_wp + 2 * H + 4; i += gridDim.x * blockDim.x) {
-        if (i >= n_w4 + 2 * n_wp) {
+    const int o_w2n = o_img + 2 * n_w4 + 2 * n_wp, o_z0 = o_w2n + H, o_sb1 = o_z0 + 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_w4 + n_wp + 2 * H + 4; i += gridDim.x * blockDim.x) {
+        if (i >= n_w4 + n_wp) {
             // the edge network's second layer for gnnseg_fused.cu: -2 w2, b2 + sum(w2), 2^(log2e b1)
-            const int r = i - (n_w4 + 2 * n_wp);
+            const int r = i - (n_w4 + n_wp);
             if (r < H) blob[o_w2n + r] = -2.f * blob[o_w2 + r];
             else if (r < H + 4) {
                 float z = 0.f;
@@ -99,18 +99,13 @@ __global__ void pack_tc_images_kernel(int H, float* __restrict__ blob) {
             continue;
         }
         const bool is_w4 = i < n_w4;
-        const bool state_order = i >= n_w4 + n_wp;                // second projection image: rows in state-row order
-        const int f = is_w4 ? i : (i - n_w4) % n_wp;              // float index inside the image
+        const int f = is_w4 ? i : i - n_w4;                       // float index inside the image
         const int K = is_w4 ? H : D4P;                            // padded K of this operand
         const int sbo = (K / 4) * 128;                            // bytes between 8-row groups
         const int bytes = f * 4;
         const int grp = bytes / sbo, rem = bytes % sbo;
-        int row = grp * 8 + (rem % 128) / 16;
+        const int row = grp * 8 + (rem % 128) / 16;
         const int k = (rem / 128) * 4 + (rem % 16) / 4;
-        if (state_order) {                                        // [Ps | Qi | Pd | Qo | Qs] <- blocks 0, 2, 1, 3, 4 of [Ps | Pd | Qi | Qo | Qs]
-            const int blk = row / H;
-            row = (blk == 1 ? 2 : blk == 2 ? 1 : blk) * H + row % H;
-        }
         float v;
         // WP image, K index D4 (the first padding column): the bias of the projections.  The tensor-core
         // kernels put a constant 1 in that column of the A operand, so the GEMM adds the bias.
@@ -121,8 +116,8 @@ __global__ void pack_tc_images_kernel(int H, float* __restrict__ blob) {
         const float hi = __uint_as_float(hi_bits);
         uint32_t lo_bits;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo_bits) : "f"(v - hi));
-        const int o_hi = is_w4 ? o_img : (state_order ? o_ws : o_img + 2 * n_w4);
-        const int o_lo = is_w4 ? o_img + n_w4 : (state_order ? o_ws + n_wp : o_img + 2 * n_w4 + n_wp);
+        const int o_hi = is_w4 ? o_img : o_img + 2 * n_w4;
+        const int o_lo = is_w4 ? o_img + n_w4 : o_img + 2 * n_w4 + n_wp;
         blob[o_hi + f] = hi;
         blob[o_lo + f] = __uint_as_float(lo_bits);
     }

@@ -230,7 +230,7 @@ __device__ __forceinline__ float* proj_ptr(const ProjOut& o, const int node, con
 }
 template <int H>
 __device__ __forceinline__ bool proj_is_exp(const ProjOut& o, const int col) {
-    return o.mode == 2 || (o.mode == 1 && (col < H || (col >= 2 * H && col < 3 * H)));
+    return o.mode == 1 && col < 2 * H;
 }
 // edge projection -> 2^(log2e v), exponent clamped to [-63, 63] (gnnseg_fused.cu); a clamp raises the flag
 __device__ __forceinline__ void to_exponentials(float (&v)[16], int* __restrict__ flag) {
@@ -607,7 +607,7 @@ struct TcMlpCfg {
 template <int H, bool TMA>
 __global__ void __launch_bounds__(TcMlpCfg<H>::NT, 2)
 node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4, const float* h1,
-                   const int ld_h1, const int n_nodes, const int n_tiles, const ProjOut out, const int wp_off,
+                   const int ld_h1, const int n_nodes, const int n_tiles, const ProjOut out,
                    float* __restrict__ H_save,
                    const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
                    const __grid_constant__ CUtensorMap tmQ16) {
@@ -635,7 +635,7 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
     for (int i = tid * 4; i < 2 * H * H; i += NT * 4)                     // W4 hi, lo
         cp_async16(smem + C::O_W4H + i * 4, blob + B::TC_W4H + i);
     for (int i = tid * 4; i < 2 * NP * N::D4P; i += NT * 4)               // projection images hi, lo (either row order)
-        cp_async16(smem + C::O_WPH + i * 4, blob + wp_off + i);
+        cp_async16(smem + C::O_WPH + i * 4, blob + B::TC_WPH + i);
     for (int i = tid; i < H; i += NT) sB4[i] = __ldg(blob + B::B4 + i);
     if (tid == 0) {
         mbar_init(smem_u32(mbar), 1);
@@ -804,8 +804,7 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
                     return proj_ptr<H>(out, node_w0, col, ld);
                 };
                 const int n_full = write_q ? 2 : 1;                          // 32-column chunks hf, hf + 2 (P' only: chunk hf)
-                // state rows [SPs|Qi|SPd|Qo|Qs]: the two chunks of exponentials (0 and 2) go to different warps
-                auto chunk_of = [&](const int t) { return out.mode == 1 ? (t == 0 ? 2 * hf : 3 - 2 * hf) : hf + 2 * t; };
+                auto chunk_of = [&](const int t) { return hf + 2 * t; };
                 if constexpr (TMA) {
                     const uint32_t s_tile = smem_u32(sOut);
 #pragma unroll 1
@@ -927,7 +926,7 @@ struct Mlp64 {
 template <bool INPUT>
 __global__ void __launch_bounds__(Mlp64::NT, 1)
 node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, const float* h1, const int ld_h1,
-                     const int n_nodes, const int n_tiles, const ProjOut out, const int wp_off,
+                     const int n_nodes, const int n_tiles, const ProjOut out,
                      float* __restrict__ H_save, const float* __restrict__ Xraw, const int F) {
     using C = Mlp64;
     using B = Blob<64>;
@@ -975,8 +974,8 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, con
         auto load_wp_half = [&](const int hf, const int bar) {
             constexpr int HALF_FLOATS = C::WPH_BYTES / 4, IMG_FLOATS = C::NP * C::D4P;
             for (int i = lt * 4; i < HALF_FLOATS; i += LT * 4) {
-                cp_async16(smem + C::O_WP + i * 4, blob + wp_off + hf * HALF_FLOATS + i);
-                cp_async16(smem + C::O_WP + C::WPH_BYTES + i * 4, blob + wp_off + IMG_FLOATS + hf * HALF_FLOATS + i);
+                cp_async16(smem + C::O_WP + i * 4, blob + B::TC_WPH + hf * HALF_FLOATS + i);
+                cp_async16(smem + C::O_WP + C::WPH_BYTES + i * 4, blob + B::TC_WPH + IMG_FLOATS + hf * HALF_FLOATS + i);
             }
             cp_async_wait_all();
             fence_async_smem();
@@ -1196,7 +1195,7 @@ struct TcInCfg {
 template <int H>
 __global__ void __launch_bounds__(TcInCfg<H>::NT)
 input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, const int F, const int n_nodes,
-                const int n_tiles, float* __restrict__ X4, const ProjOut out, const int wp_off,
+                const int n_tiles, float* __restrict__ X4, const ProjOut out,
                 float* __restrict__ H_save) {
     using C = TcInCfg<H>;
     using N = TcCfg<H>;
@@ -1208,8 +1207,8 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::O_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::O_MBAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid * 4; i < 2 * NP * N::D4P; i += NT * 4)      // WP hi, WP lo: contiguous images (either row order)
-        cp_async16(smem + C::O_WPH + i * 4, blob + wp_off + i);
+    for (int i = tid * 4; i < 2 * NP * N::D4P; i += NT * 4)      // WP hi, WP lo: contiguous images
+        cp_async16(smem + C::O_WPH + i * 4, blob + B::TC_WPH + i);
     for (int i = tid; i < 5 * H; i += NT) sWin[i] = __ldg(blob + B::WIN + i);      // Win and bin are contiguous
     if (tid == 0) {
         mbar_init(smem_u32(mbar), 1);
@@ -1302,14 +1301,14 @@ input_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X, con
     }
 }
 
-int launch_input_tc32_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, bool state_order,
-                         float* H_save, cudaStream_t st);
+int launch_input_tc32_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, float* H_save,
+                         cudaStream_t st);
 int launch_input_tc32(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q,
                       float* H_save, cudaStream_t st) {
-    return launch_input_tc32_ex(blob, X, n_nodes, F, X4, ProjOut{P, Q, 0, 160, nullptr}, false, H_save, st);
+    return launch_input_tc32_ex(blob, X, n_nodes, F, X4, ProjOut{P, Q, 0, 160, nullptr}, H_save, st);
 }
-int launch_input_tc32_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, bool state_order,
-                         float* H_save, cudaStream_t st) {
+int launch_input_tc32_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, float* H_save,
+                         cudaStream_t st) {
     using C = TcInCfg<32>;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + TcCfg<32>::TM - 1) / TcCfg<32>::TM;
@@ -1318,8 +1317,7 @@ int launch_input_tc32_ex(const float* blob, const float* X, int n_nodes, int F, 
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int cap = 2 * sms;     // 256 TMEM columns and ~95 KB of shared memory per CTA: two CTAs per SM
     const int grid = n_tiles < cap ? n_tiles : cap;
-    input_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, out,
-                                                            state_order ? Blob<32>::TC_WSH : Blob<32>::TC_WPH, H_save);
+    input_kernel_tc<32><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X, F, n_nodes, n_tiles, X4, out, H_save);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
@@ -1351,18 +1349,16 @@ static bool make_store_map(CUtensorMap* tm, float* base, int rows, int cols, int
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// `out` says where the projections go; state_order picks the projection image whose rows are in state-row order
+// `out` says where the projections go
 int launch_node_mlp_tc32_ex(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, const ProjOut& out,
-                            bool state_order, float* H_save, bool pdl, cudaStream_t st) {
+                            float* H_save, bool pdl, cudaStream_t st) {
     using C = TcMlpCfg<32>;
-    using B = Blob<32>;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
     constexpr int SMEM = C::SMEM_BYTES + 1024;                      // room to align the store tiles to 1024 bytes
     const int sms = cached_sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;        // two CTAs per SM
-    const int wp_off = state_order ? B::TC_WSH : B::TC_WPH;
     static const bool tma_env = [] { const char* v = std::getenv("GNNSEG_MLP_STORE"); return v && v[0] == 't'; }();
     const bool tma = tma_env && out.mode == 0;
     CUtensorMap tmP, tmQ, tmQ16;
@@ -1373,21 +1369,20 @@ int launch_node_mlp_tc32_ex(const float* blob, const float* X4, const float* h1,
         if (write_q && (!make_store_map(&tmQ, out.q, n_nodes, 96, 32, true) || !make_store_map(&tmQ16, out.q, n_nodes, 96, 16, false)))
             return GNNSEG_ECUDA;
         if (!ensure_dynamic_smem<node_mlp_kernel_tc<32, true>>(SMEM)) return GNNSEG_ECUDA;
-        if (launch_pdl(node_mlp_kernel_tc<32, true>, grid, C::NT, SMEM, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, out, wp_off,
+        if (launch_pdl(node_mlp_kernel_tc<32, true>, grid, C::NT, SMEM, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, out,
                        H_save, tmP, tmQ, tmQ16) != cudaSuccess)
             return GNNSEG_ECUDA;
         return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
     }
     if (!ensure_dynamic_smem<node_mlp_kernel_tc<32, false>>(SMEM)) return GNNSEG_ECUDA;
-    if (launch_pdl(node_mlp_kernel_tc<32, false>, grid, C::NT, SMEM, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, out, wp_off,
+    if (launch_pdl(node_mlp_kernel_tc<32, false>, grid, C::NT, SMEM, st, pdl, blob, X4, h1, ld_h1, n_nodes, n_tiles, out,
                    H_save, tmP, tmQ, tmQ16) != cudaSuccess)
         return GNNSEG_ECUDA;
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 int launch_node_mlp_tc32(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
                          float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st) {
-    return launch_node_mlp_tc32_ex(blob, X4, h1, ld_h1, n_nodes, ProjOut{P_out, Q_out, 0, write_q ? 160 : 64, nullptr}, false, H_save,
-                                   pdl, st);
+    return launch_node_mlp_tc32_ex(blob, X4, h1, ld_h1, n_nodes, ProjOut{P_out, Q_out, 0, write_q ? 160 : 64, nullptr}, H_save, pdl, st);
 }
 
 #ifdef GNNSEG_TRACE
@@ -1400,7 +1395,7 @@ extern "C" int gnnseg_debug_read_cta(unsigned long long* out) {
 #endif
 
 int launch_node_mlp_tc64_ex(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, const ProjOut& out,
-                            bool state_order, float* H_save, bool pdl, cudaStream_t st) {
+                            float* H_save, bool pdl, cudaStream_t st) {
     using C = Mlp64;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
@@ -1408,26 +1403,24 @@ int launch_node_mlp_tc64_ex(const float* blob, const float* X4, const float* h1,
     const int sms = cached_sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    const int wp_off = state_order ? Blob<64>::TC_WSH : Blob<64>::TC_WPH;
     if (launch_pdl(node_mlp_kernel_tc64<false>, grid, C::NT, C::SMEM_BYTES, st, pdl, blob, const_cast<float*>(X4), h1, ld_h1, n_nodes,
-                   n_tiles, out, wp_off, H_save, (const float*)nullptr, 0) != cudaSuccess)
+                   n_tiles, out, H_save, (const float*)nullptr, 0) != cudaSuccess)
         return GNNSEG_ECUDA;
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 int launch_node_mlp_tc64(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, float* P_out,
                          float* Q_out, int write_q, float* H_save, bool pdl, cudaStream_t st) {
-    return launch_node_mlp_tc64_ex(blob, X4, h1, ld_h1, n_nodes, ProjOut{P_out, Q_out, 0, write_q ? 320 : 128, nullptr}, false, H_save,
-                                   pdl, st);
+    return launch_node_mlp_tc64_ex(blob, X4, h1, ld_h1, n_nodes, ProjOut{P_out, Q_out, 0, write_q ? 320 : 128, nullptr}, H_save, pdl, st);
 }
 
-int launch_input_tc64_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, bool state_order,
-                         float* H_save, cudaStream_t st);
+int launch_input_tc64_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, float* H_save,
+                         cudaStream_t st);
 int launch_input_tc64(const float* blob, const float* X, int n_nodes, int F, float* X4, float* P, float* Q, float* H_save,
                       cudaStream_t st) {
-    return launch_input_tc64_ex(blob, X, n_nodes, F, X4, ProjOut{P, Q, 0, 320, nullptr}, false, H_save, st);
+    return launch_input_tc64_ex(blob, X, n_nodes, F, X4, ProjOut{P, Q, 0, 320, nullptr}, H_save, st);
 }
-int launch_input_tc64_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, bool state_order,
-                         float* H_save, cudaStream_t st) {
+int launch_input_tc64_ex(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, float* H_save,
+                         cudaStream_t st) {
     using C = Mlp64;
     if (n_nodes == 0) return GNNSEG_OK;
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
@@ -1436,8 +1429,7 @@ int launch_input_tc64_ex(const float* blob, const float* X, int n_nodes, int F, 
     if (sms < 1) return GNNSEG_ENODEVICE;
     const int grid = n_tiles < sms ? n_tiles : sms;
     // the first kernel of a forward: launched fully serialised (it reads the blob the pack kernels wrote)
-    node_mlp_kernel_tc64<true><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X4, nullptr, 0, n_nodes, n_tiles, out,
-                                                                   state_order ? Blob<64>::TC_WSH : Blob<64>::TC_WPH, H_save, X, F);
+    node_mlp_kernel_tc64<true><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X4, nullptr, 0, n_nodes, n_tiles, out, H_save, X, F);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 

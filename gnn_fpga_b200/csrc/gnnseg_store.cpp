@@ -169,6 +169,7 @@ extern "C" int gnnseg_store_plan_host(int n_events, int F, const int64_t* n_node
     L->o_out_col = take((int64_t)L->col_bytes * to);
     L->o_y = take(4 * ty);
     L->o_perm = take(4 * tn);
+    L->o_n_edges = take(8 * (int64_t)n_events);
     L->bytes = off;
     return GNNSEG_OK;
 }
@@ -190,8 +191,10 @@ extern "C" int gnnseg_store_fill_host(const GnnsegStoreLayout* L, const float* c
     int64_t* in_off = reinterpret_cast<int64_t*>(arena + L->o_in_off);
     int64_t* out_off = reinterpret_cast<int64_t*>(arena + L->o_out_off);
     int64_t* y_off = reinterpret_cast<int64_t*>(arena + L->o_y_off);
+    int64_t* n_edges_arena = reinterpret_cast<int64_t*>(arena + L->o_n_edges);
     node_off[0] = in_off[0] = out_off[0] = y_off[0] = 0;
     for (int b = 0; b < B; ++b) {
+        n_edges_arena[b] = n_edges_host ? n_edges_host[b] : n_in_host[b];
         node_off[b + 1] = node_off[b] + n_nodes_host[b];
         in_off[b + 1] = in_off[b] + n_in_host[b];
         out_off[b + 1] = out_off[b] + n_out_host[b];

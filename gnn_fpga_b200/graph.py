@@ -173,7 +173,7 @@ class DeviceGraphBatch:
             self.scores = torch.empty(self.n_slots, dtype=torch.float32, device=dev)
         else:                          # arrays assembled elsewhere (from_store): no CSR build here
             for k in ("in_ptr", "in_eid", "in_nbr", "in_pos", "out_ptr", "out_eid", "out_nbr", "out_pos", "scores", "adj_ptr", "adj",
-                      "status"):
+                      "node_order", "status"):
                 setattr(self, k, _prebuilt[k])
             self._ws = _prebuilt.get("ws", self._ws)
             self._set_struct()
@@ -202,19 +202,24 @@ class DeviceGraphBatch:
         """GnnsegGraph over the arrays; builds the combined adjacency list of the fused inference path
         (gnnseg_build_adjacency: one launch on the current stream) if the arrays for it are there."""
         dev = self.device
-        if getattr(self, "adj_ptr", None) is None:
+        L = _lib.lib()
+        built = getattr(self, "adj_ptr", None) is not None        # arrays assembled elsewhere (gnnseg_store_load_batch)
+        if not built:
             self.adj_ptr = torch.empty(self.n_nodes + 1, dtype=torch.int32, device=dev)
-            self.adj = torch.empty(max(2 * self.n_slots, 1), dtype=torch.int32, device=dev)
+            self.adj = torch.empty(L.gnnseg_adjacency_entries(self.n_nodes, self.n_slots), dtype=torch.int32, device=dev)
+            self.node_order = torch.empty(max(self.n_nodes, 1), dtype=torch.int32, device=dev)
         if getattr(self, "status", None) is None:
             self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         self.struct = _lib.GnnsegGraph(
             self.n_nodes, self.n_slots, self.src.data_ptr(), self.dst.data_ptr(),
             self.in_ptr.data_ptr(), self.in_eid.data_ptr(), self.in_nbr.data_ptr(),
             self.out_ptr.data_ptr(), self.out_eid.data_ptr(), self.out_nbr.data_ptr(),
-            self.in_pos.data_ptr(), self.out_pos.data_ptr(), self.adj_ptr.data_ptr(), self.adj.data_ptr())
-        with torch.cuda.device(dev):
-            _lib.check(_lib.lib().gnnseg_build_adjacency(C.byref(self.struct), _ptr(self.adj_ptr), _ptr(self.adj), _stream_ptr(dev)),
-                       "gnnseg_build_adjacency")
+            self.in_pos.data_ptr(), self.out_pos.data_ptr(), self.adj_ptr.data_ptr(), self.adj.data_ptr(),
+            self.node_order.data_ptr())
+        if not built:
+            with torch.cuda.device(dev):
+                _lib.check(L.gnnseg_build_adjacency(C.byref(self.struct), _ptr(self.adj_ptr), _ptr(self.adj), _ptr(self.node_order),
+                                                    _stream_ptr(dev)), "gnnseg_build_adjacency")
 
     @classmethod
     def from_dense(cls, X, Ri, Ro, validate=True):
@@ -287,33 +292,21 @@ class DeviceGraphBatch:
         if bufs is None:
             bufs = DeviceBatchBuffers(dev, n, n_in, n_out, B * e_max, B, store.F, store.col_bytes)
         v = bufs.views(n, n_in, n_out, B * e_max, B)
-        bufs.meta_host[:meta.shape[0]] = torch.from_numpy(meta)
         compute = torch.cuda.current_stream(dev)
         cs = copy_stream if copy_stream is not None else compute
-        with torch.cuda.stream(cs):
-            v["meta"].copy_(bufs.meta_host[:meta.shape[0]], non_blocking=True)
-            for dst_t, src_t in zip((v["X"], v["in_ptr_l"], v["out_ptr_l"], v["in_col"], v["out_col"]), store.slices(lo, hi)):
-                if src_t.numel():
-                    dst_t.copy_(src_t, non_blocking=True)
-            if cs is not compute:
-                ev = torch.cuda.Event()
-                ev.record(cs)
-                compute.wait_event(ev)
-        L = _lib.lib()
         with torch.cuda.device(dev):
-            _lib.check(L.gnnseg_assemble_batch(_ptr(v["meta"]), B, n, e_max, n_in, n_out, _ptr(v["in_ptr_l"]), _ptr(v["out_ptr_l"]),
-                                               _ptr(v["in_col"]), _ptr(v["out_col"]), store.col_bytes, _ptr(v["src"]), _ptr(v["dst"]),
-                                               _ptr(v["in_ptr"]), _ptr(v["in_eid"]), _ptr(v["in_nbr"]), _ptr(v["in_pos"]),
-                                               _ptr(v["out_ptr"]), _ptr(v["out_eid"]), _ptr(v["out_nbr"]), _ptr(v["out_pos"]),
-                                               _stream_ptr(dev)), "gnnseg_assemble_batch")
+            # six asynchronous copies out of the pinned arena on `cs`, then batch assembly and adjacency on the current stream
+            _lib.check(_lib.lib().gnnseg_store_load_batch(C.byref(store.layout), store.arena.data_ptr(), lo, hi, C.byref(bufs.struct()),
+                                                          C.c_void_p(cs.cuda_stream), C.c_void_p(compute.cuda_stream), None),
+                       "gnnseg_store_load_batch")
         v["ws"] = bufs.ws
         batch = cls(v["X"], v["src"], v["dst"], B, e_max, n_nodes_per_event=np.diff(meta[:B + 1]).tolist(), _prebuilt=v)
         if store.order_column >= 0:
-            batch.node_perm = (store, lo, hi)      # resolved lazily by node_order(): only per-node outputs need it
+            batch.node_perm = (store, lo, hi)      # resolved lazily by original_node_ids(): only per-node outputs need it
         batch._bufs = bufs
         return batch
 
-    def node_order(self):
+    def original_node_ids(self):
         """None, or an int64 device tensor `orig` with orig[i] = original flattened node id of internal node i
         (batches from a store that renumbered its nodes; per-edge scores never need it)."""
         if self.node_perm is None:
@@ -393,10 +386,48 @@ class DeviceBatchBuffers:
             "in_eid": torch.empty(max(n_in, 1), **i32), "in_nbr": torch.empty(max(n_in, 1), **i32),
             "out_eid": torch.empty(max(n_out, 1), **i32), "out_nbr": torch.empty(max(n_out, 1), **i32),
             "scores": torch.empty(max(n_slots, 1), dtype=torch.float32, device=dev),
-            "adj_ptr": torch.empty(n_nodes + 1, **i32), "adj": torch.empty(max(n_in + n_out, 1), **i32),
+            "adj_ptr": torch.empty(n_nodes + 1, **i32),
+            "adj": torch.empty(_lib.lib().gnnseg_adjacency_entries(n_nodes, n_slots), **i32),
+            "node_order": torch.empty(max(n_nodes, 1), **i32),
             "status": torch.zeros(1, **i32),
         }
         self.ws = {}            # forward workspaces by hidden_dim, shared by the batches that pass through
+        self.scores_host = None     # pinned result buffers (predict_stream): set by with_host_results()
+        self.status_host = None
+        self._struct = None
+
+    def with_host_results(self):
+        """Pinned host buffers the scores and the range flag of a batch come back to (gnnseg_store_forward_batch)."""
+        if self.scores_host is None:
+            self.scores_host = torch.empty(max(self.cap[3], 1), dtype=torch.float32, pin_memory=True)
+            self.status_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+            self._struct = None
+        return self
+
+    def workspace(self, h):
+        """Forward workspace for the largest batch these buffers hold."""
+        if h not in self.ws:
+            nbytes = _lib.lib().gnnseg_forward_workspace_bytes(self.cap[0], self.cap[3], self.F, h)
+            if nbytes == 0:
+                _lib.check(-2, "gnnseg_forward_workspace_bytes(F=%d, h=%d)" % (self.F, h))
+            self.ws[h] = torch.empty(nbytes, dtype=torch.uint8, device=self.t["X"].device)
+            self._struct = None
+        return self.ws[h]
+
+    def struct(self, h=None):
+        """GnnsegBatchBuffers over the buffers (with the forward workspace for hidden_dim h when given)."""
+        key = h
+        if self._struct is None or self._struct[0] != key:
+            t = self.t
+            ws = self.workspace(h) if h is not None else None
+            p = lambda x: x.data_ptr() if x is not None else None
+            self._struct = (key, _lib.GnnsegBatchBuffers(
+                self.cap[0], self.cap[1], self.cap[2], self.cap[3], self.cap[4], 0,
+                p(t["meta"]), p(t["X"]), p(t["in_ptr_l"]), p(t["out_ptr_l"]), p(t["in_col"]), p(t["out_col"]), p(t["src"]), p(t["dst"]),
+                p(t["in_pos"]), p(t["out_pos"]), p(t["in_ptr"]), p(t["out_ptr"]), p(t["adj_ptr"]), p(t["in_eid"]), p(t["in_nbr"]),
+                p(t["out_eid"]), p(t["out_nbr"]), p(t["adj"]), p(t["node_order"]), p(t["scores"]), p(t["status"]), p(ws),
+                ws.numel() if ws is not None else 0, p(self.meta_host), p(self.scores_host), p(self.status_host)))
+        return self._struct[1]
 
     def fits(self, n_nodes, n_in, n_out, n_slots, B):
         return all(a <= b for a, b in zip((n_nodes, n_in, n_out, n_slots, B), self.cap))
@@ -410,7 +441,8 @@ class DeviceBatchBuffers:
                 "src": t["src"][:n_slots], "dst": t["dst"][:n_slots], "in_pos": t["in_pos"][:n_slots], "out_pos": t["out_pos"][:n_slots],
                 "in_ptr": t["in_ptr"][:n_nodes + 1], "out_ptr": t["out_ptr"][:n_nodes + 1], "in_eid": t["in_eid"][:n_in],
                 "in_nbr": t["in_nbr"][:n_in], "out_eid": t["out_eid"][:n_out], "out_nbr": t["out_nbr"][:n_out],
-                "scores": t["scores"][:n_slots], "adj_ptr": t["adj_ptr"][:n_nodes + 1], "adj": t["adj"], "status": t["status"]}
+                "scores": t["scores"][:n_slots], "adj_ptr": t["adj_ptr"][:n_nodes + 1], "adj": t["adj"],
+                "node_order": t["node_order"][:max(n_nodes, 1)], "status": t["status"]}
 
 
 def pack_npz_batch_host(filenames, pinned=None, n_threads=0):

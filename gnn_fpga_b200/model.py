@@ -241,7 +241,7 @@ class SegmentClassifier(nn.Module):
         from .store import StoreBatch
         dev = _require_cuda(self._device())
         depth = max(1, int(depth))
-        slots = [{"bufs": None, "out": None, "done": None, "view": None, "arena": None, "h2d": None} for _ in range(depth + 1)]
+        slots = [{"bufs": None, "done": None, "view": None, "flag": None, "arena": None, "h2d": None} for _ in range(depth + 1)]
         was_graph, self.use_cuda_graph = self.use_cuda_graph, False    # one-shot batches: plain launches
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))     # ranks sharing this host (torchrun)
         pack_threads = max(1, min(4, (os.cpu_count() or 4) // local_world - 2))
@@ -267,6 +267,14 @@ class SegmentClassifier(nn.Module):
         pool = ThreadPoolExecutor(max_workers=1)
         compute = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        L = _lib.lib()
+        h = self.hidden_dim
+        if L.gnnseg_supported(self.input_dim, h) == 0:
+            _lib.check(-2, "SegmentClassifier(input_dim=%d, hidden_dim=%d)" % (self.input_dim, h))
+        blob = self.pack_weights()                                # once: the weights do not change while the stream runs
+        flags = _lib.FWD_EXACT if self.exact else 0
+        import numpy as np
+        shape = np.zeros(4, dtype=np.int32)
         pending = deque()
         try:
             with torch.no_grad():
@@ -299,29 +307,33 @@ class SegmentClassifier(nn.Module):
                     if s["done"] is not None:
                         s["done"].synchronize()                   # the slot's previous batch has left the device buffers
                     store = sb.store
-                    _, n, e_max, n_in, n_out = store.batch_meta(sb.lo, sb.hi)
                     B = sb.hi - sb.lo
-                    if s["bufs"] is None or not s["bufs"].fits(n, n_in, n_out, B * e_max, B) or s["bufs"].F != store.F \
-                            or s["bufs"].col_bytes != store.col_bytes:
-                        g = lambda v: int(v * 1.25) + 1
-                        s["bufs"] = DeviceBatchBuffers(dev, g(n), g(n_in), g(n_out), g(B * e_max), B, store.F, store.col_bytes)
-                    batch = DeviceGraphBatch.from_store(store, sb.lo, sb.hi, dev, bufs=s["bufs"], copy_stream=s_in)
+                    while True:
+                        if s["bufs"] is None:
+                            L.gnnseg_store_batch_shape_host(C.byref(store.layout), store.arena.data_ptr(), sb.lo, sb.hi, shape.ctypes.data)
+                            n, e_max, n_in, n_out = (int(x) for x in shape)
+                            g = lambda v: int(v * 1.25) + 1
+                            s["bufs"] = DeviceBatchBuffers(dev, g(n), g(n_in), g(n_out), g(B * e_max), B, store.F,
+                                                           store.col_bytes).with_host_results()
+                        bufs = s["bufs"]
+                        rc = _lib.EWORKSPACE
+                        if bufs.F == store.F and bufs.col_bytes == store.col_bytes:
+                            torch.cuda.set_device(dev)
+                            rc = L.gnnseg_store_forward_batch(C.byref(store.layout), store.arena.data_ptr(), sb.lo, sb.hi, _ptr(blob), h,
+                                                              self.n_iters, flags, C.byref(bufs.struct(h)), C.c_void_p(s_in.cuda_stream),
+                                                              C.c_void_p(compute.cuda_stream), C.c_void_p(s_out.cuda_stream),
+                                                              shape.ctypes.data)
+                        if rc != _lib.EWORKSPACE:
+                            break
+                        s["bufs"] = None                          # the batch exceeds the slot's buffers: new ones, once
+                    _lib.check(rc, "gnnseg_store_forward_batch")
+                    e_max = int(shape[1])
                     s["h2d"] = torch.cuda.Event()
                     s["h2d"].record(s_in)
-                    scores = self._run(batch)
-                    if s["out"] is None or s["out"].numel() < scores.numel():
-                        s["out"] = torch.empty(int(scores.numel() * 1.25) + 1, dtype=torch.float32, pin_memory=True)
-                    s["view"] = s["out"][:scores.numel()].view(batch.B, batch.e_max)
-                    ev_c = torch.cuda.Event()
-                    ev_c.record(compute)
-                    s_out.wait_event(ev_c)
-                    if s.get("flag") is None:
-                        s["flag"] = torch.zeros(1, dtype=torch.int32, pin_memory=True)
-                    with torch.cuda.stream(s_out):
-                        s["view"].copy_(scores.view(batch.B, batch.e_max), non_blocking=True)
-                        s["flag"].copy_(batch.status, non_blocking=True)
-                        s["done"] = torch.cuda.Event()
-                        s["done"].record(s_out)
+                    s["done"] = torch.cuda.Event()
+                    s["done"].record(s_out)
+                    s["view"] = bufs.scores_host[:B * e_max].view(B, e_max)
+                    s["flag"] = bufs.status_host
                     pending.append(s)
                     i += 1
                 while pending:

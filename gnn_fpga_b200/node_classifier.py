@@ -99,7 +99,7 @@ class NodeClassifier(SegmentClassifier):
 def _original_order(batch, per_node):
     """Per-node values of a batch whose nodes were renumbered internally (GraphStore reorder) -> the
     order of the caller's X rows."""
-    order = batch.node_order()
+    order = batch.original_node_ids()
     if order is None:
         return per_node
     out = torch.empty_like(per_node)
@@ -135,8 +135,8 @@ class NodeClfFunction(torch.autograd.Function):
         model, batch = ctx.model, ctx.batch
         dev = batch.device
         dnode = grad_out.to(torch.float32).contiguous().view(-1)
-        if batch.node_order() is not None:
-            dnode = dnode[batch.node_order()].contiguous()
+        if batch.original_node_ids() is not None:
+            dnode = dnode[batch.original_node_ids()].contiguous()
         grads = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
         masks, keep = _mask_struct(model)
         gs = _lib.GnnsegGrads(*[g.data_ptr() for g in grads[:10]])

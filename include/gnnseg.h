@@ -90,9 +90,13 @@ typedef struct GnnsegGraph {
     const int32_t* out_pos;  /* [n_slots] position of the slot in out_eid, -1 if src[j] < 0 */
     /* combined adjacency of the fused inference path (gnnseg_build_adjacency); both NULL: the forward runs
      * the edge step and the node step as separate kernels */
-    const int32_t* adj_ptr;  /* [n_nodes+1] = in_ptr + out_ptr                                               */
-    const int32_t* adj;      /* [adj_ptr[n_nodes]] per node: in-edges (start node id), then out-edges (end
-                                node id | 0x80000000), ascending slot order; 0x7fffffff = absent neighbour  */
+    const int32_t* adj_ptr;    /* [n_nodes+1] = in_ptr + out_ptr                                             */
+    const int32_t* adj;        /* [gnnseg_adjacency_entries()] per node, starting at 4*ceil(adj_ptr[n]/4) + 4n: its
+                                  in-edges (start node id), then its out-edges (end node id | 0x80000000), ascending
+                                  slot order, padded to a multiple of four with n_nodes (= absent neighbour: the
+                                  extra row every state buffer of the fused path carries)                          */
+    const int32_t* node_order; /* [n_nodes] nullable: the order the fused kernels take the nodes in (inside every
+                                  window of 4096 nodes by decreasing length of the adjacency list)                 */
 } GnnsegGraph;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -146,10 +150,12 @@ int    gnnseg_build_graph(const int32_t* src, const int32_t* dst, int n_slots, i
 
 /*
  * The combined adjacency list the fused inference path walks: per node its in-edges then its out-edges
- * (see GnnsegGraph.adj).  adj_ptr[n_nodes+1], adj[in_ptr[n_nodes] + out_ptr[n_nodes]] (<= 2 * n_slots).
- * One launch, reads the two CSRs of `graph` (its adj_ptr / adj members are ignored).
+ * (see GnnsegGraph.adj).  adj_ptr[n_nodes+1], adj[gnnseg_adjacency_entries(n_nodes, n_slots)], node_order[n_nodes]
+ * (nullable).  Two launches, reads the two CSRs of `graph` (its adj_ptr / adj / node_order members are ignored).
  */
-int    gnnseg_build_adjacency(const GnnsegGraph* graph, int32_t* adj_ptr, int32_t* adj, void* stream);
+size_t gnnseg_adjacency_entries(int n_nodes, int n_slots);
+int    gnnseg_build_adjacency(const GnnsegGraph* graph, int32_t* adj_ptr, int32_t* adj, int32_t* node_order,
+                              void* stream);
 
 /* ---- forward: replaces SegmentClassifier.forward, gnn/model.py:140-156 ---------------- */
 
@@ -222,22 +228,26 @@ int gnnseg_node_mlp_step(const float* blob, const float* X4, const float* h1, in
 
 /*
  * The steps of the fused inference path on their own (per-kernel parity tests, per-kernel timing).
- * State rows S (n_nodes, 5h) = [SPs | Qi | SPd | Qo | Qs] with SPs = 2^(log2e Ps), SPd = 2^(log2e Pd);
- * "last" rows P (n_nodes, 2h) = [SPs | SPd] (what the final edge step reads).  hidden_dim 32 or 64.
- *   gnnseg_state_input_step : gnnseg_input_step writing state rows (mode 1) or last rows (mode 2)
+ * State rows S (n_nodes + 1, 5h) = [SPs | SPd | Qi | Qo | Qs] with SPs = 2^(log2e Ps), SPd = 2^(log2e Pd) and
+ * Qi, Qo, Qs as in gnnseg_input_step.  hidden_dim 32 or 64.  Row n_nodes is the caller's: what an absent
+ * neighbour reads.  All zeros while the buffer feeds gnnseg_fused_gather_step (such an entry then adds e * 0);
+ * exp(b1) in its first h columns for gnnseg_edge_final_step (the start-node projection of an absent start node,
+ * gnn/model.py:71-73 with a zero column of Ro).  The producing steps write rows 0 .. n_nodes-1 only.
+ *   gnnseg_state_input_step : gnnseg_input_step writing state rows; n_cols = 5h, or 2h: only [SPs | SPd]
  *   gnnseg_fused_gather_step: h1[n] = tanh(Qs[n] + sum_in e Qi[src] + sum_out e Qo[dst]) with the edge scores e
- *                             computed on the fly from SPs / SPd (gnn/model.py:69-81 inside :113-122)
- *   gnnseg_state_mlp_step   : gnnseg_node_mlp_step writing state rows (mode 1) or last rows (mode 2); h1 may
- *                             live in the first h floats of the rows it becomes (ld_h1 = 5h or 2h)
+ *                             computed on the fly from SPs / SPd (gnn/model.py:69-81 inside :113-122); walks
+ *                             graph->adj in graph->node_order
+ *   gnnseg_state_mlp_step   : gnnseg_node_mlp_step writing state rows (n_cols as above); h1 may live in the first h
+ *                             floats of the rows it becomes (ld_h1 = 5h)
  *   gnnseg_edge_final_step  : scores per slot from rows of `ld` floats holding SPs at column off_s and SPd at
- *                             column off_d (walks the destination-CSR, then the slots without an end node)
+ *                             column off_d (the in-edges of every node, then the slots without an end node)
  */
 int gnnseg_state_input_step(const float* blob, const float* X, int n_nodes, int F, int h, float* X4,
-                            float* out, int mode, int32_t* status, void* stream);
+                            float* S, int n_cols, int32_t* status, void* stream);
 int gnnseg_fused_gather_step(const float* blob, const GnnsegGraph* graph, const float* S, int h,
                              float* h1, int ld_h1, void* stream);
 int gnnseg_state_mlp_step(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes,
-                          int h, float* out, int mode, int32_t* status, void* stream);
+                          int h, float* S, int n_cols, int32_t* status, void* stream);
 int gnnseg_edge_final_step(const float* blob, const GnnsegGraph* graph, const float* P, int ld,
                            int off_s, int off_d, int h, float* scores, void* stream);
 
@@ -366,6 +376,7 @@ int gnnseg_pack_sparse_batch_host(int B, int F, int e_max,
  *   out_col  uint16|int32 [total_out]  Ro_cols in CSR order
  *   y        float32 [total_y]         labels by edge column
  *   perm     int32 [total_nodes]       internal position -> node id within the event
+ *   n_edges  int64 [n_events]          edge columns of every event (see n_edges_host)
  * Index arrays may come in any order; np.nonzero order (gnn/graph.py:23-26) is the fast case.
  * reorder: 0 keeps the node order; 1 renumbers the nodes of every event internally along the feature
  * column in which edges are most local (the forward's gathers then hit in L1; scores, being per edge
@@ -384,6 +395,7 @@ typedef struct GnnsegStoreLayout {
     int64_t o_node_off;  int64_t o_in_off;    int64_t o_out_off;  int64_t o_y_off;
     int64_t o_X;         int64_t o_in_ptr;    int64_t o_out_ptr;
     int64_t o_in_col;    int64_t o_out_col;   int64_t o_y;        int64_t o_perm;
+    int64_t o_n_edges;   /* int64 [n_events]: edge columns of every event */
     int64_t bytes;       /* size of the arena */
 } GnnsegStoreLayout;
 int gnnseg_store_plan_host(int n_events, int F, const int64_t* n_nodes_host, const int64_t* n_in_host,
@@ -414,6 +426,52 @@ int gnnseg_assemble_batch(const int32_t* meta, int B, int n_nodes, int e_max, in
                           int32_t* in_ptr, int32_t* in_eid, int32_t* in_nbr, int32_t* in_pos,
                           int32_t* out_ptr, int32_t* out_eid, int32_t* out_nbr, int32_t* out_pos,
                           void* stream);
+
+/*
+ * One batch of a store through the device in one call: the per-batch driver of pipelined inference
+ * (replaces per batch the reference's generator + model call + .cpu(), gnn/trainSegmentClassifier.py:97-111,
+ * gnn/estimator.py:137-146).  GnnsegBatchBuffers holds one pipeline slot: device buffers of the given capacities
+ * (elements) and the pinned host words the results come back to; everything caller-allocated.
+ *   gnnseg_store_batch_shape_host  shape_host[4] = n_nodes, e_max, n_in, n_out of events [lo, hi)   (pure CPU)
+ *   gnnseg_store_load_batch        copy stream: six cudaMemcpyAsync out of the arena (batch metadata + five contiguous
+ *                                  slices); compute stream: waits for them, gnnseg_assemble_batch + gnnseg_build_adjacency
+ *   gnnseg_store_forward_batch     the same, then gnnseg_forward_ex on the compute stream (blob from gnnseg_pack_weights,
+ *                                  flags as gnnseg_forward_ex) and, on the out stream after it, scores -> scores_host and
+ *                                  the range flag -> status_host (either may be NULL: the result stays on the device)
+ * GNNSEG_EWORKSPACE (with shape_host filled) when the batch exceeds a capacity.  No host synchronisation, no library
+ * state: the events ordering the three streams live inside the call; the caller records its own event on the out
+ * stream afterwards to learn when the slot may be reused.
+ */
+typedef struct GnnsegBatchBuffers {
+    int32_t  cap_nodes, cap_in, cap_out, cap_slots, cap_events, reserved_;
+    int32_t* meta;            /* [3 * (cap_events + 1)]                                  */
+    float*   X;               /* [cap_nodes * F]                                         */
+    int32_t* in_ptr_local;    /* [cap_nodes + cap_events]                                */
+    int32_t* out_ptr_local;   /* [cap_nodes + cap_events]                                */
+    void*    in_col;          /* [cap_in]  uint16 / int32 (layout->col_bytes)            */
+    void*    out_col;         /* [cap_out]                                               */
+    int32_t* src;  int32_t* dst;  int32_t* in_pos;  int32_t* out_pos;     /* [cap_slots]      */
+    int32_t* in_ptr;  int32_t* out_ptr;  int32_t* adj_ptr;                /* [cap_nodes + 1]  */
+    int32_t* in_eid;  int32_t* in_nbr;                                    /* [cap_in]         */
+    int32_t* out_eid; int32_t* out_nbr;                                   /* [cap_out]        */
+    int32_t* adj;             /* [gnnseg_adjacency_entries(cap_nodes, cap_slots)]        */
+    int32_t* node_order;      /* [cap_nodes]                                             */
+    float*   scores;          /* [cap_slots]                                             */
+    int32_t* status;          /* [1] range flag of gnnseg_forward_ex                     */
+    void*    ws;  size_t ws_bytes;   /* gnnseg_forward_workspace_bytes(cap_nodes, cap_slots, F, h) */
+    int32_t* meta_host;       /* pinned [3 * (cap_events + 1)]                           */
+    float*   scores_host;     /* pinned [cap_slots] or NULL                              */
+    int32_t* status_host;     /* pinned [1] or NULL                                      */
+} GnnsegBatchBuffers;
+int gnnseg_store_batch_shape_host(const GnnsegStoreLayout* layout, const void* arena_host, int lo, int hi,
+                                  int32_t* shape_host);
+int gnnseg_store_load_batch(const GnnsegStoreLayout* layout, const void* arena_host, int lo, int hi,
+                            const GnnsegBatchBuffers* bufs, void* copy_stream, void* compute_stream,
+                            int32_t* shape_host);
+int gnnseg_store_forward_batch(const GnnsegStoreLayout* layout, const void* arena_host, int lo, int hi,
+                               const float* blob, int h, int n_iters, int flags,
+                               const GnnsegBatchBuffers* bufs, void* copy_stream, void* compute_stream,
+                               void* out_stream, int32_t* shape_host);
 
 /* ---- segment construction: replaces construct_graph / select_segments, gnn/graph.py:44-142 --- */
 

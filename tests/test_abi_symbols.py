@@ -39,13 +39,14 @@ def test_host_only_queries():
         assert L.gnnseg_supported(F, h) == 0
         assert L.gnnseg_weights_floats(F, h) == 0
     # blob size: Win^T[4][h] + b_in + WP^T[(h+4)][5h] + bias[5h] + W2 + 4 + W4^T + b4
-    #            + tf32 hi/lo operand images of W4 [h][h] and of WP [5h][40] in both row orders
+    #            + tf32 hi/lo operand images of W4 [h][h] and of WP [5h][40]
     #            + the fused path's edge constants (-2 w2, b2 + sum w2, 2^(log2e b1))
     h = 32
     assert L.gnnseg_weights_floats(3, h) == (4 * h + h + (h + 4) * 5 * h + 5 * h + h + 4 + h * h + h
-                                             + 2 * h * h + 4 * 5 * h * 40 + 2 * h + 4)
-    # workspace: X4 + P + max(2 Q + 2 e, 2 state rows of 5h + status)
-    assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 32) >= 4 * (1000 * 4 + 1000 * 64 + 2 * 1000 * 160)
+                                             + 2 * h * h + 2 * 5 * h * 40 + 2 * h + 4)
+    # workspace: X4 + P + max(2 Q + 2 e, 2 x (n + 1) state rows of 5h + status)
+    assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 32) >= 4 * (1000 * 4 + 1000 * 64 + 2 * 1001 * 160)
+    assert L.gnnseg_adjacency_entries(1000, 5000) >= 2 * 5000 + 4 * 1000
     assert L.gnnseg_forward_workspace_bytes(10, 5000, 3, 8) >= 4 * (10 * 4 + 10 * 16 + 2 * 10 * 24 + 2 * 5000)
     assert L.gnnseg_forward_workspace_bytes(1000, 5000, 3, 12) == 0
     assert L.gnnseg_csr_workspace_bytes(1000, 5000) >= 8 * 1001
@@ -62,12 +63,15 @@ def test_argument_errors_without_device_work():
     assert L.gnnseg_build_csr(None, None, 5, 5, None, None, None, None, None, 0, None) == -1
     # the fused inference path and the event store
     assert L.gnnseg_forward_ex(None, None, None, 3, 32, 1, None, None, 0, 0, None, None) == -1
-    assert L.gnnseg_build_adjacency(None, None, None, None) == -1
+    assert L.gnnseg_build_adjacency(None, None, None, None, None) == -1
+    assert L.gnnseg_store_batch_shape_host(None, None, 0, 1, None) == -1
+    assert L.gnnseg_store_load_batch(None, None, 0, 1, None, None, None, None) == -1
+    assert L.gnnseg_store_forward_batch(None, None, 0, 1, None, 32, 1, 0, None, None, None, None, None) == -1
     assert L.gnnseg_fused_gather_step(None, None, None, 16, None, 16, None) == -2       # hidden_dim 32 / 64 only
     assert L.gnnseg_fused_gather_step(None, None, None, 32, None, 32, None) == -1
     assert L.gnnseg_edge_final_step(None, None, None, 64, 0, 32, 32, None, None) == -1
-    assert L.gnnseg_state_input_step(None, None, 10, 3, 32, None, None, 3, None, None) == -1      # mode 1 or 2
-    assert L.gnnseg_state_mlp_step(None, None, None, 32, 10, 8, None, 1, None, None) == -2
+    assert L.gnnseg_state_input_step(None, None, 10, 3, 32, None, None, 100, None, None) == -1    # n_cols: 5h or 2h
+    assert L.gnnseg_state_mlp_step(None, None, None, 32, 10, 8, None, 40, None, None) == -2
     assert L.gnnseg_assemble_batch(None, 2, 10, 5, 3, 3, None, None, None, None, 3, None, None, None, None, None, None,
                                    None, None, None, None, None) == -1                             # col_bytes 2 or 4
     assert L.gnnseg_store_plan_host(1, 0, None, None, None, None, None, None) == -1

@@ -1,8 +1,8 @@
 """The fused inference path (gnnseg_fused.cu, hidden_dim 32 / 64), one kernel at a time against the oracle,
 then the whole forward against the step-by-step kernels and the reference goldens.
 
-State rows S (n, 5h) = [SPs | Qi | SPd | Qo | Qs], SPs = exp(Ps) (= 2^(log2e Ps)), SPd = exp(Pd); last rows
-P (n, 2h) = [SPs | SPd] (include/gnnseg.h).  Reference: gnn/model.py:69-81 (edge), :113-125 (node), :140-156.
+State rows S (n + 1, 5h) = [SPs | SPd | Qi | Qo | Qs], SPs = exp(Ps) (= 2^(log2e Ps)), SPd = exp(Pd); row n is what an
+absent neighbour reads (include/gnnseg.h).  Reference: gnn/model.py:69-81 (edge), :113-125 (node), :140-156.
 """
 import ctypes as C
 
@@ -19,10 +19,15 @@ TOL = 1e-5
 CASES = ["acts_ragged_h32_it4", "acts_h64_it6", "acts_masked_h32_it4"]
 
 
-def state_rows(P, Q, h):
-    """Oracle projections -> state rows, exponentials taken in fp64."""
+def state_rows(P, Q, h, extra=None):
+    """Oracle projections -> n + 1 state rows, exponentials taken in fp64; the extra row is zeros, or `extra` (h floats:
+    the start-node projection an absent start node reads in the final edge step) in its first h columns."""
     sp = torch.exp(P.double()).float()
-    return torch.cat([sp[:, :h], Q[:, :h], sp[:, h:], Q[:, h:2 * h], Q[:, 2 * h:]], dim=1).contiguous()
+    S = torch.cat([sp, Q], dim=1)
+    last = torch.zeros(1, 5 * h)
+    if extra is not None:
+        last[0, :h] = extra
+    return torch.cat([S, last], dim=0).contiguous()
 
 
 def h1_oracle(p, H0, e, src, dst):
@@ -45,8 +50,8 @@ def test_fused_steps_against_oracle(name, cuda_device):
     src, dst, Xh = batch.src.cpu().long(), batch.dst.cpu().long(), batch.X.cpu()
     status = torch.zeros(1, dtype=torch.int32, device=cuda_device)
     X4 = torch.full((n, 4), 7.0, device=cuda_device)
-    S = torch.zeros(n, 5 * h, device=cuda_device)
-    rc = L.gnnseg_state_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(X4), _ptr(S), 1, _ptr(status), st)
+    S = torch.zeros(n + 1, 5 * h, device=cuda_device)
+    rc = L.gnnseg_state_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(X4), _ptr(S), 5 * h, _ptr(status), st)
     if h not in (32, 64):
         assert rc == -2 and L.gnnseg_fused_gather_step(_ptr(blob), C.byref(batch.struct), _ptr(S), h, _ptr(S), 5 * h, st) == -2
         return
@@ -56,10 +61,11 @@ def test_fused_steps_against_oracle(name, cuda_device):
     Pref, Qref = O.projections(p, H0)
     Sref = state_rows(Pref, Qref, h)
     assert torch.equal(X4.cpu()[:, :F], Xh) and torch.all(X4.cpu()[:, F:] == 0)
-    assert torch.allclose(S.cpu(), Sref, rtol=1e-5, atol=3e-6)
-    P2 = torch.zeros(n, 2 * h, device=cuda_device)
-    assert L.gnnseg_state_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(X4), _ptr(P2), 2, _ptr(status), st) == 0
-    assert torch.allclose(P2.cpu(), torch.exp(Pref.double()).float(), rtol=1e-5, atol=3e-6)
+    assert torch.allclose(S.cpu(), Sref, rtol=1e-5, atol=3e-6) and torch.all(S[n] == 0)
+    S2 = torch.full((n + 1, 5 * h), 9.0, device=cuda_device)
+    assert L.gnnseg_state_input_step(_ptr(blob), _ptr(batch.X), n, F, h, _ptr(X4), _ptr(S2), 2 * h, _ptr(status), st) == 0
+    assert torch.allclose(S2.cpu()[:n, :2 * h], Sref[:n, :2 * h], rtol=1e-5, atol=3e-6)
+    assert torch.all(S2[:, 2 * h:] == 9.0) and torch.all(S2[n] == 9.0)       # only the edge projections of the real rows
     # ---- fused edge + gather on the oracle's state rows: h1, in its own buffer and inside wider rows
     e_ref = O.sparse_edge(p, H0, src, dst)
     h1_ref = h1_oracle(p, H0, e_ref, src, dst)
@@ -69,38 +75,37 @@ def test_fused_steps_against_oracle(name, cuda_device):
         assert L.gnnseg_fused_gather_step(_ptr(blob), C.byref(batch.struct), _ptr(Sd), h, _ptr(h1), ld, st) == 0
         assert torch.allclose(h1.cpu()[:, :h], h1_ref, rtol=1e-5, atol=3e-6)
         assert torch.all(h1[:, h:] == 9.0)
-    # ---- tensor-core MLP writing state rows (mode 1) and last rows (mode 2); h1 inside the rows it becomes
+    # ---- tensor-core MLP writing state rows; h1 inside the rows it becomes
     H1 = torch.cat([torch.tanh(O._lin(h1_ref, p, 4)), Xh], dim=1)
     P1ref, Q1ref = O.projections(p, H1)
     S1ref = state_rows(P1ref, Q1ref, h)
     h1d = h1_ref.to(cuda_device).contiguous()
-    S1 = torch.zeros(n, 5 * h, device=cuda_device)
-    assert L.gnnseg_state_mlp_step(_ptr(blob), _ptr(X4), _ptr(h1d), h, n, h, _ptr(S1), 1, _ptr(status), st) == 0
+    S1 = torch.zeros(n + 1, 5 * h, device=cuda_device)
+    assert L.gnnseg_state_mlp_step(_ptr(blob), _ptr(X4), _ptr(h1d), h, n, h, _ptr(S1), 5 * h, _ptr(status), st) == 0
     assert torch.allclose(S1.cpu(), S1ref, rtol=1e-5, atol=4e-6)
-    S1b = torch.zeros(n, 5 * h, device=cuda_device)
-    S1b[:, :h] = h1d
-    assert L.gnnseg_state_mlp_step(_ptr(blob), _ptr(X4), _ptr(S1b), 5 * h, n, h, _ptr(S1b), 1, _ptr(status), st) == 0
+    S1b = torch.zeros(n + 1, 5 * h, device=cuda_device)
+    S1b[:n, :h] = h1d
+    assert L.gnnseg_state_mlp_step(_ptr(blob), _ptr(X4), _ptr(S1b), 5 * h, n, h, _ptr(S1b), 5 * h, _ptr(status), st) == 0
     assert torch.equal(S1b, S1)
-    Pl = torch.zeros(n, 2 * h, device=cuda_device)
-    Pl[:, :h] = h1d
-    assert L.gnnseg_state_mlp_step(_ptr(blob), _ptr(X4), _ptr(Pl), 2 * h, n, h, _ptr(Pl), 2, _ptr(status), st) == 0
-    assert torch.allclose(Pl.cpu(), torch.exp(P1ref.double()).float(), rtol=1e-5, atol=4e-6)
-    # ---- final edge step from last rows and from state rows (same numbers, other strides)
+    S1c = torch.zeros(n + 1, 5 * h, device=cuda_device)                      # last step: only [SPs | SPd]
+    S1c[:n, :h] = h1d
+    assert L.gnnseg_state_mlp_step(_ptr(blob), _ptr(X4), _ptr(S1c), 5 * h, n, h, _ptr(S1c), 2 * h, _ptr(status), st) == 0
+    assert torch.equal(S1c[:, :2 * h], S1[:, :2 * h]) and torch.all(S1c[:, 2 * h:] == 0)
+    # ---- final edge step; an absent start node reads exp(b1) from the extra row
     e1_ref = O.sparse_edge(p, H1, src, dst)
-    Pd = torch.exp(P1ref.double()).float().to(cuda_device).contiguous()
+    b1 = p[O.PARAM_KEYS[3]]
+    S1d = state_rows(P1ref, Q1ref, h, extra=torch.exp(b1.double()).float()).to(cuda_device)
     sc = torch.full((batch.n_slots,), -1.0, device=cuda_device)
-    assert L.gnnseg_edge_final_step(_ptr(blob), C.byref(batch.struct), _ptr(Pd), 2 * h, 0, h, h, _ptr(sc), st) == 0
+    assert L.gnnseg_edge_final_step(_ptr(blob), C.byref(batch.struct), _ptr(S1d), 5 * h, 0, h, h, _ptr(sc), st) == 0
     assert rel_err(sc.cpu().numpy(), e1_ref.numpy()) <= TOL
-    sc2 = torch.full((batch.n_slots,), -1.0, device=cuda_device)
-    S1d = S1ref.to(cuda_device)
-    assert L.gnnseg_edge_final_step(_ptr(blob), C.byref(batch.struct), _ptr(S1d), 5 * h, 0, 2 * h, h, _ptr(sc2), st) == 0
-    assert torch.equal(sc2, sc)
     assert int(status.item()) == 0
 
 
 def test_adjacency_is_in_edges_then_out_edges(cuda_device):
-    """gnnseg_build_adjacency: adj_ptr = in_ptr + out_ptr; per node the start nodes of its in-edges, then the end
-    nodes of its out-edges with bit 31 set, in ascending slot order; absent neighbours are 0x7fffffff."""
+    """gnnseg_build_adjacency: adj_ptr = in_ptr + out_ptr; the list of node v starts at 4*ceil(adj_ptr[v]/4) + 4v and holds
+    the start nodes of its in-edges, then the end nodes of its out-edges with bit 31 set, in ascending slot order, padded
+    to a multiple of four with n_nodes (which also stands for an absent neighbour); node_order lists every window's
+    nodes by decreasing number of four-entry batches."""
     rec = load_case("half_edges_h8_it2")
     _, batch, _ = _steps_setup(rec, cuda_device)
     n = batch.n_nodes
@@ -109,12 +114,19 @@ def test_adjacency_is_in_edges_then_out_edges(cuda_device):
     ap, adj = batch.adj_ptr.cpu().numpy().astype(np.int64), batch.adj.cpu().numpy().view(np.uint32).astype(np.int64)
     assert np.array_equal(ap, ip + op)
     saw_absent = False
+    trips = np.zeros(n, np.int64)
     for v in range(n):
-        want = [x if x >= 0 else 0x7fffffff for x in inb[ip[v]:ip[v + 1]]] + \
-               [(x | 0x80000000) if x >= 0 else 0x7fffffff for x in onb[op[v]:op[v + 1]]]
-        assert list(adj[ap[v]:ap[v + 1]]) == want
-        saw_absent |= 0x7fffffff in want
+        want = [x if x >= 0 else n for x in inb[ip[v]:ip[v + 1]]] + \
+               [(x | 0x80000000) if x >= 0 else n for x in onb[op[v]:op[v + 1]]]
+        saw_absent |= n in want
+        trips[v] = (len(want) + 3) // 4
+        want += [n] * (-len(want) % 4)
+        off = 4 * ((ap[v] + 3) // 4) + 4 * v
+        assert list(adj[off:off + len(want)]) == want
     assert saw_absent
+    order = batch.node_order.cpu().numpy()[:n]
+    assert sorted(order.tolist()) == list(range(n))
+    assert np.all(np.diff(trips[order]) <= 0)                     # one window here: longest lists first
 
 
 @pytest.mark.parametrize("name", CASES + ["toy2d_f2_h32_it10"])
