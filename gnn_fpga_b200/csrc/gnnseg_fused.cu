@@ -154,22 +154,36 @@ fused_gather_kernel(const float* __restrict__ blob, const float* __restrict__ S,
     const int grp_lane0 = lane - c;
     pdl_wait();                                    // S comes from the kernel before
 
-    for (int i0 = (blockIdx.x * 8 + warp) * NPW; i0 < n_nodes; i0 += gridDim.x * 8 * NPW) {
-        const bool live = i0 + g < n_nodes;
-        const int n = live ? (order ? __ldg(order + i0 + g) : i0 + g) : n_nodes;      // spare lanes: the zero row, no entries
-        int cum = 0, deg = 0;
-        if (live) {
-            cum = __ldg(adj_ptr + n);
-            deg = __ldg(adj_ptr + n + 1) - cum;
-        }
+    // The walk is a chain of dependent loads (node id -> list bounds -> entries -> rows); the kernel keeps one step of
+    // it in flight ahead of the arithmetic: the header of the NEXT node group is fetched while this one is worked on,
+    // and the entries of the next batch of four while the rows of this one are in flight.
+    const int step = gridDim.x * 8 * NPW;
+    auto node_of = [&](const int i) { return i < n_nodes ? (order ? __ldg(order + i) : i) : n_nodes; };   // spare lanes: the zero row
+    int i0 = (blockIdx.x * 8 + warp) * NPW;
+    int n = node_of(i0 + g), cum = 0, deg = 0;
+    if (n < n_nodes) {
+        cum = __ldg(adj_ptr + n);
+        deg = __ldg(adj_ptr + n + 1) - cum;
+    }
+    while (i0 < n_nodes) {
+        const int n_nx = node_of(i0 + step + g);                 // next group, step 1: the node id
         const int4* __restrict__ ap = reinterpret_cast<const int4*>(adj + adj_offset(cum, n));
+        const int4 pad = make_int4(n_nodes, n_nodes, n_nodes, n_nodes);
+        int4 ent_nx = pad;
+        if (deg > 0) ent_nx = __ldg(ap);
         const float4* row = S4 + (size_t)n * LD4 + c;
         const float4 sps_own = __ldg(row), spd_own = __ldg(row + G);
         float4 acc = __ldg(row + 4 * G);           // Qs[n] (holds b3)
+        int cum_nx = 0, deg_nx = 0;                // next group, step 2: its list bounds
+        if (n_nx < n_nodes) {
+            cum_nx = __ldg(adj_ptr + n_nx);
+            deg_nx = __ldg(adj_ptr + n_nx + 1) - cum_nx;
+        }
         const int trips = __reduce_max_sync(0xffffffffu, (deg + 3) >> 2);      // warp-uniform trip count
         for (int t = 0; t < trips; ++t) {
-            int4 ent = make_int4(n_nodes, n_nodes, n_nodes, n_nodes);
-            if (4 * t < deg) ent = __ldg(ap + t);
+            const int4 ent = ent_nx;
+            ent_nx = pad;
+            if (4 * (t + 1) < deg) ent_nx = __ldg(ap + t + 1);
             const int e4[4] = {ent.x, ent.y, ent.z, ent.w};
             float4 a[4], q[4];
 #pragma unroll
@@ -190,10 +204,11 @@ fused_gather_kernel(const float* __restrict__ blob, const float* __restrict__ S,
                 acc = make_float4(lo.x, lo.y, hi.x, hi.y);      // the zero row: q = 0, e finite
             }
         }
-        if (live) {
+        if (n < n_nodes) {
             acc.x = tanh_node(acc.x); acc.y = tanh_node(acc.y); acc.z = tanh_node(acc.z); acc.w = tanh_node(acc.w);
             st4(h1_out + (size_t)n * ld_out + 4 * c, acc);
         }
+        i0 += step; n = n_nx; cum = cum_nx; deg = deg_nx;
     }
 }
 
@@ -219,29 +234,44 @@ edge_final_kernel(const float* __restrict__ blob, const float* __restrict__ P, c
     const bool writer = (c & (G / 4 - 1)) == 0;           // one lane per edge total writes
     pdl_wait();
 
-    for (int i0 = (blockIdx.x * 8 + warp) * NPW; i0 < n_nodes; i0 += gridDim.x * 8 * NPW) {
-        const bool live = i0 + g < n_nodes;
-        const int n = live ? (gr.node_order ? __ldg(gr.node_order + i0 + g) : i0 + g) : n_nodes;
-        int cum = 0, k0 = 0, deg = 0;
-        if (live) {
-            cum = __ldg(gr.adj_ptr + n);
-            k0 = __ldg(gr.in_ptr + n);
-            deg = __ldg(gr.in_ptr + n + 1) - k0;           // the in-edges lead the node's adjacency list
-        }
+    const int step = gridDim.x * 8 * NPW;
+    auto node_of = [&](const int i) { return i < n_nodes ? (gr.node_order ? __ldg(gr.node_order + i) : i) : n_nodes; };
+    int i0 = (blockIdx.x * 8 + warp) * NPW;
+    int n = node_of(i0 + g), cum = 0, k0 = 0, deg = 0;
+    if (n < n_nodes) {
+        cum = __ldg(gr.adj_ptr + n);
+        k0 = __ldg(gr.in_ptr + n);
+        deg = __ldg(gr.in_ptr + n + 1) - k0;               // the in-edges lead the node's adjacency list
+    }
+    while (i0 < n_nodes) {
+        const int n_nx = node_of(i0 + step + g);
         const int4* __restrict__ ap = reinterpret_cast<const int4*>(gr.adj + adj_offset(cum, n));
+        const int4 pad = make_int4(n_nodes, n_nodes, n_nodes, n_nodes);
+        int4 ent_nx = pad;
+        if (deg > 0) ent_nx = __ldg(ap);
         const float4 spd_own = __ldg(Pd4 + (size_t)n * ld4);
+        int cum_nx = 0, k0_nx = 0, deg_nx = 0;
+        if (n_nx < n_nodes) {
+            cum_nx = __ldg(gr.adj_ptr + n_nx);
+            k0_nx = __ldg(gr.in_ptr + n_nx);
+            deg_nx = __ldg(gr.in_ptr + n_nx + 1) - k0_nx;
+        }
         const int trips = __reduce_max_sync(0xffffffffu, (deg + 3) >> 2);
         for (int t = 0; t < trips; ++t) {
-            int4 ent = make_int4(n_nodes, n_nodes, n_nodes, n_nodes);
-            if (4 * t < deg) ent = __ldg(ap + t);
+            const int4 ent = ent_nx;
+            ent_nx = pad;
+            if (4 * (t + 1) < deg) ent_nx = __ldg(ap + t + 1);
             const int e4[4] = {ent.x, ent.y, ent.z, ent.w};
+            const int k = 4 * t + my_edge;
+            int slot = -1;
+            if (writer && k < deg) slot = __ldg(gr.in_eid + k0 + k);             // (entries past deg: out-edges or padding)
             float z[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) z[u] = edge_partial(__ldg(Ps4 + (size_t)(e4[u] & 0x7fffffff) * ld4), spd_own, w2n);
             const float e_mine = sigmoid_fast(z0 + reduce4_transposed<G>(z, c));
-            const int k = 4 * t + my_edge;
-            if (writer && k < deg) scores[__ldg(gr.in_eid + k0 + k)] = e_mine;   // (entries past deg: out-edges or padding)
+            if (slot >= 0) scores[slot] = e_mine;
         }
+        i0 += step; n = n_nx; cum = cum_nx; k0 = k0_nx; deg = deg_nx;
     }
     // slots without an end node: Pd contributes nothing (SPd = 1); without a start node either: the padding constant
     const float* w2s = blob + B::W2N;

@@ -125,6 +125,7 @@ class SegmentClassifier(nn.Module):
         self._blob = None
         self.exact = False           # True: always the step-by-step kernels (GNNSEG_FWD_EXACT), see check_range
         self._range_checks = []      # (event, pinned status word) of forwards whose range flag has not been looked at
+        self._stream_cache = None    # predict_stream's pipeline slots and side streams, kept between calls
         self.use_cuda_graph = True
         self._arena = None           # reusable pinned arena for batches given as host SparseGraph tuples
 
@@ -241,7 +242,17 @@ class SegmentClassifier(nn.Module):
         from .store import StoreBatch
         dev = _require_cuda(self._device())
         depth = max(1, int(depth))
-        slots = [{"bufs": None, "done": None, "view": None, "flag": None, "arena": None, "h2d": None} for _ in range(depth + 1)]
+        # pipeline slots (device buffers, pinned result buffers, pinned arenas for tuple batches) and the two side
+        # streams are kept on the model between calls: allocating pinned memory costs more than a batch
+        cache = self._stream_cache if self._stream_cache is not None and self._stream_cache["dev"] == dev else None
+        if cache is None:
+            cache = self._stream_cache = {"dev": dev, "slots": [], "streams": (torch.cuda.Stream(dev), torch.cuda.Stream(dev))}
+        while len(cache["slots"]) < depth + 1:
+            cache["slots"].append({"bufs": None, "done": None, "view": None, "flag": None, "arena": None, "h2d": None})
+        slots = cache["slots"][:depth + 1]
+        for s_ in slots:
+            if s_["done"] is not None:
+                s_["done"].synchronize()                          # a previous stream that was abandoned half way
         was_graph, self.use_cuda_graph = self.use_cuda_graph, False    # one-shot batches: plain launches
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))     # ranks sharing this host (torchrun)
         pack_threads = max(1, min(4, (os.cpu_count() or 4) // local_world - 2))
@@ -266,7 +277,7 @@ class SegmentClassifier(nn.Module):
 
         pool = ThreadPoolExecutor(max_workers=1)
         compute = torch.cuda.current_stream(dev)
-        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        s_in, s_out = cache["streams"]
         L = _lib.lib()
         h = self.hidden_dim
         if L.gnnseg_supported(self.input_dim, h) == 0:
