@@ -421,7 +421,7 @@ def measure_workload(workload, args, rank, world, local_rank, dev, dist, sampler
         sb = store.batch(0, n_events)
         host_ref = None
         with torch.no_grad():
-            for out_host in model.predict_stream([sb] * 3):
+            for out_host in model.predict_stream([sb] * 6):      # every pipeline slot allocated and warm (kept on the model afterwards)
                 host_ref = out_host.clone()
             barrier()
             t0 = time.perf_counter()
