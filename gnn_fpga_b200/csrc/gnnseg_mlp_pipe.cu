@@ -11,7 +11,7 @@
 // the stores (1280 bytes per node leave the SM) and 5 k the tensor pipe.  Here every stage has its own warps and
 // its own mbarriers, so the chain of tile t + 1 runs under the stores of tile t:
 //
-//   loader warps (4)   h1 rows of the tile -> tf32 hi / lo -> canonical K-major A2 tile in shared memory
+//   loader warps (8)   h1 rows of the NEXT tile (registers) -> tf32 hi / lo -> canonical K-major A2 tile in shared memory
 //   MMA warp (1)       one thread issues GEMM2 (SS), then per chunk GEMM3 (TS: A = [H'] hi / lo in tensor memory,
 //                      plus one SS k-step for the [X|1] slab in shared memory); tcgen05.commit -> mbarriers
 //   epilogue warps (8) D2 -> +b4, tanh, split -> A3 in tensor memory; X slab -> shared memory
@@ -29,9 +29,25 @@
 
 namespace gnnseg {
 
+// `make trace` (-DGNNSEG_TRACE): clock64 stamps of one lane per role of CTA 0 (scripts/pipe_trace.py reads them)
+#ifdef GNNSEG_TRACE
+__device__ long long g_ptrace[5][16][16];
+__device__ unsigned long long g_pcta[160][2];
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define PT_CTA(k) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_pcta[blockIdx.x][(k)] = gtimer_ns(); } while (0)
+#define PT(role, t, k) do { if (blockIdx.x == 0 && lane == 0 && (t) < 16) g_ptrace[(role)][(t)][(k)] = clock64(); } while (0)
+#else
+#define PT(role, t, k) do { } while (0)
+#define PT_CTA(k) do { } while (0)
+#endif
+
 struct Pipe64 {
     static constexpr int H = 64, TM = 128, D4P = 72, NP = 320, NH = 160;
-    static constexpr int W_EPI = 8, W_ST = 8, W_LD = 4;
+    static constexpr int W_EPI = 8, W_ST = 8, W_LD = 8;
     static constexpr int WARP_EPI0 = 0, WARP_ST0 = W_EPI, WARP_LD0 = WARP_ST0 + W_ST, WARP_MMA = WARP_LD0 + W_LD,
                          WARP_WP = WARP_MMA + 1, NT = (WARP_WP + 1) * 32;
     static_assert(WARP_EPI0 % 4 == 0 && WARP_ST0 % 4 == 0, "a warp reaches the TMEM lanes 32 (warp % 4) ..");
@@ -82,6 +98,7 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
     const uint32_t sa = smem_u32(smem);
     auto bar = [&](const int i) { return sa + C::O_BAR + 8 * i; };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    PT_CTA(0);
 
     // this CTA's nodes, in tiles of 128 (the last one partial); chunks of 160 output columns per tile
     const int r0 = min((int)blockIdx.x * rows_per_cta, n_nodes), r1 = min(r0 + rows_per_cta, n_nodes);
@@ -128,7 +145,9 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
             constexpr int HALF_FLOATS = C::WPH_BYTES / 4, IMG_FLOATS = C::NP * C::D4P;
             const int n_loads = CH == 2 ? 2 * n_tiles : 1;        // one chunk per tile: half 0 stays
             for (int l = 0; l < n_loads; ++l) {
+                PT(4, l, 0);
                 if (l > 0) mbar_wait(bar(C::WP_EMPTY), (l & 1) ^ 1);              // GEMM3 of chunk l - 1 has read the buffer
+                PT(4, l, 1);
                 const int half = l & 1;
                 mbar_arrive_expect_tx(bar(C::WP_FULL), 2 * C::WPH_BYTES);
                 bulk_copy_g2s(sa + C::O_WP, blob + B::TC_WPH + half * HALF_FLOATS, C::WPH_BYTES, bar(C::WP_FULL));
@@ -139,98 +158,116 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
         __syncwarp();
     } else if (warp == C::WARP_MMA) {
         // ================================ MMA warp =========================================
+        // Issue order: GEMM3 chunk 0 of tile t, GEMM2 of tile t + 1, GEMM3 chunk 1 of tile t.  The epilogue warps then turn
+        // D2 of tile t + 1 into H' (registers) while the tensor pipe works on chunk 1, and only their write of A3 waits for it.
         constexpr uint32_t ID2 = idesc_tf32(TM, H), ID3 = idesc_tf32(TM, C::NH);
         const int total = CH * n_tiles;
+        auto gemm2 = [&](const int it) {                          // D2 = h1 . W4^T of tile `it`
+            mbar_wait(bar(C::A2_FULL), it & 1);
+            PT(0, it, 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_hi = sa + C::O_A, a_lo = a_hi + C::A_BYTES;
+#pragma unroll
+                for (int kq = 0; kq < H / 8; ++kq) {
+                    const uint32_t ko = kq * 2 * C::LBO;
+                    const uint64_t ah = smem_desc(a_hi + ko, C::LBO, C::SBO_H);
+                    const uint64_t al = smem_desc(a_lo + ko, C::LBO, C::SBO_H);
+                    const uint64_t bh = smem_desc(sa + C::O_W4 + ko, C::LBO, C::SBO_H);
+                    const uint64_t bl = smem_desc(sa + C::O_W4 + C::W4_BYTES + ko, C::LBO, C::SBO_H);
+                    umma_ss(tmem + C::C_D2, al, bh, ID2, kq > 0);
+                    umma_ss(tmem + C::C_D2, ah, bl, ID2, 1);
+                    umma_ss(tmem + C::C_D2, ah, bh, ID2, 1);
+                }
+                if (it + 1 < n_tiles) umma_commit(bar(C::A2_EMPTY));     // the loader may write the next tile
+                umma_commit(bar(C::D2_FULL));
+            }
+            __syncwarp();
+            PT(0, it, 2);
+        };
         int g = 0;
-        for (int it = 0; it < n_tiles; ++it) {
+        auto gemm3 = [&](const int it, const int c) {             // D3[slot] = [H'|X|1] . WP_half^T
             const bool more = it + 1 < n_tiles;
-            if (!INPUT) {
-                mbar_wait(bar(C::A2_FULL), it & 1);
-                tc_fence_after();
-                if (lane == 0) {                                  // D2 = h1 . W4^T
-                    const uint32_t a_hi = sa + C::O_A, a_lo = a_hi + C::A_BYTES;
+            const int slot = g & 1;
+            mbar_wait(bar(C::D3_EMPTY0 + slot), ((g >> 1) & 1) ^ 1);              // the store warps have read this slot
+            PT(0, it, 4 + 4 * c);
+            if (CH == 2) mbar_wait(bar(C::WP_FULL), g & 1);
+            else if (g == 0) mbar_wait(bar(C::WP_FULL), 0);
+            PT(0, it, 5 + 4 * c);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t d = tmem + C::C_D3 + slot * C::NH;
 #pragma unroll
-                    for (int kq = 0; kq < H / 8; ++kq) {
-                        const uint32_t ko = kq * 2 * C::LBO;
-                        const uint64_t ah = smem_desc(a_hi + ko, C::LBO, C::SBO_H);
-                        const uint64_t al = smem_desc(a_lo + ko, C::LBO, C::SBO_H);
-                        const uint64_t bh = smem_desc(sa + C::O_W4 + ko, C::LBO, C::SBO_H);
-                        const uint64_t bl = smem_desc(sa + C::O_W4 + C::W4_BYTES + ko, C::LBO, C::SBO_H);
-                        umma_ss(tmem + C::C_D2, al, bh, ID2, kq > 0);
-                        umma_ss(tmem + C::C_D2, ah, bl, ID2, 1);
-                        umma_ss(tmem + C::C_D2, ah, bh, ID2, 1);
-                    }
-                    if (more) umma_commit(bar(C::A2_EMPTY));      // the loader may write the next tile
-                    umma_commit(bar(C::D2_FULL));
+                for (int kq = 0; kq < H / 8; ++kq) {
+                    const uint32_t ko = kq * 2 * C::LBO;
+                    const uint64_t bh = smem_desc(sa + C::O_WP + ko, C::LBO, C::SBO_D4);
+                    const uint64_t bl = smem_desc(sa + C::O_WP + C::WPH_BYTES + ko, C::LBO, C::SBO_D4);
+                    umma_ts(d, tmem + C::C_A3L + 8 * kq, bh, ID3, kq > 0);
+                    umma_ts(d, tmem + C::C_A3H + 8 * kq, bl, ID3, 1);
+                    umma_ts(d, tmem + C::C_A3H + 8 * kq, bh, ID3, 1);
                 }
-                __syncwarp();
+                {                                                 // the [X|1|0] k-step: A from shared memory
+                    const uint32_t ko = (H / 8) * 2 * C::LBO;
+                    const uint64_t bh = smem_desc(sa + C::O_WP + ko, C::LBO, C::SBO_D4);
+                    const uint64_t bl = smem_desc(sa + C::O_WP + C::WPH_BYTES + ko, C::LBO, C::SBO_D4);
+                    const uint64_t xh = smem_desc(sa + C::O_XS, C::LBO, C::SBO_X);
+                    const uint64_t xl = smem_desc(sa + C::O_XS + C::XS_BYTES, C::LBO, C::SBO_X);
+                    umma_ss(d, xl, bh, ID3, 1);
+                    umma_ss(d, xh, bl, ID3, 1);
+                    umma_ss(d, xh, bh, ID3, 1);
+                }
+                umma_commit(bar(C::D3_FULL0 + slot));
+                if (CH == 2 && g + 1 < total) umma_commit(bar(C::WP_EMPTY));
+                if (c + 1 == CH && more) umma_commit(bar(C::A3_EMPTY));
             }
+            __syncwarp();
+            PT(0, it, 6 + 4 * c);
+            ++g;
+        };
+        if (!INPUT && n_tiles > 0) gemm2(0);
+        for (int it = 0; it < n_tiles; ++it) {
+            PT(0, it, 0);
             mbar_wait(bar(C::A3_FULL), it & 1);                    // [H'|X|1] of this tile is in place, D2 has been read
-            for (int c = 0; c < CH; ++c, ++g) {
-                const int slot = g & 1;
-                mbar_wait(bar(C::D3_EMPTY0 + slot), ((g >> 1) & 1) ^ 1);          // the store warps have read this slot
-                if (CH == 2) mbar_wait(bar(C::WP_FULL), g & 1);
-                else if (g == 0) mbar_wait(bar(C::WP_FULL), 0);
-                tc_fence_after();
-                if (lane == 0) {                                  // D3[slot] = [H'|X|1] . WP_half^T
-                    const uint32_t d = tmem + C::C_D3 + slot * C::NH;
-#pragma unroll
-                    for (int kq = 0; kq < H / 8; ++kq) {
-                        const uint32_t ko = kq * 2 * C::LBO;
-                        const uint64_t bh = smem_desc(sa + C::O_WP + ko, C::LBO, C::SBO_D4);
-                        const uint64_t bl = smem_desc(sa + C::O_WP + C::WPH_BYTES + ko, C::LBO, C::SBO_D4);
-                        umma_ts(d, tmem + C::C_A3L + 8 * kq, bh, ID3, kq > 0);
-                        umma_ts(d, tmem + C::C_A3H + 8 * kq, bl, ID3, 1);
-                        umma_ts(d, tmem + C::C_A3H + 8 * kq, bh, ID3, 1);
-                    }
-                    {                                             // the [X|1|0] k-step: A from shared memory
-                        const uint32_t ko = (H / 8) * 2 * C::LBO;
-                        const uint64_t bh = smem_desc(sa + C::O_WP + ko, C::LBO, C::SBO_D4);
-                        const uint64_t bl = smem_desc(sa + C::O_WP + C::WPH_BYTES + ko, C::LBO, C::SBO_D4);
-                        const uint64_t xh = smem_desc(sa + C::O_XS, C::LBO, C::SBO_X);
-                        const uint64_t xl = smem_desc(sa + C::O_XS + C::XS_BYTES, C::LBO, C::SBO_X);
-                        umma_ss(d, xl, bh, ID3, 1);
-                        umma_ss(d, xh, bl, ID3, 1);
-                        umma_ss(d, xh, bh, ID3, 1);
-                    }
-                    umma_commit(bar(C::D3_FULL0 + slot));
-                    if (CH == 2 && g + 1 < total) umma_commit(bar(C::WP_EMPTY));
-                    if (c + 1 == CH && more) umma_commit(bar(C::A3_EMPTY));
-                }
-                __syncwarp();
-            }
+            PT(0, it, 3);
+            gemm3(it, 0);
+            if (!INPUT && it + 1 < n_tiles) gemm2(it + 1);
+            if (CH == 2) gemm3(it, 1);
         }
     } else if (warp >= C::WARP_LD0) {
         // ================================ loader warps =====================================
         // a quarter warp holds 8 consecutive rows of ONE float4 chunk, i.e. one contiguous 128-byte row group of
         // the canonical tile: the shared-memory stores are bank-conflict free
+        // The rows of the NEXT tile are fetched into registers while this one is in flight (the loads queue behind the
+        // store warps' traffic: 5 - 11 k cycles measured); only the split and the shared-memory stores wait for GEMM2.
         if (!INPUT) {
             const int lt = tid - C::WARP_LD0 * 32, lw = lt >> 5, r7 = lt & 7, cq = (lt >> 3) & 3;
-            for (int it = 0; it < n_tiles; ++it) {
+            float4 v[8];
+            auto fetch = [&](const int it) {
                 const int base = r0 + it * TM;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = base + (lw * 2 + (j >> 2)) * 8 + r7;
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (n < r1) v[j] = lds4(h1 + (size_t)n * ld_h1 + 4 * (cq + 4 * (j & 3)));      // plain load: h1 may alias the output rows
+                }
+            };
+            if (n_tiles > 0) fetch(0);
+            for (int it = 0; it < n_tiles; ++it) {
+                if (warp == C::WARP_LD0) PT(3, it, 0);
                 if (it > 0) mbar_wait(bar(C::A2_EMPTY), (it & 1) ^ 1);            // GEMM2 of the previous tile has read A2
+                if (warp == C::WARP_LD0) PT(3, it, 1);
 #pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    float4 v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int jj = 8 * pass + j;
-                        const int n = base + (lw * 4 + (jj >> 2)) * 8 + r7;
-                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (n < r1) v[j] = lds4(h1 + (size_t)n * ld_h1 + 4 * (cq + 4 * (jj & 3)));   // plain load: h1 may alias the output rows
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int jj = 8 * pass + j;
-                        float4 hh, hl;
-                        split3(v[j].x, hh.x, hl.x); split3(v[j].y, hh.y, hl.y); split3(v[j].z, hh.z, hl.z); split3(v[j].w, hh.w, hl.w);
-                        const int off = canon_off((lw * 4 + (jj >> 2)) * 8 + r7, 4 * (cq + 4 * (jj & 3)), C::SBO_H);
-                        *reinterpret_cast<float4*>(smem + C::O_A + off) = hh;
-                        *reinterpret_cast<float4*>(smem + C::O_A + C::A_BYTES + off) = hl;
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    float4 hh, hl;
+                    split3(v[j].x, hh.x, hl.x); split3(v[j].y, hh.y, hl.y); split3(v[j].z, hh.z, hl.z); split3(v[j].w, hh.w, hl.w);
+                    const int off = canon_off((lw * 2 + (j >> 2)) * 8 + r7, 4 * (cq + 4 * (j & 3)), C::SBO_H);
+                    *reinterpret_cast<float4*>(smem + C::O_A + off) = hh;
+                    *reinterpret_cast<float4*>(smem + C::O_A + C::A_BYTES + off) = hl;
                 }
                 fence_async_smem();                                // generic-proxy writes -> tensor core reads
                 mbar_arrive(bar(C::A2_FULL));
+                if (warp == C::WARP_LD0) PT(3, it, 2);
+                if (it + 1 < n_tiles) fetch(it + 1);
             }
         }
     } else if (warp >= C::WARP_ST0) {
@@ -244,35 +281,32 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
             const int node_w0 = r0 + it * TM + q * 32;
             for (int c = 0; c < CH; ++c, ++g) {
                 const int slot = g & 1;
+                if (w == 0) PT(2, it, 3 * c);
                 mbar_wait(bar(C::D3_FULL0 + slot), (g >> 1) & 1);
+                if (w == 0) PT(2, it, 3 * c + 1);
                 tc_fence_after();
                 // the two warps of a lane quarter share the five 32-column pieces of a chunk, 3 + 2 alternating
                 for (int j = (hf + g) & 1; j < 5; j += 2) {
                     const int c0 = C::NH * c + 32 * j;
                     if (c0 >= out.n_cols) break;
+                    {
+                        float v[32];
+                        tmem_ld32(lane_base + C::C_D3 + slot * C::NH + 32 * j, v);
+                        if (proj_is_exp<H>(out, c0)) {
+                            to_exponentials(*reinterpret_cast<float (*)[16]>(&v[0]), out.range_flag);
+                            to_exponentials(*reinterpret_cast<float (*)[16]>(&v[16]), out.range_flag);
+                        }
 #pragma unroll
-                    for (int hb = 0; hb < 2; ++hb) {
-                        float v[16];
-                        tmem_ld16(lane_base + C::C_D3 + slot * C::NH + 32 * j + 16 * hb, v);
-                        if (proj_is_exp<H>(out, c0)) to_exponentials(v, out.range_flag);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)           // the bias is already in D3
-                            st4(sOut + lane * 32 + (((4 * hb + i) ^ (lane & 7)) << 2),
-                                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                        for (int i = 0; i < 8; ++i)           // the bias is already in D3
+                            st4(sOut + lane * 32 + ((i ^ (lane & 7)) << 2), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
                     }
                     __syncwarp();
-                    int ld;
-                    float* base = proj_ptr<H>(out, node_w0, c0, ld);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 4 * i + (lane >> 3), jj = lane & 7;
-                        if (node_w0 + r < r1)
-                            st4_hint(base + (size_t)r * ld + 4 * jj, lds4(sOut + r * 32 + ((jj ^ (r & 7)) << 2)), stream);
-                    }
+                    store_tile_proj<H>(out, sOut, node_w0, c0, r1 - node_w0, lane, stream);
                     __syncwarp();
                 }
                 tc_fence_before();
                 mbar_arrive(bar(C::D3_EMPTY0 + slot));
+                if (w == 0) PT(2, it, 3 * c + 2);
             }
         }
     } else {
@@ -293,35 +327,52 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
             } else if (live && hf == 0) {
                 x = ldg4(X4 + (size_t)n * 4);
             }
-            if (!INPUT) mbar_wait(bar(C::D2_FULL), it & 1);
+            if (warp == 0) PT(1, it, 0);
+            float v[32];                                           // this thread's 32 columns of H'
+            const int cb = hf * 32;
+            if (!INPUT) {
+                mbar_wait(bar(C::D2_FULL), it & 1);
+                if (warp == 0) PT(1, it, 1);
+                tc_fence_after();
+                tmem_ld32(lane_base + C::C_D2 + cb, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = tanh_node(v[i] + sB4[cb + i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float t = sWin[4 * H + cb + i];
+                    t = fmaf(x.x, sWin[0 * H + cb + i], t);
+                    t = fmaf(x.y, sWin[1 * H + cb + i], t);
+                    t = fmaf(x.z, sWin[2 * H + cb + i], t);
+                    t = fmaf(x.w, sWin[3 * H + cb + i], t);
+                    v[i] = tanh_node(t);
+                }
+            }
+            if (H_save && live) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    st4(H_save + (size_t)n * H + cb + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+            }
+            // H' is complete in registers, its first half already split, BEFORE the wait (the compiler would otherwise sink
+            // the arithmetic below it)
+            float hi0[16], lo0[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                split3(v[i], hi0[i], lo0[i]);
+                asm volatile("" : "+f"(hi0[i]), "+f"(lo0[i]), "+f"(v[16 + i]));
+            }
+            if (warp == 0) PT(1, it, 4);
             mbar_wait(bar(C::A3_EMPTY), (it & 1) ^ 1);             // GEMM3 of the previous tile has read A3 and the X slab
+            if (warp == 0) PT(1, it, 2);
             tc_fence_after();
+            tmem_st16(lane_base + C::C_A3H + cb, hi0);
+            tmem_st16(lane_base + C::C_A3L + cb, lo0);
+            {
+                float hi[16], lo[16];
 #pragma unroll
-            for (int part = 0; part < 2; ++part) {
-                const int c0 = hf * 32 + part * 16;
-                float v[16], hi[16], lo[16];
-                if (!INPUT) tmem_ld16(lane_base + C::C_D2 + c0, v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (INPUT) {
-                        float t = sWin[4 * H + c0 + i];
-                        t = fmaf(x.x, sWin[0 * H + c0 + i], t);
-                        t = fmaf(x.y, sWin[1 * H + c0 + i], t);
-                        t = fmaf(x.z, sWin[2 * H + c0 + i], t);
-                        t = fmaf(x.w, sWin[3 * H + c0 + i], t);
-                        v[i] = tanh_node(t);
-                    } else {
-                        v[i] = tanh_node(v[i] + sB4[c0 + i]);
-                    }
-                    split3(v[i], hi[i], lo[i]);
-                }
-                if (H_save && live) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        st4(H_save + (size_t)n * H + c0 + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-                }
-                tmem_st16(lane_base + C::C_A3H + c0, hi);
-                tmem_st16(lane_base + C::C_A3L + c0, lo);
+                for (int i = 0; i < 16; ++i) split3(v[16 + i], hi[i], lo[i]);
+                tmem_st16(lane_base + C::C_A3H + cb + 16, hi);
+                tmem_st16(lane_base + C::C_A3L + cb + 16, lo);
             }
             if (hf == 0) {                                         // [X | 1 | 0 0 0]: times the X rows and the bias row of the weight image
                 float4 xh, xl;
@@ -336,15 +387,26 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(bar(C::A3_FULL));
+            if (warp == 0) PT(1, it, 3);
         }
     }
     tc_fence_before();
     __syncthreads();
+    PT_CTA(1);
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
     }
 }
+
+#ifdef GNNSEG_TRACE
+extern "C" int gnnseg_debug_read_pipe_trace(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_ptrace, sizeof(long long) * 5 * 16 * 16) == cudaSuccess ? 0 : -4;
+}
+extern "C" int gnnseg_debug_read_pipe_cta(unsigned long long* out) {
+    return cudaMemcpyFromSymbol(out, g_pcta, sizeof(unsigned long long) * 160 * 2) == cudaSuccess ? 0 : -4;
+}
+#endif
 
 // one contiguous node range per CTA, one CTA per SM
 static int pipe64_grid(const int n_nodes, const int sms, int& rows_per_cta) {

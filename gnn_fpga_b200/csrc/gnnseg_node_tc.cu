@@ -166,10 +166,16 @@ __device__ __forceinline__ void tc_store_projections(const uint32_t lane_base, c
         __syncwarp();
         int ld;
         float* base = proj_ptr<H>(out, node_w0, c0, ld);
+        float4 t[8];                                               // all loads before the first store (see store_tile_rows)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
-            if (node_w0 + r < n_nodes) st4_hint(base + (size_t)r * ld + c4, lds4(sOut + r * OS + c4), stream);
+            t[i] = lds4(sOut + r * OS + c4);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3), c4 = (lane & 7) * 4;
+            if (node_w0 + r < n_nodes) st4_hint(base + (size_t)r * ld + c4, t[i], stream);
         }
         __syncwarp();
     }
@@ -704,14 +710,7 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
                         stage16(c0, 0);
                         stage16(c0 + 16, 4);
                         __syncwarp();
-                        int ld;
-                        float* base = out_ptr(c0, ld);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = 4 * i + (lane >> 3), j = lane & 7;
-                            if (node_w0 + r < n_nodes)
-                                st4_hint(base + (size_t)r * ld + 4 * j, lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2)), stream);
-                        }
+                        store_tile_proj<H>(out, sOut, node_w0, c0, n_nodes - node_w0, lane, stream);
                         __syncwarp();
                     }
                     if (write_q) {                                               // last chunk: 16 columns per warp
@@ -720,11 +719,16 @@ node_mlp_kernel_tc(const float* __restrict__ blob, const float* __restrict__ X4,
                         __syncwarp();
                         int ld;
                         float* base = out_ptr(c0, ld);
+                        float4 t4[4];                                                // all loads before the first store
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int r = 8 * i + (lane >> 2), j = lane & 3;
-                            if (node_w0 + r < n_nodes)
-                                st4_hint(base + (size_t)r * ld + 4 * j, lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2)), stream);
+                            t4[i] = lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = 8 * i + (lane >> 2), j = lane & 3;
+                            if (node_w0 + r < n_nodes) st4_hint(base + (size_t)r * ld + 4 * j, t4[i], stream);
                         }
                         __syncwarp();
                     }
@@ -897,14 +901,7 @@ node_mlp_kernel_tc64(const float* __restrict__ blob, float* __restrict__ X4, con
                         make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
             }
             __syncwarp();
-            int ld;
-            float* base = proj_ptr<H>(out, node_w0, c0, ld);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = 4 * i + (lane >> 3), j = lane & 7;
-                if (node_w0 + r < n_nodes)
-                    st4_hint(base + (size_t)r * ld + 4 * j, lds4(sOut + r * 32 + ((j ^ (r & 7)) << 2)), stream);
-            }
+            store_tile_proj<H>(out, sOut, node_w0, c0, n_nodes - node_w0, lane, stream);
             __syncwarp();
         };
         auto gemm3_half = [&](const int half) {               // D3[:, 160 half ...] = [H'|X] . WP_half^T

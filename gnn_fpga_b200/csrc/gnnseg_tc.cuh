@@ -20,9 +20,14 @@ __device__ __forceinline__ uint32_t tf32_rna(const float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// x = hi + lo for the 3xTF32 products: hi = x rounded to tf32 (cvt.rna), lo = (x - hi) rounded to tf32.  cvt runs on the
+// 16-lane XU pipe that the tanh / ex2 of the same warps need (measured: the conversions were a third of the epilogue's
+// critical path), so the second rounding is done on the integer pipe: add half an ulp of tf32 to the magnitude, clear the
+// 13 low bits -- round to nearest, ties away, what cvt.rna does.  (x - hi is exact and finite for finite x; a NaN or an
+// infinity shows in hi already.)
 __device__ __forceinline__ void split3(const float x, float& hi, float& lo) {
     hi = __uint_as_float(tf32_rna(x));
-    lo = __uint_as_float(tf32_rna(x - hi));
+    lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // TMA store of one box (shared -> global) described by a tensor map; bulk async group per issuing thread
@@ -139,17 +144,68 @@ template <int H>
 __device__ __forceinline__ bool proj_is_exp(const ProjOut& o, const int col) {
     return o.mode == 1 && col < 2 * H;
 }
+// A warp's swizzled 32 x 32 store tile (16-byte chunk j of row r at chunk j ^ (r & 7)) -> 32 rows of global memory, 128
+// bytes each: every store instruction writes four full lines.  `p0` = column c0 of the warp's first row, LD = row stride
+// in floats (compile time: the eight row offsets fold into the instructions), rows_valid = how many of the 32 rows exist.
+// All eight shared-memory loads are issued before the first store: written as load / store pairs the compiler reuses ONE
+// register quad and every pair waits for the one before (measured: 2.3 k cycles per 4 KB tile and warp).
+template <int LD>
+__device__ __forceinline__ void store_tile_rows(const float* sOut, float* p0, const int rows_valid, const int lane, const uint64_t policy) {
+    const int rq = lane >> 3, jj = lane & 7;
+    float4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + rq;
+        t[i] = lds4(sOut + r * 32 + ((jj ^ (r & 7)) << 2));
+    }
+    float* p = p0 + (size_t)rq * LD + 4 * jj;
+    if (rows_valid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st4_hint(p + (size_t)(4 * i) * LD, t[i], policy);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (4 * i + rq < rows_valid) st4_hint(p + (size_t)(4 * i) * LD, t[i], policy);
+    }
+}
+// the same, row stride picked from where the columns go (ProjOut): state rows, or P' / Q'
+template <int H>
+__device__ __forceinline__ void store_tile_proj(const ProjOut& o, const float* sOut, const int node_w0, const int c0, const int rows_valid,
+                                                const int lane, const uint64_t policy) {
+    int ld;
+    float* p0 = proj_ptr<H>(o, node_w0, c0, ld);
+    if (o.mode == 1) store_tile_rows<5 * H>(sOut, p0, rows_valid, lane, policy);
+    else if (c0 < 2 * H) store_tile_rows<2 * H>(sOut, p0, rows_valid, lane, policy);
+    else store_tile_rows<3 * H>(sOut, p0, rows_valid, lane, policy);
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane -> registers (one wait for both halves)
+__device__ __forceinline__ void tmem_ld32(const uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // edge projection -> 2^(log2e v), exponent clamped to [-63, 63] (gnnseg_fused.cu); a clamp raises the flag
 __device__ __forceinline__ void to_exponentials(float (&v)[16], int* __restrict__ flag) {
     bool clamped = false;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        float a = v[i] * 1.4426950408889634f;
+        const float a = v[i] * 1.4426950408889634f;
         clamped |= !(fabsf(a) <= 63.f);                         // also a NaN
-        const float c = fminf(fmaxf(a, -63.f), 63.f);
-        float e;
+        float c, e;
+        asm("min.NaN.f32 %0, %1, %2;" : "=f"(c) : "f"(a), "f"(63.f));        // the NaN-propagating forms: a NaN stays visible
+        asm("max.NaN.f32 %0, %1, %2;" : "=f"(c) : "f"(c), "f"(-63.f));
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(c));
-        v[i] = a != a ? a : e;                                  // fminf / fmaxf drop a NaN: keep it visible
+        v[i] = e;
     }
     if (clamped && flag) atomicOr(flag, 1);
 }
