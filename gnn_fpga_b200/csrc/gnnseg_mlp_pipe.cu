@@ -45,16 +45,19 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 #define PT_CTA(k) do { } while (0)
 #endif
 
-struct Pipe64 {
-    static constexpr int H = 64, TM = 128, D4P = 72, NP = 320, NH = 160;
+template <int HD>
+struct Pipe {
+    static constexpr int H = HD, TM = 128, D4P = (H + 4 + 7) / 8 * 8, NP = 5 * H, NH = 160;      // NH: output columns per chunk
+    static constexpr int MAXCH = NP / NH;                         // chunks per tile: 2 at hidden_dim 64 (weights streamed), 1 at 32
+    static_assert(NP % NH == 0 && MAXCH <= 2, "chunking");
     static constexpr int W_EPI = 8, W_ST = 8, W_LD = 8;
     static constexpr int WARP_EPI0 = 0, WARP_ST0 = W_EPI, WARP_LD0 = WARP_ST0 + W_ST, WARP_MMA = WARP_LD0 + W_LD,
                          WARP_WP = WARP_MMA + 1, NT = (WARP_WP + 1) * 32;
     static_assert(WARP_EPI0 % 4 == 0 && WARP_ST0 % 4 == 0, "a warp reaches the TMEM lanes 32 (warp % 4) ..");
     static constexpr int LBO = 128, SBO_H = (H / 4) * LBO, SBO_D4 = (D4P / 4) * LBO, SBO_X = 2 * LBO;
-    static constexpr int A_BYTES = (TM / 8) * SBO_H;              // 32 KB, one of hi / lo
+    static constexpr int A_BYTES = (TM / 8) * SBO_H;              // 32 KB at hidden_dim 64, one of hi / lo
     static constexpr int W4_BYTES = (H / 8) * SBO_H;              // 16 KB
-    static constexpr int WPH_BYTES = (NH / 8) * SBO_D4;           // 45 KB: one half of the outputs, one of hi / lo
+    static constexpr int WPH_BYTES = (NH / 8) * SBO_D4;           // 45 KB: the weights of one chunk, one of hi / lo
     static constexpr int XS_BYTES = (TM / 8) * SBO_X;             // 4 KB: the [X|1|0] k-step of A3, one of hi / lo
     static constexpr int O_A = 0;                                 // hi, lo  (INPUT: Win^T [4][H], bin [H] live here)
     static constexpr int O_W4 = O_A + 2 * A_BYTES;                // hi, lo
@@ -83,13 +86,13 @@ __device__ __forceinline__ void bulk_copy_g2s(const uint32_t dst_smem, const voi
 
 // INPUT = true is the input step: no GEMM2; the epilogue warps compute H0 = tanh(Win.X + bin) (K = F <= 4) straight
 // into A3, X4 is then an output (X zero padded), Xraw the (n, F) input.
-template <bool INPUT>
-__global__ void __launch_bounds__(Pipe64::NT, 1)
-node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, const float* h1, const int ld_h1,
+template <int HD, bool INPUT>
+__global__ void __launch_bounds__(Pipe<HD>::NT, 1)
+node_mlp_kernel_pipe(const float* __restrict__ blob, float* __restrict__ X4, const float* h1, const int ld_h1,
                        const int n_nodes, const int rows_per_cta, const ProjOut out,
                        float* __restrict__ H_save, const float* __restrict__ Xraw, const int F) {
-    using C = Pipe64;
-    using B = Blob<64>;
+    using C = Pipe<HD>;
+    using B = Blob<HD>;
     constexpr int H = C::H, TM = C::TM, NT = C::NT;
     extern __shared__ __align__(128) unsigned char smem[];
     float* sB4 = reinterpret_cast<float*>(smem + C::O_BIAS);
@@ -103,7 +106,7 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
     // this CTA's nodes, in tiles of 128 (the last one partial); chunks of 160 output columns per tile
     const int r0 = min((int)blockIdx.x * rows_per_cta, n_nodes), r1 = min(r0 + rows_per_cta, n_nodes);
     const int n_tiles = (r1 - r0 + TM - 1) / TM;
-    const int CH = out.n_cols > C::NH ? 2 : 1;
+    const int CH = (C::MAXCH == 2 && out.n_cols > C::NH) ? 2 : 1;
 
     if (INPUT) {
         for (int i = tid; i < 5 * H; i += NT) sWin[i] = __ldg(blob + B::WIN + i);      // Win and bin are contiguous
@@ -229,9 +232,14 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
             PT(0, it, 0);
             mbar_wait(bar(C::A3_FULL), it & 1);                    // [H'|X|1] of this tile is in place, D2 has been read
             PT(0, it, 3);
-            gemm3(it, 0);
-            if (!INPUT && it + 1 < n_tiles) gemm2(it + 1);
-            if (CH == 2) gemm3(it, 1);
+            if (CH == 1) {                                        // (no weight streaming to hide: GEMM2 of the next tile goes first)
+                if (!INPUT && it + 1 < n_tiles) gemm2(it + 1);
+                gemm3(it, 0);
+            } else {
+                gemm3(it, 0);
+                if (!INPUT && it + 1 < n_tiles) gemm2(it + 1);
+                gemm3(it, 1);
+            }
         }
     } else if (warp >= C::WARP_LD0) {
         // ================================ loader warps =====================================
@@ -241,14 +249,16 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
         // store warps' traffic: 5 - 11 k cycles measured); only the split and the shared-memory stores wait for GEMM2.
         if (!INPUT) {
             const int lt = tid - C::WARP_LD0 * 32, lw = lt >> 5, r7 = lt & 7, cq = (lt >> 3) & 3;
-            float4 v[8];
+            constexpr int CPQ = H / 16, J = 2 * CPQ;               // float4 chunk cq + 4 (j % CPQ) of row group 2 lw + j / CPQ
+            static_assert(C::W_LD == 8, "row groups");
+            float4 v[J];
             auto fetch = [&](const int it) {
                 const int base = r0 + it * TM;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int n = base + (lw * 2 + (j >> 2)) * 8 + r7;
+                for (int j = 0; j < J; ++j) {
+                    const int n = base + (lw * 2 + j / CPQ) * 8 + r7;
                     v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (n < r1) v[j] = lds4(h1 + (size_t)n * ld_h1 + 4 * (cq + 4 * (j & 3)));      // plain load: h1 may alias the output rows
+                    if (n < r1) v[j] = lds4(h1 + (size_t)n * ld_h1 + 4 * (cq + 4 * (j % CPQ)));      // plain load: h1 may alias the output rows
                 }
             };
             if (n_tiles > 0) fetch(0);
@@ -257,10 +267,10 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
                 if (it > 0) mbar_wait(bar(C::A2_EMPTY), (it & 1) ^ 1);            // GEMM2 of the previous tile has read A2
                 if (warp == C::WARP_LD0) PT(3, it, 1);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < J; ++j) {
                     float4 hh, hl;
                     split3(v[j].x, hh.x, hl.x); split3(v[j].y, hh.y, hl.y); split3(v[j].z, hh.z, hl.z); split3(v[j].w, hh.w, hl.w);
-                    const int off = canon_off((lw * 2 + (j >> 2)) * 8 + r7, 4 * (cq + 4 * (j & 3)), C::SBO_H);
+                    const int off = canon_off((lw * 2 + j / CPQ) * 8 + r7, 4 * (cq + 4 * (j % CPQ)), C::SBO_H);
                     *reinterpret_cast<float4*>(smem + C::O_A + off) = hh;
                     *reinterpret_cast<float4*>(smem + C::O_A + C::A_BYTES + off) = hl;
                 }
@@ -328,18 +338,23 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
                 x = ldg4(X4 + (size_t)n * 4);
             }
             if (warp == 0) PT(1, it, 0);
-            float v[32];                                           // this thread's 32 columns of H'
-            const int cb = hf * 32;
+            constexpr int CPT = H / 2;                             // this thread's columns of H': 32 or 16
+            float v[CPT];
+            const int cb = hf * CPT;
             if (!INPUT) {
                 mbar_wait(bar(C::D2_FULL), it & 1);
                 if (warp == 0) PT(1, it, 1);
                 tc_fence_after();
-                tmem_ld32(lane_base + C::C_D2 + cb, v);
+                if constexpr (CPT == 32) {
+                    tmem_ld32(lane_base + C::C_D2 + cb, v);
+                } else {
+                    tmem_ld16(lane_base + C::C_D2 + cb, v);
+                }
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = tanh_node(v[i] + sB4[cb + i]);
+                for (int i = 0; i < CPT; ++i) v[i] = tanh_node(v[i] + sB4[cb + i]);
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < CPT; ++i) {
                     float t = sWin[4 * H + cb + i];
                     t = fmaf(x.x, sWin[0 * H + cb + i], t);
                     t = fmaf(x.y, sWin[1 * H + cb + i], t);
@@ -350,16 +365,17 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
             }
             if (H_save && live) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < CPT / 4; ++i)
                     st4(H_save + (size_t)n * H + cb + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
             }
-            // H' is complete in registers, its first half already split, BEFORE the wait (the compiler would otherwise sink
-            // the arithmetic below it)
+            // H' is complete in registers, its first 16 columns already split, BEFORE the wait (the compiler would otherwise
+            // sink the arithmetic below it)
             float hi0[16], lo0[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 split3(v[i], hi0[i], lo0[i]);
-                asm volatile("" : "+f"(hi0[i]), "+f"(lo0[i]), "+f"(v[16 + i]));
+                asm volatile("" : "+f"(hi0[i]), "+f"(lo0[i]));
+                if constexpr (CPT == 32) asm volatile("" : "+f"(v[16 + i]));
             }
             if (warp == 0) PT(1, it, 4);
             mbar_wait(bar(C::A3_EMPTY), (it & 1) ^ 1);             // GEMM3 of the previous tile has read A3 and the X slab
@@ -367,7 +383,7 @@ node_mlp_kernel_pipe64(const float* __restrict__ blob, float* __restrict__ X4, c
             tc_fence_after();
             tmem_st16(lane_base + C::C_A3H + cb, hi0);
             tmem_st16(lane_base + C::C_A3L + cb, lo0);
-            {
+            if constexpr (CPT == 32) {
                 float hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) split3(v[16 + i], hi[i], lo[i]);
@@ -409,40 +425,53 @@ extern "C" int gnnseg_debug_read_pipe_cta(unsigned long long* out) {
 #endif
 
 // one contiguous node range per CTA, one CTA per SM
-static int pipe64_grid(const int n_nodes, const int sms, int& rows_per_cta) {
-    const int n_tiles = (n_nodes + Pipe64::TM - 1) / Pipe64::TM;
+static int pipe_grid(const int n_nodes, const int sms, int& rows_per_cta) {
+    const int n_tiles = (n_nodes + 127) / 128;
     const int grid = n_tiles < sms ? n_tiles : sms;
     rows_per_cta = (n_nodes + grid - 1) / grid;
     return grid;
 }
 
-int launch_node_mlp_pipe64(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, const ProjOut& out,
-                           float* H_save, bool pdl, cudaStream_t st) {
-    using C = Pipe64;
+template <int H>
+static int launch_mlp(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, const ProjOut& out,
+                      float* H_save, bool pdl, cudaStream_t st) {
+    using C = Pipe<H>;
     if (n_nodes == 0) return GNNSEG_OK;
-    if (!ensure_dynamic_smem<node_mlp_kernel_pipe64<false>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
+    if (!ensure_dynamic_smem<node_mlp_kernel_pipe<H, false>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
     const int sms = cached_sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
     int rows = 0;
-    const int grid = pipe64_grid(n_nodes, sms, rows);
-    if (launch_pdl(node_mlp_kernel_pipe64<false>, grid, C::NT, C::SMEM_BYTES, st, pdl, blob, const_cast<float*>(X4), h1, ld_h1, n_nodes,
+    const int grid = pipe_grid(n_nodes, sms, rows);
+    if (launch_pdl(node_mlp_kernel_pipe<H, false>, grid, C::NT, C::SMEM_BYTES, st, pdl, blob, const_cast<float*>(X4), h1, ld_h1, n_nodes,
                    rows, out, H_save, (const float*)nullptr, 0) != cudaSuccess)
         return GNNSEG_ECUDA;
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
-int launch_input_pipe64(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, float* H_save,
+template <int H>
+static int launch_input(const float* blob, const float* X, int n_nodes, int F, float* X4, const ProjOut& out, float* H_save,
                         cudaStream_t st) {
-    using C = Pipe64;
+    using C = Pipe<H>;
     if (n_nodes == 0) return GNNSEG_OK;
-    if (!ensure_dynamic_smem<node_mlp_kernel_pipe64<true>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
+    if (!ensure_dynamic_smem<node_mlp_kernel_pipe<H, true>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
     const int sms = cached_sm_count();
     if (sms < 1) return GNNSEG_ENODEVICE;
     int rows = 0;
-    const int grid = pipe64_grid(n_nodes, sms, rows);
+    const int grid = pipe_grid(n_nodes, sms, rows);
     // the first kernel of a forward: launched fully serialised (it reads the blob the pack kernels wrote)
-    node_mlp_kernel_pipe64<true><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X4, nullptr, 0, n_nodes, rows, out, H_save, X, F);
+    node_mlp_kernel_pipe<H, true><<<grid, C::NT, C::SMEM_BYTES, st>>>(blob, X4, nullptr, 0, n_nodes, rows, out, H_save, X, F);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+}
+
+int launch_node_mlp_pipe(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, int h, const ProjOut& out,
+                         float* H_save, bool pdl, cudaStream_t st) {
+    return h == 32 ? launch_mlp<32>(blob, X4, h1, ld_h1, n_nodes, out, H_save, pdl, st)
+                   : launch_mlp<64>(blob, X4, h1, ld_h1, n_nodes, out, H_save, pdl, st);
+}
+int launch_input_pipe(const float* blob, const float* X, int n_nodes, int F, int h, float* X4, const ProjOut& out, float* H_save,
+                      cudaStream_t st) {
+    return h == 32 ? launch_input<32>(blob, X, n_nodes, F, X4, out, H_save, st)
+                   : launch_input<64>(blob, X, n_nodes, F, X4, out, H_save, st);
 }
 
 }  // namespace gnnseg

@@ -29,6 +29,15 @@ namespace gnnseg {
 
 bool use_pdl(int n_slots);   // gnnseg_forward.cu
 
+// gnnseg_mlp_pipe.cu: the warp-specialised form of the MLP and input kernels of this file (the default for hidden_dim 32
+// and 64; GNNSEG_MLP_PIPE=0 picks the kernels below)
+int launch_node_mlp_pipe(const float*, const float*, const float*, int, int, int, const ProjOut&, float*, bool, cudaStream_t);
+int launch_input_pipe(const float*, const float*, int, int, int, float*, const ProjOut&, float*, cudaStream_t);
+static bool mlp_pipe() {
+    static const bool v = [] { const char* e = std::getenv("GNNSEG_MLP_PIPE"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
 // `make trace` builds ../libgnnseg_trace.so with -DGNNSEG_TRACE: node_mlp_kernel_tc<32> then records
 // clock64 stamps per role of CTA 0 at the phase boundaries of every tile and %globaltimer at entry /
 // exit of every CTA (scripts/mlp_trace.py reads them).  The shipped library has none of this.
@@ -1163,6 +1172,7 @@ int launch_input_tc32_ex(const float* blob, const float* X, int n_nodes, int F, 
                          cudaStream_t st) {
     using C = TcInCfg<32>;
     if (n_nodes == 0) return GNNSEG_OK;
+    if (mlp_pipe()) return launch_input_pipe(blob, X, n_nodes, F, 32, X4, out, H_save, st);
     const int n_tiles = (n_nodes + TcCfg<32>::TM - 1) / TcCfg<32>::TM;
     if (!ensure_dynamic_smem<input_kernel_tc<32>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
     const int sms = cached_sm_count();
@@ -1206,6 +1216,7 @@ int launch_node_mlp_tc32_ex(const float* blob, const float* X4, const float* h1,
                             float* H_save, bool pdl, cudaStream_t st) {
     using C = TcMlpCfg<32>;
     if (n_nodes == 0) return GNNSEG_OK;
+    if (mlp_pipe()) return launch_node_mlp_pipe(blob, X4, h1, ld_h1, n_nodes, 32, out, H_save, pdl, st);
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
     constexpr int SMEM = C::SMEM_BYTES + 1024;                      // room to align the store tiles to 1024 bytes
     const int sms = cached_sm_count();
@@ -1246,19 +1257,11 @@ extern "C" int gnnseg_debug_read_cta(unsigned long long* out) {
 }
 #endif
 
-// gnnseg_mlp_pipe.cu: the warp-specialised form of the two kernels below (the default; GNNSEG_MLP64=serial picks these)
-int launch_node_mlp_pipe64(const float*, const float*, const float*, int, int, const ProjOut&, float*, bool, cudaStream_t);
-int launch_input_pipe64(const float*, const float*, int, int, float*, const ProjOut&, float*, cudaStream_t);
-static bool mlp64_serial() {
-    static const bool v = [] { const char* e = std::getenv("GNNSEG_MLP64"); return e && e[0] == 's'; }();
-    return v;
-}
-
 int launch_node_mlp_tc64_ex(const float* blob, const float* X4, const float* h1, int ld_h1, int n_nodes, const ProjOut& out,
                             float* H_save, bool pdl, cudaStream_t st) {
     using C = Mlp64;
     if (n_nodes == 0) return GNNSEG_OK;
-    if (!mlp64_serial()) return launch_node_mlp_pipe64(blob, X4, h1, ld_h1, n_nodes, out, H_save, pdl, st);
+    if (mlp_pipe()) return launch_node_mlp_pipe(blob, X4, h1, ld_h1, n_nodes, 64, out, H_save, pdl, st);
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
     if (!ensure_dynamic_smem<node_mlp_kernel_tc64<false>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
     const int sms = cached_sm_count();
@@ -1284,7 +1287,7 @@ int launch_input_tc64_ex(const float* blob, const float* X, int n_nodes, int F, 
                          cudaStream_t st) {
     using C = Mlp64;
     if (n_nodes == 0) return GNNSEG_OK;
-    if (!mlp64_serial()) return launch_input_pipe64(blob, X, n_nodes, F, X4, out, H_save, st);
+    if (mlp_pipe()) return launch_input_pipe(blob, X, n_nodes, F, 64, X4, out, H_save, st);
     const int n_tiles = (n_nodes + C::TM - 1) / C::TM;
     if (!ensure_dynamic_smem<node_mlp_kernel_tc64<true>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
     const int sms = cached_sm_count();

@@ -1,13 +1,14 @@
 """clock64 stamps per role of CTA 0 of node_mlp_kernel_pipe64 (gnnseg_mlp_pipe.cu).
     make -C gnn_fpga_b200/csrc trace
-    GNNSEG_LIB=gnn_fpga_b200/libgnnseg_trace.so python scripts/pipe_trace.py [n_cols]
+    GNNSEG_LIB=gnn_fpga_b200/libgnnseg_trace.so python scripts/pipe_trace.py [n_cols | 0] [hidden_dim]
 (the instrumented library is a separate build, see the Makefile; the shipped one carries no stamps)."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from gnn_fpga_b200 import _lib, SegmentClassifier
 dev = torch.device("cuda:0")
-h, n = 64, 100000
+h = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+n = 100000 if h == 64 else 256000
 torch.manual_seed(0)
 model = SegmentClassifier(3, h, 8).to(dev).eval()
 L = _lib.lib()
@@ -17,7 +18,7 @@ X4 = torch.randn(n, 4, device=dev)
 rows = torch.tanh(torch.randn(n + 1, 5 * h, device=dev))
 status = torch.zeros(1, dtype=torch.int32, device=dev)
 ptr = lambda t: C.c_void_p(t.data_ptr())
-n_cols = int(sys.argv[1]) if len(sys.argv) > 1 else 5 * h
+n_cols = int(sys.argv[1]) if len(sys.argv) > 1 and int(sys.argv[1]) > 0 else 5 * h
 for _ in range(3):      # h1 in the first h floats of the rows it becomes, as in the forward
     _lib.check(L.gnnseg_state_mlp_step(ptr(blob), ptr(X4), ptr(rows), 5 * h, n, h, ptr(rows), n_cols, ptr(status), None), "state_mlp_step")
 torch.cuda.synchronize()
@@ -28,7 +29,7 @@ mma, epi, sto, ldr, wp = t
 t0 = mma[0, 0]
 r = lambda v: int(v - t0) if v else -1
 print("CTA 0, cycles since the MMA warp entered its loop; n_cols = %d" % n_cols)
-for it in range(8):
+for it in range(14):
     if mma[it, 0] == 0:
         break
     print("tile %d" % it)
