@@ -604,7 +604,7 @@ def record_of(res, args, world, workload, peak, peak_src):
                       "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"], "ms_per_step": e["sec"] / steps * 1e3,
                       "path": "model.predict_stream(store.batches(B)): the data set sits in a GraphStore (pinned host arena, built once at "
                               "load time: %.1f ms for this batch); per batch ONE library call (gnnseg_store_forward_batch): six H2D copies "
-                              "on a copy stream, batch assembly + forward on the compute stream, D2H of the scores into pinned memory on a "
+                              "on a copy stream followed there by the (lean) batch assembly, the forward on the compute stream, D2H of the scores into pinned memory on a "
                               "third stream; three batches in flight" % res["store_build_ms"],
                       "stages_ms": e["stages_ms"]}
         if e.get("sec_tuples"):

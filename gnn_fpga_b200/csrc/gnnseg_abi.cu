@@ -18,7 +18,7 @@ int build_csr(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int3
 int build_graph(const int32_t*, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
 int fused_gather_step(const float*, const GnnsegGraph*, const float*, int, float*, int, cudaStream_t);
 int edge_final_step(const float*, const GnnsegGraph*, const float*, int, int, int, int, float*, cudaStream_t);
-int build_adjacency(const GnnsegGraph*, int32_t*, int32_t*, int32_t*, cudaStream_t);
+int build_adjacency(const GnnsegGraph*, int32_t*, int32_t*, int32_t*, cudaStream_t, bool from_endpoints = false);
 size_t adjacency_entries(int, int);
 int launch_input_tc32_ex(const float*, const float*, int, int, float*, const ProjOut&, float*, cudaStream_t);
 int launch_input_tc64_ex(const float*, const float*, int, int, float*, const ProjOut&, float*, cudaStream_t);
@@ -26,7 +26,7 @@ int launch_node_mlp_tc32_ex(const float*, const float*, const float*, int, int, 
 int launch_node_mlp_tc64_ex(const float*, const float*, const float*, int, int, const ProjOut&, float*, bool, cudaStream_t);
 bool use_pdl(int);
 int assemble_batch(const int32_t*, int, int, int, int, int, const int32_t*, const int32_t*, const void*, const void*, int,
-                   const GnnsegGraphMut&, cudaStream_t);
+                   const GnnsegGraphMut&, cudaStream_t, bool lean = false);
 // gnnseg_backward.cu
 struct GradOut {
     float* w_in; float* b_in; float* w_e1; float* b_e1; float* w_e2; float* b_e2;
@@ -111,6 +111,12 @@ inline int state_mlp(const float* blob, const float* X4, const float* h1, int ld
 }
 
 constexpr int MAX_ITERS = 64;
+}  // namespace
+namespace gnnseg {
+// does gnnseg_forward_ex take the fused inference path for this width and these flags (given adjacency lists)?
+bool forward_is_fused(int h, int flags) { return fused_width(h) && !(flags & GNNSEG_FWD_EXACT) && !exact_env(); }
+}
+namespace {
 
 // Training workspace: everything the forward leaves behind for the backward pass, then the
 // backward scratch.  X4 | H[0..T] | h1[0..T-1] | P[0..T] | Q[0..max(T,1)-1] | e_in[T] | e_out[T] |
@@ -332,7 +338,7 @@ int gnnseg_forward_ex(const float* blob, const GnnsegGraph* g, const float* X, i
     int32_t* flag = status ? status : w.status;
     if (cudaMemsetAsync(flag, 0, sizeof(int32_t), st) != cudaSuccess) return GNNSEG_ECUDA;
 
-    const bool fused = fused_width(h) && g->adj_ptr && g->adj && !(flags & GNNSEG_FWD_EXACT) && !exact_env();
+    const bool fused = gnnseg::forward_is_fused(h, flags) && g->adj_ptr && g->adj;
     if (fused) {
         // gnnseg_fused.cu: input -> n_iters x (edge step inside the node step's CSR walk, tensor-core MLP) -> final
         // edge step over the in-edges of every node.  2 * n_iters + 2 launches.

@@ -86,6 +86,9 @@ __host__ __device__ __forceinline__ int adj_offset(const int cum, const int n) {
 // -> 2.86 trips per node group), while all SMs still sweep the same window of the batch at any moment.
 constexpr int ORDER_WINDOW = 4096;
 
+// ENDPOINTS: the neighbour of an entry is looked up through its slot (src[in_eid[k]], dst[out_eid[k]]) instead of read from
+// in_nbr / out_nbr: the lean batch assembly of the inference stream does not write those
+template <bool ENDPOINTS>
 __global__ void __launch_bounds__(256)
 build_adjacency_kernel(const GnnsegGraph g, int32_t* __restrict__ adj_ptr, int32_t* __restrict__ adj) {
     const int pad = g.n_nodes;
@@ -96,8 +99,14 @@ build_adjacency_kernel(const GnnsegGraph g, int32_t* __restrict__ adj_ptr, int32
         const int i1 = __ldg(g.in_ptr + n + 1), o1 = __ldg(g.out_ptr + n + 1);
         int w = adj_offset(i0 + o0, n);
         const int w_end = w + (((i1 - i0) + (o1 - o0) + 3) & ~3);
-        for (int k = i0; k < i1; ++k) { const int nb = __ldg(g.in_nbr + k); adj[w++] = nb >= 0 ? nb : pad; }
-        for (int k = o0; k < o1; ++k) { const int nb = __ldg(g.out_nbr + k); adj[w++] = nb >= 0 ? (nb | ADJ_OUT) : pad; }
+        for (int k = i0; k < i1; ++k) {
+            const int nb = ENDPOINTS ? __ldg(g.src + __ldg(g.in_eid + k)) : __ldg(g.in_nbr + k);
+            adj[w++] = nb >= 0 ? nb : pad;
+        }
+        for (int k = o0; k < o1; ++k) {
+            const int nb = ENDPOINTS ? __ldg(g.dst + __ldg(g.out_eid + k)) : __ldg(g.out_nbr + k);
+            adj[w++] = nb >= 0 ? (nb | ADJ_OUT) : pad;
+        }
         while (w < w_end) adj[w++] = pad;
     }
 }
@@ -347,11 +356,12 @@ int edge_final_step(const float* blob, const GnnsegGraph* g, const float* P, int
 }
 size_t adjacency_entries(int n_nodes, int n_slots) { return 2 * (size_t)n_slots + 4 * (size_t)n_nodes + 8; }
 
-int build_adjacency(const GnnsegGraph* g, int32_t* adj_ptr, int32_t* adj, int32_t* order, cudaStream_t st) {
+int build_adjacency(const GnnsegGraph* g, int32_t* adj_ptr, int32_t* adj, int32_t* order, cudaStream_t st, bool from_endpoints) {
     int grid = (g->n_nodes + 1 + 255) / 256;
     const int cap = 148 * 8;
     if (grid > cap) grid = cap;
-    build_adjacency_kernel<<<grid, 256, 0, st>>>(*g, adj_ptr, adj);
+    if (from_endpoints) build_adjacency_kernel<true><<<grid, 256, 0, st>>>(*g, adj_ptr, adj);
+    else build_adjacency_kernel<false><<<grid, 256, 0, st>>>(*g, adj_ptr, adj);
     if (order && g->n_nodes > 0) build_order_kernel<<<(g->n_nodes + ORDER_WINDOW - 1) / ORDER_WINDOW, 256, 0, st>>>(*g, order);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }

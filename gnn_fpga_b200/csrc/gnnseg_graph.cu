@@ -295,7 +295,8 @@ int build_graph(const int32_t* src, const int32_t* dst, int n_slots, int n_nodes
 // the store was validated at load time (no column listed twice), so every slot has one writer.
 // meta = [node_off (B+1) | in_base (B+1) | out_base (B+1)]: first node / first in-entry / first out-entry
 // of every event relative to the batch.
-template <typename ColT>
+// LEAN: only what the fused inference path reads (endpoints per slot, row pointers, slot ids in CSR order): no inverse maps
+template <typename ColT, bool LEAN>
 __global__ void __launch_bounds__(256)
 assemble_rows_kernel(const int32_t* __restrict__ meta, const int B, const int n_nodes, const int e_max,
                      const int32_t* __restrict__ in_ptr_l, const int32_t* __restrict__ out_ptr_l,
@@ -320,7 +321,7 @@ assemble_rows_kernel(const int32_t* __restrict__ meta, const int B, const int n_
                 const int slot = slot0 + (int)in_col[k];
                 g.dst[slot] = n;
                 g.in_eid[k] = slot;
-                g.in_pos[slot] = k;
+                if (!LEAN) g.in_pos[slot] = k;
             }
         }
         {
@@ -331,7 +332,7 @@ assemble_rows_kernel(const int32_t* __restrict__ meta, const int B, const int n_
                 const int slot = slot0 + (int)out_col[k];
                 g.src[slot] = n;
                 g.out_eid[k] = slot;
-                g.out_pos[slot] = k;
+                if (!LEAN) g.out_pos[slot] = k;
             }
         }
     }
@@ -347,12 +348,13 @@ assemble_nbr_kernel(const int n_in, const int n_out, GnnsegGraphMut g) {
 
 int assemble_batch(const int32_t* meta, int B, int n_nodes, int e_max, int n_in, int n_out, const int32_t* in_ptr_l,
                    const int32_t* out_ptr_l, const void* in_col, const void* out_col, int col_bytes,
-                   const GnnsegGraphMut& g, cudaStream_t st) {
+                   const GnnsegGraphMut& g, cudaStream_t st, bool lean) {
     const size_t n_slots = (size_t)B * e_max;
     if (n_slots > 0) {
         // padding slots (and half edges) carry -1
-        if (cudaMemsetAsync(g.src, 0xFF, n_slots * 4, st) != cudaSuccess || cudaMemsetAsync(g.dst, 0xFF, n_slots * 4, st) != cudaSuccess ||
-            cudaMemsetAsync(g.in_pos, 0xFF, n_slots * 4, st) != cudaSuccess || cudaMemsetAsync(g.out_pos, 0xFF, n_slots * 4, st) != cudaSuccess)
+        if (cudaMemsetAsync(g.src, 0xFF, n_slots * 4, st) != cudaSuccess || cudaMemsetAsync(g.dst, 0xFF, n_slots * 4, st) != cudaSuccess)
+            return GNNSEG_ECUDA;
+        if (!lean && (cudaMemsetAsync(g.in_pos, 0xFF, n_slots * 4, st) != cudaSuccess || cudaMemsetAsync(g.out_pos, 0xFF, n_slots * 4, st) != cudaSuccess))
             return GNNSEG_ECUDA;
     }
     if (n_nodes == 0) {
@@ -361,13 +363,15 @@ int assemble_batch(const int32_t* meta, int B, int n_nodes, int e_max, int n_in,
         return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
     }
     const int grid = grid_for(n_nodes, 256, 148 * 8);
-    if (col_bytes == 2)
-        assemble_rows_kernel<uint16_t><<<grid, 256, 0, st>>>(meta, B, n_nodes, e_max, in_ptr_l, out_ptr_l,
-                                                             static_cast<const uint16_t*>(in_col), static_cast<const uint16_t*>(out_col), g);
-    else
-        assemble_rows_kernel<int32_t><<<grid, 256, 0, st>>>(meta, B, n_nodes, e_max, in_ptr_l, out_ptr_l,
-                                                            static_cast<const int32_t*>(in_col), static_cast<const int32_t*>(out_col), g);
-    if (n_in > 0 || n_out > 0)
+    auto rows = [&](auto kern, auto* ic, auto* oc) { kern<<<grid, 256, 0, st>>>(meta, B, n_nodes, e_max, in_ptr_l, out_ptr_l, ic, oc, g); };
+    if (col_bytes == 2) {
+        const uint16_t* ic = static_cast<const uint16_t*>(in_col), *oc = static_cast<const uint16_t*>(out_col);
+        if (lean) rows(assemble_rows_kernel<uint16_t, true>, ic, oc); else rows(assemble_rows_kernel<uint16_t, false>, ic, oc);
+    } else {
+        const int32_t* ic = static_cast<const int32_t*>(in_col), *oc = static_cast<const int32_t*>(out_col);
+        if (lean) rows(assemble_rows_kernel<int32_t, true>, ic, oc); else rows(assemble_rows_kernel<int32_t, false>, ic, oc);
+    }
+    if (!lean && (n_in > 0 || n_out > 0))
         assemble_nbr_kernel<<<grid_for(n_in > n_out ? n_in : n_out, 256, 148 * 8), 256, 0, st>>>(n_in, n_out, g);
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }

@@ -2,14 +2,23 @@
 // inference path.  Replaces, per batch, the reference's generator + model call + .cpu()
 // (gnn/trainSegmentClassifier.py:97-111, gnn/estimator.py:137-146) with a fixed sequence of asynchronous
 // CUDA calls on three caller-owned streams:
-//   copy stream     6 cudaMemcpyAsync out of the store's pinned arena (batch metadata + five contiguous slices)
-//   compute stream  waits for the copies; gnnseg_assemble_batch, gnnseg_build_adjacency, gnnseg_forward_ex
+//   copy stream     6 cudaMemcpyAsync out of the store's pinned arena (batch metadata + five contiguous slices), then the
+//                   batch assembly and the adjacency lists (two small kernels: they run next to the previous batch's forward)
+//   compute stream  waits for those; gnnseg_forward_ex
 //   out stream      waits for the forward; scores and the range flag back into pinned host memory
 // Nothing here synchronises with the host and the library keeps no state: the two events that order the
 // streams are created and destroyed inside the call.  The caller keeps `depth` slots (GnnsegBatchBuffers)
 // in flight and records its own event on the out stream after the call to know when a slot is done.
 #include <algorithm>
+#include <cstdlib>
 #include "gnnseg_common.cuh"
+
+namespace gnnseg {
+int assemble_batch(const int32_t*, int, int, int, int, int, const int32_t*, const int32_t*, const void*, const void*, int,
+                   const GnnsegGraphMut&, cudaStream_t, bool lean);                                   // gnnseg_graph.cu
+int build_adjacency(const GnnsegGraph*, int32_t*, int32_t*, int32_t*, cudaStream_t, bool from_endpoints);   // gnnseg_fused.cu
+bool forward_is_fused(int h, int flags);                                                              // gnnseg_abi.cu
+}
 
 namespace {
 
@@ -59,9 +68,11 @@ extern "C" int gnnseg_store_batch_shape_host(const GnnsegStoreLayout* layout, co
     return GNNSEG_OK;
 }
 
-extern "C" int gnnseg_store_load_batch(const GnnsegStoreLayout* layout, const void* arena_host, int lo, int hi,
-                                       const GnnsegBatchBuffers* bufs, void* copy_stream, void* compute_stream,
-                                       int32_t* shape_host) {
+// lean: the batch feeds the fused inference path only (no inverse maps, no neighbour arrays: gnnseg_graph.cu).
+// on_copy_stream: the assembly kernels run on the copy stream behind the batch's copies, i.e. next to the PREVIOUS batch's
+// forward on the compute stream instead of in front of this one's (they are small: they fill that forward's tails).
+static int load_batch(const GnnsegStoreLayout* layout, const void* arena_host, int lo, int hi, const GnnsegBatchBuffers* bufs,
+                      void* copy_stream, void* compute_stream, int32_t* shape_host, bool lean, bool on_copy_stream) {
     if (!layout || !arena_host || !bufs || lo < 0 || hi <= lo || hi > layout->n_events) return GNNSEG_EINVAL;
     if (!bufs->meta || !bufs->meta_host || !bufs->in_ptr || !bufs->out_ptr || !bufs->adj_ptr || !bufs->adj) return GNNSEG_EINVAL;
     const char* arena = static_cast<const char*>(arena_host);
@@ -86,17 +97,34 @@ extern "C" int gnnseg_store_load_batch(const GnnsegStoreLayout* layout, const vo
     ok = ok && copy(bufs->in_col, arena + layout->o_in_col + (int64_t)cb * i0, (size_t)cb * s.n_in);
     ok = ok && copy(bufs->out_col, arena + layout->o_out_col + (int64_t)cb * o0, (size_t)cb * s.n_out);
     if (!ok) return GNNSEG_ECUDA;
-    if (cs != ks) {
+    auto order_streams = [&]() {
+        if (cs == ks) return true;
         ScopedEvent e;
-        if (!e.ok || cudaEventRecord(e.ev, cs) != cudaSuccess || cudaStreamWaitEvent(ks, e.ev, 0) != cudaSuccess) return GNNSEG_ECUDA;
-    }
-    int rc = gnnseg_assemble_batch(bufs->meta, s.B, s.n_nodes, s.e_max, s.n_in, s.n_out, bufs->in_ptr_local, bufs->out_ptr_local,
-                                   bufs->in_col, bufs->out_col, cb, bufs->src, bufs->dst, bufs->in_ptr, bufs->in_eid, bufs->in_nbr,
-                                   bufs->in_pos, bufs->out_ptr, bufs->out_eid, bufs->out_nbr, bufs->out_pos, ks);
+        return e.ok && cudaEventRecord(e.ev, cs) == cudaSuccess && cudaStreamWaitEvent(ks, e.ev, 0) == cudaSuccess;
+    };
+    const cudaStream_t as = on_copy_stream ? cs : ks;             // where the assembly runs
+    if (!on_copy_stream && !order_streams()) return GNNSEG_ECUDA;
+    if ((int64_t)s.B * s.e_max > 0 && (!bufs->src || !bufs->dst || (!lean && (!bufs->in_pos || !bufs->out_pos)))) return GNNSEG_EINVAL;
+    if ((s.n_in > 0 && (!bufs->in_col || !bufs->in_eid || (!lean && !bufs->in_nbr))) ||
+        (s.n_out > 0 && (!bufs->out_col || !bufs->out_eid || (!lean && !bufs->out_nbr))))
+        return GNNSEG_EINVAL;
+    const gnnseg::GnnsegGraphMut gm{bufs->src, bufs->dst, bufs->in_ptr, bufs->in_eid, bufs->in_nbr, bufs->in_pos,
+                                    bufs->out_ptr, bufs->out_eid, bufs->out_nbr, bufs->out_pos};
+    int rc = gnnseg::assemble_batch(bufs->meta, s.B, s.n_nodes, s.e_max, s.n_in, s.n_out, bufs->in_ptr_local, bufs->out_ptr_local,
+                                    bufs->in_col, bufs->out_col, cb, gm, as, lean);
     if (rc != GNNSEG_OK) return rc;
     const GnnsegGraph g{s.n_nodes, s.B * s.e_max, bufs->src, bufs->dst, bufs->in_ptr, bufs->in_eid, bufs->in_nbr, bufs->out_ptr,
                         bufs->out_eid, bufs->out_nbr, bufs->in_pos, bufs->out_pos, nullptr, nullptr, nullptr};
-    return gnnseg_build_adjacency(&g, bufs->adj_ptr, bufs->adj, bufs->node_order, ks);
+    rc = gnnseg::build_adjacency(&g, bufs->adj_ptr, bufs->adj, bufs->node_order, as, lean);
+    if (rc != GNNSEG_OK) return rc;
+    if (on_copy_stream && !order_streams()) return GNNSEG_ECUDA;
+    return GNNSEG_OK;
+}
+
+extern "C" int gnnseg_store_load_batch(const GnnsegStoreLayout* layout, const void* arena_host, int lo, int hi,
+                                       const GnnsegBatchBuffers* bufs, void* copy_stream, void* compute_stream,
+                                       int32_t* shape_host) {
+    return load_batch(layout, arena_host, lo, hi, bufs, copy_stream, compute_stream, shape_host, false, false);
 }
 
 extern "C" int gnnseg_store_forward_batch(const GnnsegStoreLayout* layout, const void* arena_host, int lo, int hi,
@@ -104,7 +132,10 @@ extern "C" int gnnseg_store_forward_batch(const GnnsegStoreLayout* layout, const
                                           void* copy_stream, void* compute_stream, void* out_stream, int32_t* shape_host) {
     if (!bufs || !bufs->scores || !bufs->status || !bufs->ws) return GNNSEG_EINVAL;
     int32_t shape[4] = {0, 0, 0, 0};
-    int rc = gnnseg_store_load_batch(layout, arena_host, lo, hi, bufs, copy_stream, compute_stream, shape);
+    // GNNSEG_STREAM_ASSEMBLE (A/B runs): 0 = full assembly on the compute stream, 1 = lean, 2 = lean on the copy stream (default)
+    static const int mode = [] { const char* v = std::getenv("GNNSEG_STREAM_ASSEMBLE"); return v ? std::atoi(v) : 2; }();
+    const bool lean = mode >= 1 && gnnseg::forward_is_fused(h, flags);
+    int rc = load_batch(layout, arena_host, lo, hi, bufs, copy_stream, compute_stream, shape, lean, lean && mode >= 2);
     if (shape_host) for (int i = 0; i < 4; ++i) shape_host[i] = shape[i];
     if (rc != GNNSEG_OK) return rc;
     const int B = hi - lo, n_nodes = shape[0], e_max = shape[1];

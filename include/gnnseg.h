@@ -437,7 +437,11 @@ int gnnseg_assemble_batch(const int32_t* meta, int B, int n_nodes, int e_max, in
  *                                  slices); compute stream: waits for them, gnnseg_assemble_batch + gnnseg_build_adjacency
  *   gnnseg_store_forward_batch     the same, then gnnseg_forward_ex on the compute stream (blob from gnnseg_pack_weights,
  *                                  flags as gnnseg_forward_ex) and, on the out stream after it, scores -> scores_host and
- *                                  the range flag -> status_host (either may be NULL: the result stays on the device)
+ *                                  the range flag -> status_host (either may be NULL: the result stays on the device).
+ *                                  When the forward takes the fused inference path the assembly is the lean one (src, dst,
+ *                                  row pointers, in_eid, out_eid and the adjacency lists only: in_pos / out_pos / in_nbr /
+ *                                  out_nbr of the slot are NOT written) and runs on the copy stream behind the copies,
+ *                                  i.e. next to the previous batch's forward; the compute stream waits for it
  * GNNSEG_EWORKSPACE (with shape_host filled) when the batch exceeds a capacity.  No host synchronisation, no library
  * state: the events ordering the three streams live inside the call; the caller records its own event on the out
  * stream afterwards to learn when the slot may be reused.
