@@ -54,8 +54,9 @@ def make_graphs(wl, rank):
     cfg = WORKLOADS[wl]
     if wl == "toy2d":
         return data.toy2d_graphs(cfg["batch"], input_dim=3, seed=rank)
+    n_batch = int(os.environ.get("GNNSEG_BENCH_BATCH", cfg["batch"]))     # experiments only: another batch size
     return [data.acts_like_graph(cfg["n_tracks"], seed=rank * cfg["batch"] + b, edges_per_hit=cfg["edges_per_hit"])
-            for b in range(cfg["batch"])]
+            for b in range(n_batch)]
 
 
 def algorithmic_bytes(Nt, Et, F, h, n_iters):

@@ -25,6 +25,7 @@ int launch_input_tc64_ex(const float*, const float*, int, int, float*, const Pro
 int launch_node_mlp_tc32_ex(const float*, const float*, const float*, int, int, const ProjOut&, float*, bool, cudaStream_t);
 int launch_node_mlp_tc64_ex(const float*, const float*, const float*, int, int, const ProjOut&, float*, bool, cudaStream_t);
 bool use_pdl(int);
+bool use_pdl_mlp();
 int assemble_batch(const int32_t*, int, int, int, int, int, const int32_t*, const int32_t*, const void*, const void*, int,
                    const GnnsegGraphMut&, cudaStream_t, bool lean = false);
 // gnnseg_backward.cu
@@ -343,7 +344,7 @@ int gnnseg_forward_ex(const float* blob, const GnnsegGraph* g, const float* X, i
         // gnnseg_fused.cu: input -> n_iters x (edge step inside the node step's CSR walk, tensor-core MLP) -> final
         // edge step over the in-edges of every node.  2 * n_iters + 2 launches.
         const int n = g->n_nodes;
-        const bool pdl = gnnseg::use_pdl(g->n_slots);
+        const bool pdl = gnnseg::use_pdl_mlp();
         // row n of a state buffer is what an absent neighbour reads: zeros while the buffer feeds a node step
         if (cudaMemsetAsync(w.s[0] + (size_t)n * 5 * h, 0, sizeof(float) * 5 * h, st) != cudaSuccess ||
             cudaMemsetAsync(w.s[1] + (size_t)n * 5 * h, 0, sizeof(float) * 5 * h, st) != cudaSuccess)

@@ -758,12 +758,18 @@ static inline int persistent_grid(int threads, size_t smem, int n_tiles, int* gr
 }
 
 // Programmatic dependent launch pays where the forward is launch bound (Toy2D batch: 27.9 -> 26.1 us);
-// on the large batches it measured neutral to slightly negative (acts64: 0.683 -> 0.695 ms), so it
-// is used for small graphs only.  GNNSEG_PDL=0 / 1 forces it off / on (for A/B runs).
-bool use_pdl(const int n_slots) {
+// on the large batches it measured neutral to negative for the forward as a whole (round 2: acts64 0.562 ->
+// 0.569 ms, mu200 1.10 -> 1.31 ms), so it is used for small graphs only.  GNNSEG_PDL=0 / 1 forces it off / on (A/B).
+static int pdl_forced() {
     static const int forced = [] { const char* v = getenv("GNNSEG_PDL"); return v ? (v[0] == '0' ? 0 : 1) : -1; }();
-    return forced >= 0 ? forced == 1 : n_slots < (1 << 17);
+    return forced;
 }
+bool use_pdl(const int n_slots) { return pdl_forced() >= 0 ? pdl_forced() == 1 : n_slots < (1 << 17); }
+// The exception, at every size: the MLP launch of the fused path behind the fused gather.  The one-CTA-per-SM MLP kernel
+// gets onto an SM as soon as that SM's gather CTAs have left and runs its prologue (tensor-memory allocation, barriers,
+// weights) under the gather's tail: acts64 0.562 -> 0.556 ms, mu200 1.095 -> 1.074 ms.  The other direction (a gather
+// or the final edge step as the dependent of an MLP kernel) is what loses: mu200 1.095 -> 1.32 ms.
+bool use_pdl_mlp() { return pdl_forced() != 0; }
 
 static inline int check_launch() {
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;

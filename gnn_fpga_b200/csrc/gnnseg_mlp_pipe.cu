@@ -140,7 +140,9 @@ node_mlp_kernel_pipe(const float* __restrict__ blob, float* __restrict__ X4, con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    pdl_wait();                                       // h1 comes from the kernel before
+    // Launched as a programmatic dependent of the gather kernel: only the loader warps read what that kernel writes (h1)
+    // and wait for it below; every other role hangs on the loader through the barriers, and the weight stream and the
+    // X4 loads start under the gather's tail.
 
     if (warp == C::WARP_WP) {
         // ================================ weight warp =====================================
@@ -261,6 +263,7 @@ node_mlp_kernel_pipe(const float* __restrict__ blob, float* __restrict__ X4, con
                     if (n < r1) v[j] = lds4(h1 + (size_t)n * ld_h1 + 4 * (cq + 4 * (j % CPQ)));      // plain load: h1 may alias the output rows
                 }
             };
+            pdl_wait();                                            // h1 comes from the kernel before
             if (n_tiles > 0) fetch(0);
             for (int it = 0; it < n_tiles; ++it) {
                 if (warp == C::WARP_LD0) PT(3, it, 0);
