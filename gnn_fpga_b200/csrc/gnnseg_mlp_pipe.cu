@@ -1,29 +1,30 @@
-// hidden_dim = 64: the per-node MLP of the node step (and the input step) as a warp-specialised pipeline.
+// The per-node MLP of the node step (and the input step) as a warp-specialised pipeline, hidden_dim H = 32 and 64.
 //
 // Reference: NodeNetwork.forward's two Linear + Tanh layers after the segment sums, gnn/model.py:120-125, and
 // the InputNet + first projections, gnn/model.py:144-146, in the projection-first form of gnnseg_common.cuh:
-//     H'      = tanh(h1 . W4^T + b4)                                   128 x 64 x 64     (GEMM2)
-//     [P'|Q'] = [H'|X|1] . [W1a|W1b|W3a|W3b|W3c|bias]^T                128 x 72 x 320    (GEMM3, two chunks of 160)
+//     H'      = tanh(h1 . W4^T + b4)                                   128 x H x H           (GEMM2)
+//     [P'|Q'] = [H'|X|1] . [W1a|W1b|W3a|W3b|W3c|bias]^T                128 x (H + 8) x 5H    (GEMM3, chunks of 160 columns)
 // both as tcgen05.mma kind::tf32 with the 3xTF32 split (hi.hi + hi.lo + lo.hi, fp32 accumulators in tensor memory).
 //
-// Why another kernel: node_mlp_kernel_tc64 (gnnseg_node_tc.cu) runs one tile's chain strictly in sequence on one
-// CTA per SM (GEMM2 -> epilogue -> GEMM3a -> stores -> GEMM3b -> stores), 24 k cycles per tile of which 10 k are
-// the stores (1280 bytes per node leave the SM) and 5 k the tensor pipe.  Here every stage has its own warps and
-// its own mbarriers, so the chain of tile t + 1 runs under the stores of tile t:
+// Why: the round-1 kernels (gnnseg_node_tc.cu) run one tile's chain in sequence (GEMM2 -> epilogue -> GEMM3 -> stores;
+// at H = 64: 24 k cycles per tile of which 10 k are the stores -- 1280 bytes per node leave the SM -- and 5 k the
+// tensor pipe).  Here every stage has its own warps and its own mbarriers, so the chain of tile t + 1 runs under the
+// stores of tile t, and the kernel sits at the SM's store rate:
 //
 //   loader warps (8)   h1 rows of the NEXT tile (registers) -> tf32 hi / lo -> canonical K-major A2 tile in shared memory
 //   MMA warp (1)       one thread issues GEMM2 (SS), then per chunk GEMM3 (TS: A = [H'] hi / lo in tensor memory,
 //                      plus one SS k-step for the [X|1] slab in shared memory); tcgen05.commit -> mbarriers
 //   epilogue warps (8) D2 -> +b4, tanh, split -> A3 in tensor memory; X slab -> shared memory
 //   store warps (8)    D3 chunk -> (2^(log2e v) for the edge projections) -> swizzled 32 x 32 tile -> full lines
-//   weight warp (1)    the projection weight image (184 KB hi + lo) does not fit next to A2 and W4: its two halves
+//   weight warp (1)    H = 64: the projection weight image (184 KB hi + lo) does not fit next to A2 and W4: its two halves
 //                      go through one 92 KB buffer, cp.async.bulk + mbarrier complete_tx, half c + 1 as soon as
-//                      GEMM3 of chunk c has read half c
+//                      GEMM3 of chunk c has read half c.  H = 32 (one chunk, 51 KB): loaded once
 //
-// Tensor memory (512 columns): A3 hi [0, 64), A3 lo [64, 128), D2 [128, 192), D3 slot 0 [192, 352), slot 1
-// [352, 512).  Chunk g of the launch (two per tile when Q' is wanted, else one) goes to slot g & 1.
+// Tensor memory (512 columns allocated): A3 hi [0, H), A3 lo [H, 2H), D2 [2H, 3H), D3 slot 0 [3H, 3H + 160), slot 1
+// [3H + 160, 3H + 320).  Chunk g of the launch (two per tile at H = 64 when Q' is wanted, else one) goes to slot g & 1.
 // Every CTA takes ONE contiguous range of nodes (the stores bound the kernel, so the work is balanced by rows,
 // not by whole tiles: 100 000 nodes on 148 SMs are 5.28 tiles each, not 6 for some and 5 for others).
+// Launched as a programmatic dependent of the fused gather (gnnseg_forward.cu: use_pdl_mlp).
 #include <cstdlib>
 #include "gnnseg_tc.cuh"
 
