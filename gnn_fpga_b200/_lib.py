@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.abspath(os.environ["GNNSEG_LIB"]) if os.environ.get("GNNSEG_LIB") else os.path.join(_HERE, "libgnnseg_b200.so")
 
 OK = 0
-ABI_VERSION = 4
+ABI_VERSION = 5
 ERRORS = {-1: "EINVAL", -2: "EUNSUPPORTED", -3: "EWORKSPACE", -4: "ECUDA", -5: "ENODEVICE", -6: "EIO", -7: "EFORMAT", -8: "EHYPEREDGE"}
 EHYPEREDGE = -8
 BAD_VALUE = 1
@@ -53,7 +53,7 @@ class GnnsegBatchBuffers(C.Structure):
                 [(n, C.c_void_p) for n in ("meta", "X", "in_ptr_local", "out_ptr_local", "in_col", "out_col", "src", "dst", "in_pos",
                                            "out_pos", "in_ptr", "out_ptr", "adj_ptr", "in_eid", "in_nbr", "out_eid", "out_nbr", "adj",
                                            "node_order", "scores", "status", "ws")] +
-                [("ws_bytes", C.c_size_t)] + [(n, C.c_void_p) for n in ("meta_host", "scores_host", "status_host")])
+                [("ws_bytes", C.c_size_t)] + [(n, C.c_void_p) for n in ("meta_host", "scores_host", "status_host", "assemble_stream")])
 
 
 class GnnsegGraph(C.Structure):

@@ -97,13 +97,14 @@ static int load_batch(const GnnsegStoreLayout* layout, const void* arena_host, i
     ok = ok && copy(bufs->in_col, arena + layout->o_in_col + (int64_t)cb * i0, (size_t)cb * s.n_in);
     ok = ok && copy(bufs->out_col, arena + layout->o_out_col + (int64_t)cb * o0, (size_t)cb * s.n_out);
     if (!ok) return GNNSEG_ECUDA;
-    auto order_streams = [&]() {
-        if (cs == ks) return true;
+    auto order_streams = [&](cudaStream_t from, cudaStream_t to) {
+        if (from == to) return true;
         ScopedEvent e;
-        return e.ok && cudaEventRecord(e.ev, cs) == cudaSuccess && cudaStreamWaitEvent(ks, e.ev, 0) == cudaSuccess;
+        return e.ok && cudaEventRecord(e.ev, from) == cudaSuccess && cudaStreamWaitEvent(to, e.ev, 0) == cudaSuccess;
     };
-    const cudaStream_t as = on_copy_stream ? cs : ks;             // where the assembly runs
-    if (!on_copy_stream && !order_streams()) return GNNSEG_ECUDA;
+    // where the assembly runs: the compute stream, or (lean mode) the copy stream / the slot's own assembly stream
+    const cudaStream_t as = !on_copy_stream ? ks : (bufs->assemble_stream ? static_cast<cudaStream_t>(bufs->assemble_stream) : cs);
+    if (!order_streams(cs, as)) return GNNSEG_ECUDA;
     if ((int64_t)s.B * s.e_max > 0 && (!bufs->src || !bufs->dst || (!lean && (!bufs->in_pos || !bufs->out_pos)))) return GNNSEG_EINVAL;
     if ((s.n_in > 0 && (!bufs->in_col || !bufs->in_eid || (!lean && !bufs->in_nbr))) ||
         (s.n_out > 0 && (!bufs->out_col || !bufs->out_eid || (!lean && !bufs->out_nbr))))
@@ -117,7 +118,7 @@ static int load_batch(const GnnsegStoreLayout* layout, const void* arena_host, i
                         bufs->out_eid, bufs->out_nbr, bufs->in_pos, bufs->out_pos, nullptr, nullptr, nullptr};
     rc = gnnseg::build_adjacency(&g, bufs->adj_ptr, bufs->adj, bufs->node_order, as, lean);
     if (rc != GNNSEG_OK) return rc;
-    if (on_copy_stream && !order_streams()) return GNNSEG_ECUDA;
+    if (!order_streams(as, ks)) return GNNSEG_ECUDA;
     return GNNSEG_OK;
 }
 

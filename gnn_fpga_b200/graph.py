@@ -426,7 +426,8 @@ class DeviceBatchBuffers:
                 p(t["meta"]), p(t["X"]), p(t["in_ptr_l"]), p(t["out_ptr_l"]), p(t["in_col"]), p(t["out_col"]), p(t["src"]), p(t["dst"]),
                 p(t["in_pos"]), p(t["out_pos"]), p(t["in_ptr"]), p(t["out_ptr"]), p(t["adj_ptr"]), p(t["in_eid"]), p(t["in_nbr"]),
                 p(t["out_eid"]), p(t["out_nbr"]), p(t["adj"]), p(t["node_order"]), p(t["scores"]), p(t["status"]), p(ws),
-                ws.numel() if ws is not None else 0, p(self.meta_host), p(self.scores_host), p(self.status_host)))
+                ws.numel() if ws is not None else 0, p(self.meta_host), p(self.scores_host), p(self.status_host),
+                getattr(self, "assemble_stream", None)))
         return self._struct[1]
 
     def fits(self, n_nodes, n_in, n_out, n_slots, B):

@@ -246,7 +246,8 @@ class SegmentClassifier(nn.Module):
         # streams are kept on the model between calls: allocating pinned memory costs more than a batch
         cache = self._stream_cache if self._stream_cache is not None and self._stream_cache["dev"] == dev else None
         if cache is None:
-            cache = self._stream_cache = {"dev": dev, "slots": [], "streams": (torch.cuda.Stream(dev), torch.cuda.Stream(dev))}
+            cache = self._stream_cache = {"dev": dev, "slots": [], "streams": (torch.cuda.Stream(dev), torch.cuda.Stream(dev)),
+                                          "assemble": torch.cuda.Stream(dev)}
         while len(cache["slots"]) < depth + 1:
             cache["slots"].append({"bufs": None, "done": None, "view": None, "flag": None, "arena": None, "h2d": None})
         slots = cache["slots"][:depth + 1]
@@ -326,6 +327,8 @@ class SegmentClassifier(nn.Module):
                             g = lambda v: int(v * 1.25) + 1
                             s["bufs"] = DeviceBatchBuffers(dev, g(n), g(n_in), g(n_out), g(B * e_max), B, store.F,
                                                            store.col_bytes).with_host_results()
+                            if os.environ.get("GNNSEG_ASSEMBLE_OWN_STREAM", "1") != "0":     # the batch assembly on a stream of its own
+                                s["bufs"].assemble_stream = cache["assemble"].cuda_stream
                         bufs = s["bufs"]
                         rc = _lib.EWORKSPACE
                         if bufs.F == store.F and bufs.col_bytes == store.col_bytes:

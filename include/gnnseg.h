@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNSEG_ABI_VERSION 4
+#define GNNSEG_ABI_VERSION 5
 
 /* error codes */
 #define GNNSEG_OK            0
@@ -466,6 +466,9 @@ typedef struct GnnsegBatchBuffers {
     int32_t* meta_host;       /* pinned [3 * (cap_events + 1)]                           */
     float*   scores_host;     /* pinned [cap_slots] or NULL                              */
     int32_t* status_host;     /* pinned [1] or NULL                                      */
+    void*    assemble_stream; /* nullable: a fourth stream for the lean assembly kernels of gnnseg_store_forward_batch
+                                 (default: the copy stream).  With its own stream the next batch's copies do not queue
+                                 behind assembly kernels that wait for a free SM (eight ranks sharing a host)      */
 } GnnsegBatchBuffers;
 int gnnseg_store_batch_shape_host(const GnnsegStoreLayout* layout, const void* arena_host, int lo, int hi,
                                   int32_t* shape_host);

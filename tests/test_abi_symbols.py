@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_host_only_queries():
     L = _lib.lib()
-    assert L.gnnseg_abi_version() == _lib.ABI_VERSION == 4
+    assert L.gnnseg_abi_version() == _lib.ABI_VERSION == 5
     assert L.gnnseg_strerror(0) == b"ok"
     assert b"unsupported" in L.gnnseg_strerror(-2)
     for h in (4, 8, 16, 32, 64):
