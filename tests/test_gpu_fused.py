@@ -189,3 +189,39 @@ def test_range_flag_raises_and_exact_path_is_the_cure(cuda_device):
     X, src, dst, e_max = O.flatten_sparse_batch([g])
     ref = O.sparse_forward(p, X, src, dst, 2, torch.float64).numpy()
     assert np.max(np.abs(out - ref)) <= 1e-4
+
+
+_AB_SCRIPT = """
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+sys.path.insert(0, {tests!r})
+from conftest import load_case
+from test_gpu_parity import make_model, sparse_graphs_of
+dev = torch.device("cuda:0")
+out = {{}}
+for name in {cases!r}:
+    rec = load_case(name)
+    model = make_model(rec, dev)
+    with torch.no_grad():
+        out[name] = model(sparse_graphs_of(rec)).cpu().numpy()
+np.savez({dst!r}, **out)
+"""
+
+
+def test_pipeline_mlp_kernels_equal_the_round1_kernels(tmp_path, cuda_device):
+    """The warp-specialised MLP / input kernels (gnnseg_mlp_pipe.cu, the default) against the two-CTA / serial tcgen05
+    kernels of gnnseg_node_tc.cu (GNNSEG_MLP_PIPE=0): same GEMMs, same 3xTF32 split, same k order, so the forward's
+    scores must agree to the last bit.  The switch is read once per process: two child processes."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for pipe in ("1", "0"):
+        dst = str(tmp_path / ("scores_pipe%s.npz" % pipe))
+        code = _AB_SCRIPT.format(root=root, tests=os.path.join(root, "tests"), cases=CASES, dst=dst)
+        env = dict(os.environ, GNNSEG_MLP_PIPE=pipe)
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+        res[pipe] = np.load(dst)
+    for name in CASES:
+        assert np.array_equal(res["1"][name], res["0"][name]), name
