@@ -645,7 +645,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpus = None
     if world > 1:
+        if os.environ.get("GNNSEG_BIND_CPUS", "1") != "0":       # pinned host memory on the GPU's own NUMA node
+            from gnn_fpga_b200.dist import bind_to_local_cpus
+            cpus = bind_to_local_cpus(local_rank)
         dist.init_process_group("nccl", device_id=dev)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -688,6 +692,7 @@ def main():
             line["value_with_gather"] = res["all_edges"] * args.steps / (res["total_ms_with_gather"] * 1e-3)
             line["ms_per_step_with_gather"] = res["total_ms_with_gather"] / args.steps
             line["gathered_scores_bit_equal_to_local_recompute"] = res.get("gather_bit_equal")
+            line["rank0_cpu_binding"] = ("%d cores next to the GPU (gnn_fpga_b200.dist.bind_to_local_cpus)" % len(cpus)) if cpus else "none"
         if sub is not None:
             line["mu200"] = record_of(sub, args, world, "mu200", peak, peak_src)
         if world == 1 and not args.no_cpu_baseline:

@@ -35,6 +35,31 @@ def shard_bounds(n_events, world, weights=None):
     return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
 
 
+def bind_to_local_cpus(device_index):
+    """Restrict this process to the CPU cores next to its GPU (the `local_cpulist` of the GPU's PCI device in sysfs)
+    BEFORE it allocates pinned host memory: the event store's arena and the pinned result buffers are then first
+    touched, i.e. placed, on the GPU's own NUMA node, and the H2D / D2H copies of several ranks sharing a host do
+    not cross the socket interconnect.  Returns the core list, or None when the topology cannot be read (then
+    nothing is changed).  One process per GPU (torchrun): call it right after choosing the device."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 class ScoreGatherer:
     """All-gather of the per-rank (B_r, E_r) score blocks into one (sum B_r, E_max) tensor on every rank
     (NaN where an event has fewer than E_max slots on its rank), the only collective of the inference path.
