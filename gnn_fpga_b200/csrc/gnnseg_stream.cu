@@ -133,8 +133,12 @@ extern "C" int gnnseg_store_forward_batch(const GnnsegStoreLayout* layout, const
                                           void* copy_stream, void* compute_stream, void* out_stream, int32_t* shape_host) {
     if (!bufs || !bufs->scores || !bufs->status || !bufs->ws) return GNNSEG_EINVAL;
     int32_t shape[4] = {0, 0, 0, 0};
-    // GNNSEG_STREAM_ASSEMBLE (A/B runs): 0 = full assembly on the compute stream, 1 = lean, 2 = lean on the copy stream (default)
-    static const int mode = [] { const char* v = std::getenv("GNNSEG_STREAM_ASSEMBLE"); return v ? std::atoi(v) : 2; }();
+    // Where the batch assembly runs.  GNNSEG_STREAM_ASSEMBLE (A/B runs): 0 = full assembly on the compute stream, 1 = lean
+    // assembly on the compute stream, 2 = lean assembly next to the previous batch's forward (copy / assembly stream).
+    // Default: 2, except at hidden_dim 64, where the concurrent form measured slower (mu200 event: 1.36 against 1.23 ms
+    // per batch; acts64, hidden_dim 32: 0.63 against 0.73 ms).
+    static const int forced = [] { const char* v = std::getenv("GNNSEG_STREAM_ASSEMBLE"); return v ? std::atoi(v) : -1; }();
+    const int mode = forced >= 0 ? forced : (h == 64 ? 1 : 2);
     const bool lean = mode >= 1 && gnnseg::forward_is_fused(h, flags);
     int rc = load_batch(layout, arena_host, lo, hi, bufs, copy_stream, compute_stream, shape, lean, lean && mode >= 2);
     if (shape_host) for (int i = 0; i < 4; ++i) shape_host[i] = shape[i];
