@@ -287,6 +287,36 @@ def cpu_baseline(workload, budget_s=15.0):
     return out
 
 
+def mu200_throughput(dev, steps, warmup, n_events=4):
+    """configs[3] asks for single-event latency AND throughput: the same forward on a batch of `n_events` mu200-like
+    events (batch resident, CUDA graph, L2 flushed between steps), so that the fixed cost per launch is shared."""
+    from gnn_fpga_b200 import SegmentClassifier, DeviceGraphBatch, GraphStore, data
+    cfg = WORKLOADS["mu200"]
+    graphs = [data.acts_like_graph(cfg["n_tracks"], seed=b, edges_per_hit=cfg["edges_per_hit"]) for b in range(n_events)]
+    torch.manual_seed(0)
+    model = SegmentClassifier(cfg["F"], cfg["h"], cfg["n_iters"]).to(dev).eval()
+    batch = DeviceGraphBatch.from_store(GraphStore.from_sparse_graphs(graphs, reorder="none"), 0, n_events, dev)
+    n_real = batch.count_real_edges()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    steps = min(steps, 50)
+    with torch.no_grad():
+        for _ in range(warmup):
+            model(batch)
+        torch.cuda.synchronize(dev)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for i in range(steps):
+            flush.zero_()
+            starts[i].record()
+            model._run(batch)
+            ends[i].record()
+        torch.cuda.synchronize(dev)
+        model.check_range()
+    ms = float(sum(s_.elapsed_time(e_) for s_, e_ in zip(starts, ends))) / steps
+    return {"batch": n_events, "ms_per_step": ms, "ms_per_event": ms / n_events, "value": n_real / (ms * 1e-3), "unit": "edges/s",
+            "events_per_sec": n_events / (ms * 1e-3), "steps": steps}
+
+
 # -----------------------------------------------------------------------------------------
 def measure_workload(workload, args, rank, world, local_rank, dev, dist, sampler=None, light=False):
     """Everything bench.py reports for one workload on this rank: device-timed forward (`value`), per-kernel
@@ -695,6 +725,7 @@ def main():
             line["rank0_cpu_binding"] = ("%d cores next to the GPU (gnn_fpga_b200.dist.bind_to_local_cpus)" % len(cpus)) if cpus else "none"
         if sub is not None:
             line["mu200"] = record_of(sub, args, world, "mu200", peak, peak_src)
+            line["mu200"]["throughput_batch4"] = mu200_throughput(dev, args.steps, args.warmup)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
             if sub is not None:
