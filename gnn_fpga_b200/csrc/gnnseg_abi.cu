@@ -38,7 +38,7 @@ struct TrainState {
     const float* x4;
     const float* const* Hs; const float* const* h1s; const float* const* Ps; const float* const* Qs;
     const float* const* e_in; const float* const* e_out;
-    float* dg; float* dproj; float* ds_in; float* ds_out; float* partE; float* partN;
+    float* dg; float* dproj; float* ds_in; float* ds_out; float* partE; float* partN; float* dz;
 };
 size_t edge_part_floats(int h);
 size_t node_part_floats(int h);
@@ -130,7 +130,7 @@ struct TrainWorkspace {
     float* Q[MAX_ITERS];
     float* e_in[MAX_ITERS];
     float* e_out[MAX_ITERS];
-    float* dg; float* dproj; float* ds_in; float* ds_out; float* partE; float* partN;
+    float* dg; float* dproj; float* ds_in; float* ds_out; float* partE; float* partN; float* dz;
     size_t bytes;
 };
 
@@ -157,6 +157,7 @@ TrainWorkspace carve_train(void* ws, int n_nodes, int n_slots, int h, int T) {
     w.ds_out = take(m);
     w.partE = take(gnnseg::edge_part_floats(h));
     w.partN = take(gnnseg::node_part_floats(h));
+    w.dz = take(n * h);
     w.bytes = off;
     return w;
 }
@@ -568,7 +569,7 @@ int gnnseg_backward(const float* blob, const GnnsegParams* masks, const GnnsegGr
     gnnseg::TrainState s;
     s.x4 = w.x4;
     s.Hs = w.H; s.h1s = w.h1; s.Ps = w.P; s.Qs = w.Q; s.e_in = w.e_in; s.e_out = w.e_out;
-    s.dg = w.dg; s.dproj = w.dproj; s.ds_in = w.ds_in; s.ds_out = w.ds_out; s.partE = w.partE; s.partN = w.partN;
+    s.dg = w.dg; s.dproj = w.dproj; s.ds_in = w.ds_in; s.ds_out = w.ds_out; s.partE = w.partE; s.partN = w.partN; s.dz = w.dz;
     gnnseg::GradOut go;
     go.w_in = grads->w_in; go.b_in = grads->b_in; go.w_e1 = grads->w_e1; go.b_e1 = grads->b_e1;
     go.w_e2 = grads->w_e2; go.b_e2 = grads->b_e2; go.w_n1 = grads->w_n1; go.b_n1 = grads->b_n1;
@@ -618,7 +619,7 @@ int gnnseg_backward_nodes(const float* blob, const float* head_blob, const Gnnse
     gnnseg::TrainState s;
     s.x4 = w.x4;
     s.Hs = w.H; s.h1s = w.h1; s.Ps = w.P; s.Qs = w.Q; s.e_in = w.e_in; s.e_out = w.e_out;
-    s.dg = w.dg; s.dproj = w.dproj; s.ds_in = w.ds_in; s.ds_out = w.ds_out; s.partE = w.partE; s.partN = w.partN;
+    s.dg = w.dg; s.dproj = w.dproj; s.ds_in = w.ds_in; s.ds_out = w.ds_out; s.partE = w.partE; s.partN = w.partN; s.dz = w.dz;
     gnnseg::GradOut go;
     go.w_in = grads->w_in; go.b_in = grads->b_in; go.w_e1 = grads->w_e1; go.b_e1 = grads->b_e1;
     go.w_e2 = grads->w_e2; go.b_e2 = grads->b_e2; go.w_n1 = grads->w_n1; go.b_n1 = grads->b_n1;

@@ -21,6 +21,7 @@
 //                            dg_{t-1} = (dz.W4)*(1-h1_{t-1}^2)            (t = 0: dWin, dbin instead)
 // The last edge step (scores) enters the same kernels with ds_j = dL/dscore_j * p_j (1-p_j).
 #include <cmath>
+#include <cstdlib>
 #include "gnnseg_common.cuh"
 
 namespace gnnseg {
@@ -295,19 +296,22 @@ __device__ __forceinline__ void dot_gemm(const float* __restrict__ sA, const int
 // NB = 2: dproj rows are [dPs|dPd] (after the final edge step), 5: all five projections.
 // FIRST: H_in is H_0 (input network: dWin, dbin); otherwise H_in = H_t, t > 0, produced by node
 // step t-1 from h1_prev: dW4, db4 and dg_out = dL/dg_{t-1}.
-template <int H, int NB, bool FIRST>
+// WGRAD = false (hidden_dim 32 / 64): the weight gradients are left to wgrad_tc_kernel (gnnseg_wgrad_tc.cu, tcgen05); this
+// kernel then only propagates: dz -> dz_out (which that kernel reads), dg_out.
+template <int H, int NB, bool FIRST, bool WGRAD = true>
 __global__ void __launch_bounds__(DenseCfg<H>::NT, DenseCfg<H>::MINB)
 dense_bwd_kernel(const float* __restrict__ blob, const float* __restrict__ dproj, const float* __restrict__ H_in,
                  const float* __restrict__ X4, const float* __restrict__ h1_prev, const int n_nodes,
-                 const int n_tiles, float* __restrict__ dg_out, float* __restrict__ part, const int accumulate) {
+                 const int n_tiles, float* __restrict__ dg_out, float* __restrict__ part, const int accumulate,
+                 float* __restrict__ dz_out = nullptr) {
     using C = DenseCfg<H>;
     using B = Blob<H>;
     using NP = NodePart<H>;
     constexpr int TN = C::TN, NT = C::NT, D4 = C::D4, LW = C::LW, LH = C::LH, LX = C::LX, KG = C::KG, RN = C::RN;
     constexpr int NO = NB * H;                                        // live projection columns
-    constexpr int T_WP = ((D4 / 4) * (NO / 4) + NT - 1) / NT;         // register tiles per thread
-    constexpr int T_W4 = (KG * KG + NT - 1) / NT;
-    constexpr int T_WIN = (KG + NT - 1) / NT;
+    constexpr int T_WP = WGRAD ? ((D4 / 4) * (NO / 4) + NT - 1) / NT : 1;         // register tiles per thread
+    constexpr int T_W4 = WGRAD ? (KG * KG + NT - 1) / NT : 1;
+    constexpr int T_WIN = WGRAD ? (KG + NT - 1) / NT : 1;
     extern __shared__ __align__(16) float smem[];
     float* sWP = smem;                 // [D4][LW]   WP[k][o]
     float* sW4 = sWP + D4 * LW;        // [H][LH]    W4^T: [k][o]
@@ -360,8 +364,8 @@ dense_bwd_kernel(const float* __restrict__ blob, const float* __restrict__ dproj
         }
         __syncthreads();
         // weight gradients of the projections and their bias
-        outer_acc<D4 / 4, NO / 4, TN, NT, T_WP>(sHX, LX, sDP, LW, aWP);
-        if (threadIdx.x < NO) {
+        if (WGRAD) outer_acc<D4 / 4, NO / 4, TN, NT, T_WP>(sHX, LX, sDP, LW, aWP);
+        if (WGRAD && threadIdx.x < NO) {
 #pragma unroll 8
             for (int n = 0; n < TN; ++n) aBP += sDP[n * LW + threadIdx.x];
         }
@@ -371,16 +375,22 @@ dense_bwd_kernel(const float* __restrict__ blob, const float* __restrict__ dproj
             sDZ[ln * LH + k] = v * fmaf(-hv, hv, 1.f);
         });
         __syncthreads();
-        if (threadIdx.x < H) {
+        if (!WGRAD) {
+            for (int i = threadIdx.x; i < TN * KG; i += NT) {
+                const int ln = i / KG, c = i % KG, n = node0 + ln;
+                if (n < n_nodes) st4(dz_out + (size_t)n * H + 4 * c, lds4(sDZ + ln * LH + 4 * c));
+            }
+        }
+        if (WGRAD && threadIdx.x < H) {
 #pragma unroll 8
             for (int n = 0; n < TN; ++n) aB += sDZ[n * LH + threadIdx.x];
         }
         if (FIRST) {
             // H_0 = tanh(Win.X + bin): dWin^T[f][o] += X[n][f] dz[n][o]
-            outer_acc<1, KG, TN, NT, T_WIN>(sHX + H, LX, sDZ, LH, aWin);
+            if (WGRAD) outer_acc<1, KG, TN, NT, T_WIN>(sHX + H, LX, sDZ, LH, aWin);
         } else {
             // H_t = tanh(W4.h1 + b4): dW4[o][k] += dz[n][o] h1[n][k];  dg = (dz . W4) * (1 - h1^2)
-            outer_acc<KG, KG, TN, NT, T_W4>(sDZ, LH, sH1, LH, aW4);
+            if (WGRAD) outer_acc<KG, KG, TN, NT, T_W4>(sDZ, LH, sH1, LH, aW4);
             dot_gemm<H, KG, TN, NT, RN>(sDZ, LH, sW4, LH, [&](const int ln, const int k, const float v) {
                 const int n = node0 + ln;
                 const float h1v = sH1[ln * LH + k];
@@ -388,6 +398,7 @@ dense_bwd_kernel(const float* __restrict__ blob, const float* __restrict__ dproj
             });
         }
     }
+    if (!WGRAD) return;
     float* mine = part + (size_t)blockIdx.x * NP::SIZE;
     outer_store<D4 / 4, NO / 4, NT, T_WP>(mine + NP::WP, 5 * H, aWP, accumulate != 0);
     if (threadIdx.x < NO) mine[NP::BP + threadIdx.x] = accumulate ? mine[NP::BP + threadIdx.x] + aBP : aBP;
@@ -532,7 +543,19 @@ struct TrainState {          // device arrays saved by the training forward + ba
     float* ds_out;
     float* partE;
     float* partN;
+    float* dz;                   // n x h (tensor-core weight-gradient path)
 };
+
+// gnnseg_wgrad_tc.cu
+bool wgrad_tc_width(int h);
+int wgrad_tc_grid(int n_nodes, int h, int sms);
+int wgrad_tc(int h, int nb, bool first, const float* dproj, const float* H_in, const float* X4, const float* dz, const float* h1_prev,
+             int n_nodes, float* part, int accumulate, int grid, cudaStream_t st);
+// GNNSEG_DENSE_BWD=simt keeps the all-SIMT dense backward kernel at hidden_dim 32 / 64 (A/B runs)
+static bool wgrad_tc_enabled() {
+    static const bool on = [] { const char* v = getenv("GNNSEG_DENSE_BWD"); return !(v && v[0] == 's'); }();
+    return on;
+}
 
 template <int H>
 static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, const int T, const float* dscores,
@@ -556,29 +579,60 @@ static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, c
     int gridD = n_tiles < sms * C::MINB ? n_tiles : sms * C::MINB;
     if (gridD > DENSE_BWD_MAX_BLOCKS) gridD = DENSE_BWD_MAX_BLOCKS;
     if (gridD < 1) gridD = 1;
-    auto kF2 = dense_bwd_kernel<H, 2, true>;
-    auto kI2 = dense_bwd_kernel<H, 2, false>;
-    auto kF5 = dense_bwd_kernel<H, 5, true>;
-    auto kI5 = dense_bwd_kernel<H, 5, false>;
-    if (!ensure_dynamic_smem<dense_bwd_kernel<H, 2, true>>((int)C::SMEM_BYTES) ||
-        !ensure_dynamic_smem<dense_bwd_kernel<H, 2, false>>((int)C::SMEM_BYTES) ||
-        !ensure_dynamic_smem<dense_bwd_kernel<H, 5, true>>((int)C::SMEM_BYTES) ||
-        !ensure_dynamic_smem<dense_bwd_kernel<H, 5, false>>((int)C::SMEM_BYTES))
+    // hidden_dim 32 / 64: the propagating half of the dense step on CUDA cores (dz, dg), the weight gradients on tcgen05
+    constexpr bool TCW = (H == 32 || H == 64);
+    const bool tcw = TCW && wgrad_tc_enabled();
+    const int gridW = tcw ? wgrad_tc_grid(n, H, sms) : 0;
+    const int n_part = tcw ? gridW : gridD;                  // CTAs that own a slot of partN
+    if (tcw && gridW > DENSE_BWD_MAX_BLOCKS) return GNNSEG_EINVAL;
+    auto kF2 = dense_bwd_kernel<H, 2, true, !TCW>, kF2s = dense_bwd_kernel<H, 2, true, true>;
+    auto kI2 = dense_bwd_kernel<H, 2, false, !TCW>, kI2s = dense_bwd_kernel<H, 2, false, true>;
+    auto kF5 = dense_bwd_kernel<H, 5, true, !TCW>, kF5s = dense_bwd_kernel<H, 5, true, true>;
+    auto kI5 = dense_bwd_kernel<H, 5, false, !TCW>, kI5s = dense_bwd_kernel<H, 5, false, true>;
+    if (!ensure_dynamic_smem<dense_bwd_kernel<H, 2, true, true>>((int)C::SMEM_BYTES) ||
+        !ensure_dynamic_smem<dense_bwd_kernel<H, 2, false, true>>((int)C::SMEM_BYTES) ||
+        !ensure_dynamic_smem<dense_bwd_kernel<H, 5, true, true>>((int)C::SMEM_BYTES) ||
+        !ensure_dynamic_smem<dense_bwd_kernel<H, 5, false, true>>((int)C::SMEM_BYTES) ||
+        !ensure_dynamic_smem<dense_bwd_kernel<H, 2, true, !TCW>>((int)C::SMEM_BYTES) ||
+        !ensure_dynamic_smem<dense_bwd_kernel<H, 2, false, !TCW>>((int)C::SMEM_BYTES) ||
+        !ensure_dynamic_smem<dense_bwd_kernel<H, 5, true, !TCW>>((int)C::SMEM_BYTES) ||
+        !ensure_dynamic_smem<dense_bwd_kernel<H, 5, false, !TCW>>((int)C::SMEM_BYTES))
         return GNNSEG_ECUDA;
+    int rc_w = GNNSEG_OK;
+    // one dense step: nb = 2 / 5 projections live in dproj, first = the input step
+    auto dense = [&](const float* wblob, const int nb, const bool first, const float* Hin, const float* h1p, float* dg_out, const int acc) {
+        if (tcw) {
+            if (nb == 2) {
+                if (first) kF2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(wblob, s.dproj, Hin, s.x4, nullptr, n, n_tiles, nullptr, s.partN, acc, s.dz);
+                else kI2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(wblob, s.dproj, Hin, s.x4, h1p, n, n_tiles, dg_out, s.partN, acc, s.dz);
+            } else {
+                if (first) kF5<<<gridD, C::NT, C::SMEM_BYTES, st>>>(wblob, s.dproj, Hin, s.x4, nullptr, n, n_tiles, nullptr, s.partN, acc, s.dz);
+                else kI5<<<gridD, C::NT, C::SMEM_BYTES, st>>>(wblob, s.dproj, Hin, s.x4, h1p, n, n_tiles, dg_out, s.partN, acc, s.dz);
+            }
+            const int rc = wgrad_tc(H, nb, first, s.dproj, Hin, s.x4, s.dz, h1p, n, s.partN, acc, gridW, st);
+            if (rc != GNNSEG_OK) rc_w = rc;
+        } else {
+            if (nb == 2) {
+                if (first) kF2s<<<gridD, C::NT, C::SMEM_BYTES, st>>>(wblob, s.dproj, Hin, s.x4, nullptr, n, n_tiles, nullptr, s.partN, acc, nullptr);
+                else kI2s<<<gridD, C::NT, C::SMEM_BYTES, st>>>(wblob, s.dproj, Hin, s.x4, h1p, n, n_tiles, dg_out, s.partN, acc, nullptr);
+            } else {
+                if (first) kF5s<<<gridD, C::NT, C::SMEM_BYTES, st>>>(wblob, s.dproj, Hin, s.x4, nullptr, n, n_tiles, nullptr, s.partN, acc, nullptr);
+                else kI5s<<<gridD, C::NT, C::SMEM_BYTES, st>>>(wblob, s.dproj, Hin, s.x4, h1p, n, n_tiles, dg_out, s.partN, acc, nullptr);
+            }
+        }
+    };
     // the dense kernel's partial holds slots (W4/B4 or WIN/BIN) that some launches never write
-    zero_kernel<<<64, 256, 0, st>>>(s.partN, (size_t)gridD * NodePart<H>::SIZE);
+    zero_kernel<<<64, 256, 0, st>>>(s.partN, (size_t)n_part * NodePart<H>::SIZE);
 
     const bool nodes = head_blob != nullptr;     // NodeClassifier: dscores is per node, no final edge step
     if (nodes) {
         zero_kernel<<<64, 256, 0, st>>>(s.partE, (size_t)gridE * EdgePart<H>::SIZE);
         if (n > 0) {
             head_bwd_kernel<H><<<gridG, 256, 0, st>>>(s.Ps[T], dscores, n, s.dproj);
-            if (T == 0)
-                kF2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(head_blob, s.dproj, s.Hs[0], s.x4, nullptr, n, n_tiles, nullptr, s.partN, 0);
-            else
-                kI2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(head_blob, s.dproj, s.Hs[T], s.x4, s.h1s[T - 1], n, n_tiles, s.dg, s.partN, 0);
+            if (T == 0) dense(head_blob, 2, true, s.Hs[0], nullptr, nullptr, 0);
+            else dense(head_blob, 2, false, s.Hs[T], s.h1s[T - 1], s.dg, 0);
         }
-        head_grad_kernel<H><<<1, 128, 0, st>>>(s.partN, n > 0 ? gridD : 0, F + H, g_wout, g_bout);
+        head_grad_kernel<H><<<1, 128, 0, st>>>(s.partN, n > 0 ? n_part : 0, F + H, g_wout, g_bout);
     } else {
         // ---- final edge step: scores = edge(P_T) ------------------------------------------------
         if (m > 0)
@@ -589,10 +643,8 @@ static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, c
         if (n > 0) {
             gather_bwd_kernel<H, true><<<gridG, 256, 0, st>>>(blob, *g, s.Ps[T], nullptr, nullptr, nullptr, s.ds_in,
                                                                s.ds_out, s.dproj);
-            if (T == 0)
-                kF2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(blob, s.dproj, s.Hs[0], s.x4, nullptr, n, n_tiles, nullptr, s.partN, 0);
-            else
-                kI2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(blob, s.dproj, s.Hs[T], s.x4, s.h1s[T - 1], n, n_tiles, s.dg, s.partN, 0);
+            if (T == 0) dense(blob, 2, true, s.Hs[0], nullptr, nullptr, 0);
+            else dense(blob, 2, false, s.Hs[T], s.h1s[T - 1], s.dg, 0);
         }
     }
     // ---- iterations T-1 .. 0 ------------------------------------------------------------------
@@ -603,12 +655,11 @@ static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, c
         gather_bwd_kernel<H, false><<<gridG, 256, 0, st>>>(blob, *g, s.Ps[t], s.dg, s.e_in[t], s.e_out[t], s.ds_in,
                                                             s.ds_out, s.dproj);
         // accumulate: 1 = projections only (the W4 slots are first written by launch T-1 ... ), 2 = W4 too
-        if (t == 0)
-            kF5<<<gridD, C::NT, C::SMEM_BYTES, st>>>(blob, s.dproj, s.Hs[0], s.x4, nullptr, n, n_tiles, nullptr, s.partN, 1);
-        else
-            kI5<<<gridD, C::NT, C::SMEM_BYTES, st>>>(blob, s.dproj, s.Hs[t], s.x4, s.h1s[t - 1], n, n_tiles, s.dg, s.partN, 2);
+        if (t == 0) dense(blob, 5, true, s.Hs[0], nullptr, nullptr, 1);
+        else dense(blob, 5, false, s.Hs[t], s.h1s[t - 1], s.dg, 2);
     }
-    finalize_grads_kernel<H><<<sms * 4, 256, 0, st>>>(s.partE, gridE, s.partN, n > 0 ? gridD : 0, F, T > 0, go);
+    finalize_grads_kernel<H><<<sms * 4, 256, 0, st>>>(s.partE, gridE, s.partN, n > 0 ? n_part : 0, F, T > 0, go);
+    if (rc_w != GNNSEG_OK) return rc_w;
     return bwd_check();
 }
 

@@ -1,0 +1,318 @@
+// Weight gradients of the dense backward step on tcgen05 (hidden_dim 32 / 64): every contraction of
+// Estimator.training_step's backward (gnn/estimator.py:49-60 through gnn/model.py:113-125,140-156) that sums over the
+// NODES,
+//     dWP^T[o][k] = sum_n dproj[n][o] * [H_t | X | 1][n][k]        (d[W1a|W1b|W3a|W3b|W3c] and their biases: the ones column)
+//     dW4[o][k]   = sum_n dz[n][o] * h1[n][k]                        (node network, second layer)
+//     [dWin|dbin] / db4 = sum_n dz[n][o] * [X | 1][n]                (input network at t = 0, b4 otherwise)
+// as 3xTF32 products (hi.hi + lo.hi + hi.lo, fp32 accumulation in tensor memory over ALL node tiles of the CTA).
+//
+// Both operands of such a product are MN-major: the contraction index (the node) is the row of the node-major arrays.
+// tcgen05.mma kind::tf32 takes MN-major operands in ONE shared-memory layout, SWIZZLE_128B_BASE32B
+// (scripts/micro/umma_mn32_probe.cu; SWIZZLE_NONE returns zeros): per node a 128-byte row of 32 consecutive columns,
+// four rows per 512-byte atom, the 32-byte chunks of a row XOR-ed with (node & 3); blocks of 32 columns LBO apart,
+// groups of four nodes SBO = 512 bytes apart.  A float4 of a node-major row lands in it as ONE 16-byte store: no
+// transposition anywhere, and the image of a block serves as A (its columns = rows of D) and as B alike.
+//
+// One CTA per SM, 9 warps: 8 loader warps (a thread owns one 16-byte chunk of one node per block: coalesced 128-byte
+// row pieces in, tf32 hi / lo split, two 16-byte stores out) fill a ring of three stages of SN nodes; one thread issues
+// the MMAs of a stage and commits them to the stage's `empty` barrier.  Nothing is read back per tile: the accumulators
+// stay in tensor memory until the CTA's last stage, then four warps add them to the CTA's slot of the partial buffer
+// (layout NodePart of gnnseg_backward.cu; the same grid on every launch => a fixed summation order, bit-reproducible).
+// D rows beyond the real columns (M = 128 reads four blocks, whatever lies behind) are never looked at.
+#include "gnnseg_tc.cuh"
+
+namespace gnnseg {
+
+namespace {
+
+__device__ __forceinline__ void mbar_arrive_w(const uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+// MN-major, SWIZZLE_128B_BASE32B (layout type 1), version 1
+__device__ __forceinline__ uint64_t smem_desc_mn32(const uint32_t addr, const uint32_t lbo, const uint32_t sbo) {
+    return smem_desc(addr, lbo, sbo) | ((uint64_t)1 << 61);
+}
+__host__ __device__ constexpr uint32_t idesc_tf32_mn(const int M, const int N) {
+    return idesc_tf32(M, N) | (1u << 15) | (1u << 16);
+}
+// byte offset of the 16-byte chunk c16 (columns 4 c16 .. 4 c16 + 3 of a 32-column block) of node `node` inside a block image
+__device__ __forceinline__ int mn32_off(const int node, const int c16) {
+    return ((node >> 2) << 9) + ((node & 3) << 7) + ((((c16 >> 1) ^ node) & 3) << 5) + ((c16 & 1) << 4);
+}
+
+template <int H, int NB>
+struct WCfg {
+    static constexpr int SN = (H == 32) ? 32 : 16;           // nodes per stage
+    static constexpr int KS = SN / 8;                         // MMA k-steps per stage
+    static constexpr int BI = SN * 128;                       // bytes of one block image
+    static constexpr int PB = NB * H / 32, HB = H / 32;       // blocks of dproj; of H, dz, h1
+    // One group of blocks per precision (hi, lo), laid out so that every operand's blocks are equally spaced:
+    //   HB = 1: [h1 | dz | H | X]            HB = 2: [h1.0 | dz.0 | dz.1 | h1.1 | H.0 | H.1 | X]
+    // [H.. | X] are the rows of the projection products' A operand (contiguous), [h1.. | X] the columns of the dz
+    // products' B operand (three blocks apart), dz.. the rows of their A operand (contiguous).
+    static constexpr int GB = 3 * HB + 1;
+    static constexpr int O_H1 = 0, H1_STRIDE = 3 * BI, O_DZ = BI, O_HXH = 2 * HB * BI, O_HXX = 3 * HB * BI;
+    static constexpr int G_HI = 0, G_LO = GB * BI, P_HI = 2 * GB * BI, P_LO = P_HI + PB * BI;
+    static constexpr int STAGE = P_LO + PB * BI;
+    static constexpr int STAGES = 3;
+    static constexpr int SMEM_BYTES = STAGES * STAGE + 1024;  // + alignment slack
+    static constexpr int MA = (HB + 1) * 32 <= 64 ? 64 : 128; // rows of the projection products: [H | X 1 0 ..]
+    static constexpr int NA = NB * H, NA_SPLIT = NA > 256 ? 2 : 1, NA1 = NA / NA_SPLIT;
+    static constexpr int MC = 64;                             // rows of the dz products (H <= 64)
+    static constexpr int COL_A = 0, COL_C = NA, COLS = NA + H + 16;
+    static constexpr int TMEM_COLS = COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
+    static constexpr int NT = 288;                            // 8 loader warps + the MMA warp
+    static_assert(STAGES * STAGE + 1024 <= 232448, "shared memory");
+    static_assert(COLS <= 512 && NA1 <= 256 && NA1 % 16 == 0, "tensor memory / N");
+};
+
+template <int H>
+struct NodePartW {       // = NodePart<H> of gnnseg_backward.cu
+    static constexpr int D4 = H + 4;
+    static constexpr int WP = 0, BP = WP + D4 * 5 * H, W4 = BP + 5 * H, B4 = W4 + H * H, WIN = B4 + H, BIN = WIN + 4 * H,
+                         SIZE = BIN + H;
+};
+
+// FIRST: the input step (t = 0): no h1, dz feeds dWin / dbin.  accumulate: 0 = store, 1 = add to the projection slots
+// (WIN / BIN are written once), 2 = add to the W4 / B4 slots as well.
+template <int H, int NB, bool FIRST>
+__global__ void __launch_bounds__(WCfg<H, NB>::NT, 1)
+wgrad_tc_kernel(const float* __restrict__ dproj, const float* __restrict__ H_in, const float* __restrict__ X4,
+                const float* __restrict__ dz, const float* __restrict__ h1_prev, const int n_nodes, const int n_chunks,
+                float* __restrict__ part, const int accumulate) {
+    using C = WCfg<H, NB>;
+    using NP = NodePartW<H>;
+    constexpr int SN = C::SN, BI = C::BI, S = C::STAGES;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t bars[2 * S + 1];
+    __shared__ uint32_t tmem_slot;
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](const int s) { return bar0 + 8u * s; };
+    auto empty = [&](const int s) { return bar0 + 8u * (S + s); };
+    const uint32_t done = bar0 + 8u * (2 * S);
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 8); mbar_init(empty(s), 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int n_mine = (n_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // >= 1: grid <= n_chunks
+
+    if (warp < 8) {
+        // ---------------- loaders ----------------
+        constexpr int PER_BLK = SN * 8;                      // 16-byte chunks of one block image
+        constexpr int NP_ITEMS = C::PB * PER_BLK / 256, NH_ITEMS = (C::HB * PER_BLK + 255) / 256;
+        static_assert(C::PB * PER_BLK % 256 == 0 && C::HB * PER_BLK % 256 == 0, "loader split");
+        struct StageRegs { float4 vp[NP_ITEMS], vh[NH_ITEMS], vz[NH_ITEMS], v1[NH_ITEMS], vx; };
+        // the global loads of stage `it` (a thread's chunks of every block), all issued before anything is consumed
+        auto load = [&](StageRegs& R, const int it) {
+            const int node0 = ((int)blockIdx.x + it * (int)gridDim.x) * SN;
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < NP_ITEMS; ++j) {
+                const int i = tid + 256 * j, blk = i / PER_BLK, r = i % PER_BLK, ng = node0 + (r >> 3);
+                R.vp[j] = ng < n_nodes ? ldg4(dproj + (size_t)ng * (NB * H) + 32 * blk + 4 * (r & 7)) : zero;
+            }
+#pragma unroll
+            for (int j = 0; j < NH_ITEMS; ++j) {
+                const int i = tid + 256 * j, blk = i / PER_BLK, r = i % PER_BLK, ng = node0 + (r >> 3);
+                const bool ok = ng < n_nodes;
+                const size_t off = (size_t)ng * H + 32 * blk + 4 * (r & 7);
+                R.vh[j] = ok ? ldg4(H_in + off) : zero;
+                R.vz[j] = ok ? ldg4(dz + off) : zero;
+                R.v1[j] = (!FIRST && ok) ? ldg4(h1_prev + off) : zero;
+            }
+            R.vx = zero;
+            if (tid < SN * 4) {                               // the X block: [x0 x1 x2 x3 | 1 0 0 0 | 0 ... ]: 16 columns are read
+                const int ng = node0 + (tid >> 2), c16 = tid & 3;
+                if (ng < n_nodes) {
+                    if (c16 == 0) R.vx = ldg4(X4 + (size_t)ng * 4);
+                    else if (c16 == 1) R.vx.x = 1.f;
+                }
+            }
+        };
+        // tf32 hi / lo split and the two 16-byte stores per chunk, once the MMAs that read the stage last have completed
+        auto store = [&](const StageRegs& R, const int it) {
+            const int s = it % S, round = it / S;
+            mbar_wait(empty(s), (round & 1) ^ 1);
+            unsigned char* st = smem + s * C::STAGE;
+            auto put = [&](const float4 v, const int o) {     // o: offset inside the hi group / the hi P blocks
+                float4 hi, lo;
+                split3(v.x, hi.x, lo.x); split3(v.y, hi.y, lo.y); split3(v.z, hi.z, lo.z); split3(v.w, hi.w, lo.w);
+                *reinterpret_cast<float4*>(st + o) = hi;
+                *reinterpret_cast<float4*>(st + o + (o >= C::P_HI ? C::PB * BI : C::G_LO)) = lo;
+            };
+#pragma unroll
+            for (int j = 0; j < NP_ITEMS; ++j) {
+                const int i = tid + 256 * j, blk = i / PER_BLK, r = i % PER_BLK;
+                put(R.vp[j], C::P_HI + blk * BI + mn32_off(r >> 3, r & 7));
+            }
+#pragma unroll
+            for (int j = 0; j < NH_ITEMS; ++j) {
+                const int i = tid + 256 * j, blk = i / PER_BLK, r = i % PER_BLK, o = mn32_off(r >> 3, r & 7);
+                put(R.vh[j], C::O_HXH + blk * BI + o);
+                put(R.vz[j], C::O_DZ + blk * BI + o);
+                if (!FIRST) put(R.v1[j], C::O_H1 + blk * C::H1_STRIDE + o);
+            }
+            if (tid < SN * 4) put(R.vx, C::O_HXX + mn32_off(tid >> 2, tid & 3));
+            fence_async_smem();                               // generic-proxy writes -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive_w(full(s));
+        };
+        StageRegs ra, rb;                                     // two stages of loads in flight per thread
+        load(ra, 0);
+        for (int it = 0; it < n_mine; it += 2) {
+            if (it + 1 < n_mine) load(rb, it + 1);
+            store(ra, it);
+            if (it + 1 < n_mine) {
+                if (it + 2 < n_mine) load(ra, it + 2);
+                store(rb, it + 1);
+            }
+        }
+    } else {
+      if (lane == 0) {
+        // ---------------- MMA issuer ----------------
+        constexpr int NC = FIRST ? 16 : H + 16;
+        constexpr uint32_t ID_A = idesc_tf32_mn(C::MA, C::NA1), ID_C = idesc_tf32_mn(C::MC, NC);
+        const uint32_t sbase = smem_u32(smem);
+        for (int it = 0; it < n_mine; ++it) {
+            const int s = it % S, round = it / S;
+            mbar_wait(full(s), round & 1);
+            tc_fence_after();
+            const uint32_t st = sbase + s * C::STAGE;
+#pragma unroll
+            for (int ks = 0; ks < C::KS; ++ks) {
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {        // hi.hi, lo.hi, hi.lo
+                    const uint32_t ga = st + (pass == 1 ? C::G_LO : C::G_HI) + ks * 1024;      // A side: [H | X], dz
+                    const uint32_t gb = st + (pass == 2 ? C::G_LO : C::G_HI) + ks * 1024;      // B side: [h1 | X]
+                    const uint32_t pb = st + (pass == 2 ? C::P_LO : C::P_HI) + ks * 1024;      // B side: dproj
+                    const uint32_t acc = (it > 0 || ks > 0 || pass > 0) ? 1u : 0u;
+                    // D_A[k][o] += sum_n [H | X 1][n][k] * dproj[n][o]
+                    const uint64_t a_hx = smem_desc_mn32(ga + C::O_HXH, BI, 512);
+#pragma unroll
+                    for (int h = 0; h < C::NA_SPLIT; ++h)
+                        umma_ss(tmem + C::COL_A + h * C::NA1, a_hx, smem_desc_mn32(pb + h * (C::NA1 / 32) * BI, BI, 512), ID_A, acc);
+                    // D_C[o][k | f] += sum_n dz[n][o] * [h1 | X 1][n][k | f]
+                    const uint64_t a_z = smem_desc_mn32(ga + C::O_DZ, BI, 512);
+                    const uint64_t b_c = FIRST ? smem_desc_mn32(gb + C::O_HXX, BI, 512) : smem_desc_mn32(gb + C::O_H1, C::H1_STRIDE, 512);
+                    umma_ss(tmem + C::COL_C, a_z, b_c, ID_C, acc);
+                }
+            }
+            umma_commit(empty(s));                            // arrives when the MMAs above have read the stage
+        }
+        umma_commit(done);
+      }
+      __syncwarp();
+    }
+
+    // ---------------- epilogue: accumulators -> the CTA's partial ----------------
+    // row r of an M = 64 product sits in TMEM lane 32 (r / 16) + r % 16, of an M = 128 product in lane r
+    if (warp < 4) {
+        mbar_wait(done, 0);
+        tc_fence_after();
+        float* mine = part + (size_t)blockIdx.x * NP::SIZE;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const bool add_p = accumulate != 0, add_4 = accumulate > 1;
+        {
+            const int k = C::MA == 64 ? (lane < 16 ? 16 * warp + lane : -1) : 32 * warp + lane;      // row of D_A: column of [H | X 1]
+            float* dst = nullptr;                             // this row of the partial: 5H floats apart from the next
+            if (k >= 0 && k < NP::D4) dst = mine + NP::WP + k * 5 * H;
+            else if (k == NP::D4) dst = mine + NP::BP;        // the ones column: bias sums
+#pragma unroll 1
+            for (int c0 = 0; c0 < C::NA; c0 += 16) {
+                float v[16];
+                tmem_ld16(lane_base + C::COL_A + c0, v);
+                if (dst) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 w = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        float* p = dst + c0 + i;
+                        if (add_p) { const float4 o = *reinterpret_cast<const float4*>(p); w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
+                        st4(p, w);
+                    }
+                }
+            }
+        }
+        {
+            const int o = lane < 16 ? 16 * warp + lane : -1;  // row of D_C: column of dz
+            const bool ok = o >= 0 && o < H;
+            if (!FIRST) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < H; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(lane_base + C::COL_C + c0, v);
+                    if (ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float* p = mine + NP::W4 + o * H + c0 + i;
+                            *p = add_4 ? *p + v[i] : v[i];
+                        }
+                    }
+                }
+            }
+            float v[16];
+            tmem_ld16(lane_base + C::COL_C + (FIRST ? 0 : H), v);
+            if (ok) {
+                if (FIRST) {
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) mine[NP::WIN + f * H + o] = v[f];
+                    mine[NP::BIN + o] = v[4];
+                } else {
+                    float* p = mine + NP::B4 + o;
+                    *p = add_4 ? *p + v[4] : v[4];
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
+}
+
+}  // namespace
+
+bool wgrad_tc_width(const int h) { return h == 32 || h == 64; }
+
+// grid of the weight-gradient kernel: a function of (n_nodes, SM count) only, the same on every launch of a backward pass
+int wgrad_tc_grid(const int n_nodes, const int h, const int sms) {
+    const int sn = h == 32 ? 32 : 16, n_chunks = (n_nodes + sn - 1) / sn;
+    return n_chunks < sms ? n_chunks : sms;
+}
+
+template <int H, int NB, bool FIRST>
+static int launch_wgrad(const float* dproj, const float* H_in, const float* X4, const float* dz, const float* h1_prev, const int n_nodes,
+                        float* part, const int accumulate, const int grid, cudaStream_t st) {
+    using C = WCfg<H, NB>;
+    if (!ensure_dynamic_smem<wgrad_tc_kernel<H, NB, FIRST>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
+    const int n_chunks = (n_nodes + C::SN - 1) / C::SN;
+    wgrad_tc_kernel<H, NB, FIRST><<<grid, C::NT, C::SMEM_BYTES, st>>>(dproj, H_in, X4, dz, h1_prev, n_nodes, n_chunks, part, accumulate);
+    return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+}
+
+int wgrad_tc(const int h, const int nb, const bool first, const float* dproj, const float* H_in, const float* X4, const float* dz,
+             const float* h1_prev, const int n_nodes, float* part, const int accumulate, const int grid, cudaStream_t st) {
+    if (n_nodes <= 0) return GNNSEG_OK;
+#define GNNSEG_W(HH) \
+    if (h == HH) { \
+        if (nb == 2) return first ? launch_wgrad<HH, 2, true>(dproj, H_in, X4, dz, h1_prev, n_nodes, part, accumulate, grid, st) \
+                                  : launch_wgrad<HH, 2, false>(dproj, H_in, X4, dz, h1_prev, n_nodes, part, accumulate, grid, st); \
+        return first ? launch_wgrad<HH, 5, true>(dproj, H_in, X4, dz, h1_prev, n_nodes, part, accumulate, grid, st) \
+                     : launch_wgrad<HH, 5, false>(dproj, H_in, X4, dz, h1_prev, n_nodes, part, accumulate, grid, st); \
+    }
+    GNNSEG_W(32)
+    GNNSEG_W(64)
+#undef GNNSEG_W
+    return GNNSEG_EUNSUPPORTED;
+}
+
+}  // namespace gnnseg

@@ -6,7 +6,7 @@
 // K rows SBO apart.  umma_mn_probe.cu (SWIZZLE_NONE) got zeros; this is the weight-gradient GEMM of dense_bwd:
 //     D[m][n] = sum_node X[node][m] * Y[node][n]        X [128 nodes][32], Y [128 nodes][40], rows = nodes (node-major tiles)
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../gnn_fpga_b200/csrc -I../../include -o umma_mn32_probe umma_mn32_probe.cu
-// usage: umma_mn32_probe [variant]   bit 0: swap LBO / SBO in the descriptors
+// usage: umma_mn32_probe [variant]   bit 0: swap LBO / SBO in the descriptors; bit 1: M = 64 (prints which TMEM lane holds which row of D)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ X, const 
     const uint32_t tmem = tmem_slot;
     if (tid == 0) {
         const uint32_t sa = smem_u32(smem), sb = sa + A_BYTES;
-        constexpr uint32_t ID = idesc_tf32(128, CY) | (1u << 15) | (1u << 16);      // a_major = b_major = MN
+        const uint32_t ID = idesc_tf32((variant & 2) ? 64 : 128, CY) | (1u << 15) | (1u << 16);      // a_major = b_major = MN
         for (int kg = 0; kg < TM / 8; ++kg) {                                        // K = 8 nodes per instruction: two atoms of four rows
             uint64_t a, b;
             if (variant & 1) {
@@ -95,6 +95,19 @@ int main(int argc, char** argv) {
     probe<<<1, 128, smem>>>(dX, dY, dD, variant);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    if (variant & 2) {          // X block 1 of A holds zeros, so rows 32..63 of D are zero rows: look for rows 0..31
+        for (int l = 0; l < TM; ++l) {
+            int hit = -1, nzl = 0;
+            for (int k = 0; k < CY; ++k) nzl += D[l * CY + k] != 0.f;
+            for (int m = 0; m < CX && hit < 0; ++m) {
+                bool same = true;
+                for (int k = 0; k < CY; ++k) same &= D[l * CY + k] == R[m * CY + k];
+                if (same) hit = m;
+            }
+            if (hit >= 0 || nzl) printf("lane %3d: row %d (%d non-zero)\n", l, hit, nzl);
+        }
+        return 0;
+    }
     double err = 0;
     int bad = 0, nz = 0;
     for (int m = 0; m < CX; ++m)

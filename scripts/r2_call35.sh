@@ -1,0 +1,23 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout -k 10 400 python -m pytest tests/test_gpu_training.py tests/test_gpu_nodeclf.py -m gpu -q -x > gpurun_out/r5_tests.log 2>&1; echo "tests rc $?"; tail -5 gpurun_out/r5_tests.log
+for v in tc; do
+GNNSEG_DENSE_BWD=$v timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r5_launches_$v.csv python scripts/train_profile.py ${WL:-acts64} 2 > gpurun_out/r5_ncu_$v.log 2>&1
+python - $v <<'PY'
+import csv,sys,collections
+v=sys.argv[1]
+rows=[r for r in csv.reader(open("gpurun_out/r5_launches_%s.csv"%v)) if len(r)>10]
+hdr=rows[0]; ik=hdr.index("Kernel Name"); iv=hdr.index("Metric Value"); iu=hdr.index("Metric Unit")
+agg=collections.OrderedDict()
+for r in rows[1:]:
+    name=r[ik].split("(")[0][:60]; t=float(r[iv].replace(",",""))
+    if r[iu]=="ns": t/=1000
+    elif r[iu]=="ms": t*=1000
+    agg.setdefault(name,[]).append(t)
+tot=sum(sum(x) for x in agg.values())
+print("==", v, "total us %.0f over %d launches"%(tot, sum(len(x) for x in agg.values())))
+for k,x in sorted(agg.items(), key=lambda kv:-sum(kv[1]))[:12]:
+    print("  %-62s n=%3d  sum %8.1f  last %7.1f"%(k,len(x),sum(x),x[-1]))
+PY
+done
