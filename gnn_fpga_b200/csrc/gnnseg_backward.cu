@@ -551,11 +551,17 @@ bool wgrad_tc_width(int h);
 int wgrad_tc_grid(int n_nodes, int h, int sms);
 int wgrad_tc(int h, int nb, bool first, const float* dproj, const float* H_in, const float* X4, const float* dz, const float* h1_prev,
              int n_nodes, float* part, int accumulate, int grid, cudaStream_t st);
-// GNNSEG_DENSE_BWD=simt keeps the all-SIMT dense backward kernel at hidden_dim 32 / 64 (A/B runs)
-static bool wgrad_tc_enabled() {
-    static const bool on = [] { const char* v = getenv("GNNSEG_DENSE_BWD"); return !(v && v[0] == 's'); }();
-    return on;
+// gnnseg_dprop_tc.cu
+bool dprop_tc_width(int h);
+int dprop_tc(int h, int nb, bool first, const float* blob, const float* dproj, const float* H_in, const float* h1_prev, int n_nodes,
+             float* dz_out, float* dg_out, int sms, cudaStream_t st);
+// GNNSEG_DENSE_BWD (A/B runs): simt = the all-SIMT dense backward kernel at every width; w = tcgen05 weight gradients, the
+// propagating half on CUDA cores; default = both halves on tcgen05 where compiled (hidden_dim 32; 64: weight gradients)
+static int dense_bwd_mode() {
+    static const int mode = [] { const char* v = getenv("GNNSEG_DENSE_BWD"); return !v ? 2 : v[0] == 's' ? 0 : v[0] == 'w' ? 1 : 2; }();
+    return mode;
 }
+static bool wgrad_tc_enabled() { return dense_bwd_mode() >= 1; }
 
 template <int H>
 static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, const int T, const float* dscores,
@@ -601,7 +607,11 @@ static int backward_impl(const float* blob, const GnnsegGraph* g, const int F, c
     int rc_w = GNNSEG_OK;
     // one dense step: nb = 2 / 5 projections live in dproj, first = the input step
     auto dense = [&](const float* wblob, const int nb, const bool first, const float* Hin, const float* h1p, float* dg_out, const int acc) {
-        if (tcw) {
+        if (tcw && dprop_tc_width(H) && dense_bwd_mode() >= 2) {
+            int rc = dprop_tc(H, nb, first, wblob, s.dproj, Hin, h1p, n, s.dz, dg_out, sms, st);
+            if (rc == GNNSEG_OK) rc = wgrad_tc(H, nb, first, s.dproj, Hin, s.x4, s.dz, h1p, n, s.partN, acc, gridW, st);
+            if (rc != GNNSEG_OK) rc_w = rc;
+        } else if (tcw) {
             if (nb == 2) {
                 if (first) kF2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(wblob, s.dproj, Hin, s.x4, nullptr, n, n_tiles, nullptr, s.partN, acc, s.dz);
                 else kI2<<<gridD, C::NT, C::SMEM_BYTES, st>>>(wblob, s.dproj, Hin, s.x4, h1p, n, n_tiles, dg_out, s.partN, acc, s.dz);

@@ -168,15 +168,14 @@ wgrad_tc_kernel(const float* __restrict__ dproj, const float* __restrict__ H_in,
             __syncwarp();
             if (lane == 0) mbar_arrive_w(full(s));
         };
-        StageRegs ra, rb;                                     // two stages of loads in flight per thread
-        load(ra, 0);
-        for (int it = 0; it < n_mine; it += 2) {
-            if (it + 1 < n_mine) load(rb, it + 1);
-            store(ra, it);
-            if (it + 1 < n_mine) {
-                if (it + 2 < n_mine) load(ra, it + 2);
-                store(rb, it + 1);
-            }
+        StageRegs r0, r1, r2;                                 // two stages of loads in flight behind the one being stored
+        load(r0, 0);
+        if (1 < n_mine) load(r1, 1);
+        for (int it = 0; it < n_mine; it += 3) {
+            if (it + 2 < n_mine) load(r2, it + 2);
+            store(r0, it);
+            if (it + 1 < n_mine) { if (it + 3 < n_mine) load(r0, it + 3); store(r1, it + 1); }
+            if (it + 2 < n_mine) { if (it + 4 < n_mine) load(r1, it + 4); store(r2, it + 2); }
         }
     } else {
       if (lane == 0) {

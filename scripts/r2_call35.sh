@@ -1,9 +1,9 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout -k 10 400 python -m pytest tests/test_gpu_training.py tests/test_gpu_nodeclf.py -m gpu -q -x > gpurun_out/r5_tests.log 2>&1; echo "tests rc $?"; tail -5 gpurun_out/r5_tests.log
+timeout -k 5 150 python -m pytest tests/test_gpu_training.py tests/test_gpu_nodeclf.py -m gpu -q -x > gpurun_out/r5_tests.log 2>&1; echo "tests rc $?"; tail -5 gpurun_out/r5_tests.log
 for v in tc; do
-GNNSEG_DENSE_BWD=$v timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r5_launches_$v.csv python scripts/train_profile.py ${WL:-acts64} 2 > gpurun_out/r5_ncu_$v.log 2>&1
+GNNSEG_DENSE_BWD=$v timeout -k 5 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r5_launches_$v.csv python scripts/train_profile.py ${WL:-acts64} 2 > gpurun_out/r5_ncu_$v.log 2>&1
 python - $v <<'PY'
 import csv,sys,collections
 v=sys.argv[1]
