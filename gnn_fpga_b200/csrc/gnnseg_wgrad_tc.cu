@@ -19,11 +19,21 @@
 // stay in tensor memory until the CTA's last stage, then four warps add them to the CTA's slot of the partial buffer
 // (layout NodePart of gnnseg_backward.cu; the same grid on every launch => a fixed summation order, bit-reproducible).
 // D rows beyond the real columns (M = 128 reads four blocks, whatever lies behind) are never looked at.
+#include <cstdio>
+#include <cstdlib>
 #include "gnnseg_tc.cuh"
 
 namespace gnnseg {
 
 namespace {
+
+#ifdef GNNSEG_DTRACE
+#define DT_DECL(n) long long dt_acc[n] = {}; const long long dt_start = clock64()
+#define DT_WAIT(i, ...) do { const long long dt_t0 = clock64(); __VA_ARGS__; dt_acc[i] += clock64() - dt_t0; } while (0)
+#else
+#define DT_DECL(n)
+#define DT_WAIT(i, ...) do { __VA_ARGS__; } while (0)
+#endif
 
 __device__ __forceinline__ void mbar_arrive_w(const uint32_t mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
@@ -112,6 +122,7 @@ wgrad_tc_kernel(const float* __restrict__ dproj, const float* __restrict__ H_in,
         constexpr int PER_BLK = SN * 8;                      // 16-byte chunks of one block image
         constexpr int NP_ITEMS = C::PB * PER_BLK / 256, NH_ITEMS = (C::HB * PER_BLK + 255) / 256;
         static_assert(C::PB * PER_BLK % 256 == 0 && C::HB * PER_BLK % 256 == 0, "loader split");
+        DT_DECL(1);
         struct StageRegs { float4 vp[NP_ITEMS], vh[NH_ITEMS], vz[NH_ITEMS], v1[NH_ITEMS], vx; };
         // the global loads of stage `it` (a thread's chunks of every block), all issued before anything is consumed
         auto load = [&](StageRegs& R, const int it) {
@@ -143,7 +154,7 @@ wgrad_tc_kernel(const float* __restrict__ dproj, const float* __restrict__ H_in,
         // tf32 hi / lo split and the two 16-byte stores per chunk, once the MMAs that read the stage last have completed
         auto store = [&](const StageRegs& R, const int it) {
             const int s = it % S, round = it / S;
-            mbar_wait(empty(s), (round & 1) ^ 1);
+            DT_WAIT(0, mbar_wait(empty(s), (round & 1) ^ 1));
             unsigned char* st = smem + s * C::STAGE;
             auto put = [&](const float4 v, const int o) {     // o: offset inside the hi group / the hi P blocks
                 float4 hi, lo;
@@ -177,15 +188,19 @@ wgrad_tc_kernel(const float* __restrict__ dproj, const float* __restrict__ H_in,
             if (it + 1 < n_mine) { if (it + 3 < n_mine) load(r0, it + 3); store(r1, it + 1); }
             if (it + 2 < n_mine) { if (it + 4 < n_mine) load(r1, it + 4); store(r2, it + 2); }
         }
+#ifdef GNNSEG_DTRACE
+        if (blockIdx.x == 0 && tid == 0) printf("wgrad<%d,%d> loader : total %lld, wait empty %lld (%d stages)\n", NB, (int)FIRST, clock64() - dt_start, dt_acc[0], n_mine);
+#endif
     } else {
       if (lane == 0) {
         // ---------------- MMA issuer ----------------
         constexpr int NC = FIRST ? 16 : H + 16;
         constexpr uint32_t ID_A = idesc_tf32_mn(C::MA, C::NA1), ID_C = idesc_tf32_mn(C::MC, NC);
         const uint32_t sbase = smem_u32(smem);
+        DT_DECL(1);
         for (int it = 0; it < n_mine; ++it) {
             const int s = it % S, round = it / S;
-            mbar_wait(full(s), round & 1);
+            DT_WAIT(0, mbar_wait(full(s), round & 1));
             tc_fence_after();
             const uint32_t st = sbase + s * C::STAGE;
 #pragma unroll
@@ -210,6 +225,9 @@ wgrad_tc_kernel(const float* __restrict__ dproj, const float* __restrict__ H_in,
             umma_commit(empty(s));                            // arrives when the MMAs above have read the stage
         }
         umma_commit(done);
+#ifdef GNNSEG_DTRACE
+        if (blockIdx.x == 0) printf("wgrad<%d,%d> mma    : total %lld, wait full %lld\n", NB, (int)FIRST, clock64() - dt_start, dt_acc[0]);
+#endif
       }
       __syncwarp();
     }
@@ -278,13 +296,228 @@ wgrad_tc_kernel(const float* __restrict__ dproj, const float* __restrict__ H_in,
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
 }
 
+// ---- hidden_dim 32: ONE product per k-step and precision pair ------------------------------------------------------
+// The issuing thread needs ~50 - 110 cycles per tcgen05.mma whatever its size (wait-time counters, make dtrace: the kernel
+// above spends 86 % of its time issuing 36 small products per 32 nodes), so at hidden_dim 32 all of a step's
+// contractions go into one M = 128, N <= 208 product:
+//     A rows (m-blocks)   [ H_t (32) | X 1 0.. (32) | dz (32) | (32 rows of whatever follows: ignored) ]
+//     B columns (n-blocks) [ dproj (32 NB) | h1 (32, t > 0) | X 1 0.. (16) ]
+// D rows 0..36 x the dproj columns = d[W1a|W1b|W3a|W3b|W3c]^T and their biases, rows 64..95 x the h1 columns = dW4, x the
+// last block = db4 (t > 0) or dWin | dbin (t = 0); the other quadrants are computed and never read.  Stages of 16 nodes
+// (two k-steps), ring of five.
+template <int NB, bool FIRST>
+struct MCfg {
+    static constexpr int H = 32, SN = 16, KS = SN / 8, BI = SN * 128, PB = NB;
+    static constexpr int O_HXH = 0, O_XA = BI, O_DZ = 2 * BI, O_P = 3 * BI, O_H1 = (3 + PB) * BI, O_XB = (3 + PB + (FIRST ? 0 : 1)) * BI;
+    static constexpr int GB = 3 + PB + (FIRST ? 0 : 1) + 1;
+    static constexpr int G_LO = GB * BI, STAGE = 2 * GB * BI, STAGES = 5;
+    static constexpr int SMEM_BYTES = STAGES * STAGE + 1024;
+    static constexpr int N = 32 * PB + (FIRST ? 0 : 32) + 16;
+    static constexpr int COL_H1 = 32 * PB, COL_X = 32 * PB + (FIRST ? 0 : 32);
+    static constexpr int TMEM_COLS = N <= 128 ? 128 : 256;
+    static constexpr int ARRAYS = PB + (FIRST ? 2 : 3);       // 32-column row arrays per stage: dproj blocks, H, dz, h1
+    static constexpr int ITEMS = (ARRAYS * SN * 8 + 255) / 256;
+    static constexpr int NT = 288;
+    static_assert(SMEM_BYTES <= 232448 && N <= 256 && N % 16 == 0, "merged product");
+};
+
+template <int NB, bool FIRST>
+__global__ void __launch_bounds__(MCfg<NB, FIRST>::NT, 1)
+wgrad_tc_merged_kernel(const float* __restrict__ dproj, const float* __restrict__ H_in, const float* __restrict__ X4,
+                       const float* __restrict__ dz, const float* __restrict__ h1_prev, const int n_nodes, const int n_chunks,
+                       float* __restrict__ part, const int accumulate) {
+    using C = MCfg<NB, FIRST>;
+    using NP = NodePartW<32>;
+    constexpr int H = 32, SN = C::SN, BI = C::BI, S = C::STAGES;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t bars[2 * S + 1];
+    __shared__ uint32_t tmem_slot;
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](const int s) { return bar0 + 8u * s; };
+    auto empty = [&](const int s) { return bar0 + 8u * (S + s); };
+    const uint32_t done = bar0 + 8u * (2 * S);
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 8); mbar_init(empty(s), 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int n_mine = (n_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // >= 1: grid <= n_chunks
+
+    if (warp < 8) {
+        // ---------------- loaders ----------------
+        // item i = 128 a + r: array a (dproj block a < PB, then H, dz, h1), node r >> 3 of the stage, 16-byte chunk r & 7
+        DT_DECL(1);
+        struct StageRegs { float4 v[C::ITEMS], vx; };
+        auto load = [&](StageRegs& R, const int it) {
+            const int node0 = ((int)blockIdx.x + it * (int)gridDim.x) * SN;
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < C::ITEMS; ++j) {
+                const int i = tid + 256 * j, a = i >> 7, r = i & 127, ng = node0 + (r >> 3), c = 4 * (r & 7);
+                R.v[j] = zero;
+                if (a < C::ARRAYS && ng < n_nodes) {
+                    const float* src = a < C::PB ? dproj + (size_t)ng * (NB * H) + 32 * a
+                                     : a == C::PB ? H_in + (size_t)ng * H
+                                     : a == C::PB + 1 ? dz + (size_t)ng * H : h1_prev + (size_t)ng * H;
+                    R.v[j] = ldg4(src + c);
+                }
+            }
+            R.vx = zero;
+            if (tid < SN * 4) {
+                const int ng = node0 + (tid >> 2), c16 = tid & 3;
+                if (ng < n_nodes) {
+                    if (c16 == 0) R.vx = ldg4(X4 + (size_t)ng * 4);
+                    else if (c16 == 1) R.vx.x = 1.f;
+                }
+            }
+        };
+        auto store = [&](const StageRegs& R, const int it) {
+            const int s = it % S, round = it / S;
+            DT_WAIT(0, mbar_wait(empty(s), (round & 1) ^ 1));
+            unsigned char* st = smem + s * C::STAGE;
+            auto put = [&](const float4 v, const int o) {
+                float4 hi, lo;
+                split3(v.x, hi.x, lo.x); split3(v.y, hi.y, lo.y); split3(v.z, hi.z, lo.z); split3(v.w, hi.w, lo.w);
+                *reinterpret_cast<float4*>(st + o) = hi;
+                *reinterpret_cast<float4*>(st + C::G_LO + o) = lo;
+            };
+#pragma unroll
+            for (int j = 0; j < C::ITEMS; ++j) {
+                const int i = tid + 256 * j, a = i >> 7, r = i & 127;
+                if (a < C::ARRAYS) {
+                    const int blk = a < C::PB ? C::O_P + a * BI : a == C::PB ? C::O_HXH : a == C::PB + 1 ? C::O_DZ : C::O_H1;
+                    put(R.v[j], blk + mn32_off(r >> 3, r & 7));
+                }
+            }
+            if (tid < SN * 4) {
+                const int o = mn32_off(tid >> 2, tid & 3);
+                put(R.vx, C::O_XA + o);
+                put(R.vx, C::O_XB + o);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_w(full(s));
+        };
+        StageRegs r0, r1, r2;
+        load(r0, 0);
+        if (1 < n_mine) load(r1, 1);
+        for (int it = 0; it < n_mine; it += 3) {
+            if (it + 2 < n_mine) load(r2, it + 2);
+            store(r0, it);
+            if (it + 1 < n_mine) { if (it + 3 < n_mine) load(r0, it + 3); store(r1, it + 1); }
+            if (it + 2 < n_mine) { if (it + 4 < n_mine) load(r1, it + 4); store(r2, it + 2); }
+        }
+#ifdef GNNSEG_DTRACE
+        if (blockIdx.x == 0 && tid == 0) printf("wgradM<%d,%d> loader : total %lld, wait empty %lld (%d stages)\n", NB, (int)FIRST, clock64() - dt_start, dt_acc[0], n_mine);
+#endif
+    } else {
+      if (lane == 0) {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t ID = idesc_tf32_mn(128, C::N);
+        const uint32_t sbase = smem_u32(smem);
+        DT_DECL(1);
+        for (int it = 0; it < n_mine; ++it) {
+            const int s = it % S, round = it / S;
+            DT_WAIT(0, mbar_wait(full(s), round & 1));
+            tc_fence_after();
+            const uint32_t st = sbase + s * C::STAGE;
+            const uint64_t d_a = smem_desc_mn32(st + C::O_HXH, BI, 512), d_b = smem_desc_mn32(st + C::O_P, BI, 512);
+#pragma unroll
+            for (int ks = 0; ks < C::KS; ++ks) {
+                const uint64_t k = (uint64_t)(ks * 1024 >> 4), lo = (uint64_t)(C::G_LO >> 4);
+                umma_ss(tmem, d_a + k, d_b + k, ID, (it > 0 || ks > 0) ? 1u : 0u);       // hi . hi
+                umma_ss(tmem, d_a + k + lo, d_b + k, ID, 1u);                             // lo . hi
+                umma_ss(tmem, d_a + k, d_b + k + lo, ID, 1u);                             // hi . lo
+            }
+            umma_commit(empty(s));
+        }
+        umma_commit(done);
+#ifdef GNNSEG_DTRACE
+        if (blockIdx.x == 0) printf("wgradM<%d,%d> mma    : total %lld, wait full %lld\n", NB, (int)FIRST, clock64() - dt_start, dt_acc[0]);
+#endif
+      }
+      __syncwarp();
+    }
+
+    // ---------------- epilogue: row r of D is TMEM lane r ----------------
+    if (warp < 3) {
+        mbar_wait(done, 0);
+        tc_fence_after();
+        float* mine = part + (size_t)blockIdx.x * NP::SIZE;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const bool add_p = accumulate != 0, add_4 = accumulate > 1;
+        if (warp < 2) {                                       // rows of [H | X 1]: a row of the projections' partial each
+            float* dst = nullptr;
+            if (warp == 0) dst = mine + NP::WP + lane * 5 * H;
+            else if (lane < 4) dst = mine + NP::WP + (H + lane) * 5 * H;
+            else if (lane == 4) dst = mine + NP::BP;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 32 * C::PB; c0 += 16) {
+                float v[16];
+                tmem_ld16(lane_base + c0, v);
+                if (dst) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 w = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        float* p = dst + c0 + i;
+                        if (add_p) { const float4 o = *reinterpret_cast<const float4*>(p); w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
+                        st4(p, w);
+                    }
+                }
+            }
+        } else {                                              // rows of dz: lane = column o of dz
+            const int o = lane;
+            if (!FIRST) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < H; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(lane_base + C::COL_H1 + c0, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float* p = mine + NP::W4 + o * H + c0 + i;
+                        *p = add_4 ? *p + v[i] : v[i];
+                    }
+                }
+            }
+            float v[16];
+            tmem_ld16(lane_base + C::COL_X, v);
+            if (FIRST) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) mine[NP::WIN + f * H + o] = v[f];
+                mine[NP::BIN + o] = v[4];
+            } else {
+                float* p = mine + NP::B4 + o;
+                *p = add_4 ? *p + v[4] : v[4];
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS) : "memory");
+}
+
 }  // namespace
 
 bool wgrad_tc_width(const int h) { return h == 32 || h == 64; }
 
 // grid of the weight-gradient kernel: a function of (n_nodes, SM count) only, the same on every launch of a backward pass
+// GNNSEG_WGRAD=split: the two-product kernel at hidden_dim 32 as well (A/B runs)
+static bool wgrad_merged(const int h) {
+    static const bool split = [] { const char* v = getenv("GNNSEG_WGRAD"); return v && v[0] == 's'; }();
+    return h == 32 && !split;
+}
 int wgrad_tc_grid(const int n_nodes, const int h, const int sms) {
-    const int sn = h == 32 ? 32 : 16, n_chunks = (n_nodes + sn - 1) / sn;
+    const int sn = (h == 32 && !wgrad_merged(h)) ? 32 : 16, n_chunks = (n_nodes + sn - 1) / sn;
     return n_chunks < sms ? n_chunks : sms;
 }
 
@@ -298,9 +531,25 @@ static int launch_wgrad(const float* dproj, const float* H_in, const float* X4, 
     return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
 }
 
+template <int NB, bool FIRST>
+static int launch_wgrad_merged(const float* dproj, const float* H_in, const float* X4, const float* dz, const float* h1_prev, const int n_nodes,
+                               float* part, const int accumulate, const int grid, cudaStream_t st) {
+    using C = MCfg<NB, FIRST>;
+    if (!ensure_dynamic_smem<wgrad_tc_merged_kernel<NB, FIRST>>(C::SMEM_BYTES)) return GNNSEG_ECUDA;
+    const int n_chunks = (n_nodes + C::SN - 1) / C::SN;
+    wgrad_tc_merged_kernel<NB, FIRST><<<grid, C::NT, C::SMEM_BYTES, st>>>(dproj, H_in, X4, dz, h1_prev, n_nodes, n_chunks, part, accumulate);
+    return cudaGetLastError() == cudaSuccess ? GNNSEG_OK : GNNSEG_ECUDA;
+}
+
 int wgrad_tc(const int h, const int nb, const bool first, const float* dproj, const float* H_in, const float* X4, const float* dz,
              const float* h1_prev, const int n_nodes, float* part, const int accumulate, const int grid, cudaStream_t st) {
     if (n_nodes <= 0) return GNNSEG_OK;
+    if (wgrad_merged(h)) {
+        if (nb == 2) return first ? launch_wgrad_merged<2, true>(dproj, H_in, X4, dz, h1_prev, n_nodes, part, accumulate, grid, st)
+                                  : launch_wgrad_merged<2, false>(dproj, H_in, X4, dz, h1_prev, n_nodes, part, accumulate, grid, st);
+        return first ? launch_wgrad_merged<5, true>(dproj, H_in, X4, dz, h1_prev, n_nodes, part, accumulate, grid, st)
+                     : launch_wgrad_merged<5, false>(dproj, H_in, X4, dz, h1_prev, n_nodes, part, accumulate, grid, st);
+    }
 #define GNNSEG_W(HH) \
     if (h == HH) { \
         if (nb == 2) return first ? launch_wgrad<HH, 2, true>(dproj, H_in, X4, dz, h1_prev, n_nodes, part, accumulate, grid, st) \
