@@ -304,22 +304,36 @@ wgrad_tc_kernel(const float* __restrict__ dproj, const float* __restrict__ H_in,
 //     B columns (n-blocks) [ dproj (32 NB) | h1 (32, t > 0) | X 1 0.. (16) ]
 // D rows 0..36 x the dproj columns = d[W1a|W1b|W3a|W3b|W3c]^T and their biases, rows 64..95 x the h1 columns = dW4, x the
 // last block = db4 (t > 0) or dWin | dbin (t = 0); the other quadrants are computed and never read.  Stages of 16 nodes
-// (two k-steps), ring of five.
+// (two k-steps): a raw ring of five (bulk copies) in front of an image ring of three.
 template <int NB, bool FIRST>
 struct MCfg {
     static constexpr int H = 32, SN = 16, KS = SN / 8, BI = SN * 128, PB = NB;
     static constexpr int O_HXH = 0, O_XA = BI, O_DZ = 2 * BI, O_P = 3 * BI, O_H1 = (3 + PB) * BI, O_XB = (3 + PB + (FIRST ? 0 : 1)) * BI;
     static constexpr int GB = 3 + PB + (FIRST ? 0 : 1) + 1;
-    static constexpr int G_LO = GB * BI, STAGE = 2 * GB * BI, STAGES = 5;
-    static constexpr int SMEM_BYTES = STAGES * STAGE + 1024;
+    static constexpr int G_LO = GB * BI, STAGE = 2 * GB * BI, STAGES = 3;
+    // raw ring: the node-major rows of a stage as they lie in global memory (contiguous per array), brought in by bulk
+    // copies: the loaders' own loads are capped by the L1's outstanding misses (~12 B/clk/SM measured, 3.4 TB/s chip-wide)
+    static constexpr int ROW_P = NB * H * 4, ROW_H = H * 4;
+    static constexpr int R_P = 0, R_H = SN * ROW_P, R_Z = R_H + SN * ROW_H, R_1 = R_Z + SN * ROW_H, R_X = R_1 + (FIRST ? 0 : SN * ROW_H);
+    static constexpr int RAW = R_X + SN * 16, RAW_STAGES = 5;
+    static constexpr int OFF_RAW = STAGES * STAGE;
+    static constexpr int SMEM_BYTES = OFF_RAW + RAW_STAGES * RAW + 1024;
     static constexpr int N = 32 * PB + (FIRST ? 0 : 32) + 16;
     static constexpr int COL_H1 = 32 * PB, COL_X = 32 * PB + (FIRST ? 0 : 32);
     static constexpr int TMEM_COLS = N <= 128 ? 128 : 256;
     static constexpr int ARRAYS = PB + (FIRST ? 2 : 3);       // 32-column row arrays per stage: dproj blocks, H, dz, h1
     static constexpr int ITEMS = (ARRAYS * SN * 8 + 255) / 256;
-    static constexpr int NT = 288;
-    static_assert(SMEM_BYTES <= 232448 && N <= 256 && N % 16 == 0, "merged product");
+    static constexpr int NT = 320;                            // 8 loader warps, the MMA warp, the copy warp
+    static_assert(SMEM_BYTES <= 232448 && N <= 256 && N % 16 == 0 && RAW % 128 == 0, "merged product");
 };
+
+__device__ __forceinline__ void mbar_expect_tx_w(const uint32_t mbar, const uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_w(const uint32_t dst_smem, const void* src, const uint32_t bytes, const uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
 
 template <int NB, bool FIRST>
 __global__ void __launch_bounds__(MCfg<NB, FIRST>::NT, 1)
@@ -328,18 +342,21 @@ wgrad_tc_merged_kernel(const float* __restrict__ dproj, const float* __restrict_
                        float* __restrict__ part, const int accumulate) {
     using C = MCfg<NB, FIRST>;
     using NP = NodePartW<32>;
-    constexpr int H = 32, SN = C::SN, BI = C::BI, S = C::STAGES;
+    constexpr int H = 32, SN = C::SN, BI = C::BI, S = C::STAGES, RS = C::RAW_STAGES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t bars[2 * S + 1];
+    __shared__ uint64_t bars[2 * S + 2 * RS + 1];
     __shared__ uint32_t tmem_slot;
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto full = [&](const int s) { return bar0 + 8u * s; };
     auto empty = [&](const int s) { return bar0 + 8u * (S + s); };
-    const uint32_t done = bar0 + 8u * (2 * S);
+    auto raw_full = [&](const int s) { return bar0 + 8u * (2 * S + s); };
+    auto raw_empty = [&](const int s) { return bar0 + 8u * (2 * S + RS + s); };
+    const uint32_t done = bar0 + 8u * (2 * S + 2 * RS);
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full(s), 8); mbar_init(empty(s), 1); }
+        for (int s = 0; s < RS; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 8); }
         mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -354,40 +371,37 @@ wgrad_tc_merged_kernel(const float* __restrict__ dproj, const float* __restrict_
     const int n_mine = (n_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // >= 1: grid <= n_chunks
 
     if (warp < 8) {
-        // ---------------- loaders ----------------
+        // ---------------- loaders: raw rows -> tf32 hi / lo block images ----------------
         // item i = 128 a + r: array a (dproj block a < PB, then H, dz, h1), node r >> 3 of the stage, 16-byte chunk r & 7
-        DT_DECL(1);
-        struct StageRegs { float4 v[C::ITEMS], vx; };
-        auto load = [&](StageRegs& R, const int it) {
+        DT_DECL(2);
+        for (int it = 0; it < n_mine; ++it) {
             const int node0 = ((int)blockIdx.x + it * (int)gridDim.x) * SN;
+            const int sr = it % RS, s = it % S;
             const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            const unsigned char* raw = smem + C::OFF_RAW + sr * C::RAW;
+            DT_WAIT(1, mbar_wait(raw_full(sr), (it / RS) & 1));
+            float4 v[C::ITEMS], vx = zero;
 #pragma unroll
             for (int j = 0; j < C::ITEMS; ++j) {
-                const int i = tid + 256 * j, a = i >> 7, r = i & 127, ng = node0 + (r >> 3), c = 4 * (r & 7);
-                R.v[j] = zero;
-                if (a < C::ARRAYS && ng < n_nodes) {
-                    const float* src = a < C::PB ? dproj + (size_t)ng * (NB * H) + 32 * a
-                                     : a == C::PB ? H_in + (size_t)ng * H
-                                     : a == C::PB + 1 ? dz + (size_t)ng * H : h1_prev + (size_t)ng * H;
-                    R.v[j] = ldg4(src + c);
+                const int i = tid + 256 * j, a = i >> 7, r = i & 127, nl = r >> 3, c = 16 * (r & 7);
+                v[j] = zero;
+                if (a < C::ARRAYS && node0 + nl < n_nodes) {
+                    const int off = a < C::PB ? C::R_P + nl * C::ROW_P + 128 * a
+                                  : (a == C::PB ? C::R_H : a == C::PB + 1 ? C::R_Z : C::R_1) + nl * C::ROW_H;
+                    v[j] = *reinterpret_cast<const float4*>(raw + off + c);
                 }
             }
-            R.vx = zero;
-            if (tid < SN * 4) {
-                const int ng = node0 + (tid >> 2), c16 = tid & 3;
-                if (ng < n_nodes) {
-                    if (c16 == 0) R.vx = ldg4(X4 + (size_t)ng * 4);
-                    else if (c16 == 1) R.vx.x = 1.f;
-                }
+            if (tid < SN * 4 && node0 + (tid >> 2) < n_nodes) {            // the X block: [x0 x1 x2 x3 | 1 0 0 0 | 0 ...]
+                if ((tid & 3) == 0) vx = *reinterpret_cast<const float4*>(raw + C::R_X + 16 * (tid >> 2));
+                else if ((tid & 3) == 1) vx.x = 1.f;
             }
-        };
-        auto store = [&](const StageRegs& R, const int it) {
-            const int s = it % S, round = it / S;
-            DT_WAIT(0, mbar_wait(empty(s), (round & 1) ^ 1));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_w(raw_empty(sr));     // the rows are in registers: the copy warp may refill the slot
+            DT_WAIT(0, mbar_wait(empty(s), ((it / S) & 1) ^ 1));
             unsigned char* st = smem + s * C::STAGE;
-            auto put = [&](const float4 v, const int o) {
+            auto put = [&](const float4 x, const int o) {
                 float4 hi, lo;
-                split3(v.x, hi.x, lo.x); split3(v.y, hi.y, lo.y); split3(v.z, hi.z, lo.z); split3(v.w, hi.w, lo.w);
+                split3(x.x, hi.x, lo.x); split3(x.y, hi.y, lo.y); split3(x.z, hi.z, lo.z); split3(x.w, hi.w, lo.w);
                 *reinterpret_cast<float4*>(st + o) = hi;
                 *reinterpret_cast<float4*>(st + C::G_LO + o) = lo;
             };
@@ -396,30 +410,39 @@ wgrad_tc_merged_kernel(const float* __restrict__ dproj, const float* __restrict_
                 const int i = tid + 256 * j, a = i >> 7, r = i & 127;
                 if (a < C::ARRAYS) {
                     const int blk = a < C::PB ? C::O_P + a * BI : a == C::PB ? C::O_HXH : a == C::PB + 1 ? C::O_DZ : C::O_H1;
-                    put(R.v[j], blk + mn32_off(r >> 3, r & 7));
+                    put(v[j], blk + mn32_off(r >> 3, r & 7));
                 }
             }
             if (tid < SN * 4) {
                 const int o = mn32_off(tid >> 2, tid & 3);
-                put(R.vx, C::O_XA + o);
-                put(R.vx, C::O_XB + o);
+                put(vx, C::O_XA + o);
+                put(vx, C::O_XB + o);
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_w(full(s));
-        };
-        StageRegs r0, r1, r2;
-        load(r0, 0);
-        if (1 < n_mine) load(r1, 1);
-        for (int it = 0; it < n_mine; it += 3) {
-            if (it + 2 < n_mine) load(r2, it + 2);
-            store(r0, it);
-            if (it + 1 < n_mine) { if (it + 3 < n_mine) load(r0, it + 3); store(r1, it + 1); }
-            if (it + 2 < n_mine) { if (it + 4 < n_mine) load(r1, it + 4); store(r2, it + 2); }
         }
 #ifdef GNNSEG_DTRACE
-        if (blockIdx.x == 0 && tid == 0) printf("wgradM<%d,%d> loader : total %lld, wait empty %lld (%d stages)\n", NB, (int)FIRST, clock64() - dt_start, dt_acc[0], n_mine);
+        if (blockIdx.x == 0 && tid == 0) printf("wgradM<%d,%d> loader : total %lld, wait empty %lld, raw %lld (%d stages)\n", NB, (int)FIRST, clock64() - dt_start, dt_acc[0], dt_acc[1], n_mine);
 #endif
+    } else if (warp == 9) {
+      if (lane == 0) {
+        // ---------------- copy warp: global rows -> raw ring ----------------
+        const uint32_t sraw = smem_u32(smem) + C::OFF_RAW;
+        for (int it = 0; it < n_mine; ++it) {
+            const int node0 = ((int)blockIdx.x + it * (int)gridDim.x) * SN, sr = it % RS;
+            const int nv = n_nodes - node0 < SN ? n_nodes - node0 : SN;
+            mbar_wait(raw_empty(sr), ((it / RS) & 1) ^ 1);
+            const uint32_t dst = sraw + sr * C::RAW, bar = raw_full(sr);
+            mbar_expect_tx_w(bar, (uint32_t)nv * (C::ROW_P + (FIRST ? 2 : 3) * C::ROW_H + 16));
+            bulk_g2s_w(dst + C::R_P, dproj + (size_t)node0 * (NB * H), nv * C::ROW_P, bar);
+            bulk_g2s_w(dst + C::R_H, H_in + (size_t)node0 * H, nv * C::ROW_H, bar);
+            bulk_g2s_w(dst + C::R_Z, dz + (size_t)node0 * H, nv * C::ROW_H, bar);
+            if (!FIRST) bulk_g2s_w(dst + C::R_1, h1_prev + (size_t)node0 * H, nv * C::ROW_H, bar);
+            bulk_g2s_w(dst + C::R_X, X4 + (size_t)node0 * 4, nv * 16, bar);
+        }
+      }
+      __syncwarp();
     } else {
       if (lane == 0) {
         // ---------------- MMA issuer ----------------

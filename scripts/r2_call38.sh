@@ -15,5 +15,5 @@ for r in rows[1:]:
     elif r[iu]=="ms": t*=1000
     agg.setdefault(name,[]).append(t)
 for k,x in sorted(agg.items(), key=lambda kv:-sum(kv[1])):
-    if "tc_kernel" in k: print("  %-62s n=%3d  sum %8.1f  last %7.1f"%(k,len(x),sum(x),x[-1]))
+    if "tc_" in k: print("  %-62s n=%3d  sum %8.1f  last %7.1f"%(k,len(x),sum(x),x[-1]))
 PY
