@@ -710,12 +710,13 @@ def main():
         line["clocks"] = clocks
         if "train" in res:
             tr = res["train"]
-            n_k = 2 + 1 + (it + 1) + it * (2 if h in (32, 64) else 1) + 2 + 1 + 3 * (it + 1) + 1 + 1 + 1
+            # backward: edge, gather and the dense step per (iteration + final step); the dense step is two kernels (tcgen05) at hidden_dim 32 / 64
+            n_k = 2 + 1 + (it + 1) + it * (2 if h in (32, 64) else 1) + 2 + 1 + (4 if h in (32, 64) else 3) * (it + 1) + 1 + 1 + 1
             line["train_step"] = {"ms": tr["ms"], "edges_per_sec": res["all_edges"] / (tr["ms"] * 1e-3),
                                   "events_per_sec": res["all_events"] / (tr["ms"] * 1e-3), "loss": tr["loss"],
                                   "gpu_launches_per_step": n_k,
                                   "path": "NativeTrainer.step on the resident batch: gnnseg_forward_train, gnnseg_bce_loss, "
-                                          "gnnseg_backward, gnnseg_l1_penalty, %sgnnseg_adam_step; L2 not flushed"
+                                          "gnnseg_backward (dense step on tcgen05 at hidden_dim 32 / 64), gnnseg_l1_penalty, %sgnnseg_adam_step; L2 not flushed"
                                           % ("NCCL all-reduce of the flat gradient, " if world > 1 else "")}
         if world > 1:
             line["scores_allgather_ms"] = res["gather_ms"]      # one all_gather_into_tensor of every rank's (B, E_max) scores
