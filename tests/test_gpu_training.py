@@ -223,3 +223,50 @@ def test_l1_penalty_kernel(cuda_device):
         assert torch.equal(grads[i], 1.0 + 0.25 * torch.sign(params[i].detach()))
     for i in (0, 1, 3, 5, 7, 9):
         assert torch.equal(grads[i], torch.ones_like(grads[i]))
+
+
+_DENSE_AB_SCRIPT = """
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+from gnn_fpga_b200 import SegmentClassifier, DeviceGraphBatch, data
+from oracle import segclf_oracle as O
+dev = torch.device("cuda:0")
+out = {{}}
+for h, T, n_ev in ((32, 4, 12), (64, 2, 3)):
+    graphs = data.acts_like_graphs(n_ev, n_tracks=400, seed=21)
+    m = SegmentClassifier(3, h, T)
+    m.load_state_dict(O.init_params(3, h, seed=2))
+    m = m.to(dev).train()
+    batch = DeviceGraphBatch.from_sparse_graphs(graphs, dev)
+    cot = torch.randn(batch.B, batch.e_max, device=dev, generator=torch.Generator(dev).manual_seed(5))
+    for rep in range(2):
+        m.zero_grad()
+        m(batch).backward(cot)
+        for k, v in m.named_parameters():
+            out["h%d:%d:%s" % (h, rep, k)] = v.grad.cpu().numpy()
+np.savez({dst!r}, **out)
+"""
+
+
+def test_dense_backward_tensor_core_paths_against_simt(tmp_path, cuda_device):
+    """The dense backward step on tcgen05 (gnnseg_dprop_tc.cu + gnnseg_wgrad_tc.cu, the default at hidden_dim 32; weight
+    gradients only at 64) against the all-SIMT fp32 kernel (GNNSEG_DENSE_BWD=simt) and the mixed form (=w) at batch scale:
+    12 events of 4 000 hits (48 000 nodes: every CTA sees several tiles and the partial last stage), 3xTF32 against fp32
+    within 2e-5 of each tensor's largest entry, and every path bit-reproducible from run to run.  The switch is read
+    once per process: three child processes."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("tc", "w", "simt"):
+        dst = str(tmp_path / ("grads_%s.npz" % mode))
+        env = dict(os.environ, GNNSEG_DENSE_BWD=mode)
+        subprocess.run([sys.executable, "-c", _DENSE_AB_SCRIPT.format(root=root, dst=dst)], check=True, env=env, timeout=300)
+        res[mode] = np.load(dst)
+    keys = [k for k in res["simt"].files if ":0:" in k]
+    assert len(keys) == 20
+    for k in keys:
+        for mode in ("tc", "w", "simt"):
+            assert np.array_equal(res[mode][k], res[mode][k.replace(":0:", ":1:")]), (mode, k)
+        for mode in ("tc", "w"):
+            assert grad_err(res[mode][k], res["simt"][k]) <= GTOL, (mode, k, grad_err(res[mode][k], res["simt"][k]))
