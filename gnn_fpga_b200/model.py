@@ -288,6 +288,9 @@ class SegmentClassifier(nn.Module):
         import numpy as np
         shape = np.zeros(4, dtype=np.int32)
         pending = deque()
+        # GNNSEG_STREAM_TIMING=1: host seconds spent waiting for results / inside the library call, per stream (diagnostics)
+        import time
+        stats = self._stream_stats = {"wait": 0.0, "call": 0.0, "batches": 0} if os.environ.get("GNNSEG_STREAM_TIMING") else None
         try:
             with torch.no_grad():
                 it = iter(batches)
@@ -313,11 +316,15 @@ class SegmentClassifier(nn.Module):
                     submit_next()                                 # one batch being prepared ahead
                     if len(pending) == depth:                     # keep `depth` results in flight
                         old = pending.popleft()
+                        t0 = time.perf_counter() if stats else 0.0
                         old["done"].synchronize()
+                        if stats:
+                            stats["wait"] += time.perf_counter() - t0
                         range_ok(old)
                         yield old["view"]
                     if s["done"] is not None:
                         s["done"].synchronize()                   # the slot's previous batch has left the device buffers
+                    t0 = time.perf_counter() if stats else 0.0
                     store = sb.store
                     B = sb.hi - sb.lo
                     while True:
@@ -341,6 +348,9 @@ class SegmentClassifier(nn.Module):
                             break
                         s["bufs"] = None                          # the batch exceeds the slot's buffers: new ones, once
                     _lib.check(rc, "gnnseg_store_forward_batch")
+                    if stats:
+                        stats["call"] += time.perf_counter() - t0
+                        stats["batches"] += 1
                     e_max = int(shape[1])
                     s["h2d"] = torch.cuda.Event()
                     s["h2d"].record(s_in)
