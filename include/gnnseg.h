@@ -267,9 +267,10 @@ typedef struct GnnsegGrads {
  * gnnseg_forward_train is gnnseg_forward that keeps, in the caller's workspace, what the backward
  * pass needs (per iteration: hidden states, first-layer projections, edge scores in both CSR
  * orders).  n_iters <= 64.  gnnseg_backward must be given the same workspace, untouched, and the
- * same blob / graph / sizes.  It launches 3*(n_iters+1)+2 kernels on `stream`; the weight
- * gradients are per-CTA partial sums added in a fixed order (no atomics): bit-identical from run
- * to run.
+ * same blob / graph / sizes.  It launches 3*(n_iters+1)+2 kernels on `stream` (hidden_dim 32 / 64:
+ * 4*(n_iters+1)+2, the dense step being two tcgen05 kernels: gnnseg_dprop_tc.cu, gnnseg_wgrad_tc.cu;
+ * 3xTF32 products, fp32 accumulation); the weight gradients are per-CTA partial sums added in a fixed
+ * order (no atomics): bit-identical from run to run.
  *   dscores[n_slots] = dL/dscore for every slot of the padded batch, padding slots included (the
  *                      reference's BCELoss averages over them, gnn/estimator.py:57).
  *   masks            = nullable; only m_e1, m_e2, m_n1, m_n2 are read: dW = dW_eff * mask
