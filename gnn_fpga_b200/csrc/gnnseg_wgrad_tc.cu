@@ -13,7 +13,9 @@
 // groups of four nodes SBO = 512 bytes apart.  A float4 of a node-major row lands in it as ONE 16-byte store: no
 // transposition anywhere, and the image of a block serves as A (its columns = rows of D) and as B alike.
 //
-// One CTA per SM, 9 warps: 8 loader warps (a thread owns one 16-byte chunk of one node per block: coalesced 128-byte
+// Two kernels: wgrad_tc_kernel right below (hidden_dim 64, and 32 with GNNSEG_WGRAD=split): two products per k-step;
+// wgrad_tc_merged_kernel further down (hidden_dim 32, the default there): one product per k-step, bulk-copy fed.
+// wgrad_tc_kernel: one CTA per SM, 9 warps: 8 loader warps (a thread owns one 16-byte chunk of one node per block: coalesced 128-byte
 // row pieces in, tf32 hi / lo split, two 16-byte stores out) fill a ring of three stages of SN nodes; one thread issues
 // the MMAs of a stage and commits them to the stage's `empty` barrier.  Nothing is read back per tile: the accumulators
 // stay in tensor memory until the CTA's last stage, then four warps add them to the CTA's slot of the partial buffer
