@@ -73,13 +73,15 @@ def test_padding_constant():
     assert np.allclose(rec["out"][pad], const, rtol=1e-6)
 
 
-def test_gradient_oracle_matches_reference_estimator():
+@pytest.mark.parametrize("name", ["train_step_h8_it2", "train_grads_h32_it3"])
+def test_gradient_oracle_matches_reference_estimator(name):
     """sparse_vjp (autograd over the sparse restatement, the checker of gnnseg_backward) against
     the loss and first-step gradients recorded from the reference's own Estimator.training_step
-    (tests/golden/train_step_h8_it2.npz, oracle/make_golden.py)."""
+    (tests/golden/train_step_h8_it2.npz, oracle/make_golden.py; train_grads_h32_it3.npz,
+    oracle/make_golden_train32.py: the width whose CUDA backward runs on the tensor cores)."""
     import os
     from conftest import GOLDEN
-    z = np.load(os.path.join(GOLDEN, "train_step_h8_it2.npz"))
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
     p = {k[6:]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith("param:")}
     src, dst = O.edges_from_dense(z["Ri"], z["Ro"])
     B, N, F = z["X"].shape
